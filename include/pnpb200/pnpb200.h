@@ -1,0 +1,124 @@
+/* pnp-b200 — assembly / Newton-step C ABI (drop-in boundary B.2 of SURVEY.md §8b).
+ *
+ * Replaces the BODIES of the reference's hot-path methods; every entry point cites the
+ * reference code it stands in for (paths relative to the reference root):
+ *   PDE::setup_linear_algebra            src/pde.cpp:542-555
+ *   PDE::compute_residual                src/pde.cpp:377-397
+ *   Linear_PNP::setup_fasp_linear_algebra benchmarks/pnp_exact_solution/linear_pnp.cpp:73-94
+ *   Linear_PNP::apply_eafe               benchmarks/pnp_exact_solution/linear_pnp.cpp:195-285
+ *   Linear_PNP::fasp_solve               benchmarks/pnp_exact_solution/linear_pnp.cpp:96-132
+ * The data those bodies have in hand are flat DOLFIN arrays (mesh.coordinates(), mesh.cells(),
+ * Function::vector()->get_local(), DirichletBC::get_boundary_values), which is what these
+ * functions take. Everything runs on the GPU (sm_100a, fp64); host arrays are borrowed for the
+ * duration of a call, the handle owns all device memory. Return value: 0 (FASP_SUCCESS) or a
+ * negative FASP-style status (fasp_compat.h); never abort().
+ *
+ * Dof numbering: blocked, dof = 3*vertex + component (component 0 = potential, 1..2 = log
+ * densities), the numbering fasp_format_dcsr_dbsr(...,3) needs for dense 3x3 blocks.
+ */
+#ifndef PNPB200_H
+#define PNPB200_H
+#include "fasp_compat.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pnpb200_handle pnpb200_handle;
+
+/* library / device */
+const char* pnpb200_version(void);
+int  pnpb200_device_count(void);
+
+/* create from a P1 tetrahedral mesh: xyz[3*n_vertices], cells[4*n_cells] (vertex ids).
+ * Builds on the device: vertex->cell adjacency, the BSR(3) sparsity pattern (all vertex pairs
+ * sharing a cell — what dolfin::assemble's pattern builder produces, src/pde.cpp:545), the EAFE
+ * edge table omega_ij, and the fine-level colouring. device = CUDA ordinal. */
+int  pnpb200_create(pnpb200_handle** h, int n_vertices, const double* xyz, int n_cells,
+                    const int* cells, int device);
+void pnpb200_destroy(pnpb200_handle* h);
+/* the CUDA stream (cudaStream_t as void*) all work of this handle is enqueued on; callers that
+ * time with their own events must record them on this stream */
+void* pnpb200_get_stream(pnpb200_handle* h);
+
+/* PDE::set_coefficients (src/pde.cpp:355-375): nodal coefficient fields.
+ * permittivity[Nv], fixed_charge[Nv]; diffusivity/valency/reaction [3*Nv] in dof order. */
+int  pnpb200_set_coefficients(pnpb200_handle* h, const double* permittivity,
+                              const double* fixed_charge, const double* diffusivity,
+                              const double* valency, const double* reaction);
+/* PDE::set_DirichletBC / remove_Dirichlet_dof (src/pde.cpp:433-483): homogeneous Dirichlet
+ * rows for the Newton update on the listed scalar dofs. */
+int  pnpb200_set_dirichlet(pnpb200_handle* h, int n_bc, const int* bc_dofs);
+/* PDE::set_solution / get_solution (src/pde.cpp:250-275) */
+int  pnpb200_set_solution(pnpb200_handle* h, const double* uu);
+int  pnpb200_get_solution(pnpb200_handle* h, double* uu);
+/* same, with buffers already resident on this handle's device */
+int  pnpb200_set_solution_device(pnpb200_handle* h, const double* d_uu);
+int  pnpb200_get_solution_device(pnpb200_handle* h, double* d_uu);
+/* Linear_PNP::use_eafe / no_eafe (linear_pnp.cpp:187-192) */
+int  pnpb200_use_eafe(pnpb200_handle* h, int on);
+
+/* sizes */
+int  pnpb200_num_dofs(const pnpb200_handle* h);
+int  pnpb200_num_block_rows(const pnpb200_handle* h);
+int  pnpb200_num_blocks(const pnpb200_handle* h);
+
+/* Linear_PNP::setup_fasp_linear_algebra: assemble Jacobian (Galerkin + EAFE overwrite +
+ * Dirichlet rows + zero-row fix, straight into BSR(3)) and the rhs on the device. */
+int  pnpb200_assemble(pnpb200_handle* h);
+/* copy the assembled system to host FASP structs. A_out arrays are allocated with the FASP
+ * allocator (free with fasp_dbsr_free); b_out must have row == num_dofs. Either may be NULL. */
+int  pnpb200_get_matrix(pnpb200_handle* h, dBSRmat* A_out);
+int  pnpb200_get_rhs(pnpb200_handle* h, dvector* b_out);
+/* PDE::compute_residual: assemble L at the current solution, zero Dirichlet rows, return
+ * the l2 and max norms (fused; either pointer may be NULL). */
+int  pnpb200_residual(pnpb200_handle* h, double* l2, double* linf);
+
+/* Linear_PNP::fasp_solve without the assembly: solve J du = b for the system currently on
+ * the device (AMG setup + FGMRES). status_its gets iterations >= 0 or a negative FASP status. */
+int  pnpb200_solve(pnpb200_handle* h, const itsolver_param* itparam, const AMG_param* amgparam,
+                   int* status_its);
+/* copy the last Newton update du to the host */
+int  pnpb200_get_update(pnpb200_handle* h, double* du);
+/* Linear_PNP::fasp_test_solver (linear_pnp.cpp:134-175): rhs = J*target, solve, return x */
+int  pnpb200_test_solver(pnpb200_handle* h, const double* target, double* x,
+                         const itsolver_param* itparam, const AMG_param* amgparam, int* status_its);
+
+/* One full Newton step of benchmarks/pnp_exact_solution/main.cpp:334-345, nothing leaving
+ * the device: assemble, AMG setup, FGMRES, u += du (skipped if the solver failed,
+ * linear_pnp.cpp:109-127), residual norms at the new iterate. */
+int  pnpb200_newton_step(pnpb200_handle* h, const itsolver_param* itparam, const AMG_param* amgparam,
+                         int* krylov_status_its, double* l2, double* linf);
+
+/* hierarchy policy: 0 = rebuild aggregates/patterns/colourings every solve (the reference's
+ * behaviour, default), 1 = keep the symbolic hierarchy of the previous solve and only
+ * recompute numerical values (Galerkin products, block inverses). */
+int  pnpb200_set_hierarchy_reuse(pnpb200_handle* h, int reuse);
+
+/* ---- introspection for the parity tests and the byte model of bench.py ---- */
+typedef struct pnpb200_stats {
+  int    n_levels;
+  int    level_rows[32];
+  int    level_nnzb[32];
+  int    level_colors[32];
+  int    krylov_its;          /* last solve */
+  int    launches;            /* kernels launched by the last call */
+  double ms_assemble, ms_setup, ms_krylov, ms_residual;   /* CUDA-event times of the last call */
+  double ms_spmv, ms_vcycle, ms_ortho;   /* accumulated inside the last Krylov solve (when timing detail is on) */
+} pnpb200_stats;
+int  pnpb200_get_stats(const pnpb200_handle* h, pnpb200_stats* s);
+int  pnpb200_set_timing_detail(pnpb200_handle* h, int on);
+/* copy level-l hierarchy pieces to the host (FASP layout): matrix, aggregate map (length
+ * level_rows[l], -1 = isolated), GS row order (rows sorted by colour). */
+int  pnpb200_get_level_matrix(pnpb200_handle* h, int level, dBSRmat* A_out);
+int  pnpb200_get_level_aggregates(pnpb200_handle* h, int level, int* agg, int* n_agg);
+int  pnpb200_get_level_order(pnpb200_handle* h, int level, int* order);
+/* apply one V-cycle of the current hierarchy: z = M^{-1} r (host vectors) */
+int  pnpb200_apply_vcycle(pnpb200_handle* h, const double* r, double* z);
+/* y = J x with the assembled fine-level matrix (host vectors) */
+int  pnpb200_apply_matrix(pnpb200_handle* h, const double* x, double* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,370 @@
+"""ctypes binding of libpnpb200.so — the harness side of the C ABI declared in
+include/pnpb200/pnpb200.h and include/pnpb200/fasp_compat.h (used by tests/ and bench.py;
+C/C++ callers include the headers directly). There is no CPU fallback: if the CUDA library is
+missing, loading fails loudly."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpnpb200.so")
+
+INT = C.c_int
+SHORT = C.c_short
+REAL = C.c_double
+
+
+class dCSRmat(C.Structure):
+    _fields_ = [("row", INT), ("col", INT), ("nnz", INT), ("IA", C.POINTER(INT)), ("JA", C.POINTER(INT)),
+                ("val", C.POINTER(REAL))]
+
+
+class dBSRmat(C.Structure):
+    _fields_ = [("ROW", INT), ("COL", INT), ("NNZ", INT), ("nb", INT), ("storage_manner", INT),
+                ("val", C.POINTER(REAL)), ("IA", C.POINTER(INT)), ("JA", C.POINTER(INT))]
+
+
+class dvector(C.Structure):
+    _fields_ = [("row", INT), ("val", C.POINTER(REAL))]
+
+
+class input_param(C.Structure):
+    _fields_ = [("print_level", SHORT), ("output_type", SHORT), ("inifile", C.c_char * 256), ("workdir", C.c_char * 256),
+                ("problem_num", INT), ("solver_type", SHORT), ("precond_type", SHORT), ("stop_type", SHORT),
+                ("itsolver_tol", REAL), ("itsolver_maxit", INT), ("restart", INT),
+                ("ILU_type", SHORT), ("ILU_lfil", INT), ("ILU_droptol", REAL), ("ILU_relax", REAL), ("ILU_permtol", REAL),
+                ("Schwarz_mmsize", INT), ("Schwarz_maxlvl", INT), ("Schwarz_type", INT), ("Schwarz_blksolver", INT),
+                ("AMG_type", SHORT), ("AMG_levels", SHORT), ("AMG_cycle_type", SHORT), ("AMG_smoother", SHORT),
+                ("AMG_smooth_order", SHORT), ("AMG_relaxation", REAL), ("AMG_polynomial_degree", SHORT),
+                ("AMG_presmooth_iter", SHORT), ("AMG_postsmooth_iter", SHORT), ("AMG_coarse_dof", INT), ("AMG_tol", REAL),
+                ("AMG_maxit", INT), ("AMG_ILU_levels", SHORT), ("AMG_coarse_solver", SHORT), ("AMG_coarse_scaling", SHORT),
+                ("AMG_amli_degree", SHORT), ("AMG_nl_amli_krylov_type", SHORT), ("AMG_Schwarz_levels", INT),
+                ("AMG_coarsening_type", SHORT), ("AMG_aggregation_type", SHORT), ("AMG_interpolation_type", SHORT),
+                ("AMG_strong_threshold", REAL), ("AMG_truncation_threshold", REAL), ("AMG_max_row_sum", REAL),
+                ("AMG_aggressive_level", INT), ("AMG_aggressive_path", INT), ("AMG_pair_number", INT),
+                ("AMG_quality_bound", REAL), ("AMG_strong_coupled", REAL), ("AMG_max_aggregation", INT),
+                ("AMG_tentative_smooth", REAL), ("AMG_smooth_filter", SHORT)]
+
+
+class itsolver_param(C.Structure):
+    _fields_ = [("itsolver_type", SHORT), ("precond_type", SHORT), ("stop_type", SHORT), ("maxit", INT), ("tol", REAL),
+                ("restart", INT), ("print_level", SHORT)]
+
+
+class AMG_param(C.Structure):
+    _fields_ = [("AMG_type", SHORT), ("print_level", SHORT), ("maxit", INT), ("tol", REAL), ("max_levels", SHORT),
+                ("coarse_dof", INT), ("cycle_type", SHORT), ("quality_bound", REAL), ("smoother", SHORT),
+                ("smooth_order", SHORT), ("presmooth_iter", SHORT), ("postsmooth_iter", SHORT), ("relaxation", REAL),
+                ("polynomial_degree", SHORT), ("coarse_solver", SHORT), ("coarse_scaling", SHORT), ("amli_degree", SHORT),
+                ("amli_coef", C.POINTER(REAL)), ("nl_amli_krylov_type", SHORT), ("coarsening_type", SHORT),
+                ("aggregation_type", SHORT), ("interpolation_type", SHORT), ("strong_threshold", REAL),
+                ("max_row_sum", REAL), ("truncation_threshold", REAL), ("aggressive_level", INT), ("aggressive_path", INT),
+                ("pair_number", INT), ("strong_coupled", REAL), ("max_aggregation", INT), ("tentative_smooth", REAL),
+                ("smooth_filter", SHORT), ("ILU_levels", SHORT), ("ILU_type", SHORT), ("ILU_lfil", INT),
+                ("ILU_droptol", REAL), ("ILU_relax", REAL), ("ILU_permtol", REAL), ("Schwarz_levels", INT),
+                ("Schwarz_mmsize", INT), ("Schwarz_maxlvl", INT), ("Schwarz_type", INT), ("Schwarz_blksolver", INT)]
+
+
+class ILU_param(C.Structure):
+    _fields_ = [("print_level", SHORT), ("ILU_type", SHORT), ("ILU_lfil", INT), ("ILU_droptol", REAL),
+                ("ILU_relax", REAL), ("ILU_permtol", REAL)]
+
+
+class pnpb200_stats(C.Structure):
+    _fields_ = [("n_levels", C.c_int), ("level_rows", C.c_int * 32), ("level_nnzb", C.c_int * 32),
+                ("level_colors", C.c_int * 32), ("krylov_its", C.c_int), ("launches", C.c_int),
+                ("ms_assemble", C.c_double), ("ms_setup", C.c_double), ("ms_krylov", C.c_double),
+                ("ms_residual", C.c_double), ("ms_spmv", C.c_double), ("ms_vcycle", C.c_double), ("ms_ortho", C.c_double)]
+
+
+_f8 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i4 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+_lib = None
+
+
+def lib():
+    """Load libpnpb200.so (built by __graft_entry__.build() / make -C modular-pnp_b200)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libpnpb200.so is missing (%s): build it with __graft_entry__.build(); "
+                           "pnp-b200 has no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    L.pnpb200_version.restype = C.c_char_p
+    L.pnpb200_device_count.restype = C.c_int
+    L.pnpb200_create.argtypes = [C.POINTER(H), C.c_int, _f8, C.c_int, _i4, C.c_int]
+    L.pnpb200_destroy.argtypes = [H]
+    L.pnpb200_destroy.restype = None
+    L.pnpb200_get_stream.argtypes = [H]
+    L.pnpb200_get_stream.restype = C.c_void_p
+    L.pnpb200_set_coefficients.argtypes = [H, _f8, _f8, _f8, _f8, _f8]
+    L.pnpb200_set_dirichlet.argtypes = [H, C.c_int, _i4]
+    L.pnpb200_set_solution.argtypes = [H, _f8]
+    L.pnpb200_get_solution.argtypes = [H, _f8]
+    L.pnpb200_set_solution_device.argtypes = [H, C.c_void_p]
+    L.pnpb200_get_solution_device.argtypes = [H, C.c_void_p]
+    L.pnpb200_use_eafe.argtypes = [H, C.c_int]
+    for f in ("pnpb200_num_dofs", "pnpb200_num_block_rows", "pnpb200_num_blocks"):
+        getattr(L, f).argtypes = [H]
+    L.pnpb200_assemble.argtypes = [H]
+    L.pnpb200_get_matrix.argtypes = [H, C.POINTER(dBSRmat)]
+    L.pnpb200_get_rhs.argtypes = [H, C.POINTER(dvector)]
+    L.pnpb200_residual.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.pnpb200_solve.argtypes = [H, C.POINTER(itsolver_param), C.POINTER(AMG_param), C.POINTER(C.c_int)]
+    L.pnpb200_get_update.argtypes = [H, _f8]
+    L.pnpb200_test_solver.argtypes = [H, _f8, _f8, C.POINTER(itsolver_param), C.POINTER(AMG_param), C.POINTER(C.c_int)]
+    L.pnpb200_newton_step.argtypes = [H, C.POINTER(itsolver_param), C.POINTER(AMG_param), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.pnpb200_set_hierarchy_reuse.argtypes = [H, C.c_int]
+    L.pnpb200_get_stats.argtypes = [H, C.POINTER(pnpb200_stats)]
+    L.pnpb200_set_timing_detail.argtypes = [H, C.c_int]
+    L.pnpb200_get_level_matrix.argtypes = [H, C.c_int, C.POINTER(dBSRmat)]
+    L.pnpb200_get_level_aggregates.argtypes = [H, C.c_int, _i4, C.POINTER(C.c_int)]
+    L.pnpb200_get_level_order.argtypes = [H, C.c_int, _i4]
+    L.pnpb200_apply_vcycle.argtypes = [H, _f8, _f8]
+    L.pnpb200_apply_matrix.argtypes = [H, _f8, _f8]
+    # FASP-compatible surface
+    L.fasp_param_input.argtypes = [C.c_char_p, C.POINTER(input_param)]
+    L.fasp_param_input.restype = None
+    L.fasp_param_input_init.argtypes = [C.POINTER(input_param)]
+    L.fasp_param_input_init.restype = None
+    L.fasp_param_init.argtypes = [C.POINTER(input_param), C.POINTER(itsolver_param), C.POINTER(AMG_param),
+                                  C.POINTER(ILU_param), C.c_void_p]
+    L.fasp_param_init.restype = None
+    L.fasp_param_amg_init.argtypes = [C.POINTER(AMG_param)]
+    L.fasp_param_amg_init.restype = None
+    L.fasp_param_solver_init.argtypes = [C.POINTER(itsolver_param)]
+    L.fasp_param_solver_init.restype = None
+    L.fasp_format_dcsr_dbsr.argtypes = [C.POINTER(dCSRmat), INT]
+    L.fasp_format_dcsr_dbsr.restype = dBSRmat
+    L.fasp_solver_dbsr_krylov_amg.argtypes = [C.POINTER(dBSRmat), C.POINTER(dvector), C.POINTER(dvector),
+                                              C.POINTER(itsolver_param), C.POINTER(AMG_param)]
+    L.fasp_solver_dbsr_krylov_amg.restype = INT
+    L.fasp_solver_dbsr_krylov_ilu.argtypes = [C.POINTER(dBSRmat), C.POINTER(dvector), C.POINTER(dvector),
+                                              C.POINTER(itsolver_param), C.POINTER(ILU_param)]
+    L.fasp_solver_dbsr_krylov_ilu.restype = INT
+    L.fasp_solver_dcsr_krylov.argtypes = [C.POINTER(dCSRmat), C.POINTER(dvector), C.POINTER(dvector),
+                                          C.POINTER(itsolver_param)]
+    L.fasp_solver_dcsr_krylov.restype = INT
+    L.fasp_blas_dbsr_mxv.argtypes = [C.POINTER(dBSRmat), _f8, _f8]
+    L.fasp_blas_dbsr_mxv.restype = None
+    L.fasp_blas_dbsr_aAxpy.argtypes = [REAL, C.POINTER(dBSRmat), _f8, _f8]
+    L.fasp_blas_dbsr_aAxpy.restype = None
+    L.fasp_dbsr_free.argtypes = [C.POINTER(dBSRmat)]
+    L.fasp_dbsr_free.restype = None
+    L.fasp_dvec_alloc.argtypes = [INT, C.POINTER(dvector)]
+    L.fasp_dvec_alloc.restype = None
+    L.fasp_dvec_set.argtypes = [INT, C.POINTER(dvector), REAL]
+    L.fasp_dvec_set.restype = None
+    L.fasp_dvec_free.argtypes = [C.POINTER(dvector)]
+    L.fasp_dvec_free.restype = None
+    _lib = L
+    return L
+
+
+DEFAULT_BSR_DAT = os.path.join(_HERE, "host", "bsr.dat")
+
+
+def default_params(dat_file=None, **overrides):
+    """(itsolver_param, AMG_param) from a FASP .dat file — by default the repo's copy of the
+    parameter VALUES of benchmarks/pnp_exact_solution/bsr.dat."""
+    L = lib()
+    inp, it, amg, ilu = input_param(), itsolver_param(), AMG_param(), ILU_param()
+    L.fasp_param_input((dat_file or DEFAULT_BSR_DAT).encode(), C.byref(inp))
+    L.fasp_param_init(C.byref(inp), C.byref(it), C.byref(amg), C.byref(ilu), None)
+    for k, v in overrides.items():
+        if hasattr(it, k):
+            setattr(it, k, v)
+        elif hasattr(amg, k):
+            setattr(amg, k, v)
+        else:
+            raise KeyError(k)
+    return it, amg
+
+
+def _bsr_to_numpy(m, free=True):
+    n, nnz = m.ROW, m.NNZ
+    IA = np.ctypeslib.as_array(m.IA, shape=(n + 1,)).copy()
+    JA = np.ctypeslib.as_array(m.JA, shape=(nnz,)).copy()
+    val = np.ctypeslib.as_array(m.val, shape=(9 * nnz,)).copy()
+    if free:
+        lib().fasp_dbsr_free(C.byref(m))
+    return IA.astype(np.int32), JA.astype(np.int32), val
+
+
+def numpy_to_bsr(IA, JA, val):
+    """dBSRmat view over numpy arrays (arrays must outlive the struct)."""
+    IA = np.ascontiguousarray(IA, dtype=np.int32); JA = np.ascontiguousarray(JA, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    m = dBSRmat()
+    m.ROW = m.COL = len(IA) - 1; m.NNZ = len(JA); m.nb = 3; m.storage_manner = 0
+    m.IA = IA.ctypes.data_as(C.POINTER(INT)); m.JA = JA.ctypes.data_as(C.POINTER(INT))
+    m.val = val.ctypes.data_as(C.POINTER(REAL))
+    m._keep = (IA, JA, val)
+    return m
+
+
+def numpy_to_dvec(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    v = dvector(); v.row = len(x); v.val = x.ctypes.data_as(C.POINTER(REAL)); v._keep = x
+    return v
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed with FASP status %d" % (what, rc))
+
+
+class PNP:
+    """Device-resident linearised-PNP problem: the Python mirror of the host-side
+    Linear_PNP/PDE surface (modular-pnp_b200/host/linear_pnp.hpp)."""
+
+    def __init__(self, xyz, cells, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).ravel()
+        cells = np.ascontiguousarray(cells, dtype=np.int32).ravel()
+        self.nv, self.nc = len(xyz) // 3, len(cells) // 4
+        _check(self.L.pnpb200_create(C.byref(self.h), self.nv, xyz, self.nc, cells, device), "pnpb200_create")
+        self.N = 3 * self.nv
+
+    def close(self):
+        if self.h:
+            self.L.pnpb200_destroy(self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return self.L.pnpb200_get_stream(self.h)
+
+    def set_coefficients(self, eps, fixed, diff, val, reac):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (eps, fixed, diff, val, reac)]
+        _check(self.L.pnpb200_set_coefficients(self.h, *a), "set_coefficients")
+
+    def set_dirichlet(self, dofs):
+        dofs = np.ascontiguousarray(dofs, dtype=np.int32)
+        _check(self.L.pnpb200_set_dirichlet(self.h, len(dofs), dofs), "set_dirichlet")
+
+    def set_solution(self, uu):
+        _check(self.L.pnpb200_set_solution(self.h, np.ascontiguousarray(uu, dtype=np.float64)), "set_solution")
+
+    def get_solution(self):
+        uu = np.zeros(self.N)
+        _check(self.L.pnpb200_get_solution(self.h, uu), "get_solution")
+        return uu
+
+    def use_eafe(self, on=True):
+        _check(self.L.pnpb200_use_eafe(self.h, 1 if on else 0), "use_eafe")
+
+    def assemble(self):
+        _check(self.L.pnpb200_assemble(self.h), "assemble")
+
+    def get_matrix(self):
+        m = dBSRmat()
+        _check(self.L.pnpb200_get_matrix(self.h, C.byref(m)), "get_matrix")
+        return _bsr_to_numpy(m)
+
+    def get_rhs(self):
+        b = np.zeros(self.N)
+        v = numpy_to_dvec(b)
+        _check(self.L.pnpb200_get_rhs(self.h, C.byref(v)), "get_rhs")
+        return v._keep
+
+    def residual(self):
+        a, b = C.c_double(), C.c_double()
+        _check(self.L.pnpb200_residual(self.h, C.byref(a), C.byref(b)), "residual")
+        return a.value, b.value
+
+    def solve(self, it, amg):
+        st = C.c_int()
+        _check(self.L.pnpb200_solve(self.h, C.byref(it), C.byref(amg) if amg is not None else None, C.byref(st)), "solve")
+        return st.value
+
+    def get_update(self):
+        du = np.zeros(self.N)
+        _check(self.L.pnpb200_get_update(self.h, du), "get_update")
+        return du
+
+    def test_solver(self, target, it, amg):
+        x = np.zeros(self.N); st = C.c_int()
+        _check(self.L.pnpb200_test_solver(self.h, np.ascontiguousarray(target, dtype=np.float64), x, C.byref(it),
+                                          C.byref(amg), C.byref(st)), "test_solver")
+        return x, st.value
+
+    def newton_step(self, it, amg):
+        st, a, b = C.c_int(), C.c_double(), C.c_double()
+        _check(self.L.pnpb200_newton_step(self.h, C.byref(it), C.byref(amg), C.byref(st), C.byref(a), C.byref(b)),
+               "newton_step")
+        return st.value, a.value, b.value
+
+    def set_hierarchy_reuse(self, on):
+        _check(self.L.pnpb200_set_hierarchy_reuse(self.h, 1 if on else 0), "set_hierarchy_reuse")
+
+    def set_timing_detail(self, on):
+        _check(self.L.pnpb200_set_timing_detail(self.h, 1 if on else 0), "set_timing_detail")
+
+    def stats(self):
+        s = pnpb200_stats()
+        _check(self.L.pnpb200_get_stats(self.h, C.byref(s)), "get_stats")
+        return s
+
+    def level_matrix(self, l):
+        m = dBSRmat()
+        _check(self.L.pnpb200_get_level_matrix(self.h, l, C.byref(m)), "get_level_matrix")
+        return _bsr_to_numpy(m)
+
+    def level_aggregates(self, l):
+        n = self.stats().level_rows[l]
+        agg = np.zeros(n, dtype=np.int32); na = C.c_int()
+        _check(self.L.pnpb200_get_level_aggregates(self.h, l, agg, C.byref(na)), "get_level_aggregates")
+        return agg, na.value
+
+    def level_order(self, l):
+        n = self.stats().level_rows[l]
+        o = np.zeros(n, dtype=np.int32)
+        _check(self.L.pnpb200_get_level_order(self.h, l, o), "get_level_order")
+        return o
+
+    def apply_vcycle(self, r):
+        z = np.zeros(self.N)
+        _check(self.L.pnpb200_apply_vcycle(self.h, np.ascontiguousarray(r, dtype=np.float64), z), "apply_vcycle")
+        return z
+
+    def apply_matrix(self, x):
+        y = np.zeros(self.N)
+        _check(self.L.pnpb200_apply_matrix(self.h, np.ascontiguousarray(x, dtype=np.float64), y), "apply_matrix")
+        return y
+
+
+def fasp_solver_dbsr_krylov_amg(IA, JA, val, b, it, amg, x0=None):
+    """Reference-facing call: host arrays in, GPU solve, host vector out."""
+    A = numpy_to_bsr(IA, JA, val)
+    bv = numpy_to_dvec(b)
+    x = np.zeros(len(b)) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+    xv = numpy_to_dvec(x)
+    st = lib().fasp_solver_dbsr_krylov_amg(C.byref(A), C.byref(bv), C.byref(xv), C.byref(it), C.byref(amg))
+    return xv._keep, st
+
+
+def fasp_format_dcsr_dbsr(IA, JA, val, nb=3):
+    IA = np.ascontiguousarray(IA, dtype=np.int32); JA = np.ascontiguousarray(JA, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    A = dCSRmat(); A.row = A.col = len(IA) - 1; A.nnz = len(JA)
+    A.IA = IA.ctypes.data_as(C.POINTER(INT)); A.JA = JA.ctypes.data_as(C.POINTER(INT))
+    A.val = val.ctypes.data_as(C.POINTER(REAL))
+    B = lib().fasp_format_dcsr_dbsr(C.byref(A), nb)
+    if not B.IA:
+        raise RuntimeError("fasp_format_dcsr_dbsr failed")
+    n, nnz = B.ROW, B.NNZ
+    out = (np.ctypeslib.as_array(B.IA, shape=(n + 1,)).copy(), np.ctypeslib.as_array(B.JA, shape=(nnz,)).copy(),
+           np.ctypeslib.as_array(B.val, shape=(nb * nb * nnz,)).copy())
+    lib().fasp_dbsr_free(C.byref(B))
+    return out

@@ -1,0 +1,589 @@
+// pnp-b200 — unsmoothed-aggregation AMG for BSR(3) on the device.
+// Stands in for FASP's fasp_amg_setup_ua_bsr + fasp_solver_mgcycle_bsr [EXT], called through
+// fasp_solver_dbsr_krylov_amg at benchmarks/pnp_exact_solution/linear_pnp.cpp:101.
+//   strength : a_ij^2 >= theta^2 |a_ii a_jj| on the L-inf condensed matrix (VMB criterion),
+//              theta halves per level when tentative_smooth > 0 (bsr.dat:97-99)
+//   aggregates: parallel distance-2 maximal independent set of the symmetrised strength graph
+//              (roots), root + strong neighbours, leftovers join their strongest aggregated
+//              neighbour — the parallel counterpart of VMB's three sequential steps;
+//              rows without off-diagonal coupling (Dirichlet rows) stay out of the coarse grid
+//   P        : boolean block prolongator, R = P^T, A_c = R A P by sorting blocks on their
+//              coarse (I,J) key and a segmented sum (atomic-free, deterministic)
+//   cycle    : V(nu1,nu2), multicolour block Gauss-Seidel (colours ascending / descending),
+//              exact dense solve on the coarsest level (explicit inverse, one GEMV per cycle)
+#include "internal.hpp"
+#include <cub/cub.cuh>
+#include <cmath>
+
+namespace pnpb200 {
+
+namespace {
+
+typedef unsigned long long u64;
+
+__global__ void condense_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ brow,
+                                const double* __restrict__ val, double* __restrict__ pp)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int i = brow[b], s = ia[i], len = ia[i + 1] - s;
+  const double* v = val + 9 * (size_t)s + (b - s);
+  double m = 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    m = fmax(m, fabs(v[(size_t)(3 * r) * len]) + fabs(v[(size_t)(3 * r + 1) * len]) + fabs(v[(size_t)(3 * r + 2) * len]));
+  pp[b] = m;
+}
+
+__global__ void isolated_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                                const double* __restrict__ pp, unsigned char* __restrict__ iso)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool any = false;
+  for (int p = ia[i]; p < ia[i + 1]; ++p) if (ja[p] != i && pp[p] != 0.0) { any = true; break; }
+  iso[i] = any ? 0 : 1;
+}
+
+__global__ void strength_kernel(int nnzb, const int* __restrict__ ja, const int* __restrict__ brow,
+                                const int* __restrict__ dslot, const int* __restrict__ tslot,
+                                const double* __restrict__ pp, const unsigned char* __restrict__ iso,
+                                double theta2, unsigned char* __restrict__ strong)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int i = brow[b], j = ja[b];
+  unsigned char s = 0;
+  if (i != j && !iso[i] && !iso[j]) {
+    const double dd = theta2 * fabs(pp[dslot[i]] * pp[dslot[j]]);
+    const double a = pp[b];
+    const int t = tslot[b];
+    const double at = t >= 0 ? pp[t] : 0.0;
+    s = ((a > 0.0 && a * a >= dd) || (at > 0.0 && at * at >= dd)) ? 1 : 0;
+  }
+  strong[b] = s;
+}
+
+// a non-isolated row without any strong neighbour keeps its largest coupling (select, then
+// apply, so the outcome does not depend on thread timing)
+__global__ void force_select_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                                    const double* __restrict__ pp, const unsigned char* __restrict__ iso,
+                                    const unsigned char* __restrict__ strong, int* __restrict__ sel)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int best = -1; double bv = 0.0;
+  if (!iso[i])
+    for (int p = ia[i]; p < ia[i + 1]; ++p) {
+      if (strong[p]) { best = -1; break; }
+      const int j = ja[p];
+      if (j == i || iso[j]) continue;
+      if (pp[p] > bv) { bv = pp[p]; best = p; }
+    }
+  sel[i] = best;
+}
+
+__global__ void force_apply_kernel(int n, const int* __restrict__ tslot, const int* __restrict__ sel,
+                                   unsigned char* __restrict__ strong)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = sel[i];
+  if (b >= 0) { strong[b] = 1; if (tslot[b] >= 0) strong[tslot[b]] = 1; }
+}
+
+__device__ __forceinline__ u64 mis_key(int rank, int i)
+{
+  return ((u64)rank << 62) | ((u64)(hash32((unsigned)i) & 0x3fffffffu) << 32) | (u64)(unsigned)i;
+}
+
+// state: 0 undecided, 1 root, 2 covered / excluded
+__global__ void mis_init_kernel(int n, const unsigned char* __restrict__ iso, int* __restrict__ state)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) state[i] = iso[i] ? 2 : 0;
+}
+
+template <bool FIRST>
+__global__ void mis_prop_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                                const unsigned char* __restrict__ strong, const int* __restrict__ state,
+                                const u64* __restrict__ tin, u64* __restrict__ tout)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto key = [&](int j) -> u64 {
+    if (!FIRST) return tin[j];
+    const int st = state[j];
+    return mis_key(st == 1 ? 2 : st == 0 ? 1 : 0, j);
+  };
+  u64 m = key(i);
+  for (int p = ia[i]; p < ia[i + 1]; ++p)
+    if (strong[p]) { const u64 k = key(ja[p]); m = k > m ? k : m; }
+  tout[i] = m;
+}
+
+__global__ void mis_decide_kernel(int n, const u64* __restrict__ t2, int* __restrict__ state,
+                                  int* __restrict__ undecided)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || state[i] != 0) return;
+  const u64 m = t2[i];
+  if ((int)(m & 0xffffffffu) == i) state[i] = 1;
+  else if ((m >> 62) == 2) state[i] = 2;
+  else atomicAdd(undecided, 1);
+}
+
+__global__ void root_flag_kernel(int n, const int* __restrict__ state, int* __restrict__ flag)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = state[i] == 1 ? 1 : 0;
+  if (i == n) flag[n] = 0;
+}
+
+// pass 0: roots take their id; pass >=1: unassigned rows join the strongest strong neighbour
+// that was assigned in an EARLIER pass (agg_in snapshot) — deterministic
+__global__ void agg_root_kernel(int n, const int* __restrict__ state, const int* __restrict__ rootid,
+                                const unsigned char* __restrict__ iso, int* __restrict__ agg)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  agg[i] = state[i] == 1 ? rootid[i] : (iso[i] ? -1 : -2);
+}
+
+__global__ void agg_join_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                                const unsigned char* __restrict__ strong, const double* __restrict__ pp,
+                                const int* __restrict__ agg_in, int* __restrict__ agg_out, int* __restrict__ left)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int a = agg_in[i];
+  if (a == -2) {
+    double bv = -1.0;
+    for (int p = ia[i]; p < ia[i + 1]; ++p) {
+      if (!strong[p]) continue;
+      const int aj = agg_in[ja[p]];
+      if (aj >= 0 && pp[p] > bv) { bv = pp[p]; a = aj; }
+    }
+    if (a == -2) atomicAdd(left, 1);
+  }
+  agg_out[i] = a;
+}
+
+__global__ void agg_finalize_kernel(int n, int* __restrict__ agg)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && agg[i] < -1) agg[i] = -1;
+}
+
+__global__ void agg_count_kernel(int n, const int* __restrict__ agg, int* __restrict__ cnt)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && agg[i] >= 0) atomicAdd(&cnt[agg[i]], 1);
+}
+
+__global__ void iota_kernel(int n, int* __restrict__ a)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+
+__global__ void agg_key_kernel(int n, const int* __restrict__ agg, unsigned* __restrict__ key)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) key[i] = agg[i] >= 0 ? (unsigned)agg[i] : 0xffffffffu;
+}
+
+// ---- Galerkin product with the boolean prolongator ------------------------------------------
+__global__ void rap_key_kernel(int nnzb, const int* __restrict__ ja, const int* __restrict__ brow,
+                               const int* __restrict__ agg, u64 nagg, u64* __restrict__ key, int* __restrict__ idx)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int I = agg[brow[b]], J = agg[ja[b]];
+  key[b] = (I >= 0 && J >= 0) ? (u64)I * nagg + (u64)J : ~0ull;
+  idx[b] = b;
+}
+
+__global__ void rap_head_kernel(int nnzb, const u64* __restrict__ key, int* __restrict__ head)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > nnzb) return;
+  if (p == nnzb) { head[p] = 0; return; }
+  const u64 k = key[p];
+  head[p] = (k != ~0ull && (p == 0 || key[p - 1] != k)) ? 1 : 0;
+}
+
+__global__ void rap_structure_kernel(int nnzb, const u64* __restrict__ key, const int* __restrict__ head,
+                                     const int* __restrict__ slot, u64 nagg, int* __restrict__ cja,
+                                     int* __restrict__ seg, int* __restrict__ rowcnt, int* __restrict__ nvalid)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnzb) return;
+  const u64 k = key[p];
+  if (k == ~0ull) { if (p == 0 || key[p - 1] != ~0ull) *nvalid = p; return; }
+  if (p == nnzb - 1) *nvalid = nnzb;
+  if (head[p]) {
+    const int s = slot[p];
+    cja[s] = (int)(k % nagg);
+    seg[s] = p;
+    atomicAdd(&rowcnt[(int)(k / nagg)], 1);
+  }
+}
+
+__global__ void rap_numeric_kernel(int cnnzb, const int* __restrict__ cia, const int* __restrict__ cbrow,
+                                   const int* __restrict__ seg, const int* __restrict__ perm,
+                                   const int* __restrict__ fia, const int* __restrict__ fbrow,
+                                   const double* __restrict__ fval, double* __restrict__ cval)
+{
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 9 * (size_t)cnnzb) return;
+  const int s = (int)(e / 9), t = (int)(e % 9);
+  double acc = 0.0;
+  for (int p = seg[s]; p < seg[s + 1]; ++p) {
+    const int b = perm[p];
+    const int i = fbrow[b], fs = fia[i], flen = fia[i + 1] - fs;
+    acc += fval[9 * (size_t)fs + (size_t)t * flen + (b - fs)];
+  }
+  const int I = cbrow[s], cs = cia[I], clen = cia[I + 1] - cs;
+  cval[9 * (size_t)cs + (size_t)t * clen + (s - cs)] = acc;
+}
+
+// ---- grid transfer ---------------------------------------------------------------------------
+__global__ void restrict_kernel(int nagg, const int* __restrict__ agg_ptr, const int* __restrict__ agg_rows,
+                                const double* __restrict__ r, double* __restrict__ bc)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * nagg) return;
+  const int I = e / 3, k = e % 3;
+  double a = 0.0;
+  for (int p = agg_ptr[I]; p < agg_ptr[I + 1]; ++p) a += r[3 * (size_t)agg_rows[p] + k];
+  bc[e] = a;
+}
+
+__global__ void prolong_kernel(int n, const int* __restrict__ agg, const double* __restrict__ ec,
+                               double* __restrict__ x)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * n) return;
+  const int a = agg[e / 3];
+  if (a >= 0) x[e] += ec[3 * (size_t)a + e % 3];
+}
+
+// ---- coarsest level: dense inverse -------------------------------------------------------------
+__global__ void dense_fill_kernel(int nnzb, int nd, const int* __restrict__ ia, const int* __restrict__ ja,
+                                  const int* __restrict__ brow, const double* __restrict__ val,
+                                  double* __restrict__ D)
+{
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 9 * (size_t)nnzb) return;
+  const int b = (int)(e / 9), t = (int)(e % 9);
+  const int i = brow[b], s = ia[i], len = ia[i + 1] - s;
+  D[(size_t)(3 * i + t / 3) * nd + 3 * ja[b] + t % 3] = val[9 * (size_t)s + (size_t)t * len + (b - s)];
+}
+
+__global__ void identity_kernel(int nd, double* __restrict__ D)
+{
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < (size_t)nd * nd) D[e] = (e / nd == e % nd) ? 1.0 : 0.0;
+}
+
+// Gauss-Jordan with partial pivoting, one CTA; A is destroyed, Inv receives A^{-1}
+__global__ void __launch_bounds__(1024) dense_invert_kernel(int nd, double* __restrict__ A, double* __restrict__ Inv,
+                                                           double* __restrict__ colk, int* __restrict__ singular)
+{
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_piv;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = 0; k < nd; ++k) {
+    // pivot search
+    double bv = -1.0; int bi = k;
+    for (int r = k + tid; r < nd; r += nt) { const double v = fabs(A[(size_t)r * nd + k]); if (v > bv) { bv = v; bi = r; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+      bv = tid < (nt >> 5) ? s_val[tid] : -1.0; bi = tid < (nt >> 5) ? s_idx[tid] : k;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (tid == 0) { s_piv = bi; if (!(bv > 0.0)) *singular = 1; }
+    }
+    __syncthreads();
+    const int pv = s_piv;
+    if (pv != k)
+      for (int c = tid; c < nd; c += nt) {
+        double t = A[(size_t)k * nd + c]; A[(size_t)k * nd + c] = A[(size_t)pv * nd + c]; A[(size_t)pv * nd + c] = t;
+        t = Inv[(size_t)k * nd + c]; Inv[(size_t)k * nd + c] = Inv[(size_t)pv * nd + c]; Inv[(size_t)pv * nd + c] = t;
+      }
+    __syncthreads();
+    const double ip = 1.0 / A[(size_t)k * nd + k];
+    __syncthreads();
+    for (int c = tid; c < nd; c += nt) { A[(size_t)k * nd + c] *= ip; Inv[(size_t)k * nd + c] *= ip; }
+    for (int r = tid; r < nd; r += nt) colk[r] = A[(size_t)r * nd + k];
+    __syncthreads();
+    for (size_t e = tid; e < (size_t)nd * nd; e += nt) {
+      const int r = (int)(e / nd), c = (int)(e % nd);
+      if (r == k) continue;
+      const double f = colk[r];
+      if (f == 0.0) continue;
+      if (c >= k) A[e] -= f * A[(size_t)k * nd + c];
+      Inv[e] -= f * Inv[(size_t)k * nd + c];
+    }
+    __syncthreads();
+  }
+}
+
+// x = Inv * b, one warp per row
+__global__ void dense_matvec_kernel(int nd, const double* __restrict__ Inv, const double* __restrict__ b,
+                                    double* __restrict__ x)
+{
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= nd) return;
+  double a = 0.0;
+  for (int c = lane; c < nd; c += 32) a += Inv[(size_t)row * nd + c] * b[c];
+  a = warp_sum(a);
+  if (lane == 0) x[row] = a;
+}
+
+template <typename K, typename V>
+void sort_pairs(K* kin, K* kout, V* vin, V* vout, int n, int end_bit, cudaStream_t s)
+{
+  size_t bytes = 0;
+  PNP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, end_bit, s));
+  DevBuf<unsigned char> tmp; tmp.alloc(bytes, s);
+  PNP_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, n, 0, end_bit, s));
+  PNP_COUNT_LAUNCH();
+}
+
+int bits_for(u64 v) { int b = 1; while (b < 64 && (v >> b)) ++b; return b; }
+
+// symbolic part of one coarsening step: aggregates of L and the structure of the next level
+bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
+{
+  cudaStream_t s = h.stream;
+  BsrT& A = L.A;
+  const int n = A.n, nnzb = A.nnzb;
+  DevBuf<double> pp; pp.alloc(nnzb, s);
+  condense_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ia.p, A.brow.p, A.val.p, pp.p); PNP_COUNT_LAUNCH();
+  DevBuf<unsigned char> iso, strong; iso.alloc(n, s); strong.alloc(nnzb, s);
+  isolated_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, pp.p, iso.p); PNP_COUNT_LAUNCH();
+  strength_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, A.dslot.p, A.tslot.p, pp.p, iso.p,
+                                                 theta * theta, strong.p); PNP_COUNT_LAUNCH();
+  {
+    DevBuf<int> sel; sel.alloc(n, s);
+    force_select_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, pp.p, iso.p, strong.p, sel.p); PNP_COUNT_LAUNCH();
+    force_apply_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.tslot.p, sel.p, strong.p); PNP_COUNT_LAUNCH();
+  }
+  // distance-2 MIS
+  DevBuf<int> state, cnt; state.alloc(n, s); cnt.alloc(1, s);
+  DevBuf<u64> t1, t2; t1.alloc(n, s); t2.alloc(n, s);
+  mis_init_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, iso.p, state.p); PNP_COUNT_LAUNCH();
+  int und = 1, rounds = 0;
+  while (und > 0) {
+    cnt.zero();
+    mis_prop_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, strong.p, state.p, nullptr, t1.p); PNP_COUNT_LAUNCH();
+    mis_prop_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, strong.p, state.p, t1.p, t2.p); PNP_COUNT_LAUNCH();
+    mis_decide_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, t2.p, state.p, cnt.p); PNP_COUNT_LAUNCH();
+    PNP_CUDA(cudaMemcpyAsync(&und, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaStreamSynchronize(s));
+    if (++rounds > 1000) throw Error(ERROR_AMG_COARSEING, "MIS-2 did not terminate");
+  }
+  // aggregate ids
+  DevBuf<int> flag, rootid; flag.alloc(n + 1, s); rootid.alloc(n + 1, s);
+  root_flag_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(n, state.p, flag.p); PNP_COUNT_LAUNCH();
+  exclusive_scan_int(flag.p, rootid.p, n + 1, s);
+  int nagg = 0;
+  PNP_CUDA(cudaMemcpyAsync(&nagg, rootid.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  if (nagg == 0 || nagg >= n) return false;
+  L.agg.alloc(n, s);
+  DevBuf<int> agg2; agg2.alloc(n, s);
+  agg_root_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, state.p, rootid.p, iso.p, L.agg.p); PNP_COUNT_LAUNCH();
+  int left = 1; int* cur = L.agg.p; int* nxt = agg2.p;
+  for (int pass = 0; pass < 8 && left > 0; ++pass) {
+    cnt.zero();
+    agg_join_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, strong.p, pp.p, cur, nxt, cnt.p); PNP_COUNT_LAUNCH();
+    PNP_CUDA(cudaMemcpyAsync(&left, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaStreamSynchronize(s));
+    std::swap(cur, nxt);
+  }
+  if (cur != L.agg.p) PNP_CUDA(cudaMemcpyAsync(L.agg.p, cur, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  agg_finalize_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.agg.p); PNP_COUNT_LAUNCH();
+  L.nagg = nagg;
+  // members of each aggregate (ascending rows)
+  {
+    DevBuf<int> c; c.alloc(nagg + 1, s); c.zero();
+    agg_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.agg.p, c.p); PNP_COUNT_LAUNCH();
+    L.agg_ptr.alloc(nagg + 1, s);
+    exclusive_scan_int(c.p, L.agg_ptr.p, nagg + 1, s);
+    DevBuf<unsigned> kin, kout; kin.alloc(n, s); kout.alloc(n, s);
+    DevBuf<int> vin; vin.alloc(n, s); L.agg_rows.alloc(n, s);
+    agg_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.agg.p, kin.p); PNP_COUNT_LAUNCH();
+    iota_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, vin.p); PNP_COUNT_LAUNCH();
+    sort_pairs(kin.p, kout.p, vin.p, L.agg_rows.p, n, 32, s);
+  }
+  // coarse structure: sort blocks by (I,J)
+  {
+    DevBuf<u64> kin, kout; kin.alloc(nnzb, s); kout.alloc(nnzb, s);
+    DevBuf<int> vin; vin.alloc(nnzb, s); L.rap_perm.alloc(nnzb, s);
+    rap_key_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, L.agg.p, (u64)nagg, kin.p, vin.p); PNP_COUNT_LAUNCH();
+    sort_pairs(kin.p, kout.p, vin.p, L.rap_perm.p, nnzb, 64, s);
+    DevBuf<int> head, slot; head.alloc(nnzb + 1, s); slot.alloc(nnzb + 1, s);
+    rap_head_kernel<<<cdiv(nnzb + 1, 256), 256, 0, s>>>(nnzb, kout.p, head.p); PNP_COUNT_LAUNCH();
+    exclusive_scan_int(head.p, slot.p, nnzb + 1, s);
+    int cnnzb = 0;
+    PNP_CUDA(cudaMemcpyAsync(&cnnzb, slot.p + nnzb, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaStreamSynchronize(s));
+    BsrT& Ac = C.A;
+    Ac.n = nagg; Ac.nnzb = cnnzb;
+    Ac.ja.alloc(cnnzb, s); Ac.ia.alloc(nagg + 1, s); Ac.val.alloc(9 * (size_t)cnnzb, s);
+    L.rap_seg.alloc(cnnzb + 1, s);
+    DevBuf<int> rowcnt; rowcnt.alloc(nagg + 1, s); rowcnt.zero();
+    int* nvalid = L.rap_seg.p + cnnzb;
+    rap_structure_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, kout.p, head.p, slot.p, (u64)nagg, Ac.ja.p, L.rap_seg.p,
+                                                        rowcnt.p, nvalid); PNP_COUNT_LAUNCH();
+    exclusive_scan_int(rowcnt.p, Ac.ia.p, nagg + 1, s);
+    finish_pattern_tables(Ac, s);
+  }
+  return true;
+}
+
+void rap_numeric(Handle& h, Level& L, Level& C)
+{
+  cudaStream_t s = h.stream;
+  BsrT& A = L.A; BsrT& Ac = C.A;
+  rap_numeric_kernel<<<cdiv(9 * (size_t)Ac.nnzb, 256), 256, 0, s>>>(Ac.nnzb, Ac.ia.p, Ac.brow.p, L.rap_seg.p, L.rap_perm.p,
+                                                                   A.ia.p, A.brow.p, A.val.p, Ac.val.p);
+  PNP_COUNT_LAUNCH();
+}
+
+void alloc_level_vectors(Level& L, cudaStream_t s)
+{
+  const size_t m = 3 * (size_t)L.A.n;
+  L.x.alloc(m, s); L.b.alloc(m, s); L.w.alloc(m, s);
+  L.dinv.alloc(9 * (size_t)L.A.n, s);
+}
+
+} // namespace
+
+SolverConfig make_config(const itsolver_param* it, const AMG_param* amg)
+{
+  SolverConfig c;
+  if (it) {
+    c.tol = it->tol; c.maxit = it->maxit; c.restart = it->restart > 0 ? it->restart : 30;
+    c.print_level = it->print_level;
+  }
+  if (amg) {
+    c.max_levels = amg->max_levels > 0 ? amg->max_levels : 20;
+    c.coarse_dof = amg->coarse_dof > 0 ? amg->coarse_dof : 100;
+    c.strong_coupled = amg->strong_coupled; c.max_aggregation = amg->max_aggregation;
+    c.tentative_smooth = amg->tentative_smooth;
+    c.presmooth = amg->presmooth_iter; c.postsmooth = amg->postsmooth_iter;
+    if (amg->print_level > c.print_level) c.print_level = amg->print_level;
+  } else c.use_amg = 0;
+  if (c.restart > 31) c.restart = 31;      // fused orthogonalisation kernels carry <= 32 coefficients
+  if (c.restart > c.maxit && c.maxit > 0) c.restart = c.maxit;
+  return c;
+}
+
+void amg_setup(Handle& h, const SolverConfig& cfg)
+{
+  cudaStream_t s = h.stream;
+  auto& lv = h.hier.lv;
+  Level& F = *lv[0];
+  const bool reuse = h.reuse_hierarchy && h.hier.symbolic_valid;
+  if (F.ncolors == 0) color_level(F, s);           // pattern-only: survives across solves
+  alloc_level_vectors(F, s);
+  if (!reuse) { lv.resize(1); h.hier.symbolic_valid = false; }
+  const int min_cdof = cfg.coarse_dof > 50 ? cfg.coarse_dof : 50;
+  int l = 0;
+  while (true) {
+    Level& L = *lv[l];
+    bsrt_diaginv(L.A, L.dinv.p, s);
+    if (reuse) {
+      if (l + 1 >= (int)lv.size()) break;
+      rap_numeric(h, L, *lv[l + 1]);
+      ++l; continue;
+    }
+    if (!(L.A.n > min_cdof && l < cfg.max_levels - 1)) break;
+    const double theta = cfg.tentative_smooth > 1e-20 ? cfg.strong_coupled * std::pow(0.5, l) : cfg.strong_coupled;
+    std::unique_ptr<Level> C(new Level);
+    if (!coarsen_symbolic(h, L, *C, theta)) break;
+    rap_numeric(h, L, *C);
+    alloc_level_vectors(*C, s);
+    color_level(*C, s);
+    lv.push_back(std::move(C));
+    ++l;
+  }
+  // coarsest level: explicit dense inverse
+  Level& Z = *lv.back();
+  const int nd = 3 * Z.A.n;
+  if (nd > 6144) throw Error(ERROR_AMG_COARSEING, "coarsest level too large for the dense solver");
+  h.hier.nd = nd;
+  DevBuf<double> D, colk; DevBuf<int> sing;
+  D.alloc((size_t)nd * nd, s); colk.alloc(nd, s); sing.alloc(1, s); sing.zero();
+  h.hier.dense_inv.alloc((size_t)nd * nd, s);
+  D.zero();
+  dense_fill_kernel<<<cdiv(9 * (size_t)Z.A.nnzb, 256), 256, 0, s>>>(Z.A.nnzb, nd, Z.A.ia.p, Z.A.ja.p, Z.A.brow.p, Z.A.val.p, D.p);
+  PNP_COUNT_LAUNCH();
+  identity_kernel<<<cdiv((size_t)nd * nd, 256), 256, 0, s>>>(nd, h.hier.dense_inv.p); PNP_COUNT_LAUNCH();
+  dense_invert_kernel<<<1, 1024, 0, s>>>(nd, D.p, h.hier.dense_inv.p, colk.p, sing.p); PNP_COUNT_LAUNCH();
+  PNP_LAUNCH_CHECK();
+  h.hier.symbolic_valid = true;
+  if (cfg.print_level > 0) {
+    PNP_CUDA(cudaStreamSynchronize(s));
+    for (size_t k = 0; k < lv.size(); ++k)
+      printf("  [pnpb200 amg] level %zu: rows %d nnzb %d colours %d\n", k, lv[k]->A.n, lv[k]->A.nnzb, lv[k]->ncolors);
+  }
+}
+
+// z = M^{-1} r : one V(nu1,nu2) cycle from a zero initial guess (fasp_precond_dbsr_amg [EXT])
+void amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z)
+{
+  cudaStream_t s = h.stream;
+  auto& lv = h.hier.lv;
+  const int nl = (int)lv.size();
+  const double* bl = r;
+  double* xl = z;
+  // level 0 works directly on the caller's vectors
+  for (int l = 0; l < nl - 1; ++l) {
+    Level& L = *lv[l];
+    const size_t m = 3 * (size_t)L.A.n;
+    vec_set(xl, 0.0, m, s);
+    for (int k = 0; k < cfg.presmooth; ++k) mcgs_sweep(L, bl, xl, false, s);
+    bsrt_residual(L.A, bl, xl, L.w.p, s);
+    Level& C = *lv[l + 1];
+    restrict_kernel<<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, L.agg_ptr.p, L.agg_rows.p, L.w.p, C.b.p);
+    PNP_COUNT_LAUNCH();
+    bl = C.b.p; xl = C.x.p;
+  }
+  {
+    Level& Z = *lv[nl - 1];
+    if (nl == 1) {
+      vec_set(xl, 0.0, 3 * (size_t)Z.A.n, s);
+      for (int k = 0; k < cfg.presmooth; ++k) mcgs_sweep(Z, bl, xl, false, s);
+    } else {
+      dense_matvec_kernel<<<cdiv((size_t)h.hier.nd * 32, 256), 256, 0, s>>>(h.hier.nd, h.hier.dense_inv.p, bl, xl);
+      PNP_COUNT_LAUNCH();
+    }
+  }
+  for (int l = nl - 2; l >= 0; --l) {
+    Level& L = *lv[l];
+    Level& C = *lv[l + 1];
+    double* x = l == 0 ? z : L.x.p;
+    const double* b = l == 0 ? r : L.b.p;
+    prolong_kernel<<<cdiv(3 * (size_t)L.A.n, 256), 256, 0, s>>>(L.A.n, L.agg.p, C.x.p, x); PNP_COUNT_LAUNCH();
+    for (int k = 0; k < cfg.postsmooth; ++k) mcgs_sweep(L, b, x, true, s);
+  }
+}
+
+} // namespace pnpb200

@@ -1,0 +1,389 @@
+// pnp-b200 — device assembly of the linearised PNP system:
+//   PDE::setup_linear_algebra            src/pde.cpp:542-555   (Galerkin a, L; Dirichlet rows)
+//   Linear_PNP::apply_eafe               benchmarks/pnp_exact_solution/linear_pnp.cpp:195-285
+//   BC re-apply after EAFE               linear_pnp.cpp:78-80
+//   zero-row fix                         src/pde.cpp:596-621
+// Two passes, both atomic-free and deterministic:
+//   (A) cell kernels evaluate the quadrature sums of the generated forms
+//       (forms.h:7917-8360 bilinear, 24-point rule; :8385-8644 linear, 15-point rule) once per
+//       cell into a compact record (geometry is constant per P1 cell, so the 12x12 tensor
+//       factorises into 32 numbers);
+//   (B) block kernels own one 3x3 block (i,j) each, gather the records of the cells that
+//       contain both vertices in ascending cell order (the sorted key is the block index),
+//       evaluate the EAFE edge formula (include/EAFE.h:4851-4879) for the (k,k) entries and
+//       write the finished block once, in BSR-T layout.
+#include "internal.hpp"
+#include "fem.cuh"
+
+namespace pnpb200 {
+
+namespace {
+
+constexpr int REC_EAFE = 32;   // G[10] Q[2] detM1[10] detM2[10]
+constexpr int REC_FULL = 68;   // + S[2] T1[16] T2[16] (+2 pad)
+
+// ---- (A) Jacobian cell records -------------------------------------------------------------
+template <bool FULL>
+__global__ void __launch_bounds__(128)
+cell_jacobian_kernel(int nc, const int4* __restrict__ cells, const double* __restrict__ xyz,
+                     const double* __restrict__ uu, const double* __restrict__ diff,
+                     const double* __restrict__ val, double* __restrict__ rec)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int4 cv = cells[c];
+  const int v[4] = {cv.x, cv.y, cv.z, cv.w};
+  double x[4][3], g[4][3], det;
+  load_cell_xyz(xyz, cv, x);
+  tet_geom(x, g, det);
+  double u0[4], u[2][4], D[2][4], q[2][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const size_t d = 3 * (size_t)v[r];
+    u0[r] = uu[d]; u[0][r] = uu[d + 1]; u[1][r] = uu[d + 2];
+    D[0][r] = diff[d + 1]; D[1][r] = diff[d + 2];
+    q[0][r] = val[d + 1];  q[1][r] = val[d + 2];
+  }
+  double Q[2] = {0.0, 0.0}, M[2][10];
+  double S[2] = {0.0, 0.0}, c0[2][4], c1[2][4], c2[2][4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int t = 0; t < 10; ++t) M[k][t] = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { c0[k][t] = 0.0; c1[k][t] = 0.0; c2[k][t] = 0.0; }
+  }
+#pragma unroll 1
+  for (int ip = 0; ip < 24; ++ip) {
+    const double f[4] = {c_P24[ip][0], c_P24[ip][1], c_P24[ip][2], c_P24[ip][3]};
+    const double W = c_W24[ip];
+    const double u0ip = f[0] * u0[0] + f[1] * u0[1] + f[2] * u0[2] + f[3] * u0[3];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double uk = f[0] * u[k][0] + f[1] * u[k][1] + f[2] * u[k][2] + f[3] * u[k][3];
+      const double Dk = f[0] * D[k][0] + f[1] * D[k][1] + f[2] * D[k][2] + f[3] * D[k][3];
+      const double qk = f[0] * q[k][0] + f[1] * q[k][1] + f[2] * q[k][2] + f[3] * q[k][3];
+      const double ex = exp(uk);
+      Q[k] += W * qk * Dk * ex;
+      const double t = W * qk * ex;
+      int m = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int s = r; s < 4; ++s) M[k][m++] += t * f[r] * f[s];
+      if (FULL) {
+        const double wd = W * Dk * ex;
+        S[k] += wd;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c0[k][j] += wd * f[j]; c1[k][j] += wd * qk * f[j]; c2[k][j] += wd * u0ip * f[j]; }
+      }
+    }
+  }
+  double* o = rec + (size_t)c * (FULL ? REC_FULL : REC_EAFE);
+  int m = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int s = r; s < 4; ++s) o[m++] = det * dot3(g[r], g[s]);
+  o[10] = Q[0]; o[11] = Q[1];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) { o[12 + t] = det * M[0][t]; o[22 + t] = det * M[1][t]; }
+  if (FULL) {
+    o[32] = S[0]; o[33] = S[1];
+    double gu0[3] = {0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) gu0[d] += u0[r] * g[r][d];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      double guk[3] = {0, 0, 0}, gqk[3] = {0, 0, 0};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { guk[d] += u[k][r] * g[r][d]; gqk[d] += q[k][r] * g[r][d]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double a = det * dot3(guk, g[i]), b = det * dot3(gu0, g[i]), cc = det * dot3(gqk, g[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[34 + 16 * k + 4 * i + j] = a * c0[k][j] + b * c1[k][j] + cc * c2[k][j];
+      }
+    }
+  }
+}
+
+// EAFE edge weight of the ordered pair (row r, column s) for ion k, exactly the expression of
+// include/EAFE.h:4857-4867 (no expm1, same 3e-16 branch): returns bern[r][s]
+__device__ __forceinline__ double eafe_weight(const double* __restrict__ uu, const double* __restrict__ diff,
+                                              int r, int s, int k, double qk)
+{
+  const double eta_r = uu[3 * (size_t)r + k], eta_s = uu[3 * (size_t)s + k];
+  double beta_r = eta_r, beta_s = eta_s;
+  if (qk != 0.0) { beta_r = eta_r + uu[3 * (size_t)r] * qk; beta_s = eta_s + uu[3 * (size_t)s] * qk; }
+  const double fr = eta_r - beta_r, fs = eta_s - beta_s;
+  const double d = fs - fr;
+  double aE = 0.5 * (diff[3 * (size_t)r + k] + diff[3 * (size_t)s + k]) * exp(fs);
+  aE *= (fabs(d) < 3.0e-16) ? 1.0 - 0.5 * d : d / (exp(d) - 1.0);
+  return aE * exp(beta_s);
+}
+
+// ---- (B) one thread per 3x3 block ----------------------------------------------------------
+template <bool EAFE>
+__global__ void __launch_bounds__(128)
+assemble_blocks_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ ja,
+                       const int* __restrict__ brow, const int* __restrict__ v2c_ptr,
+                       const int* __restrict__ v2c_idx, const int4* __restrict__ cells,
+                       const double* __restrict__ rec, const double* __restrict__ k00,
+                       const double* __restrict__ omega, const double* __restrict__ uu,
+                       const double* __restrict__ diff, double q1, double q2,
+                       const unsigned char* __restrict__ bcflag, double* __restrict__ val)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int i = brow[b], j = ja[b];
+  constexpr int RS = EAFE ? REC_EAFE : REC_FULL;
+  double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  a[0] = k00[b];
+  for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; ++p) {
+    const int c = v2c_idx[p];
+    const int4 cv = cells[c];
+    const int lj = local_index(cv, j);
+    if (lj < 0) continue;
+    const int li = local_index(cv, i);
+    const double* r = rec + (size_t)c * RS;
+    const int sidx = sym4(li, lj);
+    const double G = r[sidx];
+    a[3] += r[10] * G;          // (1,0): q1 D1 e^{u1} grad u0 . grad v1
+    a[6] += r[11] * G;          // (2,0)
+    a[1] -= r[12 + sidx];       // (0,1): -q1 e^{u1} u1 v0
+    a[2] -= r[22 + sidx];       // (0,2)
+    if (!EAFE) {
+      a[4] += r[32] * G + r[34 + 4 * li + lj];
+      a[8] += r[33] * G + r[50 + 4 * li + lj];
+    }
+  }
+  if (EAFE) {
+    if (i != j) {
+      const double w = omega[b];
+      a[4] = w * eafe_weight(uu, diff, i, j, 1, q1);
+      a[8] = w * eafe_weight(uu, diff, i, j, 2, q2);
+    } else {
+      // column sums vanish (EAFE.h:4876-4879): A_ii = -sum_{r != i} A_ri, omega symmetric
+      double s1 = 0.0, s2 = 0.0;
+      for (int p = ia[i]; p < ia[i + 1]; ++p) {
+        const int r = ja[p];
+        if (r == i) continue;
+        const double w = omega[p];
+        s1 -= w * eafe_weight(uu, diff, r, i, 1, q1);
+        s2 -= w * eafe_weight(uu, diff, r, i, 2, q2);
+      }
+      a[4] = s1; a[8] = s2;
+    }
+  }
+  // DirichletBC::apply: row -> identity row (pattern kept)
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (bcflag[3 * (size_t)i + k]) {
+      a[3 * k] = 0.0; a[3 * k + 1] = 0.0; a[3 * k + 2] = 0.0;
+      if (i == j) a[3 * k + k] = 1.0;
+    }
+  const int s = ia[i], len = ia[i + 1] - s;
+  double* o = val + 9 * (size_t)s + (b - s);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) o[(size_t)t * len] = a[t];
+}
+
+// zero-row fix (src/pde.cpp:596-621): a scalar row with no non-zero value gets diag = 1.
+// Such a row has a zero diagonal, so only rows whose diagonal entry is 0 are scanned.
+__global__ void zero_row_fix_kernel(int n, const int* __restrict__ ia, const int* __restrict__ dslot,
+                                    double* __restrict__ val)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = ia[i], len = ia[i + 1] - s, d = dslot[i];
+  if (d < 0) return;
+  double* base = val + 9 * (size_t)s;
+  for (int k = 0; k < 3; ++k) {
+    if (base[(size_t)(3 * k + k) * len + (d - s)] != 0.0) continue;
+    bool nz = false;
+    for (int c = 0; c < 3 && !nz; ++c)
+      for (int p = 0; p < len; ++p)
+        if (base[(size_t)(3 * k + c) * len + p] != 0.0) { nz = true; break; }
+    if (!nz) base[(size_t)(3 * k + k) * len + (d - s)] = 1.0;
+  }
+}
+
+// ---- residual: (A) per-cell 12-vector, (B) per-vertex gather + BC + norm partials ------------
+__global__ void __launch_bounds__(128)
+cell_residual_kernel(int nc, const int4* __restrict__ cells, const double* __restrict__ xyz,
+                     const double* __restrict__ uu, const double* __restrict__ eps,
+                     const double* __restrict__ fixed, const double* __restrict__ diff,
+                     const double* __restrict__ val, const double* __restrict__ reac,
+                     double* __restrict__ rec)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int4 cv = cells[c];
+  const int v[4] = {cv.x, cv.y, cv.z, cv.w};
+  double x[4][3], g[4][3], det;
+  load_cell_xyz(xyz, cv, x);
+  tet_geom(x, g, det);
+  double u0[4], e4[4], fc[4], u[2][4], D[2][4], q[2][4], rc[2][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const size_t d = 3 * (size_t)v[r];
+    u0[r] = uu[d]; u[0][r] = uu[d + 1]; u[1][r] = uu[d + 2];
+    D[0][r] = diff[d + 1]; D[1][r] = diff[d + 2];
+    q[0][r] = val[d + 1];  q[1][r] = val[d + 2];
+    rc[0][r] = reac[d + 1]; rc[1][r] = reac[d + 2];
+    e4[r] = eps[v[r]]; fc[r] = fixed[v[r]];
+  }
+  double F[4] = {0, 0, 0, 0}, E = 0.0, R[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  double s0[2] = {0, 0}, s1[2] = {0, 0}, s2[2] = {0, 0};
+#pragma unroll 1
+  for (int ip = 0; ip < 15; ++ip) {
+    const double f[4] = {c_P15[ip][0], c_P15[ip][1], c_P15[ip][2], c_P15[ip][3]};
+    const double W = c_W15[ip];
+    const double u0ip = f[0] * u0[0] + f[1] * u0[1] + f[2] * u0[2] + f[3] * u0[3];
+    const double eip = f[0] * e4[0] + f[1] * e4[1] + f[2] * e4[2] + f[3] * e4[3];
+    double src = f[0] * fc[0] + f[1] * fc[1] + f[2] * fc[2] + f[3] * fc[3];
+    E += W * eip;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double uk = f[0] * u[k][0] + f[1] * u[k][1] + f[2] * u[k][2] + f[3] * u[k][3];
+      const double Dk = f[0] * D[k][0] + f[1] * D[k][1] + f[2] * D[k][2] + f[3] * D[k][3];
+      const double qk = f[0] * q[k][0] + f[1] * q[k][1] + f[2] * q[k][2] + f[3] * q[k][3];
+      const double rk = f[0] * rc[k][0] + f[1] * rc[k][1] + f[2] * rc[k][2] + f[3] * rc[k][3];
+      const double ex = exp(uk);
+      src += qk * ex;
+      const double wd = W * Dk * ex;
+      s0[k] += wd; s1[k] += wd * qk; s2[k] += wd * u0ip;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) R[k][i] += W * rk * f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) F[i] += W * src * f[i];
+  }
+  double gu0[3] = {0, 0, 0};
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) gu0[d] += u0[r] * g[r][d];
+  double* o = rec + 12 * (size_t)c;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = det * F[i] - E * (det * dot3(gu0, g[i]));
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    double guk[3] = {0, 0, 0}, gqk[3] = {0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { guk[d] += u[k][r] * g[r][d]; gqk[d] += q[k][r] * g[r][d]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o[4 * (k + 1) + i] = det * R[k][i]
+                           - det * (s0[k] * dot3(guk, g[i]) + s1[k] * dot3(gu0, g[i]) + s2[k] * dot3(gqk, g[i]));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+residual_gather_kernel(int nv, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
+                       const int4* __restrict__ cells, const double* __restrict__ rec,
+                       const unsigned char* __restrict__ bcflag, double* __restrict__ out,
+                       double* __restrict__ partial /* [2*gridDim] sumsq, max */)
+{
+  __shared__ double sm[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double ss = 0.0, mx = 0.0;
+  if (i < nv) {
+    double b[3] = {0, 0, 0};
+    for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; ++p) {
+      const int c = v2c_idx[p];
+      const int li = local_index(cells[c], i);
+      const double* r = rec + 12 * (size_t)c;
+      b[0] += r[li]; b[1] += r[4 + li]; b[2] += r[8 + li];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (bcflag[3 * (size_t)i + k]) b[k] = 0.0;
+      out[3 * (size_t)i + k] = b[k];
+      ss += b[k] * b[k];
+      mx = fmax(mx, fabs(b[k]));
+    }
+  }
+  ss = block_sum(ss, sm);
+  mx = block_max(mx, sm);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = ss; partial[2 * blockIdx.x + 1] = mx; }
+}
+
+__global__ void __launch_bounds__(1024) finalize_norm_kernel(int nblk, const double* __restrict__ partial,
+                                                            double* __restrict__ out2)
+{
+  __shared__ double sm[32];
+  double ss = 0.0, mx = 0.0;
+  for (int t = threadIdx.x; t < nblk; t += blockDim.x) { ss += partial[2 * t]; mx = fmax(mx, partial[2 * t + 1]); }
+  ss = block_sum(ss, sm);
+  mx = block_max(mx, sm);
+  if (threadIdx.x == 0) { out2[0] = ss; out2[1] = mx; }
+}
+
+} // namespace
+
+void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf)
+{
+  cudaStream_t s = h.stream;
+  if (!h.have_coef) throw Error(ERROR_INPUT_PAR, "coefficients not set");
+  const int4* cells = reinterpret_cast<const int4*>(h.cells.p);
+  const size_t need = (size_t)h.nc * 12;
+  if (h.cellrec.n < need) h.cellrec.alloc(need, s);
+  out.alloc(3 * (size_t)h.nv, s);
+  cell_residual_kernel<<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.eps.p, h.fixed.p, h.diff.p,
+                                                      h.val.p, h.reac.p, h.cellrec.p);
+  PNP_COUNT_LAUNCH();
+  const int nblk = cdiv(h.nv, 256);
+  h.red.alloc(2 * (size_t)nblk + 2, s);
+  residual_gather_kernel<<<nblk, 256, 0, s>>>(h.nv, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.bcflag.p, out.p, h.red.p + 2);
+  PNP_COUNT_LAUNCH();
+  finalize_norm_kernel<<<1, 1024, 0, s>>>(nblk, h.red.p + 2, h.red.p);
+  PNP_COUNT_LAUNCH();
+  PNP_LAUNCH_CHECK();
+  if (l2 || linf) {
+    PNP_CUDA(cudaMemcpyAsync(h.h_red, h.red.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaStreamSynchronize(s));
+    if (l2) *l2 = sqrt(h.h_red[0]);
+    if (linf) *linf = h.h_red[1];
+  }
+}
+
+void assemble_system(Handle& h)
+{
+  cudaStream_t s = h.stream;
+  if (!h.have_coef) throw Error(ERROR_INPUT_PAR, "coefficients not set");
+  const int4* cells = reinterpret_cast<const int4*>(h.cells.p);
+  BsrT& A = h.hier.lv[0]->A;
+  // rhs first (re-uses the record buffer)
+  assemble_residual(h, h.rhs, nullptr, nullptr);
+  const int rs = h.use_eafe ? REC_EAFE : REC_FULL;
+  const size_t need = (size_t)h.nc * rs;
+  if (h.cellrec.n < need) h.cellrec.alloc(need, s);
+  if (h.use_eafe) {
+    cell_jacobian_kernel<false><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.cellrec.p);
+    PNP_COUNT_LAUNCH();
+    assemble_blocks_kernel<true><<<cdiv(A.nnzb, 128), 128, 0, s>>>(
+        A.nnzb, A.ia.p, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
+        h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
+    PNP_COUNT_LAUNCH();
+  } else {
+    cell_jacobian_kernel<true><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.cellrec.p);
+    PNP_COUNT_LAUNCH();
+    assemble_blocks_kernel<false><<<cdiv(A.nnzb, 128), 128, 0, s>>>(
+        A.nnzb, A.ia.p, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
+        h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
+    PNP_COUNT_LAUNCH();
+  }
+  zero_row_fix_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.dslot.p, A.val.p);
+  PNP_COUNT_LAUNCH();
+  PNP_LAUNCH_CHECK();
+}
+
+} // namespace pnpb200

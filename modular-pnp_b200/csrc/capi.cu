@@ -1,0 +1,580 @@
+// pnp-b200 — C-ABI entry points (include/pnpb200/pnpb200.h, include/pnpb200/fasp_compat.h).
+// Every function is a thin shell: argument checks, host<->device copies, then the device
+// pipeline. C++ exceptions never cross the boundary; failures become FASP-style negative codes.
+#include "internal.hpp"
+#include <cstring>
+#include <cmath>
+#include <mutex>
+
+using namespace pnpb200;
+
+struct pnpb200_handle { Handle h; };
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(F&& f)
+{
+  try { return f(); }
+  catch (const Error& e) { g_last_error = e.what(); fprintf(stderr, "### pnpb200 ERROR: %s\n", e.what()); return e.code; }
+  catch (const std::exception& e) { g_last_error = e.what(); fprintf(stderr, "### pnpb200 ERROR: %s\n", e.what()); return ERROR_UNKNOWN; }
+}
+
+void init_handle(Handle& h, int device)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw Error(ERROR_DEVICE, "no CUDA device available (pnp-b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) throw Error(ERROR_INPUT_PAR, "bad device ordinal");
+  h.device = device;
+  PNP_CUDA(cudaSetDevice(device));
+  PNP_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+  h.owner.s = h.stream;
+  cudaMemPool_t pool;
+  PNP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long thr = ~0ull;                 // keep freed blocks cached in the pool
+  PNP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  PNP_CUDA(cudaMallocHost((void**)&h.h_red, 64 * sizeof(double)));
+  for (int i = 0; i < 8; ++i) PNP_CUDA(cudaEventCreate(&h.ev[i]));
+  h.hier.lv.emplace_back(new Level);
+}
+
+struct EventSpan {
+  Handle& h; double& out;
+  EventSpan(Handle& hh, double& o) : h(hh), out(o) { cudaEventRecord(h.ev[0], h.stream); }
+  void stop()
+  {
+    cudaEventRecord(h.ev[1], h.stream); cudaEventSynchronize(h.ev[1]);
+    float ms = 0; cudaEventElapsedTime(&ms, h.ev[0], h.ev[1]); out = ms;
+  }
+};
+
+int solve_current(Handle& h, const itsolver_param* it, const AMG_param* amg, int* status_its)
+{
+  cudaStream_t s = h.stream;
+  const SolverConfig cfg = make_config(it, amg);
+  const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
+  h.du.alloc(N, s);
+  vec_set(h.du.p, 0.0, N, s);                       // linear_pnp.cpp:93 fasp_dvec_set(..., 0.0)
+  h.stats.ms_spmv = h.stats.ms_vcycle = h.stats.ms_ortho = 0.0;
+  { EventSpan e(h, h.stats.ms_setup); if (cfg.use_amg) amg_setup(h, cfg); e.stop(); }
+  int st;
+  { EventSpan e(h, h.stats.ms_krylov); st = fgmres_solve(h, cfg, h.rhs.p, h.du.p); e.stop(); }
+  if (status_its) *status_its = st;
+  return FASP_SUCCESS;
+}
+
+// temporary solver-only handle around a host FASP matrix
+struct HostSystem {
+  pnpb200_handle* ph = nullptr;
+  HostSystem(const dBSRmat* A)
+  {
+    if (!A || A->nb != 3 || A->ROW < 1 || A->NNZ < 1 || !A->IA || !A->JA || !A->val)
+      throw Error(ERROR_INPUT_PAR, "dBSRmat must be a non-empty nb=3 matrix");
+    if (A->ROW != A->COL) throw Error(ERROR_INPUT_PAR, "dBSRmat must be square");
+    int dev = 0; cudaGetDevice(&dev);
+    ph = new pnpb200_handle;
+    try {
+      init_handle(ph->h, dev);
+      Handle& h = ph->h; cudaStream_t s = h.stream;
+      BsrT& M = h.hier.lv[0]->A;
+      M.n = A->ROW; M.nnzb = A->NNZ;
+      M.ia.alloc(M.n + 1, s); M.ja.alloc(M.nnzb, s); M.val.alloc(9 * (size_t)M.nnzb, s);
+      M.ia.upload(A->IA, M.n + 1); M.ja.upload(A->JA, M.nnzb);
+      finish_pattern_tables(M, s);
+      DevBuf<double> tmp; tmp.alloc(9 * (size_t)M.nnzb, s);
+      tmp.upload(A->val, 9 * (size_t)M.nnzb);
+      bsrt_from_fasp(M.ia.p, M.ja.p, tmp.p, M, s);
+      std::vector<int> ds = M.dslot.to_host(M.n);
+      for (int v : ds) if (v < 0) throw Error(ERROR_DATA_STRUCTURE, "dBSRmat row without a diagonal block");
+    } catch (...) { delete ph; ph = nullptr; throw; }
+  }
+  ~HostSystem() { delete ph; }
+};
+
+} // namespace
+
+// ---- fasp_format_dcsr_dbsr on the device -------------------------------------------------------
+namespace {
+// one thread per block row: nb-way merge of the (sorted) scalar rows
+template <bool FILL>
+__global__ void csr2bsr_kernel(int nbrow, int nb, const int* __restrict__ IA, const int* __restrict__ JA,
+                               const double* __restrict__ val, int* __restrict__ cnt, const int* __restrict__ bIA,
+                               int* __restrict__ bJA, double* __restrict__ bval, int* __restrict__ err)
+{
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= nbrow) return;
+  int ptr[8], end[8];
+  for (int r = 0; r < nb; ++r) { ptr[r] = IA[nb * I + r]; end[r] = IA[nb * I + r + 1]; }
+  int count = 0, last = -1;
+  while (true) {
+    int c = 0x7fffffff;
+    for (int r = 0; r < nb; ++r) if (ptr[r] < end[r]) { const int cc = JA[ptr[r]] / nb; c = cc < c ? cc : c; }
+    if (c == 0x7fffffff) break;
+    if (c <= last) { *err = 1; break; }      // unsorted input rows
+    last = c;
+    const int slot = FILL ? bIA[I] + count : 0;
+    if (FILL) bJA[slot] = c;
+    for (int r = 0; r < nb; ++r)
+      while (ptr[r] < end[r] && JA[ptr[r]] / nb == c) {
+        if (FILL) bval[(size_t)slot * nb * nb + r * nb + JA[ptr[r]] % nb] = val[ptr[r]];
+        ++ptr[r];
+      }
+    ++count;
+  }
+  if (!FILL) cnt[I] = count;
+}
+}
+
+extern "C" {
+
+const char* pnpb200_version(void) { return "pnp-b200 0.1 (sm_100a, fp64)"; }
+
+int pnpb200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int pnpb200_create(pnpb200_handle** out, int nv, const double* xyz, int nc, const int* cells, int device)
+{
+  if (!out) return ERROR_INPUT_PAR;
+  *out = nullptr;
+  return guarded([&]() -> int {
+    if (nv < 4 || nc < 1 || !xyz || !cells) throw Error(ERROR_INPUT_PAR, "pnpb200_create: empty mesh");
+    pnpb200_handle* ph = new pnpb200_handle;
+    try {
+      Handle& h = ph->h;
+      init_handle(h, device);
+      cudaStream_t s = h.stream;
+      h.nv = nv; h.nc = nc;
+      h.xyz.alloc(3 * (size_t)nv, s); h.xyz.upload(xyz, 3 * (size_t)nv);
+      h.cells.alloc(4 * (size_t)nc, s); h.cells.upload(cells, 4 * (size_t)nc);
+      const size_t N = 3 * (size_t)nv;
+      h.uu.alloc(N, s); h.uu.zero();
+      h.bcflag.alloc(N, s); h.bcflag.zero();
+      g_launches = 0;
+      build_mesh_tables(h);
+      color_level(*h.hier.lv[0], s);
+      PNP_CUDA(cudaStreamSynchronize(s));
+      h.stats.launches = g_launches;
+    } catch (...) { delete ph; throw; }
+    *out = ph;
+    return FASP_SUCCESS;
+  });
+}
+
+void pnpb200_destroy(pnpb200_handle* ph)
+{
+  delete ph;
+}
+
+void* pnpb200_get_stream(pnpb200_handle* ph) { return ph ? (void*)ph->h.stream : nullptr; }
+
+int pnpb200_set_coefficients(pnpb200_handle* ph, const double* eps, const double* fixed, const double* diff,
+                             const double* val, const double* reac)
+{
+  if (!ph || !eps || !fixed || !diff || !val || !reac) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    const size_t nv = h.nv, N = 3 * nv;
+    h.eps.alloc(nv, s); h.fixed.alloc(nv, s); h.diff.alloc(N, s); h.val.alloc(N, s); h.reac.alloc(N, s);
+    h.eps.upload(eps, nv); h.fixed.upload(fixed, nv); h.diff.upload(diff, N); h.val.upload(val, N); h.reac.upload(reac, N);
+    // Linear_PNP::apply_eafe reads the valency Function's first three dof values (linear_pnp.cpp:220-224)
+    h.q_eafe[0] = 0.0; h.q_eafe[1] = val[1]; h.q_eafe[2] = val[2];
+    compute_k00(h);
+    PNP_CUDA(cudaStreamSynchronize(s));
+    h.have_coef = true;
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_set_dirichlet(pnpb200_handle* ph, int n_bc, const int* bc_dofs)
+{
+  if (!ph || n_bc < 0 || (n_bc > 0 && !bc_dofs)) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    const size_t N = 3 * (size_t)h.nv;
+    std::vector<unsigned char> f(N, 0);
+    for (int i = 0; i < n_bc; ++i) {
+      if (bc_dofs[i] < 0 || (size_t)bc_dofs[i] >= N) throw Error(ERROR_INPUT_PAR, "Dirichlet dof out of range");
+      f[bc_dofs[i]] = 1;
+    }
+    h.bcflag.upload(f.data(), N);
+    PNP_CUDA(cudaStreamSynchronize(s));
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_set_solution(pnpb200_handle* ph, const double* uu)
+{
+  if (!ph || !uu) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaSetDevice(h.device));
+    h.uu.upload(uu, 3 * (size_t)h.nv);
+    PNP_CUDA(cudaStreamSynchronize(h.stream));
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_get_solution(pnpb200_handle* ph, double* uu)
+{
+  if (!ph || !uu) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int { PNP_CUDA(cudaSetDevice(ph->h.device)); ph->h.uu.download(uu, 3 * (size_t)ph->h.nv); return FASP_SUCCESS; });
+}
+
+int pnpb200_set_solution_device(pnpb200_handle* ph, const double* d_uu)
+{
+  if (!ph || !d_uu) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaMemcpyAsync(h.uu.p, d_uu, 3 * (size_t)h.nv * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
+    PNP_CUDA(cudaStreamSynchronize(h.stream));
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_get_solution_device(pnpb200_handle* ph, double* d_uu)
+{
+  if (!ph || !d_uu) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaMemcpyAsync(d_uu, h.uu.p, 3 * (size_t)h.nv * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
+    PNP_CUDA(cudaStreamSynchronize(h.stream));
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_use_eafe(pnpb200_handle* ph, int on) { if (!ph) return ERROR_INPUT_PAR; ph->h.use_eafe = on ? 1 : 0; return FASP_SUCCESS; }
+int pnpb200_num_dofs(const pnpb200_handle* ph) { return ph ? 3 * ph->h.hier.lv[0]->A.n : 0; }
+int pnpb200_num_block_rows(const pnpb200_handle* ph) { return ph ? ph->h.hier.lv[0]->A.n : 0; }
+int pnpb200_num_blocks(const pnpb200_handle* ph) { return ph ? ph->h.hier.lv[0]->A.nnzb : 0; }
+int pnpb200_set_hierarchy_reuse(pnpb200_handle* ph, int reuse) { if (!ph) return ERROR_INPUT_PAR; ph->h.reuse_hierarchy = reuse; if (!reuse) ph->h.hier.symbolic_valid = false; return FASP_SUCCESS; }
+int pnpb200_set_timing_detail(pnpb200_handle* ph, int on) { if (!ph) return ERROR_INPUT_PAR; ph->h.timing_detail = on; return FASP_SUCCESS; }
+
+int pnpb200_assemble(pnpb200_handle* ph)
+{
+  if (!ph) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaSetDevice(h.device));
+    if (h.nv == 0) throw Error(ERROR_INPUT_PAR, "handle has no mesh");
+    g_launches = 0;
+    EventSpan e(h, h.stats.ms_assemble);
+    assemble_system(h);
+    e.stop();
+    h.stats.launches = g_launches;
+    return FASP_SUCCESS;
+  });
+}
+
+static int copy_level_matrix(Handle& h, const BsrT& A, dBSRmat* out)
+{
+  cudaStream_t s = h.stream;
+  out->ROW = out->COL = A.n; out->NNZ = A.nnzb; out->nb = 3; out->storage_manner = 0;
+  out->IA = (INT*)calloc((size_t)A.n + 1, sizeof(INT));
+  out->JA = (INT*)calloc((size_t)A.nnzb, sizeof(INT));
+  out->val = (REAL*)calloc(9 * (size_t)A.nnzb, sizeof(REAL));
+  if (!out->IA || !out->JA || !out->val) throw Error(ERROR_ALLOC_MEM, "host allocation failed");
+  DevBuf<double> tmp; tmp.alloc(9 * (size_t)A.nnzb, s);
+  bsrt_to_fasp(A, tmp.p, s);
+  A.ia.download(out->IA, A.n + 1); A.ja.download(out->JA, A.nnzb);
+  tmp.download(out->val, 9 * (size_t)A.nnzb);
+  return FASP_SUCCESS;
+}
+
+int pnpb200_get_matrix(pnpb200_handle* ph, dBSRmat* out)
+{
+  if (!ph || !out) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int { PNP_CUDA(cudaSetDevice(ph->h.device)); return copy_level_matrix(ph->h, ph->h.hier.lv[0]->A, out); });
+}
+
+int pnpb200_get_rhs(pnpb200_handle* ph, dvector* b)
+{
+  if (!ph || !b || !b->val) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    if (b->row != 3 * h.nv || h.rhs.n < (size_t)b->row) throw Error(ERROR_INPUT_PAR, "rhs size mismatch / not assembled");
+    h.rhs.download(b->val, b->row);
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_residual(pnpb200_handle* ph, double* l2, double* linf)
+{
+  if (!ph) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaSetDevice(h.device));
+    g_launches = 0;
+    double a = 0, b = 0;
+    EventSpan e(h, h.stats.ms_residual);
+    assemble_residual(h, h.rhs, &a, &b);
+    e.stop();
+    h.stats.launches = g_launches;
+    if (l2) *l2 = a;
+    if (linf) *linf = b;
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_solve(pnpb200_handle* ph, const itsolver_param* it, const AMG_param* amg, int* status_its)
+{
+  if (!ph || !it) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaSetDevice(h.device));
+    g_launches = 0;
+    const int rc = solve_current(h, it, amg, status_its);
+    h.stats.launches = g_launches;
+    return rc;
+  });
+}
+
+int pnpb200_get_update(pnpb200_handle* ph, double* du)
+{
+  if (!ph || !du) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int { ph->h.du.download(du, 3 * (size_t)ph->h.hier.lv[0]->A.n); return FASP_SUCCESS; });
+}
+
+int pnpb200_test_solver(pnpb200_handle* ph, const double* target, double* x, const itsolver_param* it,
+                        const AMG_param* amg, int* status_its)
+{
+  if (!ph || !target || !x || !it) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    g_launches = 0;
+    assemble_system(h);                                   // linear_pnp.cpp:137
+    const size_t N = 3 * (size_t)h.nv;
+    DevBuf<double> t; t.alloc(N, s); t.upload(target, N);
+    bsrt_spmv(h.hier.lv[0]->A, t.p, h.rhs.p, s);          // rhs = J * target, linear_pnp.cpp:144
+    int st = 0;
+    solve_current(h, it, amg, &st);
+    if (status_its) *status_its = st;
+    if (st < 0) memcpy(x, target, N * sizeof(double));    // linear_pnp.cpp:158-162
+    else h.du.download(x, N);
+    h.stats.launches = g_launches;
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_newton_step(pnpb200_handle* ph, const itsolver_param* it, const AMG_param* amg, int* krylov_status,
+                        double* l2, double* linf)
+{
+  if (!ph || !it) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    g_launches = 0;
+    { EventSpan e(h, h.stats.ms_assemble); assemble_system(h); e.stop(); }
+    int st = 0;
+    solve_current(h, it, amg, &st);
+    if (krylov_status) *krylov_status = st;
+    const size_t N = 3 * (size_t)h.nv;
+    if (st >= 0) vec_axpy(1.0, h.du.p, h.uu.p, N, s);     // linear_pnp.cpp:109-127
+    double a = 0, b = 0;
+    { EventSpan e(h, h.stats.ms_residual); assemble_residual(h, h.rhs, &a, &b); e.stop(); }
+    if (l2) *l2 = a;
+    if (linf) *linf = b;
+    h.stats.launches = g_launches;
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_get_stats(const pnpb200_handle* ph, pnpb200_stats* st)
+{
+  if (!ph || !st) return ERROR_INPUT_PAR;
+  const Handle& h = ph->h;
+  memset(st, 0, sizeof(*st));
+  st->n_levels = (int)h.hier.lv.size();
+  for (int l = 0; l < st->n_levels && l < 32; ++l) {
+    st->level_rows[l] = h.hier.lv[l]->A.n; st->level_nnzb[l] = h.hier.lv[l]->A.nnzb; st->level_colors[l] = h.hier.lv[l]->ncolors;
+  }
+  st->krylov_its = h.stats.krylov_its; st->launches = (int)h.stats.launches;
+  st->ms_assemble = h.stats.ms_assemble; st->ms_setup = h.stats.ms_setup; st->ms_krylov = h.stats.ms_krylov;
+  st->ms_residual = h.stats.ms_residual; st->ms_spmv = h.stats.ms_spmv; st->ms_vcycle = h.stats.ms_vcycle;
+  st->ms_ortho = h.stats.ms_ortho;
+  return FASP_SUCCESS;
+}
+
+int pnpb200_get_level_matrix(pnpb200_handle* ph, int level, dBSRmat* out)
+{
+  if (!ph || !out || level < 0 || level >= (int)ph->h.hier.lv.size()) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int { return copy_level_matrix(ph->h, ph->h.hier.lv[level]->A, out); });
+}
+
+int pnpb200_get_level_aggregates(pnpb200_handle* ph, int level, int* agg, int* n_agg)
+{
+  if (!ph || !agg || level < 0 || level + 1 >= (int)ph->h.hier.lv.size()) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Level& L = *ph->h.hier.lv[level];
+    L.agg.download(agg, L.A.n);
+    if (n_agg) *n_agg = L.nagg;
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_get_level_order(pnpb200_handle* ph, int level, int* order)
+{
+  if (!ph || !order || level < 0 || level >= (int)ph->h.hier.lv.size()) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Level& L = *ph->h.hier.lv[level];
+    if (L.ncolors == 0) throw Error(ERROR_INPUT_PAR, "level not coloured yet");
+    L.color_rows.download(order, L.A.n);
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_apply_vcycle(pnpb200_handle* ph, const double* r, double* z)
+{
+  if (!ph || !r || !z) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    if (!h.hier.symbolic_valid) throw Error(ERROR_INPUT_PAR, "no hierarchy: call pnpb200_solve first");
+    const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
+    DevBuf<double> dr, dz; dr.alloc(N, s); dz.alloc(N, s);
+    dr.upload(r, N);
+    SolverConfig cfg;                       // V(1,1)
+    amg_vcycle(h, cfg, dr.p, dz.p);
+    dz.download(z, N);
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_apply_matrix(pnpb200_handle* ph, const double* x, double* y)
+{
+  if (!ph || !x || !y) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
+    DevBuf<double> dx, dy; dx.alloc(N, s); dy.alloc(N, s);
+    dx.upload(x, N);
+    bsrt_spmv(h.hier.lv[0]->A, dx.p, dy.p, s);
+    dy.download(y, N);
+    return FASP_SUCCESS;
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// FASP-compatible solver entry points (host structs in, GPU solve, host vector out)
+// ---------------------------------------------------------------------------------------------
+static INT solve_host_bsr(dBSRmat* A, dvector* b, dvector* x, itsolver_param* it, AMG_param* amg)
+{
+  if (!A || !b || !x || !it || !b->val || !x->val) return ERROR_INPUT_PAR;
+  int status = ERROR_UNKNOWN;
+  const int rc = guarded([&]() -> int {
+    if (b->row != 3 * A->ROW || x->row != 3 * A->ROW) throw Error(ERROR_INPUT_PAR, "vector / matrix size mismatch");
+    HostSystem sys(A);
+    Handle& h = sys.ph->h; cudaStream_t s = h.stream;
+    const size_t N = (size_t)b->row;
+    const SolverConfig cfg = make_config(it, amg);
+    h.rhs.alloc(N, s); h.rhs.upload(b->val, N);
+    h.du.alloc(N, s); h.du.upload(x->val, N);          // x is the initial guess
+    if (cfg.use_amg) amg_setup(h, cfg);
+    status = fgmres_solve(h, cfg, h.rhs.p, h.du.p);
+    h.du.download(x->val, N);                           // last iterate even on failure
+    return FASP_SUCCESS;
+  });
+  return rc < 0 ? rc : status;
+}
+
+INT fasp_solver_dbsr_krylov_amg(dBSRmat* A, dvector* b, dvector* x, itsolver_param* it, AMG_param* amg)
+{
+  if (!amg) return ERROR_INPUT_PAR;
+  return solve_host_bsr(A, b, x, it, amg);
+}
+
+INT fasp_solver_dbsr_krylov_ilu(dBSRmat* A, dvector* b, dvector* x, itsolver_param* it, ILU_param* ilu)
+{
+  (void)ilu;                      // "next" tier: block-ILU(k) not built; AMG with bsr.dat defaults instead
+  AMG_param amg;
+  fasp_param_amg_init(&amg);
+  return solve_host_bsr(A, b, x, it, &amg);
+}
+
+void fasp_blas_dbsr_aAxpy(const REAL alpha, const dBSRmat* A, const REAL* x, REAL* y)
+{
+  guarded([&]() -> int {
+    HostSystem sys(A);
+    Handle& h = sys.ph->h; cudaStream_t s = h.stream;
+    const size_t N = 3 * (size_t)A->ROW;
+    DevBuf<double> dx, dy, dz; dx.alloc(N, s); dy.alloc(N, s); dz.alloc(N, s);
+    dx.upload(x, N); dy.upload(y, N);
+    bsrt_spmv(h.hier.lv[0]->A, dx.p, dz.p, s);
+    vec_axpy(alpha, dz.p, dy.p, N, s);
+    dy.download(y, N);
+    return 0;
+  });
+}
+
+void fasp_blas_dbsr_mxv(const dBSRmat* A, const REAL* x, REAL* y)
+{
+  guarded([&]() -> int {
+    HostSystem sys(A);
+    Handle& h = sys.ph->h; cudaStream_t s = h.stream;
+    const size_t N = 3 * (size_t)A->ROW;
+    DevBuf<double> dx, dy; dx.alloc(N, s); dy.alloc(N, s);
+    dx.upload(x, N);
+    bsrt_spmv(h.hier.lv[0]->A, dx.p, dy.p, s);
+    dy.download(y, N);
+    return 0;
+  });
+}
+
+dBSRmat fasp_format_dcsr_dbsr(const dCSRmat* A, const INT nb)
+{
+  dBSRmat B; memset(&B, 0, sizeof(B));
+  guarded([&]() -> int {
+    if (!A || nb < 1 || nb > 8 || A->row % nb != 0 || A->col % nb != 0) throw Error(ERROR_INPUT_PAR, "fasp_format_dcsr_dbsr: bad size");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error(ERROR_DEVICE, "no CUDA device");
+    cudaStream_t s; PNP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    const int n = A->row, nbrow = n / nb;
+    const int nnz = A->IA[n] - A->IA[0];
+    {
+      DevBuf<int> IA, JA, cnt, bIA, bJA, err; DevBuf<double> val, bval;
+      IA.alloc(n + 1, s); JA.alloc(nnz, s); val.alloc(nnz, s); cnt.alloc(nbrow + 1, s); bIA.alloc(nbrow + 1, s); err.alloc(1, s);
+      IA.upload(A->IA, n + 1); JA.upload(A->JA, nnz); val.upload(A->val, nnz); cnt.zero(); err.zero();
+      csr2bsr_kernel<false><<<cdiv(nbrow, 128), 128, 0, s>>>(nbrow, nb, IA.p, JA.p, val.p, cnt.p, nullptr, nullptr, nullptr, err.p);
+      exclusive_scan_int(cnt.p, bIA.p, nbrow + 1, s);
+      B.IA = (INT*)calloc((size_t)nbrow + 1, sizeof(INT));
+      bIA.download(B.IA, nbrow + 1);
+      int herr = 0; err.download(&herr, 1);
+      if (herr) { free(B.IA); B.IA = nullptr; throw Error(ERROR_DATA_STRUCTURE, "fasp_format_dcsr_dbsr: CSR rows must have ascending columns"); }
+      const int NNZ = B.IA[nbrow];
+      bJA.alloc(NNZ, s); bval.alloc((size_t)NNZ * nb * nb, s); bval.zero();
+      csr2bsr_kernel<true><<<cdiv(nbrow, 128), 128, 0, s>>>(nbrow, nb, IA.p, JA.p, val.p, nullptr, bIA.p, bJA.p, bval.p, err.p);
+      B.JA = (INT*)calloc((size_t)NNZ, sizeof(INT));
+      B.val = (REAL*)calloc((size_t)NNZ * nb * nb, sizeof(REAL));
+      bJA.download(B.JA, NNZ); bval.download(B.val, (size_t)NNZ * nb * nb);
+      B.ROW = nbrow; B.COL = A->col / nb; B.NNZ = NNZ; B.nb = nb; B.storage_manner = 0;
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    return 0;
+  });
+  return B;
+}
+
+// scalar CSR Krylov (tests/eafe_tests/test_eafe.cpp:170): pad to BSR(3)? No — treat each scalar row as
+// a 1x1 system is outside the nb=3 kernels; the entry converts CSR (n % 3 == 0) to BSR(3) on the device.
+INT fasp_solver_dcsr_krylov(dCSRmat* A, dvector* b, dvector* x, itsolver_param* it)
+{
+  if (!A || A->row % 3 != 0) return ERROR_INPUT_PAR;
+  dBSRmat B = fasp_format_dcsr_dbsr(A, 3);
+  if (!B.IA) return ERROR_DATA_STRUCTURE;
+  const INT st = solve_host_bsr(&B, b, x, it, nullptr);
+  fasp_dbsr_free(&B);
+  return st;
+}
+
+// ---- multi-GPU bootstrap: implemented in comm.cu -----------------------------------------------
+
+}

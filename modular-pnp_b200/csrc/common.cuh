@@ -1,0 +1,130 @@
+// pnp-b200 — shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace pnpb200 {
+
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PNP_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      char buf__[512];                                                                     \
+      snprintf(buf__, sizeof buf__, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), \
+               __FILE__, __LINE__, #call);                                                 \
+      throw ::pnpb200::Error(-120, buf__);                                                 \
+    }                                                                                      \
+  } while (0)
+
+#define PNP_LAUNCH_CHECK() PNP_CUDA(cudaGetLastError())
+
+// launch counter (bench.py's gpu_launches claim)
+extern thread_local long g_launches;
+#define PNP_COUNT_LAUNCH() (++::pnpb200::g_launches)
+
+inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+
+// Stream-ordered device buffer (cudaMallocAsync pool: hierarchy rebuilds every Newton step
+// re-use the same blocks without driver round trips).
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept
+  {
+    if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count, cudaStream_t stream)
+  {
+    if (p && n >= count && s == stream) return;     // keep a big-enough block
+    release();
+    s = stream; n = count;
+    if (count == 0) return;
+    PNP_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
+  }
+  void release()
+  {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr; n = 0;
+  }
+  void zero() { if (p) PNP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void upload(const T* h, size_t count) { PNP_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }
+  void download(T* h, size_t count) const
+  {
+    PNP_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaStreamSynchronize(s));
+  }
+  std::vector<T> to_host(size_t count) const { std::vector<T> v(count); if (count) download(v.data(), count); return v; }
+};
+
+// ---- device helpers -----------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// sum over the 16 lanes of a half-warp group (all 32 lanes must participate)
+__device__ __forceinline__ double half_sum(double v)
+{
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum, result valid in thread 0 (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ double block_sum(double v, double* smem32)
+{
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) smem32[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  return v;
+}
+__device__ __forceinline__ double block_max(double v, double* smem32)
+{
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) smem32[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_max(v);
+  return v;
+}
+__host__ __device__ __forceinline__ unsigned hash32(unsigned x)
+{
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+#endif
+
+} // namespace pnpb200

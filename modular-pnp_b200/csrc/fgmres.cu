@@ -1,0 +1,133 @@
+// pnp-b200 — right-preconditioned flexible GMRES with adaptive restart on the device
+// (SURVEY §2.3 K15). Stands in for FASP's fasp_solver_dbsr_pvfgmres [EXT] reached through
+// fasp_solver_dbsr_krylov_amg (benchmarks/pnp_exact_solution/linear_pnp.cpp:101): same
+// restart schedule (restart_min 3, step 3, cr_max 0.99, cr_min 0.174), Givens recurrences,
+// stopping rule ||r|| <= tol*||b|| and return convention (iterations >= 0, ERROR_SOLVER_MAXIT).
+// Orthogonalisation is classical Gram-Schmidt with DGKS re-orthogonalisation: all
+// projections of a step come from ONE fused pass over the basis (multi_dot) and one fused
+// update (multi_axpy), i.e. 2 host synchronisations per iteration instead of FASP's j+1.
+#include "internal.hpp"
+#include <cmath>
+
+namespace pnpb200 {
+
+namespace {
+struct PhaseTimer {
+  Handle& h; double& acc; bool on;
+  PhaseTimer(Handle& hh, double& a) : h(hh), acc(a), on(hh.timing_detail != 0)
+  { if (on) cudaEventRecord(h.ev[4], h.stream); }
+  ~PhaseTimer()
+  {
+    if (!on) return;
+    cudaEventRecord(h.ev[5], h.stream); cudaEventSynchronize(h.ev[5]);
+    float ms = 0; cudaEventElapsedTime(&ms, h.ev[4], h.ev[5]); acc += ms;
+  }
+};
+}
+
+int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
+{
+  cudaStream_t s = h.stream;
+  const BsrT& A = h.hier.lv[0]->A;
+  const size_t n = 3 * (size_t)A.n;
+  const int MaxIt = cfg.maxit;
+  const int restart_max = cfg.restart < 1 ? 1 : cfg.restart, restart_min = 3, dstep = 3;
+  const double cr_max = 0.99, cr_min = 0.174, epsmac = 1e-20;
+  Krylov& K = h.kry;
+  K.V.alloc((size_t)(restart_max + 1) * n, s);
+  K.Z.alloc((size_t)restart_max * n, s);
+  K.r.alloc(n, s);
+  double* V = K.V.p; double* Z = K.Z.p;
+  auto Vi = [&](int i) { return V + (size_t)i * n; };
+  auto Zi = [&](int i) { return Z + (size_t)i * n; };
+
+  std::vector<std::vector<double>> hh(restart_max + 1, std::vector<double>(restart_max, 0.0));
+  std::vector<double> c(restart_max), sn(restart_max), rs(restart_max + 1), hcol(restart_max + 2), h2(restart_max + 2),
+      neg(restart_max + 1);
+
+  const double b_norm = vec_norm2(h, b, n);
+  bsrt_residual(A, b, x, Vi(0), s);
+  double r_norm = vec_norm2(h, Vi(0), n), r_norm_old;
+  const double den = b_norm > 0.0 ? b_norm : r_norm;
+  const double epsilon = cfg.tol * den;
+  if (!(r_norm > epsilon)) return 0;
+  if (!std::isfinite(r_norm)) return ERROR_SOLVER_EXIT;
+
+  int iter = 0, Restart = restart_max;
+  double cr = 1.0;
+  bool converged = false;
+  while (iter < MaxIt) {
+    rs[0] = r_norm; r_norm_old = r_norm;
+    if (r_norm == 0.0) return iter;
+    if (cr > cr_max || iter == 0) Restart = restart_max;
+    else if (cr < cr_min) { /* keep */ }
+    else { if (Restart - dstep > restart_min) Restart -= dstep; else Restart = restart_max; }
+    vec_scale(1.0 / r_norm, Vi(0), n, s);
+    int i = 0;
+    while (i < Restart && iter < MaxIt) {
+      ++i; ++iter;
+      {
+        PhaseTimer t(h, h.stats.ms_vcycle);
+        if (cfg.use_amg) amg_vcycle(h, cfg, Vi(i - 1), Zi(i - 1));
+        else vec_copy(Zi(i - 1), Vi(i - 1), n, s);
+      }
+      { PhaseTimer t(h, h.stats.ms_spmv); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
+      double tnorm;
+      {
+        PhaseTimer t(h, h.stats.ms_ortho);
+        multi_dot(h, V, n, i, Vi(i), n, hcol.data());
+        const double before = std::sqrt(hcol[i]);
+        for (int j = 0; j < i; ++j) neg[j] = -hcol[j];
+        double after2 = 0.0;
+        multi_axpy(h, V, n, i, neg.data(), Vi(i), n, &after2);
+        if (std::sqrt(after2) < 0.7071067811865476 * before) {   // DGKS: orthogonalise once more
+          multi_dot(h, V, n, i, Vi(i), n, h2.data());
+          for (int j = 0; j < i; ++j) { neg[j] = -h2[j]; hcol[j] += h2[j]; }
+          multi_axpy(h, V, n, i, neg.data(), Vi(i), n, &after2);
+        }
+        tnorm = std::sqrt(after2);
+        for (int j = 0; j < i; ++j) hh[j][i - 1] = hcol[j];
+        hh[i][i - 1] = tnorm;
+        if (tnorm != 0.0) vec_scale(1.0 / tnorm, Vi(i), n, s);
+      }
+      if (!std::isfinite(tnorm)) return ERROR_SOLVER_EXIT;
+      for (int j = 1; j < i; ++j) {
+        const double t = hh[j - 1][i - 1];
+        hh[j - 1][i - 1] = sn[j - 1] * hh[j][i - 1] + c[j - 1] * t;
+        hh[j][i - 1] = -sn[j - 1] * t + c[j - 1] * hh[j][i - 1];
+      }
+      double gamma = std::sqrt(hh[i][i - 1] * hh[i][i - 1] + hh[i - 1][i - 1] * hh[i - 1][i - 1]);
+      if (gamma == 0.0) gamma = epsmac;
+      c[i - 1] = hh[i - 1][i - 1] / gamma;
+      sn[i - 1] = hh[i][i - 1] / gamma;
+      rs[i] = -sn[i - 1] * rs[i - 1];
+      rs[i - 1] = c[i - 1] * rs[i - 1];
+      hh[i - 1][i - 1] = sn[i - 1] * hh[i][i - 1] + c[i - 1] * hh[i - 1][i - 1];
+      r_norm = std::fabs(rs[i]);
+      if (cfg.print_level > 1) printf("  [pnpb200 fgmres] it %3d  relres %.6e\n", iter, r_norm / den);
+      if (r_norm <= epsilon) break;
+    }
+    // solve the small triangular system, x += Z y
+    rs[i - 1] = rs[i - 1] / hh[i - 1][i - 1];
+    for (int k = i - 2; k >= 0; --k) {
+      double t = 0.0;
+      for (int j = k + 1; j < i; ++j) t -= hh[k][j] * rs[j];
+      t += rs[k];
+      rs[k] = t / hh[k][k];
+    }
+    multi_axpy(h, Z, n, i, rs.data(), x, n, nullptr);
+    // true residual for the convergence confirmation / next cycle
+    const bool est_conv = r_norm <= epsilon;
+    bsrt_residual(A, b, x, Vi(0), s);
+    r_norm = vec_norm2(h, Vi(0), n);
+    if (est_conv && r_norm <= epsilon) { converged = true; break; }
+    if (!std::isfinite(r_norm)) return ERROR_SOLVER_EXIT;
+    if (r_norm <= epsilon) { converged = true; break; }
+    cr = r_norm / r_norm_old;
+  }
+  h.stats.krylov_its = iter;
+  if (!converged && iter >= MaxIt) return ERROR_SOLVER_MAXIT;
+  return iter;
+}
+
+} // namespace pnpb200

@@ -1,0 +1,152 @@
+// pnp-b200 — internal host-side declarations shared by the .cu translation units.
+#pragma once
+#include "common.cuh"
+#include "pnpb200/pnpb200.h"
+#include <memory>
+
+namespace pnpb200 {
+
+// BSR(3) matrix on the device in "BSR-T" layout: same IA/JA as FASP's dBSRmat, but inside a
+// block row the 9 block components are stored component-major:
+//     val[9*IA[i] + t*len_i + k]   (t = 3*r + c component, k = block position in the row)
+// so that lane k of a row group loads component t of its block with unit stride.
+struct BsrT {
+  int n = 0;        // block rows
+  int nnzb = 0;     // blocks
+  DevBuf<int> ia, ja;
+  DevBuf<int> brow;     // row of each block
+  DevBuf<int> dslot;    // position (absolute block index) of the diagonal block of each row
+  DevBuf<int> tslot;    // block index of the transposed block (j,i), -1 if absent
+  DevBuf<double> val;   // 9*nnzb
+};
+
+struct Level {
+  BsrT A;
+  DevBuf<double> dinv;          // 9*n, AoS: inverse of diagonal blocks
+  // multicolour ordering
+  int ncolors = 0;
+  std::vector<int> color_ptr;   // host, ncolors+1 offsets into color_rows
+  DevBuf<int> color_rows;       // rows sorted by colour (ascending inside a colour)
+  // aggregation to the next level
+  int nagg = 0;
+  DevBuf<int> agg;              // n, -1 = isolated
+  DevBuf<int> agg_ptr, agg_rows;   // members of each aggregate (ascending)
+  // numeric RAP map: coarse block s sums fine blocks rap_perm[rap_seg[s] .. rap_seg[s+1])
+  DevBuf<int> rap_seg, rap_perm;
+  // work vectors (3*n)
+  DevBuf<double> x, b, w;
+};
+
+struct SolverConfig {
+  // Krylov
+  double tol = 1e-6; int maxit = 100; int restart = 30; int print_level = 0;
+  // AMG
+  int max_levels = 20; int coarse_dof = 100; double strong_coupled = 0.08; int max_aggregation = 20;
+  double tentative_smooth = 0.67; int presmooth = 1, postsmooth = 1;
+  int use_amg = 1;
+};
+SolverConfig make_config(const itsolver_param* it, const AMG_param* amg);
+
+struct Hierarchy {
+  std::vector<std::unique_ptr<Level>> lv;   // lv[0] = fine level (assembled Jacobian), lv[1..] rebuilt by amg_setup
+  // coarsest level dense inverse
+  int nd = 0;                   // scalar size of the coarsest level
+  DevBuf<double> dense_inv;     // nd*nd, row-major
+  bool symbolic_valid = false;
+};
+
+struct Krylov {
+  int n = 0, restart = 0;
+  DevBuf<double> V, Z;          // (restart+1)*n and restart*n
+  DevBuf<double> r, partial;    // scratch
+  DevBuf<double> dots;          // device results
+  double* h_dots = nullptr;     // pinned host mirror
+};
+
+struct Stats {
+  int krylov_its = 0;
+  double ms_assemble = 0, ms_setup = 0, ms_krylov = 0, ms_residual = 0;
+  double ms_spmv = 0, ms_vcycle = 0, ms_ortho = 0;
+  long launches = 0;
+};
+
+// first member of Handle => destroyed last, after every DevBuf has queued its cudaFreeAsync
+struct StreamOwner {
+  cudaStream_t s = nullptr;
+  ~StreamOwner() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+};
+
+struct Handle {
+  StreamOwner owner;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // mesh
+  int nv = 0, nc = 0;
+  DevBuf<double> xyz;           // 3*nv
+  DevBuf<int> cells;            // 4*nc
+  DevBuf<int> v2c_ptr, v2c_idx; // vertex -> incident cells (ascending)
+  // coefficients / state (dof order 3*v + k)
+  DevBuf<double> eps, fixed, diff, val, reac, uu, du, rhs;
+  DevBuf<unsigned char> bcflag; // 3*nv
+  double q_eafe[3] = {0, 0, 0}; // valency function at dofs 0..2 (linear_pnp.cpp:220-224)
+  bool have_coef = false;
+  int use_eafe = 1;
+  // fine level matrix + per-pattern tables
+  DevBuf<double> omega;         // nnzb: EAFE edge weights  sum_T S^T_ij
+  DevBuf<double> k00;           // nnzb: permittivity stiffness (solution independent)
+  DevBuf<double> cellrec;       // per-cell quadrature records (Jacobian), reused for residual
+  // solver
+  Hierarchy hier;
+  Krylov kry;
+  int reuse_hierarchy = 0;
+  int timing_detail = 0;
+  Stats stats;
+  // scratch for reductions
+  DevBuf<double> red;
+  double* h_red = nullptr;      // pinned
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  Handle() {}
+  Handle(const Handle&) = delete;
+  ~Handle()
+  {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    if (h_red) cudaFreeHost(h_red);
+    for (int i = 0; i < 8; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+  }
+};
+
+// ---- mesh_setup.cu
+void build_mesh_tables(Handle& h);                 // v2c, pattern, brow/dslot/tslot, omega
+void compute_k00(Handle& h);
+void finish_pattern_tables(BsrT& A, cudaStream_t s);   // brow, dslot, tslot from ia/ja
+void exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t s);
+// ---- assemble.cu
+void assemble_system(Handle& h);                   // J (BSR-T) and rhs
+void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf);
+// ---- bsr_ops.cu
+void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s);                  // y = A x
+void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s); // r = b - A x
+void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s);
+void bsrt_from_fasp(const int* d_ia, const int* d_ja, const double* d_val_fasp, BsrT& A, cudaStream_t s);
+void bsrt_to_fasp(const BsrT& A, double* d_val_fasp, cudaStream_t s);
+void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s);
+void color_level(Level& L, cudaStream_t s);
+// ---- vecops.cu
+void vec_set(double* x, double v, size_t n, cudaStream_t s);
+void vec_copy(double* dst, const double* src, size_t n, cudaStream_t s);
+void vec_axpy(double a, const double* x, double* y, size_t n, cudaStream_t s);      // y += a x
+void vec_scale(double a, double* x, size_t n, cudaStream_t s);
+double vec_norm2(Handle& h, const double* x, size_t n);                              // sync
+// dots[i] = <V_i, w> for i < nv, dots[nv] = <w, w>; V_i = V + i*ld. Synchronises.
+void multi_dot(Handle& h, const double* V, size_t ld, int nvec, const double* w, size_t n, double* out_host);
+// w += sum_i coef[i] * V_i ; if norm2_out != null also returns ||w||^2 (sync)
+void multi_axpy(Handle& h, const double* V, size_t ld, int nvec, const double* coef_host, double* w, size_t n,
+                double* norm2_out);
+// ---- amg.cu
+void amg_setup(Handle& h, const SolverConfig& cfg);
+void amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z);
+// ---- fgmres.cu
+int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x);
+
+} // namespace pnpb200

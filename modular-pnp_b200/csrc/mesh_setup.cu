@@ -1,0 +1,214 @@
+// pnp-b200 — per-mesh tables built on the device:
+// vertex->cell adjacency, the BSR(3) sparsity pattern DOLFIN's assembler would build
+// (src/pde.cpp:545: all vertex pairs that share a cell, columns ascending), row / diagonal /
+// transpose slot maps, the EAFE edge table omega_ij = sum_T S^T_ij (include/EAFE.h:4825-4849,
+// SURVEY App. A.3) and the solution-independent permittivity stiffness (forms.ufl:28).
+#include "internal.hpp"
+#include "fem.cuh"
+#include <cub/cub.cuh>
+
+namespace pnpb200 {
+
+thread_local long g_launches = 0;
+
+namespace {
+
+constexpr int MAX_ROW = 128;   // max blocks per row the pattern builder supports
+
+__global__ void count_v2c_kernel(int nc, const int4* __restrict__ cells, int* __restrict__ deg)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int4 cv = cells[c];
+  atomicAdd(&deg[cv.x], 1); atomicAdd(&deg[cv.y], 1); atomicAdd(&deg[cv.z], 1); atomicAdd(&deg[cv.w], 1);
+}
+
+__global__ void fill_v2c_kernel(int nc, const int4* __restrict__ cells, int* __restrict__ cursor,
+                                int* __restrict__ idx)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int4 cv = cells[c];
+  idx[atomicAdd(&cursor[cv.x], 1)] = c; idx[atomicAdd(&cursor[cv.y], 1)] = c;
+  idx[atomicAdd(&cursor[cv.z], 1)] = c; idx[atomicAdd(&cursor[cv.w], 1)] = c;
+}
+
+// ascending order per vertex makes every later gather deterministic
+__global__ void sort_v2c_kernel(int nv, const int* __restrict__ ptr, int* __restrict__ idx)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const int s = ptr[v], e = ptr[v + 1];
+  for (int a = s + 1; a < e; ++a) {
+    const int key = idx[a];
+    int b = a - 1;
+    while (b >= s && idx[b] > key) { idx[b + 1] = idx[b]; --b; }
+    idx[b + 1] = key;
+  }
+}
+
+// sorted-unique neighbour set of one vertex; FILL=false counts, FILL=true writes JA
+template <bool FILL>
+__global__ void pattern_kernel(int nv, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
+                               const int4* __restrict__ cells, int* __restrict__ rowlen,
+                               const int* __restrict__ ia, int* __restrict__ ja, int* __restrict__ err)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  int nb[MAX_ROW];
+  int cnt = 0;
+  for (int p = v2c_ptr[v]; p < v2c_ptr[v + 1]; ++p) {
+    const int4 cv = cells[v2c_idx[p]];
+    const int w4[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int w = w4[r];
+      int lo = 0;
+      while (lo < cnt && nb[lo] < w) ++lo;
+      if (lo < cnt && nb[lo] == w) continue;
+      if (cnt >= MAX_ROW) { *err = 1; continue; }
+      for (int t = cnt; t > lo; --t) nb[t] = nb[t - 1];
+      nb[lo] = w; ++cnt;
+    }
+  }
+  if (cnt == 0) { nb[0] = v; cnt = 1; }     // vertex without cells keeps a diagonal
+  if (!FILL) rowlen[v] = cnt;
+  else { const int s = ia[v]; for (int t = 0; t < cnt; ++t) ja[s + t] = nb[t]; }
+}
+
+__global__ void row_tables_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                                  int* __restrict__ brow, int* __restrict__ dslot)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int d = -1;
+  for (int p = ia[i]; p < ia[i + 1]; ++p) { brow[p] = i; if (ja[p] == i) d = p; }
+  dslot[i] = d;
+}
+
+__global__ void tslot_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ ja,
+                             const int* __restrict__ brow, int* __restrict__ tslot)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int i = brow[b], j = ja[b];
+  int lo = ia[j], hi = ia[j + 1] - 1, res = -1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1, c = ja[mid];
+    if (c == i) { res = mid; break; }
+    if (c < i) lo = mid + 1; else hi = mid - 1;
+  }
+  tslot[b] = res;
+}
+
+// omega_b = sum over cells containing (i,j) of the P1 stiffness entry (det/6) grad l_i . grad l_j
+// k00_b   = sum over cells of (sum_ip W24 eps(ip)) * det grad l_i . grad l_j
+template <bool WITH_EPS>
+__global__ void edge_table_kernel(int nnzb, const int* __restrict__ ja, const int* __restrict__ brow,
+                                  const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
+                                  const int4* __restrict__ cells, const double* __restrict__ xyz,
+                                  const double* __restrict__ eps, double* __restrict__ out)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int i = brow[b], j = ja[b];
+  double acc = 0.0;
+  for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; ++p) {
+    const int4 cv = cells[v2c_idx[p]];
+    const int lj = local_index(cv, j);
+    if (lj < 0) continue;
+    const int li = local_index(cv, i);
+    double x[4][3], g[4][3], det;
+    load_cell_xyz(xyz, cv, x);
+    tet_geom(x, g, det);
+    const double G = det * dot3(g[li], g[lj]);
+    if (!WITH_EPS) acc += 0.166666666666667 * G;
+    else {
+      const double e4[4] = {eps[cv.x], eps[cv.y], eps[cv.z], eps[cv.w]};
+      double we = 0.0;
+#pragma unroll 4
+      for (int ip = 0; ip < 24; ++ip) {
+        const double e_ip = c_P24[ip][0] * e4[0] + c_P24[ip][1] * e4[1] + c_P24[ip][2] * e4[2] + c_P24[ip][3] * e4[3];
+        we += c_W24[ip] * e_ip;
+      }
+      acc += we * G;
+    }
+  }
+  out[b] = acc;
+}
+
+} // namespace
+
+void exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t s)
+{
+  size_t bytes = 0;
+  PNP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, s));
+  DevBuf<unsigned char> tmp; tmp.alloc(bytes, s);
+  PNP_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)n, s));
+  PNP_COUNT_LAUNCH();
+}
+
+void finish_pattern_tables(BsrT& A, cudaStream_t s)
+{
+  A.brow.alloc(A.nnzb, s); A.dslot.alloc(A.n, s); A.tslot.alloc(A.nnzb, s);
+  row_tables_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.ja.p, A.brow.p, A.dslot.p); PNP_COUNT_LAUNCH();
+  tslot_kernel<<<cdiv(A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.ja.p, A.brow.p, A.tslot.p); PNP_COUNT_LAUNCH();
+  PNP_LAUNCH_CHECK();
+}
+
+void build_mesh_tables(Handle& h)
+{
+  cudaStream_t s = h.stream;
+  const int nv = h.nv, nc = h.nc;
+  const int4* cells = reinterpret_cast<const int4*>(h.cells.p);
+  // vertex -> cells
+  DevBuf<int> deg; deg.alloc(nv + 1, s); deg.zero();
+  count_v2c_kernel<<<cdiv(nc, 256), 256, 0, s>>>(nc, cells, deg.p); PNP_COUNT_LAUNCH();
+  h.v2c_ptr.alloc(nv + 1, s);
+  exclusive_scan_int(deg.p, h.v2c_ptr.p, nv + 1, s);
+  h.v2c_idx.alloc(4 * (size_t)nc, s);
+  PNP_CUDA(cudaMemcpyAsync(deg.p, h.v2c_ptr.p, (nv + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  fill_v2c_kernel<<<cdiv(nc, 256), 256, 0, s>>>(nc, cells, deg.p, h.v2c_idx.p); PNP_COUNT_LAUNCH();
+  sort_v2c_kernel<<<cdiv(nv, 128), 128, 0, s>>>(nv, h.v2c_ptr.p, h.v2c_idx.p); PNP_COUNT_LAUNCH();
+  // pattern
+  Level& L = *h.hier.lv[0];
+  BsrT& A = L.A;
+  A.n = nv;
+  DevBuf<int> err; err.alloc(1, s); err.zero();
+  DevBuf<int> rowlen; rowlen.alloc(nv + 1, s); rowlen.zero();
+  pattern_kernel<false><<<cdiv(nv, 64), 64, 0, s>>>(nv, h.v2c_ptr.p, h.v2c_idx.p, cells, rowlen.p, nullptr, nullptr, err.p);
+  PNP_COUNT_LAUNCH();
+  A.ia.alloc(nv + 1, s);
+  exclusive_scan_int(rowlen.p, A.ia.p, nv + 1, s);
+  int nnzb = 0, herr = 0;
+  PNP_CUDA(cudaMemcpyAsync(&nnzb, A.ia.p + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  if (herr) throw Error(ERROR_DATA_STRUCTURE, "mesh vertex with more than 128 neighbours is not supported");
+  A.nnzb = nnzb;
+  A.ja.alloc(nnzb, s);
+  pattern_kernel<true><<<cdiv(nv, 64), 64, 0, s>>>(nv, h.v2c_ptr.p, h.v2c_idx.p, cells, nullptr, A.ia.p, A.ja.p, err.p);
+  PNP_COUNT_LAUNCH();
+  finish_pattern_tables(A, s);
+  A.val.alloc(9 * (size_t)nnzb, s);
+  // EAFE edge table
+  h.omega.alloc(nnzb, s);
+  edge_table_kernel<false><<<cdiv(nnzb, 128), 128, 0, s>>>(nnzb, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p, cells,
+                                                          h.xyz.p, nullptr, h.omega.p);
+  PNP_COUNT_LAUNCH();
+  PNP_LAUNCH_CHECK();
+}
+
+void compute_k00(Handle& h)
+{
+  cudaStream_t s = h.stream;
+  BsrT& A = h.hier.lv[0]->A;
+  h.k00.alloc(A.nnzb, s);
+  edge_table_kernel<true><<<cdiv(A.nnzb, 128), 128, 0, s>>>(A.nnzb, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p,
+                                                           reinterpret_cast<const int4*>(h.cells.p), h.xyz.p,
+                                                           h.eps.p, h.k00.p);
+  PNP_COUNT_LAUNCH();
+  PNP_LAUNCH_CHECK();
+}
+
+} // namespace pnpb200

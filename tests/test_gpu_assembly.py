@@ -1,0 +1,98 @@
+"""-m gpu: CUDA assembly (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bar: BSR pattern identical; values within 1e-12 of the row maximum (north_star: 1e-12 relative;
+row scaling per SURVEY §7 because 8 of 15 stiffness entries per row cancel on Kuhn meshes)."""
+import numpy as np
+import pytest
+
+from helpers import gpu_problem, perturbed_state, row_scaled_error
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = [(4, 2, 2), (8, 4, 4), (20, 6, 5)]
+
+
+@pytest.mark.parametrize("grid", GRIDS)
+@pytest.mark.parametrize("use_eafe", [True, False])
+def test_matrix_and_rhs_parity(oracle, pkg, gpu_lib, grid, use_eafe):
+    P = oracle.Problem(*grid)
+    uu = perturbed_state(P, quantize=True)
+    A_ref, b_ref = P.assemble(uu, use_eafe=use_eafe)
+    g = gpu_problem(pkg, P, uu)
+    g.use_eafe(use_eafe)
+    g.assemble()
+    IA, JA, val = g.get_matrix()
+    assert np.array_equal(IA, P.IA) and np.array_equal(JA, P.JA)
+    err = row_scaled_error(IA, val, A_ref)
+    assert err <= 1e-12, "matrix row-scaled error %.3e" % err
+    b = g.get_rhs()
+    assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    # Dirichlet rows are exactly identity rows, rhs exactly zero there
+    bc = np.nonzero(P.bcflag)[0]
+    assert np.all(b[bc] == 0.0)
+    V = val.reshape(-1, 3, 3)
+    rows = np.repeat(np.arange(P.nv), np.diff(IA))
+    for d in bc[:50]:
+        i, k = divmod(int(d), 3)
+        sel = rows == i
+        blk = V[sel, k, :]
+        diag = JA[sel] == i
+        assert blk[diag, k] == 1.0 and np.abs(blk).sum() == 1.0
+    g.close()
+
+
+def test_matrix_parity_unquantized_is_conditioning_limited(oracle, pkg, gpu_lib):
+    """Continuous random potentials: the reference's own d/(exp(d)-1) carries eps/|d| relative
+    error, so parity is checked against 1e-12 + 8 eps/|d_min| per row."""
+    P = oracle.Problem(8, 4, 4)
+    uu = perturbed_state(P, quantize=False)
+    A_ref, _ = P.assemble(uu, use_eafe=True)
+    g = gpu_problem(pkg, P, uu)
+    g.assemble()
+    IA, JA, val = g.get_matrix()
+    rows = np.repeat(np.arange(P.nv), np.diff(IA))
+    d = np.abs(uu[0::3][JA] - uu[0::3][rows])
+    d = d[d > 3e-16]
+    tol = 1e-12 + 8 * 2.2e-16 / d.min()
+    err = row_scaled_error(IA, val, A_ref)
+    assert err <= tol, "row-scaled error %.3e > %.3e" % (err, tol)
+    g.close()
+
+
+@pytest.mark.parametrize("grid", GRIDS)
+def test_residual_norms(oracle, pkg, gpu_lib, grid):
+    P = oracle.Problem(*grid)
+    for uu in (P.uu0, perturbed_state(P)):
+        _, l2, li = P.residual(uu)
+        g = gpu_problem(pkg, P, uu)
+        a, b = g.residual()
+        assert abs(a - l2) <= 1e-12 * l2 and abs(b - li) <= 1e-12 * li
+        g.close()
+
+
+def test_full_size_box_invariants(oracle, pkg, gpu_lib):
+    """64^3 box (0.82 M dof): size-independent properties instead of the oracle —
+    EAFE (k,k) column sums vanish on interior columns, (k,1-k) coupling blocks are zero,
+    Dirichlet rows are identity rows, J*1 restricted to the potential row of phi-phi block is 0."""
+    n = 64
+    P = oracle.Problem(n, n, n, 2.0, 2.0, 2.0)
+    uu = perturbed_state(P)
+    g = gpu_problem(pkg, P, uu)
+    g.assemble()
+    IA, JA, val = g.get_matrix()
+    V = val.reshape(-1, 3, 3)
+    assert np.all(V[:, 1, 2] == 0.0) and np.all(V[:, 2, 1] == 0.0)
+    rows = np.repeat(np.arange(P.nv), np.diff(IA))
+    interior_rows = P.bcflag[0::3][rows] == 0
+    for k in (1, 2):
+        colsum = np.zeros(P.nv)
+        np.add.at(colsum, JA[interior_rows], V[interior_rows, k, k])
+        # columns all of whose rows are interior
+        touched_bc = np.zeros(P.nv, dtype=bool)
+        touched_bc[JA[~interior_rows]] = True
+        scale = np.abs(V[:, k, k]).max()
+        assert np.abs(colsum[~touched_bc]).max() <= 1e-12 * scale
+    # permittivity stiffness annihilates constants on interior rows
+    rowsum = np.zeros(P.nv)
+    np.add.at(rowsum, rows, V[:, 0, 0])
+    assert np.abs(rowsum[P.bcflag[0::3] == 0]).max() <= 1e-12 * np.abs(V[:, 0, 0]).max()
+    g.close()
