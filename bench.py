@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — Newton steps/s of the linearised-PNP hot path (EAFE assembly + AMG-FGMRES solve).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # CPU reference arm (oracle, 1 core)
+
+A "step" is one full Newton step (benchmarks/pnp_exact_solution/main.cpp:334-345: assemble the
+Jacobian with the EAFE overwrite and the rhs, AMG setup, FGMRES solve, u += du, residual norms)
+started from the Dirichlet interpolant of the pnp_exact_solution physics on an n^3 Kuhn box mesh
+of [-1,1]^3 (BASELINE.json configs[4]; default n=256 = 50.9 M dof, the north-star size). Every
+timed step does the same work: the state is reset to the initial guess first.
+  value : steps/s with the initial guess already in HBM (device-to-device reset)
+  e2e   : steps/s through the C ABI with HOST buffers: pnpb200_set_solution (H2D) +
+          pnpb200_newton_step + pnpb200_get_solution (D2H) inside the timed region
+Timing: CUDA events on the handle's stream, max over ranks; inputs (matrix ~18 GB) exceed L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "newton_steps_per_s"
+UNIT = "Newton steps/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def byte_model(stats, nv, nc, krylov_its, restart):
+    """Algorithmic bytes of one Newton step, SURVEY.md §8(d), from the run's actual level sizes
+    and iteration count (fp64 = 8 B, int32 = 4 B; every array touched once per logical pass)."""
+    N = 3 * nv
+    rows = [stats.level_rows[l] for l in range(stats.n_levels)]
+    nnzb = [stats.level_nnzb[l] for l in range(stats.n_levels)]
+    b_mat = [nnzb[l] * 76 + (rows[l] + 1) * 4 for l in range(len(rows))]
+    b_spmv = [b_mat[l] + 2 * 3 * rows[l] * 8 for l in range(len(rows))]
+    b_asm = nc * 16 + nv * 24 + N * 8 + nv * 16 + N * 8 * 2 + nnzb[0] * 72
+    b_eafe = 2 * (nnzb[0] * 12 + nv * 24)
+    b_res = nc * 16 + nv * 24 + N * 8 * 2 + nv * 16 + N * 8 * 3
+    b_setup = sum(2 * b_mat[l] + b_mat[l + 1] + rows[l] * 76 for l in range(len(rows) - 1))
+    b_vc = sum(3 * b_spmv[l] for l in range(len(rows) - 1)) + \
+        sum(2 * 3 * (rows[l] + rows[l + 1]) * 8 for l in range(len(rows) - 1))
+    b_kry = 0
+    for it in range(max(krylov_its, 0)):
+        j = it % restart
+        b_kry += b_spmv[0] + b_vc + (2 * (j + 1) + 2) * N * 8
+    return b_asm + b_eafe + 2 * b_res + b_setup + b_kry + 4 * N * 8
+
+
+def cpu_reference_leg(sample_n, steps=1):
+    """Oracle (reference element kernels when oracle/_ref is present + restated DOLFIN/FASP
+    orchestration), one host core like the serial reference, first Newton step on a bounded
+    sample box; returns seconds per step on the sample and its dof count."""
+    from oracle import oracle as O
+    used_ref = False
+    if O.ref_available():
+        try:
+            O.use_ref_kernels(True); used_ref = True
+        except Exception:
+            used_ref = False
+    ts, its = [], None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _, res = O.newton_exact(sample_n, sample_n, sample_n, 2.0, 2.0, 2.0, max_newton=1)
+        ts.append(time.perf_counter() - t0)
+        its = res.krylov_its[0]
+    if used_ref:
+        O.use_ref_kernels(False)
+    dof = 3 * (sample_n + 1) ** 3
+    return min(ts), dof, its, used_ref
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("PNPB200_BENCH_N", "256")))
+    ap.add_argument("--cpu-sample-n", type=int, default=48)
+    ap.add_argument("--cycle", default=os.environ.get("PNPB200_BENCH_CYCLE", "V"))
+    ap.add_argument("--maxit", type=int, default=int(os.environ.get("PNPB200_BENCH_MAXIT", "100")))
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n = args.n
+    nv, nc = (n + 1) ** 3, 6 * n ** 3
+    workload = "pnp_exact_solution physics, %d^3 Kuhn box of [-1,1]^3 (%.1f M dof), Newton step 1 from the Dirichlet interpolant" % (n, 3 * nv / 1e6)
+    config = {"workload": workload, "n": n, "dofs": 3 * nv, "cells": nc, "solver": "bsr.dat (UA-AMG %s-cycle(1,1) mc-GS + vFGMRES(30), tol 1e-6, maxit %d)" % (args.cycle, args.maxit),
+              "l2_policy": "inputs_larger_than_l2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        W, K = max(args.warmup, 0), max(args.steps, 1)
+        for _ in range(min(W, 1)):
+            cpu_reference_leg(16)
+        sec, dof, its, used_ref = cpu_reference_leg(args.cpu_sample_n, steps=min(K, 2))
+        scale = dof / float(3 * nv)             # linear-in-dof extrapolation (favours the CPU: its grow with n)
+        val = scale / sec
+        sample = ("first Newton step on a %d^3 box (%d dof, %d Krylov its), %.2f s on 1 core; scaled linearly in dof to the %d^3 workload"
+                  % (args.cpu_sample_n, dof, its, sec, n))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+                          "warmup": W, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1,
+                                           "kind": "port", "sample": sample + ("; reference element kernels (oracle/_ref)" if used_ref else "")},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import numpy as np
+    import torch
+    from pnpb200_loader import load_package
+    from importlib import import_module
+    pkg = load_package()
+    problems = import_module("modular_pnp_b200.problems")
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    torch.cuda.set_device(dev)
+
+    g = pkg.PNP(box=(n, n, n, 2.0, 2.0, 2.0), device=dev)
+    pr = problems.exact_solution_problem(n, n, n, 2.0, 2.0, 2.0)
+    g.set_coefficients(pr["eps"], pr["fixed"], pr["diff"], pr["val"], pr["reac"])
+    g.set_dirichlet(pr["bc_dofs"])
+    cyc = {"V": 1, "W": 2, "A": 3, "NA": 4}[args.cycle]
+    it, amg = pkg.default_params(maxit=args.maxit, cycle_type=cyc)
+    uu0_host = torch.from_numpy(pr["uu0"]).pin_memory()
+    uu_out_host = torch.empty_like(uu0_host).pin_memory()
+    uu0_dev = uu0_host.to("cuda:%d" % dev)
+    stream = torch.cuda.ExternalStream(g.stream, device=dev)
+    L, h = g.L, g.h
+    import ctypes as C
+
+    def step_resident():
+        L.pnpb200_set_solution_device(h, C.c_void_p(uu0_dev.data_ptr()))
+        return g.newton_step(it, amg)
+
+    def step_e2e():
+        L.pnpb200_set_solution(h, uu0_host.numpy())
+        r = g.newton_step(it, amg)
+        L.pnpb200_get_solution(h, uu_out_host.numpy())
+        return r
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, K):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches, its, last = 0, [], None
+        e0.record(stream)
+        for _ in range(K):
+            last = fn()
+            launches += g.stats().launches
+            its.append(last[0])
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda:%d" % dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, its, last
+
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    for _ in range(W):
+        step_resident()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    ms, launches, its, last = timed(step_resident, K)
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e, _, _, _ = timed(step_e2e, K)
+    stats = g.stats()
+    kits = its[-1]
+
+    # roofline of the dominant kernel (fine-level BSR SpMV: Krylov matvec + every V-cycle residual)
+    peak, peak_src = peaks()
+    probe_ms, probe_bytes = g.probe_kernel(0, 20)
+    gs_ms, gs_bytes = g.probe_kernel(2, 10)
+    achieved = probe_bytes / probe_ms / 1e6
+    b_step = byte_model(stats, nv, nc, kits if kits > 0 else stats.krylov_its, it.restart)
+    step_gbs = b_step / (ms / K) / 1e6
+    # traffic: dram bytes of one bsrt_spmv_kernel<0> launch from the committed ncu capture, if any
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get("n") == n:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    if rank == 0:
+        value = world * K / (ms / 1e3)
+        e2e_v = world * K / (ms_e2e / 1e3)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=("1 GPU" if world == 1 else "replicas x%d (row partition + halo exchange: next)" % world)),
+               "krylov_its_per_step": its, "krylov_status_ok": bool(kits > 0),
+               "relative_residual_after_step": None if last is None else last[1],
+               "levels": [[stats.level_rows[l], stats.level_nnzb[l], stats.level_colors[l]] for l in range(stats.n_levels)],
+               "stage_ms_last_step": {"assemble": stats.ms_assemble, "amg_setup": stats.ms_setup, "krylov": stats.ms_krylov,
+                                      "residual": stats.ms_residual},
+               "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": 3 * nv * 8, "d2h_bytes_per_step": 3 * nv * 8},
+               "gpu_launches": launches,
+               "clocks": clocks,
+               "roofline": {"bound": "hbm", "kernel": "bsrt_spmv_kernel<0> (fine level)", "achieved": achieved, "peak": peak,
+                            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": probe_bytes, "ms_per_launch": probe_ms,
+                            "gs_sweep": {"achieved": gs_bytes / gs_ms / 1e6, "frac": gs_bytes / gs_ms / 1e6 / peak, "ms": gs_ms},
+                            "whole_step": {"algorithmic_bytes": b_step, "achieved": step_gbs, "frac": step_gbs / peak}}}
+        # CPU baseline on the box's host cores (bounded sample), N=1 only
+        if world == 1:
+            try:
+                sec, dof, cits, used_ref = cpu_reference_leg(args.cpu_sample_n)
+                cval = (dof / float(3 * nv)) / sec
+                out["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": 1, "kind": "port",
+                                       "host_cores_available": os.cpu_count(),
+                                       "sample": "oracle first Newton step on a %d^3 box (%d dof, %d Krylov its) took %.2f s on 1 core; "
+                                                 "scaled linearly in dof to %d^3%s" % (args.cpu_sample_n, dof, cits, sec, n,
+                                                                                       "; reference element kernels (oracle/_ref)" if used_ref else "")}
+            except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "unavailable: %r" % (e,)}
+        print(json.dumps(out))
+    g.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,6 +36,14 @@ int  pnpb200_device_count(void);
  * edge table omega_ij, and the fine-level colouring. device = CUDA ordinal. */
 int  pnpb200_create(pnpb200_handle** h, int n_vertices, const double* xyz, int n_cells,
                     const int* cells, int device);
+/* domain_build (src/domain.cpp:290-311): the centred dolfin::BoxMesh(-L/2, +L/2, nx, ny, nz) every
+ * BASELINE config runs on, generated directly in device memory (no host mesh), then as create. */
+int  pnpb200_create_box(pnpb200_handle** h, int nx, int ny, int nz, double lx, double ly, double lz,
+                        int device);
+/* copy the mesh back (xyz[3*Nv], cells[4*Nc]; either may be NULL) */
+int  pnpb200_get_mesh(pnpb200_handle* h, double* xyz, int* cells);
+int  pnpb200_num_vertices(const pnpb200_handle* h);
+int  pnpb200_num_cells(const pnpb200_handle* h);
 void pnpb200_destroy(pnpb200_handle* h);
 /* the CUDA stream (cudaStream_t as void*) all work of this handle is enqueued on; callers that
  * time with their own events must record them on this stream */
@@ -115,6 +123,14 @@ int  pnpb200_get_level_aggregates(pnpb200_handle* h, int level, int* agg, int* n
 int  pnpb200_get_level_order(pnpb200_handle* h, int level, int* order);
 /* apply one V-cycle of the current hierarchy: z = M^{-1} r (host vectors) */
 int  pnpb200_apply_vcycle(pnpb200_handle* h, const double* r, double* z);
+/* roofline probe: run `reps` back-to-back launches of one hot kernel on the fine level, timed
+ * with CUDA events on the handle's stream; returns the mean ms per launch and the ALGORITHMIC
+ * bytes one launch moves (SURVEY §8d model). which: 0 = BSR SpMV y=Ax, 1 = residual r=b-Ax,
+ * 2 = one multicolour Gauss-Seidel sweep (all colours = one matrix pass),
+ * 3 = fused multi-dot over 16 basis vectors, 4 = residual cell kernel, 5 = Jacobian cell kernel,
+ * 6 = block assembly kernel. Needs an assembled system (and a solve for 2/3). */
+int  pnpb200_probe_kernel(pnpb200_handle* h, int which, int reps, double* ms_per_launch,
+                          double* algorithmic_bytes);
 /* y = J x with the assembled fine-level matrix (host vectors) */
 int  pnpb200_apply_matrix(pnpb200_handle* h, const double* x, double* y);
 

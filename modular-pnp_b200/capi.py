@@ -96,6 +96,11 @@ def lib():
     L.pnpb200_version.restype = C.c_char_p
     L.pnpb200_device_count.restype = C.c_int
     L.pnpb200_create.argtypes = [C.POINTER(H), C.c_int, _f8, C.c_int, _i4, C.c_int]
+    L.pnpb200_create_box.argtypes = [C.POINTER(H), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+    L.pnpb200_get_mesh.argtypes = [H, C.c_void_p, C.c_void_p]
+    L.pnpb200_num_vertices.argtypes = [H]
+    L.pnpb200_num_cells.argtypes = [H]
+    L.pnpb200_probe_kernel.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pnpb200_destroy.argtypes = [H]
     L.pnpb200_destroy.restype = None
     L.pnpb200_get_stream.argtypes = [H]
@@ -222,14 +227,29 @@ class PNP:
     """Device-resident linearised-PNP problem: the Python mirror of the host-side
     Linear_PNP/PDE surface (modular-pnp_b200/host/linear_pnp.hpp)."""
 
-    def __init__(self, xyz, cells, device=0):
+    def __init__(self, xyz=None, cells=None, device=0, box=None):
         self.L = lib()
         self.h = C.c_void_p()
-        xyz = np.ascontiguousarray(xyz, dtype=np.float64).ravel()
-        cells = np.ascontiguousarray(cells, dtype=np.int32).ravel()
-        self.nv, self.nc = len(xyz) // 3, len(cells) // 4
-        _check(self.L.pnpb200_create(C.byref(self.h), self.nv, xyz, self.nc, cells, device), "pnpb200_create")
+        if box is not None:
+            nx, ny, nz, lx, ly, lz = box
+            _check(self.L.pnpb200_create_box(C.byref(self.h), nx, ny, nz, lx, ly, lz, device), "pnpb200_create_box")
+            self.nv, self.nc = self.L.pnpb200_num_vertices(self.h), self.L.pnpb200_num_cells(self.h)
+        else:
+            xyz = np.ascontiguousarray(xyz, dtype=np.float64).ravel()
+            cells = np.ascontiguousarray(cells, dtype=np.int32).ravel()
+            self.nv, self.nc = len(xyz) // 3, len(cells) // 4
+            _check(self.L.pnpb200_create(C.byref(self.h), self.nv, xyz, self.nc, cells, device), "pnpb200_create")
         self.N = 3 * self.nv
+
+    def get_mesh(self):
+        xyz = np.zeros(3 * self.nv); cells = np.zeros(4 * self.nc, dtype=np.int32)
+        _check(self.L.pnpb200_get_mesh(self.h, xyz.ctypes.data, cells.ctypes.data), "get_mesh")
+        return xyz, cells
+
+    def probe_kernel(self, which, reps=10):
+        ms, by = C.c_double(), C.c_double()
+        _check(self.L.pnpb200_probe_kernel(self.h, which, reps, C.byref(ms), C.byref(by)), "probe_kernel")
+        return ms.value, by.value
 
     def close(self):
         if self.h:

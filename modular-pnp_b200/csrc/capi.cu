@@ -167,6 +167,45 @@ int pnpb200_create(pnpb200_handle** out, int nv, const double* xyz, int nc, cons
   });
 }
 
+int pnpb200_create_box(pnpb200_handle** out, int nx, int ny, int nz, double lx, double ly, double lz, int device)
+{
+  if (!out) return ERROR_INPUT_PAR;
+  *out = nullptr;
+  return guarded([&]() -> int {
+    if (nx < 1 || ny < 1 || nz < 1 || !(lx > 0) || !(ly > 0) || !(lz > 0)) throw Error(ERROR_INPUT_PAR, "pnpb200_create_box: bad grid");
+    pnpb200_handle* ph = new pnpb200_handle;
+    try {
+      Handle& h = ph->h;
+      init_handle(h, device);
+      cudaStream_t s = h.stream;
+      g_launches = 0;
+      generate_box_mesh(h, nx, ny, nz, lx, ly, lz);
+      const size_t N = 3 * (size_t)h.nv;
+      h.uu.alloc(N, s); h.uu.zero();
+      h.bcflag.alloc(N, s); h.bcflag.zero();
+      build_mesh_tables(h);
+      color_level(*h.hier.lv[0], s);
+      PNP_CUDA(cudaStreamSynchronize(s));
+      h.stats.launches = g_launches;
+    } catch (...) { delete ph; throw; }
+    *out = ph;
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_get_mesh(pnpb200_handle* ph, double* xyz, int* cells)
+{
+  if (!ph) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    if (xyz) h.xyz.download(xyz, 3 * (size_t)h.nv);
+    if (cells) h.cells.download(cells, 4 * (size_t)h.nc);
+    return FASP_SUCCESS;
+  });
+}
+int pnpb200_num_vertices(const pnpb200_handle* ph) { return ph ? ph->h.nv : 0; }
+int pnpb200_num_cells(const pnpb200_handle* ph) { return ph ? ph->h.nc : 0; }
+
 void pnpb200_destroy(pnpb200_handle* ph)
 {
   delete ph;
@@ -444,6 +483,52 @@ int pnpb200_apply_vcycle(pnpb200_handle* ph, const double* r, double* z)
     SolverConfig cfg;                       // V(1,1)
     amg_vcycle(h, cfg, dr.p, dz.p);
     dz.download(z, N);
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_probe_kernel(pnpb200_handle* ph, int which, int reps, double* ms_per_launch, double* algorithmic_bytes)
+{
+  if (!ph || reps < 1) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    Level& L = *h.hier.lv[0];
+    const BsrT& A = L.A;
+    const size_t N = 3 * (size_t)A.n;
+    DevBuf<double> x, y; x.alloc(N, s); y.alloc(N, s);
+    vec_set(x.p, 1.0, N, s); vec_set(y.p, 0.5, N, s);
+    const double b_mat = (double)A.nnzb * 76.0 + ((double)A.n + 1.0) * 4.0;
+    double bytes = 0.0;
+    auto run = [&](int k) {
+      switch (which) {
+        case 0: bsrt_spmv(A, x.p, y.p, s); break;
+        case 1: bsrt_residual(A, h.rhs.p, x.p, y.p, s); break;
+        case 2: mcgs_sweep(L, h.rhs.p, y.p, (k & 1) != 0, s); break;
+        case 3: { double out[32]; multi_dot(h, h.kry.V.p, N, 16, y.p, N, out); break; }
+        case 4: { assemble_residual(h, h.rhs, nullptr, nullptr); break; }
+        case 5: case 6: assemble_system(h); break;
+        default: throw Error(ERROR_INPUT_PAR, "unknown probe");
+      }
+    };
+    switch (which) {
+      case 0: bytes = b_mat + 2.0 * N * 8.0; break;
+      case 1: bytes = b_mat + 3.0 * N * 8.0; break;
+      case 2: if (L.ncolors == 0 || L.dinv.n < 9 * (size_t)A.n) throw Error(ERROR_INPUT_PAR, "probe 2 needs a solve first");
+              bytes = b_mat + 3.0 * N * 8.0 + 72.0 * A.n; break;
+      case 3: if (h.kry.V.n < 17 * N) throw Error(ERROR_INPUT_PAR, "probe 3 needs a solve first");
+              bytes = 17.0 * N * 8.0; break;
+      case 4: bytes = (double)h.nc * 16.0 + (double)h.nv * 24.0 + N * 8.0 * 2.0 + (double)h.nv * 16.0 + N * 8.0 * 2.0; break;
+      default: bytes = (double)h.nc * 16.0 + (double)h.nv * 24.0 + N * 8.0 + (double)h.nv * 16.0 + N * 8.0 * 2.0 + (double)A.nnzb * 72.0; break;
+    }
+    run(0);                                            // warm-up
+    PNP_CUDA(cudaEventRecord(h.ev[2], s));
+    for (int k = 0; k < reps; ++k) run(k);
+    PNP_CUDA(cudaEventRecord(h.ev[3], s));
+    PNP_CUDA(cudaEventSynchronize(h.ev[3]));
+    float ms = 0; PNP_CUDA(cudaEventElapsedTime(&ms, h.ev[2], h.ev[3]));
+    if (ms_per_launch) *ms_per_launch = ms / reps;
+    if (algorithmic_bytes) *algorithmic_bytes = bytes;
     return FASP_SUCCESS;
   });
 }

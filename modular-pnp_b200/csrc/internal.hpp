@@ -119,6 +119,7 @@ struct Handle {
 // ---- mesh_setup.cu
 void build_mesh_tables(Handle& h);                 // v2c, pattern, brow/dslot/tslot, omega
 void compute_k00(Handle& h);
+void generate_box_mesh(Handle& h, int nx, int ny, int nz, double lx, double ly, double lz);   // domain_build
 void finish_pattern_tables(BsrT& A, cudaStream_t s);   // brow, dslot, tslot from ia/ja
 void exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t s);
 // ---- assemble.cu

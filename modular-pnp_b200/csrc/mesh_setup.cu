@@ -212,3 +212,48 @@ void compute_k00(Handle& h)
 }
 
 } // namespace pnpb200
+
+// ---- domain_build (src/domain.cpp:290-311): centred dolfin::BoxMesh generated on the device ----
+namespace pnpb200 {
+namespace {
+__global__ void box_vertices_kernel(int nx, int ny, int nz, double lx, double ly, double lz, double* __restrict__ xyz)
+{
+  const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nvx = nx + 1, nvy = ny + 1, nv = nvx * nvy * (size_t)(nz + 1);
+  if (v >= nv) return;
+  const int ix = (int)(v % nvx), iy = (int)((v / nvx) % nvy), iz = (int)(v / (nvx * nvy));
+  // DOLFIN BoxMesh [EXT]: x = a + ix*(b-a)/nx with a = -L/2, b = +L/2
+  const double a = -lx / 2, b = lx / 2, c = -ly / 2, d = ly / 2, e = -lz / 2, f = lz / 2;
+  xyz[3 * v]     = a + ((double)ix) * (b - a) / (double)nx;
+  xyz[3 * v + 1] = c + ((double)iy) * (d - c) / (double)ny;
+  xyz[3 * v + 2] = e + ((double)iz) * (f - e) / (double)nz;
+}
+
+__global__ void box_cells_kernel(int nx, int ny, int nz, int4* __restrict__ cells)
+{
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t ncube = (size_t)nx * ny * nz;
+  if (q >= ncube) return;
+  const int ix = (int)(q % nx), iy = (int)((q / nx) % ny), iz = (int)(q / ((size_t)nx * ny));
+  const int sx = nx + 1, sxy = (nx + 1) * (ny + 1);
+  const int v0 = iz * sxy + iy * sx + ix, v1 = v0 + 1, v2 = v0 + sx, v3 = v1 + sx;
+  const int v4 = v0 + sxy, v5 = v1 + sxy, v6 = v2 + sxy, v7 = v3 + sxy;
+  // six tetrahedra around the v0-v7 diagonal, vertices ascending (UFC order)
+  int4* o = cells + 6 * q;
+  o[0] = make_int4(v0, v1, v3, v7); o[1] = make_int4(v0, v1, v5, v7); o[2] = make_int4(v0, v4, v5, v7);
+  o[3] = make_int4(v0, v2, v3, v7); o[4] = make_int4(v0, v4, v6, v7); o[5] = make_int4(v0, v2, v6, v7);
+}
+} // namespace
+
+void generate_box_mesh(Handle& h, int nx, int ny, int nz, double lx, double ly, double lz)
+{
+  cudaStream_t s = h.stream;
+  const size_t nv = (size_t)(nx + 1) * (ny + 1) * (nz + 1), ncube = (size_t)nx * ny * nz;
+  if (nv > 0x7fffffffull / 16 || 6 * ncube > 0x7fffffffull / 4) throw Error(ERROR_INPUT_PAR, "box mesh too large for 32-bit indices");
+  h.nv = (int)nv; h.nc = (int)(6 * ncube);
+  h.xyz.alloc(3 * nv, s); h.cells.alloc(4 * (size_t)h.nc, s);
+  box_vertices_kernel<<<cdiv(nv, 256), 256, 0, s>>>(nx, ny, nz, lx, ly, lz, h.xyz.p); PNP_COUNT_LAUNCH();
+  box_cells_kernel<<<cdiv(ncube, 256), 256, 0, s>>>(nx, ny, nz, reinterpret_cast<int4*>(h.cells.p)); PNP_COUNT_LAUNCH();
+  PNP_LAUNCH_CHECK();
+}
+} // namespace pnpb200
