@@ -354,17 +354,89 @@ __global__ void dense_matvec_kernel(int nd, const double* __restrict__ Inv, cons
   if (lane == 0) x[row] = a;
 }
 
+
+// ---- K-cycle (nonlinear AMLI, FASP cycle_type NL_AMLI [EXT]; Notay's 2-step GCR form) ----------
+// All scalars stay on the device so that one preconditioner application is a fixed launch
+// sequence without host synchronisation.
+//   out[q] = <a_q, b_q>, q < NP; single launch, deterministic (last block sums the partials in order)
+template <int NP>
+__global__ void __launch_bounds__(256)
+kdots_kernel(size_t n, const double* __restrict__ a0, const double* __restrict__ b0,
+             const double* __restrict__ a1, const double* __restrict__ b1,
+             const double* __restrict__ a2, const double* __restrict__ b2,
+             double* __restrict__ partial, unsigned* __restrict__ counter, double* __restrict__ out)
+{
+  __shared__ double sm[32];
+  __shared__ bool last;
+  double acc[NP];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) acc[q] = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    acc[0] += a0[i] * b0[i];
+    if (NP > 1) acc[1] += a1[i] * b1[i];
+    if (NP > 2) acc[2] += a2[i] * b2[i];
+  }
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    const double r = block_sum(acc[q], sm);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * NP + q] = r;
+  }
+  __threadfence();
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x < NP) {
+      double t = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) t += partial[(size_t)b * NP + threadIdx.x];
+      out[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// sc[0] = <v,b>, sc[1] = <v,v>:  rt = b - (sc0/sc1) v
+__global__ void kc_step1_kernel(size_t n, const double* __restrict__ sc, const double* __restrict__ b,
+                                const double* __restrict__ v, double* __restrict__ rt)
+{
+  const double a = sc[1] != 0.0 ? sc[0] / sc[1] : 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    rt[i] = b[i] - a * v[i];
+}
+
+// sc[2] = <w,v>, sc[3] = <w,w>, sc[4] = <w,rt>:  x = (a1 - g*a2/(r1*r2)) c + (a2/r2) d
+__global__ void kc_final_kernel(size_t n, const double* __restrict__ sc, const double* __restrict__ c,
+                                const double* __restrict__ d, double* __restrict__ x)
+{
+  const double r1 = sc[1], a1 = r1 != 0.0 ? sc[0] / r1 : 0.0;
+  const double g = sc[2];
+  const double r2 = r1 != 0.0 ? sc[3] - g * g / r1 : 0.0;
+  double k1 = a1, k2 = 0.0;
+  if (r2 > 0.0 && r1 != 0.0) { k2 = sc[4] / r2; k1 = a1 - g * k2 / r1; }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = k1 * c[i] + k2 * d[i];
+}
+
 template <typename K, typename V>
-void sort_pairs(K* kin, K* kout, V* vin, V* vout, int n, int end_bit, cudaStream_t s)
+void sort_pairs(Workspace& ws, K* kin, K* kout, V* vin, V* vout, int n, int end_bit, cudaStream_t s)
 {
   size_t bytes = 0;
   PNP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, end_bit, s));
-  DevBuf<unsigned char> tmp; tmp.alloc(bytes, s);
-  PNP_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, n, 0, end_bit, s));
+  unsigned char* tmp = ws.get<unsigned char>(bytes);
+  PNP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, n, 0, end_bit, s));
   PNP_COUNT_LAUNCH();
 }
 
 int bits_for(u64 v) { int b = 1; while (b < 64 && (v >> b)) ++b; return b; }
+
+// setup phase timing (print_level >= 3 only): host clock around a stream sync
+struct Phase {
+  cudaStream_t s; bool on; const char* name; int lvl; double t0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  Phase(cudaStream_t st, bool o, const char* n, int l) : s(st), on(o), name(n), lvl(l), t0(0) { if (on) { cudaStreamSynchronize(s); t0 = now(); } }
+  ~Phase() { if (on) { cudaStreamSynchronize(s); printf("    [setup l%d] %-18s %8.2f ms\n", lvl, name, now() - t0); } }
+};
+bool g_phase = false; int g_phase_lvl = 0;
+#define PHASE(name) Phase phase__(s, g_phase, name, g_phase_lvl)
 
 // symbolic part of one coarsening step: aggregates of L and the structure of the next level
 bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
@@ -372,24 +444,36 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   cudaStream_t s = h.stream;
   BsrT& A = L.A;
   const int n = A.n, nnzb = A.nnzb;
-  DevBuf<double> pp; pp.alloc(nnzb, s);
+  // all large temporaries of this coarsening step live in the handle's workspace
+  Workspace& ws = h.ws;
+  ws.reserve((size_t)nnzb * 56 + (size_t)n * 64 + (64u << 20), s);
+  ws.reset();
+  struct P1 { double* p; } pp; struct P2 { unsigned char* p; } iso, strong; struct P3 { int* p; void zero(cudaStream_t st) { cudaMemsetAsync(p, 0, sizeof(int), st); } } state, cnt;
+  struct P4 { u64* p; } t1, t2;
+  {
+  PHASE("strength");
+  pp.p = ws.get<double>(nnzb);
   condense_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ia.p, A.brow.p, A.val.p, pp.p); PNP_COUNT_LAUNCH();
-  DevBuf<unsigned char> iso, strong; iso.alloc(n, s); strong.alloc(nnzb, s);
+  iso.p = ws.get<unsigned char>(n); strong.p = ws.get<unsigned char>(nnzb);
   isolated_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, pp.p, iso.p); PNP_COUNT_LAUNCH();
   strength_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, A.dslot.p, A.tslot.p, pp.p, iso.p,
                                                  theta * theta, strong.p); PNP_COUNT_LAUNCH();
   {
-    DevBuf<int> sel; sel.alloc(n, s);
+    struct { int* p; } sel; sel.p = ws.get<int>(n);
     force_select_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, pp.p, iso.p, strong.p, sel.p); PNP_COUNT_LAUNCH();
     force_apply_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.tslot.p, sel.p, strong.p); PNP_COUNT_LAUNCH();
   }
+  }
   // distance-2 MIS
-  DevBuf<int> state, cnt; state.alloc(n, s); cnt.alloc(1, s);
-  DevBuf<u64> t1, t2; t1.alloc(n, s); t2.alloc(n, s);
+  int rounds = 0;
+  {
+  PHASE("mis2");
+  state.p = ws.get<int>(n); cnt.p = ws.get<int>(1);
+  t1.p = ws.get<u64>(n); t2.p = ws.get<u64>(n);
   mis_init_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, iso.p, state.p); PNP_COUNT_LAUNCH();
-  int und = 1, rounds = 0;
+  int und = 1;
   while (und > 0) {
-    cnt.zero();
+    cnt.zero(s);
     mis_prop_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, strong.p, state.p, nullptr, t1.p); PNP_COUNT_LAUNCH();
     mis_prop_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, strong.p, state.p, t1.p, t2.p); PNP_COUNT_LAUNCH();
     mis_decide_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, t2.p, state.p, cnt.p); PNP_COUNT_LAUNCH();
@@ -397,8 +481,11 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
     PNP_CUDA(cudaStreamSynchronize(s));
     if (++rounds > 1000) throw Error(ERROR_AMG_COARSEING, "MIS-2 did not terminate");
   }
+  }
+  if (g_phase) printf("    [setup l%d] mis2 rounds %d\n", g_phase_lvl, rounds);
+  PHASE("aggregate+rap_sym");
   // aggregate ids
-  DevBuf<int> flag, rootid; flag.alloc(n + 1, s); rootid.alloc(n + 1, s);
+  struct { int* p; } flag, rootid, agg2; flag.p = ws.get<int>(n + 1); rootid.p = ws.get<int>(n + 1); agg2.p = ws.get<int>(n);
   root_flag_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(n, state.p, flag.p); PNP_COUNT_LAUNCH();
   exclusive_scan_int(flag.p, rootid.p, n + 1, s);
   int nagg = 0;
@@ -406,11 +493,10 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   PNP_CUDA(cudaStreamSynchronize(s));
   if (nagg == 0 || nagg >= n) return false;
   L.agg.alloc(n, s);
-  DevBuf<int> agg2; agg2.alloc(n, s);
   agg_root_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, state.p, rootid.p, iso.p, L.agg.p); PNP_COUNT_LAUNCH();
   int left = 1; int* cur = L.agg.p; int* nxt = agg2.p;
   for (int pass = 0; pass < 8 && left > 0; ++pass) {
-    cnt.zero();
+    cnt.zero(s);
     agg_join_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, strong.p, pp.p, cur, nxt, cnt.p); PNP_COUNT_LAUNCH();
     PNP_CUDA(cudaMemcpyAsync(&left, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     PNP_CUDA(cudaStreamSynchronize(s));
@@ -421,23 +507,24 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   L.nagg = nagg;
   // members of each aggregate (ascending rows)
   {
-    DevBuf<int> c; c.alloc(nagg + 1, s); c.zero();
+    struct { int* p; } c; c.p = ws.get<int>(nagg + 1);
+    PNP_CUDA(cudaMemsetAsync(c.p, 0, (size_t)(nagg + 1) * sizeof(int), s));
     agg_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.agg.p, c.p); PNP_COUNT_LAUNCH();
     L.agg_ptr.alloc(nagg + 1, s);
     exclusive_scan_int(c.p, L.agg_ptr.p, nagg + 1, s);
-    DevBuf<unsigned> kin, kout; kin.alloc(n, s); kout.alloc(n, s);
-    DevBuf<int> vin; vin.alloc(n, s); L.agg_rows.alloc(n, s);
+    struct { unsigned* p; } kin, kout; kin.p = ws.get<unsigned>(n); kout.p = ws.get<unsigned>(n);
+    struct { int* p; } vin; vin.p = ws.get<int>(n); L.agg_rows.alloc(n, s);
     agg_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.agg.p, kin.p); PNP_COUNT_LAUNCH();
     iota_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, vin.p); PNP_COUNT_LAUNCH();
-    sort_pairs(kin.p, kout.p, vin.p, L.agg_rows.p, n, 32, s);
+    sort_pairs(ws, kin.p, kout.p, vin.p, L.agg_rows.p, n, 32, s);
   }
   // coarse structure: sort blocks by (I,J)
   {
-    DevBuf<u64> kin, kout; kin.alloc(nnzb, s); kout.alloc(nnzb, s);
-    DevBuf<int> vin; vin.alloc(nnzb, s); L.rap_perm.alloc(nnzb, s);
+    struct { u64* p; } kin, kout; kin.p = ws.get<u64>(nnzb); kout.p = ws.get<u64>(nnzb);
+    struct { int* p; } vin; vin.p = ws.get<int>(nnzb); L.rap_perm.alloc(nnzb, s);
     rap_key_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, L.agg.p, (u64)nagg, kin.p, vin.p); PNP_COUNT_LAUNCH();
-    sort_pairs(kin.p, kout.p, vin.p, L.rap_perm.p, nnzb, 64, s);
-    DevBuf<int> head, slot; head.alloc(nnzb + 1, s); slot.alloc(nnzb + 1, s);
+    sort_pairs(ws, kin.p, kout.p, vin.p, L.rap_perm.p, nnzb, 2 * bits_for((u64)nagg) + 1, s);
+    struct { int* p; } head, slot; head.p = ws.get<int>(nnzb + 1); slot.p = ws.get<int>(nnzb + 1);
     rap_head_kernel<<<cdiv(nnzb + 1, 256), 256, 0, s>>>(nnzb, kout.p, head.p); PNP_COUNT_LAUNCH();
     exclusive_scan_int(head.p, slot.p, nnzb + 1, s);
     int cnnzb = 0;
@@ -447,7 +534,8 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
     Ac.n = nagg; Ac.nnzb = cnnzb;
     Ac.ja.alloc(cnnzb, s); Ac.ia.alloc(nagg + 1, s); Ac.val.alloc(9 * (size_t)cnnzb, s);
     L.rap_seg.alloc(cnnzb + 1, s);
-    DevBuf<int> rowcnt; rowcnt.alloc(nagg + 1, s); rowcnt.zero();
+    struct { int* p; } rowcnt; rowcnt.p = ws.get<int>(nagg + 1);
+    PNP_CUDA(cudaMemsetAsync(rowcnt.p, 0, (size_t)(nagg + 1) * sizeof(int), s));
     int* nvalid = L.rap_seg.p + cnnzb;
     rap_structure_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, kout.p, head.p, slot.p, (u64)nagg, Ac.ja.p, L.rap_seg.p,
                                                         rowcnt.p, nvalid); PNP_COUNT_LAUNCH();
@@ -489,6 +577,8 @@ SolverConfig make_config(const itsolver_param* it, const AMG_param* amg)
     c.tentative_smooth = amg->tentative_smooth;
     c.presmooth = amg->presmooth_iter; c.postsmooth = amg->postsmooth_iter;
     if (amg->print_level > c.print_level) c.print_level = amg->print_level;
+    c.cycle_type = amg->cycle_type > 0 ? amg->cycle_type : V_CYCLE;
+    if (const char* e = getenv("PNPB200_KCYCLE_LEVELS")) c.kcycle_levels = atoi(e);
   } else c.use_amg = 0;
   if (c.restart > 31) c.restart = 31;      // fused orthogonalisation kernels carry <= 32 coefficients
   if (c.restart > c.maxit && c.maxit > 0) c.restart = c.maxit;
@@ -503,7 +593,7 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
   const bool reuse = h.reuse_hierarchy && h.hier.symbolic_valid;
   if (F.ncolors == 0) color_level(F, s);           // pattern-only: survives across solves
   alloc_level_vectors(F, s);
-  if (!reuse) { lv.resize(1); h.hier.symbolic_valid = false; }
+  if (!reuse) h.hier.symbolic_valid = false;
   const int min_cdof = cfg.coarse_dof > 50 ? cfg.coarse_dof : 50;
   int l = 0;
   while (true) {
@@ -516,14 +606,17 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
     }
     if (!(L.A.n > min_cdof && l < cfg.max_levels - 1)) break;
     const double theta = cfg.tentative_smooth > 1e-20 ? cfg.strong_coupled * std::pow(0.5, l) : cfg.strong_coupled;
-    std::unique_ptr<Level> C(new Level);
-    if (!coarsen_symbolic(h, L, *C, theta)) break;
-    rap_numeric(h, L, *C);
-    alloc_level_vectors(*C, s);
-    color_level(*C, s);
-    lv.push_back(std::move(C));
+    // Level objects (and their device buffers) are recycled from the previous hierarchy
+    if (l + 1 >= (int)lv.size()) lv.emplace_back(new Level);
+    Level& C = *lv[l + 1];
+    g_phase = cfg.print_level >= 3; g_phase_lvl = l;
+    if (!coarsen_symbolic(h, L, C, theta)) break;
+    { PHASE("rap_numeric"); rap_numeric(h, L, C); }
+    alloc_level_vectors(C, s);
+    { PHASE("colour"); color_level(C, s); }
     ++l;
   }
+  if (!reuse) lv.resize(l + 1);
   // coarsest level: explicit dense inverse
   Level& Z = *lv.back();
   const int nd = 3 * Z.A.n;
@@ -546,44 +639,76 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
   }
 }
 
-// z = M^{-1} r : one V(nu1,nu2) cycle from a zero initial guess (fasp_precond_dbsr_amg [EXT])
+namespace {
+
+inline int small_grid(size_t n) { const size_t b = (n + 255) / 256; return (int)(b < 1 ? 1 : (b > 592 ? 592 : b)); }
+
+void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x);
+
+// one multigrid cycle on level l from a zero initial guess: x = B_l b
+void mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x)
+{
+  cudaStream_t s = h.stream;
+  Level& L = *h.hier.lv[l];
+  Level& C = *h.hier.lv[l + 1];
+  const size_t m = 3 * (size_t)L.A.n;
+  vec_set(x, 0.0, m, s);
+  for (int k = 0; k < cfg.presmooth; ++k) mcgs_sweep(L, b, x, false, s);
+  bsrt_residual(L.A, b, x, L.w.p, s);
+  restrict_kernel<<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, L.agg_ptr.p, L.agg_rows.p, L.w.p, C.b.p);
+  PNP_COUNT_LAUNCH();
+  solve_level(h, cfg, l + 1, C.b.p, C.x.p);
+  prolong_kernel<<<cdiv(m, 256), 256, 0, s>>>(L.A.n, L.agg.p, C.x.p, x); PNP_COUNT_LAUNCH();
+  for (int k = 0; k < cfg.postsmooth; ++k) mcgs_sweep(L, b, x, true, s);
+}
+
+// approximate solve of A_l x = b on a coarse level l >= 1
+void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x)
+{
+  cudaStream_t s = h.stream;
+  const int nl = (int)h.hier.lv.size();
+  Level& L = *h.hier.lv[l];
+  if (l == nl - 1) {
+    dense_matvec_kernel<<<cdiv((size_t)h.hier.nd * 32, 256), 256, 0, s>>>(h.hier.nd, h.hier.dense_inv.p, b, x);
+    PNP_COUNT_LAUNCH();
+    return;
+  }
+  const bool kcyc = cfg.cycle_type != V_CYCLE && l <= cfg.kcycle_levels;
+  if (!kcyc) { mg_cycle(h, cfg, l, b, x); return; }
+  // K-cycle: two GCR steps preconditioned by the cycle of this level (device scalars only)
+  const size_t m = 3 * (size_t)L.A.n;
+  L.kc.alloc(5 * m + 0, s);
+  L.ksc.alloc(8 + 3 * 592, s);
+  if (!L.kcnt.p) { L.kcnt.alloc(1, s); L.kcnt.zero(); }
+  double* c = L.kc.p; double* v = c + m; double* rt = v + m; double* d = rt + m; double* w = d + m;
+  double* sc = L.ksc.p; double* partial = sc + 8;
+  const int g = small_grid(m);
+  mg_cycle(h, cfg, l, b, c);
+  bsrt_spmv(L.A, c, v, s);
+  kdots_kernel<2><<<g, 256, 0, s>>>(m, v, b, v, v, nullptr, nullptr, partial, L.kcnt.p, sc); PNP_COUNT_LAUNCH();
+  kc_step1_kernel<<<g, 256, 0, s>>>(m, sc, b, v, rt); PNP_COUNT_LAUNCH();
+  mg_cycle(h, cfg, l, rt, d);
+  bsrt_spmv(L.A, d, w, s);
+  kdots_kernel<3><<<g, 256, 0, s>>>(m, w, v, w, w, w, rt, partial, L.kcnt.p, sc + 2); PNP_COUNT_LAUNCH();
+  kc_final_kernel<<<g, 256, 0, s>>>(m, sc, c, d, x); PNP_COUNT_LAUNCH();
+}
+
+} // namespace
+
+// z = M^{-1} r : one multigrid cycle from a zero initial guess (fasp_precond_dbsr_amg [EXT]):
+// V(nu1,nu2), or with AMG_cycle_type != V the K-cycle on the first cfg.kcycle_levels coarse levels
 void amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z)
 {
   cudaStream_t s = h.stream;
   auto& lv = h.hier.lv;
   const int nl = (int)lv.size();
-  const double* bl = r;
-  double* xl = z;
-  // level 0 works directly on the caller's vectors
-  for (int l = 0; l < nl - 1; ++l) {
-    Level& L = *lv[l];
-    const size_t m = 3 * (size_t)L.A.n;
-    vec_set(xl, 0.0, m, s);
-    for (int k = 0; k < cfg.presmooth; ++k) mcgs_sweep(L, bl, xl, false, s);
-    bsrt_residual(L.A, bl, xl, L.w.p, s);
-    Level& C = *lv[l + 1];
-    restrict_kernel<<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, L.agg_ptr.p, L.agg_rows.p, L.w.p, C.b.p);
-    PNP_COUNT_LAUNCH();
-    bl = C.b.p; xl = C.x.p;
+  if (nl == 1) {
+    Level& Z = *lv[0];
+    vec_set(z, 0.0, 3 * (size_t)Z.A.n, s);
+    for (int k = 0; k < cfg.presmooth; ++k) mcgs_sweep(Z, r, z, false, s);
+    return;
   }
-  {
-    Level& Z = *lv[nl - 1];
-    if (nl == 1) {
-      vec_set(xl, 0.0, 3 * (size_t)Z.A.n, s);
-      for (int k = 0; k < cfg.presmooth; ++k) mcgs_sweep(Z, bl, xl, false, s);
-    } else {
-      dense_matvec_kernel<<<cdiv((size_t)h.hier.nd * 32, 256), 256, 0, s>>>(h.hier.nd, h.hier.dense_inv.p, bl, xl);
-      PNP_COUNT_LAUNCH();
-    }
-  }
-  for (int l = nl - 2; l >= 0; --l) {
-    Level& L = *lv[l];
-    Level& C = *lv[l + 1];
-    double* x = l == 0 ? z : L.x.p;
-    const double* b = l == 0 ? r : L.b.p;
-    prolong_kernel<<<cdiv(3 * (size_t)L.A.n, 256), 256, 0, s>>>(L.A.n, L.agg.p, C.x.p, x); PNP_COUNT_LAUNCH();
-    for (int k = 0; k < cfg.postsmooth; ++k) mcgs_sweep(L, b, x, true, s);
-  }
+  mg_cycle(h, cfg, 0, r, z);
 }
 
 } // namespace pnpb200

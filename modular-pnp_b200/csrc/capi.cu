@@ -58,6 +58,7 @@ int solve_current(Handle& h, const itsolver_param* it, const AMG_param* amg, int
   const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
   h.du.alloc(N, s);
   vec_set(h.du.p, 0.0, N, s);                       // linear_pnp.cpp:93 fasp_dvec_set(..., 0.0)
+  h.last_cfg = cfg;
   h.stats.ms_spmv = h.stats.ms_vcycle = h.stats.ms_ortho = 0.0;
   { EventSpan e(h, h.stats.ms_setup); if (cfg.use_amg) amg_setup(h, cfg); e.stop(); }
   int st;
@@ -480,7 +481,7 @@ int pnpb200_apply_vcycle(pnpb200_handle* ph, const double* r, double* z)
     const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
     DevBuf<double> dr, dz; dr.alloc(N, s); dz.alloc(N, s);
     dr.upload(r, N);
-    SolverConfig cfg;                       // V(1,1)
+    const SolverConfig cfg = h.last_cfg;    // cycle of the last solve
     amg_vcycle(h, cfg, dr.p, dz.p);
     dz.download(z, N);
     return FASP_SUCCESS;

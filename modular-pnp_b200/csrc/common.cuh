@@ -30,7 +30,22 @@ struct Error : public std::runtime_error {
 
 // launch counter (bench.py's gpu_launches claim)
 extern thread_local long g_launches;
-#define PNP_COUNT_LAUNCH() (++::pnpb200::g_launches)
+struct Error;
+extern int g_debug_sync;      // PNPB200_DEBUG_SYNC=1: synchronise + check after every launch
+inline void count_launch(const char* file, int line)
+{
+  ++g_launches;
+  if (g_debug_sync) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      char buf[512];
+      snprintf(buf, sizeof buf, "CUDA error %s after the launch at %s:%d", cudaGetErrorString(e), file, line);
+      throw Error(-120, buf);
+    }
+  }
+}
+#define PNP_COUNT_LAUNCH() ::pnpb200::count_launch(__FILE__, __LINE__)
 
 inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
@@ -55,6 +70,7 @@ struct DevBuf {
   {
     if (p && n >= count && s == stream) return;     // keep a big-enough block
     release();
+    count += count / 16;                            // slack: sizes drift a little between Newton steps
     s = stream; n = count;
     if (count == 0) return;
     PNP_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
@@ -72,6 +88,30 @@ struct DevBuf {
     PNP_CUDA(cudaStreamSynchronize(s));
   }
   std::vector<T> to_host(size_t count) const { std::vector<T> v(count); if (count) download(v.data(), count); return v; }
+};
+
+// Bump allocator over one persistent device block: the AMG setup's large temporaries (sort keys,
+// strength flags, CUB scratch) come from here so that a hierarchy rebuild never goes back to the
+// driver for memory.
+struct Workspace {
+  DevBuf<unsigned char> buf;
+  size_t off = 0;
+  void reserve(size_t bytes, cudaStream_t s)
+  {
+    if (buf.n >= bytes) return;
+    PNP_CUDA(cudaStreamSynchronize(s));
+    buf.release();
+    buf.alloc(bytes, s);
+  }
+  void reset() { off = 0; }
+  template <typename T> T* get(size_t count)
+  {
+    const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (off + bytes > buf.n) throw Error(-15, "pnpb200 workspace exhausted");
+    T* r = reinterpret_cast<T*>(buf.p + off);
+    off += bytes;
+    return r;
+  }
 };
 
 // ---- device helpers -----------------------------------------------------------------------

@@ -80,7 +80,7 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
         for (int j = 0; j < i; ++j) neg[j] = -hcol[j];
         double after2 = 0.0;
         multi_axpy(h, V, n, i, neg.data(), Vi(i), n, &after2);
-        if (std::sqrt(after2) < 0.7071067811865476 * before) {   // DGKS: orthogonalise once more
+        if (std::sqrt(after2) < 0.1 * before) {   // DGKS: orthogonalise once more
           multi_dot(h, V, n, i, Vi(i), n, h2.data());
           for (int j = 0; j < i; ++j) { neg[j] = -h2[j]; hcol[j] += h2[j]; }
           multi_axpy(h, V, n, i, neg.data(), Vi(i), n, &after2);

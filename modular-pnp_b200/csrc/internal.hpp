@@ -35,6 +35,9 @@ struct Level {
   DevBuf<int> rap_seg, rap_perm;
   // work vectors (3*n)
   DevBuf<double> x, b, w;
+  // K-cycle scratch: 5 vectors, device scalars + partials, block counter
+  DevBuf<double> kc, ksc;
+  DevBuf<unsigned> kcnt;
 };
 
 struct SolverConfig {
@@ -44,6 +47,8 @@ struct SolverConfig {
   int max_levels = 20; int coarse_dof = 100; double strong_coupled = 0.08; int max_aggregation = 20;
   double tentative_smooth = 0.67; int presmooth = 1, postsmooth = 1;
   int use_amg = 1;
+  int cycle_type = 1;       // V_CYCLE; anything else = K-cycle (nonlinear AMLI)
+  int kcycle_levels = 2;    // coarse levels 1..kcycle_levels get the Krylov acceleration
 };
 SolverConfig make_config(const itsolver_param* it, const AMG_param* amg);
 
@@ -100,7 +105,9 @@ struct Handle {
   Krylov kry;
   int reuse_hierarchy = 0;
   int timing_detail = 0;
+  SolverConfig last_cfg;
   Stats stats;
+  Workspace ws;                 // AMG setup temporaries
   // scratch for reductions
   DevBuf<double> red;
   double* h_red = nullptr;      // pinned

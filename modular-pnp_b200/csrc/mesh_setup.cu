@@ -10,6 +10,7 @@
 namespace pnpb200 {
 
 thread_local long g_launches = 0;
+int g_debug_sync = getenv("PNPB200_DEBUG_SYNC") ? atoi(getenv("PNPB200_DEBUG_SYNC")) : 0;
 
 namespace {
 

@@ -298,7 +298,7 @@ void orc_default_param(orc_solver_param* p)
   p->max_levels = 20; p->coarse_dof = 100;
   p->strong_coupled = 0.08; p->max_aggregation = 20; p->tentative_smooth = 0.67;
   p->amg_tol = 1e-6; p->presmooth = 1; p->postsmooth = 1; p->print_level = 0;
-  p->coarse_dense = 0; p->ortho_cgs = 0;
+  p->coarse_dense = 0; p->ortho_cgs = 0; p->cycle_type = 1; p->kcycle_levels = 2;
 }
 
 void orc_bsr_spmv(int n, const int* IA, const int* JA, const double* val, double alpha,
@@ -404,48 +404,82 @@ void orc_amg_level_agg(const orc_amg* h, int l, int* agg)
 
 void orc_amg_free(orc_amg* h) { delete h; }
 
-// fasp_precond_dbsr_amg + fasp_solver_mgcycle_bsr [EXT]: one V-cycle from a zero guess
+// fasp_precond_dbsr_amg + fasp_solver_mgcycle_bsr [EXT]: one cycle from a zero guess.
+// cycle_type 1 = V-cycle (bsr.dat). Any other value = K-cycle (FASP's nonlinear AMLI cycle in
+// Notay's two-step GCR form) on coarse levels 1..kcycle_levels — the mirror of the CUDA path.
+static void solve_level(orc_amg* h, int l, const std::vector<double>& b, std::vector<double>& x);
+
+static void mg_cycle(orc_amg* h, int l, const std::vector<double>& b, std::vector<double>& x)
+{
+  const orc_solver_param& p = h->p;
+  Level& L = h->lv[l];
+  Level& C = h->lv[l + 1];
+  auto smooth = [&](bool reverse) {
+    bsr_gs(L.A.ROW, L.A.IA.data(), L.A.JA.data(), L.A.val.data(), L.dinv.data(), b.data(), x.data(),
+           L.order.empty() ? nullptr : L.order.data(), (int)L.order.size(), reverse);
+  };
+  std::fill(x.begin(), x.end(), 0.0);
+  for (int s = 0; s < p.presmooth; ++s) smooth(false);
+  L.w = b;
+  bsr_spmv(L.A.ROW, L.A.IA.data(), L.A.JA.data(), L.A.val.data(), -1.0, x.data(), 1.0, L.w.data());
+  std::fill(C.b.begin(), C.b.end(), 0.0);
+  for (int i = 0; i < L.A.ROW; ++i)
+    if (L.agg[i] >= 0) for (int k = 0; k < 3; ++k) C.b[3 * (size_t)L.agg[i] + k] += L.w[3 * (size_t)i + k];
+  solve_level(h, l + 1, C.b, C.x);
+  for (int i = 0; i < L.A.ROW; ++i)
+    if (L.agg[i] >= 0) for (int k = 0; k < 3; ++k) x[3 * (size_t)i + k] += C.x[3 * (size_t)L.agg[i] + k];
+  for (int s = 0; s < p.postsmooth; ++s) smooth(true);
+}
+
+static void solve_level(orc_amg* h, int l, const std::vector<double>& b, std::vector<double>& x)
+{
+  const orc_solver_param& p = h->p;
+  const int nl = (int)h->lv.size();
+  Level& L = h->lv[l];
+  if (l == nl - 1) {
+    if (p.coarse_dense) h->lu.solve(b.data(), x.data());
+    else {
+      const int n = 3 * L.A.ROW;
+      std::fill(x.begin(), x.end(), 0.0);
+      coarse_gmres(L.A, b.data(), x.data(), p.amg_tol, std::min(n * n, 200), 25);
+    }
+    return;
+  }
+  const bool kcyc = p.cycle_type != 1 && p.cycle_type != 0 && l <= p.kcycle_levels;
+  if (!kcyc) { mg_cycle(h, l, b, x); return; }
+  const size_t m = 3 * (size_t)L.A.ROW;
+  std::vector<double> c(m), v(m), rt(m), d(m), w(m);
+  auto dot = [&](const std::vector<double>& a, const std::vector<double>& bb) { double t = 0; for (size_t i = 0; i < m; ++i) t += a[i] * bb[i]; return t; };
+  mg_cycle(h, l, b, c);
+  bsr_spmv(L.A.ROW, L.A.IA.data(), L.A.JA.data(), L.A.val.data(), 1.0, c.data(), 0.0, v.data());
+  const double al1 = dot(v, b), r1 = dot(v, v);
+  const double a1 = r1 != 0.0 ? al1 / r1 : 0.0;
+  for (size_t i = 0; i < m; ++i) rt[i] = b[i] - a1 * v[i];
+  mg_cycle(h, l, rt, d);
+  bsr_spmv(L.A.ROW, L.A.IA.data(), L.A.JA.data(), L.A.val.data(), 1.0, d.data(), 0.0, w.data());
+  const double g = dot(w, v), be = dot(w, w), al2 = dot(w, rt);
+  const double r2 = r1 != 0.0 ? be - g * g / r1 : 0.0;
+  double k1 = a1, k2 = 0.0;
+  if (r2 > 0.0 && r1 != 0.0) { k2 = al2 / r2; k1 = a1 - g * k2 / r1; }
+  for (size_t i = 0; i < m; ++i) x[i] = k1 * c[i] + k2 * d[i];
+}
+
 void orc_amg_vcycle(orc_amg* h, const double* r, double* z)
 {
   const int nl = (int)h->lv.size();
   const orc_solver_param& p = h->p;
-  std::copy(r, r + 3 * (size_t)h->lv[0].A.ROW, h->lv[0].b.begin());
-  std::fill(h->lv[0].x.begin(), h->lv[0].x.end(), 0.0);
-  auto smooth = [&](Level& L, bool reverse) {
-    bsr_gs(L.A.ROW, L.A.IA.data(), L.A.JA.data(), L.A.val.data(), L.dinv.data(), L.b.data(), L.x.data(),
-           L.order.empty() ? nullptr : L.order.data(), (int)L.order.size(), reverse);
-  };
-  int l = 0;
-  while (l < nl - 1) {
-    Level& L = h->lv[l];
-    for (int s = 0; s < p.presmooth; ++s) smooth(L, false);
-    L.w = L.b;
-    bsr_spmv(L.A.ROW, L.A.IA.data(), L.A.JA.data(), L.A.val.data(), -1.0, L.x.data(), 1.0, L.w.data());
-    Level& C = h->lv[l + 1];
-    std::fill(C.b.begin(), C.b.end(), 0.0);
-    for (int i = 0; i < L.A.ROW; ++i)
-      if (L.agg[i] >= 0) for (int k = 0; k < 3; ++k) C.b[3 * (size_t)L.agg[i] + k] += L.w[3 * (size_t)i + k];
-    ++l;
-    std::fill(h->lv[l].x.begin(), h->lv[l].x.end(), 0.0);
+  Level& F = h->lv[0];
+  std::copy(r, r + 3 * (size_t)F.A.ROW, F.b.begin());
+  if (nl == 1) {   // degenerate: single level, smoothing only
+    std::fill(F.x.begin(), F.x.end(), 0.0);
+    for (int s = 0; s < p.presmooth; ++s)
+      bsr_gs(F.A.ROW, F.A.IA.data(), F.A.JA.data(), F.A.val.data(), F.dinv.data(), F.b.data(), F.x.data(),
+             F.order.empty() ? nullptr : F.order.data(), (int)F.order.size(), false);
+  } else {
+    std::vector<double> bb(F.b);
+    mg_cycle(h, 0, bb, F.x);
   }
-  {
-    Level& C = h->lv[nl - 1];
-    if (nl == 1) { for (int s = 0; s < p.presmooth; ++s) smooth(C, false); }   // degenerate: single level
-    else if (p.coarse_dense) h->lu.solve(C.b.data(), C.x.data());
-    else {
-      const int n = 3 * C.A.ROW;
-      coarse_gmres(C.A, C.b.data(), C.x.data(), p.amg_tol, std::min(n * n, 200), 25);
-    }
-  }
-  while (l > 0) {
-    --l;
-    Level& L = h->lv[l];
-    const Level& C = h->lv[l + 1];
-    for (int i = 0; i < L.A.ROW; ++i)
-      if (L.agg[i] >= 0) for (int k = 0; k < 3; ++k) L.x[3 * (size_t)i + k] += C.x[3 * (size_t)L.agg[i] + k];
-    for (int s = 0; s < p.postsmooth; ++s) smooth(L, true);
-  }
-  std::copy(h->lv[0].x.begin(), h->lv[0].x.end(), z);
+  std::copy(F.x.begin(), F.x.end(), z);
 }
 
 // fasp_solver_dbsr_pvfgmres restated [EXT]
@@ -495,7 +529,7 @@ int orc_pvfgmres(int nrow, const int* IA, const int* JA, const double* val, cons
         std::vector<double> hcol(i);
         for (int j = 0; j < i; ++j) hcol[j] = dotp(pv[j], pv[i]);
         for (int j = 0; j < i; ++j) for (int k = 0; k < n; ++k) pv[i][k] -= hcol[j] * pv[j][k];
-        if (nrm2(pv[i]) < 0.7071067811865476 * before) {
+        if (nrm2(pv[i]) < 0.1 * before) {
           std::vector<double> h2(i);
           for (int j = 0; j < i; ++j) h2[j] = dotp(pv[j], pv[i]);
           for (int j = 0; j < i; ++j) { for (int k = 0; k < n; ++k) pv[i][k] -= h2[j] * pv[j][k]; hcol[j] += h2[j]; }

@@ -23,7 +23,7 @@ class SolverParam(C.Structure):
                 ("strong_coupled", C.c_double), ("max_aggregation", C.c_int),
                 ("tentative_smooth", C.c_double), ("amg_tol", C.c_double),
                 ("presmooth", C.c_int), ("postsmooth", C.c_int), ("print_level", C.c_int),
-                ("coarse_dense", C.c_int), ("ortho_cgs", C.c_int)]
+                ("coarse_dense", C.c_int), ("ortho_cgs", C.c_int), ("cycle_type", C.c_int), ("kcycle_levels", C.c_int)]
 
 
 class NewtonResult(C.Structure):

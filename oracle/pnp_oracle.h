@@ -107,6 +107,8 @@ typedef struct {
   /* mirror mode (to replay the GPU's hierarchy on the CPU): */
   int    coarse_dense;   /* 1: dense LU on the coarsest level instead of GMRES(25) */
   int    ortho_cgs;      /* 1: classical Gram-Schmidt with DGKS re-orthogonalisation (GPU Krylov) */
+  int    cycle_type;     /* 1 V-cycle (bsr.dat); else K-cycle (nonlinear AMLI) on coarse levels 1..kcycle_levels */
+  int    kcycle_levels;
 } orc_solver_param;
 void orc_default_param(orc_solver_param* p); /* benchmarks/pnp_exact_solution/bsr.dat */
 

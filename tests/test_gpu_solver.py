@@ -45,9 +45,10 @@ def test_fasp_blas_and_format(oracle, pkg, system):
     assert np.array_equal(bIA, IA) and np.array_equal(bJA, JA) and np.array_equal(bval, val)
 
 
-def test_solve_hierarchy_and_vcycle(oracle, pkg, system):
+@pytest.mark.parametrize("cycle", [1, 4])      # V_CYCLE (bsr.dat) and NL_AMLI (K-cycle)
+def test_solve_hierarchy_and_vcycle(oracle, pkg, system, cycle):
     P, g, IA, JA, val, b = system
-    it, amg = pkg.default_params()
+    it, amg = pkg.default_params(cycle_type=cycle)
     its = g.solve(it, amg)
     assert its > 0, "solver status %d" % its
     du = g.get_update()
@@ -74,7 +75,7 @@ def test_solve_hierarchy_and_vcycle(oracle, pkg, system):
             assert np.abs(cval - gval).max() <= 1e-13 * np.abs(cval).max()
             aggs.append(agg); naggs.append(na)
     # one V-cycle: GPU vs oracle replaying the same hierarchy
-    prm = oracle.default_param(coarse_dense=1, ortho_cgs=1)
+    prm = oracle.default_param(coarse_dense=1, ortho_cgs=1, cycle_type=cycle, kcycle_levels=2)
     H = oracle.AMG(IA, JA, val, prm, ext_agg=aggs, ext_nagg=naggs, ext_order=orders)
     assert H.nlevels() == nl
     rr = np.random.default_rng(9).uniform(-1, 1, P.N)
