@@ -137,7 +137,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("PNPB200_BENCH_N", "256")))
     ap.add_argument("--cpu-sample-n", type=int, default=48)
-    ap.add_argument("--cycle", default=os.environ.get("PNPB200_BENCH_CYCLE", "V"))
+    ap.add_argument("--cycle", default=os.environ.get("PNPB200_BENCH_CYCLE", "NA"),
+                    help="AMG_cycle_type: V (bsr.dat) or NA (FASP nonlinear AMLI = K-cycle; needed above ~20 M dof where V exceeds itsolver_maxit)")
+    ap.add_argument("--profile", action="store_true",
+                    help="short run for ncu: 1 warm-up + 1 timed step, no e2e / cpu_baseline / probe legs")
     ap.add_argument("--maxit", type=int, default=int(os.environ.get("PNPB200_BENCH_MAXIT", "100")))
     args = ap.parse_args()
 
@@ -232,6 +235,8 @@ def main():
         return ms, launches, its, last
 
     W, K = max(args.warmup, 3), max(args.steps, 1)
+    if args.profile:
+        W, K = 1, 1
     for _ in range(W):
         step_resident()
     sampler = ClockSampler(dev)
@@ -239,6 +244,12 @@ def main():
         sampler.start()
     ms, launches, its, last = timed(step_resident, K)
     clocks = sampler.stop() if rank == 0 else None
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / K, "krylov_its": its, "gpu_launches": launches,
+                              "config": config}))
+        g.close()
+        return 0
     step_e2e()
     ms_e2e, _, _, _ = timed(step_e2e, K)
     stats = g.stats()

@@ -1,0 +1,57 @@
+"""Generates tests/golden/element_kernels.npz from the REFERENCE's own compiled element kernels
+(oracle/_ref/libpnpref.so, built by oracle/Makefile from /root/reference/include/EAFE.h and
+benchmarks/pnp_exact_solution/vector_linear_pnp_forms.h). Run in the authoring container only
+(needs /root/reference); the vectors travel with the repo.
+    python tests/golden/make_golden.py
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+
+def main():
+    ref = C.CDLL(O.REF_PATH)
+    f8 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    ref.ref_eafe_tabulate.argtypes = [f8] * 6
+    ref.ref_jac_tabulate.argtypes = [f8] * 6
+    ref.ref_res_tabulate.argtypes = [f8] * 8
+    rng = np.random.default_rng(1234)
+    n = 64
+    X = np.zeros((n, 12)); UU = np.zeros((n, 12)); EPS = np.zeros((n, 4)); D = np.zeros((n, 12)); Q = np.zeros((n, 12))
+    FC = np.zeros((n, 4)); RE = np.zeros((n, 12)); ETA = np.zeros((n, 4)); AL = np.zeros((n, 4)); BE = np.zeros((n, 4)); GA = np.zeros((n, 4))
+    A_eafe = np.zeros((n, 16)); A_jac = np.zeros((n, 144)); b_res = np.zeros((n, 12))
+    base = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1.0])
+    for t in range(n):
+        X[t] = (base + 0.2 * rng.uniform(-1, 1, 12)) * rng.uniform(0.01, 2.0)
+        UU[t] = rng.uniform(-1, 1, 12); EPS[t] = rng.uniform(0.5, 2, 4); D[t] = rng.uniform(0.1, 2, 12)
+        Q[t] = rng.uniform(-2, 2, 12); FC[t] = rng.uniform(-1, 1, 4); RE[t] = rng.uniform(-1, 1, 12)
+        ETA[t] = rng.uniform(-1, 1, 4); AL[t] = rng.uniform(0.1, 2, 4); GA[t] = rng.uniform(0, 1, 4)
+        # potentials on a 1/64 lattice: every edge difference is 0 or >= 1/64 (well-conditioned Bernoulli)
+        BE[t] = ETA[t] + np.round(rng.uniform(-3, 3, 4) * 64) / 64
+        if t % 8 == 0:
+            BE[t, 1] = BE[t, 0] + (ETA[t, 1] - ETA[t, 0])      # an exactly-zero edge difference: |d| < DOLFIN_EPS branch
+        ref.ref_eafe_tabulate(A_eafe[t], ETA[t], AL[t], BE[t], GA[t], X[t])
+        ref.ref_jac_tabulate(A_jac[t], UU[t], EPS[t], D[t], Q[t], X[t])
+        ref.ref_res_tabulate(b_res[t], UU[t], EPS[t], FC[t], D[t], Q[t], RE[t], X[t])
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "element_kernels.npz"), X=X, UU=UU, EPS=EPS, D=D, Q=Q, FC=FC,
+                        RE=RE, ETA=ETA, AL=AL, BE=BE, GA=GA, A_eafe=A_eafe, A_jac=A_jac, b_res=b_res)
+    # global fixture: the oracle assembler DRIVEN BY THE REFERENCE KERNELS on a 4x2x2 box
+    O.use_ref_kernels(True)
+    P = O.Problem(4, 2, 2)
+    uu = P.exact + 0.1 * np.random.default_rng(1234).uniform(-1, 1, P.N)
+    uu[0::3] = np.round(uu[0::3] * 64) / 64
+    A, b = P.assemble(uu, use_eafe=True)
+    A2, _ = P.assemble(uu, use_eafe=False)
+    O.use_ref_kernels(False)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "assembled_4x2x2.npz"), uu=uu, IA=P.IA, JA=P.JA, A_eafe=A, A_galerkin=A2, b=b)
+    print("golden vectors written")
+
+
+if __name__ == "__main__":
+    main()
