@@ -149,3 +149,15 @@ def test_newton_exact_solution_config(oracle, pkg, gpu_lib):
     for k in range(min(4, len(hist))):
         assert abs(hist[k][1] - res.rel_res[k]) <= 1e-3 * res.rel_res[k]
     assert np.abs(uu - uu_ref).max() <= 1e-5
+
+
+def test_host_driver_binary(gpu_lib):
+    """the C++ host-side mirror of main.cpp (modular-pnp_b200/host/) runs the reference config
+    through the C ABI: 8 Newton steps like the oracle, converged."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "modular-pnp_b200", "host", "pnp_exact_solution")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("NEWTON_ITERATIONS")][0].split()
+    assert int(line[1]) == 8 and int(line[3]) == 1 and float(line[5]) < 1e-8
