@@ -255,24 +255,31 @@ def main():
     stats = g.stats()
     kits = its[-1]
 
-    # roofline of the dominant kernel (fine-level BSR SpMV: Krylov matvec + every V-cycle residual)
+    # roofline of the dominant kernel. profiles/README.md (ncu launch list): the multicolour
+    # Gauss-Seidel sweep (bsrt_row_kernel<2>, one launch per colour) is ~2/3 of the device time,
+    # the SpMV/residual pass (bsrt_row_kernel<0/1>) ~1/4. One "launch" of the roofline line = one
+    # full sweep over the fine-level matrix (all colour launches), timed live with CUDA events.
     peak, peak_src = peaks()
-    probe_ms, probe_bytes = g.probe_kernel(0, 20)
+    spmv_ms, spmv_bytes = g.probe_kernel(0, 20)
     gs_ms, gs_bytes = g.probe_kernel(2, 10)
-    achieved = probe_bytes / probe_ms / 1e6
+    achieved = gs_bytes / gs_ms / 1e6
     b_step = byte_model(stats, nv, nc, kits if kits > 0 else stats.krylov_its, it.restart)
     step_gbs = b_step / (ms / K) / 1e6
-    # traffic: dram bytes of one bsrt_spmv_kernel<0> launch from the committed ncu capture, if any
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")
+    # traffic: dram bytes of one sweep from the committed ncu capture (only taken at n = 128: ncu
+    # cannot save/restore the 100 GB working set of the 256^3 run)
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic_n128.json")
     if os.path.exists(tp):
         try:
             with open(tp) as f:
                 tj = json.load(f)
+            ratio = tj["gs_sweep"]["dram_bytes_per_sweep"] / tj["gs_sweep"]["algorithmic_bytes"]
+            traffic_note = "ncu at n=128: %.3g B dram per sweep = %.2fx algorithmic (x re-read once per colour, partial sectors)" % (
+                tj["gs_sweep"]["dram_bytes_per_sweep"], ratio)
             if tj.get("n") == n:
-                traffic = tj.get("dram_bytes_per_launch")
+                traffic = tj["gs_sweep"]["dram_bytes_per_sweep"]
         except Exception:
-            traffic = None
+            pass
 
     if rank == 0:
         value = world * K / (ms / 1e3)
@@ -288,10 +295,12 @@ def main():
                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": 3 * nv * 8, "d2h_bytes_per_step": 3 * nv * 8},
                "gpu_launches": launches,
                "clocks": clocks,
-               "roofline": {"bound": "hbm", "kernel": "bsrt_spmv_kernel<0> (fine level)", "achieved": achieved, "peak": peak,
-                            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                            "algorithmic_bytes_per_launch": probe_bytes, "ms_per_launch": probe_ms,
-                            "gs_sweep": {"achieved": gs_bytes / gs_ms / 1e6, "frac": gs_bytes / gs_ms / 1e6 / peak, "ms": gs_ms},
+               "roofline": {"bound": "hbm", "kernel": "bsrt_row_kernel<2>: one multicolour Gauss-Seidel sweep of the fine level (%d colour launches)" % stats.level_colors[0],
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "traffic_note": traffic_note, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": gs_bytes, "ms_per_launch": gs_ms,
+                            "spmv": {"kernel": "bsrt_row_kernel<0> (y = A x, fine level)", "achieved": spmv_bytes / spmv_ms / 1e6,
+                                     "frac": spmv_bytes / spmv_ms / 1e6 / peak, "ms": spmv_ms, "algorithmic_bytes": spmv_bytes},
                             "whole_step": {"algorithmic_bytes": b_step, "achieved": step_gbs, "frac": step_gbs / peak}}}
         # CPU baseline on the box's host cores (bounded sample), N=1 only
         if world == 1:

@@ -21,12 +21,12 @@ namespace {
 
 typedef unsigned long long u64;
 
-__global__ void condense_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ brow,
-                                const double* __restrict__ val, double* __restrict__ pp)
+__global__ void condense_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ rs,
+                                const int* __restrict__ brow, const double* __restrict__ val, double* __restrict__ pp)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nnzb) return;
-  const int i = brow[b], s = ia[i], len = ia[i + 1] - s;
+  const int i = brow[b], s = rs[i], len = ia[i + 1] - ia[i];
   const double* v = val + 9 * (size_t)s + (b - s);
   double m = 0.0;
 #pragma unroll
@@ -35,13 +35,13 @@ __global__ void condense_kernel(int nnzb, const int* __restrict__ ia, const int*
   pp[b] = m;
 }
 
-__global__ void isolated_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
-                                const double* __restrict__ pp, unsigned char* __restrict__ iso)
+__global__ void isolated_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                                const int* __restrict__ ja, const double* __restrict__ pp, unsigned char* __restrict__ iso)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   bool any = false;
-  for (int p = ia[i]; p < ia[i + 1]; ++p) if (ja[p] != i && pp[p] != 0.0) { any = true; break; }
+  for (int p = rs[i], e = rs[i] + ia[i + 1] - ia[i]; p < e; ++p) if (ja[p] != i && pp[p] != 0.0) { any = true; break; }
   iso[i] = any ? 0 : 1;
 }
 
@@ -66,15 +66,15 @@ __global__ void strength_kernel(int nnzb, const int* __restrict__ ja, const int*
 
 // a non-isolated row without any strong neighbour keeps its largest coupling (select, then
 // apply, so the outcome does not depend on thread timing)
-__global__ void force_select_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
-                                    const double* __restrict__ pp, const unsigned char* __restrict__ iso,
+__global__ void force_select_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                                    const int* __restrict__ ja, const double* __restrict__ pp, const unsigned char* __restrict__ iso,
                                     const unsigned char* __restrict__ strong, int* __restrict__ sel)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int best = -1; double bv = 0.0;
   if (!iso[i])
-    for (int p = ia[i]; p < ia[i + 1]; ++p) {
+    for (int p = rs[i], e = rs[i] + ia[i + 1] - ia[i]; p < e; ++p) {
       if (strong[p]) { best = -1; break; }
       const int j = ja[p];
       if (j == i || iso[j]) continue;
@@ -105,8 +105,8 @@ __global__ void mis_init_kernel(int n, const unsigned char* __restrict__ iso, in
 }
 
 template <bool FIRST>
-__global__ void mis_prop_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
-                                const unsigned char* __restrict__ strong, const int* __restrict__ state,
+__global__ void mis_prop_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                                const int* __restrict__ ja, const unsigned char* __restrict__ strong, const int* __restrict__ state,
                                 const u64* __restrict__ tin, u64* __restrict__ tout)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,7 +117,7 @@ __global__ void mis_prop_kernel(int n, const int* __restrict__ ia, const int* __
     return mis_key(st == 1 ? 2 : st == 0 ? 1 : 0, j);
   };
   u64 m = key(i);
-  for (int p = ia[i]; p < ia[i + 1]; ++p)
+  for (int p = rs[i], e = rs[i] + ia[i + 1] - ia[i]; p < e; ++p)
     if (strong[p]) { const u64 k = key(ja[p]); m = k > m ? k : m; }
   tout[i] = m;
 }
@@ -150,8 +150,8 @@ __global__ void agg_root_kernel(int n, const int* __restrict__ state, const int*
   agg[i] = state[i] == 1 ? rootid[i] : (iso[i] ? -1 : -2);
 }
 
-__global__ void agg_join_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
-                                const unsigned char* __restrict__ strong, const double* __restrict__ pp,
+__global__ void agg_join_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                                const int* __restrict__ ja, const unsigned char* __restrict__ strong, const double* __restrict__ pp,
                                 const int* __restrict__ agg_in, int* __restrict__ agg_out, int* __restrict__ left)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,7 +159,7 @@ __global__ void agg_join_kernel(int n, const int* __restrict__ ia, const int* __
   int a = agg_in[i];
   if (a == -2) {
     double bv = -1.0;
-    for (int p = ia[i]; p < ia[i + 1]; ++p) {
+    for (int p = rs[i], e = rs[i] + ia[i + 1] - ia[i]; p < e; ++p) {
       if (!strong[p]) continue;
       const int aj = agg_in[ja[p]];
       if (aj >= 0 && pp[p] > bv) { bv = pp[p]; a = aj; }
@@ -215,7 +215,8 @@ __global__ void rap_head_kernel(int nnzb, const u64* __restrict__ key, int* __re
 
 __global__ void rap_structure_kernel(int nnzb, const u64* __restrict__ key, const int* __restrict__ head,
                                      const int* __restrict__ slot, u64 nagg, int* __restrict__ cja,
-                                     int* __restrict__ seg, int* __restrict__ rowcnt, int* __restrict__ nvalid)
+                                     int* __restrict__ crow, int* __restrict__ seg, int* __restrict__ rowcnt,
+                                     int* __restrict__ nvalid)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nnzb) return;
@@ -225,26 +226,40 @@ __global__ void rap_structure_kernel(int nnzb, const u64* __restrict__ key, cons
   if (head[p]) {
     const int s = slot[p];
     cja[s] = (int)(k % nagg);
+    crow[s] = (int)(k / nagg);
     seg[s] = p;
     atomicAdd(&rowcnt[(int)(k / nagg)], 1);
   }
 }
 
-__global__ void rap_numeric_kernel(int cnnzb, const int* __restrict__ cia, const int* __restrict__ cbrow,
-                                   const int* __restrict__ seg, const int* __restrict__ perm,
-                                   const int* __restrict__ fia, const int* __restrict__ fbrow,
-                                   const double* __restrict__ fval, double* __restrict__ cval)
+// natural coarse block s (row I) -> physical block crs[I] + (s - cia[I]); its fine segment
+__global__ void rap_remap_kernel(int cnnzb, const int* __restrict__ crow, const int* __restrict__ cia,
+                                 const int* __restrict__ crs, const int* __restrict__ seg,
+                                 int* __restrict__ beg, int* __restrict__ end)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cnnzb) return;
+  const int I = crow[s], b = crs[I] + (s - cia[I]);
+  beg[b] = seg[s]; end[b] = seg[s + 1];
+}
+
+__global__ void rap_numeric_kernel(int cnnzb, const int* __restrict__ cia, const int* __restrict__ crs,
+                                   const int* __restrict__ cbrow, const int* __restrict__ beg,
+                                   const int* __restrict__ end, const int* __restrict__ perm,
+                                   const int* __restrict__ fia, const int* __restrict__ frs,
+                                   const int* __restrict__ fbrow, const double* __restrict__ fval,
+                                   double* __restrict__ cval)
 {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 9 * (size_t)cnnzb) return;
-  const int s = (int)(e / 9), t = (int)(e % 9);
+  const int s = (int)(e / 9), t = (int)(e % 9);          // s = physical coarse block
   double acc = 0.0;
-  for (int p = seg[s]; p < seg[s + 1]; ++p) {
+  for (int p = beg[s]; p < end[s]; ++p) {
     const int b = perm[p];
-    const int i = fbrow[b], fs = fia[i], flen = fia[i + 1] - fs;
+    const int i = fbrow[b], fs = frs[i], flen = fia[i + 1] - fia[i];
     acc += fval[9 * (size_t)fs + (size_t)t * flen + (b - fs)];
   }
-  const int I = cbrow[s], cs = cia[I], clen = cia[I + 1] - cs;
+  const int I = cbrow[s], cs = crs[I], clen = cia[I + 1] - cia[I];
   cval[9 * (size_t)cs + (size_t)t * clen + (s - cs)] = acc;
 }
 
@@ -270,14 +285,14 @@ __global__ void prolong_kernel(int n, const int* __restrict__ agg, const double*
 }
 
 // ---- coarsest level: dense inverse -------------------------------------------------------------
-__global__ void dense_fill_kernel(int nnzb, int nd, const int* __restrict__ ia, const int* __restrict__ ja,
-                                  const int* __restrict__ brow, const double* __restrict__ val,
+__global__ void dense_fill_kernel(int nnzb, int nd, const int* __restrict__ ia, const int* __restrict__ rs,
+                                  const int* __restrict__ ja, const int* __restrict__ brow, const double* __restrict__ val,
                                   double* __restrict__ D)
 {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 9 * (size_t)nnzb) return;
   const int b = (int)(e / 9), t = (int)(e % 9);
-  const int i = brow[b], s = ia[i], len = ia[i + 1] - s;
+  const int i = brow[b], s = rs[i], len = ia[i + 1] - ia[i];
   D[(size_t)(3 * i + t / 3) * nd + 3 * ja[b] + t % 3] = val[9 * (size_t)s + (size_t)t * len + (b - s)];
 }
 
@@ -446,21 +461,21 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   const int n = A.n, nnzb = A.nnzb;
   // all large temporaries of this coarsening step live in the handle's workspace
   Workspace& ws = h.ws;
-  ws.reserve((size_t)nnzb * 56 + (size_t)n * 64 + (64u << 20), s);
+  ws.reserve((size_t)nnzb * 60 + (size_t)n * 96 + (64u << 20), s);
   ws.reset();
   struct P1 { double* p; } pp; struct P2 { unsigned char* p; } iso, strong; struct P3 { int* p; void zero(cudaStream_t st) { cudaMemsetAsync(p, 0, sizeof(int), st); } } state, cnt;
   struct P4 { u64* p; } t1, t2;
   {
   PHASE("strength");
   pp.p = ws.get<double>(nnzb);
-  condense_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ia.p, A.brow.p, A.val.p, pp.p); PNP_COUNT_LAUNCH();
+  condense_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ia.p, A.rs.p, A.brow.p, A.val.p, pp.p); PNP_COUNT_LAUNCH();
   iso.p = ws.get<unsigned char>(n); strong.p = ws.get<unsigned char>(nnzb);
-  isolated_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, pp.p, iso.p); PNP_COUNT_LAUNCH();
+  isolated_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, pp.p, iso.p); PNP_COUNT_LAUNCH();
   strength_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, A.dslot.p, A.tslot.p, pp.p, iso.p,
                                                  theta * theta, strong.p); PNP_COUNT_LAUNCH();
   {
     struct { int* p; } sel; sel.p = ws.get<int>(n);
-    force_select_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, pp.p, iso.p, strong.p, sel.p); PNP_COUNT_LAUNCH();
+    force_select_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, pp.p, iso.p, strong.p, sel.p); PNP_COUNT_LAUNCH();
     force_apply_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.tslot.p, sel.p, strong.p); PNP_COUNT_LAUNCH();
   }
   }
@@ -474,8 +489,8 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   int und = 1;
   while (und > 0) {
     cnt.zero(s);
-    mis_prop_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, strong.p, state.p, nullptr, t1.p); PNP_COUNT_LAUNCH();
-    mis_prop_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, strong.p, state.p, t1.p, t2.p); PNP_COUNT_LAUNCH();
+    mis_prop_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, strong.p, state.p, nullptr, t1.p); PNP_COUNT_LAUNCH();
+    mis_prop_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, strong.p, state.p, t1.p, t2.p); PNP_COUNT_LAUNCH();
     mis_decide_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, t2.p, state.p, cnt.p); PNP_COUNT_LAUNCH();
     PNP_CUDA(cudaMemcpyAsync(&und, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     PNP_CUDA(cudaStreamSynchronize(s));
@@ -497,7 +512,7 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   int left = 1; int* cur = L.agg.p; int* nxt = agg2.p;
   for (int pass = 0; pass < 8 && left > 0; ++pass) {
     cnt.zero(s);
-    agg_join_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, strong.p, pp.p, cur, nxt, cnt.p); PNP_COUNT_LAUNCH();
+    agg_join_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, strong.p, pp.p, cur, nxt, cnt.p); PNP_COUNT_LAUNCH();
     PNP_CUDA(cudaMemcpyAsync(&left, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     PNP_CUDA(cudaStreamSynchronize(s));
     std::swap(cur, nxt);
@@ -532,15 +547,19 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
     PNP_CUDA(cudaStreamSynchronize(s));
     BsrT& Ac = C.A;
     Ac.n = nagg; Ac.nnzb = cnnzb;
-    Ac.ja.alloc(cnnzb, s); Ac.ia.alloc(nagg + 1, s); Ac.val.alloc(9 * (size_t)cnnzb, s);
-    L.rap_seg.alloc(cnnzb + 1, s);
+    Ac.ia.alloc(nagg + 1, s); Ac.val.alloc(9 * (size_t)cnnzb, s);
+    struct { int* p; } cja_nat, crow, seg; cja_nat.p = ws.get<int>(cnnzb); crow.p = ws.get<int>(cnnzb); seg.p = ws.get<int>(cnnzb + 1);
+    L.rap_beg.alloc(cnnzb, s); L.rap_end.alloc(cnnzb, s);
     struct { int* p; } rowcnt; rowcnt.p = ws.get<int>(nagg + 1);
     PNP_CUDA(cudaMemsetAsync(rowcnt.p, 0, (size_t)(nagg + 1) * sizeof(int), s));
-    int* nvalid = L.rap_seg.p + cnnzb;
-    rap_structure_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, kout.p, head.p, slot.p, (u64)nagg, Ac.ja.p, L.rap_seg.p,
+    int* nvalid = seg.p + cnnzb;
+    rap_structure_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, kout.p, head.p, slot.p, (u64)nagg, cja_nat.p, crow.p, seg.p,
                                                         rowcnt.p, nvalid); PNP_COUNT_LAUNCH();
     exclusive_scan_int(rowcnt.p, Ac.ia.p, nagg + 1, s);
-    finish_pattern_tables(Ac, s);
+    // colour the coarse graph and store it colour by colour, then re-key the numeric map
+    color_and_layout(C, cja_nat.p, &ws, s);
+    rap_remap_kernel<<<cdiv(cnnzb, 256), 256, 0, s>>>(cnnzb, crow.p, Ac.ia.p, Ac.rs.p, seg.p, L.rap_beg.p, L.rap_end.p);
+    PNP_COUNT_LAUNCH();
   }
   return true;
 }
@@ -549,8 +568,8 @@ void rap_numeric(Handle& h, Level& L, Level& C)
 {
   cudaStream_t s = h.stream;
   BsrT& A = L.A; BsrT& Ac = C.A;
-  rap_numeric_kernel<<<cdiv(9 * (size_t)Ac.nnzb, 256), 256, 0, s>>>(Ac.nnzb, Ac.ia.p, Ac.brow.p, L.rap_seg.p, L.rap_perm.p,
-                                                                   A.ia.p, A.brow.p, A.val.p, Ac.val.p);
+  rap_numeric_kernel<<<cdiv(9 * (size_t)Ac.nnzb, 256), 256, 0, s>>>(Ac.nnzb, Ac.ia.p, Ac.rs.p, Ac.brow.p, L.rap_beg.p, L.rap_end.p,
+                                                                   L.rap_perm.p, A.ia.p, A.rs.p, A.brow.p, A.val.p, Ac.val.p);
   PNP_COUNT_LAUNCH();
 }
 
@@ -591,7 +610,7 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
   auto& lv = h.hier.lv;
   Level& F = *lv[0];
   const bool reuse = h.reuse_hierarchy && h.hier.symbolic_valid;
-  if (F.ncolors == 0) color_level(F, s);           // pattern-only: survives across solves
+  if (F.ncolors == 0) throw Error(ERROR_DATA_STRUCTURE, "fine level not coloured");   // done at create / upload
   alloc_level_vectors(F, s);
   if (!reuse) h.hier.symbolic_valid = false;
   const int min_cdof = cfg.coarse_dof > 50 ? cfg.coarse_dof : 50;
@@ -613,7 +632,6 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
     if (!coarsen_symbolic(h, L, C, theta)) break;
     { PHASE("rap_numeric"); rap_numeric(h, L, C); }
     alloc_level_vectors(C, s);
-    { PHASE("colour"); color_level(C, s); }
     ++l;
   }
   if (!reuse) lv.resize(l + 1);
@@ -626,7 +644,7 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
   D.alloc((size_t)nd * nd, s); colk.alloc(nd, s); sing.alloc(1, s); sing.zero();
   h.hier.dense_inv.alloc((size_t)nd * nd, s);
   D.zero();
-  dense_fill_kernel<<<cdiv(9 * (size_t)Z.A.nnzb, 256), 256, 0, s>>>(Z.A.nnzb, nd, Z.A.ia.p, Z.A.ja.p, Z.A.brow.p, Z.A.val.p, D.p);
+  dense_fill_kernel<<<cdiv(9 * (size_t)Z.A.nnzb, 256), 256, 0, s>>>(Z.A.nnzb, nd, Z.A.ia.p, Z.A.rs.p, Z.A.ja.p, Z.A.brow.p, Z.A.val.p, D.p);
   PNP_COUNT_LAUNCH();
   identity_kernel<<<cdiv((size_t)nd * nd, 256), 256, 0, s>>>(nd, h.hier.dense_inv.p); PNP_COUNT_LAUNCH();
   dense_invert_kernel<<<1, 1024, 0, s>>>(nd, D.p, h.hier.dense_inv.p, colk.p, sing.p); PNP_COUNT_LAUNCH();

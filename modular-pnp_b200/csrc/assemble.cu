@@ -127,80 +127,83 @@ __device__ __forceinline__ double eafe_weight(const double* __restrict__ uu, con
   return aE * exp(beta_s);
 }
 
-// ---- (B) one thread per 3x3 block ----------------------------------------------------------
+// ---- (B) a half-warp per block row, lane k = block k of the row ------------------------------
+// (rows are visited in natural order so that the cell records stream through L2 once; the
+// finished blocks go to the row's physical, colour-major position)
 template <bool EAFE>
-__global__ void __launch_bounds__(128)
-assemble_blocks_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ ja,
-                       const int* __restrict__ brow, const int* __restrict__ v2c_ptr,
-                       const int* __restrict__ v2c_idx, const int4* __restrict__ cells,
-                       const double* __restrict__ rec, const double* __restrict__ k00,
-                       const double* __restrict__ omega, const double* __restrict__ uu,
-                       const double* __restrict__ diff, double q1, double q2,
+__global__ void __launch_bounds__(256)
+assemble_blocks_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs, const int* __restrict__ ja,
+                       const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
+                       const int4* __restrict__ cells, const double* __restrict__ rec,
+                       const double* __restrict__ k00, const double* __restrict__ omega,
+                       const double* __restrict__ uu, const double* __restrict__ diff, double q1, double q2,
                        const unsigned char* __restrict__ bcflag, double* __restrict__ val)
 {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nnzb) return;
-  const int i = brow[b], j = ja[b];
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int lane = threadIdx.x & 15;
+  if (i >= n) return;
   constexpr int RS = EAFE ? REC_EAFE : REC_FULL;
-  double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  a[0] = k00[b];
-  for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; ++p) {
-    const int c = v2c_idx[p];
-    const int4 cv = cells[c];
-    const int lj = local_index(cv, j);
-    if (lj < 0) continue;
-    const int li = local_index(cv, i);
-    const double* r = rec + (size_t)c * RS;
-    const int sidx = sym4(li, lj);
-    const double G = r[sidx];
-    a[3] += r[10] * G;          // (1,0): q1 D1 e^{u1} grad u0 . grad v1
-    a[6] += r[11] * G;          // (2,0)
-    a[1] -= r[12 + sidx];       // (0,1): -q1 e^{u1} u1 v0
-    a[2] -= r[22 + sidx];       // (0,2)
-    if (!EAFE) {
-      a[4] += r[32] * G + r[34 + 4 * li + lj];
-      a[8] += r[33] * G + r[50 + 4 * li + lj];
-    }
-  }
-  if (EAFE) {
-    if (i != j) {
-      const double w = omega[b];
-      a[4] = w * eafe_weight(uu, diff, i, j, 1, q1);
-      a[8] = w * eafe_weight(uu, diff, i, j, 2, q2);
-    } else {
-      // column sums vanish (EAFE.h:4876-4879): A_ii = -sum_{r != i} A_ri, omega symmetric
-      double s1 = 0.0, s2 = 0.0;
-      for (int p = ia[i]; p < ia[i + 1]; ++p) {
-        const int r = ja[p];
-        if (r == i) continue;
-        const double w = omega[p];
-        s1 -= w * eafe_weight(uu, diff, r, i, 1, q1);
-        s2 -= w * eafe_weight(uu, diff, r, i, 2, q2);
+  const int s = rs[i], len = ia[i + 1] - ia[i];
+  const int c0 = v2c_ptr[i], c1 = v2c_ptr[i + 1];
+  const bool bc0 = bcflag[3 * (size_t)i] != 0, bc1 = bcflag[3 * (size_t)i + 1] != 0, bc2 = bcflag[3 * (size_t)i + 2] != 0;
+  for (int k = lane; k < len; k += 16) {
+    const int b = s + k, j = ja[b];
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    a[0] = k00[b];
+    for (int p = c0; p < c1; ++p) {
+      const int c = v2c_idx[p];
+      const int4 cv = cells[c];
+      const int lj = local_index(cv, j);
+      if (lj < 0) continue;
+      const int li = local_index(cv, i);
+      const double* r = rec + (size_t)c * RS;
+      const int sidx = sym4(li, lj);
+      const double G = r[sidx];
+      a[3] += r[10] * G;          // (1,0): q1 D1 e^{u1} grad u0 . grad v1
+      a[6] += r[11] * G;          // (2,0)
+      a[1] -= r[12 + sidx];       // (0,1): -q1 e^{u1} u1 v0
+      a[2] -= r[22 + sidx];       // (0,2)
+      if (!EAFE) {
+        a[4] += r[32] * G + r[34 + 4 * li + lj];
+        a[8] += r[33] * G + r[50 + 4 * li + lj];
       }
-      a[4] = s1; a[8] = s2;
     }
+    if (EAFE) {
+      if (i != j) {
+        const double w = omega[b];
+        a[4] = w * eafe_weight(uu, diff, i, j, 1, q1);
+        a[8] = w * eafe_weight(uu, diff, i, j, 2, q2);
+      } else {
+        // column sums vanish (EAFE.h:4876-4879): A_ii = -sum_{r != i} A_ri, omega symmetric
+        double s1 = 0.0, s2 = 0.0;
+        for (int p = s; p < s + len; ++p) {
+          const int r = ja[p];
+          if (r == i) continue;
+          const double w = omega[p];
+          s1 -= w * eafe_weight(uu, diff, r, i, 1, q1);
+          s2 -= w * eafe_weight(uu, diff, r, i, 2, q2);
+        }
+        a[4] = s1; a[8] = s2;
+      }
+    }
+    // DirichletBC::apply: row -> identity row (pattern kept)
+    if (bc0) { a[0] = (i == j) ? 1.0 : 0.0; a[1] = 0.0; a[2] = 0.0; }
+    if (bc1) { a[3] = 0.0; a[4] = (i == j) ? 1.0 : 0.0; a[5] = 0.0; }
+    if (bc2) { a[6] = 0.0; a[7] = 0.0; a[8] = (i == j) ? 1.0 : 0.0; }
+    double* o = val + 9 * (size_t)s + k;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) o[(size_t)t * len] = a[t];
   }
-  // DirichletBC::apply: row -> identity row (pattern kept)
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-    if (bcflag[3 * (size_t)i + k]) {
-      a[3 * k] = 0.0; a[3 * k + 1] = 0.0; a[3 * k + 2] = 0.0;
-      if (i == j) a[3 * k + k] = 1.0;
-    }
-  const int s = ia[i], len = ia[i + 1] - s;
-  double* o = val + 9 * (size_t)s + (b - s);
-#pragma unroll
-  for (int t = 0; t < 9; ++t) o[(size_t)t * len] = a[t];
 }
 
 // zero-row fix (src/pde.cpp:596-621): a scalar row with no non-zero value gets diag = 1.
 // Such a row has a zero diagonal, so only rows whose diagonal entry is 0 are scanned.
-__global__ void zero_row_fix_kernel(int n, const int* __restrict__ ia, const int* __restrict__ dslot,
-                                    double* __restrict__ val)
+__global__ void zero_row_fix_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                                    const int* __restrict__ dslot, double* __restrict__ val)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int s = ia[i], len = ia[i + 1] - s, d = dslot[i];
+  const int s = rs[i], len = ia[i + 1] - ia[i], d = dslot[i];
   if (d < 0) return;
   double* base = val + 9 * (size_t)s;
   for (int k = 0; k < 3; ++k) {
@@ -369,19 +372,19 @@ void assemble_system(Handle& h)
   if (h.use_eafe) {
     cell_jacobian_kernel<false><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.cellrec.p);
     PNP_COUNT_LAUNCH();
-    assemble_blocks_kernel<true><<<cdiv(A.nnzb, 128), 128, 0, s>>>(
-        A.nnzb, A.ia.p, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
+    assemble_blocks_kernel<true><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
+        A.n, A.ia.p, A.rs.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
         h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
     PNP_COUNT_LAUNCH();
   } else {
     cell_jacobian_kernel<true><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.cellrec.p);
     PNP_COUNT_LAUNCH();
-    assemble_blocks_kernel<false><<<cdiv(A.nnzb, 128), 128, 0, s>>>(
-        A.nnzb, A.ia.p, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
+    assemble_blocks_kernel<false><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
+        A.n, A.ia.p, A.rs.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
         h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
     PNP_COUNT_LAUNCH();
   }
-  zero_row_fix_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.dslot.p, A.val.p);
+  zero_row_fix_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.rs.p, A.dslot.p, A.val.p);
   PNP_COUNT_LAUNCH();
   PNP_LAUNCH_CHECK();
 }

@@ -3,7 +3,10 @@
 //   fasp_dbsr_getdiaginv         [EXT FASP]      -> bsrt_diaginv
 //   fasp_smoother_dbsr_gs_*      [EXT FASP]      -> multicolour block Gauss-Seidel
 // A half-warp (16 lanes) owns one block row; lane k owns block k of the row, so each of the 9
-// component loads is unit-stride across lanes. All kernels are HBM-bound streaming kernels.
+// component loads is unit-stride across lanes. Rows are STORED colour by colour (rs[] = physical
+// start of a row, rowid[] = row at a physical position): one Gauss-Seidel colour is one contiguous
+// piece of ja/val, and SpMV walks the rows in the same physical order. All kernels here are
+// HBM-bound streaming kernels.
 #include "internal.hpp"
 #include <cub/cub.cuh>
 
@@ -11,40 +14,85 @@ namespace pnpb200 {
 
 namespace {
 
-// y = A x   (MODE 0)     y = b - A x   (MODE 1)
-template <int MODE>
-__global__ void __launch_bounds__(256)
-bsrt_spmv_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
-                 const double* __restrict__ val, const double* __restrict__ x,
-                 const double* __restrict__ b, double* __restrict__ y)
+// L2 cache-policy loads: matrix data is touched once per pass (evict_first), the vectors a sweep
+// gathers from are re-used by every colour (evict_last). L1 allocation is unchanged.
+__device__ __forceinline__ unsigned long long policy_evict_first()
 {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_last()
+{
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double ld_hint(const double* a, unsigned long long pol)
+{
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ld_hint(const int* a, unsigned long long pol)
+{
+  int v;
+  asm volatile("ld.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
+}
+
+// rows = rowid + first position; y = A x (MODE 0), y = b - A x (MODE 1),
+// x_row = D^{-1}(b - sum_{j != row} A_row,j x_j) (MODE 2: one Gauss-Seidel colour, y == x)
+template <int MODE, bool HINT>
+__global__ void __launch_bounds__(256)
+bsrt_row_kernel(int nrows, const int* __restrict__ rows, const int* __restrict__ ia,
+                const int* __restrict__ rs, const int* __restrict__ ja, const double* __restrict__ val,
+                const double* __restrict__ dinv, const double* __restrict__ b, const double* x, double* y)
+{
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int lane = threadIdx.x & 15;
-  int s = 0, len = 0;
-  if (row < n) { s = ia[row]; len = ia[row + 1] - s; }
+  int row = -1, s = 0, len = 0;
+  if (t < nrows) { row = rows ? rows[t] : t; s = rs[row]; len = ia[row + 1] - ia[row]; }
   const double* v = val + 9 * (size_t)s;
+  const unsigned long long pf = policy_evict_first(), pl = policy_evict_last();
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   for (int k = lane; k < len; k += 16) {
-    const size_t j = 3 * (size_t)ja[s + k];
-    const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
-    a0 += v[k] * x0 + v[len + k] * x1 + v[2 * len + k] * x2;
-    a1 += v[3 * len + k] * x0 + v[4 * len + k] * x1 + v[5 * len + k] * x2;
-    a2 += v[6 * len + k] * x0 + v[7 * len + k] * x1 + v[8 * len + k] * x2;
+    const int jc = HINT ? ld_hint(ja + s + k, pf) : ja[s + k];
+    if (MODE == 2 && jc == row) continue;
+    const size_t j = 3 * (size_t)jc;
+    double x0, x1, x2;
+    if (HINT) { x0 = ld_hint(x + j, pl); x1 = ld_hint(x + j + 1, pl); x2 = ld_hint(x + j + 2, pl); }
+    else { x0 = x[j]; x1 = x[j + 1]; x2 = x[j + 2]; }
+    if (HINT) {
+      a0 += ld_hint(v + k, pf) * x0 + ld_hint(v + len + k, pf) * x1 + ld_hint(v + 2 * len + k, pf) * x2;
+      a1 += ld_hint(v + 3 * len + k, pf) * x0 + ld_hint(v + 4 * len + k, pf) * x1 + ld_hint(v + 5 * len + k, pf) * x2;
+      a2 += ld_hint(v + 6 * len + k, pf) * x0 + ld_hint(v + 7 * len + k, pf) * x1 + ld_hint(v + 8 * len + k, pf) * x2;
+    } else {
+      a0 += v[k] * x0 + v[len + k] * x1 + v[2 * len + k] * x2;
+      a1 += v[3 * len + k] * x0 + v[4 * len + k] * x1 + v[5 * len + k] * x2;
+      a2 += v[6 * len + k] * x0 + v[7 * len + k] * x1 + v[8 * len + k] * x2;
+    }
   }
   a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
-  if (row < n && lane < 3) {
-    const double r = lane == 0 ? a0 : lane == 1 ? a1 : a2;
-    const size_t o = 3 * (size_t)row + lane;
-    y[o] = MODE == 0 ? r : b[o] - r;
+  if (row >= 0 && lane < 3) {
+    const size_t o = 3 * (size_t)row;
+    if (MODE == 0) y[o + lane] = lane == 0 ? a0 : lane == 1 ? a1 : a2;
+    else if (MODE == 1) y[o + lane] = b[o + lane] - (lane == 0 ? a0 : lane == 1 ? a1 : a2);
+    else {
+      const double r0 = b[o] - a0, r1 = b[o + 1] - a1, r2 = b[o + 2] - a2;
+      const double* d = dinv + 9 * (size_t)row + 3 * lane;
+      y[o + lane] = d[0] * r0 + d[1] * r1 + d[2] * r2;
+    }
   }
 }
 
-__global__ void diaginv_kernel(int n, const int* __restrict__ ia, const int* __restrict__ dslot,
-                               const double* __restrict__ val, double* __restrict__ dinv)
+__global__ void diaginv_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                               const int* __restrict__ dslot, const double* __restrict__ val,
+                               double* __restrict__ dinv)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int s = ia[i], len = ia[i + 1] - s, d = dslot[i] - s;
+  const int s = rs[i], len = ia[i + 1] - ia[i], d = dslot[i] - s;
   double a[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) a[t] = val[9 * (size_t)s + (size_t)t * len + d];
@@ -57,51 +105,74 @@ __global__ void diaginv_kernel(int n, const int* __restrict__ ia, const int* __r
   o[6] = c2 * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
 }
 
-// FASP layout (block-major, row-major 3x3) <-> BSR-T
+// FASP layout (natural block order, row-major 3x3 per block) <-> BSR-T (physical)
 template <bool TO_T>
-__global__ void relayout_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ brow,
-                                const double* __restrict__ in, double* __restrict__ out)
+__global__ void relayout_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ rs,
+                                const int* __restrict__ brow, const double* __restrict__ in, double* __restrict__ out)
 {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 9 * (size_t)nnzb) return;
-  const int b = (int)(e / 9), t = (int)(e % 9);
-  const int i = brow[b], s = ia[i], len = ia[i + 1] - s;
-  const size_t et = 9 * (size_t)s + (size_t)t * len + (b - s);
-  if (TO_T) out[et] = in[e]; else out[e] = in[et];
+  const int b = (int)(e / 9), t = (int)(e % 9);          // b = physical block
+  const int i = brow[b], s = rs[i], len = ia[i + 1] - ia[i], k = b - s;
+  const size_t et = 9 * (size_t)s + (size_t)t * len + k;
+  const size_t ef = 9 * ((size_t)ia[i] + k) + t;
+  if (TO_T) out[et] = in[ef]; else out[ef] = in[et];
 }
 
-// one colour of block Gauss-Seidel: x_i = D_i^{-1} (b_i - sum_{j != i} A_ij x_j)
-__global__ void __launch_bounds__(256)
-mcgs_kernel(int nrows_color, const int* __restrict__ rows, const int* __restrict__ ia,
-            const int* __restrict__ ja, const double* __restrict__ val,
-            const double* __restrict__ dinv, const double* __restrict__ b, double* __restrict__ x)
+// natural <-> physical column arrays (row granularity)
+template <bool TO_PHYS>
+__global__ void permute_ja_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                                  const int* __restrict__ in, int* __restrict__ out)
 {
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-  const int lane = threadIdx.x & 15;
-  int row = -1, s = 0, len = 0;
-  if (t < nrows_color) { row = rows[t]; s = ia[row]; len = ia[row + 1] - s; }
-  const double* v = val + 9 * (size_t)s;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  for (int k = lane; k < len; k += 16) {
-    const int jc = ja[s + k];
-    if (jc == row) continue;
-    const size_t j = 3 * (size_t)jc;
-    const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
-    a0 += v[k] * x0 + v[len + k] * x1 + v[2 * len + k] * x2;
-    a1 += v[3 * len + k] * x0 + v[4 * len + k] * x1 + v[5 * len + k] * x2;
-    a2 += v[6 * len + k] * x0 + v[7 * len + k] * x1 + v[8 * len + k] * x2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int a = ia[i], len = ia[i + 1] - a, s = rs[i];
+  for (int k = 0; k < len; ++k) { if (TO_PHYS) out[s + k] = in[a + k]; else out[a + k] = in[s + k]; }
+}
+
+__global__ void row_tables_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                                  const int* __restrict__ ja, int* __restrict__ brow, int* __restrict__ dslot)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = rs[i], len = ia[i + 1] - ia[i];
+  int d = -1;
+  for (int p = s; p < s + len; ++p) { brow[p] = i; if (ja[p] == i) d = p; }
+  dslot[i] = d;
+}
+
+__global__ void tslot_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ rs,
+                             const int* __restrict__ ja, const int* __restrict__ brow, int* __restrict__ tslot)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int i = brow[b], j = ja[b];
+  int lo = rs[j], hi = rs[j] + (ia[j + 1] - ia[j]) - 1, res = -1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1, c = ja[mid];
+    if (c == i) { res = mid; break; }
+    if (c < i) lo = mid + 1; else hi = mid - 1;
   }
-  a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
-  if (row >= 0 && lane < 3) {
-    const size_t o = 3 * (size_t)row;
-    const double r0 = b[o] - a0, r1 = b[o + 1] - a1, r2 = b[o + 2] - a2;
-    const double* d = dinv + 9 * (size_t)row + 3 * lane;
-    x[o + lane] = d[0] * r0 + d[1] * r1 + d[2] * r2;
-  }
+  tslot[b] = res;
+}
+
+// physical row starts: rs[rowid[p]] = exclusive prefix over p of len(rowid[p])
+__global__ void rowlen_by_position_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rowid,
+                                          int* __restrict__ len)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) { const int i = rowid[p]; len[p] = ia[i + 1] - ia[i]; }
+  if (p == n) len[n] = 0;
+}
+__global__ void scatter_rs_kernel(int n, const int* __restrict__ rowid, const int* __restrict__ start,
+                                  int* __restrict__ rs)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) rs[rowid[p]] = start[p];
 }
 
 // ---- Jones-Plassmann colouring with hashed priorities (two kernels per round so that the
-// result does not depend on thread timing) ---------------------------------------------------
+// result does not depend on thread timing); natural CSR graph ------------------------------------
 __global__ void color_select_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
                                     const int* __restrict__ color, unsigned char* __restrict__ cand,
                                     int* __restrict__ remaining)
@@ -138,10 +209,41 @@ __global__ void color_assign_kernel(int n, const int* __restrict__ ia, const int
   if (c < 0 || c >= 63) { *overflow = 1; color[i] = 62; } else color[i] = c;
 }
 
-__global__ void color_hist_kernel(int n, const int* __restrict__ color, int* __restrict__ hist)
+__global__ void max_color_kernel(int n, const int* __restrict__ color, int* __restrict__ out)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&hist[color[i]], 1);
+  int c = i < n ? color[i] : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, c, o); c = t > c ? t : c; }
+  if ((threadIdx.x & 31) == 0 && c >= 0) atomicMax(out, c);
+}
+
+// Culberson's iterated greedy: rebuild the colouring class by class (members of a class are
+// independent, so a class can be recoloured in parallel); never uses more colours than before
+__global__ void recolor_class_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                                     const int* __restrict__ oldc, int cls, int* __restrict__ newc)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || oldc[i] != cls) return;
+  unsigned long long used = 0ull;
+  for (int p = ia[i]; p < ia[i + 1]; ++p) {
+    const int j = ja[p];
+    if (j == i) continue;
+    const int cj = newc[j];
+    if (cj >= 0) used |= 1ull << cj;
+  }
+  newc[i] = __ffsll(~used) - 1;
+}
+
+// sort key = (tile of the row, colour): a sweep visits tile after tile and, inside a tile, colour
+// after colour, so the x-window a tile gathers from stays in L2 across its colours
+__global__ void group_key_kernel(int n, int tile_rows, int* __restrict__ color, int* __restrict__ hist)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int key = (i / tile_rows) * 64 + color[i];
+  color[i] = key;
+  atomicAdd(&hist[key], 1);
 }
 
 __global__ void iota_kernel(int n, int* __restrict__ a)
@@ -154,84 +256,151 @@ __global__ void iota_kernel(int n, int* __restrict__ a)
 
 void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s)
 {
-  bsrt_spmv_kernel<0><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, A.ia.p, A.ja.p, A.val.p, x, nullptr, y);
+  bsrt_row_kernel<0, false><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, nullptr, A.ia.p, A.rs.p, A.ja.p, A.val.p,
+                                                                nullptr, nullptr, x, y);
   PNP_COUNT_LAUNCH();
 }
 
 void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s)
 {
-  bsrt_spmv_kernel<1><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, A.ia.p, A.ja.p, A.val.p, x, b, r);
+  bsrt_row_kernel<1, false><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, nullptr, A.ia.p, A.rs.p, A.ja.p, A.val.p,
+                                                                nullptr, b, x, r);
   PNP_COUNT_LAUNCH();
 }
 
 void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s)
 {
-  diaginv_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.dslot.p, A.val.p, dinv);
+  diaginv_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.rs.p, A.dslot.p, A.val.p, dinv);
   PNP_COUNT_LAUNCH();
 }
 
-void bsrt_from_fasp(const int* d_ia, const int* d_ja, const double* d_val_fasp, BsrT& A, cudaStream_t s)
+void bsrt_from_fasp(const double* d_val_fasp, BsrT& A, cudaStream_t s)
 {
-  (void)d_ia; (void)d_ja;
-  relayout_kernel<true><<<cdiv(9 * (size_t)A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.brow.p, d_val_fasp, A.val.p);
+  relayout_kernel<true><<<cdiv(9 * (size_t)A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.brow.p, d_val_fasp, A.val.p);
   PNP_COUNT_LAUNCH();
 }
 
 void bsrt_to_fasp(const BsrT& A, double* d_val_fasp, cudaStream_t s)
 {
-  relayout_kernel<false><<<cdiv(9 * (size_t)A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.brow.p, A.val.p, d_val_fasp);
+  relayout_kernel<false><<<cdiv(9 * (size_t)A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.brow.p, A.val.p, d_val_fasp);
   PNP_COUNT_LAUNCH();
 }
+
+void bsrt_export_ja(const BsrT& A, int* d_ja_nat, cudaStream_t s)
+{
+  permute_ja_kernel<false><<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.rs.p, A.ja.p, d_ja_nat);
+  PNP_COUNT_LAUNCH();
+}
+
+static int g_gs_hint = getenv("PNPB200_GS_HINT") ? atoi(getenv("PNPB200_GS_HINT")) : 0;
 
 void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s)
 {
   const BsrT& A = L.A;
-  for (int cc = 0; cc < L.ncolors; ++cc) {
-    const int c = reverse ? L.ncolors - 1 - cc : cc;
+  for (int cc = 0; cc < L.ngroups; ++cc) {
+    const int c = reverse ? L.ngroups - 1 - cc : cc;
     const int cnt = L.color_ptr[c + 1] - L.color_ptr[c];
     if (cnt == 0) continue;
-    mcgs_kernel<<<cdiv((size_t)cnt * 16, 256), 256, 0, s>>>(cnt, L.color_rows.p + L.color_ptr[c], A.ia.p, A.ja.p,
-                                                           A.val.p, L.dinv.p, b, x);
+    if (g_gs_hint)
+      bsrt_row_kernel<2, true><<<cdiv((size_t)cnt * 16, 256), 256, 0, s>>>(cnt, A.rowid.p + L.color_ptr[c], A.ia.p, A.rs.p,
+                                                                          A.ja.p, A.val.p, L.dinv.p, b, x, x);
+    else
+      bsrt_row_kernel<2, false><<<cdiv((size_t)cnt * 16, 256), 256, 0, s>>>(cnt, A.rowid.p + L.color_ptr[c], A.ia.p, A.rs.p,
+                                                                           A.ja.p, A.val.p, L.dinv.p, b, x, x);
     PNP_COUNT_LAUNCH();
   }
 }
 
-void color_level(Level& L, cudaStream_t s)
+// Colour the natural graph (A.ia, ja_nat), then lay the matrix out colour by colour.
+// `ws` (optional) supplies the temporaries during AMG setup; at create time they come from the pool.
+void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s)
 {
   BsrT& A = L.A;
   const int n = A.n;
-  DevBuf<int> color; color.alloc(n, s);
-  PNP_CUDA(cudaMemsetAsync(color.p, 0xff, n * sizeof(int), s));
-  DevBuf<unsigned char> cand; cand.alloc(n, s);
-  DevBuf<int> rem; rem.alloc(66, s); rem.zero();     // [0] remaining, [1] overflow, [2..65] histogram
+  DevBuf<int> t_color, t_rem, t_rows, t_cout, t_len, t_start, t_hist, t_newc; DevBuf<unsigned char> t_cand, t_cub;
+  auto geti = [&](DevBuf<int>& own, size_t cnt) -> int* { if (ws) return ws->get<int>(cnt); own.alloc(cnt, s); return own.p; };
+  int* color = geti(t_color, n);
+  int* rem = geti(t_rem, 2);                       // [0] remaining, [1] overflow
+  unsigned char* cand;
+  if (ws) cand = ws->get<unsigned char>(n); else { t_cand.alloc(n, s); cand = t_cand.p; }
+  PNP_CUDA(cudaMemsetAsync(color, 0xff, (size_t)n * sizeof(int), s));
+  PNP_CUDA(cudaMemsetAsync(rem, 0, 2 * sizeof(int), s));
   int hrem = n, rounds = 0;
   while (hrem > 0) {
-    PNP_CUDA(cudaMemsetAsync(rem.p, 0, sizeof(int), s));
-    color_select_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, color.p, cand.p, rem.p);
-    PNP_COUNT_LAUNCH();
-    color_assign_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.ja.p, color.p, cand.p, rem.p + 1);
-    PNP_COUNT_LAUNCH();
-    PNP_CUDA(cudaMemcpyAsync(&hrem, rem.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaMemsetAsync(rem, 0, sizeof(int), s));
+    color_select_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, ja_nat, color, cand, rem); PNP_COUNT_LAUNCH();
+    color_assign_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, ja_nat, color, cand, rem + 1); PNP_COUNT_LAUNCH();
+    PNP_CUDA(cudaMemcpyAsync(&hrem, rem, sizeof(int), cudaMemcpyDeviceToHost, s));
     PNP_CUDA(cudaStreamSynchronize(s));
     if (++rounds > 100000) throw Error(ERROR_UNKNOWN, "colouring did not terminate");
   }
-  color_hist_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, color.p, rem.p + 2); PNP_COUNT_LAUNCH();
-  std::vector<int> hh = rem.to_host(66);
-  if (hh[1]) throw Error(ERROR_DATA_STRUCTURE, "matrix graph needs more than 62 colours");
-  int nc = 0;
-  for (int c = 0; c < 64; ++c) if (hh[2 + c] > 0) nc = c + 1;
-  L.ncolors = nc;
-  L.color_ptr.assign(nc + 1, 0);
-  for (int c = 0; c < nc; ++c) L.color_ptr[c + 1] = L.color_ptr[c] + hh[2 + c];
-  // rows sorted by colour, ascending inside a colour (stable radix sort on 6 bits)
-  DevBuf<int> rows_in, color_out; rows_in.alloc(n, s); color_out.alloc(n, s);
-  L.color_rows.alloc(n, s);
-  iota_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, rows_in.p); PNP_COUNT_LAUNCH();
+  int hh2[2];
+  PNP_CUDA(cudaMemcpyAsync(hh2, rem, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  if (hh2[1]) throw Error(ERROR_DATA_STRUCTURE, "matrix graph needs more than 62 colours");
+  // iterated greedy passes (reverse class order, then forward): fewer, fuller colour classes
+  {
+    int passes = 3;
+    if (const char* e = getenv("PNPB200_RECOLOR_PASSES")) passes = atoi(e);
+    int* newc = geti(t_newc, n);
+    for (int ps = 0; ps < passes; ++ps) {
+      int ncol_now = 0;
+      PNP_CUDA(cudaMemsetAsync(rem, 0, sizeof(int), s));
+      max_color_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, color, rem); PNP_COUNT_LAUNCH();
+      PNP_CUDA(cudaMemcpyAsync(&ncol_now, rem, sizeof(int), cudaMemcpyDeviceToHost, s));
+      PNP_CUDA(cudaStreamSynchronize(s));
+      ++ncol_now;
+      PNP_CUDA(cudaMemsetAsync(newc, 0xff, (size_t)n * sizeof(int), s));
+      for (int q = 0; q < ncol_now; ++q) {
+        const int cls = (ps % 2 == 0) ? ncol_now - 1 - q : q;
+        recolor_class_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, ja_nat, color, cls, newc); PNP_COUNT_LAUNCH();
+      }
+      PNP_CUDA(cudaMemcpyAsync(color, newc, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  // optional row tiles (sweep order tile -> colour); measured on B200 at 256^3: no gain over one
+  // tile (6.8 ms vs 5.6 ms per sweep: 26x more launches, L2 does not hold the window), so default 1
+  int ntiles = 1;
+  if (const char* e = getenv("PNPB200_GS_TILES")) { ntiles = atoi(e); if (ntiles < 1) ntiles = 1; if (ntiles > 64) ntiles = 64; }
+  const int tile_rows = (n + ntiles - 1) / ntiles;
+  const int ngroups_max = ntiles * 64;
+  int* hist = geti(t_hist, ngroups_max);
+  PNP_CUDA(cudaMemsetAsync(hist, 0, (size_t)ngroups_max * sizeof(int), s));
+  group_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, tile_rows, color, hist); PNP_COUNT_LAUNCH();
+  std::vector<int> hh(ngroups_max);
+  PNP_CUDA(cudaMemcpyAsync(hh.data(), hist, (size_t)ngroups_max * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  // non-empty (tile, colour) groups in sweep order
+  L.color_ptr.assign(1, 0);
+  int maxc = 0;
+  for (int g = 0; g < ngroups_max; ++g)
+    if (hh[g] > 0) { L.color_ptr.push_back(L.color_ptr.back() + hh[g]); if (g % 64 + 1 > maxc) maxc = g % 64 + 1; }
+  L.ngroups = (int)L.color_ptr.size() - 1;
+  L.ncolors = maxc;
+  int key_bits = 6; while ((1 << key_bits) < ngroups_max) ++key_bits;
+  // rowid = rows sorted by (tile, colour), ascending inside a group (stable radix sort)
+  int* rows_in = geti(t_rows, n);
+  int* color_out = geti(t_cout, n);
+  A.rowid.alloc(n, s);
+  iota_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, rows_in); PNP_COUNT_LAUNCH();
   size_t bytes = 0;
-  PNP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, color.p, color_out.p, rows_in.p, L.color_rows.p, n, 0, 6, s));
-  DevBuf<unsigned char> tmp; tmp.alloc(bytes, s);
-  PNP_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, color.p, color_out.p, rows_in.p, L.color_rows.p, n, 0, 6, s));
+  PNP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, color, color_out, rows_in, A.rowid.p, n, 0, key_bits, s));
+  unsigned char* tmp;
+  if (ws) tmp = ws->get<unsigned char>(bytes); else { t_cub.alloc(bytes, s); tmp = t_cub.p; }
+  PNP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, color, color_out, rows_in, A.rowid.p, n, 0, key_bits, s));
   PNP_COUNT_LAUNCH();
+  // physical row starts and the physical column array
+  int* len = geti(t_len, n + 1);
+  int* start = geti(t_start, n + 1);
+  rowlen_by_position_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(n, A.ia.p, A.rowid.p, len); PNP_COUNT_LAUNCH();
+  exclusive_scan_int(len, start, n + 1, s);
+  A.rs.alloc(n, s);
+  scatter_rs_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, start, A.rs.p); PNP_COUNT_LAUNCH();
+  A.ja.alloc(A.nnzb, s);
+  permute_ja_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, ja_nat, A.ja.p); PNP_COUNT_LAUNCH();
+  A.brow.alloc(A.nnzb, s); A.dslot.alloc(n, s); A.tslot.alloc(A.nnzb, s);
+  row_tables_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, A.brow.p, A.dslot.p); PNP_COUNT_LAUNCH();
+  tslot_kernel<<<cdiv(A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.ja.p, A.brow.p, A.tslot.p); PNP_COUNT_LAUNCH();
   PNP_LAUNCH_CHECK();
 }
 

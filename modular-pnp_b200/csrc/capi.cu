@@ -82,12 +82,13 @@ struct HostSystem {
       Handle& h = ph->h; cudaStream_t s = h.stream;
       BsrT& M = h.hier.lv[0]->A;
       M.n = A->ROW; M.nnzb = A->NNZ;
-      M.ia.alloc(M.n + 1, s); M.ja.alloc(M.nnzb, s); M.val.alloc(9 * (size_t)M.nnzb, s);
-      M.ia.upload(A->IA, M.n + 1); M.ja.upload(A->JA, M.nnzb);
-      finish_pattern_tables(M, s);
+      M.ia.alloc(M.n + 1, s); M.val.alloc(9 * (size_t)M.nnzb, s);
+      M.ia.upload(A->IA, M.n + 1);
+      DevBuf<int> ja_nat; ja_nat.alloc(M.nnzb, s); ja_nat.upload(A->JA, M.nnzb);
+      color_and_layout(*h.hier.lv[0], ja_nat.p, nullptr, s);
       DevBuf<double> tmp; tmp.alloc(9 * (size_t)M.nnzb, s);
       tmp.upload(A->val, 9 * (size_t)M.nnzb);
-      bsrt_from_fasp(M.ia.p, M.ja.p, tmp.p, M, s);
+      bsrt_from_fasp(tmp.p, M, s);
       std::vector<int> ds = M.dslot.to_host(M.n);
       for (int v : ds) if (v < 0) throw Error(ERROR_DATA_STRUCTURE, "dBSRmat row without a diagonal block");
     } catch (...) { delete ph; ph = nullptr; throw; }
@@ -159,7 +160,6 @@ int pnpb200_create(pnpb200_handle** out, int nv, const double* xyz, int nc, cons
       h.bcflag.alloc(N, s); h.bcflag.zero();
       g_launches = 0;
       build_mesh_tables(h);
-      color_level(*h.hier.lv[0], s);
       PNP_CUDA(cudaStreamSynchronize(s));
       h.stats.launches = g_launches;
     } catch (...) { delete ph; throw; }
@@ -185,7 +185,6 @@ int pnpb200_create_box(pnpb200_handle** out, int nx, int ny, int nz, double lx, 
       h.uu.alloc(N, s); h.uu.zero();
       h.bcflag.alloc(N, s); h.bcflag.zero();
       build_mesh_tables(h);
-      color_level(*h.hier.lv[0], s);
       PNP_CUDA(cudaStreamSynchronize(s));
       h.stats.launches = g_launches;
     } catch (...) { delete ph; throw; }
@@ -323,8 +322,10 @@ static int copy_level_matrix(Handle& h, const BsrT& A, dBSRmat* out)
   out->val = (REAL*)calloc(9 * (size_t)A.nnzb, sizeof(REAL));
   if (!out->IA || !out->JA || !out->val) throw Error(ERROR_ALLOC_MEM, "host allocation failed");
   DevBuf<double> tmp; tmp.alloc(9 * (size_t)A.nnzb, s);
+  DevBuf<int> ja_nat; ja_nat.alloc(A.nnzb, s);
   bsrt_to_fasp(A, tmp.p, s);
-  A.ia.download(out->IA, A.n + 1); A.ja.download(out->JA, A.nnzb);
+  bsrt_export_ja(A, ja_nat.p, s);
+  A.ia.download(out->IA, A.n + 1); ja_nat.download(out->JA, A.nnzb);
   tmp.download(out->val, 9 * (size_t)A.nnzb);
   return FASP_SUCCESS;
 }
@@ -467,7 +468,7 @@ int pnpb200_get_level_order(pnpb200_handle* ph, int level, int* order)
   return guarded([&]() -> int {
     Level& L = *ph->h.hier.lv[level];
     if (L.ncolors == 0) throw Error(ERROR_INPUT_PAR, "level not coloured yet");
-    L.color_rows.download(order, L.A.n);
+    L.A.rowid.download(order, L.A.n);
     return FASP_SUCCESS;
   });
 }

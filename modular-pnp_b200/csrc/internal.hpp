@@ -8,12 +8,16 @@ namespace pnpb200 {
 
 // BSR(3) matrix on the device in "BSR-T" layout: same IA/JA as FASP's dBSRmat, but inside a
 // block row the 9 block components are stored component-major:
-//     val[9*IA[i] + t*len_i + k]   (t = 3*r + c component, k = block position in the row)
+//     val[9*rs[i] + t*len_i + k]   (t = 3*r + c component, k = block position in the row)
 // so that lane k of a row group loads component t of its block with unit stride.
 struct BsrT {
   int n = 0;        // block rows
   int nnzb = 0;     // blocks
-  DevBuf<int> ia, ja;
+  DevBuf<int> ia;       // natural CSR offsets (row lengths, FASP import/export)
+  DevBuf<int> rs;       // physical start of each row's blocks: rows are STORED colour by colour, so that a
+                        // Gauss-Seidel colour sweep streams one contiguous piece of ja/val
+  DevBuf<int> rowid;    // physical row position -> row id (= rows sorted by colour)
+  DevBuf<int> ja;       // column of each block, physical order (ascending inside a row)
   DevBuf<int> brow;     // row of each block
   DevBuf<int> dslot;    // position (absolute block index) of the diagonal block of each row
   DevBuf<int> tslot;    // block index of the transposed block (j,i), -1 if absent
@@ -24,15 +28,15 @@ struct Level {
   BsrT A;
   DevBuf<double> dinv;          // 9*n, AoS: inverse of diagonal blocks
   // multicolour ordering
-  int ncolors = 0;
-  std::vector<int> color_ptr;   // host, ncolors+1 offsets into color_rows
-  DevBuf<int> color_rows;       // rows sorted by colour (ascending inside a colour)
+  int ncolors = 0;              // colours of the graph
+  int ngroups = 0;              // (tile, colour) groups of one sweep, in order
+  std::vector<int> color_ptr;   // host, ngroups+1 offsets into A.rowid
   // aggregation to the next level
   int nagg = 0;
   DevBuf<int> agg;              // n, -1 = isolated
   DevBuf<int> agg_ptr, agg_rows;   // members of each aggregate (ascending)
   // numeric RAP map: coarse block s sums fine blocks rap_perm[rap_seg[s] .. rap_seg[s+1])
-  DevBuf<int> rap_seg, rap_perm;
+  DevBuf<int> rap_beg, rap_end, rap_perm;
   // work vectors (3*n)
   DevBuf<double> x, b, w;
   // K-cycle scratch: 5 vectors, device scalars + partials, block counter
@@ -48,7 +52,7 @@ struct SolverConfig {
   double tentative_smooth = 0.67; int presmooth = 1, postsmooth = 1;
   int use_amg = 1;
   int cycle_type = 1;       // V_CYCLE; anything else = K-cycle (nonlinear AMLI)
-  int kcycle_levels = 2;    // coarse levels 1..kcycle_levels get the Krylov acceleration
+  int kcycle_levels = 3;    // coarse levels 1..kcycle_levels get the Krylov acceleration (measured best at 256^3)
 };
 SolverConfig make_config(const itsolver_param* it, const AMG_param* amg);
 
@@ -127,7 +131,9 @@ struct Handle {
 void build_mesh_tables(Handle& h);                 // v2c, pattern, brow/dslot/tslot, omega
 void compute_k00(Handle& h);
 void generate_box_mesh(Handle& h, int nx, int ny, int nz, double lx, double ly, double lz);   // domain_build
-void finish_pattern_tables(BsrT& A, cudaStream_t s);   // brow, dslot, tslot from ia/ja
+// colour the graph given in natural CSR (ia, ja_nat), lay the rows out colour by colour (rs, rowid,
+// physical ja) and build brow/dslot/tslot
+void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s);
 void exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t s);
 // ---- assemble.cu
 void assemble_system(Handle& h);                   // J (BSR-T) and rhs
@@ -136,10 +142,10 @@ void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf)
 void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s);                  // y = A x
 void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s); // r = b - A x
 void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s);
-void bsrt_from_fasp(const int* d_ia, const int* d_ja, const double* d_val_fasp, BsrT& A, cudaStream_t s);
+void bsrt_from_fasp(const double* d_val_fasp, BsrT& A, cudaStream_t s);
+void bsrt_export_ja(const BsrT& A, int* d_ja_nat, cudaStream_t s);
 void bsrt_to_fasp(const BsrT& A, double* d_val_fasp, cudaStream_t s);
 void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s);
-void color_level(Level& L, cudaStream_t s);
 // ---- vecops.cu
 void vec_set(double* x, double v, size_t n, cudaStream_t s);
 void vec_copy(double* dst, const double* src, size_t n, cudaStream_t s);

@@ -77,31 +77,6 @@ __global__ void pattern_kernel(int nv, const int* __restrict__ v2c_ptr, const in
   else { const int s = ia[v]; for (int t = 0; t < cnt; ++t) ja[s + t] = nb[t]; }
 }
 
-__global__ void row_tables_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
-                                  int* __restrict__ brow, int* __restrict__ dslot)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int d = -1;
-  for (int p = ia[i]; p < ia[i + 1]; ++p) { brow[p] = i; if (ja[p] == i) d = p; }
-  dslot[i] = d;
-}
-
-__global__ void tslot_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ ja,
-                             const int* __restrict__ brow, int* __restrict__ tslot)
-{
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nnzb) return;
-  const int i = brow[b], j = ja[b];
-  int lo = ia[j], hi = ia[j + 1] - 1, res = -1;
-  while (lo <= hi) {
-    const int mid = (lo + hi) >> 1, c = ja[mid];
-    if (c == i) { res = mid; break; }
-    if (c < i) lo = mid + 1; else hi = mid - 1;
-  }
-  tslot[b] = res;
-}
-
 // omega_b = sum over cells containing (i,j) of the P1 stiffness entry (det/6) grad l_i . grad l_j
 // k00_b   = sum over cells of (sum_ip W24 eps(ip)) * det grad l_i . grad l_j
 template <bool WITH_EPS>
@@ -149,14 +124,6 @@ void exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t s)
   PNP_COUNT_LAUNCH();
 }
 
-void finish_pattern_tables(BsrT& A, cudaStream_t s)
-{
-  A.brow.alloc(A.nnzb, s); A.dslot.alloc(A.n, s); A.tslot.alloc(A.nnzb, s);
-  row_tables_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.ja.p, A.brow.p, A.dslot.p); PNP_COUNT_LAUNCH();
-  tslot_kernel<<<cdiv(A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.ja.p, A.brow.p, A.tslot.p); PNP_COUNT_LAUNCH();
-  PNP_LAUNCH_CHECK();
-}
-
 void build_mesh_tables(Handle& h)
 {
   cudaStream_t s = h.stream;
@@ -187,10 +154,12 @@ void build_mesh_tables(Handle& h)
   PNP_CUDA(cudaStreamSynchronize(s));
   if (herr) throw Error(ERROR_DATA_STRUCTURE, "mesh vertex with more than 128 neighbours is not supported");
   A.nnzb = nnzb;
-  A.ja.alloc(nnzb, s);
-  pattern_kernel<true><<<cdiv(nv, 64), 64, 0, s>>>(nv, h.v2c_ptr.p, h.v2c_idx.p, cells, nullptr, A.ia.p, A.ja.p, err.p);
-  PNP_COUNT_LAUNCH();
-  finish_pattern_tables(A, s);
+  {
+    DevBuf<int> ja_nat; ja_nat.alloc(nnzb, s);
+    pattern_kernel<true><<<cdiv(nv, 64), 64, 0, s>>>(nv, h.v2c_ptr.p, h.v2c_idx.p, cells, nullptr, A.ia.p, ja_nat.p, err.p);
+    PNP_COUNT_LAUNCH();
+    color_and_layout(L, ja_nat.p, nullptr, s);      // fine-level colouring + colour-major row storage
+  }
   A.val.alloc(9 * (size_t)nnzb, s);
   // EAFE edge table
   h.omega.alloc(nnzb, s);

@@ -298,7 +298,7 @@ void orc_default_param(orc_solver_param* p)
   p->max_levels = 20; p->coarse_dof = 100;
   p->strong_coupled = 0.08; p->max_aggregation = 20; p->tentative_smooth = 0.67;
   p->amg_tol = 1e-6; p->presmooth = 1; p->postsmooth = 1; p->print_level = 0;
-  p->coarse_dense = 0; p->ortho_cgs = 0; p->cycle_type = 1; p->kcycle_levels = 2;
+  p->coarse_dense = 0; p->ortho_cgs = 0; p->cycle_type = 1; p->kcycle_levels = 3;
 }
 
 void orc_bsr_spmv(int n, const int* IA, const int* JA, const double* val, double alpha,

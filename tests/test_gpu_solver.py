@@ -75,7 +75,7 @@ def test_solve_hierarchy_and_vcycle(oracle, pkg, system, cycle):
             assert np.abs(cval - gval).max() <= 1e-13 * np.abs(cval).max()
             aggs.append(agg); naggs.append(na)
     # one V-cycle: GPU vs oracle replaying the same hierarchy
-    prm = oracle.default_param(coarse_dense=1, ortho_cgs=1, cycle_type=cycle, kcycle_levels=2)
+    prm = oracle.default_param(coarse_dense=1, ortho_cgs=1, cycle_type=cycle, kcycle_levels=3)
     H = oracle.AMG(IA, JA, val, prm, ext_agg=aggs, ext_nagg=naggs, ext_order=orders)
     assert H.nlevels() == nl
     rr = np.random.default_rng(9).uniform(-1, 1, P.N)
