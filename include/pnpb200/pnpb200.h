@@ -134,6 +134,22 @@ int  pnpb200_probe_kernel(pnpb200_handle* h, int which, int reps, double* ms_per
 /* y = J x with the assembled fine-level matrix (host vectors) */
 int  pnpb200_apply_matrix(pnpb200_handle* h, const double* x, double* y);
 
+/* ---- multi-GPU: one process per GPU, block rows partitioned by vertex ----
+ * Each rank creates its handle from its LOCAL mesh: owned vertices first (local ids
+ * 0..n_owned-1), then the ghost vertices its cells touch, grouped by owning neighbour rank;
+ * cells = every cell that touches an owned vertex. Ghost dofs are identity rows of the local
+ * matrix; their values are refreshed by halo exchange (grouped ncclSend/ncclRecv) before every
+ * global SpMV / residual / assembly, and every dot product / norm is an fp64 ncclAllReduce.
+ * pnpb200_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller's own bootstrap hands
+ * it to every rank (bench.py uses torch.distributed), then every rank calls pnpb200_comm_init. */
+int  pnpb200_comm_unique_id(unsigned char id[128]);
+int  pnpb200_comm_init(pnpb200_handle* h, const unsigned char id[128], int rank, int n_ranks);
+/* neighbour k: send the owned vertices send_idx[send_ptr[k] .. send_ptr[k+1]) (in that order) and
+ * receive its values into the local ghost vertices [recv_ptr[k], recv_ptr[k+1]). Call before
+ * pnpb200_set_dirichlet / after create. */
+int  pnpb200_set_partition(pnpb200_handle* h, int n_owned, int n_neighbors, const int* neighbor_ranks,
+                           const int* send_ptr, const int* send_idx, const int* recv_ptr);
+
 #ifdef __cplusplus
 }
 #endif

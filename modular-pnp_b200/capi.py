@@ -131,6 +131,9 @@ def lib():
     L.pnpb200_get_level_order.argtypes = [H, C.c_int, _i4]
     L.pnpb200_apply_vcycle.argtypes = [H, _f8, _f8]
     L.pnpb200_apply_matrix.argtypes = [H, _f8, _f8]
+    L.pnpb200_comm_unique_id.argtypes = [C.c_char_p]
+    L.pnpb200_comm_init.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
+    L.pnpb200_set_partition.argtypes = [H, C.c_int, C.c_int, _i4, _i4, _i4, _i4]
     # FASP-compatible surface
     L.fasp_param_input.argtypes = [C.c_char_p, C.POINTER(input_param)]
     L.fasp_param_input.restype = None
@@ -245,6 +248,15 @@ class PNP:
         xyz = np.zeros(3 * self.nv); cells = np.zeros(4 * self.nc, dtype=np.int32)
         _check(self.L.pnpb200_get_mesh(self.h, xyz.ctypes.data, cells.ctypes.data), "get_mesh")
         return xyz, cells
+
+    def set_partition(self, part):
+        nb = len(part["nbr"])
+        pad = lambda a: np.ascontiguousarray(a if len(a) else np.zeros(1), dtype=np.int32)
+        _check(self.L.pnpb200_set_partition(self.h, int(part["n_own"]), nb, pad(part["nbr"]), pad(part["send_ptr"]),
+                                            pad(part["send_idx"]), pad(part["recv_ptr"])), "set_partition")
+
+    def comm_init(self, unique_id, rank, nranks):
+        _check(self.L.pnpb200_comm_init(self.h, bytes(unique_id), rank, nranks), "comm_init")
 
     def probe_kernel(self, which, reps=10):
         ms, by = C.c_double(), C.c_double()
@@ -362,6 +374,12 @@ class PNP:
         y = np.zeros(self.N)
         _check(self.L.pnpb200_apply_matrix(self.h, np.ascontiguousarray(x, dtype=np.float64), y), "apply_matrix")
         return y
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().pnpb200_comm_unique_id(buf), "comm_unique_id")
+    return buf.raw
 
 
 def fasp_solver_dbsr_krylov_amg(IA, JA, val, b, it, amg, x0=None):

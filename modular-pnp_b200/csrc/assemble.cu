@@ -351,6 +351,8 @@ void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf)
   PNP_COUNT_LAUNCH();
   PNP_LAUNCH_CHECK();
   if (l2 || linf) {
+    comm_allreduce(h, h.red.p, 1, false);        // sum of squares over all ranks (ghost rows are zero)
+    comm_allreduce(h, h.red.p + 1, 1, true);     // max
     PNP_CUDA(cudaMemcpyAsync(h.h_red, h.red.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     PNP_CUDA(cudaStreamSynchronize(s));
     if (l2) *l2 = sqrt(h.h_red[0]);

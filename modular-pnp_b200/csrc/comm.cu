@@ -1,0 +1,142 @@
+// pnp-b200 — multi-GPU layer: one process per GPU, block rows partitioned by vertex,
+// ghost vertices appended after the owned ones, halo exchange of 3-vectors with grouped
+// ncclSend/ncclRecv and fp64 allreduce of the fused dot-product batches. NCCL is resolved at run
+// time (dlopen) so that the process hosting us (bench.py under torchrun, which has loaded torch's
+// libnccl.so.2 already) does not end up with two copies.
+#include "internal.hpp"
+#include <dlfcn.h>
+#include <cstring>
+
+namespace pnpb200 {
+
+namespace {
+struct ncclUniqueId_t { char internal[128]; };
+typedef int (*fn_getid)(ncclUniqueId_t*);
+typedef int (*fn_init)(void**, int, ncclUniqueId_t, int);
+typedef int (*fn_destroy)(void*);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_sendrecv)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_csendrecv)(const void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_group)(void);
+constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+
+struct Api {
+  void* lib = nullptr;
+  fn_getid getid; fn_init init; fn_destroy destroy; fn_allreduce allreduce; fn_csendrecv send; fn_sendrecv recv;
+  fn_group gstart, gend;
+};
+Api& api()
+{
+  static Api a;
+  if (!a.lib) {
+    a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!a.lib) throw Error(ERROR_DEVICE, std::string("cannot load libnccl.so.2: ") + dlerror());
+    auto sym = [&](const char* n) { void* f = dlsym(a.lib, n); if (!f) throw Error(ERROR_DEVICE, std::string("NCCL symbol missing: ") + n); return f; };
+    a.getid = (fn_getid)sym("ncclGetUniqueId"); a.init = (fn_init)sym("ncclCommInitRank");
+    a.destroy = (fn_destroy)sym("ncclCommDestroy"); a.allreduce = (fn_allreduce)sym("ncclAllReduce");
+    a.send = (fn_csendrecv)sym("ncclSend"); a.recv = (fn_sendrecv)sym("ncclRecv");
+    a.gstart = (fn_group)sym("ncclGroupStart"); a.gend = (fn_group)sym("ncclGroupEnd");
+  }
+  return a;
+}
+inline void nccl_check(int rc, const char* what)
+{
+  if (rc != 0) throw Error(ERROR_DEVICE, std::string("NCCL failure in ") + what + " (code " + std::to_string(rc) + ")");
+}
+
+// sendbuf[3*q + k] = vec[3*idx[q] + k]
+__global__ void pack3_kernel(int n, const int* __restrict__ idx, const double* __restrict__ vec, double* __restrict__ buf)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * n) return;
+  buf[e] = vec[3 * (size_t)idx[e / 3] + e % 3];
+}
+} // namespace
+
+Comm::~Comm() { if (nccl) { try { api().destroy(nccl); } catch (...) {} } }
+
+void comm_allreduce(Handle& h, double* dev, int count, bool is_max)
+{
+  if (!h.comm.nccl || h.comm.nranks == 1) return;
+  nccl_check(api().allreduce(dev, dev, (size_t)count, NCCL_DOUBLE, is_max ? NCCL_MAX : NCCL_SUM, h.comm.nccl, h.stream), "allreduce");
+}
+
+// refresh the ghost entries of a dof vector (3 per vertex) from their owners
+void halo_exchange(Handle& h, double* vec)
+{
+  Comm& c = h.comm;
+  if (!c.nccl || c.nbr.empty()) return;
+  cudaStream_t s = h.stream;
+  const int nsend = c.send_ptr.back();
+  if (nsend > 0) { pack3_kernel<<<cdiv(3 * (size_t)nsend, 256), 256, 0, s>>>(nsend, c.send_idx.p, vec, c.sendbuf.p); PNP_COUNT_LAUNCH(); }
+  Api& a = api();
+  nccl_check(a.gstart(), "groupStart");
+  for (size_t k = 0; k < c.nbr.size(); ++k) {
+    const int ns = c.send_ptr[k + 1] - c.send_ptr[k], nr = c.recv_ptr[k + 1] - c.recv_ptr[k];
+    if (ns > 0) nccl_check(a.send(c.sendbuf.p + 3 * (size_t)c.send_ptr[k], 3 * (size_t)ns, NCCL_DOUBLE, c.nbr[k], c.nccl, s), "send");
+    if (nr > 0) nccl_check(a.recv(vec + 3 * (size_t)c.recv_ptr[k], 3 * (size_t)nr, NCCL_DOUBLE, c.nbr[k], c.nccl, s), "recv");
+  }
+  nccl_check(a.gend(), "groupEnd");
+}
+
+} // namespace pnpb200
+
+using namespace pnpb200;
+struct pnpb200_handle { Handle h; };
+
+extern "C" {
+
+int pnpb200_comm_unique_id(unsigned char id[128])
+{
+  try {
+    ncclUniqueId_t u;
+    nccl_check(api().getid(&u), "ncclGetUniqueId");
+    memcpy(id, u.internal, 128);
+    return FASP_SUCCESS;
+  } catch (const Error& e) { fprintf(stderr, "### pnpb200 ERROR: %s\n", e.what()); return e.code; }
+}
+
+int pnpb200_comm_init(pnpb200_handle* ph, const unsigned char id[128], int rank, int n_ranks)
+{
+  if (!ph || !id || rank < 0 || rank >= n_ranks) return ERROR_INPUT_PAR;
+  try {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaSetDevice(h.device));
+    ncclUniqueId_t u; memcpy(u.internal, id, 128);
+    nccl_check(api().init(&h.comm.nccl, n_ranks, u, rank), "ncclCommInitRank");
+    h.comm.rank = rank; h.comm.nranks = n_ranks;
+    return FASP_SUCCESS;
+  } catch (const Error& e) { fprintf(stderr, "### pnpb200 ERROR: %s\n", e.what()); return e.code; }
+}
+
+int pnpb200_set_partition(pnpb200_handle* ph, int n_owned, int n_neighbors, const int* neighbor_ranks,
+                          const int* send_ptr, const int* send_idx, const int* recv_ptr)
+{
+  if (!ph || n_owned < 1 || n_neighbors < 0) return ERROR_INPUT_PAR;
+  try {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    if (n_owned > h.nv) throw Error(ERROR_INPUT_PAR, "n_owned exceeds the local vertex count");
+    Comm& c = h.comm;
+    h.n_own = n_owned;
+    c.nbr.assign(neighbor_ranks, neighbor_ranks + n_neighbors);
+    c.send_ptr.assign(send_ptr, send_ptr + n_neighbors + 1);
+    c.recv_ptr.assign(recv_ptr, recv_ptr + n_neighbors + 1);
+    const int nsend = n_neighbors ? c.send_ptr.back() : 0;
+    for (int q = 0; q < nsend; ++q) if (send_idx[q] < 0 || send_idx[q] >= n_owned) throw Error(ERROR_INPUT_PAR, "send index is not an owned vertex");
+    for (int k = 0; k <= n_neighbors; ++k) if (c.recv_ptr[k] < n_owned || c.recv_ptr[k] > h.nv) throw Error(ERROR_INPUT_PAR, "ghost range outside [n_owned, n_local]");
+    c.send_idx.alloc(nsend ? nsend : 1, s);
+    if (nsend) c.send_idx.upload(send_idx, nsend);
+    c.sendbuf.alloc(3 * (size_t)(nsend ? nsend : 1), s);
+    // ghost dofs become identity rows of the local matrix (like Dirichlet rows)
+    const size_t N = 3 * (size_t)h.nv;
+    std::vector<unsigned char> f = h.bc_user;
+    f.resize(N, 0);
+    for (size_t i = 3 * (size_t)n_owned; i < N; ++i) f[i] = 1;
+    h.bcflag.upload(f.data(), N);
+    PNP_CUDA(cudaStreamSynchronize(s));
+    return FASP_SUCCESS;
+  } catch (const Error& e) { fprintf(stderr, "### pnpb200 ERROR: %s\n", e.what()); return e.code; }
+}
+
+}

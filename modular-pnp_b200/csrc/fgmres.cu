@@ -29,7 +29,10 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
 {
   cudaStream_t s = h.stream;
   const BsrT& A = h.hier.lv[0]->A;
-  const size_t n = 3 * (size_t)A.n;
+  const size_t n = 3 * (size_t)A.n;          // local vector length (owned + ghost dofs) = basis stride
+  const size_t m = owned_dofs(h);            // reductions and updates run over the owned dofs only
+  const bool dist = h.comm.nccl != nullptr && h.comm.nranks > 1;
+  auto zero_ghost = [&](double* v) { if (n > m) PNP_CUDA(cudaMemsetAsync(v + m, 0, (n - m) * sizeof(double), s)); };
   const int MaxIt = cfg.maxit;
   const int restart_max = cfg.restart < 1 ? 1 : cfg.restart, restart_min = 3, dstep = 3;
   const double cr_max = 0.99, cr_min = 0.174, epsmac = 1e-20;
@@ -45,9 +48,10 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
   std::vector<double> c(restart_max), sn(restart_max), rs(restart_max + 1), hcol(restart_max + 2), h2(restart_max + 2),
       neg(restart_max + 1);
 
-  const double b_norm = vec_norm2(h, b, n);
+  const double b_norm = vec_norm2(h, b, m);
+  if (dist) halo_exchange(h, x);
   bsrt_residual(A, b, x, Vi(0), s);
-  double r_norm = vec_norm2(h, Vi(0), n), r_norm_old;
+  double r_norm = vec_norm2(h, Vi(0), m), r_norm_old;
   const double den = b_norm > 0.0 ? b_norm : r_norm;
   const double epsilon = cfg.tol * den;
   if (!(r_norm > epsilon)) return 0;
@@ -62,33 +66,34 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
     if (cr > cr_max || iter == 0) Restart = restart_max;
     else if (cr < cr_min) { /* keep */ }
     else { if (Restart - dstep > restart_min) Restart -= dstep; else Restart = restart_max; }
-    vec_scale(1.0 / r_norm, Vi(0), n, s);
+    vec_scale(1.0 / r_norm, Vi(0), m, s);
     int i = 0;
     while (i < Restart && iter < MaxIt) {
       ++i; ++iter;
       {
         PhaseTimer t(h, h.stats.ms_vcycle);
+        zero_ghost(Vi(i - 1));     // the preconditioner is local to the rank (block Jacobi across GPUs)
         if (cfg.use_amg) amg_vcycle(h, cfg, Vi(i - 1), Zi(i - 1));
         else vec_copy(Zi(i - 1), Vi(i - 1), n, s);
       }
-      { PhaseTimer t(h, h.stats.ms_spmv); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
+      { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, Zi(i - 1)); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
       double tnorm;
       {
         PhaseTimer t(h, h.stats.ms_ortho);
-        multi_dot(h, V, n, i, Vi(i), n, hcol.data());
+        multi_dot(h, V, n, i, Vi(i), m, hcol.data());
         const double before = std::sqrt(hcol[i]);
         for (int j = 0; j < i; ++j) neg[j] = -hcol[j];
         double after2 = 0.0;
-        multi_axpy(h, V, n, i, neg.data(), Vi(i), n, &after2);
+        multi_axpy(h, V, n, i, neg.data(), Vi(i), m, &after2);
         if (std::sqrt(after2) < 0.1 * before) {   // DGKS: orthogonalise once more
-          multi_dot(h, V, n, i, Vi(i), n, h2.data());
+          multi_dot(h, V, n, i, Vi(i), m, h2.data());
           for (int j = 0; j < i; ++j) { neg[j] = -h2[j]; hcol[j] += h2[j]; }
-          multi_axpy(h, V, n, i, neg.data(), Vi(i), n, &after2);
+          multi_axpy(h, V, n, i, neg.data(), Vi(i), m, &after2);
         }
         tnorm = std::sqrt(after2);
         for (int j = 0; j < i; ++j) hh[j][i - 1] = hcol[j];
         hh[i][i - 1] = tnorm;
-        if (tnorm != 0.0) vec_scale(1.0 / tnorm, Vi(i), n, s);
+        if (tnorm != 0.0) vec_scale(1.0 / tnorm, Vi(i), m, s);
       }
       if (!std::isfinite(tnorm)) return ERROR_SOLVER_EXIT;
       for (int j = 1; j < i; ++j) {
@@ -115,11 +120,12 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
       t += rs[k];
       rs[k] = t / hh[k][k];
     }
-    multi_axpy(h, Z, n, i, rs.data(), x, n, nullptr);
+    multi_axpy(h, Z, n, i, rs.data(), x, m, nullptr);
     // true residual for the convergence confirmation / next cycle
     const bool est_conv = r_norm <= epsilon;
+    if (dist) halo_exchange(h, x);
     bsrt_residual(A, b, x, Vi(0), s);
-    r_norm = vec_norm2(h, Vi(0), n);
+    r_norm = vec_norm2(h, Vi(0), m);
     if (est_conv && r_norm <= epsilon) { converged = true; break; }
     if (!std::isfinite(r_norm)) return ERROR_SOLVER_EXIT;
     if (r_norm <= epsilon) { converged = true; break; }

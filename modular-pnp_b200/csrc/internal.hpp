@@ -85,12 +85,26 @@ struct StreamOwner {
   ~StreamOwner() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
 };
 
+// multi-GPU state: NCCL communicator, neighbour ranks, halo lists (vertex granularity)
+struct Comm {
+  void* nccl = nullptr;
+  int rank = 0, nranks = 1;
+  std::vector<int> nbr, send_ptr, recv_ptr;   // per neighbour: [send_ptr[k], send_ptr[k+1]) into send_idx;
+                                              // ghosts of neighbour k are local vertices [recv_ptr[k], recv_ptr[k+1])
+  DevBuf<int> send_idx;                       // owned local vertex ids to send
+  DevBuf<double> sendbuf;
+  ~Comm();
+};
+
 struct Handle {
   StreamOwner owner;
   int device = 0;
   cudaStream_t stream = nullptr;
   // mesh
   int nv = 0, nc = 0;
+  int n_own = -1;               // owned vertices (first n_own local ids); -1 = all (single GPU)
+  Comm comm;
+  std::vector<unsigned char> bc_user;   // Dirichlet flags as set by the caller (ghost flags are added on top)
   DevBuf<double> xyz;           // 3*nv
   DevBuf<int> cells;            // 4*nc
   DevBuf<int> v2c_ptr, v2c_idx; // vertex -> incident cells (ascending)
@@ -157,6 +171,10 @@ void multi_dot(Handle& h, const double* V, size_t ld, int nvec, const double* w,
 // w += sum_i coef[i] * V_i ; if norm2_out != null also returns ||w||^2 (sync)
 void multi_axpy(Handle& h, const double* V, size_t ld, int nvec, const double* coef_host, double* w, size_t n,
                 double* norm2_out);
+// ---- comm.cu
+void halo_exchange(Handle& h, double* vec);
+void comm_allreduce(Handle& h, double* dev, int count, bool is_max);
+inline size_t owned_dofs(const Handle& h) { return 3 * (size_t)(h.n_own >= 0 ? h.n_own : h.hier.lv[0]->A.n); }
 // ---- amg.cu
 void amg_setup(Handle& h, const SolverConfig& cfg);
 void amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z);

@@ -131,6 +131,7 @@ void multi_dot(Handle& h, const double* V, size_t ld, int nvec, const double* w,
     PNP_COUNT_LAUNCH();
   }
   reduce_partials_kernel<<<nvec + 1, 256, 0, s>>>(partial, g, h.red.p); PNP_COUNT_LAUNCH();
+  comm_allreduce(h, h.red.p, nvec + 1, false);   // one allreduce for the whole Gram-Schmidt batch
   PNP_CUDA(cudaMemcpyAsync(h.h_red, h.red.p, (nvec + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
   PNP_CUDA(cudaStreamSynchronize(s));
   for (int i = 0; i <= nvec; ++i) out_host[i] = h.h_red[i];
@@ -148,6 +149,7 @@ void multi_axpy(Handle& h, const double* V, size_t ld, int nvec, const double* c
     h.red.alloc((size_t)g + 64, s);
     multi_axpy_kernel<true><<<g, VB, 0, s>>>(V, ld, nvec, cf, w, n, h.red.p + 64); PNP_COUNT_LAUNCH();
     reduce_partials_kernel<<<1, 256, 0, s>>>(h.red.p + 64, g, h.red.p); PNP_COUNT_LAUNCH();
+    comm_allreduce(h, h.red.p, 1, false);
     PNP_CUDA(cudaMemcpyAsync(h.h_red, h.red.p, sizeof(double), cudaMemcpyDeviceToHost, s));
     PNP_CUDA(cudaStreamSynchronize(s));
     *norm2_out = h.h_red[0];

@@ -43,3 +43,28 @@ def exact_solution_problem(nx, ny, nz, lx=2.0, ly=0.4, lz=0.4):
     bcv = np.nonzero((ix == 0) | (ix == nx))[0]
     out["bc_dofs"] = (3 * bcv[:, None] + np.arange(3)[None, :]).ravel().astype(np.int32)
     return out
+
+
+def exact_solution_fields(x):
+    """Same physics for an arbitrary list of vertex x-coordinates (one entry per local vertex of a
+    partitioned mesh): returns dict(eps, fixed, diff, val, reac, uu0, exact) in dof order 3*v+k.
+    The Dirichlet interpolant uses the global x-range [-1, 1] of the benchmark boxes."""
+    x = np.asarray(x, dtype=np.float64)
+    nv = x.shape[0]
+    E, cref, perm = 1.0, 1.0, 1.0
+    s = np.stack([x * E + np.sin(PI * x), np.log(cref) - x * x * E, np.log(cref) + x * x * E], axis=1)
+    ds = np.stack([E + PI * np.cos(PI * x), -2.0 * x * E, 2.0 * x * E], axis=1)
+    dds = np.stack([-(PI * PI) * np.sin(PI * x), -2.0 * E * np.ones_like(x), 2.0 * E * np.ones_like(x)], axis=1)
+    D = np.array([0.0, 1.0, 1.0])
+    reac = np.zeros((nv, 3))
+    reac[:, 1] = -D[1] * np.exp(s[:, 1]) * (ds[:, 1] * (ds[:, 1] + ds[:, 0]) + (dds[:, 1] + dds[:, 0]))
+    reac[:, 2] = -D[2] * np.exp(s[:, 2]) * (ds[:, 2] * (ds[:, 2] - ds[:, 0]) + (dds[:, 2] - dds[:, 0]))
+    left = np.array([-1.0 * E + np.sin(PI * -1.0), np.log(cref) - 1.0 * E, np.log(cref) + 1.0 * E])
+    right = np.array([1.0 * E + np.sin(PI * 1.0), np.log(cref) - 1.0 * E, np.log(cref) + 1.0 * E])
+    xmin, xmax = -1.0, 1.0
+    dist = 1.0 / (xmax - xmin)
+    init = left[None, :] * ((xmax - x) * dist)[:, None]
+    init = init + right[None, :] * ((x - xmin) * dist)[:, None]
+    return dict(eps=np.full(nv, perm), fixed=-perm * dds[:, 0] - (np.exp(s[:, 1]) - np.exp(s[:, 2])),
+                diff=np.ascontiguousarray(np.tile(D, nv)), val=np.ascontiguousarray(np.tile(np.array([0.0, 1.0, -1.0]), nv)),
+                reac=np.ascontiguousarray(reac.ravel()), uu0=np.ascontiguousarray(init.ravel()), exact=np.ascontiguousarray(s.ravel()))

@@ -1,0 +1,66 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): the row-partitioned Newton step (NCCL halo exchange
++ allreduce, one process per GPU) against the single-GPU path on the same global mesh."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent('''
+    import os, sys
+    import numpy as np
+    import torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from pnpb200_loader import load_package
+    from importlib import import_module
+    pkg = load_package()
+    part_mod = import_module("modular_pnp_b200.partition"); prob = import_module("modular_pnp_b200.problems")
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    nx, ny, nz, lx, ly, lz = 24, 10, 24, 2.0, 0.8, 2.0
+    P = part_mod.box_slab_partition(nx, ny, nz, lx, ly, lz, rank, world)
+    g = pkg.PNP(P["xyz"], P["cells"], device=rank)
+    uid = [pkg.capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    g.comm_init(uid[0], rank, world); g.set_partition(P)
+    f = prob.exact_solution_fields(P["xyz"][0::3])
+    g.set_coefficients(f["eps"], f["fixed"], f["diff"], f["val"], f["reac"])
+    g.set_dirichlet((3 * P["bc_vertices"][:, None] + np.arange(3)).ravel().astype(np.int32))
+    g.set_solution(f["uu0"])
+    it, amg = pkg.default_params()
+    r0 = g.residual()
+    hist = [g.newton_step(it, amg) for _ in range(3)]
+    uu = g.get_solution()[:3 * P["n_own"]]
+    g.close()
+    if rank == 0:
+        s = pkg.PNP(box=(nx, ny, nz, lx, ly, lz), device=0)
+        pr = prob.exact_solution_problem(nx, ny, nz, lx, ly, lz)
+        s.set_coefficients(pr["eps"], pr["fixed"], pr["diff"], pr["val"], pr["reac"]); s.set_dirichlet(pr["bc_dofs"]); s.set_solution(pr["uu0"])
+        q0 = s.residual()
+        ref = [s.newton_step(it, amg) for _ in range(3)]
+        uu_ref = s.get_solution()[:3 * P["n_own"]]
+        s.close()
+        assert abs(r0[0] - q0[0]) <= 1e-12 * q0[0] and abs(r0[1] - q0[1]) <= 1e-12 * q0[1], (r0, q0)
+        for (st, l2, mx), (st2, l22, mx2) in zip(hist, ref):
+            assert st > 0 and st2 > 0
+            assert abs(l2 - l22) <= 2e-3 * l22, (hist, ref)
+        assert np.abs(uu - uu_ref).max() <= 1e-4
+        print("MULTI_OK", [h[0] for h in hist], [h[0] for h in ref])
+    dist.barrier(); dist.destroy_process_group()
+''') % ROOT
+
+
+def test_two_gpu_newton_matches_single_gpu(gpu_lib, tmp_path):
+    if gpu_lib.pnpb200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29621", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTI_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
