@@ -305,7 +305,7 @@ def main():
         e2e_v = world * K / (ms_e2e / 1e3)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=("1 GPU" if world == 1 else "%d GPUs: block rows in z-slabs of a %dx%dx%d box (%.1f M dof), NCCL halo exchange + fp64 allreduce, rank-local AMG (block Jacobi across GPUs)" % (world, n, n, n * world, 3 * (n + 1) * (n + 1) * (n * world + 1) / 1e6))),
+               "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=("1 GPU" if world == 1 else "%d GPUs: block rows in z-slabs of a %dx%dx%d box (%.1f M dof), NCCL halo exchange at every AMG level + fp64 allreduce, aggregates local to a rank, replicated dense coarsest solve" % (world, n, n, n * world, 3 * (n + 1) * (n + 1) * (n * world + 1) / 1e6))),
                "krylov_its_per_step": its, "krylov_status_ok": bool(kits > 0),
                "relative_residual_after_step": None if last is None else last[1],
                "levels": [[stats.level_rows[l], stats.level_nnzb[l], stats.level_colors[l]] for l in range(stats.n_levels)],

@@ -14,6 +14,7 @@
 #include "internal.hpp"
 #include <cub/cub.cuh>
 #include <cmath>
+#include <algorithm>
 
 namespace pnpb200 {
 
@@ -175,6 +176,12 @@ __global__ void agg_finalize_kernel(int n, int* __restrict__ agg)
   if (i < n && agg[i] < -1) agg[i] = -1;
 }
 
+__global__ void gather_int_kernel(int n, const int* __restrict__ idx, const int* __restrict__ v, int* __restrict__ out)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) out[e] = v[idx[e]];
+}
+
 __global__ void agg_count_kernel(int n, const int* __restrict__ agg, int* __restrict__ cnt)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,13 +201,16 @@ __global__ void agg_key_kernel(int n, const int* __restrict__ agg, unsigned* __r
 }
 
 // ---- Galerkin product with the boolean prolongator ------------------------------------------
-__global__ void rap_key_kernel(int nnzb, const int* __restrict__ ja, const int* __restrict__ brow,
+// key of fine block b = (coarse row, coarse column); only coarse rows owned by this rank are formed
+// here. Entries nnzb .. nnzb+nghost-1 are the identity diagonals of the coarse ghost rows (idx = -1).
+__global__ void rap_key_kernel(int nnzb, int nghost, int nown_c, const int* __restrict__ ja, const int* __restrict__ brow,
                                const int* __restrict__ agg, u64 nagg, u64* __restrict__ key, int* __restrict__ idx)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nnzb) return;
+  if (b >= nnzb + nghost) return;
+  if (b >= nnzb) { const u64 G = (u64)(nown_c + (b - nnzb)); key[b] = G * nagg + G; idx[b] = -1; return; }
   const int I = agg[brow[b]], J = agg[ja[b]];
-  key[b] = (I >= 0 && J >= 0) ? (u64)I * nagg + (u64)J : ~0ull;
+  key[b] = (I >= 0 && I < nown_c && J >= 0) ? (u64)I * nagg + (u64)J : ~0ull;
   idx[b] = b;
 }
 
@@ -256,6 +266,7 @@ __global__ void rap_numeric_kernel(int cnnzb, const int* __restrict__ cia, const
   double acc = 0.0;
   for (int p = beg[s]; p < end[s]; ++p) {
     const int b = perm[p];
+    if (b < 0) { acc += (t == 0 || t == 4 || t == 8) ? 1.0 : 0.0; continue; }   // identity row of a coarse ghost
     const int i = fbrow[b], fs = frs[i], flen = fia[i + 1] - fia[i];
     acc += fval[9 * (size_t)fs + (size_t)t * flen + (b - fs)];
   }
@@ -506,7 +517,18 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   int nagg = 0;
   PNP_CUDA(cudaMemcpyAsync(&nagg, rootid.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
   PNP_CUDA(cudaStreamSynchronize(s));
-  if (nagg == 0 || nagg >= n) return false;
+  const bool dist = h.comm.active();
+  const int n_own = owned_rows(L);
+  {
+    int fail = (nagg == 0 || nagg >= n_own) ? 1 : 0;
+    if (dist) {      // every rank must take the same branch (the cycle is a collective)
+      PNP_CUDA(cudaMemcpyAsync(cnt.p, &fail, sizeof(int), cudaMemcpyHostToDevice, s));
+      comm_allreduce_int(h, cnt.p, 1, true);
+      PNP_CUDA(cudaMemcpyAsync(&fail, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      PNP_CUDA(cudaStreamSynchronize(s));
+    }
+    if (fail) return false;
+  }
   L.agg.alloc(n, s);
   agg_root_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, state.p, rootid.p, iso.p, L.agg.p); PNP_COUNT_LAUNCH();
   int left = 1; int* cur = L.agg.p; int* nxt = agg2.p;
@@ -519,14 +541,56 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   }
   if (cur != L.agg.p) PNP_CUDA(cudaMemcpyAsync(L.agg.p, cur, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
   agg_finalize_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.agg.p); PNP_COUNT_LAUNCH();
-  L.nagg = nagg;
+  L.nagg = nagg;                 // aggregates owned by this rank = owned coarse rows
+  // multi-GPU: aggregates never cross ranks. A ghost row learns its owner's aggregate; the distinct
+  // remote aggregates a neighbour references become the ghost rows of the coarse level (ascending
+  // owner-local id on both sides, so sender and receiver agree on the order without talking)
+  int ncoarse = nagg;
+  C.n_own = -1; C.halo = Halo();
+  if (dist) {
+    Halo& hl = L.halo; Halo& hc = C.halo;
+    halo_exchange_int(h, hl, L.agg.p);
+    const int nghost = n - n_own, nsend = hl.active() ? hl.send_ptr.back() : 0;
+    std::vector<int> gval(nghost > 0 ? nghost : 1), sval(nsend > 0 ? nsend : 1);
+    if (nghost > 0) PNP_CUDA(cudaMemcpyAsync(gval.data(), L.agg.p + n_own, (size_t)nghost * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (nsend > 0) {
+      hl.isendbuf.alloc(nsend, s);
+      gather_int_kernel<<<cdiv(nsend, 256), 256, 0, s>>>(nsend, hl.send_idx.p, L.agg.p, hl.isendbuf.p); PNP_COUNT_LAUNCH();
+      PNP_CUDA(cudaMemcpyAsync(sval.data(), hl.isendbuf.p, (size_t)nsend * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    PNP_CUDA(cudaStreamSynchronize(s));
+    hc.nbr = hl.nbr; hc.send_ptr.assign(1, 0); hc.recv_ptr.assign(1, nagg);
+    std::vector<int> csend;
+    for (size_t k = 0; k < hl.nbr.size(); ++k) {
+      std::vector<int> u(gval.begin() + (hl.recv_ptr[k] - n_own), gval.begin() + (hl.recv_ptr[k + 1] - n_own));
+      std::sort(u.begin(), u.end()); u.erase(std::unique(u.begin(), u.end()), u.end());
+      while (!u.empty() && u.front() < 0) u.erase(u.begin());
+      const int base = hc.recv_ptr.back();
+      for (int g = hl.recv_ptr[k] - n_own; g < hl.recv_ptr[k + 1] - n_own; ++g)
+        if (gval[g] >= 0) gval[g] = base + (int)(std::lower_bound(u.begin(), u.end(), gval[g]) - u.begin());
+      hc.recv_ptr.push_back(base + (int)u.size());
+      std::vector<int> v(sval.begin() + hl.send_ptr[k], sval.begin() + hl.send_ptr[k + 1]);
+      std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end());
+      while (!v.empty() && v.front() < 0) v.erase(v.begin());
+      csend.insert(csend.end(), v.begin(), v.end());
+      hc.send_ptr.push_back((int)csend.size());
+    }
+    ncoarse = hc.recv_ptr.back();
+    if (nghost > 0) PNP_CUDA(cudaMemcpyAsync(L.agg.p + n_own, gval.data(), (size_t)nghost * sizeof(int), cudaMemcpyHostToDevice, s));
+    hc.send_idx.alloc(csend.empty() ? 1 : csend.size(), s);
+    if (!csend.empty()) hc.send_idx.upload(csend.data(), csend.size());
+    hc.sendbuf.alloc(3 * (csend.empty() ? 1 : csend.size()), s);
+    PNP_CUDA(cudaStreamSynchronize(s));     // gval / csend are host temporaries
+    C.n_own = nagg;
+  }
+  const int nghost_c = ncoarse - nagg;
   // members of each aggregate (ascending rows)
   {
-    struct { int* p; } c; c.p = ws.get<int>(nagg + 1);
-    PNP_CUDA(cudaMemsetAsync(c.p, 0, (size_t)(nagg + 1) * sizeof(int), s));
+    struct { int* p; } c; c.p = ws.get<int>(ncoarse + 1);
+    PNP_CUDA(cudaMemsetAsync(c.p, 0, (size_t)(ncoarse + 1) * sizeof(int), s));
     agg_count_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.agg.p, c.p); PNP_COUNT_LAUNCH();
-    L.agg_ptr.alloc(nagg + 1, s);
-    exclusive_scan_int(c.p, L.agg_ptr.p, nagg + 1, s);
+    L.agg_ptr.alloc(ncoarse + 1, s);
+    exclusive_scan_int(c.p, L.agg_ptr.p, ncoarse + 1, s);
     struct { unsigned* p; } kin, kout; kin.p = ws.get<unsigned>(n); kout.p = ws.get<unsigned>(n);
     struct { int* p; } vin; vin.p = ws.get<int>(n); L.agg_rows.alloc(n, s);
     agg_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, L.agg.p, kin.p); PNP_COUNT_LAUNCH();
@@ -535,27 +599,29 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   }
   // coarse structure: sort blocks by (I,J)
   {
-    struct { u64* p; } kin, kout; kin.p = ws.get<u64>(nnzb); kout.p = ws.get<u64>(nnzb);
-    struct { int* p; } vin; vin.p = ws.get<int>(nnzb); L.rap_perm.alloc(nnzb, s);
-    rap_key_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, L.agg.p, (u64)nagg, kin.p, vin.p); PNP_COUNT_LAUNCH();
-    sort_pairs(ws, kin.p, kout.p, vin.p, L.rap_perm.p, nnzb, 2 * bits_for((u64)nagg) + 1, s);
-    struct { int* p; } head, slot; head.p = ws.get<int>(nnzb + 1); slot.p = ws.get<int>(nnzb + 1);
-    rap_head_kernel<<<cdiv(nnzb + 1, 256), 256, 0, s>>>(nnzb, kout.p, head.p); PNP_COUNT_LAUNCH();
-    exclusive_scan_int(head.p, slot.p, nnzb + 1, s);
+    const int nnzx = nnzb + nghost_c;      // fine blocks + identity diagonals of the coarse ghost rows
+    const u64 nagg64 = (u64)ncoarse;
+    struct { u64* p; } kin, kout; kin.p = ws.get<u64>(nnzx); kout.p = ws.get<u64>(nnzx);
+    struct { int* p; } vin; vin.p = ws.get<int>(nnzx); L.rap_perm.alloc(nnzx, s);
+    rap_key_kernel<<<cdiv(nnzx, 256), 256, 0, s>>>(nnzb, nghost_c, nagg, A.ja.p, A.brow.p, L.agg.p, nagg64, kin.p, vin.p); PNP_COUNT_LAUNCH();
+    sort_pairs(ws, kin.p, kout.p, vin.p, L.rap_perm.p, nnzx, 2 * bits_for(nagg64) + 1, s);
+    struct { int* p; } head, slot; head.p = ws.get<int>(nnzx + 1); slot.p = ws.get<int>(nnzx + 1);
+    rap_head_kernel<<<cdiv(nnzx + 1, 256), 256, 0, s>>>(nnzx, kout.p, head.p); PNP_COUNT_LAUNCH();
+    exclusive_scan_int(head.p, slot.p, nnzx + 1, s);
     int cnnzb = 0;
-    PNP_CUDA(cudaMemcpyAsync(&cnnzb, slot.p + nnzb, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaMemcpyAsync(&cnnzb, slot.p + nnzx, sizeof(int), cudaMemcpyDeviceToHost, s));
     PNP_CUDA(cudaStreamSynchronize(s));
     BsrT& Ac = C.A;
-    Ac.n = nagg; Ac.nnzb = cnnzb;
-    Ac.ia.alloc(nagg + 1, s); Ac.val.alloc(9 * (size_t)cnnzb, s);
+    Ac.n = ncoarse; Ac.nnzb = cnnzb;
+    Ac.ia.alloc(ncoarse + 1, s); Ac.val.alloc(9 * (size_t)cnnzb, s);
     struct { int* p; } cja_nat, crow, seg; cja_nat.p = ws.get<int>(cnnzb); crow.p = ws.get<int>(cnnzb); seg.p = ws.get<int>(cnnzb + 1);
     L.rap_beg.alloc(cnnzb, s); L.rap_end.alloc(cnnzb, s);
-    struct { int* p; } rowcnt; rowcnt.p = ws.get<int>(nagg + 1);
-    PNP_CUDA(cudaMemsetAsync(rowcnt.p, 0, (size_t)(nagg + 1) * sizeof(int), s));
+    struct { int* p; } rowcnt; rowcnt.p = ws.get<int>(ncoarse + 1);
+    PNP_CUDA(cudaMemsetAsync(rowcnt.p, 0, (size_t)(ncoarse + 1) * sizeof(int), s));
     int* nvalid = seg.p + cnnzb;
-    rap_structure_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, kout.p, head.p, slot.p, (u64)nagg, cja_nat.p, crow.p, seg.p,
+    rap_structure_kernel<<<cdiv(nnzx, 256), 256, 0, s>>>(nnzx, kout.p, head.p, slot.p, nagg64, cja_nat.p, crow.p, seg.p,
                                                         rowcnt.p, nvalid); PNP_COUNT_LAUNCH();
-    exclusive_scan_int(rowcnt.p, Ac.ia.p, nagg + 1, s);
+    exclusive_scan_int(rowcnt.p, Ac.ia.p, ncoarse + 1, s);
     // colour the coarse graph and store it colour by colour, then re-key the numeric map
     color_and_layout(C, cja_nat.p, &ws, s);
     rap_remap_kernel<<<cdiv(cnnzb, 256), 256, 0, s>>>(cnnzb, crow.p, Ac.ia.p, Ac.rs.p, seg.p, L.rap_beg.p, L.rap_end.p);
@@ -604,6 +670,138 @@ SolverConfig make_config(const itsolver_param* it, const AMG_param* amg)
   return c;
 }
 
+namespace {
+
+// (sum of owned rows over ranks, min of owned rows over ranks) — a collective when distributed
+void global_rows(Handle& h, int own, int* sum, int* mn)
+{
+  *sum = own; *mn = own;
+  if (!h.comm.active()) return;
+  cudaStream_t s = h.stream;
+  DevBuf<int> t; t.alloc(2, s);
+  int v[2] = {own, -own};
+  PNP_CUDA(cudaMemcpyAsync(t.p, v, 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+  comm_allreduce_int(h, t.p, 1, false);
+  comm_allreduce_int(h, t.p + 1, 1, true);
+  PNP_CUDA(cudaMemcpyAsync(v, t.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  *sum = v[0]; *mn = -v[1];
+}
+
+__global__ void gid_kernel(int n_own, int offset, int* __restrict__ gid)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_own) gid[i] = offset + i;
+}
+
+// dense rows of the owned block rows with GLOBAL column ids (row-major, ld = ndg)
+__global__ void dense_fill_rows_kernel(int nnzb, int n_own, int ndg, const int* __restrict__ ia, const int* __restrict__ rs,
+                                       const int* __restrict__ ja, const int* __restrict__ brow, const int* __restrict__ gid,
+                                       const double* __restrict__ val, double* __restrict__ D)
+{
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 9 * (size_t)nnzb) return;
+  const int b = (int)(e / 9), t = (int)(e % 9);
+  const int i = brow[b];
+  if (i >= n_own) return;
+  const int s = rs[i], len = ia[i + 1] - ia[i];
+  D[(size_t)(3 * i + t / 3) * ndg + 3 * gid[ja[b]] + t % 3] = val[9 * (size_t)s + (size_t)t * len + (b - s)];
+}
+
+// bglob[3*off[r] + q] = ball[r*3*maxown + q], q < 3*cnt[r]
+__global__ void compact_b_kernel(int nranks, int maxown3, const int* __restrict__ off3, const int* __restrict__ cnt3,
+                                 const double* __restrict__ ball, double* __restrict__ bglob)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nranks * maxown3) return;
+  const int r = e / maxown3, q = e % maxown3;
+  if (q < cnt3[r]) bglob[off3[r] + q] = ball[e];
+}
+
+// x[row] = Inv[row0 + row, :] . b   for row < nrows, one warp per row
+__global__ void dense_matvec_rows_kernel(int nrows, int row0, int nd, const double* __restrict__ Inv,
+                                         const double* __restrict__ b, double* __restrict__ x)
+{
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  double a = 0.0;
+  for (int c = lane; c < nd; c += 32) a += Inv[(size_t)(row0 + row) * nd + c] * b[c];
+  a = warp_sum(a);
+  if (lane == 0) x[row] = a;
+}
+
+// coarsest level: every rank inverts the (small) GLOBAL coarsest matrix
+void setup_coarsest(Handle& h)
+{
+  cudaStream_t s = h.stream;
+  Hierarchy& H = h.hier;
+  Level& Z = *H.lv.back();
+  const int nr = h.comm.active() ? h.comm.nranks : 1, me = h.comm.active() ? h.comm.rank : 0;
+  const int own = owned_rows(Z);
+  DevBuf<int> t; t.alloc(nr + 1, s);
+  PNP_CUDA(cudaMemcpyAsync(t.p + nr, &own, sizeof(int), cudaMemcpyHostToDevice, s));
+  comm_allgather(h, t.p + nr, t.p, sizeof(int));
+  std::vector<int> cnt = t.to_host(nr);
+  std::vector<int> off(nr + 1, 0);
+  int maxown = 1;
+  for (int r = 0; r < nr; ++r) { off[r + 1] = off[r] + cnt[r]; if (cnt[r] > maxown) maxown = cnt[r]; }
+  const int ng = off[nr], nd = 3 * ng;
+  if (nd > 6144) throw Error(ERROR_AMG_COARSEING, "coarsest level too large for the dense solver");
+  H.nd = nd; H.c_own = own; H.c_row0 = 3 * off[me]; H.c_maxown3 = 3 * maxown; H.c_nranks = nr;
+  std::vector<int> off3(nr), cnt3(nr);
+  for (int r = 0; r < nr; ++r) { off3[r] = 3 * off[r]; cnt3[r] = 3 * cnt[r]; }
+  H.c_off3.alloc(nr, s); H.c_cnt3.alloc(nr, s);
+  H.c_off3.upload(off3.data(), nr); H.c_cnt3.upload(cnt3.data(), nr);
+  // global ids of the local rows (ghosts from their owners)
+  DevBuf<int> gid; gid.alloc(Z.A.n > 0 ? Z.A.n : 1, s);
+  if (own > 0) { gid_kernel<<<cdiv(own, 256), 256, 0, s>>>(own, off[me], gid.p); PNP_COUNT_LAUNCH(); }
+  halo_exchange_int(h, Z.halo, gid.p);
+  // my dense rows, padded to the largest rank, then gathered and compacted
+  const size_t rowblk = (size_t)3 * maxown * nd;
+  DevBuf<double> Drow, Dall, D, colk; DevBuf<int> sing;
+  Drow.alloc(rowblk, s); Drow.zero();
+  Dall.alloc(rowblk * nr, s);
+  if (Z.A.nnzb > 0) {
+    dense_fill_rows_kernel<<<cdiv(9 * (size_t)Z.A.nnzb, 256), 256, 0, s>>>(Z.A.nnzb, own, nd, Z.A.ia.p, Z.A.rs.p, Z.A.ja.p, Z.A.brow.p,
+                                                                          gid.p, Z.A.val.p, Drow.p);
+    PNP_COUNT_LAUNCH();
+  }
+  comm_allgather(h, Drow.p, Dall.p, rowblk * sizeof(double));
+  D.alloc((size_t)nd * nd, s); colk.alloc(nd, s); sing.alloc(1, s); sing.zero();
+  for (int r = 0; r < nr; ++r)
+    if (cnt[r] > 0)
+      PNP_CUDA(cudaMemcpyAsync(D.p + (size_t)3 * off[r] * nd, Dall.p + rowblk * r, (size_t)3 * cnt[r] * nd * sizeof(double),
+                               cudaMemcpyDeviceToDevice, s));
+  H.dense_inv.alloc((size_t)nd * nd, s);
+  identity_kernel<<<cdiv((size_t)nd * nd, 256), 256, 0, s>>>(nd, H.dense_inv.p); PNP_COUNT_LAUNCH();
+  dense_invert_kernel<<<1, 1024, 0, s>>>(nd, D.p, H.dense_inv.p, colk.p, sing.p); PNP_COUNT_LAUNCH();
+  H.c_bpad.alloc((size_t)3 * maxown, s); H.c_ball.alloc((size_t)3 * maxown * nr, s); H.c_bglob.alloc(nd, s);
+  PNP_CUDA(cudaStreamSynchronize(s));     // host staging vectors above go out of scope
+  PNP_LAUNCH_CHECK();
+}
+
+void solve_coarsest(Handle& h, const double* b, double* x)
+{
+  cudaStream_t s = h.stream;
+  Hierarchy& H = h.hier;
+  const double* bg = b;
+  if (H.c_nranks > 1) {
+    PNP_CUDA(cudaMemsetAsync(H.c_bpad.p, 0, (size_t)H.c_maxown3 * sizeof(double), s));
+    if (H.c_own > 0) PNP_CUDA(cudaMemcpyAsync(H.c_bpad.p, b, (size_t)3 * H.c_own * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    comm_allgather(h, H.c_bpad.p, H.c_ball.p, (size_t)H.c_maxown3 * sizeof(double));
+    compact_b_kernel<<<cdiv((size_t)H.c_nranks * H.c_maxown3, 256), 256, 0, s>>>(H.c_nranks, H.c_maxown3, H.c_off3.p, H.c_cnt3.p,
+                                                                                H.c_ball.p, H.c_bglob.p);
+    PNP_COUNT_LAUNCH();
+    bg = H.c_bglob.p;
+  }
+  if (H.c_own > 0) {
+    dense_matvec_rows_kernel<<<cdiv((size_t)3 * H.c_own * 32, 256), 256, 0, s>>>(3 * H.c_own, H.c_row0, H.nd, H.dense_inv.p, bg, x);
+    PNP_COUNT_LAUNCH();
+  }
+}
+
+} // namespace
+
 void amg_setup(Handle& h, const SolverConfig& cfg)
 {
   cudaStream_t s = h.stream;
@@ -623,7 +821,12 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
       rap_numeric(h, L, *lv[l + 1]);
       ++l; continue;
     }
-    if (!(L.A.n > min_cdof && l < cfg.max_levels - 1)) break;
+    // the decision to coarsen further is taken on GLOBAL sizes so that every rank builds the
+    // same number of levels (each level of the cycle is a collective)
+    int nglob, nmin;
+    global_rows(h, owned_rows(L), &nglob, &nmin);
+    if (!(nglob > min_cdof && l < cfg.max_levels - 1)) break;
+    if (h.comm.active() && nmin < 8) break;
     const double theta = cfg.tentative_smooth > 1e-20 ? cfg.strong_coupled * std::pow(0.5, l) : cfg.strong_coupled;
     // Level objects (and their device buffers) are recycled from the previous hierarchy
     if (l + 1 >= (int)lv.size()) lv.emplace_back(new Level);
@@ -635,25 +838,13 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
     ++l;
   }
   if (!reuse) lv.resize(l + 1);
-  // coarsest level: explicit dense inverse
-  Level& Z = *lv.back();
-  const int nd = 3 * Z.A.n;
-  if (nd > 6144) throw Error(ERROR_AMG_COARSEING, "coarsest level too large for the dense solver");
-  h.hier.nd = nd;
-  DevBuf<double> D, colk; DevBuf<int> sing;
-  D.alloc((size_t)nd * nd, s); colk.alloc(nd, s); sing.alloc(1, s); sing.zero();
-  h.hier.dense_inv.alloc((size_t)nd * nd, s);
-  D.zero();
-  dense_fill_kernel<<<cdiv(9 * (size_t)Z.A.nnzb, 256), 256, 0, s>>>(Z.A.nnzb, nd, Z.A.ia.p, Z.A.rs.p, Z.A.ja.p, Z.A.brow.p, Z.A.val.p, D.p);
-  PNP_COUNT_LAUNCH();
-  identity_kernel<<<cdiv((size_t)nd * nd, 256), 256, 0, s>>>(nd, h.hier.dense_inv.p); PNP_COUNT_LAUNCH();
-  dense_invert_kernel<<<1, 1024, 0, s>>>(nd, D.p, h.hier.dense_inv.p, colk.p, sing.p); PNP_COUNT_LAUNCH();
-  PNP_LAUNCH_CHECK();
+  setup_coarsest(h);
   h.hier.symbolic_valid = true;
   if (cfg.print_level > 0) {
     PNP_CUDA(cudaStreamSynchronize(s));
     for (size_t k = 0; k < lv.size(); ++k)
-      printf("  [pnpb200 amg] level %zu: rows %d nnzb %d colours %d\n", k, lv[k]->A.n, lv[k]->A.nnzb, lv[k]->ncolors);
+      printf("  [pnpb200 amg] rank %d level %zu: rows %d (owned %d) nnzb %d colours %d\n", h.comm.rank, k, lv[k]->A.n, owned_rows(*lv[k]),
+             lv[k]->A.nnzb, lv[k]->ncolors);
   }
 }
 
@@ -663,21 +854,27 @@ inline int small_grid(size_t n) { const size_t b = (n + 255) / 256; return (int)
 
 void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x);
 
-// one multigrid cycle on level l from a zero initial guess: x = B_l b
+// one multigrid cycle on level l from a zero initial guess: x = B_l b. Multi-GPU: hybrid
+// Gauss-Seidel (ghost values refreshed from their owners before every sweep / residual).
 void mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x)
 {
   cudaStream_t s = h.stream;
   Level& L = *h.hier.lv[l];
   Level& C = *h.hier.lv[l + 1];
   const size_t m = 3 * (size_t)L.A.n;
+  const int own = owned_rows(L);
+  const bool dist = h.comm.active();
   vec_set(x, 0.0, m, s);
-  for (int k = 0; k < cfg.presmooth; ++k) mcgs_sweep(L, b, x, false, s);
+  for (int k = 0; k < cfg.presmooth; ++k) { if (dist && k > 0) halo_exchange(h, L.halo, x); mcgs_sweep(L, b, x, false, s); }
+  if (dist) halo_exchange(h, L.halo, x);
   bsrt_residual(L.A, b, x, L.w.p, s);
-  restrict_kernel<<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, L.agg_ptr.p, L.agg_rows.p, L.w.p, C.b.p);
-  PNP_COUNT_LAUNCH();
+  if (L.nagg > 0) {
+    restrict_kernel<<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, L.agg_ptr.p, L.agg_rows.p, L.w.p, C.b.p);
+    PNP_COUNT_LAUNCH();
+  }
   solve_level(h, cfg, l + 1, C.b.p, C.x.p);
-  prolong_kernel<<<cdiv(m, 256), 256, 0, s>>>(L.A.n, L.agg.p, C.x.p, x); PNP_COUNT_LAUNCH();
-  for (int k = 0; k < cfg.postsmooth; ++k) mcgs_sweep(L, b, x, true, s);
+  if (own > 0) { prolong_kernel<<<cdiv(3 * (size_t)own, 256), 256, 0, s>>>(own, L.agg.p, C.x.p, x); PNP_COUNT_LAUNCH(); }
+  for (int k = 0; k < cfg.postsmooth; ++k) { if (dist) halo_exchange(h, L.halo, x); mcgs_sweep(L, b, x, true, s); }
 }
 
 // approximate solve of A_l x = b on a coarse level l >= 1
@@ -686,29 +883,31 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
   cudaStream_t s = h.stream;
   const int nl = (int)h.hier.lv.size();
   Level& L = *h.hier.lv[l];
-  if (l == nl - 1) {
-    dense_matvec_kernel<<<cdiv((size_t)h.hier.nd * 32, 256), 256, 0, s>>>(h.hier.nd, h.hier.dense_inv.p, b, x);
-    PNP_COUNT_LAUNCH();
-    return;
-  }
+  if (l == nl - 1) { solve_coarsest(h, b, x); return; }
   const bool kcyc = cfg.cycle_type != V_CYCLE && l <= cfg.kcycle_levels;
   if (!kcyc) { mg_cycle(h, cfg, l, b, x); return; }
-  // K-cycle: two GCR steps preconditioned by the cycle of this level (device scalars only)
-  const size_t m = 3 * (size_t)L.A.n;
-  L.kc.alloc(5 * m + 0, s);
+  // K-cycle: two GCR steps preconditioned by the cycle of this level (device scalars only;
+  // multi-GPU: the dot products run over the owned rows and are summed with ncclAllReduce)
+  const size_t m = 3 * (size_t)L.A.n, mo = 3 * (size_t)owned_rows(L);
+  const bool dist = h.comm.active();
+  L.kc.alloc(5 * m + 8, s);
   L.ksc.alloc(8 + 3 * 592, s);
   if (!L.kcnt.p) { L.kcnt.alloc(1, s); L.kcnt.zero(); }
   double* c = L.kc.p; double* v = c + m; double* rt = v + m; double* d = rt + m; double* w = d + m;
   double* sc = L.ksc.p; double* partial = sc + 8;
-  const int g = small_grid(m);
+  const int g = small_grid(mo);
   mg_cycle(h, cfg, l, b, c);
+  if (dist) halo_exchange(h, L.halo, c);
   bsrt_spmv(L.A, c, v, s);
-  kdots_kernel<2><<<g, 256, 0, s>>>(m, v, b, v, v, nullptr, nullptr, partial, L.kcnt.p, sc); PNP_COUNT_LAUNCH();
-  kc_step1_kernel<<<g, 256, 0, s>>>(m, sc, b, v, rt); PNP_COUNT_LAUNCH();
+  kdots_kernel<2><<<g, 256, 0, s>>>(mo, v, b, v, v, nullptr, nullptr, partial, L.kcnt.p, sc); PNP_COUNT_LAUNCH();
+  if (dist) comm_allreduce(h, sc, 2, false);
+  kc_step1_kernel<<<g, 256, 0, s>>>(mo, sc, b, v, rt); PNP_COUNT_LAUNCH();
   mg_cycle(h, cfg, l, rt, d);
+  if (dist) halo_exchange(h, L.halo, d);
   bsrt_spmv(L.A, d, w, s);
-  kdots_kernel<3><<<g, 256, 0, s>>>(m, w, v, w, w, w, rt, partial, L.kcnt.p, sc + 2); PNP_COUNT_LAUNCH();
-  kc_final_kernel<<<g, 256, 0, s>>>(m, sc, c, d, x); PNP_COUNT_LAUNCH();
+  kdots_kernel<3><<<g, 256, 0, s>>>(mo, w, v, w, w, w, rt, partial, L.kcnt.p, sc + 2); PNP_COUNT_LAUNCH();
+  if (dist) comm_allreduce(h, sc + 2, 3, false);
+  kc_final_kernel<<<g, 256, 0, s>>>(mo, sc, c, d, x); PNP_COUNT_LAUNCH();
 }
 
 } // namespace

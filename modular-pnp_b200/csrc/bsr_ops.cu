@@ -237,11 +237,11 @@ __global__ void recolor_class_kernel(int n, const int* __restrict__ ia, const in
 
 // sort key = (tile of the row, colour): a sweep visits tile after tile and, inside a tile, colour
 // after colour, so the x-window a tile gathers from stays in L2 across its colours
-__global__ void group_key_kernel(int n, int tile_rows, int* __restrict__ color, int* __restrict__ hist)
+__global__ void group_key_kernel(int n, int n_own, int ghost_key, int tile_rows, int* __restrict__ color, int* __restrict__ hist)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int key = (i / tile_rows) * 64 + color[i];
+  const int key = i >= n_own ? ghost_key : (i / tile_rows) * 64 + color[i];   // ghost rows: last group, never swept
   color[i] = key;
   atomicAdd(&hist[key], 1);
 }
@@ -366,7 +366,8 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
   const int ngroups_max = ntiles * 64;
   int* hist = geti(t_hist, ngroups_max);
   PNP_CUDA(cudaMemsetAsync(hist, 0, (size_t)ngroups_max * sizeof(int), s));
-  group_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, tile_rows, color, hist); PNP_COUNT_LAUNCH();
+  const int n_own = owned_rows(L);
+  group_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, n_own, ngroups_max - 1, tile_rows, color, hist); PNP_COUNT_LAUNCH();
   std::vector<int> hh(ngroups_max);
   PNP_CUDA(cudaMemcpyAsync(hh.data(), hist, (size_t)ngroups_max * sizeof(int), cudaMemcpyDeviceToHost, s));
   PNP_CUDA(cudaStreamSynchronize(s));
@@ -376,6 +377,7 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
   for (int g = 0; g < ngroups_max; ++g)
     if (hh[g] > 0) { L.color_ptr.push_back(L.color_ptr.back() + hh[g]); if (g % 64 + 1 > maxc) maxc = g % 64 + 1; }
   L.ngroups = (int)L.color_ptr.size() - 1;
+  if (n_own < n && hh[ngroups_max - 1] > 0) { --L.ngroups; maxc = 0; for (int g = 0; g < ngroups_max - 1; ++g) if (hh[g] > 0 && g % 64 + 1 > maxc) maxc = g % 64 + 1; }
   L.ncolors = maxc;
   int key_bits = 6; while ((1 << key_bits) < ngroups_max) ++key_bits;
   // rowid = rows sorted by (tile, colour), ascending inside a group (stable radix sort)

@@ -245,7 +245,7 @@ int pnpb200_set_dirichlet(pnpb200_handle* ph, int n_bc, const int* bc_dofs)
       f[bc_dofs[i]] = 1;
     }
     h.bc_user = f;
-    if (h.n_own >= 0) for (size_t i = 3 * (size_t)h.n_own; i < N; ++i) f[i] = 1;   // ghost rows stay identity rows
+    for (size_t i = owned_dofs(h); i < N; ++i) f[i] = 1;   // ghost rows stay identity rows
     h.bcflag.upload(f.data(), N);
     PNP_CUDA(cudaStreamSynchronize(s));
     return FASP_SUCCESS;
@@ -307,7 +307,7 @@ int pnpb200_assemble(pnpb200_handle* ph)
     PNP_CUDA(cudaSetDevice(h.device));
     if (h.nv == 0) throw Error(ERROR_INPUT_PAR, "handle has no mesh");
     g_launches = 0;
-    halo_exchange(h, h.uu.p);
+    halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
     EventSpan e(h, h.stats.ms_assemble);
     assemble_system(h);
     e.stop();
@@ -358,7 +358,7 @@ int pnpb200_residual(pnpb200_handle* ph, double* l2, double* linf)
     PNP_CUDA(cudaSetDevice(h.device));
     g_launches = 0;
     double a = 0, b = 0;
-    halo_exchange(h, h.uu.p);
+    halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
     EventSpan e(h, h.stats.ms_residual);
     assemble_residual(h, h.rhs, &a, &b);
     e.stop();
@@ -418,14 +418,14 @@ int pnpb200_newton_step(pnpb200_handle* ph, const itsolver_param* it, const AMG_
     Handle& h = ph->h; cudaStream_t s = h.stream;
     PNP_CUDA(cudaSetDevice(h.device));
     g_launches = 0;
-    halo_exchange(h, h.uu.p);
+    halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
     { EventSpan e(h, h.stats.ms_assemble); assemble_system(h); e.stop(); }
     int st = 0;
     solve_current(h, it, amg, &st);
     if (krylov_status) *krylov_status = st;
     const size_t N = 3 * (size_t)h.nv;
     if (st >= 0) vec_axpy(1.0, h.du.p, h.uu.p, owned_dofs(h), s);     // linear_pnp.cpp:109-127
-    halo_exchange(h, h.uu.p);
+    halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
     double a = 0, b = 0;
     { EventSpan e(h, h.stats.ms_residual); assemble_residual(h, h.rhs, &a, &b); e.stop(); }
     if (l2) *l2 = a;

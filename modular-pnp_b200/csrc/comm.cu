@@ -18,12 +18,13 @@ typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStr
 typedef int (*fn_sendrecv)(void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_csendrecv)(const void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_group)(void);
-constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
+constexpr int NCCL_DOUBLE = 8, NCCL_INT32 = 2, NCCL_INT8 = 0, NCCL_SUM = 0, NCCL_MAX = 2;
 
 struct Api {
   void* lib = nullptr;
   fn_getid getid; fn_init init; fn_destroy destroy; fn_allreduce allreduce; fn_csendrecv send; fn_sendrecv recv;
-  fn_group gstart, gend;
+  fn_group gstart, gend; fn_allgather allgather;
 };
 Api& api()
 {
@@ -36,6 +37,7 @@ Api& api()
     a.destroy = (fn_destroy)sym("ncclCommDestroy"); a.allreduce = (fn_allreduce)sym("ncclAllReduce");
     a.send = (fn_csendrecv)sym("ncclSend"); a.recv = (fn_sendrecv)sym("ncclRecv");
     a.gstart = (fn_group)sym("ncclGroupStart"); a.gend = (fn_group)sym("ncclGroupEnd");
+    a.allgather = (fn_allgather)sym("ncclAllGather");
   }
   return a;
 }
@@ -57,15 +59,30 @@ Comm::~Comm() { if (nccl) { try { api().destroy(nccl); } catch (...) {} } }
 
 void comm_allreduce(Handle& h, double* dev, int count, bool is_max)
 {
-  if (!h.comm.nccl || h.comm.nranks == 1) return;
+  if (!h.comm.active()) return;
   nccl_check(api().allreduce(dev, dev, (size_t)count, NCCL_DOUBLE, is_max ? NCCL_MAX : NCCL_SUM, h.comm.nccl, h.stream), "allreduce");
 }
-
-// refresh the ghost entries of a dof vector (3 per vertex) from their owners
-void halo_exchange(Handle& h, double* vec)
+void comm_allreduce_int(Handle& h, int* dev, int count, bool is_max)
 {
-  Comm& c = h.comm;
-  if (!c.nccl || c.nbr.empty()) return;
+  if (!h.comm.active()) return;
+  nccl_check(api().allreduce(dev, dev, (size_t)count, NCCL_INT32, is_max ? NCCL_MAX : NCCL_SUM, h.comm.nccl, h.stream), "allreduce(int)");
+}
+void comm_allgather(Handle& h, const void* send, void* recv, size_t bytes_per_rank)
+{
+  if (!h.comm.active()) { PNP_CUDA(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, h.stream)); return; }
+  nccl_check(api().allgather(send, recv, bytes_per_rank, NCCL_INT8, h.comm.nccl, h.stream), "allgather");
+}
+
+__global__ void pack1_kernel(int n, const int* __restrict__ idx, const int* __restrict__ vec, int* __restrict__ buf)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) buf[e] = vec[idx[e]];
+}
+
+// refresh the ghost entries of a block vector (3 doubles per row) from their owners
+void halo_exchange(Handle& h, Halo& c, double* vec)
+{
+  if (!h.comm.active() || !c.active()) return;
   cudaStream_t s = h.stream;
   const int nsend = c.send_ptr.back();
   if (nsend > 0) { pack3_kernel<<<cdiv(3 * (size_t)nsend, 256), 256, 0, s>>>(nsend, c.send_idx.p, vec, c.sendbuf.p); PNP_COUNT_LAUNCH(); }
@@ -73,8 +90,25 @@ void halo_exchange(Handle& h, double* vec)
   nccl_check(a.gstart(), "groupStart");
   for (size_t k = 0; k < c.nbr.size(); ++k) {
     const int ns = c.send_ptr[k + 1] - c.send_ptr[k], nr = c.recv_ptr[k + 1] - c.recv_ptr[k];
-    if (ns > 0) nccl_check(a.send(c.sendbuf.p + 3 * (size_t)c.send_ptr[k], 3 * (size_t)ns, NCCL_DOUBLE, c.nbr[k], c.nccl, s), "send");
-    if (nr > 0) nccl_check(a.recv(vec + 3 * (size_t)c.recv_ptr[k], 3 * (size_t)nr, NCCL_DOUBLE, c.nbr[k], c.nccl, s), "recv");
+    if (ns > 0) nccl_check(a.send(c.sendbuf.p + 3 * (size_t)c.send_ptr[k], 3 * (size_t)ns, NCCL_DOUBLE, c.nbr[k], h.comm.nccl, s), "send");
+    if (nr > 0) nccl_check(a.recv(vec + 3 * (size_t)c.recv_ptr[k], 3 * (size_t)nr, NCCL_DOUBLE, c.nbr[k], h.comm.nccl, s), "recv");
+  }
+  nccl_check(a.gend(), "groupEnd");
+}
+
+void halo_exchange_int(Handle& h, Halo& c, int* vec)
+{
+  if (!h.comm.active() || !c.active()) return;
+  cudaStream_t s = h.stream;
+  const int nsend = c.send_ptr.back();
+  c.isendbuf.alloc(nsend ? nsend : 1, s);
+  if (nsend > 0) { pack1_kernel<<<cdiv(nsend, 256), 256, 0, s>>>(nsend, c.send_idx.p, vec, c.isendbuf.p); PNP_COUNT_LAUNCH(); }
+  Api& a = api();
+  nccl_check(a.gstart(), "groupStart");
+  for (size_t k = 0; k < c.nbr.size(); ++k) {
+    const int ns = c.send_ptr[k + 1] - c.send_ptr[k], nr = c.recv_ptr[k + 1] - c.recv_ptr[k];
+    if (ns > 0) nccl_check(a.send(c.isendbuf.p + c.send_ptr[k], (size_t)ns, NCCL_INT32, c.nbr[k], h.comm.nccl, s), "send(int)");
+    if (nr > 0) nccl_check(a.recv(vec + c.recv_ptr[k], (size_t)nr, NCCL_INT32, c.nbr[k], h.comm.nccl, s), "recv(int)");
   }
   nccl_check(a.gend(), "groupEnd");
 }
@@ -117,8 +151,9 @@ int pnpb200_set_partition(pnpb200_handle* ph, int n_owned, int n_neighbors, cons
     Handle& h = ph->h; cudaStream_t s = h.stream;
     PNP_CUDA(cudaSetDevice(h.device));
     if (n_owned > h.nv) throw Error(ERROR_INPUT_PAR, "n_owned exceeds the local vertex count");
-    Comm& c = h.comm;
-    h.n_own = n_owned;
+    Level& F = *h.hier.lv[0];
+    Halo& c = F.halo;
+    F.n_own = n_owned;
     c.nbr.assign(neighbor_ranks, neighbor_ranks + n_neighbors);
     c.send_ptr.assign(send_ptr, send_ptr + n_neighbors + 1);
     c.recv_ptr.assign(recv_ptr, recv_ptr + n_neighbors + 1);
@@ -128,6 +163,8 @@ int pnpb200_set_partition(pnpb200_handle* ph, int n_owned, int n_neighbors, cons
     c.send_idx.alloc(nsend ? nsend : 1, s);
     if (nsend) c.send_idx.upload(send_idx, nsend);
     c.sendbuf.alloc(3 * (size_t)(nsend ? nsend : 1), s);
+    // ghost rows must not be part of the Gauss-Seidel colour groups: lay the fine level out again
+    relayout_fine_level(h);
     // ghost dofs become identity rows of the local matrix (like Dirichlet rows)
     const size_t N = 3 * (size_t)h.nv;
     std::vector<unsigned char> f = h.bc_user;

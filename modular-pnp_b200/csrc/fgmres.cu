@@ -31,7 +31,8 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
   const BsrT& A = h.hier.lv[0]->A;
   const size_t n = 3 * (size_t)A.n;          // local vector length (owned + ghost dofs) = basis stride
   const size_t m = owned_dofs(h);            // reductions and updates run over the owned dofs only
-  const bool dist = h.comm.nccl != nullptr && h.comm.nranks > 1;
+  const bool dist = h.comm.active();
+  Halo& halo = h.hier.lv[0]->halo;
   auto zero_ghost = [&](double* v) { if (n > m) PNP_CUDA(cudaMemsetAsync(v + m, 0, (n - m) * sizeof(double), s)); };
   const int MaxIt = cfg.maxit;
   const int restart_max = cfg.restart < 1 ? 1 : cfg.restart, restart_min = 3, dstep = 3;
@@ -49,7 +50,7 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
       neg(restart_max + 1);
 
   const double b_norm = vec_norm2(h, b, m);
-  if (dist) halo_exchange(h, x);
+  if (dist) halo_exchange(h, halo, x);
   bsrt_residual(A, b, x, Vi(0), s);
   double r_norm = vec_norm2(h, Vi(0), m), r_norm_old;
   const double den = b_norm > 0.0 ? b_norm : r_norm;
@@ -76,7 +77,7 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
         if (cfg.use_amg) amg_vcycle(h, cfg, Vi(i - 1), Zi(i - 1));
         else vec_copy(Zi(i - 1), Vi(i - 1), n, s);
       }
-      { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, Zi(i - 1)); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
+      { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, halo, Zi(i - 1)); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
       double tnorm;
       {
         PhaseTimer t(h, h.stats.ms_ortho);
@@ -123,7 +124,7 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
     multi_axpy(h, Z, n, i, rs.data(), x, m, nullptr);
     // true residual for the convergence confirmation / next cycle
     const bool est_conv = r_norm <= epsilon;
-    if (dist) halo_exchange(h, x);
+    if (dist) halo_exchange(h, halo, x);
     bsrt_residual(A, b, x, Vi(0), s);
     r_norm = vec_norm2(h, Vi(0), m);
     if (est_conv && r_norm <= epsilon) { converged = true; break; }

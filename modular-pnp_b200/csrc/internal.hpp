@@ -24,8 +24,21 @@ struct BsrT {
   DevBuf<double> val;   // 9*nnzb
 };
 
+// halo lists of one level (block-row granularity): neighbour k gets the owned rows
+// send_idx[send_ptr[k] .. send_ptr[k+1]) and fills the local ghost rows [recv_ptr[k], recv_ptr[k+1])
+struct Halo {
+  std::vector<int> nbr, send_ptr, recv_ptr;
+  DevBuf<int> send_idx;
+  DevBuf<double> sendbuf;
+  DevBuf<int> isendbuf;
+  bool active() const { return !nbr.empty(); }
+};
+
 struct Level {
   BsrT A;
+  int n_own = -1;               // owned block rows (first n_own local rows); -1 = all rows (single GPU).
+                                // Ghost rows are identity rows of A; their vector entries come from the owner.
+  Halo halo;
   DevBuf<double> dinv;          // 9*n, AoS: inverse of diagonal blocks
   // multicolour ordering
   int ncolors = 0;              // colours of the graph
@@ -59,8 +72,12 @@ SolverConfig make_config(const itsolver_param* it, const AMG_param* amg);
 struct Hierarchy {
   std::vector<std::unique_ptr<Level>> lv;   // lv[0] = fine level (assembled Jacobian), lv[1..] rebuilt by amg_setup
   // coarsest level dense inverse
-  int nd = 0;                   // scalar size of the coarsest level
-  DevBuf<double> dense_inv;     // nd*nd, row-major
+  int nd = 0;                   // scalar size of the GLOBAL coarsest level
+  DevBuf<double> dense_inv;     // nd*nd, row-major, replicated on every rank
+  // distributed coarsest solve: my rows [c_row0, c_row0 + 3*c_own), gather layout of the rhs
+  int c_own = 0, c_row0 = 0, c_maxown3 = 0, c_nranks = 1;
+  DevBuf<int> c_off3, c_cnt3;
+  DevBuf<double> c_bpad, c_ball, c_bglob;
   bool symbolic_valid = false;
 };
 
@@ -85,14 +102,11 @@ struct StreamOwner {
   ~StreamOwner() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
 };
 
-// multi-GPU state: NCCL communicator, neighbour ranks, halo lists (vertex granularity)
+// multi-GPU state: one NCCL communicator per handle
 struct Comm {
   void* nccl = nullptr;
   int rank = 0, nranks = 1;
-  std::vector<int> nbr, send_ptr, recv_ptr;   // per neighbour: [send_ptr[k], send_ptr[k+1]) into send_idx;
-                                              // ghosts of neighbour k are local vertices [recv_ptr[k], recv_ptr[k+1])
-  DevBuf<int> send_idx;                       // owned local vertex ids to send
-  DevBuf<double> sendbuf;
+  bool active() const { return nccl != nullptr && nranks > 1; }
   ~Comm();
 };
 
@@ -102,7 +116,6 @@ struct Handle {
   cudaStream_t stream = nullptr;
   // mesh
   int nv = 0, nc = 0;
-  int n_own = -1;               // owned vertices (first n_own local ids); -1 = all (single GPU)
   Comm comm;
   std::vector<unsigned char> bc_user;   // Dirichlet flags as set by the caller (ghost flags are added on top)
   DevBuf<double> xyz;           // 3*nv
@@ -144,6 +157,7 @@ struct Handle {
 // ---- mesh_setup.cu
 void build_mesh_tables(Handle& h);                 // v2c, pattern, brow/dslot/tslot, omega
 void compute_k00(Handle& h);
+void relayout_fine_level(Handle& h);                // after the partition (ghost rows) is known
 void generate_box_mesh(Handle& h, int nx, int ny, int nz, double lx, double ly, double lz);   // domain_build
 // colour the graph given in natural CSR (ia, ja_nat), lay the rows out colour by colour (rs, rowid,
 // physical ja) and build brow/dslot/tslot
@@ -172,9 +186,13 @@ void multi_dot(Handle& h, const double* V, size_t ld, int nvec, const double* w,
 void multi_axpy(Handle& h, const double* V, size_t ld, int nvec, const double* coef_host, double* w, size_t n,
                 double* norm2_out);
 // ---- comm.cu
-void halo_exchange(Handle& h, double* vec);
+void halo_exchange(Handle& h, Halo& halo, double* vec);      // 3 doubles per block row
+void halo_exchange_int(Handle& h, Halo& halo, int* vec);     // 1 int per block row
 void comm_allreduce(Handle& h, double* dev, int count, bool is_max);
-inline size_t owned_dofs(const Handle& h) { return 3 * (size_t)(h.n_own >= 0 ? h.n_own : h.hier.lv[0]->A.n); }
+void comm_allreduce_int(Handle& h, int* dev, int count, bool is_max);
+void comm_allgather(Handle& h, const void* send, void* recv, size_t bytes_per_rank);
+inline int owned_rows(const Level& L) { return L.n_own >= 0 ? L.n_own : L.A.n; }
+inline size_t owned_dofs(const Handle& h) { return 3 * (size_t)owned_rows(*h.hier.lv[0]); }
 // ---- amg.cu
 void amg_setup(Handle& h, const SolverConfig& cfg);
 void amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z);

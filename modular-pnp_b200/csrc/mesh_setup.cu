@@ -169,6 +169,21 @@ void build_mesh_tables(Handle& h)
   PNP_LAUNCH_CHECK();
 }
 
+void relayout_fine_level(Handle& h)
+{
+  cudaStream_t s = h.stream;
+  Level& L = *h.hier.lv[0];
+  BsrT& A = L.A;
+  DevBuf<int> ja_nat; ja_nat.alloc(A.nnzb, s);
+  bsrt_export_ja(A, ja_nat.p, s);
+  color_and_layout(L, ja_nat.p, nullptr, s);
+  edge_table_kernel<false><<<cdiv(A.nnzb, 128), 128, 0, s>>>(A.nnzb, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p,
+                                                            reinterpret_cast<const int4*>(h.cells.p), h.xyz.p, nullptr, h.omega.p);
+  PNP_COUNT_LAUNCH();
+  if (h.have_coef) compute_k00(h);
+  h.hier.symbolic_valid = false;
+}
+
 void compute_k00(Handle& h)
 {
   cudaStream_t s = h.stream;
