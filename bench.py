@@ -85,7 +85,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def byte_model(stats, nv, nc, krylov_its, restart):
+def byte_model(stats, nv, nc, krylov_its, restart, kcycle_levels=0):
     """Algorithmic bytes of one Newton step, SURVEY.md §8(d), from the run's actual level sizes
     and iteration count (fp64 = 8 B, int32 = 4 B; every array touched once per logical pass)."""
     N = 3 * nv
@@ -97,8 +97,19 @@ def byte_model(stats, nv, nc, krylov_its, restart):
     b_eafe = 2 * (nnzb[0] * 12 + nv * 24)
     b_res = nc * 16 + nv * 24 + N * 8 * 2 + nv * 16 + N * 8 * 3
     b_setup = sum(2 * b_mat[l] + b_mat[l + 1] + rows[l] * 76 for l in range(len(rows) - 1))
-    b_vc = sum(3 * b_spmv[l] for l in range(len(rows) - 1)) + \
-        sum(2 * 3 * (rows[l] + rows[l + 1]) * 8 for l in range(len(rows) - 1))
+    # cycles per preconditioner application on each level: the K-cycle (kcycle_levels > 0) runs two
+    # cycles + two matvecs + ~12 vector passes per visit of a K level
+    nl = len(rows)
+    cyc = [1] * nl
+    b_vc = 0
+    for l in range(nl - 1):
+        if l >= 1:
+            if l <= kcycle_levels:
+                cyc[l] = 2 * cyc[l - 1]
+                b_vc += cyc[l - 1] * (2 * b_spmv[l] + 12 * 3 * rows[l] * 8)
+            else:
+                cyc[l] = cyc[l - 1]
+        b_vc += cyc[l] * (3 * b_spmv[l] + 2 * 3 * (rows[l] + rows[l + 1]) * 8)
     b_kry = 0
     for it in range(max(krylov_its, 0)):
         j = it % restart
@@ -280,7 +291,8 @@ def main():
     spmv_ms, spmv_bytes = g.probe_kernel(0, 20)
     gs_ms, gs_bytes = g.probe_kernel(2, 10)
     achieved = gs_bytes / gs_ms / 1e6
-    b_step = byte_model(stats, nv, nc, kits if kits > 0 else stats.krylov_its, it.restart)
+    b_step = byte_model(stats, nv, nc, kits if kits > 0 else stats.krylov_its, it.restart,
+                        kcycle_levels=(3 if cyc != 1 else 0))
     step_gbs = b_step / (ms / K) / 1e6
     # traffic: dram bytes of one sweep from the committed ncu capture (only taken at n = 128: ncu
     # cannot save/restore the 100 GB working set of the 256^3 run)
