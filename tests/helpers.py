@@ -57,3 +57,70 @@ def bsr_to_csr(IA, JA, val):
             sJA[s:s + len(cols)] = cols
             sval[s:s + len(cols)] = V[p0:p1, r, :].ravel()
     return sIA, sJA, sval
+
+
+class GeneralProblem:
+    """PNP problem on an arbitrary conforming tetrahedral mesh (oracle side): same fields as
+    oracle.Problem but built from (xyz, cells) — the unstructured path an adaptively refined mesh
+    takes (benchmarks/pnp_refine_exact/main.cpp:242-268)."""
+
+    def __init__(self, O, xyz, cells):
+        import ctypes as C
+        L = O.lib()
+        self.O = O
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float64).ravel()
+        self.cells = np.ascontiguousarray(cells, dtype=np.int32).ravel()
+        self.nv, self.nc = len(self.xyz) // 3, len(self.cells) // 4
+        self.N = 3 * self.nv
+        self.eps = np.zeros(self.nv); self.fixed = np.zeros(self.nv)
+        self.diff = np.zeros(self.N); self.val = np.zeros(self.N); self.reac = np.zeros(self.N)
+        self.uu0 = np.zeros(self.N); self.exact = np.zeros(self.N)
+        L.orc_exact_problem(self.nv, self.xyz, self.eps, self.fixed, self.diff, self.val, self.reac, self.uu0,
+                            self.exact.ctypes.data)
+        vflag = np.zeros(self.nv, dtype=np.uint8)
+        L.orc_dirichlet_vertices(self.nv, self.xyz, self.nc, self.cells, 0, vflag)
+        self.bcflag = np.repeat(vflag, 3).astype(np.uint8)
+        self.IA = np.zeros(self.nv + 1, dtype=np.int32)
+        self.nnzb = L.orc_block_pattern_count(self.nv, self.nc, self.cells, self.IA)
+        self.JA = np.zeros(self.nnzb, dtype=np.int32)
+        L.orc_block_pattern_fill(self.nv, self.nc, self.cells, self.IA, self.JA)
+
+    def assemble(self, uu, use_eafe=True):
+        A = np.zeros(9 * self.nnzb); b = np.zeros(self.N)
+        self.O.lib().orc_assemble(self.nv, self.xyz, self.nc, self.cells, self.IA, self.JA, np.ascontiguousarray(uu),
+                                  self.eps, self.fixed, self.diff, self.val, self.reac, self.bcflag,
+                                  1 if use_eafe else 0, A, b)
+        return A, b
+
+    def residual(self, uu):
+        import ctypes as C
+        b = np.zeros(self.N); l2, li = C.c_double(), C.c_double()
+        self.O.lib().orc_residual(self.nv, self.xyz, self.nc, self.cells, np.ascontiguousarray(uu), self.eps, self.fixed,
+                                  self.diff, self.val, self.reac, self.bcflag, b, C.byref(l2), C.byref(li))
+        return b, l2.value, li.value
+
+
+def irregular_mesh(O, nx, ny, nz, seed=11, refine_fraction=0.25, jitter=0.15):
+    """Kuhn box with jittered interior vertices and a random quarter of the cells split at their
+    centroid (1 -> 4, conforming): irregular row lengths, vertex degrees and cell volumes."""
+    P = O.Problem(nx, ny, nz)
+    rng = np.random.default_rng(seed)
+    X = P.xyz.reshape(-1, 3).copy()
+    cells = P.cells.reshape(-1, 4).astype(np.int64)
+    h = np.array([2.0 / nx, 0.4 / ny, 0.4 / nz])
+    interior = np.all((np.abs(X) < np.array([1.0, 0.2, 0.2]) - 1e-12), axis=1)
+    X[interior] += jitter * h * rng.uniform(-1, 1, (int(interior.sum()), 3))
+    pick = rng.uniform(size=len(cells)) < refine_fraction
+    keep = cells[~pick]
+    split = cells[pick]
+    cent = X[split].mean(axis=1)
+    new_ids = len(X) + np.arange(len(split))
+    X = np.vstack([X, cent])
+    subs = []
+    for drop in range(4):
+        t = split.copy()
+        t[:, drop] = new_ids
+        subs.append(t)
+    cells = np.vstack([keep] + subs)
+    cells = np.sort(cells, axis=1)          # UFC ordering (ascending vertex ids)
+    return np.ascontiguousarray(X.ravel()), np.ascontiguousarray(cells.astype(np.int32).ravel())
