@@ -296,17 +296,6 @@ __global__ void prolong_kernel(int n, const int* __restrict__ agg, const double*
 }
 
 // ---- coarsest level: dense inverse -------------------------------------------------------------
-__global__ void dense_fill_kernel(int nnzb, int nd, const int* __restrict__ ia, const int* __restrict__ rs,
-                                  const int* __restrict__ ja, const int* __restrict__ brow, const double* __restrict__ val,
-                                  double* __restrict__ D)
-{
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 9 * (size_t)nnzb) return;
-  const int b = (int)(e / 9), t = (int)(e % 9);
-  const int i = brow[b], s = rs[i], len = ia[i + 1] - ia[i];
-  D[(size_t)(3 * i + t / 3) * nd + 3 * ja[b] + t % 3] = val[9 * (size_t)s + (size_t)t * len + (b - s)];
-}
-
 __global__ void identity_kernel(int nd, double* __restrict__ D)
 {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,19 +356,6 @@ __global__ void __launch_bounds__(1024) dense_invert_kernel(int nd, double* __re
     __syncthreads();
   }
 }
-
-// x = Inv * b, one warp per row
-__global__ void dense_matvec_kernel(int nd, const double* __restrict__ Inv, const double* __restrict__ b,
-                                    double* __restrict__ x)
-{
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= nd) return;
-  double a = 0.0;
-  for (int c = lane; c < nd; c += 32) a += Inv[(size_t)row * nd + c] * b[c];
-  a = warp_sum(a);
-  if (lane == 0) x[row] = a;
-}
-
 
 // ---- K-cycle (nonlinear AMLI, FASP cycle_type NL_AMLI [EXT]; Notay's 2-step GCR form) ----------
 // All scalars stay on the device so that one preconditioner application is a fixed launch

@@ -19,7 +19,7 @@ namespace pnpb200 {
 
 namespace {
 
-constexpr int REC_EAFE = 32;   // G[10] Q[2] detM1[10] detM2[10]
+constexpr int REC_EAFE = 32;   // 10 x (G, det*M1, det*M2) pair-major, then Q[2]
 constexpr int REC_FULL = 68;   // + S[2] T1[16] T2[16] (+2 pad)
 
 // ---- (A) Jacobian cell records -------------------------------------------------------------
@@ -80,14 +80,13 @@ cell_jacobian_kernel(int nc, const int4* __restrict__ cells, const double* __res
     }
   }
   double* o = rec + (size_t)c * (FULL ? REC_FULL : REC_EAFE);
+  // pair-major: the three numbers a block (i,j) needs from this cell are contiguous
   int m = 0;
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int s = r; s < 4; ++s) o[m++] = det * dot3(g[r], g[s]);
-  o[10] = Q[0]; o[11] = Q[1];
-#pragma unroll
-  for (int t = 0; t < 10; ++t) { o[12 + t] = det * M[0][t]; o[22 + t] = det * M[1][t]; }
+    for (int s = r; s < 4; ++s) { o[3 * m] = det * dot3(g[r], g[s]); o[3 * m + 1] = det * M[0][m]; o[3 * m + 2] = det * M[1][m]; ++m; }
+  o[30] = Q[0]; o[31] = Q[1];
   if (FULL) {
     o[32] = S[0]; o[33] = S[1];
     double gu0[3] = {0, 0, 0};
@@ -128,8 +127,12 @@ __device__ __forceinline__ double eafe_weight(const double* __restrict__ uu, con
 }
 
 // ---- (B) a half-warp per block row, lane k = block k of the row ------------------------------
-// (rows are visited in natural order so that the cell records stream through L2 once; the
-// finished blocks go to the row's physical, colour-major position)
+// Rows are visited in natural order so that the cell records stream through L2 once; the finished
+// blocks go to the row's physical, colour-major position. The row's incident cells are loaded
+// cooperatively (one cell per lane) and broadcast with shuffles in ascending cell order, so every
+// lane accumulates its block in the same deterministic order without re-reading the cell list.
+// The EAFE diagonal (zero column sums, EAFE.h:4876-4879) is a half-warp reduction of the transposed
+// edge weights each off-diagonal lane evaluates next to its own.
 template <bool EAFE>
 __global__ void __launch_bounds__(256)
 assemble_blocks_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs, const int* __restrict__ ja,
@@ -141,58 +144,86 @@ assemble_blocks_kernel(int n, const int* __restrict__ ia, const int* __restrict_
 {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int lane = threadIdx.x & 15;
-  if (i >= n) return;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);      // my half-warp
   constexpr int RS = EAFE ? REC_EAFE : REC_FULL;
-  const int s = rs[i], len = ia[i + 1] - ia[i];
-  const int c0 = v2c_ptr[i], c1 = v2c_ptr[i + 1];
-  const bool bc0 = bcflag[3 * (size_t)i] != 0, bc1 = bcflag[3 * (size_t)i + 1] != 0, bc2 = bcflag[3 * (size_t)i + 2] != 0;
-  for (int k = lane; k < len; k += 16) {
-    const int b = s + k, j = ja[b];
+  int s = 0, len = 0, c0 = 0, c1 = 0;
+  bool bc0 = false, bc1 = false, bc2 = false;
+  if (i < n) {
+    s = rs[i]; len = ia[i + 1] - ia[i]; c0 = v2c_ptr[i]; c1 = v2c_ptr[i + 1];
+    bc0 = bcflag[3 * (size_t)i] != 0; bc1 = bcflag[3 * (size_t)i + 1] != 0; bc2 = bcflag[3 * (size_t)i + 2] != 0;
+  }
+  const int npass = (len + 15) >> 4;                          // uniform over the half-warp
+  double d1 = 0.0, d2 = 0.0;                                  // -(column sums) of the EAFE off-diagonals
+  int diag_k = -1; double diag_a[9];
+  for (int ps = 0; ps < npass; ++ps) {
+    const int k = ps * 16 + lane;
+    const bool act = k < len;
+    const int b = s + (act ? k : 0), j = act ? ja[b] : -1;
     double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    a[0] = k00[b];
-    for (int p = c0; p < c1; ++p) {
-      const int c = v2c_idx[p];
-      const int4 cv = cells[c];
-      const int lj = local_index(cv, j);
-      if (lj < 0) continue;
-      const int li = local_index(cv, i);
-      const double* r = rec + (size_t)c * RS;
-      const int sidx = sym4(li, lj);
-      const double G = r[sidx];
-      a[3] += r[10] * G;          // (1,0): q1 D1 e^{u1} grad u0 . grad v1
-      a[6] += r[11] * G;          // (2,0)
-      a[1] -= r[12 + sidx];       // (0,1): -q1 e^{u1} u1 v0
-      a[2] -= r[22 + sidx];       // (0,2)
-      if (!EAFE) {
-        a[4] += r[32] * G + r[34 + 4 * li + lj];
-        a[8] += r[33] * G + r[50 + 4 * li + lj];
-      }
-    }
-    if (EAFE) {
-      if (i != j) {
-        const double w = omega[b];
-        a[4] = w * eafe_weight(uu, diff, i, j, 1, q1);
-        a[8] = w * eafe_weight(uu, diff, i, j, 2, q2);
-      } else {
-        // column sums vanish (EAFE.h:4876-4879): A_ii = -sum_{r != i} A_ri, omega symmetric
-        double s1 = 0.0, s2 = 0.0;
-        for (int p = s; p < s + len; ++p) {
-          const int r = ja[p];
-          if (r == i) continue;
-          const double w = omega[p];
-          s1 -= w * eafe_weight(uu, diff, r, i, 1, q1);
-          s2 -= w * eafe_weight(uu, diff, r, i, 2, q2);
+    if (act) a[0] = k00[b];
+    // cells of row i, 16 at a time: lane q loads cell c0 + base + q, everybody reads it by shuffle
+    for (int base = c0; base < c1; base += 16) {
+      const int mine = base + lane < c1 ? v2c_idx[base + lane] : -1;
+      int4 mycv = make_int4(-1, -1, -1, -1);
+      if (mine >= 0) mycv = cells[mine];
+      const int cnt = c1 - base < 16 ? c1 - base : 16;
+      for (int q = 0; q < cnt; ++q) {
+        const int src = (threadIdx.x & 16) + q;
+        int4 cv;
+        cv.x = __shfl_sync(hmask, mycv.x, src); cv.y = __shfl_sync(hmask, mycv.y, src);
+        cv.z = __shfl_sync(hmask, mycv.z, src); cv.w = __shfl_sync(hmask, mycv.w, src);
+        const int c = __shfl_sync(hmask, mine, src);
+        const int lj = act ? local_index(cv, j) : -1;
+        if (lj < 0) continue;
+        const int li = local_index(cv, i);
+        const double* r = rec + (size_t)c * RS;
+        const int sidx = sym4(li, lj);
+        const double G = r[3 * sidx];
+        a[3] += r[30] * G;          // (1,0): q1 D1 e^{u1} grad u0 . grad v1
+        a[6] += r[31] * G;          // (2,0)
+        a[1] -= r[3 * sidx + 1];    // (0,1): -q1 e^{u1} u1 v0
+        a[2] -= r[3 * sidx + 2];    // (0,2)
+        if (!EAFE) {
+          a[4] += r[32] * G + r[34 + 4 * li + lj];
+          a[8] += r[33] * G + r[50 + 4 * li + lj];
         }
-        a[4] = s1; a[8] = s2;
       }
     }
-    // DirichletBC::apply: row -> identity row (pattern kept)
-    if (bc0) { a[0] = (i == j) ? 1.0 : 0.0; a[1] = 0.0; a[2] = 0.0; }
-    if (bc1) { a[3] = 0.0; a[4] = (i == j) ? 1.0 : 0.0; a[5] = 0.0; }
-    if (bc2) { a[6] = 0.0; a[7] = 0.0; a[8] = (i == j) ? 1.0 : 0.0; }
-    double* o = val + 9 * (size_t)s + k;
+    if (EAFE && act && i != j) {
+      const double w = omega[b];                 // omega is symmetric: the same weight serves A_ij and A_ji
+      a[4] = w * eafe_weight(uu, diff, i, j, 1, q1);
+      a[8] = w * eafe_weight(uu, diff, i, j, 2, q2);
+      d1 -= w * eafe_weight(uu, diff, j, i, 1, q1);
+      d2 -= w * eafe_weight(uu, diff, j, i, 2, q2);
+    }
+    if (act && i == j) {                          // keep the diagonal block until the column sums are known
+      diag_k = k;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) o[(size_t)t * len] = a[t];
+      for (int t = 0; t < 9; ++t) diag_a[t] = a[t];
+      continue;
+    }
+    if (act) {
+      // DirichletBC::apply: row -> identity row (pattern kept)
+      if (bc0) { a[0] = 0.0; a[1] = 0.0; a[2] = 0.0; }
+      if (bc1) { a[3] = 0.0; a[4] = 0.0; a[5] = 0.0; }
+      if (bc2) { a[6] = 0.0; a[7] = 0.0; a[8] = 0.0; }
+      double* o = val + 9 * (size_t)s + k;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) o[(size_t)t * len] = a[t];
+    }
+  }
+  if (EAFE) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { d1 += __shfl_xor_sync(hmask, d1, o); d2 += __shfl_xor_sync(hmask, d2, o); }
+  }
+  if (diag_k >= 0) {
+    if (EAFE) { diag_a[4] = d1; diag_a[8] = d2; }
+    if (bc0) { diag_a[0] = 1.0; diag_a[1] = 0.0; diag_a[2] = 0.0; }
+    if (bc1) { diag_a[3] = 0.0; diag_a[4] = 1.0; diag_a[5] = 0.0; }
+    if (bc2) { diag_a[6] = 0.0; diag_a[7] = 0.0; diag_a[8] = 1.0; }
+    double* o = val + 9 * (size_t)s + diag_k;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) o[(size_t)t * len] = diag_a[t];
   }
 }
 
@@ -350,6 +381,7 @@ void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf)
   finalize_norm_kernel<<<1, 1024, 0, s>>>(nblk, h.red.p + 2, h.red.p);
   PNP_COUNT_LAUNCH();
   PNP_LAUNCH_CHECK();
+  h.rhs_current = (&out == &h.rhs);
   if (l2 || linf) {
     comm_allreduce(h, h.red.p, 1, false);        // sum of squares over all ranks (ghost rows are zero)
     comm_allreduce(h, h.red.p + 1, 1, true);     // max
@@ -366,14 +398,20 @@ void assemble_system(Handle& h)
   if (!h.have_coef) throw Error(ERROR_INPUT_PAR, "coefficients not set");
   const int4* cells = reinterpret_cast<const int4*>(h.cells.p);
   BsrT& A = h.hier.lv[0]->A;
-  // rhs first (re-uses the record buffer)
-  assemble_residual(h, h.rhs, nullptr, nullptr);
+  static const bool timing = getenv("PNPB200_ASM_TIMING") != nullptr;
+  auto mark = [&](int k) { if (timing) cudaEventRecord(h.ev[4 + k], s); };
+  mark(0);
+  // rhs first (re-uses the record buffer); the residual the previous Newton step ended with IS this
+  // step's rhs (the reference assembles it again, src/pde.cpp:546), so it is only rebuilt if stale
+  if (!h.rhs_current) assemble_residual(h, h.rhs, nullptr, nullptr);
+  mark(1);
   const int rs = h.use_eafe ? REC_EAFE : REC_FULL;
   const size_t need = (size_t)h.nc * rs;
   if (h.cellrec.n < need) h.cellrec.alloc(need, s);
   if (h.use_eafe) {
     cell_jacobian_kernel<false><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.cellrec.p);
     PNP_COUNT_LAUNCH();
+    mark(2);
     assemble_blocks_kernel<true><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
         A.n, A.ia.p, A.rs.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
         h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
@@ -381,14 +419,23 @@ void assemble_system(Handle& h)
   } else {
     cell_jacobian_kernel<true><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.cellrec.p);
     PNP_COUNT_LAUNCH();
+    mark(2);
     assemble_blocks_kernel<false><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
         A.n, A.ia.p, A.rs.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
         h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
     PNP_COUNT_LAUNCH();
   }
+  mark(3);
   zero_row_fix_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.rs.p, A.dslot.p, A.val.p);
   PNP_COUNT_LAUNCH();
   PNP_LAUNCH_CHECK();
+  if (timing) {
+    cudaEventRecord(h.ev[3], s); cudaEventSynchronize(h.ev[3]);
+    float a, b, c, d;
+    cudaEventElapsedTime(&a, h.ev[4], h.ev[5]); cudaEventElapsedTime(&b, h.ev[5], h.ev[6]);
+    cudaEventElapsedTime(&c, h.ev[6], h.ev[7]); cudaEventElapsedTime(&d, h.ev[7], h.ev[3]);
+    fprintf(stderr, "[pnpb200 asm] residual %.2f ms | jacobian cells %.2f | blocks %.2f | zero-row %.2f\n", a, b, c, d);
+  }
 }
 
 } // namespace pnpb200

@@ -227,7 +227,7 @@ int pnpb200_set_coefficients(pnpb200_handle* ph, const double* eps, const double
     h.q_eafe[0] = 0.0; h.q_eafe[1] = val[1]; h.q_eafe[2] = val[2];
     compute_k00(h);
     PNP_CUDA(cudaStreamSynchronize(s));
-    h.have_coef = true;
+    h.have_coef = true; h.rhs_current = false;
     return FASP_SUCCESS;
   });
 }
@@ -244,7 +244,7 @@ int pnpb200_set_dirichlet(pnpb200_handle* ph, int n_bc, const int* bc_dofs)
       if (bc_dofs[i] < 0 || (size_t)bc_dofs[i] >= N) throw Error(ERROR_INPUT_PAR, "Dirichlet dof out of range");
       f[bc_dofs[i]] = 1;
     }
-    h.bc_user = f;
+    h.bc_user = f; h.rhs_current = false;
     for (size_t i = owned_dofs(h); i < N; ++i) f[i] = 1;   // ghost rows stay identity rows
     h.bcflag.upload(f.data(), N);
     PNP_CUDA(cudaStreamSynchronize(s));
@@ -258,6 +258,7 @@ int pnpb200_set_solution(pnpb200_handle* ph, const double* uu)
   return guarded([&]() -> int {
     Handle& h = ph->h;
     PNP_CUDA(cudaSetDevice(h.device));
+    h.rhs_current = false;
     h.uu.upload(uu, 3 * (size_t)h.nv);
     PNP_CUDA(cudaStreamSynchronize(h.stream));
     return FASP_SUCCESS;
@@ -275,6 +276,7 @@ int pnpb200_set_solution_device(pnpb200_handle* ph, const double* d_uu)
   if (!ph || !d_uu) return ERROR_INPUT_PAR;
   return guarded([&]() -> int {
     Handle& h = ph->h;
+    h.rhs_current = false;
     PNP_CUDA(cudaMemcpyAsync(h.uu.p, d_uu, 3 * (size_t)h.nv * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
     PNP_CUDA(cudaStreamSynchronize(h.stream));
     return FASP_SUCCESS;
@@ -400,6 +402,7 @@ int pnpb200_test_solver(pnpb200_handle* ph, const double* target, double* x, con
     const size_t N = 3 * (size_t)h.nv;
     DevBuf<double> t; t.alloc(N, s); t.upload(target, N);
     bsrt_spmv(h.hier.lv[0]->A, t.p, h.rhs.p, s);          // rhs = J * target, linear_pnp.cpp:144
+    h.rhs_current = false;
     int st = 0;
     solve_current(h, it, amg, &st);
     if (status_its) *status_its = st;
@@ -424,7 +427,7 @@ int pnpb200_newton_step(pnpb200_handle* ph, const itsolver_param* it, const AMG_
     solve_current(h, it, amg, &st);
     if (krylov_status) *krylov_status = st;
     const size_t N = 3 * (size_t)h.nv;
-    if (st >= 0) vec_axpy(1.0, h.du.p, h.uu.p, owned_dofs(h), s);     // linear_pnp.cpp:109-127
+    if (st >= 0) { vec_axpy(1.0, h.du.p, h.uu.p, owned_dofs(h), s); h.rhs_current = false; }    // linear_pnp.cpp:109-127
     halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
     double a = 0, b = 0;
     { EventSpan e(h, h.stats.ms_residual); assemble_residual(h, h.rhs, &a, &b); e.stop(); }

@@ -171,6 +171,7 @@ int pnpb200_set_partition(pnpb200_handle* ph, int n_owned, int n_neighbors, cons
     f.resize(N, 0);
     for (size_t i = 3 * (size_t)n_owned; i < N; ++i) f[i] = 1;
     h.bcflag.upload(f.data(), N);
+    h.rhs_current = false;
     PNP_CUDA(cudaStreamSynchronize(s));
     return FASP_SUCCESS;
   } catch (const Error& e) { fprintf(stderr, "### pnpb200 ERROR: %s\n", e.what()); return e.code; }

@@ -126,6 +126,7 @@ struct Handle {
   DevBuf<unsigned char> bcflag; // 3*nv
   double q_eafe[3] = {0, 0, 0}; // valency function at dofs 0..2 (linear_pnp.cpp:220-224)
   bool have_coef = false;
+  bool rhs_current = false;     // h.rhs holds the residual of the CURRENT solution (reused as the next step's rhs)
   int use_eafe = 1;
   // fine level matrix + per-pattern tables
   DevBuf<double> omega;         // nnzb: EAFE edge weights  sum_T S^T_ij
