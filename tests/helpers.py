@@ -124,3 +124,28 @@ def irregular_mesh(O, nx, ny, nz, seed=11, refine_fraction=0.25, jitter=0.15):
     cells = np.vstack([keep] + subs)
     cells = np.sort(cells, axis=1)          # UFC ordering (ascending vertex ids)
     return np.ascontiguousarray(X.ravel()), np.ascontiguousarray(cells.astype(np.int32).ravel())
+
+
+def manufactured_sources(O, P, uu_star):
+    """Source-manufactured problem in the spirit of tests/pnp_tests/test_pnp_eafe.cpp:107-138: choose
+    the P1 fields fixed_charge / reaction such that the given nodal vector uu_star is an EXACT root
+    of the discrete residual L (forms.ufl:36-43): M fc = -r_phi(uu*), M reac_k = -r_k(uu*), with M the
+    P1 mass matrix. Returns (fixed, reac)."""
+    import ctypes as C
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    zero_nv, zero_N = np.zeros(P.nv), np.zeros(P.N)
+    r = np.zeros(P.N); l2, li = C.c_double(), C.c_double()
+    O.lib().orc_residual(P.nv, P.xyz, P.nc, P.cells, np.ascontiguousarray(uu_star), P.eps, zero_nv, P.diff, P.val, zero_N,
+                         np.zeros(P.N, dtype=np.uint8), r, C.byref(l2), C.byref(li))
+    X = P.xyz.reshape(-1, 3); cv = P.cells.reshape(-1, 4)
+    vol = np.abs(np.linalg.det(X[cv][:, 1:] - X[cv][:, :1])) / 6
+    Ml = (np.ones((4, 4)) + np.eye(4)) / 20.0
+    rows = np.repeat(cv, 4, axis=1).ravel(); cols = np.tile(cv, (1, 4)).ravel()
+    vals = (vol[:, None, None] * Ml[None]).ravel()
+    M = sp.csr_matrix((vals, (rows, cols)), shape=(P.nv, P.nv))
+    lu = spla.splu(M.tocsc())
+    fixed = -lu.solve(r[0::3])
+    reac = np.zeros(P.N)
+    reac[1::3] = -lu.solve(r[1::3]); reac[2::3] = -lu.solve(r[2::3])
+    return fixed, reac
