@@ -66,6 +66,13 @@ int  pnpb200_get_solution_device(pnpb200_handle* h, double* d_uu);
 /* Linear_PNP::use_eafe / no_eafe (linear_pnp.cpp:187-192) */
 int  pnpb200_use_eafe(pnpb200_handle* h, int on);
 
+/* Form variant of benchmarks/pnp_diode/vector_linear_pnp_forms.{ufl,h}: `poisson_scale` (a UFL
+ * Constant there) multiplies the charge terms of the Poisson row in a and L
+ * (forms.h:8721-8724, L I[9]); with conc_cutoff != 0 the Jacobian's diffusion terms use
+ * w > -50 ? exp(w) : 0 (forms.h:8606-8608 — the generated header, which is what runs, not the
+ * rational tail of the .ufl). Default (1.0, 0) = the pnp_exact_solution forms. */
+int  pnpb200_set_form_variant(pnpb200_handle* h, double poisson_scale, int conc_cutoff);
+
 /* sizes */
 int  pnpb200_num_dofs(const pnpb200_handle* h);
 int  pnpb200_num_block_rows(const pnpb200_handle* h);

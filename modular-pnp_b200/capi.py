@@ -112,6 +112,7 @@ def lib():
     L.pnpb200_set_solution_device.argtypes = [H, C.c_void_p]
     L.pnpb200_get_solution_device.argtypes = [H, C.c_void_p]
     L.pnpb200_use_eafe.argtypes = [H, C.c_int]
+    L.pnpb200_set_form_variant.argtypes = [H, C.c_double, C.c_int]
     for f in ("pnpb200_num_dofs", "pnpb200_num_block_rows", "pnpb200_num_blocks"):
         getattr(L, f).argtypes = [H]
     L.pnpb200_assemble.argtypes = [H]
@@ -292,6 +293,9 @@ class PNP:
         uu = np.zeros(self.N)
         _check(self.L.pnpb200_get_solution(self.h, uu), "get_solution")
         return uu
+
+    def set_form_variant(self, poisson_scale=1.0, conc_cutoff=False):
+        _check(self.L.pnpb200_set_form_variant(self.h, float(poisson_scale), 1 if conc_cutoff else 0), "set_form_variant")
 
     def use_eafe(self, on=True):
         _check(self.L.pnpb200_use_eafe(self.h, 1 if on else 0), "use_eafe")

@@ -27,7 +27,7 @@ template <bool FULL>
 __global__ void __launch_bounds__(128)
 cell_jacobian_kernel(int nc, const int4* __restrict__ cells, const double* __restrict__ xyz,
                      const double* __restrict__ uu, const double* __restrict__ diff,
-                     const double* __restrict__ val, double* __restrict__ rec)
+                     const double* __restrict__ val, double pscale, int cutoff, double* __restrict__ rec)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
@@ -64,15 +64,16 @@ cell_jacobian_kernel(int nc, const int4* __restrict__ cells, const double* __res
       const double Dk = f[0] * D[k][0] + f[1] * D[k][1] + f[2] * D[k][2] + f[3] * D[k][3];
       const double qk = f[0] * q[k][0] + f[1] * q[k][1] + f[2] * q[k][2] + f[3] * q[k][3];
       const double ex = exp(uk);
-      Q[k] += W * qk * Dk * ex;
-      const double t = W * qk * ex;
+      const double cx = (cutoff && !(uk > -50.0)) ? 0.0 : ex;     // diode conc(w), pnp_diode forms.h:8606-8608
+      Q[k] += W * qk * Dk * cx;
+      const double t = W * qk * ex * pscale;                      // poisson_scale, pnp_diode forms.h:8721-8724
       int m = 0;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int s = r; s < 4; ++s) M[k][m++] += t * f[r] * f[s];
       if (FULL) {
-        const double wd = W * Dk * ex;
+        const double wd = W * Dk * cx;
         S[k] += wd;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { c0[k][j] += wd * f[j]; c1[k][j] += wd * qk * f[j]; c2[k][j] += wd * u0ip * f[j]; }
@@ -253,7 +254,7 @@ cell_residual_kernel(int nc, const int4* __restrict__ cells, const double* __res
                      const double* __restrict__ uu, const double* __restrict__ eps,
                      const double* __restrict__ fixed, const double* __restrict__ diff,
                      const double* __restrict__ val, const double* __restrict__ reac,
-                     double* __restrict__ rec)
+                     double pscale, double* __restrict__ rec)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
@@ -305,7 +306,7 @@ cell_residual_kernel(int nc, const int4* __restrict__ cells, const double* __res
     for (int d = 0; d < 3; ++d) gu0[d] += u0[r] * g[r][d];
   double* o = rec + 12 * (size_t)c;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) o[i] = det * F[i] - E * (det * dot3(gu0, g[i]));
+  for (int i = 0; i < 4; ++i) o[i] = det * pscale * F[i] - E * (det * dot3(gu0, g[i]));
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     double guk[3] = {0, 0, 0}, gqk[3] = {0, 0, 0};
@@ -372,7 +373,7 @@ void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf)
   if (h.cellrec.n < need) h.cellrec.alloc(need, s);
   out.alloc(3 * (size_t)h.nv, s);
   cell_residual_kernel<<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.eps.p, h.fixed.p, h.diff.p,
-                                                      h.val.p, h.reac.p, h.cellrec.p);
+                                                      h.val.p, h.reac.p, h.poisson_scale, h.cellrec.p);
   PNP_COUNT_LAUNCH();
   const int nblk = cdiv(h.nv, 256);
   h.red.alloc(2 * (size_t)nblk + 2, s);
@@ -409,7 +410,7 @@ void assemble_system(Handle& h)
   const size_t need = (size_t)h.nc * rs;
   if (h.cellrec.n < need) h.cellrec.alloc(need, s);
   if (h.use_eafe) {
-    cell_jacobian_kernel<false><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.cellrec.p);
+    cell_jacobian_kernel<false><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, h.cellrec.p);
     PNP_COUNT_LAUNCH();
     mark(2);
     assemble_blocks_kernel<true><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
@@ -417,7 +418,7 @@ void assemble_system(Handle& h)
         h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
     PNP_COUNT_LAUNCH();
   } else {
-    cell_jacobian_kernel<true><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.cellrec.p);
+    cell_jacobian_kernel<true><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, h.cellrec.p);
     PNP_COUNT_LAUNCH();
     mark(2);
     assemble_blocks_kernel<false><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(

@@ -294,6 +294,12 @@ int pnpb200_get_solution_device(pnpb200_handle* ph, double* d_uu)
   });
 }
 
+int pnpb200_set_form_variant(pnpb200_handle* ph, double poisson_scale, int conc_cutoff)
+{
+  if (!ph) return ERROR_INPUT_PAR;
+  ph->h.poisson_scale = poisson_scale; ph->h.conc_cutoff = conc_cutoff ? 1 : 0; ph->h.rhs_current = false;
+  return FASP_SUCCESS;
+}
 int pnpb200_use_eafe(pnpb200_handle* ph, int on) { if (!ph) return ERROR_INPUT_PAR; ph->h.use_eafe = on ? 1 : 0; return FASP_SUCCESS; }
 int pnpb200_num_dofs(const pnpb200_handle* ph) { return ph ? 3 * ph->h.hier.lv[0]->A.n : 0; }
 int pnpb200_num_block_rows(const pnpb200_handle* ph) { return ph ? ph->h.hier.lv[0]->A.n : 0; }

@@ -128,6 +128,8 @@ struct Handle {
   bool have_coef = false;
   bool rhs_current = false;     // h.rhs holds the residual of the CURRENT solution (reused as the next step's rhs)
   int use_eafe = 1;
+  double poisson_scale = 1.0;   // diode forms: scale of the charge terms in the Poisson row
+  int conc_cutoff = 0;          // diode forms: exp(w) -> (w > -50 ? exp(w) : 0) in the Jacobian's diffusion terms
   // fine level matrix + per-pattern tables
   DevBuf<double> omega;         // nnzb: EAFE edge weights  sum_T S^T_ij
   DevBuf<double> k00;           // nnzb: permittivity stiffness (solution independent)

@@ -20,6 +20,12 @@ static double W24[24], P24[24][4];
 // 15-point degree-5 rule (forms.h:8409-8411): centroid, two 4-orbits, one 6-orbit.
 static double W15[15], P15[15][4];
 static bool tables_ready = false;
+// form variant of benchmarks/pnp_diode/vector_linear_pnp_forms.h (:8606-8608, :8721-8724, L :I[9]):
+// poisson_scale multiplies the charge terms of the Poisson row; with conc_cutoff the Jacobian's
+// diffusion terms use exp(w) only for w > -50 (else 0). Defaults reproduce pnp_exact_solution.
+static double g_poisson_scale = 1.0;
+static int g_conc_cutoff = 0;
+static void (*g_ref_set_scale)(double) = nullptr;
 
 static void set_pt(double P[4], double x, double y, double z)
 {
@@ -161,18 +167,19 @@ void jac_element(double* A, const double* uu, const double* eps, const double* D
       double Dk = 0.0, qk = 0.0, uk = 0.0;
       for (int r = 0; r < 4; ++r) { Dk += f[r] * D[4 * k + r]; qk += f[r] * q[4 * k + r]; uk += f[r] * uu[4 * k + r]; }
       const double ex = std::exp(uk);
+      const double cx = (g_conc_cutoff && !(uk > -50.0)) ? 0.0 : ex;      // diode conc(w)
       // drift vector  grad(uu_k + q_k uu_0) = grad uu_k + q grad uu_0 + uu_0 grad q
       double bv[3];
       for (int d = 0; d < 3; ++d) bv[d] = gu[k][d] + qk * gu[0][d] + u0 * gq[k][d];
       for (int i = 0; i < 4; ++i) {
         const double bi = det * dot3(bv, g[i]);
         for (int j = 0; j < 4; ++j) {
-          // (k,k): D e^{u} (grad u_k + drift * u_k) . grad v_k
-          A[(4 * k + i) * 12 + 4 * k + j] += W * Dk * ex * (G[i][j] + bi * f[j]);
-          // (k,0): q D e^{u} grad u_0 . grad v_k
-          A[(4 * k + i) * 12 + j] += W * qk * Dk * ex * G[i][j];
-          // (0,k): -q e^{u} u_k v_0
-          A[i * 12 + 4 * k + j] += -(W * det) * qk * ex * f[i] * f[j];
+          // (k,k): D conc(u) (grad u_k + drift * u_k) . grad v_k
+          A[(4 * k + i) * 12 + 4 * k + j] += W * Dk * cx * (G[i][j] + bi * f[j]);
+          // (k,0): q D conc(u) grad u_0 . grad v_k
+          A[(4 * k + i) * 12 + j] += W * qk * Dk * cx * G[i][j];
+          // (0,k): -poisson_scale q e^{u} u_k v_0
+          A[i * 12 + 4 * k + j] += -(W * det) * g_poisson_scale * qk * ex * f[i] * f[j];
         }
       }
     }
@@ -211,7 +218,7 @@ void res_element(double* b, const double* uu, const double* eps, const double* f
         b[4 * k + i] += W * det * rk * f[i] - W * Dk * ex * (det * dot3(bv, g[i]));
     }
     for (int i = 0; i < 4; ++i)
-      b[i] += W * det * src * f[i] - W * e_ip * (det * dot3(gu[0], g[i]));
+      b[i] += W * det * g_poisson_scale * src * f[i] - W * e_ip * (det * dot3(gu[0], g[i]));
   }
 }
 
@@ -239,6 +246,7 @@ int orc_use_ref_kernels(int on, const char* libpath)
 {
   if (!on) {
     orc::kernels = {orc::eafe_element, orc::jac_element, orc::res_element, 0};
+    orc::g_ref_set_scale = nullptr;
     return 0;
   }
   void* h = dlopen(libpath, RTLD_NOW | RTLD_LOCAL);
@@ -248,7 +256,16 @@ int orc_use_ref_kernels(int on, const char* libpath)
   auto r = (orc::res_fn)dlsym(h, "ref_res_tabulate");
   if (!e || !j || !r) return -1;
   orc::kernels = {e, j, r, 1};
+  orc::g_ref_set_scale = (void (*)(double))dlsym(h, "ref_set_poisson_scale");   // diode kernels only
+  if (orc::g_ref_set_scale) orc::g_ref_set_scale(orc::g_poisson_scale);
   return 0;
+}
+
+void orc_set_form_variant(double poisson_scale, int conc_cutoff)
+{
+  orc::g_poisson_scale = poisson_scale;
+  orc::g_conc_cutoff = conc_cutoff;
+  if (orc::g_ref_set_scale) orc::g_ref_set_scale(poisson_scale);
 }
 
 }

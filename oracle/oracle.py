@@ -48,6 +48,8 @@ def lib():
         L.orc_res_element.argtypes = [_f8] * 8
         L.orc_use_ref_kernels.argtypes = [C.c_int, C.c_char_p]
         L.orc_use_ref_kernels.restype = C.c_int
+        L.orc_set_form_variant.argtypes = [C.c_double, C.c_int]
+        L.orc_set_form_variant.restype = None
         L.orc_box_mesh_counts.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int)] * 2
         L.orc_box_mesh.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [_f8, _i4]
         L.orc_dirichlet_vertices.argtypes = [C.c_int, _f8, C.c_int, _i4, C.c_int, _u1]
@@ -98,8 +100,15 @@ def ref_available():
     return os.path.exists(REF_PATH)
 
 
-def use_ref_kernels(on=True):
-    rc = lib().orc_use_ref_kernels(1 if on else 0, REF_PATH.encode())
+REF_DIODE_PATH = os.path.join(_HERE, "_ref", "libpnpref_diode.so")
+
+
+def set_form_variant(poisson_scale=1.0, conc_cutoff=False):
+    lib().orc_set_form_variant(float(poisson_scale), 1 if conc_cutoff else 0)
+
+
+def use_ref_kernels(on=True, diode=False):
+    rc = lib().orc_use_ref_kernels(1 if on else 0, (REF_DIODE_PATH if diode else REF_PATH).encode())
     if rc != 0:
         raise RuntimeError("reference kernels unavailable (oracle/_ref/libpnpref.so)")
 

@@ -37,6 +37,10 @@ void orc_res_element(double* b12, const double* uu12, const double* eps4, const 
 /* choose which element kernels the assembler drives: 0 = restated (default),
  * 1 = the reference's own (needs oracle/_ref/libpnpref.so; returns -1 if absent) */
 int  orc_use_ref_kernels(int on, const char* libpath);
+/* form variant of benchmarks/pnp_diode/vector_linear_pnp_forms.{ufl,h}: poisson_scale on the charge
+ * terms of the Poisson row, exp cutoff (w > -50 ? exp(w) : 0) in the Jacobian's diffusion terms.
+ * (1.0, 0) = pnp_exact_solution forms (default). */
+void orc_set_form_variant(double poisson_scale, int conc_cutoff);
 
 /* ---- mesh / dofs / BC ---- */
 void orc_box_mesh_counts(int nx, int ny, int nz, int* nv, int* nc);

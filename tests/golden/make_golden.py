@@ -55,3 +55,37 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def diode():
+    """golden vectors of the DIODE variant of the forms from the reference's own compiled kernels
+    (oracle/_ref/libpnpref_diode.so <- benchmarks/pnp_diode/vector_linear_pnp_forms.h)"""
+    ref = C.CDLL(O.REF_DIODE_PATH)
+    f8 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    ref.ref_jac_tabulate.argtypes = [f8] * 6
+    ref.ref_res_tabulate.argtypes = [f8] * 8
+    ref.ref_set_poisson_scale.argtypes = [C.c_double]
+    rng = np.random.default_rng(4321)
+    n = 48
+    ps = 37.5
+    ref.ref_set_poisson_scale(ps)
+    X = np.zeros((n, 12)); UU = np.zeros((n, 12)); EPS = np.zeros((n, 4)); D = np.zeros((n, 12)); Q = np.zeros((n, 12))
+    FC = np.zeros((n, 4)); RE = np.zeros((n, 12)); A_jac = np.zeros((n, 144)); b_res = np.zeros((n, 12))
+    base = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1.0])
+    for t in range(n):
+        X[t] = (base + 0.2 * rng.uniform(-1, 1, 12)) * rng.uniform(0.01, 2.0)
+        UU[t] = rng.uniform(-1, 1, 12); EPS[t] = rng.uniform(0.5, 2, 4); D[t] = rng.uniform(0.1, 2, 12)
+        Q[t] = rng.uniform(-2, 2, 12); FC[t] = rng.uniform(-1, 1, 4); RE[t] = rng.uniform(-1, 1, 12)
+        if t % 3 == 0:       # log-densities straddling the -50 cutoff of conc(w)
+            UU[t, 4:8] = -50.0 + rng.uniform(-3, 3, 4)
+        if t % 3 == 1:
+            UU[t, 8:12] = -50.0 + rng.uniform(-1, 1, 4); UU[t, 0:4] = 20.0 * rng.uniform(-1, 1, 4)
+        ref.ref_jac_tabulate(A_jac[t], UU[t], EPS[t], D[t], Q[t], X[t])
+        ref.ref_res_tabulate(b_res[t], UU[t], EPS[t], FC[t], D[t], Q[t], RE[t], X[t])
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "element_kernels_diode.npz"), poisson_scale=ps, X=X, UU=UU, EPS=EPS,
+                        D=D, Q=Q, FC=FC, RE=RE, A_jac=A_jac, b_res=b_res)
+    print("diode golden vectors written")
+
+
+if __name__ == "__main__":
+    diode()

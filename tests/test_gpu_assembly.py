@@ -96,3 +96,31 @@ def test_full_size_box_invariants(oracle, pkg, gpu_lib):
     np.add.at(rowsum, rows, V[:, 0, 0])
     assert np.abs(rowsum[P.bcflag[0::3] == 0]).max() <= 1e-12 * np.abs(V[:, 0, 0]).max()
     g.close()
+
+
+@pytest.mark.parametrize("use_eafe", [True, False])
+def test_diode_form_variant_parity(oracle, pkg, gpu_lib, use_eafe):
+    """diode-like input — poisson_scale != 1, diffusivity jump, |q phi| up to 20
+    (stresses the Bernoulli branch) and log-densities below the -50 cutoff of conc(w)."""
+    P = oracle.Problem(10, 4, 4)
+    rng = np.random.default_rng(77)
+    x = P.xyz[0::3]
+    uu = np.zeros(P.N)
+    uu[0::3] = np.round(20.0 * np.tanh(3 * x) * 64) / 64 + np.round(rng.uniform(-0.5, 0.5, P.nv) * 64) / 64
+    uu[1::3] = -26.0 * (1 + np.tanh(4 * x)) + 0.1 * rng.uniform(-1, 1, P.nv)      # down to -52
+    uu[2::3] = -26.0 * (1 - np.tanh(4 * x)) + 0.1 * rng.uniform(-1, 1, P.nv)
+    P.diff[1::3] = np.where(x > 0, 1.0, 0.1); P.diff[2::3] = np.where(x > 0, 2.0, 0.1)
+    ps = 12.5
+    oracle.set_form_variant(ps, True)
+    try:
+        A_ref, b_ref = P.assemble(uu, use_eafe=use_eafe)
+    finally:
+        oracle.set_form_variant(1.0, False)
+    g = gpu_problem(pkg, P, uu)
+    g.set_form_variant(ps, True)
+    g.use_eafe(use_eafe)
+    g.assemble()
+    IA, JA, val = g.get_matrix()
+    assert row_scaled_error(IA, val, A_ref) <= 1e-12
+    assert np.abs(g.get_rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    g.close()

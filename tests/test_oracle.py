@@ -201,3 +201,19 @@ def test_pvfgmres_amg_converges_and_newton_counts(oracle):
     assert res.converged == 1 and res.newton_its < 15
     assert res.rel_res[res.newton_its - 1] < 1e-8 or res.max_res[res.newton_its - 1] < 1e-10
     assert np.abs(uu - P.exact).max() < 0.05      # discretisation error of the manufactured solution
+
+
+def test_diode_form_variant_matches_reference_golden(oracle):
+    """pnp_diode forms (poisson_scale, exp cutoff at -50): restated kernels vs golden vectors from
+    the reference's compiled benchmarks/pnp_diode/vector_linear_pnp_forms.h:8388-9755"""
+    g = np.load(os.path.join(GOLD, "element_kernels_diode.npz"))
+    L = oracle.lib()
+    oracle.set_form_variant(float(g["poisson_scale"]), True)
+    try:
+        for t in range(g["X"].shape[0]):
+            J = np.zeros(144); L.orc_jac_element(J, g["UU"][t].copy(), g["EPS"][t].copy(), g["D"][t].copy(), g["Q"][t].copy(), g["X"][t].copy())
+            assert _rel(J, g["A_jac"][t]) <= 1e-13
+            b = np.zeros(12); L.orc_res_element(b, g["UU"][t].copy(), g["EPS"][t].copy(), g["FC"][t].copy(), g["D"][t].copy(), g["Q"][t].copy(), g["RE"][t].copy(), g["X"][t].copy())
+            assert _rel(b, g["b_res"][t]) <= 1e-13
+    finally:
+        oracle.set_form_variant(1.0, False)
