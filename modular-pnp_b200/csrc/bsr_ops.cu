@@ -4,9 +4,9 @@
 //   fasp_smoother_dbsr_gs_*      [EXT FASP]      -> multicolour block Gauss-Seidel
 // A half-warp (16 lanes) owns one block row; lane k owns block k of the row, so each of the 9
 // component loads is unit-stride across lanes. Rows are STORED colour by colour (rs[] = physical
-// start of a row, rowid[] = row at a physical position): one Gauss-Seidel colour is one contiguous
-// piece of ja/val, and SpMV walks the rows in the same physical order. All kernels here are
-// HBM-bound streaming kernels.
+// start of a row, rowid[] = row at a physical position, pia[] = CSR offsets in physical order): one
+// Gauss-Seidel colour is one contiguous piece of ja/val; SpMV walks the rows in natural order. All
+// kernels here are HBM-bound streaming kernels.
 #include "internal.hpp"
 #include <cub/cub.cuh>
 
@@ -14,64 +14,41 @@ namespace pnpb200 {
 
 namespace {
 
-// L2 cache-policy loads: matrix data is touched once per pass (evict_first), the vectors a sweep
-// gathers from are re-used by every colour (evict_last). L1 allocation is unchanged.
-__device__ __forceinline__ unsigned long long policy_evict_first()
-{
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ unsigned long long policy_evict_last()
-{
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ double ld_hint(const double* a, unsigned long long pol)
-{
-  double v;
-  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ int ld_hint(const int* a, unsigned long long pol)
-{
-  int v;
-  asm volatile("ld.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
-  return v;
-}
-
-// rows = rowid + first position; y = A x (MODE 0), y = b - A x (MODE 1),
-// x_row = D^{-1}(b - sum_{j != row} A_row,j x_j) (MODE 2: one Gauss-Seidel colour, y == x)
-template <int MODE, bool HINT>
-__global__ void __launch_bounds__(256)
-bsrt_row_kernel(int nrows, const int* __restrict__ rows, const int* __restrict__ ia,
-                const int* __restrict__ rs, const int* __restrict__ ja, const double* __restrict__ val,
+// One block row per half-warp, lane k = block k of the row.
+//   MODE 0: y = A x          MODE 1: y = b - A x      (rows in natural order; idx = packed
+//           (physical start, length) per row, one 8-byte load)
+//   MODE 2: x_row = D^{-1}(b - sum_{j != row} A_row,j x_j), y == x: one Gauss-Seidel colour.
+//           rows[] = rowid + p0 and idx = pia + p0 are indexed by physical position, so row id,
+//           start and length come from one level of loads.
+// The kernels are latency/occupancy bound (ncu: long-scoreboard stalls, 66-68 % achieved warps):
+// the colour kernel is compiled for 8 resident CTAs per SM (32 registers, no spills; measured
+// 4.7 ms vs 5.3 ms per fine-level sweep at 256^3), the natural-order passes for 6 (they spill at 8).
+// Tried and measured slower: ld.global.cs / L2 evict_first+evict_last hints on the matrix loads
+// (6.3-7.2 ms per sweep), requesting b and D^{-1} before the row's blocks (6.2 vs 5.5 ms: the extra
+// registers cost more occupancy than the overlap gains).
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+bsrt_row_kernel(int nrows, const int* __restrict__ rows, const int* __restrict__ idx,
+                const int* __restrict__ ja, const double* __restrict__ val,
                 const double* __restrict__ dinv, const double* __restrict__ b, const double* x, double* y)
 {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int lane = threadIdx.x & 15;
   int row = -1, s = 0, len = 0;
-  if (t < nrows) { row = rows ? rows[t] : t; s = rs[row]; len = ia[row + 1] - ia[row]; }
+  if (t < nrows) {
+    if (MODE == 2) { row = rows[t]; s = idx[t]; len = idx[t + 1] - s; }
+    else { row = t; const int2 sl = reinterpret_cast<const int2*>(idx)[t]; s = sl.x; len = sl.y; }
+  }
   const double* v = val + 9 * (size_t)s;
-  const unsigned long long pf = policy_evict_first(), pl = policy_evict_last();
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   for (int k = lane; k < len; k += 16) {
-    const int jc = HINT ? ld_hint(ja + s + k, pf) : ja[s + k];
+    const int jc = ja[s + k];
     if (MODE == 2 && jc == row) continue;
     const size_t j = 3 * (size_t)jc;
-    double x0, x1, x2;
-    if (HINT) { x0 = ld_hint(x + j, pl); x1 = ld_hint(x + j + 1, pl); x2 = ld_hint(x + j + 2, pl); }
-    else { x0 = x[j]; x1 = x[j + 1]; x2 = x[j + 2]; }
-    if (HINT) {
-      a0 += ld_hint(v + k, pf) * x0 + ld_hint(v + len + k, pf) * x1 + ld_hint(v + 2 * len + k, pf) * x2;
-      a1 += ld_hint(v + 3 * len + k, pf) * x0 + ld_hint(v + 4 * len + k, pf) * x1 + ld_hint(v + 5 * len + k, pf) * x2;
-      a2 += ld_hint(v + 6 * len + k, pf) * x0 + ld_hint(v + 7 * len + k, pf) * x1 + ld_hint(v + 8 * len + k, pf) * x2;
-    } else {
-      a0 += v[k] * x0 + v[len + k] * x1 + v[2 * len + k] * x2;
-      a1 += v[3 * len + k] * x0 + v[4 * len + k] * x1 + v[5 * len + k] * x2;
-      a2 += v[6 * len + k] * x0 + v[7 * len + k] * x1 + v[8 * len + k] * x2;
-    }
+    const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
+    a0 += v[k] * x0 + v[len + k] * x1 + v[2 * len + k] * x2;
+    a1 += v[3 * len + k] * x0 + v[4 * len + k] * x1 + v[5 * len + k] * x2;
+    a2 += v[6 * len + k] * x0 + v[7 * len + k] * x1 + v[8 * len + k] * x2;
   }
   a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
   if (row >= 0 && lane < 3) {
@@ -165,10 +142,10 @@ __global__ void rowlen_by_position_kernel(int n, const int* __restrict__ ia, con
   if (p == n) len[n] = 0;
 }
 __global__ void scatter_rs_kernel(int n, const int* __restrict__ rowid, const int* __restrict__ start,
-                                  int* __restrict__ rs)
+                                  int* __restrict__ rs, int2* __restrict__ rsl)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n) rs[rowid[p]] = start[p];
+  if (p < n) { const int i = rowid[p]; rs[i] = start[p]; rsl[i] = make_int2(start[p], start[p + 1] - start[p]); }
 }
 
 // ---- Jones-Plassmann colouring with hashed priorities (two kernels per round so that the
@@ -256,15 +233,15 @@ __global__ void iota_kernel(int n, int* __restrict__ a)
 
 void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s)
 {
-  bsrt_row_kernel<0, false><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, nullptr, A.ia.p, A.rs.p, A.ja.p, A.val.p,
-                                                                nullptr, nullptr, x, y);
+  bsrt_row_kernel<0, 6><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, nullptr, reinterpret_cast<const int*>(A.rsl.p), A.ja.p, A.val.p,
+                                                                   nullptr, nullptr, x, y);
   PNP_COUNT_LAUNCH();
 }
 
 void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s)
 {
-  bsrt_row_kernel<1, false><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, nullptr, A.ia.p, A.rs.p, A.ja.p, A.val.p,
-                                                                nullptr, b, x, r);
+  bsrt_row_kernel<1, 6><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, nullptr, reinterpret_cast<const int*>(A.rsl.p), A.ja.p, A.val.p,
+                                                                   nullptr, b, x, r);
   PNP_COUNT_LAUNCH();
 }
 
@@ -292,8 +269,6 @@ void bsrt_export_ja(const BsrT& A, int* d_ja_nat, cudaStream_t s)
   PNP_COUNT_LAUNCH();
 }
 
-static int g_gs_hint = getenv("PNPB200_GS_HINT") ? atoi(getenv("PNPB200_GS_HINT")) : 0;
-
 void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s)
 {
   const BsrT& A = L.A;
@@ -301,12 +276,8 @@ void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaSt
     const int c = reverse ? L.ngroups - 1 - cc : cc;
     const int cnt = L.color_ptr[c + 1] - L.color_ptr[c];
     if (cnt == 0) continue;
-    if (g_gs_hint)
-      bsrt_row_kernel<2, true><<<cdiv((size_t)cnt * 16, 256), 256, 0, s>>>(cnt, A.rowid.p + L.color_ptr[c], A.ia.p, A.rs.p,
-                                                                          A.ja.p, A.val.p, L.dinv.p, b, x, x);
-    else
-      bsrt_row_kernel<2, false><<<cdiv((size_t)cnt * 16, 256), 256, 0, s>>>(cnt, A.rowid.p + L.color_ptr[c], A.ia.p, A.rs.p,
-                                                                           A.ja.p, A.val.p, L.dinv.p, b, x, x);
+    bsrt_row_kernel<2, 8><<<cdiv((size_t)cnt * 16, 256), 256, 0, s>>>(cnt, A.rowid.p + L.color_ptr[c], A.pia.p + L.color_ptr[c],
+                                                                     A.ja.p, A.val.p, L.dinv.p, b, x, x);
     PNP_COUNT_LAUNCH();
   }
 }
@@ -393,11 +364,12 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
   PNP_COUNT_LAUNCH();
   // physical row starts and the physical column array
   int* len = geti(t_len, n + 1);
-  int* start = geti(t_start, n + 1);
+  A.pia.alloc(n + 1, s);
+  int* start = A.pia.p;
   rowlen_by_position_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(n, A.ia.p, A.rowid.p, len); PNP_COUNT_LAUNCH();
   exclusive_scan_int(len, start, n + 1, s);
-  A.rs.alloc(n, s);
-  scatter_rs_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, start, A.rs.p); PNP_COUNT_LAUNCH();
+  A.rs.alloc(n, s); A.rsl.alloc(n, s);
+  scatter_rs_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, start, A.rs.p, A.rsl.p); PNP_COUNT_LAUNCH();
   A.ja.alloc(A.nnzb, s);
   permute_ja_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, ja_nat, A.ja.p); PNP_COUNT_LAUNCH();
   A.brow.alloc(A.nnzb, s); A.dslot.alloc(n, s); A.tslot.alloc(A.nnzb, s);

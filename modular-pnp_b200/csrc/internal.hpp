@@ -17,6 +17,8 @@ struct BsrT {
   DevBuf<int> rs;       // physical start of each row's blocks: rows are STORED colour by colour, so that a
                         // Gauss-Seidel colour sweep streams one contiguous piece of ja/val
   DevBuf<int> rowid;    // physical row position -> row id (= rows sorted by colour)
+  DevBuf<int> pia;      // CSR offsets in PHYSICAL order: row rowid[p] owns blocks [pia[p], pia[p+1])
+  DevBuf<int2> rsl;     // (physical start, length) of row i: one 8-byte load for the natural-order kernels
   DevBuf<int> ja;       // column of each block, physical order (ascending inside a row)
   DevBuf<int> brow;     // row of each block
   DevBuf<int> dslot;    // position (absolute block index) of the diagonal block of each row
