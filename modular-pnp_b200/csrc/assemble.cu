@@ -23,8 +23,8 @@ constexpr int REC_EAFE = 32;   // 10 x (G, det*M1, det*M2) pair-major, then Q[2]
 constexpr int REC_FULL = 68;   // + S[2] T1[16] T2[16] (+2 pad)
 
 // ---- (A) Jacobian cell records -------------------------------------------------------------
-template <bool FULL>
-__global__ void __launch_bounds__(128)
+template <bool FULL, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 cell_jacobian_kernel(int nc, const int4* __restrict__ cells, const double* __restrict__ xyz,
                      const double* __restrict__ uu, const double* __restrict__ diff,
                      const double* __restrict__ val, double pscale, int cutoff, double* __restrict__ rec)
@@ -134,8 +134,8 @@ __device__ __forceinline__ double eafe_weight(const double* __restrict__ uu, con
 // lane accumulates its block in the same deterministic order without re-reading the cell list.
 // The EAFE diagonal (zero column sums, EAFE.h:4876-4879) is a half-warp reduction of the transposed
 // edge weights each off-diagonal lane evaluates next to its own.
-template <bool EAFE>
-__global__ void __launch_bounds__(256)
+template <bool EAFE, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 assemble_blocks_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs, const int* __restrict__ ja,
                        const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
                        const int4* __restrict__ cells, const double* __restrict__ rec,
@@ -249,7 +249,8 @@ __global__ void zero_row_fix_kernel(int n, const int* __restrict__ ia, const int
 }
 
 // ---- residual: (A) per-cell 12-vector, (B) per-vertex gather + BC + norm partials ------------
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 cell_residual_kernel(int nc, const int4* __restrict__ cells, const double* __restrict__ xyz,
                      const double* __restrict__ uu, const double* __restrict__ eps,
                      const double* __restrict__ fixed, const double* __restrict__ diff,
@@ -372,8 +373,9 @@ void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf)
   const size_t need = (size_t)h.nc * 12;
   if (h.cellrec.n < need) h.cellrec.alloc(need, s);
   out.alloc(3 * (size_t)h.nv, s);
-  cell_residual_kernel<<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.eps.p, h.fixed.p, h.diff.p,
-                                                      h.val.p, h.reac.p, h.poisson_scale, h.cellrec.p);
+  // 4 CTAs/SM (128 registers): measured 26.7 ms per residual at 256^3 vs 32.0 at 2 CTAs/SM
+  cell_residual_kernel<4><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.eps.p, h.fixed.p, h.diff.p,
+                                                         h.val.p, h.reac.p, h.poisson_scale, h.cellrec.p);
   PNP_COUNT_LAUNCH();
   const int nblk = cdiv(h.nv, 256);
   h.red.alloc(2 * (size_t)nblk + 2, s);
@@ -410,18 +412,21 @@ void assemble_system(Handle& h)
   const size_t need = (size_t)h.nc * rs;
   if (h.cellrec.n < need) h.cellrec.alloc(need, s);
   if (h.use_eafe) {
-    cell_jacobian_kernel<false><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, h.cellrec.p);
+    // exp-bound: 3 CTAs/SM (136 registers) is the measured optimum (23 ms; 25 at 4, 35 at 6)
+    cell_jacobian_kernel<false, 3><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, h.cellrec.p);
     PNP_COUNT_LAUNCH();
     mark(2);
-    assemble_blocks_kernel<true><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
+    // 6 CTAs/SM (40 registers, some spills): the gather is latency bound, occupancy beats registers
+    // (measured at 256^3: 55 ms at 3 CTAs/SM, 44 at 4, 40 at 6)
+    assemble_blocks_kernel<true, 6><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
         A.n, A.ia.p, A.rs.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
         h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
     PNP_COUNT_LAUNCH();
   } else {
-    cell_jacobian_kernel<true><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, h.cellrec.p);
+    cell_jacobian_kernel<true, 2><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, h.cellrec.p);
     PNP_COUNT_LAUNCH();
     mark(2);
-    assemble_blocks_kernel<false><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
+    assemble_blocks_kernel<false, 4><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
         A.n, A.ia.p, A.rs.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
         h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
     PNP_COUNT_LAUNCH();
