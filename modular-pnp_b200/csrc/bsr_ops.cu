@@ -63,6 +63,48 @@ bsrt_row_kernel(int nrows, const int* __restrict__ rows, const int* __restrict__
   }
 }
 
+// Small levels (<= SMALL_LEVEL_ROWS rows): the whole multicolour sweep in ONE launch of one CTA,
+// colours separated by __syncthreads() instead of kernel boundaries (the coarsest levels of the
+// K-cycle are visited 8-16 times per Krylov iteration and are pure launch latency). Measured at
+// 256^3: threshold 600 -> -1.3 % Krylov time, threshold 6144 -> +2.5 % (one SM is too slow for a
+// 3.5 k-row level), so only the last one or two levels take this path.
+constexpr int SMALL_LEVEL_ROWS = 512;
+__global__ void __launch_bounds__(1024, 1)
+mcgs_small_kernel(int ngroups, int reverse, const int* __restrict__ gptr, const int* __restrict__ rowid,
+                  const int* __restrict__ pia, const int* __restrict__ ja, const double* __restrict__ val,
+                  const double* __restrict__ dinv, const double* __restrict__ b, double* x)
+{
+  const int hw = threadIdx.x >> 4, nhw = blockDim.x >> 4, lane = threadIdx.x & 15;
+  for (int gg = 0; gg < ngroups; ++gg) {
+    const int g = reverse ? ngroups - 1 - gg : gg;
+    const int p0 = gptr[g], p1 = gptr[g + 1];
+    for (int base = p0; base < p1; base += nhw) {        // uniform trip count: shuffles stay converged
+      const int p = base + hw;
+      int row = -1, s = 0, len = 0;
+      if (p < p1) { row = rowid[p]; s = pia[p]; len = pia[p + 1] - s; }
+      const double* v = val + 9 * (size_t)s;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int k = lane; k < len; k += 16) {
+        const int jc = ja[s + k];
+        if (jc == row) continue;
+        const size_t j = 3 * (size_t)jc;
+        const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
+        a0 += v[k] * x0 + v[len + k] * x1 + v[2 * len + k] * x2;
+        a1 += v[3 * len + k] * x0 + v[4 * len + k] * x1 + v[5 * len + k] * x2;
+        a2 += v[6 * len + k] * x0 + v[7 * len + k] * x1 + v[8 * len + k] * x2;
+      }
+      a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
+      if (row >= 0 && lane < 3) {
+        const size_t o = 3 * (size_t)row;
+        const double r0 = b[o] - a0, r1 = b[o + 1] - a1, r2 = b[o + 2] - a2;
+        const double* d = dinv + 9 * (size_t)row + 3 * lane;
+        x[o + lane] = d[0] * r0 + d[1] * r1 + d[2] * r2;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void diaginv_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
                                const int* __restrict__ dslot, const double* __restrict__ val,
                                double* __restrict__ dinv)
@@ -272,6 +314,12 @@ void bsrt_export_ja(const BsrT& A, int* d_ja_nat, cudaStream_t s)
 void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s)
 {
   const BsrT& A = L.A;
+  if (A.n <= SMALL_LEVEL_ROWS && L.ngroups > 0) {
+    mcgs_small_kernel<<<1, 1024, 0, s>>>(L.ngroups, reverse ? 1 : 0, L.d_color_ptr.p, A.rowid.p, A.pia.p, A.ja.p, A.val.p,
+                                        L.dinv.p, b, x);
+    PNP_COUNT_LAUNCH();
+    return;
+  }
   for (int cc = 0; cc < L.ngroups; ++cc) {
     const int c = reverse ? L.ngroups - 1 - cc : cc;
     const int cnt = L.color_ptr[c + 1] - L.color_ptr[c];
@@ -348,6 +396,8 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
   for (int g = 0; g < ngroups_max; ++g)
     if (hh[g] > 0) { L.color_ptr.push_back(L.color_ptr.back() + hh[g]); if (g % 64 + 1 > maxc) maxc = g % 64 + 1; }
   L.ngroups = (int)L.color_ptr.size() - 1;
+  L.d_color_ptr.alloc(L.color_ptr.size(), s);
+  L.d_color_ptr.upload(L.color_ptr.data(), L.color_ptr.size());
   if (n_own < n && hh[ngroups_max - 1] > 0) { --L.ngroups; maxc = 0; for (int g = 0; g < ngroups_max - 1; ++g) if (hh[g] > 0 && g % 64 + 1 > maxc) maxc = g % 64 + 1; }
   L.ncolors = maxc;
   int key_bits = 6; while ((1 << key_bits) < ngroups_max) ++key_bits;

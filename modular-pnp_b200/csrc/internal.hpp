@@ -46,6 +46,7 @@ struct Level {
   int ncolors = 0;              // colours of the graph
   int ngroups = 0;              // (tile, colour) groups of one sweep, in order
   std::vector<int> color_ptr;   // host, ngroups+1 offsets into A.rowid
+  DevBuf<int> d_color_ptr;      // the same offsets on the device (single-CTA sweep of small levels)
   // aggregation to the next level
   int nagg = 0;
   DevBuf<int> agg;              // n, -1 = isolated
