@@ -396,6 +396,25 @@ def fasp_solver_dbsr_krylov_amg(IA, JA, val, b, it, amg, x0=None):
     return xv._keep, st
 
 
+def fasp_solver_dcsr_krylov(IA, JA, val, b, it):
+    """tests/eafe_tests/test_eafe.cpp:170 entry: scalar CSR (n % 3 == 0), unpreconditioned FGMRES on the GPU"""
+    IA = np.ascontiguousarray(IA, dtype=np.int32); JA = np.ascontiguousarray(JA, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    A = dCSRmat(); A.row = A.col = len(IA) - 1; A.nnz = len(JA)
+    A.IA = IA.ctypes.data_as(C.POINTER(INT)); A.JA = JA.ctypes.data_as(C.POINTER(INT)); A.val = val.ctypes.data_as(C.POINTER(REAL))
+    bv = numpy_to_dvec(b); xv = numpy_to_dvec(np.zeros(len(b)))
+    st = lib().fasp_solver_dcsr_krylov(C.byref(A), C.byref(bv), C.byref(xv), C.byref(it))
+    return xv._keep, st
+
+
+def fasp_solver_dbsr_krylov_ilu(IA, JA, val, b, it):
+    A = numpy_to_bsr(IA, JA, val)
+    bv = numpy_to_dvec(b); xv = numpy_to_dvec(np.zeros(len(b)))
+    ilu = ILU_param()
+    st = lib().fasp_solver_dbsr_krylov_ilu(C.byref(A), C.byref(bv), C.byref(xv), C.byref(it), C.byref(ilu))
+    return xv._keep, st
+
+
 def fasp_format_dcsr_dbsr(IA, JA, val, nb=3):
     IA = np.ascontiguousarray(IA, dtype=np.int32); JA = np.ascontiguousarray(JA, dtype=np.int32)
     val = np.ascontiguousarray(val, dtype=np.float64)

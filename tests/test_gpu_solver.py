@@ -161,3 +161,48 @@ def test_host_driver_binary(gpu_lib):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("NEWTON_ITERATIONS")][0].split()
     assert int(line[1]) == 8 and int(line[3]) == 1 and float(line[5]) < 1e-8
+
+
+def test_hierarchy_reuse_mode(oracle, pkg, system):
+    """pnpb200_set_hierarchy_reuse(1): the second solve keeps aggregates / patterns / colourings and
+    only redoes the numerical Galerkin products; the solve must still meet the tolerance."""
+    P, g, IA, JA, val, b = system
+    it, amg = pkg.default_params()
+    g.set_hierarchy_reuse(False)
+    its0 = g.solve(it, amg)
+    lv0 = [(g.stats().level_rows[l], g.stats().level_nnzb[l]) for l in range(g.stats().n_levels)]
+    g.set_hierarchy_reuse(True)
+    its1 = g.solve(it, amg)
+    lv1 = [(g.stats().level_rows[l], g.stats().level_nnzb[l]) for l in range(g.stats().n_levels)]
+    g.set_hierarchy_reuse(False)
+    assert its0 > 0 and its1 == its0 and lv0 == lv1
+    b_now = g.get_rhs()          # earlier tests of this module replaced the device rhs (test_solver)
+    r = b_now - oracle.bsr_spmv(IA, JA, val, g.get_update())
+    assert np.linalg.norm(r) <= 1.0001 * it.tol * np.linalg.norm(b_now)
+
+
+def test_other_fasp_entry_points(oracle, pkg, system):
+    P, g, IA, JA, val, b = system
+    # fasp_blas_dbsr_aAxpy
+    rng = np.random.default_rng(21)
+    x = rng.uniform(-1, 1, P.N); y = rng.uniform(-1, 1, P.N)
+    A = pkg.capi.numpy_to_bsr(IA, JA, val)
+    y2 = y.copy()
+    pkg.lib().fasp_blas_dbsr_aAxpy(-0.5, C.byref(A), x, y2)
+    ref = y - 0.5 * oracle.bsr_spmv(IA, JA, val, x)
+    assert np.abs(y2 - ref).max() <= 1e-13 * np.abs(ref).max()
+    # fasp_solver_dbsr_krylov_ilu (routed to the AMG path, DESIGN.md §6)
+    it, amg = pkg.default_params()
+    xs, st = pkg.capi.fasp_solver_dbsr_krylov_ilu(IA, JA, val, b, it)
+    assert st > 0
+    assert np.linalg.norm(b - oracle.bsr_spmv(IA, JA, val, xs)) <= 1.0001 * it.tol * np.linalg.norm(b)
+    # fasp_solver_dcsr_krylov: unpreconditioned FGMRES on a scalar CSR (diagonally dominant 3n x 3n)
+    n = 300
+    import scipy.sparse as sp
+    M = sp.random(n, n, density=0.02, random_state=5, format="csr") + sp.identity(n) * 4.0
+    M = M.tocsr(); M.sort_indices()
+    rhs = rng.uniform(-1, 1, n)
+    it2, _ = pkg.default_params(maxit=200)
+    xs, st = pkg.capi.fasp_solver_dcsr_krylov(M.indptr, M.indices, M.data, rhs, it2)
+    assert st > 0
+    assert np.linalg.norm(M @ xs - rhs) <= 1.0001 * it2.tol * np.linalg.norm(rhs)
