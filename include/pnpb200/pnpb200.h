@@ -105,6 +105,14 @@ int  pnpb200_test_solver(pnpb200_handle* h, const double* target, double* x,
 int  pnpb200_newton_step(pnpb200_handle* h, const itsolver_param* itparam, const AMG_param* amgparam,
                          int* krylov_status_its, double* l2, double* linf);
 
+/* Post-processing on the device. Error::compute_l2_error / compute_h1_error
+ * (src/error.cpp:58-103) against the NODAL interpolant `exact[3*Nv]` of the exact solution, summed
+ * over the three components: l2 = sqrt(sum_k int e_k^2), h1 = sqrt(l2^2 + sum_k int |grad e_k|^2).
+ * (single-GPU handles; on a partitioned handle ghost cells would be counted twice). */
+int  pnpb200_error_norms(pnpb200_handle* h, const double* exact, double* l2_error, double* h1_error);
+/* Linear_PNP::get_total_charge (linear_pnp.cpp:322-351): nodal fixed_charge + sum_k q_k exp(u_k), charge[Nv] */
+int  pnpb200_total_charge(pnpb200_handle* h, double* charge);
+
 /* hierarchy policy: 0 = rebuild aggregates/patterns/colourings every solve (the reference's
  * behaviour, default), 1 = keep the symbolic hierarchy of the previous solve and only
  * recompute numerical values (Galerkin products, block inverses). */

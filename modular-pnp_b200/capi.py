@@ -125,6 +125,8 @@ def lib():
     L.pnpb200_newton_step.argtypes = [H, C.POINTER(itsolver_param), C.POINTER(AMG_param), C.POINTER(C.c_int),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pnpb200_set_hierarchy_reuse.argtypes = [H, C.c_int]
+    L.pnpb200_error_norms.argtypes = [H, _f8, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.pnpb200_total_charge.argtypes = [H, _f8]
     L.pnpb200_get_stats.argtypes = [H, C.POINTER(pnpb200_stats)]
     L.pnpb200_set_timing_detail.argtypes = [H, C.c_int]
     L.pnpb200_get_level_matrix.argtypes = [H, C.c_int, C.POINTER(dBSRmat)]
@@ -340,6 +342,16 @@ class PNP:
         _check(self.L.pnpb200_newton_step(self.h, C.byref(it), C.byref(amg), C.byref(st), C.byref(a), C.byref(b)),
                "newton_step")
         return st.value, a.value, b.value
+
+    def error_norms(self, exact):
+        a, b = C.c_double(), C.c_double()
+        _check(self.L.pnpb200_error_norms(self.h, np.ascontiguousarray(exact, dtype=np.float64), C.byref(a), C.byref(b)), "error_norms")
+        return a.value, b.value
+
+    def total_charge(self):
+        out = np.zeros(self.nv)
+        _check(self.L.pnpb200_total_charge(self.h, out), "total_charge")
+        return out
 
     def set_hierarchy_reuse(self, on):
         _check(self.L.pnpb200_set_hierarchy_reuse(self.h, 1 if on else 0), "set_hierarchy_reuse")

@@ -363,7 +363,82 @@ __global__ void __launch_bounds__(1024) finalize_norm_kernel(int nblk, const dou
   if (threadIdx.x == 0) { out2[0] = ss; out2[1] = mx; }
 }
 
+// ---- post-processing functionals ------------------------------------------------
+// Error::compute_l2_error / compute_semi_h1_error (src/error.cpp:58-103 with include/L2Error.h,
+// include/SemiH1error.h): sum over components of int e_k^2 and int |grad e_k|^2, e = u_h - u_exact
+// nodal (P1): exact with the element mass matrix det/120 (1 + delta_rs) and the constant gradient.
+__global__ void __launch_bounds__(256)
+error_cells_kernel(int nc, const int4* __restrict__ cells, const double* __restrict__ xyz,
+                   const double* __restrict__ uu, const double* __restrict__ exact, double* __restrict__ partial)
+{
+  __shared__ double sm[32];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double l2 = 0.0, h1 = 0.0;
+  if (c < nc) {
+    const int4 cv = cells[c];
+    const int v[4] = {cv.x, cv.y, cv.z, cv.w};
+    double x[4][3], g[4][3], det;
+    load_cell_xyz(xyz, cv, x);
+    tet_geom(x, g, det);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double e[4], sum = 0.0, sq = 0.0, gr[3] = {0, 0, 0};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        e[r] = uu[3 * (size_t)v[r] + k] - exact[3 * (size_t)v[r] + k];
+        sum += e[r]; sq += e[r] * e[r];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gr[d] += e[r] * g[r][d];
+      }
+      l2 += det * (sum * sum + sq) / 120.0;
+      h1 += det * dot3(gr, gr) / 6.0;
+    }
+  }
+  l2 = block_sum(l2, sm);
+  h1 = block_sum(h1, sm);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = l2; partial[2 * blockIdx.x + 1] = h1; }
+}
+
+__global__ void __launch_bounds__(1024) finalize_sum2_kernel(int nblk, const double* __restrict__ partial, double* __restrict__ out2)
+{
+  __shared__ double sm[32];
+  double a = 0.0, b = 0.0;
+  for (int t = threadIdx.x; t < nblk; t += blockDim.x) { a += partial[2 * t]; b += partial[2 * t + 1]; }
+  a = block_sum(a, sm);
+  b = block_sum(b, sm);
+  if (threadIdx.x == 0) { out2[0] = a; out2[1] = b; }
+}
+
+// Linear_PNP::get_total_charge (linear_pnp.cpp:322-351): fixed_charge + sum_k q_k exp(u_k), nodal
+__global__ void total_charge_kernel(int nv, const double* __restrict__ uu, const double* __restrict__ fixed,
+                                    const double* __restrict__ val, double* __restrict__ out)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  out[v] = fixed[v] + val[1] * exp(uu[3 * (size_t)v + 1]) + val[2] * exp(uu[3 * (size_t)v + 2]);
+}
+
 } // namespace
+
+void error_norms(Handle& h, const double* d_exact, double* l2, double* h1)
+{
+  cudaStream_t s = h.stream;
+  const int nblk = cdiv(h.nc, 256);
+  h.red.alloc(2 * (size_t)nblk + 2, s);
+  error_cells_kernel<<<nblk, 256, 0, s>>>(h.nc, reinterpret_cast<const int4*>(h.cells.p), h.xyz.p, h.uu.p, d_exact, h.red.p + 2);
+  PNP_COUNT_LAUNCH();
+  finalize_sum2_kernel<<<1, 1024, 0, s>>>(nblk, h.red.p + 2, h.red.p); PNP_COUNT_LAUNCH();
+  PNP_CUDA(cudaMemcpyAsync(h.h_red, h.red.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  *l2 = sqrt(h.h_red[0]);
+  *h1 = sqrt(h.h_red[0] + h.h_red[1]);       // Error::compute_h1_error: sqrt(l2^2 + semi_h1^2)
+}
+
+void total_charge(Handle& h, double* d_out)
+{
+  total_charge_kernel<<<cdiv(h.nv, 256), 256, 0, h.stream>>>(h.nv, h.uu.p, h.fixed.p, h.val.p, d_out);
+  PNP_COUNT_LAUNCH();
+}
 
 void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf)
 {

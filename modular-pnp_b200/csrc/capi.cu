@@ -444,6 +444,34 @@ int pnpb200_newton_step(pnpb200_handle* ph, const itsolver_param* it, const AMG_
   });
 }
 
+int pnpb200_error_norms(pnpb200_handle* ph, const double* exact, double* l2_error, double* h1_error)
+{
+  if (!ph || !exact || !l2_error || !h1_error) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    if (h.nv == 0) throw Error(ERROR_INPUT_PAR, "handle has no mesh");
+    const size_t N = 3 * (size_t)h.nv;
+    DevBuf<double> ex; ex.alloc(N, s); ex.upload(exact, N);
+    error_norms(h, ex.p, l2_error, h1_error);
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_total_charge(pnpb200_handle* ph, double* charge)
+{
+  if (!ph || !charge) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    if (!h.have_coef) throw Error(ERROR_INPUT_PAR, "coefficients not set");
+    DevBuf<double> out; out.alloc(h.nv, s);
+    total_charge(h, out.p);
+    out.download(charge, h.nv);
+    return FASP_SUCCESS;
+  });
+}
+
 int pnpb200_get_stats(const pnpb200_handle* ph, pnpb200_stats* st)
 {
   if (!ph || !st) return ERROR_INPUT_PAR;

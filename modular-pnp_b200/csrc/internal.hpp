@@ -172,6 +172,8 @@ void exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t s);
 // ---- assemble.cu
 void assemble_system(Handle& h);                   // J (BSR-T) and rhs
 void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf);
+void error_norms(Handle& h, const double* d_exact, double* l2, double* h1);   // src/error.cpp:58-103
+void total_charge(Handle& h, double* d_out);                                  // linear_pnp.cpp:322-351
 // ---- bsr_ops.cu
 void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s);                  // y = A x
 void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s); // r = b - A x

@@ -113,6 +113,19 @@ public:
     return x;
   }
 
+  // Error::compute_l2_error / compute_h1_error (src/error.cpp:58-103) against a nodal exact solution
+  void compute_error(const std::vector<double>& exact, double& l2_error, double& h1_error)
+  {
+    check(pnpb200_error_norms(_h, exact.data(), &l2_error, &h1_error), "compute_error");
+  }
+  // Linear_PNP::get_total_charge (linear_pnp.cpp:322-351)
+  std::vector<double> get_total_charge()
+  {
+    std::vector<double> q((size_t)_nv);
+    check(pnpb200_total_charge(_h, q.data()), "get_total_charge");
+    return q;
+  }
+
   pnpb200_handle* handle() { return _h; }
 
 private:

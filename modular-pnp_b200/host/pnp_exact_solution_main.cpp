@@ -101,7 +101,10 @@ int main(int argc, char** argv)
   std::vector<double> uu = pnp_problem.get_solution();
   double err = 0.0;
   for (size_t i = 0; i < N; ++i) err = std::fmax(err, std::fabs(uu[i] - exact[i]));
-  printf("\nMeasuring error of computed solution wrt interpolant\n\tmax nodal error: %e\n", err);
+  double l2_error = 0.0, h1_error = 0.0;
+  pnp_problem.compute_error(exact, l2_error, h1_error);     // main.cpp:368-390
+  printf("\nMeasuring error of computed solution wrt interpolant\n\tL2 error: %e\n\tH1 error: %e\n\tmax nodal error: %e\n",
+         l2_error, h1_error, err);
   printf("NEWTON_ITERATIONS %lu CONVERGED %d RELRES %.6e\n", (unsigned long)(newton.iteration - 1), newton.converged() ? 1 : 0,
          newton.relative_residual);
   printf("\nSolver exiting\n");

@@ -289,6 +289,32 @@ void orc_residual(int nv, const double* xyz, int nc, const int* cells, const dou
   if (linf) *linf = m;   // src/pde.cpp:386-390: max(max, -min)
 }
 
+// ---- Error::compute_l2_error / compute_h1_error restated (src/error.cpp:58-103; forms
+// include/L2Error.h, include/SemiH1error.h: int e^2 dx and int |grad e|^2 dx per component) ------
+void orc_error_norms(int nv, const double* xyz, int nc, const int* cells, const double* uu,
+                     const double* exact, double* l2, double* h1)
+{
+  (void)nv;
+  double a = 0.0, b = 0.0;
+  for (int c = 0; c < nc; ++c) {
+    const int* cv = cells + 4 * c;
+    double x12[12], g[4][3], det;
+    for (int r = 0; r < 4; ++r) for (int d = 0; d < 3; ++d) x12[3 * r + d] = xyz[3 * cv[r] + d];
+    tet_geometry(x12, g, &det);
+    for (int k = 0; k < 3; ++k) {
+      double e[4], gr[3] = {0, 0, 0};
+      for (int r = 0; r < 4; ++r) {
+        e[r] = uu[3 * cv[r] + k] - exact[3 * cv[r] + k];
+        for (int d = 0; d < 3; ++d) gr[d] += e[r] * g[r][d];
+      }
+      for (int r = 0; r < 4; ++r) for (int s = 0; s < 4; ++s) a += det * e[r] * e[s] * (r == s ? 1.0 / 60.0 : 1.0 / 120.0);
+      b += det / 6.0 * (gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
+    }
+  }
+  *l2 = std::sqrt(a);
+  *h1 = std::sqrt(a + b);
+}
+
 // ---- fasp_format_dcsr_dbsr restated for nb = 3 [EXT, SURVEY App. B] -------------------------
 void orc_csr_to_bsr3_count(int n, const int* IA, const int* JA, int* bIA)
 {

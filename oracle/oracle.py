@@ -61,6 +61,7 @@ def lib():
         L.orc_residual.argtypes = [C.c_int, _f8, C.c_int, _i4] + [_f8] * 6 + [_u1, _f8,
                                                                              C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_eafe_matrix.argtypes = [C.c_int, _f8, C.c_int, _i4, _i4, _i4, _f8, _f8, _f8, _f8, _f8]
+        L.orc_error_norms.argtypes = [C.c_int, _f8, C.c_int, _i4, _f8, _f8, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_csr_to_bsr3_count.argtypes = [C.c_int, _i4, _i4, _i4]
         L.orc_csr_to_bsr3_fill.argtypes = [C.c_int, _i4, _i4, _f8, _i4, _i4, _f8]
         L.orc_bsr_spmv.argtypes = [C.c_int, _i4, _i4, _f8, C.c_double, _f8, C.c_double, _f8]
@@ -152,6 +153,12 @@ class Problem:
                            self.eps, self.fixed, self.diff, self.val, self.reac, self.bcflag,
                            1 if use_eafe else 0, A, b)
         return A, b
+
+    def error_norms(self, uu, exact=None):
+        a, b = C.c_double(), C.c_double()
+        lib().orc_error_norms(self.nv, self.xyz, self.nc, self.cells, np.ascontiguousarray(uu),
+                              np.ascontiguousarray(self.exact if exact is None else exact), C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def residual(self, uu):
         b = np.zeros(self.N); l2, li = C.c_double(), C.c_double()

@@ -75,6 +75,10 @@ void orc_eafe_matrix(int nv, const double* xyz, int nc, const int* cells,
                      const double* eta, const double* alpha, const double* beta, const double* gamma,
                      double* val /*nnz of vertex pattern*/);
 
+/* L2 / H1 error against a nodal exact solution, src/error.cpp:58-103 */
+void orc_error_norms(int nv, const double* xyz, int nc, const int* cells, const double* uu,
+                     const double* exact, double* l2, double* h1);
+
 /* ---- FASP-restated linear algebra (BSR nb=3) ---- */
 void orc_csr_to_bsr3_count(int n, const int* IA, const int* JA, int* bIA);
 void orc_csr_to_bsr3_fill(int n, const int* IA, const int* JA, const double* val,

@@ -124,3 +124,18 @@ def test_diode_form_variant_parity(oracle, pkg, gpu_lib, use_eafe):
     assert row_scaled_error(IA, val, A_ref) <= 1e-12
     assert np.abs(g.get_rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
     g.close()
+
+
+def test_error_norms_and_total_charge(oracle, pkg, gpu_lib):
+    """L2/H1 error functionals (src/error.cpp:58-103) and the nodal total charge
+    (linear_pnp.cpp:322-351) on the device vs the oracle / numpy."""
+    P = oracle.Problem(12, 5, 4)
+    uu = perturbed_state(P)
+    g = gpu_problem(pkg, P, uu)
+    l2, h1 = g.error_norms(P.exact)
+    l2_ref, h1_ref = P.error_norms(uu)
+    assert abs(l2 - l2_ref) <= 1e-12 * l2_ref and abs(h1 - h1_ref) <= 1e-12 * h1_ref
+    q = g.total_charge()
+    q_ref = P.fixed + P.val[1] * np.exp(uu[1::3]) + P.val[2] * np.exp(uu[2::3])
+    assert np.abs(q - q_ref).max() <= 1e-13 * np.abs(q_ref).max()
+    g.close()

@@ -217,3 +217,21 @@ def test_diode_form_variant_matches_reference_golden(oracle):
             assert _rel(b, g["b_res"][t]) <= 1e-13
     finally:
         oracle.set_form_variant(1.0, False)
+
+
+def test_error_norms_against_closed_form(oracle):
+    """src/error.cpp:58-103 restated: for e = (a.x + c) in every component on the box the L2 / H1
+    norms have closed forms (P1 represents linear functions exactly)."""
+    P = oracle.Problem(6, 3, 3)
+    x, y, z = P.xyz[0::3], P.xyz[1::3], P.xyz[2::3]
+    e = 0.3 * x - 0.2 * y + 0.5 * z + 0.1
+    uu = P.exact.copy()
+    for k in range(3):
+        uu[k::3] += e
+    l2, h1 = P.error_norms(uu)
+    lx, ly, lz = 2.0, 0.4, 0.4
+    vol = lx * ly * lz
+    int_e2 = vol * (0.1 ** 2 + 0.3 ** 2 * lx ** 2 / 12 + 0.2 ** 2 * ly ** 2 / 12 + 0.5 ** 2 * lz ** 2 / 12)
+    semi = vol * (0.3 ** 2 + 0.2 ** 2 + 0.5 ** 2)
+    assert abs(l2 - np.sqrt(3 * int_e2)) <= 1e-12 * l2
+    assert abs(h1 - np.sqrt(3 * int_e2 + 3 * semi)) <= 1e-12 * h1
