@@ -117,6 +117,12 @@ int  pnpb200_total_charge(pnpb200_handle* h, double* charge);
  * behaviour, default), 1 = keep the symbolic hierarchy of the previous solve and only
  * recompute numerical values (Galerkin products, block inverses). */
 int  pnpb200_set_hierarchy_reuse(pnpb200_handle* h, int reuse);
+/* sweep shortcuts: 1 (default) = the cycle exploits the [L | D | U] row storage: forward sweep from
+ * the zero initial guess reads L only, the residual after it U only, and A*z after the last backward
+ * sweep is b + L*(z_new - z_old); 0 = every sweep / residual / matvec reads full rows. Same
+ * arithmetic up to rounding (tests/test_gpu_solver.py), 2.5 instead of 4 matrix passes per
+ * Krylov iteration on every level. */
+int  pnpb200_set_sweep_shortcuts(pnpb200_handle* h, int on);
 
 /* ---- introspection for the parity tests and the byte model of bench.py ---- */
 typedef struct pnpb200_stats {

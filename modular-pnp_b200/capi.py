@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpnpb200.so")
+LIB_PATH = os.environ.get("PNPB200_LIB") or os.path.join(_HERE, "libpnpb200.so")   # PNPB200_LIB: variant builds (development)
 
 INT = C.c_int
 SHORT = C.c_short
@@ -125,6 +125,7 @@ def lib():
     L.pnpb200_newton_step.argtypes = [H, C.POINTER(itsolver_param), C.POINTER(AMG_param), C.POINTER(C.c_int),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pnpb200_set_hierarchy_reuse.argtypes = [H, C.c_int]
+    L.pnpb200_set_sweep_shortcuts.argtypes = [H, C.c_int]
     L.pnpb200_error_norms.argtypes = [H, _f8, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pnpb200_total_charge.argtypes = [H, _f8]
     L.pnpb200_get_stats.argtypes = [H, C.POINTER(pnpb200_stats)]
@@ -355,6 +356,9 @@ class PNP:
 
     def set_hierarchy_reuse(self, on):
         _check(self.L.pnpb200_set_hierarchy_reuse(self.h, 1 if on else 0), "set_hierarchy_reuse")
+
+    def set_sweep_shortcuts(self, on):
+        _check(self.L.pnpb200_set_sweep_shortcuts(self.h, 1 if on else 0), "set_sweep_shortcuts")
 
     def set_timing_detail(self, on):
         _check(self.L.pnpb200_set_timing_detail(self.h, 1 if on else 0), "set_timing_detail")

@@ -23,16 +23,18 @@ namespace {
 typedef unsigned long long u64;
 
 __global__ void condense_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ rs,
-                                const int* __restrict__ brow, const double* __restrict__ val, double* __restrict__ pp)
+                                const int* __restrict__ dslot, const int* __restrict__ brow,
+                                const double* __restrict__ val, double* __restrict__ pp)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nnzb) return;
   const int i = brow[b], s = rs[i], len = ia[i + 1] - ia[i];
-  const double* v = val + 9 * (size_t)s + (b - s);
+  int st;
+  const double* v = val + bsrt_off(s, len, dslot[i] - s, b - s, st);
   double m = 0.0;
 #pragma unroll
   for (int r = 0; r < 3; ++r)
-    m = fmax(m, fabs(v[(size_t)(3 * r) * len]) + fabs(v[(size_t)(3 * r + 1) * len]) + fabs(v[(size_t)(3 * r + 2) * len]));
+    m = fmax(m, fabs(v[(size_t)(3 * r) * st]) + fabs(v[(size_t)(3 * r + 1) * st]) + fabs(v[(size_t)(3 * r + 2) * st]));
   pp[b] = m;
 }
 
@@ -242,21 +244,26 @@ __global__ void rap_structure_kernel(int nnzb, const u64* __restrict__ key, cons
   }
 }
 
-// natural coarse block s (row I) -> physical block crs[I] + (s - cia[I]); its fine segment
-__global__ void rap_remap_kernel(int cnnzb, const int* __restrict__ crow, const int* __restrict__ cia,
-                                 const int* __restrict__ crs, const int* __restrict__ seg,
-                                 int* __restrict__ beg, int* __restrict__ end)
+// natural coarse block s (row I, column cja_nat[s]) -> its physical block in the [L | D | U] row; its fine segment
+__global__ void rap_remap_kernel(int cnnzb, const int* __restrict__ crow, const int* __restrict__ cja_nat,
+                                 const int* __restrict__ cia, const int* __restrict__ crs, const int* __restrict__ cja,
+                                 const int* __restrict__ seg, int* __restrict__ beg, int* __restrict__ end)
 {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= cnnzb) return;
-  const int I = crow[s], b = crs[I] + (s - cia[I]);
+  const int I = crow[s], J = cja_nat[s];
+  int b = crs[I];
+  const int e = b + (cia[I + 1] - cia[I]);
+  while (b < e && cja[b] != J) ++b;
   beg[b] = seg[s]; end[b] = seg[s + 1];
 }
 
 __global__ void rap_numeric_kernel(int cnnzb, const int* __restrict__ cia, const int* __restrict__ crs,
+                                   const int* __restrict__ cdslot,
                                    const int* __restrict__ cbrow, const int* __restrict__ beg,
                                    const int* __restrict__ end, const int* __restrict__ perm,
                                    const int* __restrict__ fia, const int* __restrict__ frs,
+                                   const int* __restrict__ fdslot,
                                    const int* __restrict__ fbrow, const double* __restrict__ fval,
                                    double* __restrict__ cval)
 {
@@ -268,10 +275,14 @@ __global__ void rap_numeric_kernel(int cnnzb, const int* __restrict__ cia, const
     const int b = perm[p];
     if (b < 0) { acc += (t == 0 || t == 4 || t == 8) ? 1.0 : 0.0; continue; }   // identity row of a coarse ghost
     const int i = fbrow[b], fs = frs[i], flen = fia[i + 1] - fia[i];
-    acc += fval[9 * (size_t)fs + (size_t)t * flen + (b - fs)];
+    int st;
+    const size_t o = bsrt_off(fs, flen, fdslot[i] - fs, b - fs, st);
+    acc += fval[o + (size_t)t * st];
   }
   const int I = cbrow[s], cs = crs[I], clen = cia[I + 1] - cia[I];
-  cval[9 * (size_t)cs + (size_t)t * clen + (s - cs)] = acc;
+  int cst;
+  const size_t co = bsrt_off(cs, clen, cdslot[I] - cs, s - cs, cst);
+  cval[co + (size_t)t * cst] = acc;
 }
 
 // ---- grid transfer ---------------------------------------------------------------------------
@@ -455,7 +466,7 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   {
   PHASE("strength");
   pp.p = ws.get<double>(nnzb);
-  condense_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ia.p, A.rs.p, A.brow.p, A.val.p, pp.p); PNP_COUNT_LAUNCH();
+  condense_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ia.p, A.rs.p, A.dslot.p, A.brow.p, A.val.p, pp.p); PNP_COUNT_LAUNCH();
   iso.p = ws.get<unsigned char>(n); strong.p = ws.get<unsigned char>(nnzb);
   isolated_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, pp.p, iso.p); PNP_COUNT_LAUNCH();
   strength_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, A.dslot.p, A.tslot.p, pp.p, iso.p,
@@ -600,7 +611,7 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
     exclusive_scan_int(rowcnt.p, Ac.ia.p, ncoarse + 1, s);
     // colour the coarse graph and store it colour by colour, then re-key the numeric map
     color_and_layout(C, cja_nat.p, &ws, s);
-    rap_remap_kernel<<<cdiv(cnnzb, 256), 256, 0, s>>>(cnnzb, crow.p, Ac.ia.p, Ac.rs.p, seg.p, L.rap_beg.p, L.rap_end.p);
+    rap_remap_kernel<<<cdiv(cnnzb, 256), 256, 0, s>>>(cnnzb, crow.p, cja_nat.p, Ac.ia.p, Ac.rs.p, Ac.ja.p, seg.p, L.rap_beg.p, L.rap_end.p);
     PNP_COUNT_LAUNCH();
   }
   return true;
@@ -610,8 +621,8 @@ void rap_numeric(Handle& h, Level& L, Level& C)
 {
   cudaStream_t s = h.stream;
   BsrT& A = L.A; BsrT& Ac = C.A;
-  rap_numeric_kernel<<<cdiv(9 * (size_t)Ac.nnzb, 256), 256, 0, s>>>(Ac.nnzb, Ac.ia.p, Ac.rs.p, Ac.brow.p, L.rap_beg.p, L.rap_end.p,
-                                                                   L.rap_perm.p, A.ia.p, A.rs.p, A.brow.p, A.val.p, Ac.val.p);
+  rap_numeric_kernel<<<cdiv(9 * (size_t)Ac.nnzb, 256), 256, 0, s>>>(Ac.nnzb, Ac.ia.p, Ac.rs.p, Ac.dslot.p, Ac.brow.p, L.rap_beg.p, L.rap_end.p,
+                                                                   L.rap_perm.p, A.ia.p, A.rs.p, A.dslot.p, A.brow.p, A.val.p, Ac.val.p);
   PNP_COUNT_LAUNCH();
 }
 
@@ -672,7 +683,7 @@ __global__ void gid_kernel(int n_own, int offset, int* __restrict__ gid)
 
 // dense rows of the owned block rows with GLOBAL column ids (row-major, ld = ndg)
 __global__ void dense_fill_rows_kernel(int nnzb, int n_own, int ndg, const int* __restrict__ ia, const int* __restrict__ rs,
-                                       const int* __restrict__ ja, const int* __restrict__ brow, const int* __restrict__ gid,
+                                       const int* __restrict__ dslot, const int* __restrict__ ja, const int* __restrict__ brow, const int* __restrict__ gid,
                                        const double* __restrict__ val, double* __restrict__ D)
 {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -681,7 +692,9 @@ __global__ void dense_fill_rows_kernel(int nnzb, int n_own, int ndg, const int* 
   const int i = brow[b];
   if (i >= n_own) return;
   const int s = rs[i], len = ia[i + 1] - ia[i];
-  D[(size_t)(3 * i + t / 3) * ndg + 3 * gid[ja[b]] + t % 3] = val[9 * (size_t)s + (size_t)t * len + (b - s)];
+  int st;
+  const size_t o = bsrt_off(s, len, dslot[i] - s, b - s, st);
+  D[(size_t)(3 * i + t / 3) * ndg + 3 * gid[ja[b]] + t % 3] = val[o + (size_t)t * st];
 }
 
 // bglob[3*off[r] + q] = ball[r*3*maxown + q], q < 3*cnt[r]
@@ -738,7 +751,7 @@ void setup_coarsest(Handle& h)
   Drow.alloc(rowblk, s); Drow.zero();
   Dall.alloc(rowblk * nr, s);
   if (Z.A.nnzb > 0) {
-    dense_fill_rows_kernel<<<cdiv(9 * (size_t)Z.A.nnzb, 256), 256, 0, s>>>(Z.A.nnzb, own, nd, Z.A.ia.p, Z.A.rs.p, Z.A.ja.p, Z.A.brow.p,
+    dense_fill_rows_kernel<<<cdiv(9 * (size_t)Z.A.nnzb, 256), 256, 0, s>>>(Z.A.nnzb, own, nd, Z.A.ia.p, Z.A.rs.p, Z.A.dslot.p, Z.A.ja.p, Z.A.brow.p,
                                                                           gid.p, Z.A.val.p, Drow.p);
     PNP_COUNT_LAUNCH();
   }
@@ -832,7 +845,12 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
 
 // one multigrid cycle on level l from a zero initial guess: x = B_l b. Multi-GPU: hybrid
 // Gauss-Seidel (ghost values refreshed from their owners before every sweep / residual).
-void mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x)
+// With one pre-smoothing sweep the zero initial guess is exploited: the forward sweep reads only
+// the lower parts of the rows and the residual after it only the upper parts (bsr_ops.cu).
+// If Ax != nullptr (single GPU, >= 1 post-smoothing sweep) the last backward sweep also records
+// delta = x_new - x_old in L.w, and Ax = A x = b + L delta costs half a matrix pass; returns
+// whether Ax was produced.
+bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x, double* Ax)
 {
   cudaStream_t s = h.stream;
   Level& L = *h.hier.lv[l];
@@ -840,17 +858,31 @@ void mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double
   const size_t m = 3 * (size_t)L.A.n;
   const int own = owned_rows(L);
   const bool dist = h.comm.active();
-  vec_set(x, 0.0, m, s);
-  for (int k = 0; k < cfg.presmooth; ++k) { if (dist && k > 0) halo_exchange(h, L.halo, x); mcgs_sweep(L, b, x, false, s); }
-  if (dist) halo_exchange(h, L.halo, x);
-  bsrt_residual(L.A, b, x, L.w.p, s);
+  if (cfg.presmooth == 1 && h.sweep_shortcuts) {
+    if (m > 3 * (size_t)own) PNP_CUDA(cudaMemsetAsync(x + 3 * (size_t)own, 0, (m - 3 * (size_t)own) * sizeof(double), s));
+    mcgs_sweep_from_zero(L, b, x, s);
+    if (dist) halo_exchange(h, L.halo, x);
+    bsrt_residual_after_sweep(L, b, x, L.w.p, s);
+  } else {
+    vec_set(x, 0.0, m, s);
+    for (int k = 0; k < cfg.presmooth; ++k) { if (dist && k > 0) halo_exchange(h, L.halo, x); mcgs_sweep(L, b, x, false, s); }
+    if (dist) halo_exchange(h, L.halo, x);
+    bsrt_residual(L.A, b, x, L.w.p, s);
+  }
   if (L.nagg > 0) {
     restrict_kernel<<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, L.agg_ptr.p, L.agg_rows.p, L.w.p, C.b.p);
     PNP_COUNT_LAUNCH();
   }
   solve_level(h, cfg, l + 1, C.b.p, C.x.p);
   if (own > 0) { prolong_kernel<<<cdiv(3 * (size_t)own, 256), 256, 0, s>>>(own, L.agg.p, C.x.p, x); PNP_COUNT_LAUNCH(); }
-  for (int k = 0; k < cfg.postsmooth; ++k) { if (dist) halo_exchange(h, L.halo, x); mcgs_sweep(L, b, x, true, s); }
+  const bool want_ax = Ax != nullptr && !dist && cfg.postsmooth >= 1 && h.sweep_shortcuts;
+  for (int k = 0; k < cfg.postsmooth; ++k) {
+    if (dist) halo_exchange(h, L.halo, x);
+    if (want_ax && k == cfg.postsmooth - 1) mcgs_sweep_back_delta(L, b, x, L.w.p, s);
+    else mcgs_sweep(L, b, x, true, s);
+  }
+  if (want_ax) bsrt_apply_after_sweep(L, b, L.w.p, Ax, s);
+  return want_ax;
 }
 
 // approximate solve of A_l x = b on a coarse level l >= 1
@@ -861,7 +893,7 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
   Level& L = *h.hier.lv[l];
   if (l == nl - 1) { solve_coarsest(h, b, x); return; }
   const bool kcyc = cfg.cycle_type != V_CYCLE && l <= cfg.kcycle_levels;
-  if (!kcyc) { mg_cycle(h, cfg, l, b, x); return; }
+  if (!kcyc) { mg_cycle(h, cfg, l, b, x, nullptr); return; }
   // K-cycle: two GCR steps preconditioned by the cycle of this level (device scalars only;
   // multi-GPU: the dot products run over the owned rows and are summed with ncclAllReduce)
   const size_t m = 3 * (size_t)L.A.n, mo = 3 * (size_t)owned_rows(L);
@@ -872,15 +904,17 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
   double* c = L.kc.p; double* v = c + m; double* rt = v + m; double* d = rt + m; double* w = d + m;
   double* sc = L.ksc.p; double* partial = sc + 8;
   const int g = small_grid(mo);
-  mg_cycle(h, cfg, l, b, c);
-  if (dist) halo_exchange(h, L.halo, c);
-  bsrt_spmv(L.A, c, v, s);
+  if (!mg_cycle(h, cfg, l, b, c, v)) {
+    if (dist) halo_exchange(h, L.halo, c);
+    bsrt_spmv(L.A, c, v, s);
+  }
   kdots_kernel<2><<<g, 256, 0, s>>>(mo, v, b, v, v, nullptr, nullptr, partial, L.kcnt.p, sc); PNP_COUNT_LAUNCH();
   if (dist) comm_allreduce(h, sc, 2, false);
   kc_step1_kernel<<<g, 256, 0, s>>>(mo, sc, b, v, rt); PNP_COUNT_LAUNCH();
-  mg_cycle(h, cfg, l, rt, d);
-  if (dist) halo_exchange(h, L.halo, d);
-  bsrt_spmv(L.A, d, w, s);
+  if (!mg_cycle(h, cfg, l, rt, d, w)) {
+    if (dist) halo_exchange(h, L.halo, d);
+    bsrt_spmv(L.A, d, w, s);
+  }
   kdots_kernel<3><<<g, 256, 0, s>>>(mo, w, v, w, w, w, rt, partial, L.kcnt.p, sc + 2); PNP_COUNT_LAUNCH();
   if (dist) comm_allreduce(h, sc + 2, 3, false);
   kc_final_kernel<<<g, 256, 0, s>>>(mo, sc, c, d, x); PNP_COUNT_LAUNCH();
@@ -890,7 +924,7 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
 
 // z = M^{-1} r : one multigrid cycle from a zero initial guess (fasp_precond_dbsr_amg [EXT]):
 // V(nu1,nu2), or with AMG_cycle_type != V the K-cycle on the first cfg.kcycle_levels coarse levels
-void amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z)
+bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az)
 {
   cudaStream_t s = h.stream;
   auto& lv = h.hier.lv;
@@ -899,9 +933,9 @@ void amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z)
     Level& Z = *lv[0];
     vec_set(z, 0.0, 3 * (size_t)Z.A.n, s);
     for (int k = 0; k < cfg.presmooth; ++k) mcgs_sweep(Z, r, z, false, s);
-    return;
+    return false;
   }
-  mg_cycle(h, cfg, 0, r, z);
+  return mg_cycle(h, cfg, 0, r, z, Az);
 }
 
 } // namespace pnpb200

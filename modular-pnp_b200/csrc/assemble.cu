@@ -136,7 +136,7 @@ __device__ __forceinline__ double eafe_weight(const double* __restrict__ uu, con
 // edge weights each off-diagonal lane evaluates next to its own.
 template <bool EAFE, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-assemble_blocks_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs, const int* __restrict__ ja,
+assemble_blocks_kernel(int n, const int4* __restrict__ rd, const int* __restrict__ ja,
                        const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
                        const int4* __restrict__ cells, const double* __restrict__ rec,
                        const double* __restrict__ k00, const double* __restrict__ omega,
@@ -147,10 +147,11 @@ assemble_blocks_kernel(int n, const int* __restrict__ ia, const int* __restrict_
   const int lane = threadIdx.x & 15;
   const unsigned hmask = 0xffffu << (threadIdx.x & 16);      // my half-warp
   constexpr int RS = EAFE ? REC_EAFE : REC_FULL;
-  int s = 0, len = 0, c0 = 0, c1 = 0;
+  int s = 0, len = 0, nl = 0, c0 = 0, c1 = 0;
   bool bc0 = false, bc1 = false, bc2 = false;
   if (i < n) {
-    s = rs[i]; len = ia[i + 1] - ia[i]; c0 = v2c_ptr[i]; c1 = v2c_ptr[i + 1];
+    const int4 d = rd[i];
+    s = d.x; len = d.y; nl = d.z; c0 = v2c_ptr[i]; c1 = v2c_ptr[i + 1];
     bc0 = bcflag[3 * (size_t)i] != 0; bc1 = bcflag[3 * (size_t)i + 1] != 0; bc2 = bcflag[3 * (size_t)i + 2] != 0;
   }
   const int npass = (len + 15) >> 4;                          // uniform over the half-warp
@@ -208,9 +209,10 @@ assemble_blocks_kernel(int n, const int* __restrict__ ia, const int* __restrict_
       if (bc0) { a[0] = 0.0; a[1] = 0.0; a[2] = 0.0; }
       if (bc1) { a[3] = 0.0; a[4] = 0.0; a[5] = 0.0; }
       if (bc2) { a[6] = 0.0; a[7] = 0.0; a[8] = 0.0; }
-      double* o = val + 9 * (size_t)s + k;
+      int st;
+      double* o = val + bsrt_off(s, len, nl, k, st);
 #pragma unroll
-      for (int t = 0; t < 9; ++t) o[(size_t)t * len] = a[t];
+      for (int t = 0; t < 9; ++t) o[(size_t)t * st] = a[t];
     }
   }
   if (EAFE) {
@@ -222,9 +224,10 @@ assemble_blocks_kernel(int n, const int* __restrict__ ia, const int* __restrict_
     if (bc0) { diag_a[0] = 1.0; diag_a[1] = 0.0; diag_a[2] = 0.0; }
     if (bc1) { diag_a[3] = 0.0; diag_a[4] = 1.0; diag_a[5] = 0.0; }
     if (bc2) { diag_a[6] = 0.0; diag_a[7] = 0.0; diag_a[8] = 1.0; }
-    double* o = val + 9 * (size_t)s + diag_k;
+    int st;
+    double* o = val + bsrt_off(s, len, nl, diag_k, st);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) o[(size_t)t * len] = diag_a[t];
+    for (int t = 0; t < 9; ++t) o[(size_t)t * st] = diag_a[t];
   }
 }
 
@@ -237,14 +240,19 @@ __global__ void zero_row_fix_kernel(int n, const int* __restrict__ ia, const int
   if (i >= n) return;
   const int s = rs[i], len = ia[i + 1] - ia[i], d = dslot[i];
   if (d < 0) return;
-  double* base = val + 9 * (size_t)s;
+  const int nl = d - s;
+  int std_;
+  double* dg = val + bsrt_off(s, len, nl, nl, std_);
   for (int k = 0; k < 3; ++k) {
-    if (base[(size_t)(3 * k + k) * len + (d - s)] != 0.0) continue;
+    if (dg[(size_t)(3 * k + k) * std_] != 0.0) continue;
     bool nz = false;
-    for (int c = 0; c < 3 && !nz; ++c)
-      for (int p = 0; p < len; ++p)
-        if (base[(size_t)(3 * k + c) * len + p] != 0.0) { nz = true; break; }
-    if (!nz) base[(size_t)(3 * k + k) * len + (d - s)] = 1.0;
+    for (int p = 0; p < len && !nz; ++p) {
+      int st;
+      const double* v = val + bsrt_off(s, len, nl, p, st);
+      for (int c = 0; c < 3; ++c)
+        if (v[(size_t)(3 * k + c) * st] != 0.0) { nz = true; break; }
+    }
+    if (!nz) dg[(size_t)(3 * k + k) * std_] = 1.0;
   }
 }
 
@@ -494,7 +502,7 @@ void assemble_system(Handle& h)
     // 6 CTAs/SM (40 registers, some spills): the gather is latency bound, occupancy beats registers
     // (measured at 256^3: 55 ms at 3 CTAs/SM, 44 at 4, 40 at 6)
     assemble_blocks_kernel<true, 6><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
-        A.n, A.ia.p, A.rs.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
+        A.n, A.rd.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
         h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
     PNP_COUNT_LAUNCH();
   } else {
@@ -502,7 +510,7 @@ void assemble_system(Handle& h)
     PNP_COUNT_LAUNCH();
     mark(2);
     assemble_blocks_kernel<false, 4><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
-        A.n, A.ia.p, A.rs.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
+        A.n, A.rd.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
         h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
     PNP_COUNT_LAUNCH();
   }

@@ -14,53 +14,243 @@ namespace pnpb200 {
 
 namespace {
 
-// One block row per half-warp, lane k = block k of the row.
-//   MODE 0: y = A x          MODE 1: y = b - A x      (rows in natural order; idx = packed
-//           (physical start, length) per row, one 8-byte load)
-//   MODE 2: x_row = D^{-1}(b - sum_{j != row} A_row,j x_j), y == x: one Gauss-Seidel colour.
-//           rows[] = rowid + p0 and idx = pia + p0 are indexed by physical position, so row id,
-//           start and length come from one level of loads.
-// The kernels are latency/occupancy bound (ncu: long-scoreboard stalls, 66-68 % achieved warps):
-// the colour kernel is compiled for 8 resident CTAs per SM (32 registers, no spills; measured
-// 4.7 ms vs 5.3 ms per fine-level sweep at 256^3), the natural-order passes for 6 (they spill at 8).
+// One block row per half-warp, lane k = block k of the row (BSR-T/LDU layout, internal.hpp).
+// rd[] holds one 16-byte descriptor (start, length, nl, row) per row: the natural-order kernels
+// index it by row, the colour kernels get prd + p0 (descriptors in sweep order), so row id, start,
+// length and the L/U split come from ONE load.
+//   M_SPMV   y = A x                     M_RES  y = b - A x             (natural order, full rows)
+//   M_GS     x_row = D^{-1}(b - sum_{j != row} A_row,j x_j), y == x: one Gauss-Seidel colour
+//   M_GS0    the same from a ZERO initial guess, forward sweep: only the lower part contributes
+//            (the upper neighbours are still zero), so only L is read
+//   M_RESU   r = b - A x right after an M_GS0 sweep: the row equation holds with the lower part,
+//            so r_row = -sum_{upper} A_row,j x_j and only U is read (rows >= n_swept, the ghost
+//            rows of a multi-GPU level, take the full row)
+//   M_GSD    M_GS that also writes delta_row = x_new - x_old
+//   M_LDELTA y = A x_new after a BACKWARD M_GSD sweep = b + sum_{lower} A_row,j delta_j: row i was
+//            updated with the new upper and the old lower neighbours, so A x_new differs from b
+//            only by L (x_new - x_old); only L is read (x = delta)
+// One preconditioner application + Krylov matvec therefore reads the fine matrix 2.5 times
+// (L, U, L+D+U, L) instead of 4 times. The kernels are latency/occupancy bound (ncu:
+// long-scoreboard stalls, 66-68 % achieved warps): the colour kernels are compiled for 8 resident
+// CTAs per SM, the natural-order passes for 6.
 // Tried and measured slower: ld.global.cs / L2 evict_first+evict_last hints on the matrix loads
 // (6.3-7.2 ms per sweep), requesting b and D^{-1} before the row's blocks (6.2 vs 5.5 ms: the extra
 // registers cost more occupancy than the overlap gains).
+#ifndef PNPB200_SUM3
+#define PNPB200_SUM3 1
+#endif
+enum { M_SPMV = 0, M_RES = 1, M_GS = 2, M_GS0 = 3, M_RESU = 4, M_GSD = 5, M_LDELTA = 6 };
+
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-bsrt_row_kernel(int nrows, const int* __restrict__ rows, const int* __restrict__ idx,
-                const int* __restrict__ ja, const double* __restrict__ val,
-                const double* __restrict__ dinv, const double* __restrict__ b, const double* x, double* y)
+bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* __restrict__ ja,
+                const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
+                const double* x, double* y, double* dl)
 {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int lane = threadIdx.x & 15;
-  int row = -1, s = 0, len = 0;
-  if (t < nrows) {
-    if (MODE == 2) { row = rows[t]; s = idx[t]; len = idx[t + 1] - s; }
-    else { row = t; const int2 sl = reinterpret_cast<const int2*>(idx)[t]; s = sl.x; len = sl.y; }
-  }
-  const double* v = val + 9 * (size_t)s;
+  int row = -1, s = 0, len = 0, nl = 0;
+  if (t < nrows) { const int4 d = rd[t]; s = d.x; len = d.y; nl = d.z; row = d.w; }
+  int k0 = 0, k1 = len;
+  if (MODE == M_GS0 || MODE == M_LDELTA) k1 = nl;
+  if (MODE == M_RESU && row < n_swept) k0 = nl + 1;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  for (int k = lane; k < len; k += 16) {
-    const int jc = ja[s + k];
-    if (MODE == 2 && jc == row) continue;
-    const size_t j = 3 * (size_t)jc;
+  auto block = [&](int k) {
+    if ((MODE == M_GS || MODE == M_GSD) && k == nl) return;
+#if PNPB200_SPLIT_ROWS
+    // lower part: component stride nl; D + U part (k >= nl) starts 9*nl further: stride len - nl
+    const bool lo = (MODE == M_GS0 || MODE == M_LDELTA) ? true : k < nl;
+    const double* v = val + (9 * (size_t)s + (size_t)(lo ? k : 8 * nl + k));
+    const int st = lo ? nl : len - nl;
+#else
+    const double* v = val + (9 * (size_t)s + (size_t)k);
+    const int st = len;
+#endif
+    const size_t j = 3 * (size_t)ja[s + k];
     const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
-    a0 += v[k] * x0 + v[len + k] * x1 + v[2 * len + k] * x2;
-    a1 += v[3 * len + k] * x0 + v[4 * len + k] * x1 + v[5 * len + k] * x2;
-    a2 += v[6 * len + k] * x0 + v[7 * len + k] * x1 + v[8 * len + k] * x2;
+    a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
+    a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
+    a2 += v[6 * st] * x0 + v[7 * st] * x1 + v[8 * st] * x2;
+  };
+  // the first 16 blocks of the row are peeled out of the loop so that the compiler issues their 13
+  // loads back to back (a rolled loop under the register cap interleaves loads and FMAs and pays
+  // several serial DRAM round trips per row: measured 0.66 vs 0.46 ms for the SpMV at 128^3)
+  int k = k0 + lane;
+  if (k < k1) block(k);
+#pragma unroll 1
+  for (k += 16; k < k1; k += 16) block(k);
+#if PNPB200_SUM3
+  // lane (c, i) = (lane >> 2, lane & 3) of the half-warp holds the row sum of component c
+  const double a = half_sum3(a0, a1, a2, lane);
+  const int c = lane >> 2, i = lane & 3;
+  if (MODE == M_SPMV || MODE == M_RES || MODE == M_RESU || MODE == M_LDELTA) {
+    if (row >= 0 && i == 0 && c < 3) {
+      const size_t o = 3 * (size_t)row + c;
+      if (MODE == M_SPMV) y[o] = a;
+      else if (MODE == M_RES) y[o] = b[o] - a;
+      else if (MODE == M_RESU) y[o] = row < n_swept ? -a : b[o] - a;
+      else y[o] = b[o] + a;
+    }
+  } else {
+    // x_new[i] = sum_c Dinv[i][c] (b_c - a_c): lane (c, i) forms one product, two shuffles add the three c
+    double part = 0.0;
+    if (row >= 0 && c < 3 && i < 3) part = dinv[9 * (size_t)row + 3 * i + c] * (b[3 * (size_t)row + c] - a);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    part += __shfl_xor_sync(0xffffffffu, part, 8);
+    if (row >= 0 && lane < 3) {
+      const size_t o = 3 * (size_t)row + lane;
+      if (MODE == M_GSD) dl[o] = part - x[o];
+      y[o] = part;
+    }
   }
+#else
   a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
   if (row >= 0 && lane < 3) {
     const size_t o = 3 * (size_t)row;
-    if (MODE == 0) y[o + lane] = lane == 0 ? a0 : lane == 1 ? a1 : a2;
-    else if (MODE == 1) y[o + lane] = b[o + lane] - (lane == 0 ? a0 : lane == 1 ? a1 : a2);
+    const double a = lane == 0 ? a0 : lane == 1 ? a1 : a2;
+    if (MODE == M_SPMV) y[o + lane] = a;
+    else if (MODE == M_RES) y[o + lane] = b[o + lane] - a;
+    else if (MODE == M_RESU) y[o + lane] = row < n_swept ? -a : b[o + lane] - a;
+    else if (MODE == M_LDELTA) y[o + lane] = b[o + lane] + a;
     else {
       const double r0 = b[o] - a0, r1 = b[o + 1] - a1, r2 = b[o + 2] - a2;
       const double* d = dinv + 9 * (size_t)row + 3 * lane;
-      y[o + lane] = d[0] * r0 + d[1] * r1 + d[2] * r2;
+      const double xn = d[0] * r0 + d[1] * r1 + d[2] * r2;
+      if (MODE == M_GSD) dl[o + lane] = xn - x[o + lane];
+      y[o + lane] = xn;
     }
   }
+#endif
+}
+
+// Software-pipelined, persistent form of bsrt_row_kernel (same modes, same arithmetic). In the
+// one-row-per-half-warp kernel every row pays a chain of three dependent memory round trips
+// (descriptor -> column indices -> gathered x), so the passes that read only part of a row (L or U)
+// gain little: they are latency bound, not bandwidth bound. Here a half-warp walks rows t, t+H,
+// t+2H, ... (H = half-warps in the grid) and carries the descriptor of the next two rows and the
+// column indices of the next row in registers, so that the matrix values AND the x gather of a row
+// are requested in the same instant and a row costs ONE exposed round trip.
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* __restrict__ ja,
+                     const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
+                     const double* x, double* y, double* dl)
+{
+  const int lane = threadIdx.x & 15;
+  const int H = (gridDim.x * blockDim.x) >> 4;
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int4 none = make_int4(0, 0, 0, -1);
+  // first block index of a row's range in this mode, and one past its last
+  auto range = [&](const int4& d, int& k0, int& k1) {
+    k0 = 0; k1 = d.y;
+    if (MODE == M_GS0 || MODE == M_LDELTA) k1 = d.z;
+    if (MODE == M_RESU && d.w < n_swept) k0 = d.z + 1;
+  };
+  auto first_ja = [&](const int4& d) -> int {
+    int k0, k1; range(d, k0, k1);
+    const int k = k0 + lane;
+    return (d.w >= 0 && k < k1) ? ja[d.x + k] : -1;
+  };
+  int4 d0 = t < nrows ? rd[t] : none;
+  int4 d1 = t + H < nrows ? rd[t + H] : none;
+  int jc0 = first_ja(d0);
+  // the loop bound is uniform over the warp (its two half-warps own rows t and t + 1)
+  for (int tw = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 1; tw < nrows; tw += H) {
+    // requests for the rows after this one
+    const int4 d2 = t + 2 * H < nrows ? rd[t + 2 * H] : none;
+    const int jc1 = first_ja(d1);
+    // this row
+    const int s = d0.x, len = d0.y, nl = d0.z, row = d0.w;
+    int k0, k1; range(d0, k0, k1);
+    const int c = lane >> 2, i = lane & 3;
+    double bq = 0.0, dq = 0.0;          // epilogue operands, requested up front as well
+    if (row >= 0 && c < 3) {
+      if (MODE == M_RES || MODE == M_LDELTA || (MODE == M_RESU && row >= n_swept)) { if (i == 0) bq = b[3 * (size_t)row + c]; }
+      if (MODE == M_GS || MODE == M_GS0 || MODE == M_GSD) { if (i < 3) { bq = b[3 * (size_t)row + c]; dq = dinv[9 * (size_t)row + 3 * i + c]; } }
+    }
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    auto block = [&](int k, int jc) {
+      if ((MODE == M_GS || MODE == M_GSD) && k == nl) return;
+#if PNPB200_SPLIT_ROWS
+      const bool lo = (MODE == M_GS0 || MODE == M_LDELTA) ? true : k < nl;
+      const double* v = val + (9 * (size_t)s + (size_t)(lo ? k : 8 * nl + k));
+      const int st = lo ? nl : len - nl;
+#else
+      const double* v = val + (9 * (size_t)s + (size_t)k);
+      const int st = len;
+#endif
+      const size_t j = 3 * (size_t)jc;
+      const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
+      a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
+      a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
+      a2 += v[6 * st] * x0 + v[7 * st] * x1 + v[8 * st] * x2;
+    };
+    int k = k0 + lane;
+    if (jc0 >= 0) block(k, jc0);
+#pragma unroll 1
+    for (k += 16; k < k1; k += 16) block(k, ja[s + k]);      // rows with more than 16 blocks in range (rare)
+    const double a = half_sum3(a0, a1, a2, lane);
+    if (MODE == M_SPMV || MODE == M_RES || MODE == M_RESU || MODE == M_LDELTA) {
+      if (row >= 0 && i == 0 && c < 3) {
+        const size_t o = 3 * (size_t)row + c;
+        if (MODE == M_SPMV) y[o] = a;
+        else if (MODE == M_RES) y[o] = bq - a;
+        else if (MODE == M_RESU) y[o] = row < n_swept ? -a : bq - a;
+        else y[o] = bq + a;
+      }
+    } else {
+      double part = dq * (bq - a);        // lanes outside (c < 3, i < 3): dq = 0
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      part += __shfl_xor_sync(0xffffffffu, part, 8);
+      if (row >= 0 && lane < 3) {
+        const size_t o = 3 * (size_t)row + lane;
+        if (MODE == M_GSD) dl[o] = part - x[o];
+        y[o] = part;
+      }
+    }
+    d0 = d1; d1 = d2; jc0 = jc1; t += H;
+  }
+}
+
+// launch one pass over nrows rows described by rd[]. Measured at 256^3 (fine level, ms per pass;
+// "plain" = bsrt_row_kernel, "pipe" = bsrt_row_pipe_kernel, n = resident CTAs per SM):
+//   pass            plain(6/8)  pipe(4)  pipe(6, spills)
+//   y = A x           3.39       3.30      3.31
+//   r = b - A x       3.71       3.39      3.39
+//   r = -U x          2.93       2.47      2.57
+//   y = b + L delta   3.18       2.48      2.48
+//   GS sweep          4.53       5.20      6.93        (colour launches: plain kernel, 8 CTAs/SM)
+//   GS sweep, L only  3.73       3.74      4.95
+// so the natural-order passes run pipelined with 64 registers, the colour launches plain with 32.
+#ifndef PNPB200_PIPE
+#define PNPB200_PIPE 1
+#endif
+#ifndef PNPB200_NAT_CTAS
+#define PNPB200_NAT_CTAS 4        // resident CTAs per SM the natural-order passes are compiled for
+#endif
+#ifndef PNPB200_GS_CTAS
+#define PNPB200_GS_CTAS 8         // ... and the colour sweeps
+#endif
+int g_sm_count = 0;
+template <int MODE, int MINB, bool PIPE>
+void launch_rows(int nrows, int n_swept, const int4* rd, const BsrT& A, const double* dinv, const double* b,
+                 const double* x, double* y, double* dl, cudaStream_t s)
+{
+  if (nrows <= 0) return;
+  const int full = cdiv((size_t)nrows * 16, 256);
+  if constexpr (PIPE && PNPB200_PIPE) {
+  // persistent grid = exactly the CTAs that are resident at once (a second wave would walk the
+  // gathered x window a second time: measured 6.5 vs 4.5 ms per Gauss-Seidel sweep)
+  if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
+  static int per_sm = 0;             // one static per (MODE, MINB) instantiation
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bsrt_row_pipe_kernel<MODE, MINB>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = MINB;
+  }
+  const int cap = g_sm_count * per_sm;
+  bsrt_row_pipe_kernel<MODE, MINB><<<full < cap ? full : cap, 256, 0, s>>>(nrows, n_swept, rd, A.ja.p, A.val.p, dinv, b, x, y, dl);
+  } else
+  bsrt_row_kernel<MODE, MINB><<<full, 256, 0, s>>>(nrows, n_swept, rd, A.ja.p, A.val.p, dinv, b, x, y, dl);
+  PNP_COUNT_LAUNCH();
 }
 
 // Small levels (<= SMALL_LEVEL_ROWS rows): the whole multicolour sweep in ONE launch of one CTA,
@@ -68,11 +258,13 @@ bsrt_row_kernel(int nrows, const int* __restrict__ rows, const int* __restrict__
 // K-cycle are visited 8-16 times per Krylov iteration and are pure launch latency). Measured at
 // 256^3: threshold 600 -> -1.3 % Krylov time, threshold 6144 -> +2.5 % (one SM is too slow for a
 // 3.5 k-row level), so only the last one or two levels take this path.
+// mode 0: plain sweep, 1: forward sweep from a zero initial guess (lower parts only),
+// 2: sweep that also writes delta = x_new - x_old.
 constexpr int SMALL_LEVEL_ROWS = 512;
 __global__ void __launch_bounds__(1024, 1)
-mcgs_small_kernel(int ngroups, int reverse, const int* __restrict__ gptr, const int* __restrict__ rowid,
-                  const int* __restrict__ pia, const int* __restrict__ ja, const double* __restrict__ val,
-                  const double* __restrict__ dinv, const double* __restrict__ b, double* x)
+mcgs_small_kernel(int ngroups, int reverse, int mode, const int* __restrict__ gptr, const int4* __restrict__ prd,
+                  const int* __restrict__ ja, const double* __restrict__ val,
+                  const double* __restrict__ dinv, const double* __restrict__ b, double* x, double* dl)
 {
   const int hw = threadIdx.x >> 4, nhw = blockDim.x >> 4, lane = threadIdx.x & 15;
   for (int gg = 0; gg < ngroups; ++gg) {
@@ -80,25 +272,28 @@ mcgs_small_kernel(int ngroups, int reverse, const int* __restrict__ gptr, const 
     const int p0 = gptr[g], p1 = gptr[g + 1];
     for (int base = p0; base < p1; base += nhw) {        // uniform trip count: shuffles stay converged
       const int p = base + hw;
-      int row = -1, s = 0, len = 0;
-      if (p < p1) { row = rowid[p]; s = pia[p]; len = pia[p + 1] - s; }
-      const double* v = val + 9 * (size_t)s;
+      int row = -1, s = 0, len = 0, nl = 0;
+      if (p < p1) { const int4 d = prd[p]; s = d.x; len = d.y; nl = d.z; row = d.w; }
+      const int k1 = mode == 1 ? nl : len;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-      for (int k = lane; k < len; k += 16) {
-        const int jc = ja[s + k];
-        if (jc == row) continue;
-        const size_t j = 3 * (size_t)jc;
+      for (int k = lane; k < k1; k += 16) {
+        if (k == nl) continue;
+        int st;
+        const double* v = val + bsrt_off(s, len, nl, k, st);
+        const size_t j = 3 * (size_t)ja[s + k];
         const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
-        a0 += v[k] * x0 + v[len + k] * x1 + v[2 * len + k] * x2;
-        a1 += v[3 * len + k] * x0 + v[4 * len + k] * x1 + v[5 * len + k] * x2;
-        a2 += v[6 * len + k] * x0 + v[7 * len + k] * x1 + v[8 * len + k] * x2;
+        a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
+        a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
+        a2 += v[6 * st] * x0 + v[7 * st] * x1 + v[8 * st] * x2;
       }
       a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
       if (row >= 0 && lane < 3) {
         const size_t o = 3 * (size_t)row;
         const double r0 = b[o] - a0, r1 = b[o + 1] - a1, r2 = b[o + 2] - a2;
         const double* d = dinv + 9 * (size_t)row + 3 * lane;
-        x[o + lane] = d[0] * r0 + d[1] * r1 + d[2] * r2;
+        const double xn = d[0] * r0 + d[1] * r1 + d[2] * r2;
+        if (mode == 2) dl[o + lane] = xn - x[o + lane];
+        x[o + lane] = xn;
       }
     }
     __syncthreads();
@@ -111,10 +306,12 @@ __global__ void diaginv_kernel(int n, const int* __restrict__ ia, const int* __r
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int s = rs[i], len = ia[i + 1] - ia[i], d = dslot[i] - s;
+  const int s = rs[i], len = ia[i + 1] - ia[i], nl = dslot[i] - s;
+  int st;
+  const double* v = val + bsrt_off(s, len, nl, nl, st);
   double a[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) a[t] = val[9 * (size_t)s + (size_t)t * len + d];
+  for (int t = 0; t < 9; ++t) a[t] = v[(size_t)t * st];
   const double c0 = a[4] * a[8] - a[5] * a[7], c1 = a[5] * a[6] - a[3] * a[8], c2 = a[3] * a[7] - a[4] * a[6];
   const double det = a[0] * c0 + a[1] * c1 + a[2] * c2;
   const double id = 1.0 / det;
@@ -124,53 +321,93 @@ __global__ void diaginv_kernel(int n, const int* __restrict__ ia, const int* __r
   o[6] = c2 * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
 }
 
-// FASP layout (natural block order, row-major 3x3 per block) <-> BSR-T (physical)
+// position of physical block b of row i in the row's NATURAL (column-ascending) order
+__device__ __forceinline__ int natural_pos(const int* __restrict__ ja, int s, int len, int b)
+{
+  const int c = ja[b];
+  int kn = 0;
+  for (int p = s; p < s + len; ++p) kn += ja[p] < c ? 1 : 0;
+  return kn;
+}
+
+// FASP layout (natural block order, row-major 3x3 per block) <-> BSR-T/LDU (physical)
 template <bool TO_T>
 __global__ void relayout_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ rs,
+                                const int* __restrict__ dslot, const int* __restrict__ ja,
                                 const int* __restrict__ brow, const double* __restrict__ in, double* __restrict__ out)
 {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 9 * (size_t)nnzb) return;
   const int b = (int)(e / 9), t = (int)(e % 9);          // b = physical block
   const int i = brow[b], s = rs[i], len = ia[i + 1] - ia[i], k = b - s;
-  const size_t et = 9 * (size_t)s + (size_t)t * len + k;
-  const size_t ef = 9 * ((size_t)ia[i] + k) + t;
+  int st;
+  size_t et = bsrt_off(s, len, dslot[i] - s, k, st);
+  et += (size_t)t * st;
+  const size_t ef = 9 * ((size_t)ia[i] + natural_pos(ja, s, len, b)) + t;
   if (TO_T) out[et] = in[ef]; else out[ef] = in[et];
 }
 
-// natural <-> physical column arrays (row granularity)
-template <bool TO_PHYS>
-__global__ void permute_ja_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
-                                  const int* __restrict__ in, int* __restrict__ out)
+// physical -> natural column array (row granularity)
+__global__ void export_ja_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                                 const int* __restrict__ in, int* __restrict__ out)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int a = ia[i], len = ia[i + 1] - a, s = rs[i];
-  for (int k = 0; k < len; ++k) { if (TO_PHYS) out[s + k] = in[a + k]; else out[a + k] = in[s + k]; }
+  for (int k = 0; k < len; ++k) out[a + natural_pos(in, s, len, s + k)] = in[s + k];
 }
 
-__global__ void row_tables_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
-                                  const int* __restrict__ ja, int* __restrict__ brow, int* __restrict__ dslot)
+// natural -> physical: row i's blocks in the order [L | D | U] given the sweep key of every row
+// (L = columns with a smaller key, i.e. swept before row i in a forward sweep); also the row of
+// each block, the diagonal slot and the two row descriptors
+__global__ void layout_row_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs, const int* __restrict__ key,
+                                  const int* __restrict__ ja_nat, int* __restrict__ ja, int* __restrict__ brow,
+                                  int* __restrict__ dslot, int4* __restrict__ rd, int* __restrict__ err)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int s = rs[i], len = ia[i + 1] - ia[i];
-  int d = -1;
-  for (int p = s; p < s + len; ++p) { brow[p] = i; if (ja[p] == i) d = p; }
-  dslot[i] = d;
+  const int a = ia[i], len = ia[i + 1] - a, s = rs[i], ki = key[i];
+  int w = s;
+  bool hasd = false;
+  for (int k = 0; k < len; ++k) { const int j = ja_nat[a + k]; if (j == i) hasd = true; else if (key[j] < ki) ja[w++] = j; }
+  const int nl = w - s;
+  if (hasd) ja[w++] = i; else *err = 1;
+  for (int k = 0; k < len; ++k) { const int j = ja_nat[a + k]; if (j != i && key[j] >= ki) ja[w++] = j; }
+  for (int p = s; p < s + len; ++p) brow[p] = i;
+  dslot[i] = hasd ? s + nl : -1;
+  rd[i] = make_int4(s, len, nl, i);
+}
+
+__global__ void physical_descriptor_kernel(int n, const int* __restrict__ rowid, const int4* __restrict__ rd,
+                                           int4* __restrict__ prd)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) prd[p] = rd[rowid[p]];
+}
+
+__device__ __forceinline__ int find_sorted(const int* __restrict__ ja, int lo, int hi, int c)   // [lo, hi]
+{
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1, v = ja[mid];
+    if (v == c) return mid;
+    if (v < c) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
 }
 
 __global__ void tslot_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ rs,
-                             const int* __restrict__ ja, const int* __restrict__ brow, int* __restrict__ tslot)
+                             const int* __restrict__ dslot, const int* __restrict__ ja,
+                             const int* __restrict__ brow, int* __restrict__ tslot)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nnzb) return;
   const int i = brow[b], j = ja[b];
-  int lo = rs[j], hi = rs[j] + (ia[j + 1] - ia[j]) - 1, res = -1;
-  while (lo <= hi) {
-    const int mid = (lo + hi) >> 1, c = ja[mid];
-    if (c == i) { res = mid; break; }
-    if (c < i) lo = mid + 1; else hi = mid - 1;
+  const int s = rs[j], e = s + (ia[j + 1] - ia[j]) - 1, d = dslot[j];
+  int res;
+  if (i == j) res = d;
+  else {
+    res = find_sorted(ja, s, d - 1, i);              // lower part of row j
+    if (res < 0) res = find_sorted(ja, d + 1, e, i); // upper part
   }
   tslot[b] = res;
 }
@@ -184,10 +421,10 @@ __global__ void rowlen_by_position_kernel(int n, const int* __restrict__ ia, con
   if (p == n) len[n] = 0;
 }
 __global__ void scatter_rs_kernel(int n, const int* __restrict__ rowid, const int* __restrict__ start,
-                                  int* __restrict__ rs, int2* __restrict__ rsl)
+                                  int* __restrict__ rs)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n) { const int i = rowid[p]; rs[i] = start[p]; rsl[i] = make_int2(start[p], start[p + 1] - start[p]); }
+  if (p < n) rs[rowid[p]] = start[p];
 }
 
 // ---- Jones-Plassmann colouring with hashed priorities (two kernels per round so that the
@@ -275,16 +512,25 @@ __global__ void iota_kernel(int n, int* __restrict__ a)
 
 void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s)
 {
-  bsrt_row_kernel<0, 6><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, nullptr, reinterpret_cast<const int*>(A.rsl.p), A.ja.p, A.val.p,
-                                                                   nullptr, nullptr, x, y);
-  PNP_COUNT_LAUNCH();
+  launch_rows<M_SPMV, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A, nullptr, nullptr, x, y, nullptr, s);
 }
 
 void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s)
 {
-  bsrt_row_kernel<1, 6><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(A.n, nullptr, reinterpret_cast<const int*>(A.rsl.p), A.ja.p, A.val.p,
-                                                                   nullptr, b, x, r);
-  PNP_COUNT_LAUNCH();
+  launch_rows<M_RES, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A, nullptr, b, x, r, nullptr, s);
+}
+
+void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x, double* r, cudaStream_t s)
+{
+  const BsrT& A = L.A;
+  launch_rows<M_RESU, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.rd.p, A, nullptr, b, x, r, nullptr, s);
+}
+
+void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s)
+{
+  const BsrT& A = L.A;
+  if (owned_rows(L) != A.n) throw Error(ERROR_UNKNOWN, "bsrt_apply_after_sweep: single-GPU levels only");
+  launch_rows<M_LDELTA, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A, nullptr, b, delta, y, nullptr, s);
 }
 
 void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s)
@@ -295,28 +541,30 @@ void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s)
 
 void bsrt_from_fasp(const double* d_val_fasp, BsrT& A, cudaStream_t s)
 {
-  relayout_kernel<true><<<cdiv(9 * (size_t)A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.brow.p, d_val_fasp, A.val.p);
+  relayout_kernel<true><<<cdiv(9 * (size_t)A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.dslot.p, A.ja.p, A.brow.p, d_val_fasp, A.val.p);
   PNP_COUNT_LAUNCH();
 }
 
 void bsrt_to_fasp(const BsrT& A, double* d_val_fasp, cudaStream_t s)
 {
-  relayout_kernel<false><<<cdiv(9 * (size_t)A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.brow.p, A.val.p, d_val_fasp);
+  relayout_kernel<false><<<cdiv(9 * (size_t)A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.dslot.p, A.ja.p, A.brow.p, A.val.p, d_val_fasp);
   PNP_COUNT_LAUNCH();
 }
 
 void bsrt_export_ja(const BsrT& A, int* d_ja_nat, cudaStream_t s)
 {
-  permute_ja_kernel<false><<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.rs.p, A.ja.p, d_ja_nat);
+  export_ja_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.rs.p, A.ja.p, d_ja_nat);
   PNP_COUNT_LAUNCH();
 }
 
-void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s)
+namespace {
+// mode 0: plain, 1: forward from a zero initial guess, 2: with delta output
+void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool reverse, int mode, cudaStream_t s)
 {
   const BsrT& A = L.A;
   if (A.n <= SMALL_LEVEL_ROWS && L.ngroups > 0) {
-    mcgs_small_kernel<<<1, 1024, 0, s>>>(L.ngroups, reverse ? 1 : 0, L.d_color_ptr.p, A.rowid.p, A.pia.p, A.ja.p, A.val.p,
-                                        L.dinv.p, b, x);
+    mcgs_small_kernel<<<1, 1024, 0, s>>>(L.ngroups, reverse ? 1 : 0, mode, L.d_color_ptr.p, A.prd.p, A.ja.p, A.val.p,
+                                        L.dinv.p, b, x, dl);
     PNP_COUNT_LAUNCH();
     return;
   }
@@ -324,11 +572,17 @@ void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaSt
     const int c = reverse ? L.ngroups - 1 - cc : cc;
     const int cnt = L.color_ptr[c + 1] - L.color_ptr[c];
     if (cnt == 0) continue;
-    bsrt_row_kernel<2, 8><<<cdiv((size_t)cnt * 16, 256), 256, 0, s>>>(cnt, A.rowid.p + L.color_ptr[c], A.pia.p + L.color_ptr[c],
-                                                                     A.ja.p, A.val.p, L.dinv.p, b, x, x);
-    PNP_COUNT_LAUNCH();
+    const int4* rd = A.prd.p + L.color_ptr[c];
+    if (mode == 1) launch_rows<M_GS0, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, L.dinv.p, b, x, x, nullptr, s);
+    else if (mode == 2) launch_rows<M_GSD, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, L.dinv.p, b, x, x, dl, s);
+    else launch_rows<M_GS, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, L.dinv.p, b, x, x, nullptr, s);
   }
 }
+} // namespace
+
+void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s) { sweep_impl(L, b, x, nullptr, reverse, 0, s); }
+void mcgs_sweep_from_zero(const Level& L, const double* b, double* x, cudaStream_t s) { sweep_impl(L, b, x, nullptr, false, 1, s); }
+void mcgs_sweep_back_delta(const Level& L, const double* b, double* x, double* delta, cudaStream_t s) { sweep_impl(L, b, x, delta, true, 2, s); }
 
 // Colour the natural graph (A.ia, ja_nat), then lay the matrix out colour by colour.
 // `ws` (optional) supplies the temporaries during AMG setup; at create time they come from the pool.
@@ -412,19 +666,26 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
   if (ws) tmp = ws->get<unsigned char>(bytes); else { t_cub.alloc(bytes, s); tmp = t_cub.p; }
   PNP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, color, color_out, rows_in, A.rowid.p, n, 0, key_bits, s));
   PNP_COUNT_LAUNCH();
-  // physical row starts and the physical column array
+  // physical row starts, then the physical column array in [L | D | U] order per row
+  // (color[] still holds the sweep key of every row; ghost rows carry the largest key)
   int* len = geti(t_len, n + 1);
   A.pia.alloc(n + 1, s);
   int* start = A.pia.p;
   rowlen_by_position_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(n, A.ia.p, A.rowid.p, len); PNP_COUNT_LAUNCH();
   exclusive_scan_int(len, start, n + 1, s);
-  A.rs.alloc(n, s); A.rsl.alloc(n, s);
-  scatter_rs_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, start, A.rs.p, A.rsl.p); PNP_COUNT_LAUNCH();
+  A.rs.alloc(n, s); A.rd.alloc(n, s); A.prd.alloc(n, s);
+  scatter_rs_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, start, A.rs.p); PNP_COUNT_LAUNCH();
   A.ja.alloc(A.nnzb, s);
-  permute_ja_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, ja_nat, A.ja.p); PNP_COUNT_LAUNCH();
   A.brow.alloc(A.nnzb, s); A.dslot.alloc(n, s); A.tslot.alloc(A.nnzb, s);
-  row_tables_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, A.brow.p, A.dslot.p); PNP_COUNT_LAUNCH();
-  tslot_kernel<<<cdiv(A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.ja.p, A.brow.p, A.tslot.p); PNP_COUNT_LAUNCH();
+  PNP_CUDA(cudaMemsetAsync(rem, 0, sizeof(int), s));
+  layout_row_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, color, ja_nat, A.ja.p, A.brow.p, A.dslot.p, A.rd.p, rem);
+  PNP_COUNT_LAUNCH();
+  physical_descriptor_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, A.rd.p, A.prd.p); PNP_COUNT_LAUNCH();
+  int nodiag = 0;
+  PNP_CUDA(cudaMemcpyAsync(&nodiag, rem, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  if (nodiag) throw Error(ERROR_DATA_STRUCTURE, "matrix row without a diagonal block");
+  tslot_kernel<<<cdiv(A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.dslot.p, A.ja.p, A.brow.p, A.tslot.p); PNP_COUNT_LAUNCH();
   PNP_LAUNCH_CHECK();
 }
 

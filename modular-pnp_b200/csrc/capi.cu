@@ -304,6 +304,7 @@ int pnpb200_use_eafe(pnpb200_handle* ph, int on) { if (!ph) return ERROR_INPUT_P
 int pnpb200_num_dofs(const pnpb200_handle* ph) { return ph ? 3 * ph->h.hier.lv[0]->A.n : 0; }
 int pnpb200_num_block_rows(const pnpb200_handle* ph) { return ph ? ph->h.hier.lv[0]->A.n : 0; }
 int pnpb200_num_blocks(const pnpb200_handle* ph) { return ph ? ph->h.hier.lv[0]->A.nnzb : 0; }
+int pnpb200_set_sweep_shortcuts(pnpb200_handle* ph, int on) { if (!ph) return ERROR_INPUT_PAR; ph->h.sweep_shortcuts = on ? 1 : 0; return FASP_SUCCESS; }
 int pnpb200_set_hierarchy_reuse(pnpb200_handle* ph, int reuse) { if (!ph) return ERROR_INPUT_PAR; ph->h.reuse_hierarchy = reuse; if (!reuse) ph->h.hier.symbolic_valid = false; return FASP_SUCCESS; }
 int pnpb200_set_timing_detail(pnpb200_handle* ph, int on) { if (!ph) return ERROR_INPUT_PAR; ph->h.timing_detail = on; return FASP_SUCCESS; }
 
@@ -553,14 +554,20 @@ int pnpb200_probe_kernel(pnpb200_handle* ph, int which, int reps, double* ms_per
         case 3: { double out[32]; multi_dot(h, h.kry.V.p, N, 16, y.p, N, out); break; }
         case 4: { assemble_residual(h, h.rhs, nullptr, nullptr); break; }
         case 5: case 6: assemble_system(h); break;
+        case 7: mcgs_sweep_from_zero(L, h.rhs.p, y.p, s); break;
+        case 8: bsrt_residual_after_sweep(L, h.rhs.p, x.p, y.p, s); break;
+        case 9: mcgs_sweep_back_delta(L, h.rhs.p, y.p, x.p, s); break;
+        case 10: bsrt_apply_after_sweep(L, h.rhs.p, x.p, y.p, s); break;
         default: throw Error(ERROR_INPUT_PAR, "unknown probe");
       }
     };
     switch (which) {
       case 0: bytes = b_mat + 2.0 * N * 8.0; break;
       case 1: bytes = b_mat + 3.0 * N * 8.0; break;
-      case 2: if (L.ncolors == 0 || L.dinv.n < 9 * (size_t)A.n) throw Error(ERROR_INPUT_PAR, "probe 2 needs a solve first");
+      case 2: case 7: case 9:
+              if (L.ncolors == 0 || L.dinv.n < 9 * (size_t)A.n) throw Error(ERROR_INPUT_PAR, "probe 2 needs a solve first");
               bytes = b_mat + 3.0 * N * 8.0 + 72.0 * A.n; break;
+      case 8: case 10: bytes = b_mat + 3.0 * N * 8.0; break;
       case 3: if (h.kry.V.n < 17 * N) throw Error(ERROR_INPUT_PAR, "probe 3 needs a solve first");
               bytes = 17.0 * N * 8.0; break;
       case 4: bytes = (double)h.nc * 16.0 + (double)h.nv * 24.0 + N * 8.0 * 2.0 + (double)h.nv * 16.0 + N * 8.0 * 2.0; break;

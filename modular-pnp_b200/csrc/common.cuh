@@ -135,6 +135,23 @@ __device__ __forceinline__ double half_sum(double v)
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// sums of a0, a1, a2 over the 16 lanes of a half-warp with 5 instead of 12 double shuffles (the
+// shuffles share the L1 data pipe with the loads, which ncu shows at 55-75 % in the row kernels):
+// lane L of the half-warp returns the total of a_c, c = (L & 15) >> 2 (c = 3: 0). Every step halves
+// the lanes a value lives on while it doubles the lanes it has been summed over.
+__device__ __forceinline__ double half_sum3(double a0, double a1, double a2, int lane)
+{
+  const bool hi = (lane & 8) != 0;
+  const double r1 = __shfl_xor_sync(0xffffffffu, hi ? a0 : a2, 8);
+  const double r2 = __shfl_xor_sync(0xffffffffu, hi ? a1 : 0.0, 8);
+  const double p = (hi ? a2 : a0) + r1;
+  const double q = hi ? 0.0 : a1 + r2;
+  const bool b2 = (lane & 4) != 0;
+  double v = (b2 ? q : p) + __shfl_xor_sync(0xffffffffu, b2 ? p : q, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
 // block-wide sum, result valid in thread 0 (blockDim.x multiple of 32, <= 1024)
 __device__ __forceinline__ double block_sum(double v, double* smem32)
 {
@@ -159,6 +176,26 @@ __device__ __forceinline__ double block_max(double v, double* smem32)
   v = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.0;
   if (w == 0) v = warp_max(v);
   return v;
+}
+// BSR-T/LDU addressing (internal.hpp): a row that starts at block s with len blocks, of which the
+// first nl are "lower" (their columns are swept before the row), stores the lower part
+// component-major with stride nl and the diagonal + upper part component-major with stride len-nl.
+// Returns the offset of component 0 of block k (k-th block of the row, physical order) and the
+// component stride: component t lives at val[off + t*stride].
+#ifndef PNPB200_SPLIT_ROWS
+#define PNPB200_SPLIT_ROWS 1
+#endif
+__device__ __forceinline__ size_t bsrt_off(int s, int len, int nl, int k, int& stride)
+{
+#if PNPB200_SPLIT_ROWS
+  if (k < nl) { stride = nl; return 9 * (size_t)s + (size_t)k; }
+  stride = len - nl;
+  return 9 * (size_t)s + 9 * (size_t)nl + (size_t)(k - nl);
+#else
+  (void)nl;
+  stride = len;
+  return 9 * (size_t)s + (size_t)k;
+#endif
 }
 __host__ __device__ __forceinline__ unsigned hash32(unsigned x)
 {

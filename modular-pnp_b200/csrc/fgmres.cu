@@ -71,13 +71,14 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
     int i = 0;
     while (i < Restart && iter < MaxIt) {
       ++i; ++iter;
+      bool have_Az = false;      // the cycle's last backward sweep can deliver A z for half a matrix pass
       {
         PhaseTimer t(h, h.stats.ms_vcycle);
         zero_ghost(Vi(i - 1));     // the preconditioner is local to the rank (block Jacobi across GPUs)
-        if (cfg.use_amg) amg_vcycle(h, cfg, Vi(i - 1), Zi(i - 1));
+        if (cfg.use_amg) have_Az = amg_vcycle(h, cfg, Vi(i - 1), Zi(i - 1), Vi(i));
         else vec_copy(Zi(i - 1), Vi(i - 1), n, s);
       }
-      { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, halo, Zi(i - 1)); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
+      if (!have_Az) { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, halo, Zi(i - 1)); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
       double tnorm;
       {
         PhaseTimer t(h, h.stats.ms_ortho);

@@ -6,10 +6,17 @@
 
 namespace pnpb200 {
 
-// BSR(3) matrix on the device in "BSR-T" layout: same IA/JA as FASP's dBSRmat, but inside a
-// block row the 9 block components are stored component-major:
-//     val[9*rs[i] + t*len_i + k]   (t = 3*r + c component, k = block position in the row)
-// so that lane k of a row group loads component t of its block with unit stride.
+// BSR(3) matrix on the device in "BSR-T/LDU" layout. Rows are stored in Gauss-Seidel sweep order
+// (colour by colour). Inside a row the blocks are ordered [L | D | U]: first the nl blocks whose
+// columns are swept BEFORE the row (lower part, columns ascending), then the diagonal block, then
+// the blocks whose columns are swept after it (upper part, columns ascending). Each of the two
+// parts is stored component-major,
+//     lower:  val[9*s + t*nl + k]                    k <  nl
+//     D + U:  val[9*s + 9*nl + t*(len-nl) + (k-nl)]  k >= nl      (t = 3*r + c, s = rs[i])
+// so that lane k of a row group loads component t of its block with unit stride AND the lower /
+// upper part of a row is one contiguous piece of memory: a forward sweep from a zero initial
+// guess streams only L, the residual after it only U, and A*x after a backward sweep is
+// b + L*(x_new - x_old) (bsr_ops.cu). common.cuh: bsrt_off().
 struct BsrT {
   int n = 0;        // block rows
   int nnzb = 0;     // blocks
@@ -18,10 +25,11 @@ struct BsrT {
                         // Gauss-Seidel colour sweep streams one contiguous piece of ja/val
   DevBuf<int> rowid;    // physical row position -> row id (= rows sorted by colour)
   DevBuf<int> pia;      // CSR offsets in PHYSICAL order: row rowid[p] owns blocks [pia[p], pia[p+1])
-  DevBuf<int2> rsl;     // (physical start, length) of row i: one 8-byte load for the natural-order kernels
-  DevBuf<int> ja;       // column of each block, physical order (ascending inside a row)
+  DevBuf<int4> rd;      // row descriptor of row i: (physical start, length, nl, i) — one 16-byte load
+  DevBuf<int4> prd;     // the same descriptors in physical (sweep) order: prd[p] describes row rowid[p]
+  DevBuf<int> ja;       // column of each block, physical order ([L | D | U], ascending inside each part)
   DevBuf<int> brow;     // row of each block
-  DevBuf<int> dslot;    // position (absolute block index) of the diagonal block of each row
+  DevBuf<int> dslot;    // position (absolute block index) of the diagonal block of each row (= rs[i] + nl_i)
   DevBuf<int> tslot;    // block index of the transposed block (j,i), -1 if absent
   DevBuf<double> val;   // 9*nnzb
 };
@@ -141,6 +149,7 @@ struct Handle {
   Hierarchy hier;
   Krylov kry;
   int reuse_hierarchy = 0;
+  int sweep_shortcuts = getenv("PNPB200_NO_SWEEP_SHORTCUTS") ? 0 : 1;   // L-only / U-only / L*delta passes in the cycle
   int timing_detail = 0;
   SolverConfig last_cfg;
   Stats stats;
@@ -182,6 +191,13 @@ void bsrt_from_fasp(const double* d_val_fasp, BsrT& A, cudaStream_t s);
 void bsrt_export_ja(const BsrT& A, int* d_ja_nat, cudaStream_t s);
 void bsrt_to_fasp(const BsrT& A, double* d_val_fasp, cudaStream_t s);
 void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s);
+// forward sweep from a ZERO initial guess (x need not be initialised on the swept rows): lower parts only
+void mcgs_sweep_from_zero(const Level& L, const double* b, double* x, cudaStream_t s);
+// r = b - A x right after mcgs_sweep_from_zero (swept rows: r = -U x; ghost rows: full row)
+void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x, double* r, cudaStream_t s);
+// backward sweep that also returns delta = x_new - x_old, and y = A x_new = b + L delta after it
+void mcgs_sweep_back_delta(const Level& L, const double* b, double* x, double* delta, cudaStream_t s);
+void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s);
 // ---- vecops.cu
 void vec_set(double* x, double v, size_t n, cudaStream_t s);
 void vec_copy(double* dst, const double* src, size_t n, cudaStream_t s);
@@ -203,7 +219,9 @@ inline int owned_rows(const Level& L) { return L.n_own >= 0 ? L.n_own : L.A.n; }
 inline size_t owned_dofs(const Handle& h) { return 3 * (size_t)owned_rows(*h.hier.lv[0]); }
 // ---- amg.cu
 void amg_setup(Handle& h, const SolverConfig& cfg);
-void amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z);
+// z = M^{-1} r. If Az != nullptr and the cycle can deliver it for half a matrix pass (single GPU,
+// at least one post-smoothing sweep), Az = A z is written too and true is returned.
+bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az = nullptr);
 // ---- fgmres.cu
 int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x);
 

@@ -206,3 +206,25 @@ def test_other_fasp_entry_points(oracle, pkg, system):
     xs, st = pkg.capi.fasp_solver_dcsr_krylov(M.indptr, M.indices, M.data, rhs, it2)
     assert st > 0
     assert np.linalg.norm(M @ xs - rhs) <= 1.0001 * it2.tol * np.linalg.norm(rhs)
+
+
+@pytest.mark.parametrize("cycle", [1, 4])
+def test_sweep_shortcuts_are_the_same_arithmetic(oracle, pkg, system, cycle):
+    """[L | D | U] row storage: forward sweep from zero reads L only, the residual after it U only,
+    A*z after the backward sweep = b + L*(z_new - z_old). On/off must agree to rounding: the cycle
+    output, the Krylov iteration count and the Krylov solution."""
+    P, g, IA, JA, val, b = system
+    b0 = g.get_rhs()
+    it, amg = pkg.default_params(cycle_type=cycle)
+    rr = np.random.default_rng(11).uniform(-1, 1, P.N)
+    out = {}
+    for on in (True, False):
+        g.set_sweep_shortcuts(on)
+        its = g.solve(it, amg)
+        out[on] = (its, g.get_update(), g.apply_vcycle(rr))
+    g.set_sweep_shortcuts(True)
+    assert out[True][0] > 0 and out[True][0] == out[False][0]
+    assert np.abs(out[True][2] - out[False][2]).max() <= 1e-12 * np.abs(out[False][2]).max()
+    assert np.abs(out[True][1] - out[False][1]).max() <= 1e-9 * np.abs(out[False][1]).max()
+    r = b0 - oracle.bsr_spmv(IA, JA, val, out[True][1])
+    assert np.linalg.norm(r) <= 1.0001 * it.tol * np.linalg.norm(b0)

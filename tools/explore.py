@@ -30,7 +30,8 @@ def run(n, steps=2, lx=2.0, ly=2.0, lz=2.0, reuse=False, **kw):
               % (k + 1, st, l2 / l2_0, dt, s.ms_assemble, s.ms_setup, s.ms_krylov, s.ms_residual, s.ms_vcycle, s.ms_spmv, s.ms_ortho, s.launches), flush=True)
     s = g.stats()
     print("  levels:", [(s.level_rows[l], s.level_nnzb[l], s.level_colors[l]) for l in range(s.n_levels)])
-    for w, name in [(0, "spmv"), (1, "residual"), (2, "gs_sweep"), (3, "multidot16"), (4, "res_asm"), (5, "jac_asm")]:
+    for w, name in [(0, "spmv"), (1, "residual"), (2, "gs_sweep"), (3, "multidot16"), (4, "res_asm"), (5, "jac_asm"),
+                    (7, "gs0_fwd_L"), (8, "res_U"), (9, "gsd_back"), (10, "apply_Ldelta")]:
         ms, by = g.probe_kernel(w, 5)
         print("  probe %-10s %.3f ms  %.1f GB/s (algorithmic %.2f GB)" % (name, ms, by / ms / 1e6, by / 1e9))
     import torch
