@@ -85,14 +85,22 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def byte_model(stats, nv, nc, krylov_its, restart, kcycle_levels=0):
+def byte_model(stats, nv, nc, krylov_its, restart, kcycle_levels=0, shortcuts=False):
     """Algorithmic bytes of one Newton step, SURVEY.md §8(d), from the run's actual level sizes
-    and iteration count (fp64 = 8 B, int32 = 4 B; every array touched once per logical pass)."""
+    and iteration count (fp64 = 8 B, int32 = 4 B; every array touched once per logical pass).
+    shortcuts=False is the SURVEY model (a cycle = 3 full matrix sweeps per level, a matvec = 1);
+    shortcuts=True counts what the [L | D | U] schedule of this library actually has to read:
+    forward sweep from zero = L, residual after it = U, backward sweep = full row, and the matvec
+    after a cycle = L (2.5 instead of 4 matrix passes per cycle + matvec)."""
     N = 3 * nv
     rows = [stats.level_rows[l] for l in range(stats.n_levels)]
     nnzb = [stats.level_nnzb[l] for l in range(stats.n_levels)]
     b_mat = [nnzb[l] * 76 + (rows[l] + 1) * 4 for l in range(len(rows))]
     b_spmv = [b_mat[l] + 2 * 3 * rows[l] * 8 for l in range(len(rows))]
+    # half-row pass: the off-diagonal blocks split evenly between L and U
+    b_half = [(nnzb[l] - rows[l]) // 2 * 76 + (rows[l] + 1) * 4 + 2 * 3 * rows[l] * 8 for l in range(len(rows))]
+    sweeps3 = [(2 * b_half[l] + b_spmv[l]) if shortcuts else 3 * b_spmv[l] for l in range(len(rows))]
+    matvec = [b_half[l] if shortcuts else b_spmv[l] for l in range(len(rows))]
     b_asm = nc * 16 + nv * 24 + N * 8 + nv * 16 + N * 8 * 2 + nnzb[0] * 72
     b_eafe = 2 * (nnzb[0] * 12 + nv * 24)
     b_res = nc * 16 + nv * 24 + N * 8 * 2 + nv * 16 + N * 8 * 3
@@ -106,14 +114,14 @@ def byte_model(stats, nv, nc, krylov_its, restart, kcycle_levels=0):
         if l >= 1:
             if l <= kcycle_levels:
                 cyc[l] = 2 * cyc[l - 1]
-                b_vc += cyc[l - 1] * (2 * b_spmv[l] + 12 * 3 * rows[l] * 8)
+                b_vc += cyc[l - 1] * (2 * matvec[l] + 12 * 3 * rows[l] * 8)
             else:
                 cyc[l] = cyc[l - 1]
-        b_vc += cyc[l] * (3 * b_spmv[l] + 2 * 3 * (rows[l] + rows[l + 1]) * 8)
+        b_vc += cyc[l] * (sweeps3[l] + 2 * 3 * (rows[l] + rows[l + 1]) * 8)
     b_kry = 0
     for it in range(max(krylov_its, 0)):
         j = it % restart
-        b_kry += b_spmv[0] + b_vc + (2 * (j + 1) + 2) * N * 8
+        b_kry += matvec[0] + b_vc + (2 * (j + 1) + 2) * N * 8
     return b_asm + b_eafe + 2 * b_res + b_setup + b_kry + 4 * N * 8
 
 
@@ -270,7 +278,11 @@ def main():
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
+    if args.profile:                # ncu --profile-from-start off: only the timed step is captured
+        torch.cuda.cudart().cudaProfilerStart()
     ms, launches, its, last = timed(step_resident, K)
+    if args.profile:
+        torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if rank == 0 else None
     if args.profile:
         if rank == 0:
@@ -284,20 +296,29 @@ def main():
     kits = its[-1]
 
     # roofline of the dominant kernel. profiles/README.md (ncu launch list): the multicolour
-    # Gauss-Seidel sweep (bsrt_row_kernel<2>, one launch per colour) is ~2/3 of the device time,
-    # the SpMV/residual pass (bsrt_row_kernel<0/1>) ~1/4. One "launch" of the roofline line = one
-    # full sweep over the fine-level matrix (all colour launches), timed live with CUDA events.
+    # Gauss-Seidel colour launches are the largest share of the device time. One "launch" of the
+    # roofline line = one full backward sweep over the fine-level matrix as the cycle runs it
+    # (bsrt_row_kernel<M_GSD>: all colour launches, also writes delta = x_new - x_old), timed live
+    # with CUDA events on the library's stream. The other passes of a cycle are listed next to it.
     peak, peak_src = peaks()
     spmv_ms, spmv_bytes = g.probe_kernel(0, 20)
-    gs_ms, gs_bytes = g.probe_kernel(2, 10)
+    gs_ms, gs_bytes = g.probe_kernel(9, 10)
+    gs_bytes += 3 * nv * 8                     # the delta vector it writes
+    passes = {}
+    for w, name in [(7, "forward sweep from zero (L only)"), (8, "residual after it (U only)"),
+                    (10, "A*z after the backward sweep (L only)"), (1, "full residual r = b - A x")]:
+        pm, pb = g.probe_kernel(w, 10)
+        passes[name] = {"ms": pm, "full_row_algorithmic_gbs": pb / pm / 1e6}
     achieved = gs_bytes / gs_ms / 1e6
-    b_step = byte_model(stats, nv, nc, kits if kits > 0 else stats.krylov_its, it.restart,
-                        kcycle_levels=(3 if cyc != 1 else 0))
+    klev = 3 if cyc != 1 else 0
+    kk = kits if kits > 0 else stats.krylov_its
+    b_step = byte_model(stats, nv, nc, kk, it.restart, kcycle_levels=klev)
+    b_sched = byte_model(stats, nv, nc, kk, it.restart, kcycle_levels=klev, shortcuts=True)
     step_gbs = b_step / (ms / K) / 1e6
     # traffic: dram bytes of one sweep from the committed ncu capture (only taken at n = 128: ncu
     # cannot save/restore the 100 GB working set of the 256^3 run)
     traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic_n128.json")
+    tp = os.path.join(ROOT, "profiles", "r01_traffic_ldu_n128.json")
     if os.path.exists(tp):
         try:
             with open(tp) as f:
@@ -326,13 +347,16 @@ def main():
                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": n_local_dofs * 8 * world, "d2h_bytes_per_step": n_local_dofs * 8 * world},
                "gpu_launches": launches,
                "clocks": clocks,
-               "roofline": {"bound": "hbm", "kernel": "bsrt_row_kernel<2>: one multicolour Gauss-Seidel sweep of the fine level (%d colour launches)" % stats.level_colors[0],
+               "roofline": {"bound": "hbm", "kernel": "bsrt_row_kernel<M_GSD>: one backward multicolour Gauss-Seidel sweep of the fine level (%d colour launches)" % stats.level_colors[0],
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                             "traffic_note": traffic_note, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": gs_bytes, "ms_per_launch": gs_ms,
-                            "spmv": {"kernel": "bsrt_row_kernel<0> (y = A x, fine level)", "achieved": spmv_bytes / spmv_ms / 1e6,
+                            "other_passes": passes,
+                            "spmv": {"kernel": "bsrt_row_pipe_kernel<M_SPMV> (y = A x, fine level)", "achieved": spmv_bytes / spmv_ms / 1e6,
                                      "frac": spmv_bytes / spmv_ms / 1e6 / peak, "ms": spmv_ms, "algorithmic_bytes": spmv_bytes},
-                            "whole_step": {"algorithmic_bytes": b_step, "achieved": step_gbs, "frac": step_gbs / peak}}}
+                            "whole_step": {"algorithmic_bytes": b_step, "achieved": step_gbs, "frac": step_gbs / peak,
+                                           "note": "algorithmic_bytes = SURVEY 8(d) model (3 full sweeps + 1 matvec per cycle); scheduled_bytes = what the [L|D|U] schedule reads (2.5 passes)",
+                                           "scheduled_bytes": b_sched, "scheduled_frac": b_sched / (ms / K) / 1e6 / peak}}}
         # CPU baseline on the box's host cores (bounded sample), N=1 only
         if world == 1:
             try:

@@ -22,15 +22,14 @@ namespace {
 
 typedef unsigned long long u64;
 
-__global__ void condense_kernel(int nnzb, const int* __restrict__ ia, const int* __restrict__ rs,
-                                const int* __restrict__ dslot, const int* __restrict__ brow,
+__global__ void condense_kernel(int nnzb, const int4* __restrict__ rd, const int* __restrict__ brow,
                                 const double* __restrict__ val, double* __restrict__ pp)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nnzb) return;
-  const int i = brow[b], s = rs[i], len = ia[i + 1] - ia[i];
+  const int4 d = rd[brow[b]];
   int st;
-  const double* v = val + bsrt_off(s, len, dslot[i] - s, b - s, st);
+  const double* v = val + bsrt_off(d.x, d.y, d.z, b - d.x, st);
   double m = 0.0;
 #pragma unroll
   for (int r = 0; r < 3; ++r)
@@ -258,12 +257,9 @@ __global__ void rap_remap_kernel(int cnnzb, const int* __restrict__ crow, const 
   beg[b] = seg[s]; end[b] = seg[s + 1];
 }
 
-__global__ void rap_numeric_kernel(int cnnzb, const int* __restrict__ cia, const int* __restrict__ crs,
-                                   const int* __restrict__ cdslot,
-                                   const int* __restrict__ cbrow, const int* __restrict__ beg,
-                                   const int* __restrict__ end, const int* __restrict__ perm,
-                                   const int* __restrict__ fia, const int* __restrict__ frs,
-                                   const int* __restrict__ fdslot,
+__global__ void rap_numeric_kernel(int cnnzb, const int4* __restrict__ crd, const int* __restrict__ cbrow,
+                                   const int* __restrict__ beg, const int* __restrict__ end,
+                                   const int* __restrict__ perm, const int4* __restrict__ frd,
                                    const int* __restrict__ fbrow, const double* __restrict__ fval,
                                    double* __restrict__ cval)
 {
@@ -274,14 +270,14 @@ __global__ void rap_numeric_kernel(int cnnzb, const int* __restrict__ cia, const
   for (int p = beg[s]; p < end[s]; ++p) {
     const int b = perm[p];
     if (b < 0) { acc += (t == 0 || t == 4 || t == 8) ? 1.0 : 0.0; continue; }   // identity row of a coarse ghost
-    const int i = fbrow[b], fs = frs[i], flen = fia[i + 1] - fia[i];
+    const int4 d = frd[fbrow[b]];                        // (start, length, nl, row) of the fine row
     int st;
-    const size_t o = bsrt_off(fs, flen, fdslot[i] - fs, b - fs, st);
+    const size_t o = bsrt_off(d.x, d.y, d.z, b - d.x, st);
     acc += fval[o + (size_t)t * st];
   }
-  const int I = cbrow[s], cs = crs[I], clen = cia[I + 1] - cia[I];
+  const int4 c = crd[cbrow[s]];
   int cst;
-  const size_t co = bsrt_off(cs, clen, cdslot[I] - cs, s - cs, cst);
+  const size_t co = bsrt_off(c.x, c.y, c.z, s - c.x, cst);
   cval[co + (size_t)t * cst] = acc;
 }
 
@@ -466,7 +462,7 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   {
   PHASE("strength");
   pp.p = ws.get<double>(nnzb);
-  condense_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ia.p, A.rs.p, A.dslot.p, A.brow.p, A.val.p, pp.p); PNP_COUNT_LAUNCH();
+  condense_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.rd.p, A.brow.p, A.val.p, pp.p); PNP_COUNT_LAUNCH();
   iso.p = ws.get<unsigned char>(n); strong.p = ws.get<unsigned char>(nnzb);
   isolated_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, pp.p, iso.p); PNP_COUNT_LAUNCH();
   strength_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, A.dslot.p, A.tslot.p, pp.p, iso.p,
@@ -621,8 +617,8 @@ void rap_numeric(Handle& h, Level& L, Level& C)
 {
   cudaStream_t s = h.stream;
   BsrT& A = L.A; BsrT& Ac = C.A;
-  rap_numeric_kernel<<<cdiv(9 * (size_t)Ac.nnzb, 256), 256, 0, s>>>(Ac.nnzb, Ac.ia.p, Ac.rs.p, Ac.dslot.p, Ac.brow.p, L.rap_beg.p, L.rap_end.p,
-                                                                   L.rap_perm.p, A.ia.p, A.rs.p, A.dslot.p, A.brow.p, A.val.p, Ac.val.p);
+  rap_numeric_kernel<<<cdiv(9 * (size_t)Ac.nnzb, 256), 256, 0, s>>>(Ac.nnzb, Ac.rd.p, Ac.brow.p, L.rap_beg.p, L.rap_end.p,
+                                                                   L.rap_perm.p, A.rd.p, A.brow.p, A.val.p, Ac.val.p);
   PNP_COUNT_LAUNCH();
 }
 

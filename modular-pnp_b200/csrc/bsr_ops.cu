@@ -35,7 +35,8 @@ namespace {
 // CTAs per SM, the natural-order passes for 6.
 // Tried and measured slower: ld.global.cs / L2 evict_first+evict_last hints on the matrix loads
 // (6.3-7.2 ms per sweep), requesting b and D^{-1} before the row's blocks (6.2 vs 5.5 ms: the extra
-// registers cost more occupancy than the overlap gains).
+// registers cost more occupancy than the overlap gains); gathering the 24 bytes of a vertex with one
+// 16-byte + one 8-byte load instead of three 8-byte loads (SpMV 3.78 vs 3.33 ms).
 #ifndef PNPB200_SUM3
 #define PNPB200_SUM3 1
 #endif
@@ -94,7 +95,7 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
   } else {
     // x_new[i] = sum_c Dinv[i][c] (b_c - a_c): lane (c, i) forms one product, two shuffles add the three c
     double part = 0.0;
-    if (row >= 0 && c < 3 && i < 3) part = dinv[9 * (size_t)row + 3 * i + c] * (b[3 * (size_t)row + c] - a);
+    if (row >= 0 && c < 3 && i < 3) part = dinv[9 * (size_t)t + 3 * i + c] * (b[3 * (size_t)row + c] - a);   // dinv: sweep order
     part += __shfl_xor_sync(0xffffffffu, part, 4);
     part += __shfl_xor_sync(0xffffffffu, part, 8);
     if (row >= 0 && lane < 3) {
@@ -114,7 +115,7 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
     else if (MODE == M_LDELTA) y[o + lane] = b[o + lane] + a;
     else {
       const double r0 = b[o] - a0, r1 = b[o + 1] - a1, r2 = b[o + 2] - a2;
-      const double* d = dinv + 9 * (size_t)row + 3 * lane;
+      const double* d = dinv + 9 * (size_t)t + 3 * lane;
       const double xn = d[0] * r0 + d[1] * r1 + d[2] * r2;
       if (MODE == M_GSD) dl[o + lane] = xn - x[o + lane];
       y[o + lane] = xn;
@@ -166,7 +167,7 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
     double bq = 0.0, dq = 0.0;          // epilogue operands, requested up front as well
     if (row >= 0 && c < 3) {
       if (MODE == M_RES || MODE == M_LDELTA || (MODE == M_RESU && row >= n_swept)) { if (i == 0) bq = b[3 * (size_t)row + c]; }
-      if (MODE == M_GS || MODE == M_GS0 || MODE == M_GSD) { if (i < 3) { bq = b[3 * (size_t)row + c]; dq = dinv[9 * (size_t)row + 3 * i + c]; } }
+      if (MODE == M_GS || MODE == M_GS0 || MODE == M_GSD) { if (i < 3) { bq = b[3 * (size_t)row + c]; dq = dinv[9 * (size_t)t + 3 * i + c]; } }
     }
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     auto block = [&](int k, int jc) {
@@ -290,7 +291,7 @@ mcgs_small_kernel(int ngroups, int reverse, int mode, const int* __restrict__ gp
       if (row >= 0 && lane < 3) {
         const size_t o = 3 * (size_t)row;
         const double r0 = b[o] - a0, r1 = b[o + 1] - a1, r2 = b[o + 2] - a2;
-        const double* d = dinv + 9 * (size_t)row + 3 * lane;
+        const double* d = dinv + 9 * (size_t)p + 3 * lane;
         const double xn = d[0] * r0 + d[1] * r1 + d[2] * r2;
         if (mode == 2) dl[o + lane] = xn - x[o + lane];
         x[o + lane] = xn;
@@ -300,22 +301,23 @@ mcgs_small_kernel(int ngroups, int reverse, int mode, const int* __restrict__ gp
   }
 }
 
-__global__ void diaginv_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
-                               const int* __restrict__ dslot, const double* __restrict__ val,
+// inverse of the diagonal blocks, stored in SWEEP order (dinv[9*p..] belongs to row rowid[p]): a
+// colour launch of the smoother reads one contiguous piece of it
+__global__ void diaginv_kernel(int n, const int4* __restrict__ prd, const double* __restrict__ val,
                                double* __restrict__ dinv)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int s = rs[i], len = ia[i + 1] - ia[i], nl = dslot[i] - s;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int4 d = prd[p];
   int st;
-  const double* v = val + bsrt_off(s, len, nl, nl, st);
+  const double* v = val + bsrt_off(d.x, d.y, d.z, d.z, st);
   double a[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) a[t] = v[(size_t)t * st];
   const double c0 = a[4] * a[8] - a[5] * a[7], c1 = a[5] * a[6] - a[3] * a[8], c2 = a[3] * a[7] - a[4] * a[6];
   const double det = a[0] * c0 + a[1] * c1 + a[2] * c2;
   const double id = 1.0 / det;
-  double* o = dinv + 9 * (size_t)i;
+  double* o = dinv + 9 * (size_t)p;
   o[0] = c0 * id; o[1] = (a[2] * a[7] - a[1] * a[8]) * id; o[2] = (a[1] * a[5] - a[2] * a[4]) * id;
   o[3] = c1 * id; o[4] = (a[0] * a[8] - a[2] * a[6]) * id; o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
   o[6] = c2 * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
@@ -535,7 +537,7 @@ void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta
 
 void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s)
 {
-  diaginv_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, A.rs.p, A.dslot.p, A.val.p, dinv);
+  diaginv_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.prd.p, A.val.p, dinv);
   PNP_COUNT_LAUNCH();
 }
 
@@ -573,9 +575,10 @@ void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool rev
     const int cnt = L.color_ptr[c + 1] - L.color_ptr[c];
     if (cnt == 0) continue;
     const int4* rd = A.prd.p + L.color_ptr[c];
-    if (mode == 1) launch_rows<M_GS0, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, L.dinv.p, b, x, x, nullptr, s);
-    else if (mode == 2) launch_rows<M_GSD, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, L.dinv.p, b, x, x, dl, s);
-    else launch_rows<M_GS, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, L.dinv.p, b, x, x, nullptr, s);
+    const double* dinv = L.dinv.p + 9 * (size_t)L.color_ptr[c];      // sweep order: this colour's piece
+    if (mode == 1) launch_rows<M_GS0, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, dinv, b, x, x, nullptr, s);
+    else if (mode == 2) launch_rows<M_GSD, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, dinv, b, x, x, dl, s);
+    else launch_rows<M_GS, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, dinv, b, x, x, nullptr, s);
   }
 }
 } // namespace

@@ -533,13 +533,18 @@ int pnpb200_apply_vcycle(pnpb200_handle* ph, const double* r, double* z)
   });
 }
 
-int pnpb200_probe_kernel(pnpb200_handle* ph, int which, int reps, double* ms_per_launch, double* algorithmic_bytes)
+int pnpb200_probe_kernel(pnpb200_handle* ph, int which_in, int reps, double* ms_per_launch, double* algorithmic_bytes)
 {
   if (!ph || reps < 1) return ERROR_INPUT_PAR;
   return guarded([&]() -> int {
     Handle& h = ph->h; cudaStream_t s = h.stream;
     PNP_CUDA(cudaSetDevice(h.device));
-    Level& L = *h.hier.lv[0];
+    // which + 100 * level: the matrix passes (0, 1, 2, 7..10) of a coarser level of the current hierarchy
+    const int level = which_in / 100, which = which_in % 100;
+    if (level < 0 || level >= (int)h.hier.lv.size()) throw Error(ERROR_INPUT_PAR, "probe level out of range");
+    if (level > 0 && !(which <= 2 || (which >= 7 && which <= 10))) throw Error(ERROR_INPUT_PAR, "coarse-level probes: matrix passes only");
+    Level& L = *h.hier.lv[level];
+    const double* rhs = level == 0 ? h.rhs.p : L.b.p;
     const BsrT& A = L.A;
     const size_t N = 3 * (size_t)A.n;
     DevBuf<double> x, y; x.alloc(N, s); y.alloc(N, s);
@@ -549,15 +554,15 @@ int pnpb200_probe_kernel(pnpb200_handle* ph, int which, int reps, double* ms_per
     auto run = [&](int k) {
       switch (which) {
         case 0: bsrt_spmv(A, x.p, y.p, s); break;
-        case 1: bsrt_residual(A, h.rhs.p, x.p, y.p, s); break;
-        case 2: mcgs_sweep(L, h.rhs.p, y.p, (k & 1) != 0, s); break;
+        case 1: bsrt_residual(A, rhs, x.p, y.p, s); break;
+        case 2: mcgs_sweep(L, rhs, y.p, (k & 1) != 0, s); break;
         case 3: { double out[32]; multi_dot(h, h.kry.V.p, N, 16, y.p, N, out); break; }
         case 4: { assemble_residual(h, h.rhs, nullptr, nullptr); break; }
         case 5: case 6: assemble_system(h); break;
-        case 7: mcgs_sweep_from_zero(L, h.rhs.p, y.p, s); break;
-        case 8: bsrt_residual_after_sweep(L, h.rhs.p, x.p, y.p, s); break;
-        case 9: mcgs_sweep_back_delta(L, h.rhs.p, y.p, x.p, s); break;
-        case 10: bsrt_apply_after_sweep(L, h.rhs.p, x.p, y.p, s); break;
+        case 7: mcgs_sweep_from_zero(L, rhs, y.p, s); break;
+        case 8: bsrt_residual_after_sweep(L, rhs, x.p, y.p, s); break;
+        case 9: mcgs_sweep_back_delta(L, rhs, y.p, x.p, s); break;
+        case 10: bsrt_apply_after_sweep(L, rhs, x.p, y.p, s); break;
         default: throw Error(ERROR_INPUT_PAR, "unknown probe");
       }
     };

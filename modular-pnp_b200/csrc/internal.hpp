@@ -49,7 +49,7 @@ struct Level {
   int n_own = -1;               // owned block rows (first n_own local rows); -1 = all rows (single GPU).
                                 // Ghost rows are identity rows of A; their vector entries come from the owner.
   Halo halo;
-  DevBuf<double> dinv;          // 9*n, AoS: inverse of diagonal blocks
+  DevBuf<double> dinv;          // 9*n, AoS: inverse of the diagonal blocks in SWEEP order (entry p = row A.rowid[p])
   // multicolour ordering
   int ncolors = 0;              // colours of the graph
   int ngroups = 0;              // (tile, colour) groups of one sweep, in order
