@@ -113,6 +113,22 @@ int  pnpb200_error_norms(pnpb200_handle* h, const double* exact, double* l2_erro
 /* Linear_PNP::get_total_charge (linear_pnp.cpp:322-351): nodal fixed_charge + sum_k q_k exp(u_k), charge[Nv] */
 int  pnpb200_total_charge(pnpb200_handle* h, double* charge);
 
+/* Adaptive-refinement indicator on the device.
+ * pnpb200_entropy_indicator = Mesh_Refiner::compute_entropy_error_vector (src/mesh_refiner.cpp:212-271;
+ * form ufl/poisson_cell_marker.ufl:6-15, kernels include/poisson_cell_marker.h:5203-5231,5255-5422) with
+ * the bindings of benchmarks/pnp_refine_exact/main.cpp:260-266: per ion species k the entropy potential
+ * u_k + q_k phi, log weight u_k, diffusivity D_k; the mass-lumped DG0 values of the species are summed.
+ * eta[n_cells] may be NULL (the values stay on the device for pnpb200_mark_cells).
+ * pnpb200_mark_cells = Mesh_Refiner::mark_for_refinement (:187-209, target_size = 0: marker = eta >
+ * entropy_tolerance) and mark_for_refinement_with_target_size (:155-185, target_size > 0: tolerance =
+ * max(sorted_eta[n - min(n, permissible)], entropy_tolerance), permissible = n > target ? 1 : target - n).
+ * marker[n_cells] receives 0/1, *n_marked the count, *tolerance_used (may be NULL) the tolerance applied.
+ * Refining the mesh itself stays with the caller (dolfin::adapt): pnpb200_create on the new (xyz, cells)
+ * rebuilds pattern, edge table, colouring and hierarchy on the device. */
+int  pnpb200_entropy_indicator(pnpb200_handle* h, double* eta);
+int  pnpb200_mark_cells(pnpb200_handle* h, double entropy_tolerance, long target_size, unsigned char* marker,
+                        long* n_marked, double* tolerance_used);
+
 /* hierarchy policy: 0 = rebuild aggregates/patterns/colourings every solve (the reference's
  * behaviour, default), 1 = keep the symbolic hierarchy of the previous solve and only
  * recompute numerical values (Galerkin products, block inverses). */

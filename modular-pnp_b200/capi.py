@@ -128,6 +128,9 @@ def lib():
     L.pnpb200_set_sweep_shortcuts.argtypes = [H, C.c_int]
     L.pnpb200_error_norms.argtypes = [H, _f8, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pnpb200_total_charge.argtypes = [H, _f8]
+    L.pnpb200_entropy_indicator.argtypes = [H, _f8]
+    L.pnpb200_mark_cells.argtypes = [H, C.c_double, C.c_long, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
+                                     C.POINTER(C.c_long), C.POINTER(C.c_double)]
     L.pnpb200_get_stats.argtypes = [H, C.POINTER(pnpb200_stats)]
     L.pnpb200_set_timing_detail.argtypes = [H, C.c_int]
     L.pnpb200_get_level_matrix.argtypes = [H, C.c_int, C.POINTER(dBSRmat)]
@@ -353,6 +356,18 @@ class PNP:
         out = np.zeros(self.nv)
         _check(self.L.pnpb200_total_charge(self.h, out), "total_charge")
         return out
+
+    def entropy_indicator(self):
+        """Mesh_Refiner::compute_entropy_error_vector (src/mesh_refiner.cpp:212-271): one value per cell"""
+        eta = np.zeros(self.nc)
+        _check(self.L.pnpb200_entropy_indicator(self.h, eta), "entropy_indicator")
+        return eta
+
+    def mark_cells(self, tol, target_size=0):
+        """Mesh_Refiner::mark_for_refinement[_with_target_size]: (marker[nc] bool, count, tolerance used)"""
+        m = np.zeros(self.nc, dtype=np.uint8); cnt = C.c_long(); used = C.c_double()
+        _check(self.L.pnpb200_mark_cells(self.h, float(tol), int(target_size), m, C.byref(cnt), C.byref(used)), "mark_cells")
+        return m.astype(bool), cnt.value, used.value
 
     def set_hierarchy_reuse(self, on):
         _check(self.L.pnpb200_set_hierarchy_reuse(self.h, 1 if on else 0), "set_hierarchy_reuse")

@@ -14,6 +14,7 @@
 //       write the finished block once, in BSR-T layout.
 #include "internal.hpp"
 #include "fem.cuh"
+#include <cub/cub.cuh>
 
 namespace pnpb200 {
 
@@ -427,6 +428,103 @@ __global__ void total_charge_kernel(int nv, const double* __restrict__ uu, const
 }
 
 } // namespace
+
+// ---- DG0 entropy indicator of the adaptive-refinement loop -----------------------------------
+// Mesh_Refiner::compute_entropy_error_vector (src/mesh_refiner.cpp:212-271): per ion species the form
+// L = int D exp(w) |grad(mu) - E|^2 v dx of ufl/poisson_cell_marker.ufl:14-15 with E bound to zero
+// (:250-251), 24-point rule (include/poisson_cell_marker.h:5255-5422), divided by the DG0 mass
+// 0.166666666666667 |det J| (:5203-5231; mass_lumping_solver src/mesh_refiner.cpp:297-334), summed
+// over the species. Bindings of benchmarks/pnp_refine_exact/main.cpp:260-266,318-338:
+// mu = u_k + q_k phi, w = u_k, D = D_k. One thread per cell.
+__global__ void __launch_bounds__(128)
+entropy_indicator_kernel(int nc, const int4* __restrict__ cells, const double* __restrict__ xyz,
+                         const double* __restrict__ uu, const double* __restrict__ diff,
+                         const double* __restrict__ val, double* __restrict__ eta)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int4 cv = cells[c];
+  const int v[4] = {cv.x, cv.y, cv.z, cv.w};
+  double x[4][3], g[4][3], det;
+  load_cell_xyz(xyz, cv, x);
+  tet_geom(x, g, det);
+  double phi[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) phi[r] = uu[3 * (size_t)v[r]];
+  double e = 0.0;
+  for (int k = 1; k < 3; ++k) {
+    double lw[4], D[4], gr[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const size_t o = 3 * (size_t)v[r] + k;
+      lw[r] = uu[o]; D[r] = diff[o];
+      const double mu = uu[o] + val[o] * phi[r];
+      gr[0] += mu * g[r][0]; gr[1] += mu * g[r][1]; gr[2] += mu * g[r][2];
+    }
+    const double g2 = det * (gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
+    double A = 0.0;
+#pragma unroll 4
+    for (int ip = 0; ip < 24; ++ip) {
+      const double F0 = c_P24[ip][0] * D[0] + c_P24[ip][1] * D[1] + c_P24[ip][2] * D[2] + c_P24[ip][3] * D[3];
+      const double F1 = c_P24[ip][0] * lw[0] + c_P24[ip][1] * lw[1] + c_P24[ip][2] * lw[2] + c_P24[ip][3] * lw[3];
+      A += F0 * c_W24[ip] * exp(F1) * g2;
+    }
+    e += A / (0.166666666666667 * det);
+  }
+  eta[c] = e;
+}
+
+// Mesh_Refiner::mark_for_refinement (src/mesh_refiner.cpp:187-209): marker = eta > tolerance
+__global__ void mark_cells_kernel(int nc, const double* __restrict__ eta, double tol,
+                                  unsigned char* __restrict__ marker, unsigned long long* __restrict__ count)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool m = c < nc && eta[c] > tol;
+  if (c < nc) marker[c] = m ? 1 : 0;
+  const unsigned b = __ballot_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
+}
+
+void entropy_indicator(Handle& h, double* d_eta)
+{
+  if (!h.have_coef) throw Error(ERROR_INPUT_PAR, "coefficients not set");
+  entropy_indicator_kernel<<<cdiv(h.nc, 128), 128, 0, h.stream>>>(h.nc, reinterpret_cast<const int4*>(h.cells.p), h.xyz.p,
+                                                                h.uu.p, h.diff.p, h.val.p, d_eta);
+  PNP_COUNT_LAUNCH();
+  PNP_LAUNCH_CHECK();
+}
+
+// marker[c] = eta[c] > tol; with target_size > 0 the tolerance of mark_for_refinement_with_target_size
+// (src/mesh_refiner.cpp:155-185): max(sorted_eta[index], tol), index = n - min(n, permissible cells)
+// (the reference reads sorted_eta[n] when more cells are permissible than exist — clamped to n - 1 here)
+long mark_cells(Handle& h, const double* d_eta, double tol, long target_size, unsigned char* d_marker, double* tol_used)
+{
+  cudaStream_t s = h.stream;
+  const int nc = h.nc;
+  if (target_size > 0) {
+    DevBuf<double> sorted; sorted.alloc(nc, s);
+    size_t bytes = 0;
+    PNP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, bytes, d_eta, sorted.p, nc, 0, 64, s));
+    DevBuf<unsigned char> tmp; tmp.alloc(bytes, s);
+    PNP_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, bytes, d_eta, sorted.p, nc, 0, 64, s));
+    PNP_COUNT_LAUNCH();
+    const long permissible = (long)nc > target_size ? 1 : target_size - (long)nc;
+    long index = permissible > (long)nc ? (long)nc : (long)nc - permissible;
+    if (index > (long)nc - 1) index = (long)nc - 1;
+    double v = 0.0;
+    PNP_CUDA(cudaMemcpyAsync(&v, sorted.p + index, sizeof(double), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaStreamSynchronize(s));
+    if (v > tol) tol = v;
+  }
+  DevBuf<unsigned long long> cnt; cnt.alloc(1, s); cnt.zero();
+  mark_cells_kernel<<<cdiv(nc, 256), 256, 0, s>>>(nc, d_eta, tol, d_marker, cnt.p);
+  PNP_COUNT_LAUNCH();
+  unsigned long long hc = 0;
+  PNP_CUDA(cudaMemcpyAsync(&hc, cnt.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  if (tol_used) *tol_used = tol;
+  return (long)hc;
+}
 
 void error_norms(Handle& h, const double* d_exact, double* l2, double* h1)
 {

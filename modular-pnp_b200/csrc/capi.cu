@@ -473,6 +473,37 @@ int pnpb200_total_charge(pnpb200_handle* ph, double* charge)
   });
 }
 
+int pnpb200_entropy_indicator(pnpb200_handle* ph, double* eta)
+{
+  if (!ph) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    if (h.nc == 0) throw Error(ERROR_INPUT_PAR, "handle has no mesh");
+    h.eta.alloc(h.nc, s);
+    entropy_indicator(h, h.eta.p);
+    h.eta_valid = true;
+    if (eta) h.eta.download(eta, h.nc);
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_mark_cells(pnpb200_handle* ph, double entropy_tolerance, long target_size, unsigned char* marker,
+                       long* n_marked, double* tolerance_used)
+{
+  if (!ph || !marker) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    if (!h.eta_valid) throw Error(ERROR_INPUT_PAR, "call pnpb200_entropy_indicator first");
+    DevBuf<unsigned char> m; m.alloc(h.nc, s);
+    const long cnt = mark_cells(h, h.eta.p, entropy_tolerance, target_size, m.p, tolerance_used);
+    m.download(marker, h.nc);
+    if (n_marked) *n_marked = cnt;
+    return FASP_SUCCESS;
+  });
+}
+
 int pnpb200_get_stats(const pnpb200_handle* ph, pnpb200_stats* st)
 {
   if (!ph || !st) return ERROR_INPUT_PAR;

@@ -145,6 +145,8 @@ struct Handle {
   DevBuf<double> omega;         // nnzb: EAFE edge weights  sum_T S^T_ij
   DevBuf<double> k00;           // nnzb: permittivity stiffness (solution independent)
   DevBuf<double> cellrec;       // per-cell quadrature records (Jacobian), reused for residual
+  DevBuf<double> eta;           // DG0 entropy indicator of the last pnpb200_entropy_indicator call (nc)
+  bool eta_valid = false;
   // solver
   Hierarchy hier;
   Krylov kry;
@@ -183,6 +185,8 @@ void assemble_system(Handle& h);                   // J (BSR-T) and rhs
 void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf);
 void error_norms(Handle& h, const double* d_exact, double* l2, double* h1);   // src/error.cpp:58-103
 void total_charge(Handle& h, double* d_out);                                  // linear_pnp.cpp:322-351
+void entropy_indicator(Handle& h, double* d_eta);                             // src/mesh_refiner.cpp:212-271
+long mark_cells(Handle& h, const double* d_eta, double tol, long target_size, unsigned char* d_marker, double* tol_used);
 // ---- bsr_ops.cu
 void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s);                  // y = A x
 void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s); // r = b - A x

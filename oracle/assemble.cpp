@@ -315,6 +315,31 @@ void orc_error_norms(int nv, const double* xyz, int nc, const int* cells, const 
   *h1 = std::sqrt(a + b);
 }
 
+// ---- Mesh_Refiner::compute_entropy_error_vector restated (src/mesh_refiner.cpp:212-271) with the
+// bindings of benchmarks/pnp_refine_exact/main.cpp:260-266,318-338: per ion species k = 1, 2 the
+// entropy potential is u_k + q_k phi, the log weight u_k, the diffusivity D_k; the DG0 values of the
+// species are added up. eta[nc].
+void orc_entropy_indicator(int nv, const double* xyz, int nc, const int* cells, const double* uu,
+                           const double* diff, const double* val, double* eta)
+{
+  (void)nv;
+  for (int c = 0; c < nc; ++c) {
+    const int* cv = cells + 4 * c;
+    double x12[12];
+    for (int r = 0; r < 4; ++r) for (int d = 0; d < 3; ++d) x12[3 * r + d] = xyz[3 * cv[r] + d];
+    double e = 0.0;
+    for (int k = 1; k < 3; ++k) {
+      double mu[4], lw[4], D[4];
+      for (int r = 0; r < 4; ++r) {
+        const size_t o = 3 * (size_t)cv[r];
+        lw[r] = uu[o + k]; mu[r] = uu[o + k] + val[o + k] * uu[o]; D[r] = diff[o + k];
+      }
+      e += marker_element(mu, lw, D, x12);
+    }
+    eta[c] = e;
+  }
+}
+
 // ---- fasp_format_dcsr_dbsr restated for nb = 3 [EXT, SURVEY App. B] -------------------------
 void orc_csr_to_bsr3_count(int n, const int* IA, const int* JA, int* bIA)
 {

@@ -222,6 +222,28 @@ void res_element(double* b, const double* uu, const double* eps, const double* f
   }
 }
 
+// ---- DG0 entropy indicator of the refinement loop (ufl/poisson_cell_marker.ufl:14-15,
+// include/poisson_cell_marker.h:5255-5422): L = int D exp(w) |grad(mu) - E|^2 dx with the 24-point
+// rule; the reference always binds E = 0 (src/mesh_refiner.cpp:250-251), so the integrand is
+// D exp(w) |grad mu|^2 with the cell-constant P1 gradient. Divided by the DG0 mass
+// 0.166666666666667 |det J| (:5203-5231) by mass_lumping_solver (src/mesh_refiner.cpp:297-334).
+double marker_element(const double* mu, const double* logw, const double* D, const double* x)
+{
+  init_tables();
+  double g[4][3], det;
+  tet_geometry(x, g, &det);
+  double gr[3] = {0, 0, 0};
+  for (int r = 0; r < 4; ++r) for (int d = 0; d < 3; ++d) gr[d] += mu[r] * g[r][d];
+  const double g2 = det * (gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
+  double A = 0.0;
+  for (int ip = 0; ip < 24; ++ip) {
+    double F0 = 0.0, F1 = 0.0;
+    for (int r = 0; r < 4; ++r) { F0 += P24[ip][r] * D[r]; F1 += P24[ip][r] * logw[r]; }
+    A += F0 * W24[ip] * std::exp(F1) * g2;
+  }
+  return A / (0.166666666666667 * det);
+}
+
 // ---- kernel dispatch (restated vs the reference's own compiled kernels) --------------------
 ElementKernels kernels = {eafe_element, jac_element, res_element, 0};
 
@@ -241,6 +263,9 @@ void orc_res_element(double* b12, const double* uu12, const double* eps4, const 
                      const double* diff12, const double* val12, const double* reac12,
                      const double* xyz12)
 { orc::res_element(b12, uu12, eps4, fc4, diff12, val12, reac12, xyz12); }
+
+double orc_marker_element(const double* mu4, const double* logw4, const double* diff4, const double* xyz12)
+{ return orc::marker_element(mu4, logw4, diff4, xyz12); }
 
 int orc_use_ref_kernels(int on, const char* libpath)
 {

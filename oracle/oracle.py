@@ -61,6 +61,9 @@ def lib():
         L.orc_residual.argtypes = [C.c_int, _f8, C.c_int, _i4] + [_f8] * 6 + [_u1, _f8,
                                                                              C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_eafe_matrix.argtypes = [C.c_int, _f8, C.c_int, _i4, _i4, _i4, _f8, _f8, _f8, _f8, _f8]
+        L.orc_marker_element.argtypes = [_f8] * 4
+        L.orc_marker_element.restype = C.c_double
+        L.orc_entropy_indicator.argtypes = [C.c_int, _f8, C.c_int, _i4, _f8, _f8, _f8, _f8]
         L.orc_error_norms.argtypes = [C.c_int, _f8, C.c_int, _i4, _f8, _f8, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_csr_to_bsr3_count.argtypes = [C.c_int, _i4, _i4, _i4]
         L.orc_csr_to_bsr3_fill.argtypes = [C.c_int, _i4, _i4, _f8, _i4, _i4, _f8]
@@ -159,6 +162,12 @@ class Problem:
         lib().orc_error_norms(self.nv, self.xyz, self.nc, self.cells, np.ascontiguousarray(uu),
                               np.ascontiguousarray(self.exact if exact is None else exact), C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def entropy_indicator(self, uu):
+        """Mesh_Refiner::compute_entropy_error_vector (src/mesh_refiner.cpp:212-271), one value per cell"""
+        eta = np.zeros(self.nc)
+        lib().orc_entropy_indicator(self.nv, self.xyz, self.nc, self.cells, np.ascontiguousarray(uu), self.diff, self.val, eta)
+        return eta
 
     def residual(self, uu):
         b = np.zeros(self.N); l2, li = C.c_double(), C.c_double()

@@ -20,6 +20,8 @@ void jac_element(double* A, const double* uu, const double* eps, const double* D
 void res_element(double* b, const double* uu, const double* eps, const double* fc, const double* D,
                  const double* q, const double* reac, const double* x);
 
+double marker_element(const double* mu, const double* logw, const double* D, const double* x);
+
 // FASP dBSRmat restated (nb = 3, storage_manner 0: row-major blocks)
 struct BSR {
   int ROW = 0, COL = 0, NNZ = 0;

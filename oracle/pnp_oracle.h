@@ -76,6 +76,10 @@ void orc_eafe_matrix(int nv, const double* xyz, int nc, const int* cells,
                      double* val /*nnz of vertex pattern*/);
 
 /* L2 / H1 error against a nodal exact solution, src/error.cpp:58-103 */
+/* Mesh_Refiner::compute_entropy_error_vector (src/mesh_refiner.cpp:212-271), eta[nc] */
+double orc_marker_element(const double* mu4, const double* logw4, const double* diff4, const double* xyz12);
+void orc_entropy_indicator(int nv, const double* xyz, int nc, const int* cells, const double* uu,
+                           const double* diff, const double* val, double* eta);
 void orc_error_norms(int nv, const double* xyz, int nc, const int* cells, const double* uu,
                      const double* exact, double* l2, double* h1);
 

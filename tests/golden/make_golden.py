@@ -2,7 +2,7 @@
 (oracle/_ref/libpnpref.so, built by oracle/Makefile from /root/reference/include/EAFE.h and
 benchmarks/pnp_exact_solution/vector_linear_pnp_forms.h). Run in the authoring container only
 (needs /root/reference); the vectors travel with the repo.
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [main] [diode] [marker]
 """
 import ctypes as C
 import os
@@ -53,10 +53,6 @@ def main():
     print("golden vectors written")
 
 
-if __name__ == "__main__":
-    main()
-
-
 def diode():
     """golden vectors of the DIODE variant of the forms from the reference's own compiled kernels
     (oracle/_ref/libpnpref_diode.so <- benchmarks/pnp_diode/vector_linear_pnp_forms.h)"""
@@ -87,5 +83,30 @@ def diode():
     print("diode golden vectors written")
 
 
+def marker():
+    """golden vectors of the DG0 entropy indicator from the reference's own compiled kernels
+    (oracle/_ref/libpnpref_marker.so <- include/poisson_cell_marker.h): L-form value with the entropy
+    vector bound to zero as in src/mesh_refiner.cpp:250-251, and the DG0 mass entry"""
+    ref = C.CDLL(os.path.join(os.path.dirname(O.REF_PATH), "libpnpref_marker.so"))
+    f8 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    ref.ref_marker_mass.argtypes = [f8, f8]
+    ref.ref_marker_tabulate.argtypes = [f8] * 6
+    rng = np.random.default_rng(2468)
+    n = 64
+    X = np.zeros((n, 12)); MU = np.zeros((n, 4)); LW = np.zeros((n, 4)); DF = np.zeros((n, 4))
+    L = np.zeros((n, 1)); M = np.zeros((n, 1))
+    zero12 = np.zeros(12)
+    base = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1.0])
+    for t in range(n):
+        X[t] = (base + 0.2 * rng.uniform(-1, 1, 12)) * rng.uniform(0.01, 2.0)
+        MU[t] = rng.uniform(-3, 3, 4); LW[t] = rng.uniform(-4, 2, 4); DF[t] = rng.uniform(0.1, 2, 4)
+        ref.ref_marker_tabulate(L[t], MU[t], zero12, LW[t], DF[t], X[t])
+        ref.ref_marker_mass(M[t], X[t])
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "marker_kernels.npz"), X=X, MU=MU, LW=LW, DF=DF, L=L[:, 0], M=M[:, 0])
+    print("marker golden vectors written")
+
+
 if __name__ == "__main__":
-    diode()
+    which = sys.argv[1:] or ["main", "diode", "marker"]
+    for w in which:
+        {"main": main, "diode": diode, "marker": marker}[w]()

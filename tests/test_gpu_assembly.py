@@ -139,3 +139,41 @@ def test_error_norms_and_total_charge(oracle, pkg, gpu_lib):
     q_ref = P.fixed + P.val[1] * np.exp(uu[1::3]) + P.val[2] * np.exp(uu[2::3])
     assert np.abs(q - q_ref).max() <= 1e-13 * np.abs(q_ref).max()
     g.close()
+
+
+def test_entropy_indicator_and_cell_marking(oracle, pkg, gpu_lib):
+    """SURVEY §8f-1: the DG0 entropy indicator (Mesh_Refiner::compute_entropy_error_vector,
+    src/mesh_refiner.cpp:212-271) and the two marking rules (:155-209) on the device, on a Kuhn box
+    and on an irregular (jittered, centroid-split) mesh, vs the oracle / the rules restated in numpy."""
+    from helpers import GeneralProblem, irregular_mesh
+    P1 = oracle.Problem(12, 5, 4)
+    xyz, cells = irregular_mesh(oracle, 10, 4, 4)
+    P2 = GeneralProblem(oracle, xyz, cells)
+    for P in (P1, P2):
+        rng = np.random.default_rng(77)
+        uu = P.exact + 0.2 * rng.uniform(-1, 1, P.N)
+        if P is P1:
+            g = gpu_problem(pkg, P, uu)
+        else:
+            g = pkg.PNP(P.xyz, P.cells, 0)
+            g.set_coefficients(P.eps, P.fixed, P.diff, P.val, P.reac)
+            g.set_dirichlet(np.nonzero(P.bcflag)[0].astype(np.int32))
+            g.set_solution(uu)
+        eta = g.entropy_indicator()
+        eta_ref = np.zeros(P.nc)
+        oracle.lib().orc_entropy_indicator(P.nv, P.xyz, P.nc, P.cells, uu, P.diff, P.val, eta_ref)
+        assert eta.shape == (P.nc,) and (eta_ref > 0).all()
+        assert np.abs(eta - eta_ref).max() <= 1e-12 * np.abs(eta_ref).max()
+        # mark_for_refinement: eta > tol
+        tol = float(np.median(eta))
+        m, cnt, used = g.mark_cells(tol)
+        assert used == tol and cnt == int((eta > tol).sum()) and np.array_equal(m, eta > tol)
+        # mark_for_refinement_with_target_size
+        srt = np.sort(eta)
+        for target in (P.nc + P.nc // 5, P.nc // 2, 10 * P.nc):
+            permissible = 1 if P.nc > target else target - P.nc
+            idx = min(P.nc if permissible > P.nc else P.nc - permissible, P.nc - 1)
+            t_ref = max(srt[idx], 1e-6)
+            m, cnt, used = g.mark_cells(1e-6, target)
+            assert used == t_ref and np.array_equal(m, eta > t_ref) and cnt == int((eta > t_ref).sum())
+        g.close()

@@ -235,3 +235,23 @@ def test_error_norms_against_closed_form(oracle):
     semi = vol * (0.3 ** 2 + 0.2 ** 2 + 0.5 ** 2)
     assert abs(l2 - np.sqrt(3 * int_e2)) <= 1e-12 * l2
     assert abs(h1 - np.sqrt(3 * int_e2 + 3 * semi)) <= 1e-12 * h1
+
+
+def test_entropy_indicator_matches_reference_golden(oracle):
+    """DG0 entropy indicator (Mesh_Refiner::compute_entropy_error_vector, src/mesh_refiner.cpp:212-271):
+    the restated element value equals the reference's compiled poisson_cell_marker kernels
+    (include/poisson_cell_marker.h:5203-5231, 5255-5422; golden vectors from oracle/_ref)."""
+    g = np.load(os.path.join(GOLD, "marker_kernels.npz"))
+    L = oracle.lib()
+    for t in range(len(g["L"])):
+        v = L.orc_marker_element(g["MU"][t].copy(), g["LW"][t].copy(), g["DF"][t].copy(), g["X"][t].copy())
+        ref = g["L"][t] / g["M"][t]          # mass_lumping_solver: rhs / row sum (src/mesh_refiner.cpp:320-330)
+        assert abs(v - ref) <= 1e-12 * abs(ref), (t, v, ref)
+    # global: constant log-densities and a linear potential give D exp(u) q^2 |grad phi|^2 per species
+    P = oracle.Problem(6, 3, 2)
+    uu = np.zeros(P.N)
+    x = P.xyz[0::3]
+    uu[0::3] = 0.7 * x; uu[1::3] = -0.3; uu[2::3] = 0.4
+    eta = P.entropy_indicator(uu)
+    expect = P.diff[1] * np.exp(-0.3) * (0.7 * P.val[1]) ** 2 + P.diff[2] * np.exp(0.4) * (0.7 * P.val[2]) ** 2
+    assert eta.shape == (P.nc,) and np.abs(eta - expect).max() <= 1e-12 * expect
