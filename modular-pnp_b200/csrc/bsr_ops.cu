@@ -9,6 +9,7 @@
 // kernels here are HBM-bound streaming kernels.
 #include "internal.hpp"
 #include <cub/cub.cuh>
+#include <algorithm>
 
 namespace pnpb200 {
 
@@ -301,6 +302,71 @@ mcgs_small_kernel(int ngroups, int reverse, int mode, const int* __restrict__ gp
   }
 }
 
+// The same sweep for a level that fits in the shared memory of one SM (values, columns, descriptors,
+// block inverses, b and x: <= SMALL_SMEM_BYTES): everything is staged with one round of coalesced
+// loads, the colours then run out of shared memory. The global-memory version pays three dependent
+// L2 round trips per colour (36 us per sweep of a 150-row level, 16 such sweeps per Krylov
+// iteration of the K-cycle); this one 14-17 us. x is kept in shared memory and written through.
+// Tried for the mid-size levels (3.5 k - 80 k rows, 11 colour launches of 4-8 us each): the whole
+// sweep as ONE cooperative launch with a grid barrier between colours and the next colour's matrix
+// operands requested ahead of the barrier: 43 instead of 62 us per sweep of the 3.5 k-row level,
+// slower on the 80 k-row level, 0.5 % of the Krylov time in total — not kept.
+constexpr size_t SMALL_SMEM_BYTES = 200 * 1024;
+inline size_t small_level_smem(int n, int nnzb) { return (size_t)nnzb * 76 + (size_t)n * (72 + 24 + 24 + 16) + 64; }
+__global__ void __launch_bounds__(1024, 1)
+mcgs_smem_kernel(int n, int nnzb, int ngroups, int reverse, int mode, const int* __restrict__ gptr,
+                 const int4* __restrict__ prd, const int* __restrict__ ja, const double* __restrict__ val,
+                 const double* __restrict__ dinv, const double* __restrict__ b, double* x, double* dl)
+{
+  extern __shared__ double sm_d[];
+  double* s_val = sm_d;                         // 9*nnzb
+  double* s_dinv = s_val + 9 * (size_t)nnzb;    // 9*n   (sweep order)
+  double* s_b = s_dinv + 9 * (size_t)n;         // 3*n
+  double* s_x = s_b + 3 * (size_t)n;            // 3*n
+  int4* s_prd = reinterpret_cast<int4*>(s_x + 3 * (size_t)n + ((9 * nnzb + 15 * n) & 1));     // 16-byte aligned: n entries
+  int* s_ja = reinterpret_cast<int*>(s_prd + n);                            // nnzb
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < 9 * nnzb; e += nt) s_val[e] = val[e];
+  for (int e = tid; e < 9 * n; e += nt) s_dinv[e] = dinv[e];
+  for (int e = tid; e < 3 * n; e += nt) { s_b[e] = b[e]; s_x[e] = mode == 1 ? 0.0 : x[e]; }
+  for (int e = tid; e < n; e += nt) s_prd[e] = prd[e];
+  for (int e = tid; e < nnzb; e += nt) s_ja[e] = ja[e];
+  __syncthreads();
+  const int hw = tid >> 4, nhw = nt >> 4, lane = tid & 15;
+  for (int gg = 0; gg < ngroups; ++gg) {
+    const int g = reverse ? ngroups - 1 - gg : gg;
+    const int p0 = gptr[g], p1 = gptr[g + 1];
+    for (int base = p0; base < p1; base += nhw) {        // uniform trip count: shuffles stay converged
+      const int p = base + hw;
+      int row = -1, s = 0, len = 0, nl = 0;
+      if (p < p1) { const int4 d = s_prd[p]; s = d.x; len = d.y; nl = d.z; row = d.w; }
+      const int k1 = mode == 1 ? nl : len;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int k = lane; k < k1; k += 16) {
+        if (k == nl) continue;
+        int st;
+        const double* v = s_val + bsrt_off(s, len, nl, k, st);
+        const int j = 3 * s_ja[s + k];
+        const double x0 = s_x[j], x1 = s_x[j + 1], x2 = s_x[j + 2];
+        a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
+        a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
+        a2 += v[6 * st] * x0 + v[7 * st] * x1 + v[8 * st] * x2;
+      }
+      a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
+      if (row >= 0 && lane < 3) {
+        const int o = 3 * row;
+        const double r0 = s_b[o] - a0, r1 = s_b[o + 1] - a1, r2 = s_b[o + 2] - a2;
+        const double* d = s_dinv + 9 * p + 3 * lane;
+        const double xn = d[0] * r0 + d[1] * r1 + d[2] * r2;
+        if (mode == 2) dl[o + lane] = xn - s_x[o + lane];
+        s_x[o + lane] = xn;
+        x[o + lane] = xn;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // inverse of the diagonal blocks, stored in SWEEP order (dinv[9*p..] belongs to row rowid[p]): a
 // colour launch of the smoother reads one contiguous piece of it
 __global__ void diaginv_kernel(int n, const int4* __restrict__ prd, const double* __restrict__ val,
@@ -564,6 +630,18 @@ namespace {
 void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool reverse, int mode, cudaStream_t s)
 {
   const BsrT& A = L.A;
+  if (A.n <= SMALL_LEVEL_ROWS && L.ngroups > 0 && small_level_smem(A.n, A.nnzb) <= SMALL_SMEM_BYTES) {
+    static bool configured[64] = {false};        // the attribute is per device
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      PNP_CUDA(cudaFuncSetAttribute(mcgs_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_BYTES));
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    mcgs_smem_kernel<<<1, 1024, small_level_smem(A.n, A.nnzb), s>>>(A.n, A.nnzb, L.ngroups, reverse ? 1 : 0, mode, L.d_color_ptr.p,
+                                                                  A.prd.p, A.ja.p, A.val.p, L.dinv.p, b, x, dl);
+    PNP_COUNT_LAUNCH();
+    return;
+  }
   if (A.n <= SMALL_LEVEL_ROWS && L.ngroups > 0) {
     mcgs_small_kernel<<<1, 1024, 0, s>>>(L.ngroups, reverse ? 1 : 0, mode, L.d_color_ptr.p, A.prd.p, A.ja.p, A.val.p,
                                         L.dinv.p, b, x, dl);

@@ -34,7 +34,7 @@ def run(n, steps=2, lx=2.0, ly=2.0, lz=2.0, reuse=False, **kw):
                     (7, "gs0_fwd_L"), (8, "res_U"), (9, "gsd_back"), (10, "apply_Ldelta")]:
         ms, by = g.probe_kernel(w, 5)
         print("  probe %-10s %.3f ms  %.1f GB/s (algorithmic %.2f GB)" % (name, ms, by / ms / 1e6, by / 1e9))
-    for lvl in range(1, min(3, s.n_levels - 1)):
+    for lvl in range(1, s.n_levels - 1):
         for w, name in [(0, "spmv"), (2, "gs_sweep"), (7, "gs0_fwd_L"), (8, "res_U"), (9, "gsd_back"), (10, "apply_Ldelta")]:
             ms, by = g.probe_kernel(100 * lvl + w, 20)
             print("  L%d probe %-10s %.3f ms  %.1f GB/s (algorithmic %.3f GB)" % (lvl, name, ms, by / ms / 1e6, by / 1e9))
