@@ -843,7 +843,7 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
 // Gauss-Seidel (ghost values refreshed from their owners before every sweep / residual).
 // With one pre-smoothing sweep the zero initial guess is exploited: the forward sweep reads only
 // the lower parts of the rows and the residual after it only the upper parts (bsr_ops.cu).
-// If Ax != nullptr (single GPU, >= 1 post-smoothing sweep) the last backward sweep also records
+// If Ax != nullptr (>= 1 post-smoothing sweep) the last backward sweep also records
 // delta = x_new - x_old in L.w, and Ax = A x = b + L delta costs half a matrix pass; returns
 // whether Ax was produced.
 bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x, double* Ax)
@@ -871,13 +871,18 @@ bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double
   }
   solve_level(h, cfg, l + 1, C.b.p, C.x.p);
   if (own > 0) { prolong_kernel<<<cdiv(3 * (size_t)own, 256), 256, 0, s>>>(own, L.agg.p, C.x.p, x); PNP_COUNT_LAUNCH(); }
-  const bool want_ax = Ax != nullptr && !dist && cfg.postsmooth >= 1 && h.sweep_shortcuts;
+  const bool want_ax = Ax != nullptr && cfg.postsmooth >= 1 && h.sweep_shortcuts;
   for (int k = 0; k < cfg.postsmooth; ++k) {
     if (dist) halo_exchange(h, L.halo, x);
     if (want_ax && k == cfg.postsmooth - 1) mcgs_sweep_back_delta(L, b, x, L.w.p, s);
     else mcgs_sweep(L, b, x, true, s);
   }
-  if (want_ax) bsrt_apply_after_sweep(L, b, L.w.p, Ax, s);
+  if (want_ax) {
+    // multi-GPU (hybrid GS): the ghost columns kept their pre-sweep value, so their delta — the
+    // owners' delta, one halo exchange — enters the product as well
+    if (dist) halo_exchange(h, L.halo, L.w.p);
+    bsrt_apply_after_sweep(L, b, L.w.p, Ax, s);
+  }
   return want_ax;
 }
 

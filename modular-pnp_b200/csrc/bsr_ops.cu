@@ -30,6 +30,11 @@ namespace {
 //   M_LDELTA y = A x_new after a BACKWARD M_GSD sweep = b + sum_{lower} A_row,j delta_j: row i was
 //            updated with the new upper and the old lower neighbours, so A x_new differs from b
 //            only by L (x_new - x_old); only L is read (x = delta)
+//   M_LDELTAG the same on a multi-GPU level (hybrid Gauss-Seidel: ghost columns keep their
+//            pre-sweep value during the sweep): y = b + sum_{lower or ghost} A_row,j delta_j with
+//            delta_ghost = halo exchange of the owners' delta. Ghost columns (>= n_swept) are the
+//            tail of the upper part; their column indices are read for the whole row, their
+//            values only where needed. Ghost rows get y = b.
 // One preconditioner application + Krylov matvec therefore reads the fine matrix 2.5 times
 // (L, U, L+D+U, L) instead of 4 times. The kernels are latency/occupancy bound (ncu:
 // long-scoreboard stalls, 66-68 % achieved warps): the colour kernels are compiled for 8 resident
@@ -41,7 +46,7 @@ namespace {
 #ifndef PNPB200_SUM3
 #define PNPB200_SUM3 1
 #endif
-enum { M_SPMV = 0, M_RES = 1, M_GS = 2, M_GS0 = 3, M_RESU = 4, M_GSD = 5, M_LDELTA = 6 };
+enum { M_SPMV = 0, M_RES = 1, M_GS = 2, M_GS0 = 3, M_RESU = 4, M_GSD = 5, M_LDELTA = 6, M_LDELTAG = 7 };
 
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(256, MINB)
@@ -55,6 +60,7 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
   if (t < nrows) { const int4 d = rd[t]; s = d.x; len = d.y; nl = d.z; row = d.w; }
   int k0 = 0, k1 = len;
   if (MODE == M_GS0 || MODE == M_LDELTA) k1 = nl;
+  if (MODE == M_LDELTAG && row >= n_swept) k1 = 0;
   if (MODE == M_RESU && row < n_swept) k0 = nl + 1;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   auto block = [&](int k) {
@@ -68,7 +74,9 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
     const double* v = val + (9 * (size_t)s + (size_t)k);
     const int st = len;
 #endif
-    const size_t j = 3 * (size_t)ja[s + k];
+    const int jcol = ja[s + k];
+    if (MODE == M_LDELTAG && k >= nl && (k == nl || jcol < n_swept)) return;
+    const size_t j = 3 * (size_t)jcol;
     const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
     a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
     a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
@@ -85,7 +93,7 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
   // lane (c, i) = (lane >> 2, lane & 3) of the half-warp holds the row sum of component c
   const double a = half_sum3(a0, a1, a2, lane);
   const int c = lane >> 2, i = lane & 3;
-  if (MODE == M_SPMV || MODE == M_RES || MODE == M_RESU || MODE == M_LDELTA) {
+  if (MODE == M_SPMV || MODE == M_RES || MODE == M_RESU || MODE == M_LDELTA || MODE == M_LDELTAG) {
     if (row >= 0 && i == 0 && c < 3) {
       const size_t o = 3 * (size_t)row + c;
       if (MODE == M_SPMV) y[o] = a;
@@ -113,7 +121,7 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
     if (MODE == M_SPMV) y[o + lane] = a;
     else if (MODE == M_RES) y[o + lane] = b[o + lane] - a;
     else if (MODE == M_RESU) y[o + lane] = row < n_swept ? -a : b[o + lane] - a;
-    else if (MODE == M_LDELTA) y[o + lane] = b[o + lane] + a;
+    else if (MODE == M_LDELTA || MODE == M_LDELTAG) y[o + lane] = b[o + lane] + a;
     else {
       const double r0 = b[o] - a0, r1 = b[o + 1] - a1, r2 = b[o + 2] - a2;
       const double* d = dinv + 9 * (size_t)t + 3 * lane;
@@ -146,6 +154,7 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
   auto range = [&](const int4& d, int& k0, int& k1) {
     k0 = 0; k1 = d.y;
     if (MODE == M_GS0 || MODE == M_LDELTA) k1 = d.z;
+    if (MODE == M_LDELTAG && d.w >= n_swept) k1 = 0;
     if (MODE == M_RESU && d.w < n_swept) k0 = d.z + 1;
   };
   auto first_ja = [&](const int4& d) -> int {
@@ -167,12 +176,13 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
     const int c = lane >> 2, i = lane & 3;
     double bq = 0.0, dq = 0.0;          // epilogue operands, requested up front as well
     if (row >= 0 && c < 3) {
-      if (MODE == M_RES || MODE == M_LDELTA || (MODE == M_RESU && row >= n_swept)) { if (i == 0) bq = b[3 * (size_t)row + c]; }
+      if (MODE == M_RES || MODE == M_LDELTA || MODE == M_LDELTAG || (MODE == M_RESU && row >= n_swept)) { if (i == 0) bq = b[3 * (size_t)row + c]; }
       if (MODE == M_GS || MODE == M_GS0 || MODE == M_GSD) { if (i < 3) { bq = b[3 * (size_t)row + c]; dq = dinv[9 * (size_t)t + 3 * i + c]; } }
     }
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     auto block = [&](int k, int jc) {
       if ((MODE == M_GS || MODE == M_GSD) && k == nl) return;
+      if (MODE == M_LDELTAG && k >= nl && (k == nl || jc < n_swept)) return;
 #if PNPB200_SPLIT_ROWS
       const bool lo = (MODE == M_GS0 || MODE == M_LDELTA) ? true : k < nl;
       const double* v = val + (9 * (size_t)s + (size_t)(lo ? k : 8 * nl + k));
@@ -192,7 +202,7 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
 #pragma unroll 1
     for (k += 16; k < k1; k += 16) block(k, ja[s + k]);      // rows with more than 16 blocks in range (rare)
     const double a = half_sum3(a0, a1, a2, lane);
-    if (MODE == M_SPMV || MODE == M_RES || MODE == M_RESU || MODE == M_LDELTA) {
+    if (MODE == M_SPMV || MODE == M_RES || MODE == M_RESU || MODE == M_LDELTA || MODE == M_LDELTAG) {
       if (row >= 0 && i == 0 && c < 3) {
         const size_t o = 3 * (size_t)row + c;
         if (MODE == M_SPMV) y[o] = a;
@@ -597,8 +607,8 @@ void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x,
 void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s)
 {
   const BsrT& A = L.A;
-  if (owned_rows(L) != A.n) throw Error(ERROR_UNKNOWN, "bsrt_apply_after_sweep: single-GPU levels only");
-  launch_rows<M_LDELTA, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A, nullptr, b, delta, y, nullptr, s);
+  if (owned_rows(L) != A.n) launch_rows<M_LDELTAG, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.rd.p, A, nullptr, b, delta, y, nullptr, s);
+  else launch_rows<M_LDELTA, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A, nullptr, b, delta, y, nullptr, s);
 }
 
 void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s)

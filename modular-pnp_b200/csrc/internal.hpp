@@ -223,8 +223,8 @@ inline int owned_rows(const Level& L) { return L.n_own >= 0 ? L.n_own : L.A.n; }
 inline size_t owned_dofs(const Handle& h) { return 3 * (size_t)owned_rows(*h.hier.lv[0]); }
 // ---- amg.cu
 void amg_setup(Handle& h, const SolverConfig& cfg);
-// z = M^{-1} r. If Az != nullptr and the cycle can deliver it for half a matrix pass (single GPU,
-// at least one post-smoothing sweep), Az = A z is written too and true is returned.
+// z = M^{-1} r. If Az != nullptr and the cycle can deliver it for half a matrix pass (at least one
+// post-smoothing sweep), Az = A z is written too and true is returned.
 bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az = nullptr);
 // ---- fgmres.cu
 int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x);
