@@ -106,13 +106,19 @@ __global__ void mis_init_kernel(int n, const unsigned char* __restrict__ iso, in
   if (i < n) state[i] = iso[i] ? 2 : 0;
 }
 
+// Only rows that can still influence a decision are visited: the second propagation (FIRST =
+// false) feeds mis_decide_kernel, which looks at undecided rows only; the first one must be current
+// for the strong neighbours of undecided rows (need[] is set by mis_decide_kernel for every row it
+// leaves undecided and for that row's strong neighbours). After three rounds < 10 % of the rows
+// are active, so the 16 rounds of the 256^3 fine level cost about as much as four full ones.
 template <bool FIRST>
 __global__ void mis_prop_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
                                 const int* __restrict__ ja, const unsigned char* __restrict__ strong, const int* __restrict__ state,
-                                const u64* __restrict__ tin, u64* __restrict__ tout)
+                                const unsigned char* __restrict__ need, const u64* __restrict__ tin, u64* __restrict__ tout)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (FIRST ? !need[i] : state[i] != 0) return;
   auto key = [&](int j) -> u64 {
     if (!FIRST) return tin[j];
     const int st = state[j];
@@ -124,15 +130,21 @@ __global__ void mis_prop_kernel(int n, const int* __restrict__ ia, const int* __
   tout[i] = m;
 }
 
-__global__ void mis_decide_kernel(int n, const u64* __restrict__ t2, int* __restrict__ state,
-                                  int* __restrict__ undecided)
+__global__ void mis_decide_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
+                                  const int* __restrict__ ja, const unsigned char* __restrict__ strong,
+                                  const u64* __restrict__ t2, int* __restrict__ state,
+                                  unsigned char* __restrict__ need_next, int* __restrict__ undecided)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || state[i] != 0) return;
   const u64 m = t2[i];
   if ((int)(m & 0xffffffffu) == i) state[i] = 1;
   else if ((m >> 62) == 2) state[i] = 2;
-  else atomicAdd(undecided, 1);
+  else {
+    atomicAdd(undecided, 1);
+    need_next[i] = 1;                 // benign races: every writer stores 1
+    for (int p = rs[i], e = rs[i] + ia[i + 1] - ia[i]; p < e; ++p) if (strong[p]) need_next[ja[p]] = 1;
+  }
 }
 
 __global__ void root_flag_kernel(int n, const int* __restrict__ state, int* __restrict__ flag)
@@ -455,7 +467,7 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   const int n = A.n, nnzb = A.nnzb;
   // all large temporaries of this coarsening step live in the handle's workspace
   Workspace& ws = h.ws;
-  ws.reserve((size_t)nnzb * 60 + (size_t)n * 96 + (64u << 20), s);
+  ws.reserve((size_t)nnzb * 60 + (size_t)n * 104 + (64u << 20), s);
   ws.reset();
   struct P1 { double* p; } pp; struct P2 { unsigned char* p; } iso, strong; struct P3 { int* p; void zero(cudaStream_t st) { cudaMemsetAsync(p, 0, sizeof(int), st); } } state, cnt;
   struct P4 { u64* p; } t1, t2;
@@ -479,20 +491,24 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   PHASE("mis2");
   state.p = ws.get<int>(n); cnt.p = ws.get<int>(1);
   t1.p = ws.get<u64>(n); t2.p = ws.get<u64>(n);
+  unsigned char* need = ws.get<unsigned char>(n); unsigned char* need_next = ws.get<unsigned char>(n);
+  PNP_CUDA(cudaMemsetAsync(need, 1, n, s));
   mis_init_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, iso.p, state.p); PNP_COUNT_LAUNCH();
   int und = 1;
   while (und > 0) {
     cnt.zero(s);
-    mis_prop_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, strong.p, state.p, nullptr, t1.p); PNP_COUNT_LAUNCH();
-    mis_prop_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, strong.p, state.p, t1.p, t2.p); PNP_COUNT_LAUNCH();
-    mis_decide_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, t2.p, state.p, cnt.p); PNP_COUNT_LAUNCH();
+    PNP_CUDA(cudaMemsetAsync(need_next, 0, n, s));
+    mis_prop_kernel<true><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, strong.p, state.p, need, nullptr, t1.p); PNP_COUNT_LAUNCH();
+    mis_prop_kernel<false><<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, strong.p, state.p, need, t1.p, t2.p); PNP_COUNT_LAUNCH();
+    mis_decide_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, strong.p, t2.p, state.p, need_next, cnt.p); PNP_COUNT_LAUNCH();
+    std::swap(need, need_next);
     PNP_CUDA(cudaMemcpyAsync(&und, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     PNP_CUDA(cudaStreamSynchronize(s));
     if (++rounds > 1000) throw Error(ERROR_AMG_COARSEING, "MIS-2 did not terminate");
   }
   }
   if (g_phase) printf("    [setup l%d] mis2 rounds %d\n", g_phase_lvl, rounds);
-  PHASE("aggregate+rap_sym");
+  std::unique_ptr<Phase> ph(new Phase(s, g_phase, "aggregate", g_phase_lvl));
   // aggregate ids
   struct { int* p; } flag, rootid, agg2; flag.p = ws.get<int>(n + 1); rootid.p = ws.get<int>(n + 1); agg2.p = ws.get<int>(n);
   root_flag_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(n, state.p, flag.p); PNP_COUNT_LAUNCH();
@@ -580,7 +596,11 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
     iota_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, vin.p); PNP_COUNT_LAUNCH();
     sort_pairs(ws, kin.p, kout.p, vin.p, L.agg_rows.p, n, 32, s);
   }
-  // coarse structure: sort blocks by (I,J)
+  // coarse structure: sort blocks by (I,J). (Tried: gathering the blocks aggregate by aggregate and
+  // sorting each aggregate's ~165 entries on J with cub::DeviceSegmentedSort — the segmented sort
+  // alone took 52 ms at 192^3 (107 M entries in 640 k segments) where this whole radix-sort path
+  // takes 22 ms at 256^3 (253 M entries).)
+  ph.reset(); ph.reset(new Phase(s, g_phase, "rap_sort+structure", g_phase_lvl));
   {
     const int nnzx = nnzb + nghost_c;      // fine blocks + identity diagonals of the coarse ghost rows
     const u64 nagg64 = (u64)ncoarse;
@@ -606,6 +626,7 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
                                                         rowcnt.p, nvalid); PNP_COUNT_LAUNCH();
     exclusive_scan_int(rowcnt.p, Ac.ia.p, ncoarse + 1, s);
     // colour the coarse graph and store it colour by colour, then re-key the numeric map
+    ph.reset(); ph.reset(new Phase(s, g_phase, "coarse colour+layout", g_phase_lvl));
     color_and_layout(C, cja_nat.p, &ws, s);
     rap_remap_kernel<<<cdiv(cnnzb, 256), 256, 0, s>>>(cnnzb, crow.p, cja_nat.p, Ac.ia.p, Ac.rs.p, Ac.ja.p, seg.p, L.rap_beg.p, L.rap_end.p);
     PNP_COUNT_LAUNCH();
