@@ -62,7 +62,7 @@ int solve_current(Handle& h, const itsolver_param* it, const AMG_param* amg, int
   h.stats.ms_spmv = h.stats.ms_vcycle = h.stats.ms_ortho = 0.0;
   { EventSpan e(h, h.stats.ms_setup); if (cfg.use_amg) amg_setup(h, cfg); e.stop(); }
   int st;
-  { EventSpan e(h, h.stats.ms_krylov); st = fgmres_solve(h, cfg, h.rhs.p, h.du.p); e.stop(); }
+  { EventSpan e(h, h.stats.ms_krylov); st = fgmres_solve(h, cfg, h.rhs.p, h.du.p, true); e.stop(); }
   if (status_its) *status_its = st;
   return FASP_SUCCESS;
 }

@@ -25,7 +25,7 @@ struct PhaseTimer {
 };
 }
 
-int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
+int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x, bool zero_guess)
 {
   cudaStream_t s = h.stream;
   const BsrT& A = h.hier.lv[0]->A;
@@ -50,9 +50,15 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x)
       neg(restart_max + 1);
 
   const double b_norm = vec_norm2(h, b, m);
-  if (dist) halo_exchange(h, halo, x);
-  bsrt_residual(A, b, x, Vi(0), s);
-  double r_norm = vec_norm2(h, Vi(0), m), r_norm_old;
+  double r_norm, r_norm_old;
+  if (zero_guess) {                 // r0 = b - A*0
+    vec_copy(Vi(0), b, n, s);
+    r_norm = b_norm;
+  } else {
+    if (dist) halo_exchange(h, halo, x);
+    bsrt_residual(A, b, x, Vi(0), s);
+    r_norm = vec_norm2(h, Vi(0), m);
+  }
   const double den = b_norm > 0.0 ? b_norm : r_norm;
   const double epsilon = cfg.tol * den;
   if (!(r_norm > epsilon)) return 0;

@@ -227,6 +227,7 @@ void amg_setup(Handle& h, const SolverConfig& cfg);
 // post-smoothing sweep), Az = A z is written too and true is returned.
 bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az = nullptr);
 // ---- fgmres.cu
-int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x);
+// zero_guess: x is known to be all zeros on entry (linear_pnp.cpp:93), so r0 = b needs no matvec
+int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x, bool zero_guess = false);
 
 } // namespace pnpb200
