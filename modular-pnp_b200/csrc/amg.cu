@@ -293,25 +293,39 @@ __global__ void rap_numeric_kernel(int cnnzb, const int4* __restrict__ crd, cons
   cval[co + (size_t)t * cst] = acc;
 }
 
-// ---- grid transfer ---------------------------------------------------------------------------
-__global__ void restrict_kernel(int nagg, const int* __restrict__ agg_ptr, const int* __restrict__ agg_rows,
-                                const double* __restrict__ r, double* __restrict__ bc)
+// ---- grid transfer (sweep space, internal.hpp) --------------------------------------------------
+// coarse position P <- sum of the fine positions of aggregate c_rowid[P] (coarsest level: P itself)
+__global__ void restrict_kernel(int nagg, const int* __restrict__ c_rowid, const int* __restrict__ agg_ptr,
+                                const int* __restrict__ agg_rows_pos, const double* __restrict__ r, double* __restrict__ bc)
 {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 3 * nagg) return;
-  const int I = e / 3, k = e % 3;
+  const int P = e / 3, k = e % 3;
+  const int I = c_rowid ? c_rowid[P] : P;
   double a = 0.0;
-  for (int p = agg_ptr[I]; p < agg_ptr[I + 1]; ++p) a += r[3 * (size_t)agg_rows[p] + k];
+  for (int p = agg_ptr[I]; p < agg_ptr[I + 1]; ++p) a += r[3 * (size_t)agg_rows_pos[p] + k];
   bc[e] = a;
 }
 
-__global__ void prolong_kernel(int n, const int* __restrict__ agg, const double* __restrict__ ec,
+__global__ void prolong_kernel(int n, const int* __restrict__ agg_pos, const double* __restrict__ ec,
                                double* __restrict__ x)
 {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 3 * n) return;
-  const int a = agg[e / 3];
+  const int a = agg_pos[e / 3];
   if (a >= 0) x[e] += ec[3 * (size_t)a + e % 3];
+}
+
+// agg_pos[p] = coarse position of the aggregate of row rowid[p]; agg_rows_pos[q] = position of member agg_rows[q]
+__global__ void transfer_maps_kernel(int n, const int* __restrict__ rowid, const int* __restrict__ pos,
+                                     const int* __restrict__ agg, const int* __restrict__ agg_rows,
+                                     const int* __restrict__ c_pos, int* __restrict__ agg_pos, int* __restrict__ agg_rows_pos)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int a = agg[rowid[p]];
+  agg_pos[p] = a < 0 ? -1 : (c_pos ? c_pos[a] : a);
+  agg_rows_pos[p] = pos[agg_rows[p]];      // entries behind the last aggregate's members are unused rows (agg < 0)
 }
 
 // ---- coarsest level: dense inverse -------------------------------------------------------------
@@ -843,7 +857,19 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
     alloc_level_vectors(C, s);
     ++l;
   }
-  if (!reuse) lv.resize(l + 1);
+  if (!reuse) {
+    lv.resize(l + 1);
+    // grid transfer maps in sweep space; the coarsest level (dense solve) keeps row-id order
+    for (int k = 0; k + 1 < (int)lv.size(); ++k) {
+      Level& Lk = *lv[k]; Level& Ck = *lv[k + 1];
+      Lk.coarse_identity = (k + 2 == (int)lv.size());
+      const int nk = Lk.A.n;
+      Lk.agg_pos.alloc(nk, s); Lk.agg_rows_pos.alloc(nk, s);
+      transfer_maps_kernel<<<cdiv(nk, 256), 256, 0, s>>>(nk, Lk.A.vrowid.p, Lk.A.pos.p, Lk.agg.p, Lk.agg_rows.p,
+                                                        Lk.coarse_identity ? nullptr : Ck.A.pos.p, Lk.agg_pos.p, Lk.agg_rows_pos.p);
+      PNP_COUNT_LAUNCH();
+    }
+  }
   setup_coarsest(h);
   h.hier.symbolic_valid = true;
   if (cfg.print_level > 0) {
@@ -878,30 +904,31 @@ bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double
   if (cfg.presmooth == 1 && h.sweep_shortcuts) {
     if (m > 3 * (size_t)own) PNP_CUDA(cudaMemsetAsync(x + 3 * (size_t)own, 0, (m - 3 * (size_t)own) * sizeof(double), s));
     mcgs_sweep_from_zero(L, b, x, s);
-    if (dist) halo_exchange(h, L.halo, x);
+    if (dist) halo_exchange(h, L.halo, x, true);
     bsrt_residual_after_sweep(L, b, x, L.w.p, s);
   } else {
     vec_set(x, 0.0, m, s);
-    for (int k = 0; k < cfg.presmooth; ++k) { if (dist && k > 0) halo_exchange(h, L.halo, x); mcgs_sweep(L, b, x, false, s); }
-    if (dist) halo_exchange(h, L.halo, x);
+    for (int k = 0; k < cfg.presmooth; ++k) { if (dist && k > 0) halo_exchange(h, L.halo, x, true); mcgs_sweep(L, b, x, false, s); }
+    if (dist) halo_exchange(h, L.halo, x, true);
     bsrt_residual(L.A, b, x, L.w.p, s);
   }
   if (L.nagg > 0) {
-    restrict_kernel<<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, L.agg_ptr.p, L.agg_rows.p, L.w.p, C.b.p);
+    restrict_kernel<<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, L.coarse_identity ? nullptr : C.A.vrowid.p, L.agg_ptr.p,
+                                                                 L.agg_rows_pos.p, L.w.p, C.b.p);
     PNP_COUNT_LAUNCH();
   }
   solve_level(h, cfg, l + 1, C.b.p, C.x.p);
-  if (own > 0) { prolong_kernel<<<cdiv(3 * (size_t)own, 256), 256, 0, s>>>(own, L.agg.p, C.x.p, x); PNP_COUNT_LAUNCH(); }
+  if (own > 0) { prolong_kernel<<<cdiv(3 * (size_t)own, 256), 256, 0, s>>>(own, L.agg_pos.p, C.x.p, x); PNP_COUNT_LAUNCH(); }
   const bool want_ax = Ax != nullptr && cfg.postsmooth >= 1 && h.sweep_shortcuts;
   for (int k = 0; k < cfg.postsmooth; ++k) {
-    if (dist) halo_exchange(h, L.halo, x);
+    if (dist) halo_exchange(h, L.halo, x, true);
     if (want_ax && k == cfg.postsmooth - 1) mcgs_sweep_back_delta(L, b, x, L.w.p, s);
     else mcgs_sweep(L, b, x, true, s);
   }
   if (want_ax) {
     // multi-GPU (hybrid GS): the ghost columns kept their pre-sweep value, so their delta — the
     // owners' delta, one halo exchange — enters the product as well
-    if (dist) halo_exchange(h, L.halo, L.w.p);
+    if (dist) halo_exchange(h, L.halo, L.w.p, true);
     bsrt_apply_after_sweep(L, b, L.w.p, Ax, s);
   }
   return want_ax;
@@ -927,14 +954,14 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
   double* sc = L.ksc.p; double* partial = sc + 8;
   const int g = small_grid(mo);
   if (!mg_cycle(h, cfg, l, b, c, v)) {
-    if (dist) halo_exchange(h, L.halo, c);
+    if (dist) halo_exchange(h, L.halo, c, true);
     bsrt_spmv(L.A, c, v, s);
   }
   kdots_kernel<2><<<g, 256, 0, s>>>(mo, v, b, v, v, nullptr, nullptr, partial, L.kcnt.p, sc); PNP_COUNT_LAUNCH();
   if (dist) comm_allreduce(h, sc, 2, false);
   kc_step1_kernel<<<g, 256, 0, s>>>(mo, sc, b, v, rt); PNP_COUNT_LAUNCH();
   if (!mg_cycle(h, cfg, l, rt, d, w)) {
-    if (dist) halo_exchange(h, L.halo, d);
+    if (dist) halo_exchange(h, L.halo, d, true);
     bsrt_spmv(L.A, d, w, s);
   }
   kdots_kernel<3><<<g, 256, 0, s>>>(mo, w, v, w, w, w, rt, partial, L.kcnt.p, sc + 2); PNP_COUNT_LAUNCH();

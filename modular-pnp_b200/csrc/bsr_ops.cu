@@ -245,7 +245,7 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
 #endif
 int g_sm_count = 0;
 template <int MODE, int MINB, bool PIPE>
-void launch_rows(int nrows, int n_swept, const int4* rd, const BsrT& A, const double* dinv, const double* b,
+void launch_rows(int nrows, int n_swept, const int4* rd, const int* ja, const BsrT& A, const double* dinv, const double* b,
                  const double* x, double* y, double* dl, cudaStream_t s)
 {
   if (nrows <= 0) return;
@@ -259,9 +259,9 @@ void launch_rows(int nrows, int n_swept, const int4* rd, const BsrT& A, const do
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bsrt_row_pipe_kernel<MODE, MINB>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = MINB;
   }
   const int cap = g_sm_count * per_sm;
-  bsrt_row_pipe_kernel<MODE, MINB><<<full < cap ? full : cap, 256, 0, s>>>(nrows, n_swept, rd, A.ja.p, A.val.p, dinv, b, x, y, dl);
+  bsrt_row_pipe_kernel<MODE, MINB><<<full < cap ? full : cap, 256, 0, s>>>(nrows, n_swept, rd, ja, A.val.p, dinv, b, x, y, dl);
   } else
-  bsrt_row_kernel<MODE, MINB><<<full, 256, 0, s>>>(nrows, n_swept, rd, A.ja.p, A.val.p, dinv, b, x, y, dl);
+  bsrt_row_kernel<MODE, MINB><<<full, 256, 0, s>>>(nrows, n_swept, rd, ja, A.val.p, dinv, b, x, y, dl);
   PNP_COUNT_LAUNCH();
 }
 
@@ -456,11 +456,11 @@ __global__ void layout_row_kernel(int n, const int* __restrict__ ia, const int* 
   rd[i] = make_int4(s, len, nl, i);
 }
 
-__global__ void physical_descriptor_kernel(int n, const int* __restrict__ rowid, const int4* __restrict__ rd,
-                                           int4* __restrict__ prd)
+__global__ void physical_descriptor_kernel(int n, const int* __restrict__ rowid, const int* __restrict__ pos,
+                                           const int4* __restrict__ rd, int4* __restrict__ prd)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n) prd[p] = rd[rowid[p]];
+  if (p < n) { const int i = rowid[p]; int4 d = rd[i]; d.w = pos[i]; prd[p] = d; }      // .w: position in the solver vectors
 }
 
 __device__ __forceinline__ int find_sorted(const int* __restrict__ ja, int lo, int hi, int c)   // [lo, hi]
@@ -503,6 +503,27 @@ __global__ void scatter_rs_kernel(int n, const int* __restrict__ rowid, const in
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < n) rs[rowid[p]] = start[p];
+}
+// vector order key: (tile of consecutive row ids, colour); ghost rows last
+__global__ void vector_key_kernel(int n, int n_own, int tile_rows, int ghost_key, const int* __restrict__ sweep_key, int* __restrict__ vkey)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) vkey[i] = i >= n_own ? ghost_key : (i / tile_rows) * 64 + (sweep_key[i] & 63);
+}
+__global__ void invert_perm_kernel(int n, const int* __restrict__ vrowid, int* __restrict__ pos)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) pos[vrowid[q]] = q;
+}
+__global__ void vector_descriptor_kernel(int n, const int* __restrict__ vrowid, const int4* __restrict__ rd, int4* __restrict__ vrd)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) { int4 d = rd[vrowid[q]]; d.w = q; vrd[q] = d; }
+}
+__global__ void gather_pos_kernel(int n, const int* __restrict__ pos, const int* __restrict__ idx, int* __restrict__ out)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) out[e] = pos[idx[e]];
 }
 
 // ---- Jones-Plassmann colouring with hashed priorities (two kernels per round so that the
@@ -590,25 +611,55 @@ __global__ void iota_kernel(int n, int* __restrict__ a)
 
 void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s)
 {
-  launch_rows<M_SPMV, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A, nullptr, nullptr, x, y, nullptr, s);
+  launch_rows<M_SPMV, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, nullptr, x, y, nullptr, s);
 }
 
 void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s)
 {
-  launch_rows<M_RES, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A, nullptr, b, x, r, nullptr, s);
+  launch_rows<M_RES, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, b, x, r, nullptr, s);
+}
+
+void bsrt_spmv_rowid(const BsrT& A, const double* x, double* y, cudaStream_t s)
+{
+  launch_rows<M_SPMV, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A.ja.p, A, nullptr, nullptr, x, y, nullptr, s);
+}
+
+void bsrt_residual_rowid(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s)
+{
+  launch_rows<M_RES, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A.ja.p, A, nullptr, b, x, r, nullptr, s);
 }
 
 void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x, double* r, cudaStream_t s)
 {
   const BsrT& A = L.A;
-  launch_rows<M_RESU, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.rd.p, A, nullptr, b, x, r, nullptr, s);
+  launch_rows<M_RESU, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.vrd.p, A.jpos.p, A, nullptr, b, x, r, nullptr, s);
 }
 
 void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s)
 {
   const BsrT& A = L.A;
-  if (owned_rows(L) != A.n) launch_rows<M_LDELTAG, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.rd.p, A, nullptr, b, delta, y, nullptr, s);
-  else launch_rows<M_LDELTA, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A, nullptr, b, delta, y, nullptr, s);
+  if (owned_rows(L) != A.n) launch_rows<M_LDELTAG, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.vrd.p, A.jpos.p, A, nullptr, b, delta, y, nullptr, s);
+  else launch_rows<M_LDELTA, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, b, delta, y, nullptr, s);
+}
+
+namespace {
+__global__ void permute3_kernel(int n, const int* __restrict__ rowid, const double* __restrict__ in, double* __restrict__ out, int to_sweep)
+{
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * (size_t)n) return;
+  const size_t p = e / 3; const int k = (int)(e % 3);
+  const size_t r = 3 * (size_t)rowid[p] + k;
+  if (to_sweep) out[e] = in[r]; else out[r] = in[e];
+}
+} // namespace
+
+void vec_to_sweep(const BsrT& A, const double* in_rowid, double* out_sweep, cudaStream_t s)
+{
+  permute3_kernel<<<cdiv(3 * (size_t)A.n, 256), 256, 0, s>>>(A.n, A.vrowid.p, in_rowid, out_sweep, 1); PNP_COUNT_LAUNCH();
+}
+void vec_from_sweep(const BsrT& A, const double* in_sweep, double* out_rowid, cudaStream_t s)
+{
+  permute3_kernel<<<cdiv(3 * (size_t)A.n, 256), 256, 0, s>>>(A.n, A.vrowid.p, in_sweep, out_rowid, 0); PNP_COUNT_LAUNCH();
 }
 
 void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s)
@@ -648,12 +699,12 @@ void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool rev
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     mcgs_smem_kernel<<<1, 1024, small_level_smem(A.n, A.nnzb), s>>>(A.n, A.nnzb, L.ngroups, reverse ? 1 : 0, mode, L.d_color_ptr.p,
-                                                                  A.prd.p, A.ja.p, A.val.p, L.dinv.p, b, x, dl);
+                                                                  A.prd.p, A.jpos.p, A.val.p, L.dinv.p, b, x, dl);
     PNP_COUNT_LAUNCH();
     return;
   }
   if (A.n <= SMALL_LEVEL_ROWS && L.ngroups > 0) {
-    mcgs_small_kernel<<<1, 1024, 0, s>>>(L.ngroups, reverse ? 1 : 0, mode, L.d_color_ptr.p, A.prd.p, A.ja.p, A.val.p,
+    mcgs_small_kernel<<<1, 1024, 0, s>>>(L.ngroups, reverse ? 1 : 0, mode, L.d_color_ptr.p, A.prd.p, A.jpos.p, A.val.p,
                                         L.dinv.p, b, x, dl);
     PNP_COUNT_LAUNCH();
     return;
@@ -664,9 +715,9 @@ void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool rev
     if (cnt == 0) continue;
     const int4* rd = A.prd.p + L.color_ptr[c];
     const double* dinv = L.dinv.p + 9 * (size_t)L.color_ptr[c];      // sweep order: this colour's piece
-    if (mode == 1) launch_rows<M_GS0, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, dinv, b, x, x, nullptr, s);
-    else if (mode == 2) launch_rows<M_GSD, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, dinv, b, x, x, dl, s);
-    else launch_rows<M_GS, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A, dinv, b, x, x, nullptr, s);
+    if (mode == 1) launch_rows<M_GS0, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, nullptr, s);
+    else if (mode == 2) launch_rows<M_GSD, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, dl, s);
+    else launch_rows<M_GS, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, nullptr, s);
   }
 }
 } // namespace
@@ -681,7 +732,7 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
 {
   BsrT& A = L.A;
   const int n = A.n;
-  DevBuf<int> t_color, t_rem, t_rows, t_cout, t_len, t_start, t_hist, t_newc; DevBuf<unsigned char> t_cand, t_cub;
+  DevBuf<int> t_color, t_rem, t_rows, t_cout, t_len, t_start, t_hist, t_newc, t_vkey, t_vkout; DevBuf<unsigned char> t_cand, t_cub, t_cub2;
   auto geti = [&](DevBuf<int>& own, size_t cnt) -> int* { if (ws) return ws->get<int>(cnt); own.alloc(cnt, s); return own.p; };
   int* color = geti(t_color, n);
   int* rem = geti(t_rem, 2);                       // [0] remaining, [1] overflow
@@ -764,19 +815,49 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
   int* start = A.pia.p;
   rowlen_by_position_kernel<<<cdiv(n + 1, 256), 256, 0, s>>>(n, A.ia.p, A.rowid.p, len); PNP_COUNT_LAUNCH();
   exclusive_scan_int(len, start, n + 1, s);
-  A.rs.alloc(n, s); A.rd.alloc(n, s); A.prd.alloc(n, s);
+  A.rs.alloc(n, s); A.rd.alloc(n, s); A.prd.alloc(n, s); A.pos.alloc(n, s); A.vrowid.alloc(n, s); A.vrd.alloc(n, s);
   scatter_rs_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, start, A.rs.p); PNP_COUNT_LAUNCH();
+  {
+    // vector order of the solver (BsrT::vrowid): rows sorted by (tile, colour), ghost rows last
+    static const int vec_tile = getenv("PNPB200_VEC_TILE") ? atoi(getenv("PNPB200_VEC_TILE")) : 4096;
+    if (vec_tile <= 0 || ntiles > 1) {
+      PNP_CUDA(cudaMemcpyAsync(A.vrowid.p, A.rowid.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s));   // = matrix order
+    } else {
+      const int nt = (n + vec_tile - 1) / vec_tile;
+      const int ghost_key = nt * 64;
+      int vbits = 1; while ((1 << vbits) <= ghost_key) ++vbits;
+      int* vkey = geti(t_vkey, n);
+      int* vkey_out = geti(t_vkout, n);
+      vector_key_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, n_own, vec_tile, ghost_key, color, vkey); PNP_COUNT_LAUNCH();
+      size_t vb = 0;
+      PNP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, vb, vkey, vkey_out, rows_in, A.vrowid.p, n, 0, vbits, s));
+      unsigned char* vtmp;
+      if (ws) vtmp = ws->get<unsigned char>(vb); else { t_cub2.alloc(vb, s); vtmp = t_cub2.p; }
+      PNP_CUDA(cub::DeviceRadixSort::SortPairs(vtmp, vb, vkey, vkey_out, rows_in, A.vrowid.p, n, 0, vbits, s));
+      PNP_COUNT_LAUNCH();
+    }
+    invert_perm_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.vrowid.p, A.pos.p); PNP_COUNT_LAUNCH();
+  }
   A.ja.alloc(A.nnzb, s);
   A.brow.alloc(A.nnzb, s); A.dslot.alloc(n, s); A.tslot.alloc(A.nnzb, s);
   PNP_CUDA(cudaMemsetAsync(rem, 0, sizeof(int), s));
   layout_row_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, color, ja_nat, A.ja.p, A.brow.p, A.dslot.p, A.rd.p, rem);
   PNP_COUNT_LAUNCH();
-  physical_descriptor_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, A.rd.p, A.prd.p); PNP_COUNT_LAUNCH();
+  physical_descriptor_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, A.pos.p, A.rd.p, A.prd.p); PNP_COUNT_LAUNCH();
+  vector_descriptor_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.vrowid.p, A.rd.p, A.vrd.p); PNP_COUNT_LAUNCH();
   int nodiag = 0;
   PNP_CUDA(cudaMemcpyAsync(&nodiag, rem, sizeof(int), cudaMemcpyDeviceToHost, s));
   PNP_CUDA(cudaStreamSynchronize(s));
   if (nodiag) throw Error(ERROR_DATA_STRUCTURE, "matrix row without a diagonal block");
   tslot_kernel<<<cdiv(A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.dslot.p, A.ja.p, A.brow.p, A.tslot.p); PNP_COUNT_LAUNCH();
+  // sweep-space index arrays of the solver kernels: columns and halo send lists as sweep positions
+  A.jpos.alloc(A.nnzb, s);
+  gather_pos_kernel<<<cdiv(A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.pos.p, A.ja.p, A.jpos.p); PNP_COUNT_LAUNCH();
+  if (L.halo.active()) {
+    const int nsend = L.halo.send_ptr.back();
+    L.halo.send_pos.alloc(nsend ? nsend : 1, s);
+    if (nsend > 0) { gather_pos_kernel<<<cdiv(nsend, 256), 256, 0, s>>>(nsend, A.pos.p, L.halo.send_idx.p, L.halo.send_pos.p); PNP_COUNT_LAUNCH(); }
+  }
   PNP_LAUNCH_CHECK();
 }
 

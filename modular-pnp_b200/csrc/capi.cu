@@ -408,7 +408,7 @@ int pnpb200_test_solver(pnpb200_handle* ph, const double* target, double* x, con
     assemble_system(h);                                   // linear_pnp.cpp:137
     const size_t N = 3 * (size_t)h.nv;
     DevBuf<double> t; t.alloc(N, s); t.upload(target, N);
-    bsrt_spmv(h.hier.lv[0]->A, t.p, h.rhs.p, s);          // rhs = J * target, linear_pnp.cpp:144
+    bsrt_spmv_rowid(h.hier.lv[0]->A, t.p, h.rhs.p, s);    // rhs = J * target, linear_pnp.cpp:144
     h.rhs_current = false;
     int st = 0;
     solve_current(h, it, amg, &st);
@@ -555,11 +555,14 @@ int pnpb200_apply_vcycle(pnpb200_handle* ph, const double* r, double* z)
     Handle& h = ph->h; cudaStream_t s = h.stream;
     if (!h.hier.symbolic_valid) throw Error(ERROR_INPUT_PAR, "no hierarchy: call pnpb200_solve first");
     const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
-    DevBuf<double> dr, dz; dr.alloc(N, s); dz.alloc(N, s);
-    dr.upload(r, N);
+    DevBuf<double> dr, dz, t; dr.alloc(N, s); dz.alloc(N, s); t.alloc(N, s);
+    t.upload(r, N);
+    const BsrT& A0 = h.hier.lv[0]->A;
+    vec_to_sweep(A0, t.p, dr.p, s);         // the cycle works in sweep order
     const SolverConfig cfg = h.last_cfg;    // cycle of the last solve
     amg_vcycle(h, cfg, dr.p, dz.p);
-    dz.download(z, N);
+    vec_from_sweep(A0, dz.p, t.p, s);
+    t.download(z, N);
     return FASP_SUCCESS;
   });
 }
@@ -629,7 +632,7 @@ int pnpb200_apply_matrix(pnpb200_handle* ph, const double* x, double* y)
     const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
     DevBuf<double> dx, dy; dx.alloc(N, s); dy.alloc(N, s);
     dx.upload(x, N);
-    bsrt_spmv(h.hier.lv[0]->A, dx.p, dy.p, s);
+    bsrt_spmv_rowid(h.hier.lv[0]->A, dx.p, dy.p, s);
     dy.download(y, N);
     return FASP_SUCCESS;
   });
@@ -680,7 +683,7 @@ void fasp_blas_dbsr_aAxpy(const REAL alpha, const dBSRmat* A, const REAL* x, REA
     const size_t N = 3 * (size_t)A->ROW;
     DevBuf<double> dx, dy, dz; dx.alloc(N, s); dy.alloc(N, s); dz.alloc(N, s);
     dx.upload(x, N); dy.upload(y, N);
-    bsrt_spmv(h.hier.lv[0]->A, dx.p, dz.p, s);
+    bsrt_spmv_rowid(h.hier.lv[0]->A, dx.p, dz.p, s);
     vec_axpy(alpha, dz.p, dy.p, N, s);
     dy.download(y, N);
     return 0;
@@ -695,7 +698,7 @@ void fasp_blas_dbsr_mxv(const dBSRmat* A, const REAL* x, REAL* y)
     const size_t N = 3 * (size_t)A->ROW;
     DevBuf<double> dx, dy; dx.alloc(N, s); dy.alloc(N, s);
     dx.upload(x, N);
-    bsrt_spmv(h.hier.lv[0]->A, dx.p, dy.p, s);
+    bsrt_spmv_rowid(h.hier.lv[0]->A, dx.p, dy.p, s);
     dy.download(y, N);
     return 0;
   });

@@ -80,12 +80,14 @@ __global__ void pack1_kernel(int n, const int* __restrict__ idx, const int* __re
 }
 
 // refresh the ghost entries of a block vector (3 doubles per row) from their owners
-void halo_exchange(Handle& h, Halo& c, double* vec)
+void halo_exchange(Handle& h, Halo& c, double* vec, bool sweep_space)
 {
   if (!h.comm.active() || !c.active()) return;
   cudaStream_t s = h.stream;
   const int nsend = c.send_ptr.back();
-  if (nsend > 0) { pack3_kernel<<<cdiv(3 * (size_t)nsend, 256), 256, 0, s>>>(nsend, c.send_idx.p, vec, c.sendbuf.p); PNP_COUNT_LAUNCH(); }
+  if (sweep_space && nsend > 0 && !c.send_pos.p) throw Error(ERROR_UNKNOWN, "halo_exchange: level has no sweep-space send list");
+  const int* idx = sweep_space ? c.send_pos.p : c.send_idx.p;      // ghost rows are the tail in both orders
+  if (nsend > 0) { pack3_kernel<<<cdiv(3 * (size_t)nsend, 256), 256, 0, s>>>(nsend, idx, vec, c.sendbuf.p); PNP_COUNT_LAUNCH(); }
   Api& a = api();
   nccl_check(a.gstart(), "groupStart");
   for (size_t k = 0; k < c.nbr.size(); ++k) {

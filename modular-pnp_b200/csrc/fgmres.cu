@@ -25,7 +25,9 @@ struct PhaseTimer {
 };
 }
 
-int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x, bool zero_guess)
+namespace {
+// the solver proper: b and x are in SWEEP order (internal.hpp), like every vector below
+int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x, bool zero_guess)
 {
   cudaStream_t s = h.stream;
   const BsrT& A = h.hier.lv[0]->A;
@@ -55,7 +57,7 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x,
     vec_copy(Vi(0), b, n, s);
     r_norm = b_norm;
   } else {
-    if (dist) halo_exchange(h, halo, x);
+    if (dist) halo_exchange(h, halo, x, true);
     bsrt_residual(A, b, x, Vi(0), s);
     r_norm = vec_norm2(h, Vi(0), m);
   }
@@ -84,7 +86,7 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x,
         if (cfg.use_amg) have_Az = amg_vcycle(h, cfg, Vi(i - 1), Zi(i - 1), Vi(i));
         else vec_copy(Zi(i - 1), Vi(i - 1), n, s);
       }
-      if (!have_Az) { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, halo, Zi(i - 1)); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
+      if (!have_Az) { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, halo, Zi(i - 1), true); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
       double tnorm;
       {
         PhaseTimer t(h, h.stats.ms_ortho);
@@ -131,7 +133,7 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x,
     multi_axpy(h, Z, n, i, rs.data(), x, m, nullptr);
     // true residual for the convergence confirmation / next cycle
     const bool est_conv = r_norm <= epsilon;
-    if (dist) halo_exchange(h, halo, x);
+    if (dist) halo_exchange(h, halo, x, true);
     bsrt_residual(A, b, x, Vi(0), s);
     r_norm = vec_norm2(h, Vi(0), m);
     if (est_conv && r_norm <= epsilon) { converged = true; break; }
@@ -142,6 +144,22 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x,
   h.stats.krylov_its = iter;
   if (!converged && iter >= MaxIt) return ERROR_SOLVER_MAXIT;
   return iter;
+}
+} // namespace
+
+// b, x in row-id order (the C ABI / assembly side); the iteration runs in sweep order
+int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x, bool zero_guess)
+{
+  cudaStream_t s = h.stream;
+  const BsrT& A = h.hier.lv[0]->A;
+  const size_t n = 3 * (size_t)A.n;
+  Krylov& K = h.kry;
+  K.bs.alloc(n, s); K.xs.alloc(n, s);
+  vec_to_sweep(A, b, K.bs.p, s);
+  if (zero_guess) vec_set(K.xs.p, 0.0, n, s); else vec_to_sweep(A, x, K.xs.p, s);
+  const int rc = fgmres_sweep(h, cfg, K.bs.p, K.xs.p, zero_guess);
+  vec_from_sweep(A, K.xs.p, x, s);      // the last iterate, also on failure
+  return rc;
 }
 
 } // namespace pnpb200

@@ -26,8 +26,15 @@ struct BsrT {
   DevBuf<int> rowid;    // physical row position -> row id (= rows sorted by colour)
   DevBuf<int> pia;      // CSR offsets in PHYSICAL order: row rowid[p] owns blocks [pia[p], pia[p+1])
   DevBuf<int4> rd;      // row descriptor of row i: (physical start, length, nl, i) — one 16-byte load
-  DevBuf<int4> prd;     // the same descriptors in physical (sweep) order: prd[p] describes row rowid[p]
-  DevBuf<int> ja;       // column of each block, physical order ([L | D | U], ascending inside each part)
+  DevBuf<int4> prd;     // the descriptors in matrix (sweep) order: prd[p] = (start, length, nl, pos[rowid[p]])
+  DevBuf<int> vrowid;   // VECTOR order of the solver: entry q of a solver vector belongs to row vrowid[q]. Rows are
+                        // ordered by (tile of VEC_TILE consecutive row ids, colour): a colour launch then reads b and
+                        // writes x in contiguous runs of ~VEC_TILE/ncolors rows, while a pass in vector order still
+                        // gathers x from a mesh-local window (pure colour order costs the matvec 37 %: measured)
+  DevBuf<int> pos;      // row id -> vector position (inverse of vrowid)
+  DevBuf<int4> vrd;     // descriptors in vector order: vrd[q] = (start, length, nl, q) of row vrowid[q]
+  DevBuf<int> ja;       // column (ROW ID) of each block, physical order ([L | D | U], ascending inside each part)
+  DevBuf<int> jpos;     // column as SWEEP POSITION: what the solver kernels gather with
   DevBuf<int> brow;     // row of each block
   DevBuf<int> dslot;    // position (absolute block index) of the diagonal block of each row (= rs[i] + nl_i)
   DevBuf<int> tslot;    // block index of the transposed block (j,i), -1 if absent
@@ -36,9 +43,11 @@ struct BsrT {
 
 // halo lists of one level (block-row granularity): neighbour k gets the owned rows
 // send_idx[send_ptr[k] .. send_ptr[k+1]) and fills the local ghost rows [recv_ptr[k], recv_ptr[k+1])
+// (ghost rows are the last rows in row-id AND in sweep order)
 struct Halo {
   std::vector<int> nbr, send_ptr, recv_ptr;
-  DevBuf<int> send_idx;
+  DevBuf<int> send_idx;         // row ids
+  DevBuf<int> send_pos;         // the same rows as sweep positions (solver vectors)
   DevBuf<double> sendbuf;
   DevBuf<int> isendbuf;
   bool active() const { return !nbr.empty(); }
@@ -58,7 +67,11 @@ struct Level {
   // aggregation to the next level
   int nagg = 0;
   DevBuf<int> agg;              // n, -1 = isolated
-  DevBuf<int> agg_ptr, agg_rows;   // members of each aggregate (ascending)
+  DevBuf<int> agg_ptr, agg_rows;   // members of each aggregate (ascending row ids)
+  // grid transfer in sweep space (built when the hierarchy is complete): coarse position of a fine
+  // position (-1: none), and the members of agg_rows as fine positions
+  DevBuf<int> agg_pos, agg_rows_pos;
+  bool coarse_identity = false;    // the next level is the coarsest (dense solve): its vectors stay in row-id order
   // numeric RAP map: coarse block s sums fine blocks rap_perm[rap_seg[s] .. rap_seg[s+1])
   DevBuf<int> rap_beg, rap_end, rap_perm;
   // work vectors (3*n)
@@ -96,6 +109,7 @@ struct Krylov {
   int n = 0, restart = 0;
   DevBuf<double> V, Z;          // (restart+1)*n and restart*n
   DevBuf<double> r, partial;    // scratch
+  DevBuf<double> bs, xs;        // rhs and iterate in sweep order
   DevBuf<double> dots;          // device results
   double* h_dots = nullptr;     // pinned host mirror
 };
@@ -188,8 +202,17 @@ void total_charge(Handle& h, double* d_out);                                  //
 void entropy_indicator(Handle& h, double* d_eta);                             // src/mesh_refiner.cpp:212-271
 long mark_cells(Handle& h, const double* d_eta, double tol, long target_size, unsigned char* d_marker, double* tol_used);
 // ---- bsr_ops.cu
-void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s);                  // y = A x
-void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s); // r = b - A x
+// Two index spaces. The assembly, the AMG setup and the C ABI address vectors by ROW ID (vertex
+// order on the fine level). The solver (cycle, Krylov) keeps every level's vectors in SWEEP order
+// (entry q belongs to row A.vrowid[q], see BsrT): a Gauss-Seidel colour then reads b and writes x
+// in long contiguous runs. Same kernels, different index arrays: (rd, ja) for row-id space,
+// (vrd or prd, jpos) for sweep space.
+void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s);                  // y = A x      (sweep space)
+void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s); // r = b - A x  (sweep space)
+void bsrt_spmv_rowid(const BsrT& A, const double* x, double* y, cudaStream_t s);            // y = A x      (row-id space)
+void bsrt_residual_rowid(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s);
+void vec_to_sweep(const BsrT& A, const double* in_rowid, double* out_sweep, cudaStream_t s);
+void vec_from_sweep(const BsrT& A, const double* in_sweep, double* out_rowid, cudaStream_t s);
 void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s);
 void bsrt_from_fasp(const double* d_val_fasp, BsrT& A, cudaStream_t s);
 void bsrt_export_ja(const BsrT& A, int* d_ja_nat, cudaStream_t s);
@@ -214,7 +237,8 @@ void multi_dot(Handle& h, const double* V, size_t ld, int nvec, const double* w,
 void multi_axpy(Handle& h, const double* V, size_t ld, int nvec, const double* coef_host, double* w, size_t n,
                 double* norm2_out);
 // ---- comm.cu
-void halo_exchange(Handle& h, Halo& halo, double* vec);      // 3 doubles per block row
+// 3 doubles per block row; sweep_space: vec is a solver vector (indexed by sweep position), else by row id
+void halo_exchange(Handle& h, Halo& halo, double* vec, bool sweep_space = false);
 void halo_exchange_int(Handle& h, Halo& halo, int* vec);     // 1 int per block row
 void comm_allreduce(Handle& h, double* dev, int count, bool is_max);
 void comm_allreduce_int(Handle& h, int* dev, int count, bool is_max);
