@@ -1,12 +1,13 @@
-// pnp-b200 — BSR(3) kernels on the BSR-T layout:
-//   fasp_blas_dbsr_mxv / aAxpy   [EXT FASP]      -> bsrt_spmv / bsrt_residual
+// pnp-b200 — BSR(3) kernels on the BSR-T/LDU layout:
+//   fasp_blas_dbsr_mxv / aAxpy   [EXT FASP]      -> bsrt_spmv / bsrt_residual (+ _rowid forms for the ABI)
 //   fasp_dbsr_getdiaginv         [EXT FASP]      -> bsrt_diaginv
 //   fasp_smoother_dbsr_gs_*      [EXT FASP]      -> multicolour block Gauss-Seidel
 // A half-warp (16 lanes) owns one block row; lane k owns block k of the row, so each of the 9
 // component loads is unit-stride across lanes. Rows are STORED colour by colour (rs[] = physical
-// start of a row, rowid[] = row at a physical position, pia[] = CSR offsets in physical order): one
-// Gauss-Seidel colour is one contiguous piece of ja/val; SpMV walks the rows in natural order. All
-// kernels here are HBM-bound streaming kernels.
+// start of a row, rowid[] = row at a physical position), each row as [L | D | U] (internal.hpp): one
+// Gauss-Seidel colour is one contiguous piece of ja/val. The solver's vectors live in sweep space
+// (BsrT::vrowid); the kernels take the index arrays of either space. All kernels here are HBM-bound
+// streaming kernels (see profiles/README.md for what bounds each of them).
 #include "internal.hpp"
 #include <cub/cub.cuh>
 #include <algorithm>
@@ -16,10 +17,11 @@ namespace pnpb200 {
 namespace {
 
 // One block row per half-warp, lane k = block k of the row (BSR-T/LDU layout, internal.hpp).
-// rd[] holds one 16-byte descriptor (start, length, nl, row) per row: the natural-order kernels
-// index it by row, the colour kernels get prd + p0 (descriptors in sweep order), so row id, start,
-// length and the L/U split come from ONE load.
-//   M_SPMV   y = A x                     M_RES  y = b - A x             (natural order, full rows)
+// rd[] holds one 16-byte descriptor (start, length, nl, vector index of the row) per row: the
+// passes over all rows get the descriptors in vector order (vrd, or rd for row-id space), the
+// colour kernels prd + p0 (descriptors in sweep order), so vector index, start, length and the L/U
+// split come from ONE load. ja[] holds the columns as indices into the vectors of the same space.
+//   M_SPMV   y = A x                     M_RES  y = b - A x             (vector order, full rows)
 //   M_GS     x_row = D^{-1}(b - sum_{j != row} A_row,j x_j), y == x: one Gauss-Seidel colour
 //   M_GS0    the same from a ZERO initial guess, forward sweep: only the lower part contributes
 //            (the upper neighbours are still zero), so only L is read
@@ -36,9 +38,8 @@ namespace {
 //            tail of the upper part; their column indices are read for the whole row, their
 //            values only where needed. Ghost rows get y = b.
 // One preconditioner application + Krylov matvec therefore reads the fine matrix 2.5 times
-// (L, U, L+D+U, L) instead of 4 times. The kernels are latency/occupancy bound (ncu:
-// long-scoreboard stalls, 66-68 % achieved warps): the colour kernels are compiled for 8 resident
-// CTAs per SM, the natural-order passes for 6.
+// (L, U, L+D+U, L) instead of 4 times. The colour kernels are compiled for 8 resident CTAs per SM
+// (32 registers), the passes over all rows run in the pipelined form below.
 // Tried and measured slower: ld.global.cs / L2 evict_first+evict_last hints on the matrix loads
 // (6.3-7.2 ms per sweep), requesting b and D^{-1} before the row's blocks (6.2 vs 5.5 ms: the extra
 // registers cost more occupancy than the overlap gains); gathering the 24 bytes of a vertex with one

@@ -126,6 +126,18 @@ public:
     return q;
   }
 
+  // Mesh_Refiner::mark_for_refinement (src/mesh_refiner.cpp:187-209) and
+  // mark_for_refinement_with_target_size (:155-185, target_size > 0) with the indicator of
+  // compute_entropy_error_vector (:212-271); returns the number of marked cells
+  long mark_for_refinement(double entropy_tolerance, std::vector<unsigned char>& cell_marker, long target_size = 0)
+  {
+    cell_marker.assign((size_t)pnpb200_num_cells(_h), 0);
+    long marked = 0;
+    check(pnpb200_entropy_indicator(_h, nullptr), "compute_entropy_error_vector");
+    check(pnpb200_mark_cells(_h, entropy_tolerance, target_size, cell_marker.data(), &marked, nullptr), "mark_for_refinement");
+    return marked;
+  }
+
   pnpb200_handle* handle() { return _h; }
 
 private:

@@ -228,3 +228,18 @@ def test_sweep_shortcuts_are_the_same_arithmetic(oracle, pkg, system, cycle):
     assert np.abs(out[True][1] - out[False][1]).max() <= 1e-9 * np.abs(out[False][1]).max()
     r = b0 - oracle.bsr_spmv(IA, JA, val, out[True][1])
     assert np.linalg.norm(r) <= 1.0001 * it.tol * np.linalg.norm(b0)
+
+
+def test_fasp_entry_point_nonzero_initial_guess(oracle, pkg, system):
+    """fasp_solver_dbsr_krylov_amg uses x as the initial guess: starting from the
+    solution of a looser solve must take fewer iterations and reach the same answer."""
+    P, g, IA, JA, val, b = system
+    it, amg = pkg.default_params()
+    x0, st0 = pkg.capi.fasp_solver_dbsr_krylov_amg(IA, JA, val, b, it, amg)
+    assert st0 > 0
+    it2, amg2 = pkg.default_params(tol=1e-10)
+    x_cold, st_cold = pkg.capi.fasp_solver_dbsr_krylov_amg(IA, JA, val, b, it2, amg2)
+    x_warm, st_warm = pkg.capi.fasp_solver_dbsr_krylov_amg(IA, JA, val, b, it2, amg2, x0=x0)
+    assert 0 < st_warm < st_cold
+    assert np.linalg.norm(b - oracle.bsr_spmv(IA, JA, val, x_warm)) <= 1.0001 * it2.tol * np.linalg.norm(b)
+    assert np.abs(x_warm - x_cold).max() <= 1e-7 * np.abs(x_cold).max()
