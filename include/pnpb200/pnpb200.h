@@ -105,6 +105,19 @@ int  pnpb200_test_solver(pnpb200_handle* h, const double* target, double* x,
 int  pnpb200_newton_step(pnpb200_handle* h, const itsolver_param* itparam, const AMG_param* amgparam,
                          int* krylov_status_its, double* l2, double* linf);
 
+/* Damped Newton of the diode benchmark (benchmarks/pnp_diode/pnp_newton_solver.h:195-284)
+ * without host round trips of the solution: every iterate that loop evaluates is
+ * base + alpha * update (full step, growth-limited step, the <= 50 backtracking steps).
+ *   pnpb200_solve_update   Linear_PNP::fasp_solve without the update: assembles J and the residual at the
+ *                          current solution, solves J du = b (du stays on the device), remembers the solution
+ *                          as `base`. *krylov_status as in pnpb200_solve.
+ *   pnpb200_update_ranges  ranges6 = {min, max} of base, of du and of base + du (:220-237, all ranks)
+ *   pnpb200_trial_residual solution <- base + alpha * du, then PDE::compute_residual there (:217, :258-268):
+ *                          one residual-only pass, the l2 and max norms in one sweep */
+int  pnpb200_solve_update(pnpb200_handle* h, const itsolver_param* itparam, const AMG_param* amgparam, int* krylov_status_its);
+int  pnpb200_update_ranges(pnpb200_handle* h, double* ranges6);
+int  pnpb200_trial_residual(pnpb200_handle* h, double alpha, double* l2, double* linf);
+
 /* Post-processing on the device. Error::compute_l2_error / compute_h1_error
  * (src/error.cpp:58-103) against the NODAL interpolant `exact[3*Nv]` of the exact solution, summed
  * over the three components: l2 = sqrt(sum_k int e_k^2), h1 = sqrt(l2^2 + sum_k int |grad e_k|^2).

@@ -125,6 +125,9 @@ def lib():
     L.pnpb200_newton_step.argtypes = [H, C.POINTER(itsolver_param), C.POINTER(AMG_param), C.POINTER(C.c_int),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pnpb200_set_hierarchy_reuse.argtypes = [H, C.c_int]
+    L.pnpb200_solve_update.argtypes = [H, C.POINTER(itsolver_param), C.POINTER(AMG_param), C.POINTER(C.c_int)]
+    L.pnpb200_update_ranges.argtypes = [H, _f8]
+    L.pnpb200_trial_residual.argtypes = [H, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pnpb200_set_sweep_shortcuts.argtypes = [H, C.c_int]
     L.pnpb200_error_norms.argtypes = [H, _f8, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pnpb200_total_charge.argtypes = [H, _f8]
@@ -368,6 +371,21 @@ class PNP:
         m = np.zeros(self.nc, dtype=np.uint8); cnt = C.c_long(); used = C.c_double()
         _check(self.L.pnpb200_mark_cells(self.h, float(tol), int(target_size), m, C.byref(cnt), C.byref(used)), "mark_cells")
         return m.astype(bool), cnt.value, used.value
+
+    def solve_update(self, it, amg=None):
+        st = C.c_int()
+        _check(self.L.pnpb200_solve_update(self.h, C.byref(it), C.byref(amg) if amg is not None else None, C.byref(st)), "solve_update")
+        return st.value
+
+    def update_ranges(self):
+        r = np.zeros(6)
+        _check(self.L.pnpb200_update_ranges(self.h, r), "update_ranges")
+        return (r[0], r[1]), (r[2], r[3]), (r[4], r[5])
+
+    def trial_residual(self, alpha):
+        a, b = C.c_double(), C.c_double()
+        _check(self.L.pnpb200_trial_residual(self.h, float(alpha), C.byref(a), C.byref(b)), "trial_residual")
+        return a.value, b.value
 
     def set_hierarchy_reuse(self, on):
         _check(self.L.pnpb200_set_hierarchy_reuse(self.h, 1 if on else 0), "set_hierarchy_reuse")

@@ -15,6 +15,7 @@
 #include "internal.hpp"
 #include "fem.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
 
 namespace pnpb200 {
 
@@ -524,6 +525,65 @@ long mark_cells(Handle& h, const double* d_eta, double tol, long target_size, un
   PNP_CUDA(cudaStreamSynchronize(s));
   if (tol_used) *tol_used = tol;
   return (long)hc;
+}
+
+// ---- damped Newton of the diode benchmark (benchmarks/pnp_diode/pnp_newton_solver.h:220-268) ----
+// ranges of the previous solution, of the update and of their sum (growth limiting), and the trial
+// iterate base + alpha * du of the backtracking loop, without leaving the device
+__global__ void __launch_bounds__(256)
+ranges_kernel(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ partial)
+{
+  __shared__ double sm[32];
+  double v[6] = {1e300, -1e300, 1e300, -1e300, 1e300, -1e300};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double x = a[i], y = b[i], z = x + y;
+    v[0] = fmin(v[0], x); v[1] = fmax(v[1], x); v[2] = fmin(v[2], y); v[3] = fmax(v[3], y); v[4] = fmin(v[4], z); v[5] = fmax(v[5], z);
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    double r = (q & 1) ? v[q] : -v[q];                       // min as max of the negation (values of any sign)
+    r = warp_max(r);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = sm[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sm[w]);
+      partial[(size_t)blockIdx.x * 6 + q] = m;
+    }
+  }
+}
+__global__ void ranges_final_kernel(int nblk, const double* __restrict__ partial, double* __restrict__ out)
+{
+  const int q = threadIdx.x;
+  if (q >= 6) return;
+  double m = partial[q];
+  for (int b = 1; b < nblk; ++b) m = fmax(m, partial[(size_t)b * 6 + q]);
+  out[q] = m;                                                // entries 0, 2, 4 hold -min
+}
+__global__ void trial_kernel(size_t n, const double* __restrict__ base, const double* __restrict__ du, double alpha, double* __restrict__ uu)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) uu[i] = base[i] + alpha * du[i];
+}
+
+void update_ranges(Handle& h, const double* a, const double* b, size_t n, double* out6)
+{
+  cudaStream_t s = h.stream;
+  const int nblk = (int)std::min<size_t>(592, (n + 255) / 256 ? (n + 255) / 256 : 1);
+  h.red.alloc((size_t)nblk * 6 + 8, s);
+  ranges_kernel<<<nblk, 256, 0, s>>>(n, a, b, h.red.p + 8); PNP_COUNT_LAUNCH();
+  ranges_final_kernel<<<1, 32, 0, s>>>(nblk, h.red.p + 8, h.red.p); PNP_COUNT_LAUNCH();
+  comm_allreduce(h, h.red.p, 6, true);
+  PNP_CUDA(cudaMemcpyAsync(h.h_red, h.red.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  for (int q = 0; q < 6; ++q) out6[q] = (q & 1) ? h.h_red[q] : -h.h_red[q];
+}
+
+void set_trial(Handle& h, double alpha)
+{
+  const size_t n = owned_dofs(h);
+  trial_kernel<<<592, 256, 0, h.stream>>>(n, h.uu_base.p, h.du.p, alpha, h.uu.p); PNP_COUNT_LAUNCH();
+  h.rhs_current = false;
 }
 
 void error_norms(Handle& h, const double* d_exact, double* l2, double* h1)

@@ -445,6 +445,58 @@ int pnpb200_newton_step(pnpb200_handle* ph, const itsolver_param* it, const AMG_
   });
 }
 
+int pnpb200_solve_update(pnpb200_handle* ph, const itsolver_param* it, const AMG_param* amg, int* krylov_status)
+{
+  if (!ph || !it) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    g_launches = 0;
+    halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
+    { EventSpan e(h, h.stats.ms_assemble); assemble_system(h); e.stop(); }
+    int st = 0;
+    solve_current(h, it, amg, &st);
+    if (krylov_status) *krylov_status = st;
+    const size_t N = 3 * (size_t)h.nv;
+    h.uu_base.alloc(N, s);
+    vec_copy(h.uu_base.p, h.uu.p, N, s);
+    h.have_update = true;
+    h.stats.launches = g_launches;
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_update_ranges(pnpb200_handle* ph, double* ranges6)
+{
+  if (!ph || !ranges6) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaSetDevice(h.device));
+    if (!h.have_update) throw Error(ERROR_INPUT_PAR, "call pnpb200_solve_update first");
+    update_ranges(h, h.uu_base.p, h.du.p, owned_dofs(h), ranges6);
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_trial_residual(pnpb200_handle* ph, double alpha, double* l2, double* linf)
+{
+  if (!ph) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaSetDevice(h.device));
+    if (!h.have_update) throw Error(ERROR_INPUT_PAR, "call pnpb200_solve_update first");
+    g_launches = 0;
+    set_trial(h, alpha);
+    halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
+    double a = 0, b = 0;
+    { EventSpan e(h, h.stats.ms_residual); assemble_residual(h, h.rhs, &a, &b); e.stop(); }
+    if (l2) *l2 = a;
+    if (linf) *linf = b;
+    h.stats.launches = g_launches;
+    return FASP_SUCCESS;
+  });
+}
+
 int pnpb200_error_norms(pnpb200_handle* ph, const double* exact, double* l2_error, double* h1_error)
 {
   if (!ph || !exact || !l2_error || !h1_error) return ERROR_INPUT_PAR;

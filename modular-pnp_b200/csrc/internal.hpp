@@ -148,6 +148,8 @@ struct Handle {
   DevBuf<int> v2c_ptr, v2c_idx; // vertex -> incident cells (ascending)
   // coefficients / state (dof order 3*v + k)
   DevBuf<double> eps, fixed, diff, val, reac, uu, du, rhs;
+  DevBuf<double> uu_base;       // solution the last pnpb200_solve_update started from (damped Newton: trial = base + alpha du)
+  bool have_update = false;
   DevBuf<unsigned char> bcflag; // 3*nv
   double q_eafe[3] = {0, 0, 0}; // valency function at dofs 0..2 (linear_pnp.cpp:220-224)
   bool have_coef = false;
@@ -199,6 +201,9 @@ void assemble_system(Handle& h);                   // J (BSR-T) and rhs
 void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf);
 void error_norms(Handle& h, const double* d_exact, double* l2, double* h1);   // src/error.cpp:58-103
 void total_charge(Handle& h, double* d_out);                                  // linear_pnp.cpp:322-351
+// min / max over the first n entries of a, of b and of a + b (out[6] on the host; all ranks' owned dofs)
+void update_ranges(Handle& h, const double* a, const double* b, size_t n, double* out6);
+void set_trial(Handle& h, double alpha);                                      // uu = uu_base + alpha * du
 void entropy_indicator(Handle& h, double* d_eta);                             // src/mesh_refiner.cpp:212-271
 long mark_cells(Handle& h, const double* d_eta, double tol, long target_size, unsigned char* d_marker, double* tol_used);
 // ---- bsr_ops.cu

@@ -68,3 +68,107 @@ def exact_solution_fields(x):
     return dict(eps=np.full(nv, perm), fixed=-perm * dds[:, 0] - (np.exp(s[:, 1]) - np.exp(s[:, 2])),
                 diff=np.ascontiguousarray(np.tile(D, nv)), val=np.ascontiguousarray(np.tile(np.array([0.0, 1.0, -1.0]), nv)),
                 reac=np.ascontiguousarray(reac.ravel()), uu0=np.ascontiguousarray(init.ravel()), exact=np.ascontiguousarray(s.ravel()))
+
+
+# ---- pnp_diode (BASELINE configs[1]): benchmarks/pnp_diode/diode.h ------------------------------
+_Q = 1.60217662e-19; _KB = 1.38064852e-23; _T = 3e+2
+DIODE_BETA = _Q / (_T * _KB)                       # thermodynamic_beta, diode.h:17
+_EPS0 = 8.854187817e-12
+_REF_LEN = 1e-5; _REF_DENS = 1.5e+22; _REF_DIFF = 2.87e+1; _REF_PERM = 1.17e+1
+DIODE_PERMITTIVITY_FACTOR = _REF_PERM * _EPS0 / (_Q * DIODE_BETA * _REF_DENS * _REF_LEN * _REF_LEN)   # diode.h:25-26
+DIODE_POISSON_SCALE = 1.0 / DIODE_PERMITTIVITY_FACTOR    # Poisson_Scale_Expression, diode.h:132-137 (the interpolated
+                                                         # function overrides the constant of pnp_newton_solver.h:60)
+_MAJ = 1.5e+22; _MIN = 6.6e+9
+
+
+def diode_contacts(voltage_drop):
+    """left_contact / right_contact (diode.h:66-79): (phi, log c1, log c2) at x = -1 and x = +1"""
+    left = np.array([0.5 * voltage_drop * DIODE_BETA, np.log(_MIN / _REF_DENS), np.log(_MAJ / _REF_DENS)])
+    right = np.array([-0.5 * voltage_drop * DIODE_BETA, np.log(_MAJ / _REF_DENS), np.log(_MIN / _REF_DENS)])
+    return left, right
+
+
+def diode_fields(x, voltage_drop):
+    """Coefficients and initial guess of the diode benchmark for a list of vertex x-coordinates:
+    dict(eps, fixed, diff, val, reac, uu0) in dof order 3*v+k (diode.h:36-64, Initial_Guess :84-116)."""
+    x = np.asarray(x, dtype=np.float64)
+    nv = x.shape[0]
+    junction = np.abs(x) < 0.05
+    ramp = 10.0 * (x + 0.05)
+    d1 = np.where(x < 0.0, 1.07e+1, 1.09e+1); d2 = np.where(x < 0.0, 2.69e+1, 2.87e+1)
+    d1 = np.where(junction, 1.07e+1 + ramp * (1.09e+1 - 1.07e+1), d1) / _REF_DIFF
+    d2 = np.where(junction, 2.69e+1 + ramp * (2.87e+1 - 2.69e+1), d2) / _REF_DIFF
+    fixed = np.where(x < 0.0, _MAJ, -_MAJ)
+    fixed = np.where(junction, _MAJ + ramp * (-2.0 * _MAJ), fixed) / _REF_DENS
+    left, right = diode_contacts(voltage_drop)
+    lin = 0.5 * (left[None, :] * (1.0 - x)[:, None] + right[None, :] * (x + 1.0)[:, None])
+    uu0 = lin.copy()
+    for k in (1, 2):
+        step = np.where(x < 0.0, left[k], right[k])
+        step = np.where(junction, left[k] + ramp * (right[k] - left[k]), step)
+        uu0[:, k] = 0.5 * lin[:, k] + 0.5 * step
+    diff = np.zeros((nv, 3)); diff[:, 1] = d1; diff[:, 2] = d2
+    return dict(eps=np.full(nv, 1.0), fixed=np.ascontiguousarray(fixed), diff=np.ascontiguousarray(diff.ravel()),
+                val=np.ascontiguousarray(np.tile(np.array([0.0, 1.0, -1.0]), nv)), reac=np.zeros(3 * nv),
+                uu0=np.ascontiguousarray(uu0.ravel()))
+
+
+class NewtonStatus:
+    """src/newton_status.cpp:11-74"""
+
+    def __init__(self, max_iterations, initial_residual, relative_tol, max_tol):
+        self.iteration = 1; self.max_iterations = max_iterations
+        self.initial_residual = initial_residual; self.relative_residual = 1.0
+        self.max_residual = None; self.relative_tol = relative_tol; self.max_tol = max_tol
+
+    def needs_to_iterate(self):
+        return (self.iteration < self.max_iterations + 1 and self.relative_residual > self.relative_tol
+                and self.max_residual > self.max_tol)
+
+    def converged(self):
+        return not (self.iteration > self.max_iterations) and (self.relative_residual < self.relative_tol
+                                                               or self.max_residual < self.max_tol)
+
+
+def damped_newton(backend, uu0, max_newton=250, rel_tol=1e-7, max_tol=1e-10, log=None):
+    """The diode benchmark's Newton loop with growth limiting and residual backtracking
+    (benchmarks/pnp_diode/pnp_newton_solver.h:171-284), on a backend that offers
+        n_dofs, set_solution(uu), residual() -> (l2, max), solve() -> status (Newton update du from the
+        current solution; the solution is NOT changed), ranges() -> (min/max of the solution, of du and
+        of solution + du), trial(alpha) -> (l2, max) of the residual at solution_base + alpha * du.
+    Every trial iterate is base + alpha * du, so the <= 50 backtracking evaluations per step are
+    residual-only passes. Returns (history, converged): history rows (krylov status, alpha, relative
+    residual, max residual, backtracks)."""
+    N = float(backend.n_dofs)
+    backend.set_solution(uu0)
+    l2, mx = backend.residual()
+    newton = NewtonStatus(max_newton, l2 / N, rel_tol, max_tol)
+    newton.max_residual = mx
+    hist, fails = [], 0
+    while newton.needs_to_iterate():
+        previous_residual = backend.residual()[0] / N
+        status = backend.solve()
+        if status < 0:
+            fails += 1
+            if fails > 10:
+                break
+        (pmin, pmax), (umin, umax), (cmin, cmax) = backend.ranges()
+        alpha = 1.0
+        residual_check = backend.trial(1.0)[0] / N          # the reference applies the full update first (:200, :217)
+        prev_range = pmax - pmin + 1e-12
+        if (cmax - cmin) > 1.1 * prev_range:                 # :229-252, increase_tolerance = 0.1
+            alpha = 0.1 * prev_range / (umax - umin + 1e-12)
+            if alpha * umax > alpha * umin + 0.1 * prev_range:
+                alpha *= (alpha * umax - alpha * umin) * 0.1 * 1e-4
+        k = 0
+        while k < 50 and (residual_check > 1.00001 * previous_residual or residual_check != residual_check):
+            k += 1
+            residual_check = backend.trial(alpha * 0.5 ** k)[0] / N      # :256-268
+        l2, mx = backend.residual()
+        newton.relative_residual = (l2 / N) / newton.initial_residual
+        newton.max_residual = mx
+        newton.iteration += 1
+        hist.append((status, alpha * 0.5 ** k if k else 1.0, newton.relative_residual, mx, k))
+        if log:
+            log(hist[-1])
+    return hist, newton.converged()

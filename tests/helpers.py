@@ -149,3 +149,72 @@ def manufactured_sources(O, P, uu_star):
     reac = np.zeros(P.N)
     reac[1::3] = -lu.solve(r[1::3]); reac[2::3] = -lu.solve(r[2::3])
     return fixed, reac
+
+
+class OracleNewtonBackend:
+    """damped_newton backend (modular-pnp_b200/problems.py) on the CPU oracle: assemble + restated
+    FASP BSR-AMG FGMRES for the update, residual-only evaluations for the trial iterates."""
+
+    def __init__(self, O, P, prm, use_eafe=True):
+        self.O, self.P, self.prm, self.use_eafe = O, P, prm, use_eafe
+        self.n_dofs = P.N
+        self.uu = None; self.base = None; self.du = None
+
+    def set_solution(self, uu):
+        self.uu = np.ascontiguousarray(uu, dtype=np.float64).copy()
+
+    def residual(self):
+        _, l2, mx = self.P.residual(self.uu)
+        return l2, mx
+
+    def solve(self):
+        A, b = self.P.assemble(self.uu, self.use_eafe)
+        dx, its = self.O.solver_dbsr_krylov_amg(self.P.IA, self.P.JA, A, b, self.prm)
+        self.base = self.uu.copy(); self.du = dx
+        return its
+
+    def ranges(self):
+        c = self.base + self.du
+        return (self.base.min(), self.base.max()), (self.du.min(), self.du.max()), (c.min(), c.max())
+
+    def trial(self, alpha):
+        self.uu = self.base + alpha * self.du
+        return self.residual()
+
+
+def diode_problem(O, nx=40, ny=4, nz=4, voltage=0.1):
+    """oracle.Problem carrying the pnp_diode physics (benchmarks/pnp_diode/diode.h, domain.dat 40x4x4
+    on 2 x 0.2 x 0.2); the caller switches the form variant (poisson_scale, exp cutoff) on and off"""
+    import sys
+    from importlib import import_module
+    from pnpb200_loader import load_package
+    load_package()
+    pr = import_module("modular_pnp_b200.problems")
+    P = O.Problem(nx, ny, nz, 2.0, 0.2, 0.2)
+    f = pr.diode_fields(P.xyz[0::3], voltage)
+    P.eps, P.fixed, P.diff, P.val, P.reac, P.uu0 = f["eps"], f["fixed"], f["diff"], f["val"], f["reac"], f["uu0"]
+    return P, pr
+
+
+class GpuNewtonBackend:
+    """damped_newton backend on the device-resident fast path of the C ABI: pnpb200_solve_update /
+    pnpb200_update_ranges / pnpb200_trial_residual (the solution never returns to the host)."""
+
+    def __init__(self, g, it, amg):
+        self.g, self.it, self.amg = g, it, amg
+        self.n_dofs = g.N
+
+    def set_solution(self, uu):
+        self.g.set_solution(np.ascontiguousarray(uu, dtype=np.float64))
+
+    def residual(self):
+        return self.g.residual()
+
+    def solve(self):
+        return self.g.solve_update(self.it, self.amg)
+
+    def ranges(self):
+        return self.g.update_ranges()
+
+    def trial(self, alpha):
+        return self.g.trial_residual(alpha)

@@ -255,3 +255,25 @@ def test_entropy_indicator_matches_reference_golden(oracle):
     eta = P.entropy_indicator(uu)
     expect = P.diff[1] * np.exp(-0.3) * (0.7 * P.val[1]) ** 2 + P.diff[2] * np.exp(0.4) * (0.7 * P.val[2]) ** 2
     assert eta.shape == (P.nc,) and np.abs(eta - expect).max() <= 1e-12 * expect
+
+
+def test_diode_damped_newton_on_the_oracle(oracle):
+    """pnp_diode physics (benchmarks/pnp_diode/diode.h) + the benchmark's damped Newton
+    (pnp_newton_solver.h:195-284) on the CPU oracle at zero bias: growth-limited first steps with one
+    backtrack each, then full steps, converged to the benchmark's tolerances (rel 1e-7)."""
+    from helpers import OracleNewtonBackend, diode_problem
+    P, pr = diode_problem(oracle, 40, 4, 4, 0.0)
+    left, right = pr.diode_contacts(0.0)
+    x = P.xyz[0::3]
+    assert np.allclose(P.uu0.reshape(-1, 3)[np.abs(x + 1) < 1e-12], left) and np.allclose(P.uu0.reshape(-1, 3)[np.abs(x - 1) < 1e-12], right)
+    assert abs(pr.DIODE_BETA - 38.6817) < 1e-3 and abs(P.fixed[np.argmin(x)] - 1.0) < 1e-15 and abs(P.fixed[np.argmax(x)] + 1.0) < 1e-15
+    prm = oracle.default_param(maxit=500)
+    oracle.set_form_variant(pr.DIODE_POISSON_SCALE, True)
+    try:
+        hist, conv = pr.damped_newton(OracleNewtonBackend(oracle, P, prm), P.uu0, max_newton=60)
+    finally:
+        oracle.set_form_variant(1.0, False)
+    assert conv and 20 <= len(hist) <= 40
+    assert all(h[0] > 0 for h in hist)
+    assert hist[0][1] < 1e-6 and hist[0][4] == 1            # the first update is cut back by the growth limit
+    assert hist[-1][1] == 1.0 and hist[-1][2] < 1e-7        # full steps at the end
