@@ -156,6 +156,23 @@ typedef struct Schwarz_param {
   SHORT print_level, Schwarz_type; INT Schwarz_maxlvl, Schwarz_mmsize, Schwarz_blksolver;
 } Schwarz_param;
 
+/* ---- fasp4ns parameter blocks (benchmarks/pnp_stokes/main.cpp:78-86). fasp4ns is not in the
+ *      reference tree; the reference only declares these, fills them with fasp_ns_param_input /
+ *      fasp_ns_param_init and passes them on by value (linear_pnp_ns.cpp:52-56,183-193), so their
+ *      layout is private to this library: three FASP parameter sets — the outer Stokes iteration,
+ *      the velocity block (keys ending in _v in ns.dat) and the pressure block (_p). */
+typedef struct input_ns_param { input_param ns, v, p; } input_ns_param;
+typedef struct itsolver_ns_param {
+  SHORT itsolver_type, precond_type, stop_type;
+  INT   maxit;
+  REAL  tol;
+  INT   restart;
+  SHORT print_level;
+  SHORT itsolver_type_v, precond_type_v; INT pre_maxit_v; REAL pre_tol_v; INT pre_restart_v;
+  SHORT itsolver_type_p, precond_type_p; INT pre_maxit_p; REAL pre_tol_p; INT pre_restart_p;
+} itsolver_ns_param;
+typedef struct AMG_ns_param { AMG_param param_v, param_p; } AMG_ns_param;
+
 /* ---- parameter input (benchmarks/pnp_exact_solution/main.cpp:170-177) */
 void  fasp_param_input(const char *filenm, input_param *inparam);
 void  fasp_param_input_init(input_param *inparam);
@@ -163,6 +180,10 @@ void  fasp_param_init(const input_param *inparam, itsolver_param *itsparam, AMG_
                       ILU_param *iluparam, Schwarz_param *schparam);
 void  fasp_param_solver_init(itsolver_param *itsparam);
 void  fasp_param_amg_init(AMG_param *amgparam);
+/* benchmarks/pnp_stokes/main.cpp:85-86 (fasp4ns): ns.dat = outer / _v / _p parameter sets */
+void  fasp_ns_param_input(const char *filenm, input_ns_param *inparam);
+void  fasp_ns_param_init(input_ns_param *inparam, itsolver_ns_param *itsparam, AMG_ns_param *amgparam,
+                         ILU_param *iluparam, Schwarz_param *schparam);
 
 /* ---- format conversion (linear_pnp.cpp:85): CSR -> BSR(nb), device kernels, returns by value */
 dBSRmat fasp_format_dcsr_dbsr(const dCSRmat *A, const INT nb);
@@ -180,6 +201,20 @@ INT fasp_solver_dcsr_krylov(dCSRmat *A, dvector *b, dvector *x, itsolver_param *
  * benchmarks/pnp_diode/linear_pnp.cpp:162); documented deviation, see DESIGN.md */
 INT fasp_solver_dbsr_krylov_ilu(dBSRmat *A, dvector *b, dvector *x, itsolver_param *itparam,
                                 ILU_param *iluparam);
+
+/* benchmarks/pnp_stokes/linear_pnp_ns.cpp:183-193 (fasp4ns) — the coupled PNP-Stokes system as a
+ * 2x2 block_dCSRmat {A_pp, A_ps, A_sp, A_ss} (PNP dofs interleaved 3 per vertex; Stokes dofs =
+ * num_velocity velocity dofs followed by num_pressure pressure dofs, linear_pnp_ns.cpp:69-107).
+ * All on the GPU: outer FGMRES (itparam) with the block upper-triangular preconditioner
+ * (bcsr.dat precond_type 33): Stokes block by FGMRES (itparam_stokes) preconditioned with an AMG
+ * cycle on the velocity block and the diagonal SIMPLE Schur complement on the pressure, then the
+ * PNP block by the BSR(3) AMG-FGMRES solve of fasp_solver_dbsr_krylov_amg (itparam_pnp,
+ * amgparam_pnp). b, x ordered [PNP; velocity; pressure]; x in/out (initial guess). Returns the
+ * outer iteration count >= 0 or ERROR_* < 0 (x = last iterate). DESIGN.md §2 f-2. */
+INT fasp_solver_bdcsr_krylov_pnp_stokes(block_dCSRmat *A, dvector *b, dvector *x, itsolver_param *itparam,
+                                        itsolver_param *itparam_pnp, AMG_param *amgparam_pnp,
+                                        itsolver_ns_param *itparam_stokes, AMG_ns_param *amgparam_stokes,
+                                        const INT num_velocity, const INT num_pressure);
 
 /* ---- BLAS-level entry used by Linear_PNP::fasp_test_solver's callers (GPU) */
 void fasp_blas_dbsr_mxv(const dBSRmat *A, const REAL *x, REAL *y);

@@ -166,6 +166,11 @@ typedef struct pnpb200_stats {
 } pnpb200_stats;
 int  pnpb200_get_stats(const pnpb200_handle* h, pnpb200_stats* s);
 int  pnpb200_set_timing_detail(pnpb200_handle* h, int on);
+/* counters of the calling thread's last fasp_solver_bdcsr_krylov_pnp_stokes call:
+ * out[0] outer iterations, out[1] PNP block solves, out[2] their Krylov iterations in total,
+ * out[3] Stokes block solves, out[4] their Krylov iterations in total; *relres = final true
+ * relative residual of the coupled system */
+int  pnpb200_last_block_solve_stats(int out[5], double* relres);
 /* copy level-l hierarchy pieces to the host (FASP layout): matrix, aggregate map (length
  * level_rows[l], -1 = isolated), GS row order (rows sorted by colour). */
 int  pnpb200_get_level_matrix(pnpb200_handle* h, int level, dBSRmat* A_out);

@@ -70,6 +70,32 @@ class ILU_param(C.Structure):
                 ("ILU_relax", REAL), ("ILU_permtol", REAL)]
 
 
+class Schwarz_param(C.Structure):
+    _fields_ = [("print_level", SHORT), ("Schwarz_type", SHORT), ("Schwarz_maxlvl", INT), ("Schwarz_mmsize", INT),
+                ("Schwarz_blksolver", INT)]
+
+
+class block_dCSRmat(C.Structure):
+    _fields_ = [("brow", INT), ("bcol", INT), ("blocks", C.POINTER(C.POINTER(dCSRmat)))]
+
+
+class input_ns_param(C.Structure):
+    _fields_ = [("ns", input_param), ("v", input_param), ("p", input_param)]
+
+
+class itsolver_ns_param(C.Structure):
+    _fields_ = [("itsolver_type", SHORT), ("precond_type", SHORT), ("stop_type", SHORT), ("maxit", INT), ("tol", REAL),
+                ("restart", INT), ("print_level", SHORT),
+                ("itsolver_type_v", SHORT), ("precond_type_v", SHORT), ("pre_maxit_v", INT), ("pre_tol_v", REAL),
+                ("pre_restart_v", INT),
+                ("itsolver_type_p", SHORT), ("precond_type_p", SHORT), ("pre_maxit_p", INT), ("pre_tol_p", REAL),
+                ("pre_restart_p", INT)]
+
+
+class AMG_ns_param(C.Structure):
+    _fields_ = [("param_v", AMG_param), ("param_p", AMG_param)]
+
+
 class pnpb200_stats(C.Structure):
     _fields_ = [("n_levels", C.c_int), ("level_rows", C.c_int * 32), ("level_nnzb", C.c_int * 32),
                 ("level_colors", C.c_int * 32), ("krylov_its", C.c_int), ("launches", C.c_int),
@@ -167,6 +193,21 @@ def lib():
     L.fasp_solver_dcsr_krylov.argtypes = [C.POINTER(dCSRmat), C.POINTER(dvector), C.POINTER(dvector),
                                           C.POINTER(itsolver_param)]
     L.fasp_solver_dcsr_krylov.restype = INT
+    L.fasp_ns_param_input.argtypes = [C.c_char_p, C.POINTER(input_ns_param)]
+    L.fasp_ns_param_input.restype = None
+    L.fasp_ns_param_init.argtypes = [C.POINTER(input_ns_param), C.POINTER(itsolver_ns_param), C.POINTER(AMG_ns_param),
+                                     C.POINTER(ILU_param), C.POINTER(Schwarz_param)]
+    L.fasp_ns_param_init.restype = None
+    L.fasp_solver_bdcsr_krylov_pnp_stokes.argtypes = [C.POINTER(block_dCSRmat), C.POINTER(dvector), C.POINTER(dvector),
+                                                      C.POINTER(itsolver_param), C.POINTER(itsolver_param),
+                                                      C.POINTER(AMG_param), C.POINTER(itsolver_ns_param),
+                                                      C.POINTER(AMG_ns_param), INT, INT]
+    L.fasp_solver_bdcsr_krylov_pnp_stokes.restype = INT
+    L.pnpb200_last_block_solve_stats.argtypes = [C.POINTER(C.c_int * 5), C.POINTER(C.c_double)]
+    L.fasp_dcsr_getblk.argtypes = [C.POINTER(dCSRmat), _i4, _i4, INT, INT, C.POINTER(dCSRmat)]
+    L.fasp_dcsr_getblk.restype = SHORT
+    L.fasp_dcsr_free.argtypes = [C.POINTER(dCSRmat)]
+    L.fasp_dcsr_free.restype = None
     L.fasp_blas_dbsr_mxv.argtypes = [C.POINTER(dBSRmat), _f8, _f8]
     L.fasp_blas_dbsr_mxv.restype = None
     L.fasp_blas_dbsr_aAxpy.argtypes = [REAL, C.POINTER(dBSRmat), _f8, _f8]
@@ -201,6 +242,55 @@ def default_params(dat_file=None, **overrides):
         else:
             raise KeyError(k)
     return it, amg
+
+
+DEFAULT_BCSR_DAT = os.path.join(_HERE, "host", "bcsr.dat")
+DEFAULT_NS_DAT = os.path.join(_HERE, "host", "ns.dat")
+
+
+def pnp_stokes_params(bcsr_dat=None, bsr_dat=None, ns_dat=None):
+    """The five parameter blocks of benchmarks/pnp_stokes/main.cpp:55-86: outer iteration
+    (bcsr.dat), PNP block (bsr.dat), Stokes block (ns.dat)."""
+    L = lib()
+    inp, it, amg, ilu = input_param(), itsolver_param(), AMG_param(), ILU_param()
+    L.fasp_param_input((bcsr_dat or DEFAULT_BCSR_DAT).encode(), C.byref(inp))
+    L.fasp_param_init(C.byref(inp), C.byref(it), C.byref(amg), C.byref(ilu), None)
+    it_pnp, amg_pnp = default_params(bsr_dat)
+    ns_in, it_ns, amg_ns, ilu_ns, sch_ns = input_ns_param(), itsolver_ns_param(), AMG_ns_param(), ILU_param(), Schwarz_param()
+    L.fasp_ns_param_input((ns_dat or DEFAULT_NS_DAT).encode(), C.byref(ns_in))
+    L.fasp_ns_param_init(C.byref(ns_in), C.byref(it_ns), C.byref(amg_ns), C.byref(ilu_ns), C.byref(sch_ns))
+    return it, it_pnp, amg_pnp, it_ns, amg_ns
+
+
+def numpy_to_csr(IA, JA, val, ncol):
+    """dCSRmat view over numpy arrays (arrays must outlive the struct)."""
+    IA = np.ascontiguousarray(IA, dtype=np.int32); JA = np.ascontiguousarray(JA, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    m = dCSRmat()
+    m.row = len(IA) - 1; m.col = int(ncol); m.nnz = len(JA)
+    m.IA = IA.ctypes.data_as(C.POINTER(INT)); m.JA = JA.ctypes.data_as(C.POINTER(INT))
+    m.val = val.ctypes.data_as(C.POINTER(REAL))
+    m._keep = (IA, JA, val)
+    return m
+
+
+def solve_pnp_stokes(blocks, b, n_vel, n_pres, params=None, x0=None):
+    """fasp_solver_bdcsr_krylov_pnp_stokes on four scipy-CSR-like blocks (objects with indptr,
+    indices, data, shape) [A_pp, A_ps, A_sp, A_ss]; returns (status, x, stats dict)."""
+    L = lib()
+    it, it_pnp, amg_pnp, it_ns, amg_ns = params or pnp_stokes_params()
+    mats = [numpy_to_csr(B.indptr, B.indices, B.data, B.shape[1]) for B in blocks]
+    arr = (C.POINTER(dCSRmat) * 4)(*[C.pointer(m) for m in mats])
+    A = block_dCSRmat(); A.brow = A.bcol = 2; A.blocks = C.cast(arr, C.POINTER(C.POINTER(dCSRmat)))
+    x = np.zeros(len(b)) if x0 is None else np.array(x0, dtype=np.float64)
+    bv, xv = numpy_to_dvec(b), numpy_to_dvec(x)
+    st = L.fasp_solver_bdcsr_krylov_pnp_stokes(C.byref(A), C.byref(bv), C.byref(xv), C.byref(it), C.byref(it_pnp),
+                                               C.byref(amg_pnp), C.byref(it_ns), C.byref(amg_ns), int(n_vel), int(n_pres))
+    out, rr = (C.c_int * 5)(), C.c_double()
+    L.pnpb200_last_block_solve_stats(C.byref(out), C.byref(rr))
+    stats = {"outer_its": out[0], "pnp_solves": out[1], "pnp_its": out[2], "stokes_solves": out[3], "stokes_its": out[4],
+             "relres": rr.value}
+    return st, xv._keep, stats
 
 
 def _bsr_to_numpy(m, free=True):

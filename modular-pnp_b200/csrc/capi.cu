@@ -5,6 +5,8 @@
 #include <cstring>
 #include <cmath>
 #include <mutex>
+#include <algorithm>
+#include <memory>
 
 using namespace pnpb200;
 
@@ -801,6 +803,114 @@ INT fasp_solver_dcsr_krylov(dCSRmat* A, dvector* b, dvector* x, itsolver_param* 
   const INT st = solve_host_bsr(&B, b, x, it, nullptr);
   fasp_dbsr_free(&B);
   return st;
+}
+
+// ---- PNP-Stokes block system: benchmarks/pnp_stokes/linear_pnp_ns.cpp:183-193 -------
+namespace {
+thread_local BlockStats g_block_stats;
+
+// host copy of a CSR matrix with the columns of every row ascending. fasp_dcsr_getblk keeps the
+// parent's entry order while it renumbers the columns (linear_pnp_ns.cpp:150-157), so the rows of
+// a block are in general NOT sorted; the CSR -> BSR kernel merges sorted rows. Index permutation
+// only, no arithmetic.
+struct HostCsr {
+  std::vector<INT> ia, ja; std::vector<REAL> val; INT row = 0, col = 0;
+  dCSRmat view() { dCSRmat A; A.row = row; A.col = col; A.nnz = (INT)ja.size(); A.IA = ia.data(); A.JA = ja.data(); A.val = val.data(); return A; }
+};
+// rows [0, nr) and columns [0, ncol) of A, sorted; rows padded with identity rows up to nr_pad
+HostCsr sorted_subblock(const dCSRmat* A, INT nr, INT ncol, INT nr_pad)
+{
+  HostCsr H; H.row = nr_pad; H.col = nr_pad > ncol ? nr_pad : ncol;
+  H.ia.assign((size_t)nr_pad + 1, 0);
+  std::vector<std::pair<INT, REAL>> tmp;
+  for (INT i = 0; i < nr; ++i) {
+    tmp.clear();
+    for (INT k = A->IA[i]; k < A->IA[i + 1]; ++k) {
+      const INT j = A->JA[k];
+      if (j < 0 || j >= A->col) throw Error(ERROR_DATA_STRUCTURE, "block matrix: column index out of range");
+      if (j < ncol) tmp.emplace_back(j, A->val[k]);
+    }
+    std::sort(tmp.begin(), tmp.end(), [](const std::pair<INT, REAL>& x, const std::pair<INT, REAL>& y) { return x.first < y.first; });
+    for (size_t q = 0; q < tmp.size(); ++q) {
+      if (q > 0 && tmp[q].first == tmp[q - 1].first) throw Error(ERROR_DATA_STRUCTURE, "block matrix: duplicate entry in a row");
+      H.ja.push_back(tmp[q].first); H.val.push_back(tmp[q].second);
+    }
+    H.ia[i + 1] = (INT)H.ja.size();
+  }
+  for (INT i = nr; i < nr_pad; ++i) { H.ja.push_back(i); H.val.push_back(1.0); H.ia[i + 1] = (INT)H.ja.size(); }
+  return H;
+}
+} // namespace
+
+INT fasp_solver_bdcsr_krylov_pnp_stokes(block_dCSRmat* A, dvector* b, dvector* x, itsolver_param* itparam,
+                                        itsolver_param* itparam_pnp, AMG_param* amgparam_pnp,
+                                        itsolver_ns_param* itparam_stokes, AMG_ns_param* amgparam_stokes,
+                                        const INT num_velocity, const INT num_pressure)
+{
+  if (!A || !b || !x || !itparam || !itparam_pnp || !amgparam_pnp || !itparam_stokes || !amgparam_stokes) return ERROR_INPUT_PAR;
+  if (A->brow != 2 || A->bcol != 2 || !A->blocks || !b->val || !x->val) return ERROR_INPUT_PAR;
+  for (int k = 0; k < 4; ++k) if (!A->blocks[k]) return ERROR_INPUT_PAR;
+  int status = ERROR_UNKNOWN;
+  g_block_stats = BlockStats();
+  const int rc = guarded([&]() -> int {
+    dCSRmat* App = A->blocks[0]; dCSRmat* Aps = A->blocks[1]; dCSRmat* Asp = A->blocks[2]; dCSRmat* Ass = A->blocks[3];
+    const INT np = App->row, ns = Ass->row, nu = num_velocity, nq = num_pressure;
+    if (np < 3 || np % 3 != 0 || App->col != np) throw Error(ERROR_INPUT_PAR, "PNP block must be square with 3 dofs per vertex");
+    if (nu < 1 || nq < 0 || nu + nq != ns || Ass->col != ns) throw Error(ERROR_INPUT_PAR, "Stokes block size != num_velocity + num_pressure");
+    if (Aps->row != np || Aps->col != ns || Asp->row != ns || Asp->col != np) throw Error(ERROR_INPUT_PAR, "coupling block sizes do not match");
+    if (b->row != np + ns || x->row != np + ns) throw Error(ERROR_INPUT_PAR, "vector / block matrix size mismatch");
+    int dev = 0; cudaGetDevice(&dev);
+    // PNP block -> BSR(3) hierarchy handle (the hot path of this library)
+    HostCsr Hp = sorted_subblock(App, np, np, np);
+    dCSRmat vp = Hp.view();
+    dBSRmat Bp = fasp_format_dcsr_dbsr(&vp, 3);
+    if (!Bp.IA) throw Error(ERROR_DATA_STRUCTURE, "PNP block: CSR -> BSR(3) failed");
+    std::unique_ptr<HostSystem> sysp;
+    try { sysp.reset(new HostSystem(&Bp)); } catch (...) { fasp_dbsr_free(&Bp); throw; }
+    fasp_dbsr_free(&Bp);
+    // velocity block: its scalar dofs grouped in threes, identity rows up to a multiple of 3
+    const INT nup = 3 * ((nu + 2) / 3);
+    HostCsr Hv = sorted_subblock(Ass, nu, nu, nup);
+    dCSRmat vv = Hv.view();
+    dBSRmat Bv = fasp_format_dcsr_dbsr(&vv, 3);
+    if (!Bv.IA) throw Error(ERROR_DATA_STRUCTURE, "velocity block: CSR -> BSR(3) failed");
+    std::unique_ptr<HostSystem> sysv;
+    try { sysv.reset(new HostSystem(&Bv)); } catch (...) { fasp_dbsr_free(&Bv); throw; }
+    fasp_dbsr_free(&Bv);
+    // outer handle: stream, reduction scratch
+    std::unique_ptr<pnpb200_handle> po(new pnpb200_handle);
+    init_handle(po->h, dev);
+    Handle& ho = po->h; cudaStream_t s = ho.stream;
+    {
+      BlockSystem S;
+      S.outer = &ho; S.pnp = &sysp->ph->h; S.vel = &sysv->ph->h;
+      S.np = np; S.ns = ns; S.nu = nu; S.npres = nq;
+      csr_upload(App, S.App, s); csr_upload(Aps, S.Aps, s); csr_upload(Asp, S.Asp, s); csr_upload(Ass, S.Ass, s);
+      S.cfg_outer = make_config(itparam, nullptr);
+      S.cfg_pnp = make_config(itparam_pnp, amgparam_pnp);
+      itsolver_param its_ns;
+      its_ns.itsolver_type = itparam_stokes->itsolver_type; its_ns.precond_type = itparam_stokes->precond_type;
+      its_ns.stop_type = itparam_stokes->stop_type; its_ns.maxit = itparam_stokes->maxit; its_ns.tol = itparam_stokes->tol;
+      its_ns.restart = itparam_stokes->restart; its_ns.print_level = itparam_stokes->print_level;
+      S.cfg_ns = make_config(&its_ns, nullptr);
+      S.cfg_vel = make_config(nullptr, &amgparam_stokes->param_v);
+      DevBuf<double> db, dx; db.alloc((size_t)np + ns, s); dx.alloc((size_t)np + ns, s);
+      db.upload(b->val, (size_t)np + ns); dx.upload(x->val, (size_t)np + ns);
+      status = block_pnp_stokes_solve(S, db.p, dx.p, &g_block_stats);
+      dx.download(x->val, (size_t)np + ns);
+      PNP_CUDA(cudaStreamSynchronize(s));
+    }
+    return FASP_SUCCESS;
+  });
+  return rc < 0 ? rc : status;
+}
+
+int pnpb200_last_block_solve_stats(int out[5], double* relres)
+{
+  if (out) { out[0] = g_block_stats.outer_its; out[1] = g_block_stats.pnp_solves; out[2] = g_block_stats.pnp_its;
+             out[3] = g_block_stats.stokes_solves; out[4] = g_block_stats.stokes_its; }
+  if (relres) *relres = g_block_stats.relres;
+  return FASP_SUCCESS;
 }
 
 // ---- multi-GPU bootstrap: implemented in comm.cu -----------------------------------------------

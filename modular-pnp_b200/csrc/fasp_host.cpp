@@ -136,22 +136,15 @@ void fasp_param_input_init(input_param* in)
 
 static bool on_off(const std::string& v) { return v == "ON" || v == "on" || v == "On"; }
 
-void fasp_param_input(const char* filenm, input_param* in)
+} // extern "C"
+
+// one `key = value` pair into an input_param: 0 = taken, 1 = bad value, 2 = unknown key
+static int set_key(input_param* in, const char* key, const char* val)
 {
-  fasp_param_input_init(in);
-  FILE* fp = fopen(filenm, "r");
-  if (!fp) { fprintf(stderr, "### ERROR: %s cannot be opened\n", filenm); fasp_chkerr(ERROR_OPEN_FILE, "fasp_param_input"); return; }
-  strncpy(in->inifile, filenm, sizeof(in->inifile) - 1);
-  char line[1024];
+  const std::string k(key), v(val);
   bool bad = false;
-  while (fgets(line, sizeof line, fp)) {
-    char key[512], eq[16], val[512];
-    if (sscanf(line, "%511s", key) != 1) continue;
-    if (key[0] == '%' || key[0] == '[' || key[0] == '|' || key[0] == '#') continue;
-    if (sscanf(line, "%511s %15s %511s", key, eq, val) != 3 || strcmp(eq, "=") != 0) { bad = true; continue; }
-    const std::string k(key), v(val);
-    auto I = [&]() { return atoi(val); };
-    auto R = [&]() { return atof(val); };
+  auto I = [&]() { return atoi(val); };
+  auto R = [&]() { return atof(val); };
     if (k == "workdir") strncpy(in->workdir, val, sizeof(in->workdir) - 1);
     else if (k == "problem_num") in->problem_num = I();
     else if (k == "print_level") in->print_level = (SHORT)I();
@@ -226,13 +219,88 @@ void fasp_param_input(const char* filenm, input_param* in)
     else if (k == "AMG_strong_coupled") in->AMG_strong_coupled = R();
     else if (k == "AMG_max_aggregation") in->AMG_max_aggregation = I();
     else if (k == "AMG_tentative_smooth") in->AMG_tentative_smooth = R();
-    else { /* unknown keys are ignored with a note, like upstream */
-      fprintf(stderr, "### WARNING: Unknown input keyword %s!\n", key);
-    }
+    else return 2;
+  return bad ? 1 : 0;
+}
+
+// shared reader: every non-comment `key = value` line goes to sink(key, value); false on a malformed line
+template <typename F>
+static bool read_dat(const char* filenm, const char* who, F&& sink)
+{
+  FILE* fp = fopen(filenm, "r");
+  if (!fp) { fprintf(stderr, "### ERROR: %s cannot be opened\n", filenm); fasp_chkerr(ERROR_OPEN_FILE, who); return false; }
+  char line[1024];
+  bool ok = true;
+  while (fgets(line, sizeof line, fp)) {
+    char key[512], eq[16], val[512];
+    if (sscanf(line, "%511s", key) != 1) continue;
+    if (key[0] == '%' || key[0] == '[' || key[0] == '|' || key[0] == '#') continue;
+    if (sscanf(line, "%511s %15s %511s", key, eq, val) != 3 || strcmp(eq, "=") != 0) { ok = false; continue; }
+    if (!sink(key, val)) ok = false;
   }
   fclose(fp);
-  if (bad || in->itsolver_tol <= 0 || in->itsolver_maxit <= 0 || in->AMG_levels < 0 || in->AMG_coarse_dof <= 0)
-    fasp_chkerr(ERROR_INPUT_PAR, "fasp_param_input");
+  return ok;
+}
+
+static bool params_sane(const input_param* in)
+{
+  return !(in->itsolver_tol <= 0 || in->itsolver_maxit <= 0 || in->AMG_levels < 0 || in->AMG_coarse_dof <= 0);
+}
+
+extern "C" {
+
+void fasp_param_input(const char* filenm, input_param* in)
+{
+  fasp_param_input_init(in);
+  strncpy(in->inifile, filenm, sizeof(in->inifile) - 1);
+  const bool ok = read_dat(filenm, "fasp_param_input", [&](const char* key, const char* val) {
+    const int rc = set_key(in, key, val);
+    if (rc == 2) fprintf(stderr, "### WARNING: Unknown input keyword %s!\n", key);   // ignored with a note, like upstream
+    return rc != 1;
+  });
+  if (!ok || !params_sane(in)) fasp_chkerr(ERROR_INPUT_PAR, "fasp_param_input");
+}
+
+// benchmarks/pnp_stokes/main.cpp:85: ns.dat holds three parameter sets in one file — the outer
+// Stokes iteration (plain keys), the velocity block (keys ending in _v) and the pressure block (_p)
+void fasp_ns_param_input(const char* filenm, input_ns_param* in)
+{
+  fasp_param_input_init(&in->ns); fasp_param_input_init(&in->v); fasp_param_input_init(&in->p);
+  strncpy(in->ns.inifile, filenm, sizeof(in->ns.inifile) - 1);
+  const bool ok = read_dat(filenm, "fasp_ns_param_input", [&](const char* key, const char* val) {
+    std::string k(key);
+    input_param* dst = &in->ns;
+    if (k.size() > 2 && k.compare(k.size() - 2, 2, "_v") == 0) { dst = &in->v; k.resize(k.size() - 2); }
+    else if (k.size() > 2 && k.compare(k.size() - 2, 2, "_p") == 0) { dst = &in->p; k.resize(k.size() - 2); }
+    const int rc = set_key(dst, k.c_str(), val);
+    if (rc == 2) fprintf(stderr, "### WARNING: Unknown input keyword %s!\n", key);
+    return rc != 1;
+  });
+  in->v.print_level = in->p.print_level = in->ns.print_level;
+  if (!ok || !params_sane(&in->ns) || !params_sane(&in->v) || !params_sane(&in->p)) fasp_chkerr(ERROR_INPUT_PAR, "fasp_ns_param_input");
+}
+
+// benchmarks/pnp_stokes/main.cpp:86
+void fasp_ns_param_init(input_ns_param* in, itsolver_ns_param* its, AMG_ns_param* amg, ILU_param* ilu, Schwarz_param* sch)
+{
+  if (its) {
+    memset(its, 0, sizeof(*its));
+    itsolver_param t;
+    fasp_param_init(in ? &in->ns : nullptr, &t, nullptr, nullptr, nullptr);
+    its->itsolver_type = t.itsolver_type; its->precond_type = t.precond_type; its->stop_type = t.stop_type;
+    its->maxit = t.maxit; its->tol = t.tol; its->restart = t.restart; its->print_level = t.print_level;
+    fasp_param_init(in ? &in->v : nullptr, &t, nullptr, nullptr, nullptr);
+    its->itsolver_type_v = t.itsolver_type; its->precond_type_v = t.precond_type; its->pre_maxit_v = t.maxit;
+    its->pre_tol_v = t.tol; its->pre_restart_v = t.restart;
+    fasp_param_init(in ? &in->p : nullptr, &t, nullptr, nullptr, nullptr);
+    its->itsolver_type_p = t.itsolver_type; its->precond_type_p = t.precond_type; its->pre_maxit_p = t.maxit;
+    its->pre_tol_p = t.tol; its->pre_restart_p = t.restart;
+  }
+  if (amg) {
+    fasp_param_init(in ? &in->v : nullptr, nullptr, &amg->param_v, nullptr, nullptr);
+    fasp_param_init(in ? &in->p : nullptr, nullptr, &amg->param_p, nullptr, nullptr);
+  }
+  fasp_param_init(in ? &in->ns : nullptr, nullptr, nullptr, ilu, sch);
 }
 
 void fasp_param_solver_init(itsolver_param* p)

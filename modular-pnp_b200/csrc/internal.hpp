@@ -250,6 +250,31 @@ void comm_allreduce_int(Handle& h, int* dev, int count, bool is_max);
 void comm_allgather(Handle& h, const void* send, void* recv, size_t bytes_per_rank);
 inline int owned_rows(const Level& L) { return L.n_own >= 0 ? L.n_own : L.A.n; }
 inline size_t owned_dofs(const Handle& h) { return 3 * (size_t)owned_rows(*h.hier.lv[0]); }
+// ---- block_solver.cu: PNP-Stokes 2x2 block system (benchmarks/pnp_stokes/linear_pnp_ns.cpp:137-235)
+// scalar CSR on the device (the coupling blocks and the Stokes block; the PNP block and the
+// velocity block additionally live as BSR(3) hierarchies in their own handles)
+struct DevCsr {
+  int nrow = 0, ncol = 0, nnz = 0;
+  DevBuf<int> ia, ja;
+  DevBuf<double> val;
+};
+void csr_upload(const dCSRmat* A, DevCsr& D, cudaStream_t s);
+// y[i - r0] = beta * y[i - r0] + alpha * sum_{c0 <= j < c1} A_ij x[j - c0]   for rows r0 <= i < r1
+void csr_spmv(const DevCsr& A, int r0, int r1, int c0, int c1, double alpha, const double* x, double beta, double* y,
+              cudaStream_t s);
+struct BlockStats { int outer_its = 0, pnp_solves = 0, pnp_its = 0, stokes_solves = 0, stokes_its = 0; double relres = 0; };
+struct BlockSystem {
+  Handle* outer = nullptr;      // stream, reduction scratch and Krylov storage of the outer iteration
+  Handle* pnp = nullptr;        // PNP block as BSR-T (3 dofs per vertex) + its AMG hierarchy
+  Handle* vel = nullptr;        // velocity block as BSR-T (dofs grouped in threes, identity padding) + hierarchy
+  DevCsr App, Aps, Asp, Ass;    // the four blocks, scalar CSR (App only for the outer matvec)
+  int np = 0, ns = 0, nu = 0, npres = 0;
+  DevBuf<double> sinv;          // npres: inverse of the diagonal of the SIMPLE Schur complement
+  SolverConfig cfg_outer, cfg_pnp, cfg_ns, cfg_vel;
+};
+// outer FGMRES with the block upper-triangular preconditioner; b, x device vectors of length np + ns
+int block_pnp_stokes_solve(BlockSystem& S, const double* b, double* x, BlockStats* st);
+
 // ---- amg.cu
 void amg_setup(Handle& h, const SolverConfig& cfg);
 // z = M^{-1} r. If Az != nullptr and the cycle can deliver it for half a matrix pass (at least one

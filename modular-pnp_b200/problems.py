@@ -113,6 +113,114 @@ def diode_fields(x, voltage_drop):
                 uu0=np.ascontiguousarray(uu0.ravel()))
 
 
+
+# ---- pnp_stokes (BASELINE configs[3]): synthetic 2x2 block system for the block solver --------
+def mac_stokes_block(n, length=2.0, mu=1.0, pressure_penalty=1e-2):
+    """Stokes saddle-point block [A_uu A_uq; A_qu A_qq] on an n^3 staggered (MAC) grid of a cube
+    of edge `length`: face-normal velocities (like the reference's RT1 dofs: one per face), one
+    pressure per cell (DG0), no-slip walls. A_uu = mu * (component-wise 7-point Laplacians, scaled
+    by the cell volume; wall-normal faces are identity rows), A_qu = discrete divergence (face
+    areas), A_uq = its transpose, A_qq = -pressure_penalty * volume / mu (removes the constant-
+    pressure null space, like the penalty terms of vector_linear_pnp_ns_forms.ufl:38-40).
+    Returns (A_ss as scipy CSR with velocity dofs first, n_vel, n_pres). Dof order: x-faces
+    (i fastest, then j, k), y-faces, z-faces, then cells."""
+    import scipy.sparse as sp
+    h = length / n
+    I = lambda m: sp.identity(m, format="csr")
+
+    def t_normal(m):        # m+1 face positions along the face normal; the two walls are Dirichlet
+        T = sp.diags([-np.ones(m), 2.0 * np.ones(m + 1), -np.ones(m)], [-1, 0, 1], format="lil")
+        for w in (0, m):
+            T[w, :] = 0.0; T[:, w] = 0.0
+        return T.tocsr()
+
+    def t_tangent(m):       # m cell-centred positions, wall by reflection (ghost = -inside)
+        d = 2.0 * np.ones(m); d[0] = d[-1] = 3.0
+        return sp.diags([-np.ones(m - 1), d, -np.ones(m - 1)], [-1, 0, 1], format="csr")
+
+    def wall_mask(m):       # 1 on interior face positions
+        w = np.ones(m + 1); w[0] = w[-1] = 0.0
+        return w
+
+    def d_normal(m):        # cells x faces difference along the normal, wall faces dropped
+        D = sp.diags([-np.ones(m), np.ones(m)], [0, 1], shape=(m, m + 1), format="csr")
+        return D @ sp.diags(wall_mask(m))
+
+    kron3 = lambda az, ay, ax: sp.kron(az, sp.kron(ay, ax, format="csr"), format="csr")   # x fastest
+    scale = mu * h                              # (1/h^2) * h^3
+    Tn, Tt, In, It = t_normal(n), t_tangent(n), I(n + 1), I(n)
+    Mn = sp.diags(wall_mask(n))
+    wall_id = lambda az, ay, ax: kron3(az, ay, ax)
+    # x-faces: (n+1) x n x n
+    Lx = scale * (kron3(It, It, Tn) + kron3(It, Tt, Mn) + kron3(Tt, It, Mn)) + wall_id(It, It, In - Mn)
+    Ly = scale * (kron3(It, Tn, It) + kron3(It, Mn, Tt) + kron3(Tt, Mn, It)) + wall_id(It, In - Mn, It)
+    Lz = scale * (kron3(Tn, It, It) + kron3(Mn, It, Tt) + kron3(Mn, Tt, It)) + wall_id(In - Mn, It, It)
+    Auu = sp.block_diag([Lx, Ly, Lz], format="csr")
+    Dn = d_normal(n)
+    B = (h * h) * sp.hstack([kron3(It, It, Dn), kron3(It, Dn, It), kron3(Dn, It, It)], format="csr")
+    nq = n ** 3
+    C = -(pressure_penalty * h ** 3 / mu) * sp.identity(nq, format="csr")
+    Ass = sp.bmat([[Auu, -B.T], [-B, C]], format="csr")
+    Ass.eliminate_zeros(); Ass.sort_indices()
+    return Ass, Auu.shape[0], nq
+
+
+def pnp_stokes_block_system(App, n, length=2.0, mu=1.0, coupling=0.05, seed=7):
+    """Synthetic coupled system of the shape benchmarks/pnp_stokes/linear_pnp_ns.cpp:150-157 builds:
+    App = the assembled PNP Jacobian on the n^3 box (scipy CSR, 3 dofs per vertex), A_ss = MAC
+    Stokes block of the same box, A_ps = ion rows x velocity columns (the convective coupling
+    (u . grad c) v couples a vertex with the faces of its cubes), A_sp = velocity rows x potential
+    columns (the electric body force). Coupling entries: coupling * h * U(-1, 1), deterministic.
+    Returns dict(blocks=[App, Aps, Asp, Ass], n_vel, n_pres, b, A) with A the assembled full
+    matrix (for the direct-solve check of the tests)."""
+    import scipy.sparse as sp
+    h = length / n
+    Ass, nu, nq = mac_stokes_block(n, length, mu)
+    nvtx = (n + 1) ** 3
+    assert App.shape == (3 * nvtx, 3 * nvtx)
+    rng = np.random.default_rng(seed)
+    ones = lambda m, k: sp.diags([np.ones(m - abs(k))], [k], shape=(m + 1, m), format="csr") if k <= 0 else None
+    # vertex <-> cell incidence along one axis: vertex i touches cells i-1 and i
+    v2c = lambda m: sp.diags([np.ones(m), np.ones(m)], [0, -1], shape=(m + 1, m), format="csr")
+    # face <-> cell incidence along the face normal (face i between cells i-1 and i), identity tangentially
+    kron3 = lambda az, ay, ax: sp.kron(az, sp.kron(ay, ax, format="csr"), format="csr")
+    V2C = kron3(v2c(n), v2c(n), v2c(n))                               # vertices x cells
+    F2C = sp.vstack([kron3(sp.identity(n), sp.identity(n), v2c(n)),   # x-faces x cells
+                     kron3(sp.identity(n), v2c(n), sp.identity(n)),
+                     kron3(v2c(n), sp.identity(n), sp.identity(n))], format="csr")
+    adj = (V2C @ F2C.T).tocsr()                                        # vertices x faces pattern
+    adj.data[:] = 1.0
+    # interior faces only (wall faces carry a homogeneous Dirichlet velocity)
+    interior = np.abs(Ass[:nu, :nu].diagonal() - 1.0) > 1e-14
+    adj = (adj @ sp.diags(interior.astype(np.float64))).tocsr(); adj.eliminate_zeros()
+    def coupling_block(rows_comp):      # 3*nvtx x nu, entries on component rows `rows_comp`
+        blocks = []
+        for k in range(3):
+            if k in rows_comp:
+                M = adj.copy(); M.data = coupling * h * rng.uniform(-1.0, 1.0, M.nnz)
+            else:
+                M = sp.csr_matrix(adj.shape)
+            blocks.append(M)
+        # interleave: row 3*v + k
+        P = [sp.csr_matrix((np.ones(nvtx), (3 * np.arange(nvtx) + k, np.arange(nvtx))), shape=(3 * nvtx, nvtx)) for k in range(3)]
+        return sum(P[k] @ blocks[k] for k in range(3)).tocsr()
+    # Dirichlet rows of the PNP block stay identity rows: no coupling on them
+    pdiag_only = np.asarray((App != 0).sum(axis=1)).ravel() == 1
+    keep = sp.diags((~pdiag_only).astype(np.float64))
+    Aps_u = (keep @ coupling_block({1, 2})).tocsr()
+    Aps = sp.hstack([Aps_u, sp.csr_matrix((3 * nvtx, nq))], format="csr")
+    Asp_u = (coupling_block({0}).T @ keep).tocsr()                    # velocity rows x PNP columns (potential, free dofs)
+    Asp = sp.vstack([Asp_u, sp.csr_matrix((nq, 3 * nvtx))], format="csr")
+    for M in (Aps, Asp):
+        M.eliminate_zeros(); M.sort_indices()
+    App = App.tocsr(); App.sort_indices()
+    A = sp.bmat([[App, Aps], [Asp, Ass]], format="csr")
+    xs = rng.uniform(-1.0, 1.0, A.shape[0])
+    xs[3 * nvtx:3 * nvtx + nu][~interior] = 0.0
+    b = A @ xs
+    return dict(blocks=[App, Aps, Asp, Ass], n_vel=nu, n_pres=nq, b=b, A=A, x_star=xs)
+
+
 class NewtonStatus:
     """src/newton_status.cpp:11-74"""
 
