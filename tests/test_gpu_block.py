@@ -101,3 +101,48 @@ def test_block_solver_argument_errors(oracle, pkg, gpu_lib):
     assert st == -13                           # ERROR_INPUT_PAR: n_vel + n_pres != rows of the Stokes block
     st, _, _ = pkg.capi.solve_pnp_stokes(S["blocks"], S["b"][:-1], S["n_vel"], S["n_pres"])
     assert st == -13
+
+
+def test_host_mirror_linear_pnp_ns_binary(oracle, pkg, gpu_lib, tmp_path):
+    """modular-pnp_b200/host/linear_pnp_ns.hpp (the C++ mirror of Linear_PNP_NS: get_dofs_fasp,
+    setup_fasp_linear_algebra, fasp_solve) on a mixed-numbered system handed over as DOLFIN would:
+    one CSR matrix, one rhs, the sorted dof list of each of the 5 solution components."""
+    import os
+    import subprocess
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    S = _system(oracle, pkg, 6, 0.5)
+    A, b = S["A"].tocsr(), S["b"]
+    N, np_, nu = A.shape[0], S["blocks"][0].shape[0], S["n_vel"]
+    # component of every block-ordered dof: PNP dofs interleaved (3 per vertex), then velocity, then pressure
+    comp = np.concatenate([np.arange(np_) % 3, np.full(nu, 3), np.full(N - np_ - nu, 4)])
+    # mixed numbering: random, but each component's dofs keep their relative order (the lists are sorted)
+    rng = np.random.default_rng(11)
+    slots = rng.permutation(N)
+    new_of = np.empty(N, dtype=np.int64)
+    dof_lists = []
+    start = 0
+    for c in range(5):
+        idx = np.nonzero(comp == c)[0]
+        mine = np.sort(slots[start:start + len(idx)]); start += len(idx)
+        new_of[idx] = mine
+        dof_lists.append(mine.astype(np.int32))
+    Pm = sp.csr_matrix((np.ones(N), (new_of, np.arange(N))), shape=(N, N))
+    Amix = (Pm @ A @ Pm.T).tocsr(); Amix.sort_indices()
+    bmix = Pm @ b
+    sysfile, outfile = str(tmp_path / "system.bin"), str(tmp_path / "update.bin")
+    with open(sysfile, "wb") as f:
+        np.array([N, Amix.nnz, 5], dtype=np.int32).tofile(f)
+        Amix.indptr.astype(np.int32).tofile(f); Amix.indices.astype(np.int32).tofile(f)
+        Amix.data.astype(np.float64).tofile(f); bmix.astype(np.float64).tofile(f)
+        for d in dof_lists:
+            np.array([len(d)], dtype=np.int32).tofile(f); d.tofile(f)
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "modular-pnp_b200", "host", "pnp_stokes_block")
+    out = subprocess.run([exe, sysfile, outfile], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    status = int([l for l in out.stdout.splitlines() if l.startswith("BLOCK_SOLVE_STATUS")][0].split()[1])
+    assert 0 < status <= 12
+    upd = np.fromfile(outfile, dtype=np.float64)
+    assert np.linalg.norm(bmix - Amix @ upd) <= 1.01e-6 * np.linalg.norm(bmix)          # bcsr.dat tolerance
+    x_ref = spl.spsolve(Amix.tocsc(), bmix)
+    assert np.linalg.norm(upd - x_ref) <= 1e-4 * np.linalg.norm(x_ref)

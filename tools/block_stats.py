@@ -10,6 +10,7 @@ pkg = load_package()
 problems = import_module("modular_pnp_b200.problems")
 from helpers import bsr_to_csr
 
+VCYC = int(os.environ.get("BLOCK_VEL_CYCLE", "1"))      # AMG_cycle_type_v: 1 = V (ns.dat), 4 = NA (K-cycle)
 for a in sys.argv[1:]:
     n = int(a)
     pr = problems.exact_solution_problem(n, n, n, 2.0, 2.0, 2.0)
@@ -22,7 +23,9 @@ for a in sys.argv[1:]:
     for coupling in (0.05, 0.5):
         S = problems.pnp_stokes_block_system(App, n, coupling=coupling)
         t0 = time.time()
-        st, x, stats = pkg.capi.solve_pnp_stokes(S["blocks"], S["b"], S["n_vel"], S["n_pres"])
+        params = list(pkg.capi.pnp_stokes_params())
+        params[4].param_v.cycle_type = VCYC
+        st, x, stats = pkg.capi.solve_pnp_stokes(S["blocks"], S["b"], S["n_vel"], S["n_pres"], params)
         dt = time.time() - t0
         rel = np.linalg.norm(S["b"] - S["A"] @ x) / np.linalg.norm(S["b"])
         print("n=%d coupling=%.2f dofs pnp %d vel %d pres %d | status %d %s | true relres %.2e | %.2f s" % (
