@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("PNPB200_BENCH_N", "256")))
+    ap.add_argument("--n", "--box-n", dest="n", type=int, default=int(os.environ.get("PNPB200_BENCH_N", "256")))
     ap.add_argument("--cpu-sample-n", type=int, default=48)
     ap.add_argument("--cycle", default=os.environ.get("PNPB200_BENCH_CYCLE", "NA"),
                     help="AMG_cycle_type: V (bsr.dat) or NA (FASP nonlinear AMLI = K-cycle; needed above ~20 M dof where V exceeds itsolver_maxit)")
@@ -315,19 +315,22 @@ def main():
     b_step = byte_model(stats, nv, nc, kk, it.restart, kcycle_levels=klev)
     b_sched = byte_model(stats, nv, nc, kk, it.restart, kcycle_levels=klev, shortcuts=True)
     step_gbs = b_step / (ms / K) / 1e6
-    # traffic: dram bytes of one sweep from the committed ncu capture (only taken at n = 128: ncu
-    # cannot save/restore the 100 GB working set of the 256^3 run)
+    # traffic: dram bytes of one sweep (dram__bytes_read.sum + dram__bytes_write.sum over its colour
+    # launches) from the committed single-pass ncu capture taken at the same n (tools/ncu_traffic.sh)
     traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic_ldu_n128.json")
-    if os.path.exists(tp):
+    for tp in (os.path.join(ROOT, "profiles", "r01_traffic_gsd_n%d.json" % n), os.path.join(ROOT, "profiles", "r01_traffic_gsd_n256.json"),
+               os.path.join(ROOT, "profiles", "r01_traffic_ldu_n128.json")):
+        if not os.path.exists(tp):
+            continue
         try:
             with open(tp) as f:
                 tj = json.load(f)
             ratio = tj["gs_sweep"]["dram_bytes_per_sweep"] / tj["gs_sweep"]["algorithmic_bytes"]
-            traffic_note = "ncu at n=128: %.3g B dram per sweep = %.2fx algorithmic (x re-read once per colour, partial sectors)" % (
-                tj["gs_sweep"]["dram_bytes_per_sweep"], ratio)
+            traffic_note = "ncu at n=%d (%s): %.4g B dram per sweep = %.2fx algorithmic (x re-read once per colour, partial sectors)" % (
+                tj.get("n"), os.path.basename(tp), tj["gs_sweep"]["dram_bytes_per_sweep"], ratio)
             if tj.get("n") == n:
                 traffic = tj["gs_sweep"]["dram_bytes_per_sweep"]
+            break
         except Exception:
             pass
 
