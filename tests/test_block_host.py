@@ -69,3 +69,53 @@ def test_synthetic_pnp_stokes_system_is_a_saddle_point_problem(oracle):
     assert Aps[:, nu:].nnz == 0 and Asp[nu:, :].nnz == 0
     x = spl.spsolve(S["A"].tocsc(), S["b"])
     assert np.linalg.norm(x - S["x_star"]) <= 1e-9 * np.linalg.norm(S["x_star"])
+
+
+def test_reference_include_pattern_compiles_and_links(pkg, tmp_path):
+    """The reference reaches FASP / fasp4ns through `extern "C" { #include "fasp.h" ... }`
+    (benchmarks/pnp_stokes/linear_pnp_ns.h:13-18) and sets its parameter blocks up as in
+    benchmarks/pnp_stokes/main.cpp:55-86. With include/pnpb200/compat on the include path that code
+    compiles against this library's headers and links libpnpb200.so (host-side calls only here)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "modular-pnp_b200", "host")
+    src = tmp_path / "main.cpp"
+    src.write_text(r'''
+#include <cstdio>
+extern "C" {
+  #include "fasp.h"
+  #include "fasp_functs.h"
+  #include "fasp4ns.h"
+  #include "fasp4ns_functs.h"
+}
+int main(int argc, char** argv) {
+  input_param inpar; itsolver_param itpar; AMG_param amgpar; ILU_param ilupar;
+  fasp_param_input(argv[1], &inpar);
+  fasp_param_init(&inpar, &itpar, &amgpar, &ilupar, NULL);
+  input_param pnp_inpar; itsolver_param pnp_itpar; AMG_param pnp_amgpar; ILU_param pnp_ilupar; Schwarz_param pnp_schpar;
+  fasp_param_input(argv[2], &pnp_inpar);
+  fasp_param_init(&pnp_inpar, &pnp_itpar, &pnp_amgpar, &pnp_ilupar, &pnp_schpar);
+  input_ns_param ns_inpar; itsolver_ns_param ns_itpar; AMG_ns_param ns_amgpar; ILU_param ns_ilupar; Schwarz_param ns_schpar;
+  fasp_ns_param_input(argv[3], &ns_inpar);
+  fasp_ns_param_init(&ns_inpar, &ns_itpar, &ns_amgpar, &ns_ilupar, &ns_schpar);
+  block_dCSRmat A; A.brow = 2; A.bcol = 2; A.blocks = NULL;
+  ivector dofs; fasp_ivec_alloc(4, &dofs);
+  dvector b, x; fasp_dvec_alloc(3, &b); fasp_dvec_alloc(3, &x);
+  INT status = fasp_solver_bdcsr_krylov_pnp_stokes(&A, &b, &x, &itpar, &pnp_itpar, &pnp_amgpar, &ns_itpar, &ns_amgpar, 2, 1);
+  printf("%d %d %d %d %d %d\n", (int)itpar.restart, (int)pnp_itpar.restart, (int)ns_itpar.restart, (int)ns_amgpar.param_p.coarse_dof,
+         dofs.row, (int)status);
+  fasp_dvec_free(&b); fasp_dvec_free(&x);
+  return 0;
+}
+''')
+    exe = str(tmp_path / "main")
+    cc = subprocess.run(["g++", "-std=c++11", "-I", os.path.join(root, "include", "pnpb200", "compat"), str(src), "-o", exe,
+                         "-L", os.path.join(root, "modular-pnp_b200"), "-lpnpb200",
+                         "-Wl,-rpath," + os.path.join(root, "modular-pnp_b200")], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    out = subprocess.run([exe, os.path.join(host, "bcsr.dat"), os.path.join(host, "bsr.dat"), os.path.join(host, "ns.dat")],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    # restart values of the three files, the pressure block's coarse size, and ERROR_INPUT_PAR for the empty block matrix
+    assert out.stdout.split() == ["10", "30", "100", "50", "4", "-13"]
