@@ -831,6 +831,7 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
   if (F.ncolors == 0) throw Error(ERROR_DATA_STRUCTURE, "fine level not coloured");   // done at create / upload
   alloc_level_vectors(F, s);
   if (!reuse) h.hier.symbolic_valid = false;
+  h.hier.drop_coarse_graph();           // buffers and launch sizes belong to the hierarchy being replaced
   const int min_cdof = cfg.coarse_dof > 50 ? cfg.coarse_dof : 50;
   int l = 0;
   while (true) {
@@ -886,6 +887,48 @@ inline int small_grid(size_t n) { const size_t b = (n + 255) / 256; return (int)
 
 void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x);
 
+// Approximate solve on level l (>= 2) with rhs lv[l]->b and result lv[l]->x, replayed from a CUDA
+// graph. Everything in there runs on fixed buffers with device-side scalars and no host
+// synchronisation, so the launch sequence is the same at every visit of one hierarchy; the
+// K-cycle makes two such visits per Krylov iteration, ~200 launches of 2-8 us kernels each.
+// First visit: direct (lazy scratch allocations, function attributes), second: capture +
+// instantiate, later ones: one cudaGraphLaunch. Single GPU only (the distributed cycle has NCCL
+// calls between the kernels). PNPB200_COARSE_GRAPH=0 switches it off, =k moves the cut to level k.
+int coarse_graph_level()
+{
+  static const int lvl = getenv("PNPB200_COARSE_GRAPH") ? atoi(getenv("PNPB200_COARSE_GRAPH")) : 2;
+  return lvl;
+}
+void coarse_solve_graphed(Handle& h, const SolverConfig& cfg, int l)
+{
+  Hierarchy& H = h.hier;
+  Level& C = *H.lv[l];
+  cudaStream_t s = h.stream;
+  const unsigned sig = hash32((unsigned)cfg.cycle_type * 7919u + (unsigned)cfg.kcycle_levels * 104729u + (unsigned)cfg.presmooth * 31u +
+                              (unsigned)cfg.postsmooth * 131u + (unsigned)h.sweep_shortcuts * 3u + (unsigned)l * 1299709u);
+  if (H.coarse_exec && H.coarse_sig != sig) H.drop_coarse_graph();
+  if (H.coarse_exec) {
+    PNP_CUDA(cudaGraphLaunch(H.coarse_exec, s));
+    g_launches += H.coarse_nodes;
+    return;
+  }
+  if (H.coarse_visits++ == 0) { solve_level(h, cfg, l, C.b.p, C.x.p); return; }
+  const long before = g_launches;
+  cudaGraph_t graph = nullptr;
+  PNP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  try { solve_level(h, cfg, l, C.b.p, C.x.p); }
+  catch (...) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+  PNP_CUDA(cudaStreamEndCapture(s, &graph));
+  H.coarse_nodes = g_launches - before;
+  g_launches = before;
+  const cudaError_t e = cudaGraphInstantiate(&H.coarse_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { H.coarse_exec = nullptr; throw Error(ERROR_DEVICE, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+  H.coarse_sig = sig;
+  PNP_CUDA(cudaGraphLaunch(H.coarse_exec, s));
+  g_launches += H.coarse_nodes;
+}
+
 // one multigrid cycle on level l from a zero initial guess: x = B_l b. Multi-GPU: hybrid
 // Gauss-Seidel (ghost values refreshed from their owners before every sweep / residual).
 // With one pre-smoothing sweep the zero initial guess is exploited: the forward sweep reads only
@@ -917,7 +960,8 @@ bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double
                                                                  L.agg_rows_pos.p, L.w.p, C.b.p);
     PNP_COUNT_LAUNCH();
   }
-  solve_level(h, cfg, l + 1, C.b.p, C.x.p);
+  if (l + 1 == coarse_graph_level() && l + 1 >= 2 && l + 2 < (int)h.hier.lv.size() && !dist && !g_debug_sync) coarse_solve_graphed(h, cfg, l + 1);
+  else solve_level(h, cfg, l + 1, C.b.p, C.x.p);
   if (own > 0) { prolong_kernel<<<cdiv(3 * (size_t)own, 256), 256, 0, s>>>(own, L.agg_pos.p, C.x.p, x); PNP_COUNT_LAUNCH(); }
   const bool want_ax = Ax != nullptr && cfg.postsmooth >= 1 && h.sweep_shortcuts;
   for (int k = 0; k < cfg.postsmooth; ++k) {

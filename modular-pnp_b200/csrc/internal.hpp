@@ -103,6 +103,15 @@ struct Hierarchy {
   DevBuf<int> c_off3, c_cnt3;
   DevBuf<double> c_bpad, c_ball, c_bglob;
   bool symbolic_valid = false;
+  // CUDA graph of the coarse part of a cycle (everything below level COARSE_GRAPH_LEVEL, amg.cu):
+  // the K-cycle visits those levels several times per Krylov iteration with ~200 launches of
+  // microsecond kernels each; captured once per hierarchy, replayed with one cudaGraphLaunch
+  cudaGraphExec_t coarse_exec = nullptr;
+  int coarse_visits = 0;        // visits since the hierarchy was built (the first one runs uncaptured)
+  long coarse_nodes = 0;        // kernels in the graph (launch counter)
+  unsigned coarse_sig = 0;      // cycle parameters the graph was captured with
+  void drop_coarse_graph() { if (coarse_exec) { cudaGraphExecDestroy(coarse_exec); coarse_exec = nullptr; } coarse_visits = 0; coarse_nodes = 0; }
+  ~Hierarchy() { if (coarse_exec) cudaGraphExecDestroy(coarse_exec); }
 };
 
 struct Krylov {
