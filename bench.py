@@ -148,7 +148,31 @@ def cpu_reference_leg(sample_n, steps=1):
     return min(ts), dof, its, used_ref
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Only the JSON line may reach stdout: libraries write there too (NCCL prints its version
+    banner on fd 1 when the communicator comes up), so fd 1 is pointed at stderr for the run and the
+    result line goes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
@@ -183,7 +207,7 @@ def main():
         val = scale / sec
         sample = ("first Newton step on a %d^3 box (%d dof, %d Krylov its), %.2f s on 1 core; scaled linearly in dof to the %d^3 workload"
                   % (args.cpu_sample_n, dof, its, sec, n))
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        emit(({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
                           "warmup": W, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1,
@@ -286,7 +310,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms / K, "krylov_its": its, "gpu_launches": launches,
+            emit(({"profile_run": True, "ms_per_step": ms / K, "krylov_its": its, "gpu_launches": launches,
                               "config": config}))
         g.close()
         return 0
@@ -372,7 +396,7 @@ def main():
                                                                                        "; reference element kernels (oracle/_ref)" if used_ref else "")}
             except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "unavailable: %r" % (e,)}
-        print(json.dumps(out))
+        emit(out)
     g.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -891,13 +891,23 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
 // graph. Everything in there runs on fixed buffers with device-side scalars and no host
 // synchronisation, so the launch sequence is the same at every visit of one hierarchy; the
 // K-cycle makes two such visits per Krylov iteration, ~200 launches of 2-8 us kernels each.
-// First visit: direct (lazy scratch allocations, function attributes), second: capture +
-// instantiate, later ones: one cudaGraphLaunch. Single GPU only (the distributed cycle has NCCL
-// calls between the kernels). PNPB200_COARSE_GRAPH=0 switches it off, =k moves the cut to level k.
+// First visit: direct (lazy scratch allocations, function attributes, NCCL connections), second:
+// capture + instantiate, later ones: one cudaGraphLaunch. PNPB200_COARSE_GRAPH=0 switches it off,
+// =k moves the cut to level k. Measured: 1 GPU 256^3 783 -> 769 ms per step; 2 GPUs 128^3 per GPU
+// 167 -> 159 ms (Krylov stage 130 -> 120 ms: the NCCL group launches of the coarse levels are
+// CPU-bound when issued one by one).
 int coarse_graph_level()
 {
   static const int lvl = getenv("PNPB200_COARSE_GRAPH") ? atoi(getenv("PNPB200_COARSE_GRAPH")) : 2;
   return lvl;
+}
+// multi-GPU: the halo exchanges and allreduces of the coarse levels are NCCL calls on the same stream
+// and are captured with the kernels (every rank captures the same sequence: the level structure is
+// decided on global sizes). PNPB200_COARSE_GRAPH_DIST=0 keeps the distributed cycle uncaptured.
+bool coarse_graph_dist()
+{
+  static const bool on = getenv("PNPB200_COARSE_GRAPH_DIST") ? atoi(getenv("PNPB200_COARSE_GRAPH_DIST")) != 0 : true;
+  return on;
 }
 void coarse_solve_graphed(Handle& h, const SolverConfig& cfg, int l)
 {
@@ -960,7 +970,7 @@ bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double
                                                                  L.agg_rows_pos.p, L.w.p, C.b.p);
     PNP_COUNT_LAUNCH();
   }
-  if (l + 1 == coarse_graph_level() && l + 1 >= 2 && l + 2 < (int)h.hier.lv.size() && !dist && !g_debug_sync) coarse_solve_graphed(h, cfg, l + 1);
+  if (l + 1 == coarse_graph_level() && l + 1 >= 1 && l + 2 < (int)h.hier.lv.size() && (!dist || coarse_graph_dist()) && !g_debug_sync) coarse_solve_graphed(h, cfg, l + 1);
   else solve_level(h, cfg, l + 1, C.b.p, C.x.p);
   if (own > 0) { prolong_kernel<<<cdiv(3 * (size_t)own, 256), 256, 0, s>>>(own, L.agg_pos.p, C.x.p, x); PNP_COUNT_LAUNCH(); }
   const bool want_ax = Ax != nullptr && cfg.postsmooth >= 1 && h.sweep_shortcuts;
