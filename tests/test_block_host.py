@@ -119,3 +119,57 @@ int main(int argc, char** argv) {
     assert out.returncode == 0, out.stderr[-2000:]
     # restart values of the three files, the pressure block's coarse size, and ERROR_INPUT_PAR for the empty block matrix
     assert out.stdout.split() == ["10", "30", "100", "50", "4", "-13"]
+
+
+def test_block_preconditioner_restated_with_exact_block_solves(oracle):
+    """The algorithm of csrc/block_solver.cu restated with scipy (test infrastructure): outer GMRES
+    with the block upper-triangular preconditioner, Stokes block by GMRES preconditioned with
+    [A_uu^-1 ; diagonal SIMPLE Schur complement]. With exact velocity / PNP block solves in place of
+    the AMG cycles this is the best the GPU path can do; it pins that the scheme itself converges in a
+    handful of outer steps on the synthetic system (the GPU tests then check the real thing)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    from helpers import bsr_to_csr
+    problems = import_module("modular_pnp_b200.problems")
+    n = 6
+    P = oracle.Problem(n, n, n, 2.0, 2.0, 2.0)
+    A, _ = P.assemble(P.uu0)
+    sIA, sJA, sval = bsr_to_csr(P.IA, P.JA, A)
+    App = sp.csr_matrix((sval, sJA, sIA), shape=(P.N, P.N)); App.eliminate_zeros()
+    S = problems.pnp_stokes_block_system(App, n, coupling=0.5)
+    App, Aps, Asp, Ass = S["blocks"]
+    nu, Afull, b = S["n_vel"], S["A"], S["b"]
+    np_, ns = App.shape[0], Ass.shape[0]
+    luP, luU = spl.splu(App.tocsc()), spl.splu(Ass[:nu, :nu].tocsc())
+    Aqu, Auq = Ass[nu:, :nu], Ass[:nu, nu:]
+    sd = Ass[nu:, nu:].diagonal() - (Aqu @ sp.diags(1.0 / Ass[:nu, :nu].diagonal()) @ Auq).diagonal()
+    assert np.all(sd < 0.0)                       # -(penalty + B D^-1 B^T): negative definite diagonal
+    inner = {"its": 0, "solves": 0}
+
+    def m_stokes(r):
+        zu = luU.solve(r[:nu])
+        return np.concatenate([zu, (r[nu:] - Aqu @ zu) / sd])
+
+    def stokes_solve(r):
+        def cb(_):
+            inner["its"] += 1
+        z, info = spl.gmres(Ass, r, M=spl.LinearOperator((ns, ns), matvec=m_stokes), rtol=1e-6, restart=31, maxiter=4,
+                            callback=cb, callback_type="pr_norm")
+        inner["solves"] += 1
+        assert info == 0
+        return z
+
+    def m_upper(r):
+        zs = stokes_solve(r[np_:])
+        return np.concatenate([luP.solve(r[:np_] - Aps @ zs), zs])
+
+    outer = {"its": 0}
+
+    def cb(_):
+        outer["its"] += 1
+    x, info = spl.gmres(Afull, b, M=spl.LinearOperator(Afull.shape, matvec=m_upper), rtol=1e-8, restart=10, maxiter=10,
+                        callback=cb, callback_type="pr_norm")
+    assert info == 0 and outer["its"] <= 8
+    assert np.linalg.norm(b - Afull @ x) <= 1e-8 * np.linalg.norm(b)
+    assert np.linalg.norm(x - S["x_star"]) <= 1e-6 * np.linalg.norm(S["x_star"])
+    assert inner["its"] / inner["solves"] <= 40   # diagonal Schur complement: mesh-size independent for a stable pair
