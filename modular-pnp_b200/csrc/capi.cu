@@ -767,17 +767,38 @@ dBSRmat fasp_format_dcsr_dbsr(const dCSRmat* A, const INT nb)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Error(ERROR_DEVICE, "no CUDA device");
     cudaStream_t s; PNP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     const int n = A->row, nbrow = n / nb;
+    if (!A->IA || A->IA[0] != 0) throw Error(ERROR_INPUT_PAR, "fasp_format_dcsr_dbsr: IA must be 0-based");
     const int nnz = A->IA[n] - A->IA[0];
+    // The device kernel merges column-sorted rows. Upstream accepts any entry order (sub-matrices
+    // cut with fasp_dcsr_getblk keep the parent's order, linear_pnp_ns.cpp:150-157): such rows are
+    // put in ascending column order on the host first (an index permutation, no arithmetic).
+    const INT* hJA = A->JA; const REAL* hval = A->val;
+    std::vector<INT> sJA; std::vector<REAL> sval;
+    bool sorted = true;
+    for (int i = 0; i < n && sorted; ++i)
+      for (INT k = A->IA[i] + 1; k < A->IA[i + 1]; ++k) if (A->JA[k] <= A->JA[k - 1]) { sorted = false; break; }
+    if (!sorted) {
+      sJA.assign(A->JA + A->IA[0], A->JA + A->IA[n]); sval.assign(A->val + A->IA[0], A->val + A->IA[n]);
+      std::vector<std::pair<INT, REAL>> row;
+      for (int i = 0; i < n; ++i) {
+        const INT a0 = A->IA[i] - A->IA[0], a1 = A->IA[i + 1] - A->IA[0];
+        row.clear();
+        for (INT k = a0; k < a1; ++k) row.emplace_back(sJA[k], sval[k]);
+        std::sort(row.begin(), row.end(), [](const std::pair<INT, REAL>& x, const std::pair<INT, REAL>& y) { return x.first < y.first; });
+        for (INT k = a0; k < a1; ++k) { sJA[k] = row[k - a0].first; sval[k] = row[k - a0].second; }
+      }
+      hJA = sJA.data() - A->IA[0]; hval = sval.data() - A->IA[0];
+    }
     {
       DevBuf<int> IA, JA, cnt, bIA, bJA, err; DevBuf<double> val, bval;
       IA.alloc(n + 1, s); JA.alloc(nnz, s); val.alloc(nnz, s); cnt.alloc(nbrow + 1, s); bIA.alloc(nbrow + 1, s); err.alloc(1, s);
-      IA.upload(A->IA, n + 1); JA.upload(A->JA, nnz); val.upload(A->val, nnz); cnt.zero(); err.zero();
+      IA.upload(A->IA, n + 1); JA.upload(hJA + A->IA[0], nnz); val.upload(hval + A->IA[0], nnz); cnt.zero(); err.zero();
       csr2bsr_kernel<false><<<cdiv(nbrow, 128), 128, 0, s>>>(nbrow, nb, IA.p, JA.p, val.p, cnt.p, nullptr, nullptr, nullptr, err.p);
       exclusive_scan_int(cnt.p, bIA.p, nbrow + 1, s);
       B.IA = (INT*)calloc((size_t)nbrow + 1, sizeof(INT));
       bIA.download(B.IA, nbrow + 1);
       int herr = 0; err.download(&herr, 1);
-      if (herr) { free(B.IA); B.IA = nullptr; throw Error(ERROR_DATA_STRUCTURE, "fasp_format_dcsr_dbsr: CSR rows must have ascending columns"); }
+      if (herr) { free(B.IA); B.IA = nullptr; throw Error(ERROR_DATA_STRUCTURE, "fasp_format_dcsr_dbsr: duplicate column in a CSR row"); }
       const int NNZ = B.IA[nbrow];
       bJA.alloc(NNZ, s); bval.alloc((size_t)NNZ * nb * nb, s); bval.zero();
       csr2bsr_kernel<true><<<cdiv(nbrow, 128), 128, 0, s>>>(nbrow, nb, IA.p, JA.p, val.p, nullptr, bIA.p, bJA.p, bval.p, err.p);

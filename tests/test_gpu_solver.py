@@ -45,6 +45,20 @@ def test_fasp_blas_and_format(oracle, pkg, system):
     assert np.array_equal(bIA, IA) and np.array_equal(bJA, JA) and np.array_equal(bval, val)
 
 
+def test_format_dcsr_dbsr_accepts_rows_in_any_entry_order(pkg, system):
+    """upstream fasp_format_dcsr_dbsr does not need column-sorted rows, and fasp_dcsr_getblk
+    (benchmarks/pnp_stokes/linear_pnp_ns.cpp:150-157) does not produce them"""
+    P, g, IA, JA, val, b = system
+    sIA, sJA, sval = bsr_to_csr(IA, JA, val)
+    rng = np.random.default_rng(21)
+    uJA, uval = sJA.copy(), sval.copy()
+    for i in range(len(sIA) - 1):
+        p = rng.permutation(sIA[i + 1] - sIA[i]) + sIA[i]
+        uJA[sIA[i]:sIA[i + 1]] = sJA[p]; uval[sIA[i]:sIA[i + 1]] = sval[p]
+    bIA, bJA, bval = pkg.capi.fasp_format_dcsr_dbsr(sIA, uJA, uval, 3)
+    assert np.array_equal(bIA, IA) and np.array_equal(bJA, JA) and np.array_equal(bval, val)
+
+
 @pytest.mark.parametrize("cycle", [1, 4])      # V_CYCLE (bsr.dat) and NL_AMLI (K-cycle)
 def test_solve_hierarchy_and_vcycle(oracle, pkg, system, cycle):
     P, g, IA, JA, val, b = system
