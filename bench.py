@@ -352,8 +352,12 @@ def main():
             ratio = tj["gs_sweep"]["dram_bytes_per_sweep"] / tj["gs_sweep"]["algorithmic_bytes"]
             traffic_note = "ncu at n=%d (%s): %.4g B dram per sweep = %.2fx algorithmic (x re-read once per colour, partial sectors)" % (
                 tj.get("n"), os.path.basename(tp), tj["gs_sweep"]["dram_bytes_per_sweep"], ratio)
-            if tj.get("n") == n:
+            ncol_cap = len(tj["gs_sweep"].get("per_launch", [])) or None
+            if tj.get("n") == n and (ncol_cap is None or ncol_cap == stats.level_colors[0]):
                 traffic = tj["gs_sweep"]["dram_bytes_per_sweep"]
+            elif ncol_cap is not None and ncol_cap != stats.level_colors[0]:
+                traffic_note += "; captured with %d colour launches per sweep (graph colouring, PNPB200_BOX_COLORING=0), this run sweeps %d colours (closed-form BoxMesh colouring: x is re-read %d instead of %d times) -> traffic not re-measured, null" % (
+                    ncol_cap, stats.level_colors[0], stats.level_colors[0] - 1, ncol_cap - 1)
             break
         except Exception:
             pass

@@ -741,7 +741,9 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
   if (ws) cand = ws->get<unsigned char>(n); else { t_cand.alloc(n, s); cand = t_cand.p; }
   PNP_CUDA(cudaMemsetAsync(color, 0xff, (size_t)n * sizeof(int), s));
   PNP_CUDA(cudaMemsetAsync(rem, 0, 2 * sizeof(int), s));
-  int hrem = n, rounds = 0;
+  const bool preset = L.preset_ncolors > 0 && L.preset_color.p && L.preset_color.n >= (size_t)n;
+  if (preset) PNP_CUDA(cudaMemcpyAsync(color, L.preset_color.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  int hrem = preset ? 0 : n, rounds = 0;
   while (hrem > 0) {
     PNP_CUDA(cudaMemsetAsync(rem, 0, sizeof(int), s));
     color_select_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, ja_nat, color, cand, rem); PNP_COUNT_LAUNCH();
@@ -755,7 +757,7 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
   PNP_CUDA(cudaStreamSynchronize(s));
   if (hh2[1]) throw Error(ERROR_DATA_STRUCTURE, "matrix graph needs more than 62 colours");
   // iterated greedy passes (reverse class order, then forward): fewer, fuller colour classes
-  {
+  if (!preset) {
     int passes = 3;
     if (const char* e = getenv("PNPB200_RECOLOR_PASSES")) passes = atoi(e);
     int* newc = geti(t_newc, n);

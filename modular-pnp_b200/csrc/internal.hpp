@@ -64,6 +64,8 @@ struct Level {
   int ngroups = 0;              // (tile, colour) groups of one sweep, in order
   std::vector<int> color_ptr;   // host, ngroups+1 offsets into A.rowid
   DevBuf<int> d_color_ptr;      // the same offsets on the device (single-CTA sweep of small levels)
+  DevBuf<int> preset_color;     // optional: a proper colouring known in closed form (box meshes, mesh_setup.cu)
+  int preset_ncolors = 0;       // 0 = colour the graph with Jones-Plassmann + iterated greedy
   // aggregation to the next level
   int nagg = 0;
   DevBuf<int> agg;              // n, -1 = isolated
@@ -150,6 +152,7 @@ struct Handle {
   cudaStream_t stream = nullptr;
   // mesh
   int nv = 0, nc = 0;
+  int box_n[3] = {0, 0, 0};     // grid of a mesh generated by generate_box_mesh (0: mesh given by the caller)
   Comm comm;
   std::vector<unsigned char> bc_user;   // Dirichlet flags as set by the caller (ghost flags are added on top)
   DevBuf<double> xyz;           // 3*nv

@@ -124,6 +124,53 @@ void exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t s)
   PNP_COUNT_LAUNCH();
 }
 
+
+// ---- closed-form colouring of dolfin::BoxMesh ---------------------------------------------------
+// The Kuhn split (6 tetrahedra per cube around the diagonal v0-v7) couples vertex (i, j, k) with
+// +-(1,0,0), +-(0,1,0), +-(0,0,1), +-(1,1,0), +-(1,0,1), +-(0,1,1), +-(1,1,1): on every one of
+// these i + j + k changes by 1, 2 or 3, so (i + j + k) mod 4 is a proper colouring with FOUR
+// balanced classes (the triangulation is balanced: the 4 vertices of every cell get the 4 colours).
+// Jones-Plassmann + iterated greedy finds 10 unbalanced ones on the same graph. Fewer colours =
+// fewer launches per Gauss-Seidel sweep and, since every colour launch re-reads most of the
+// gathered x (profiles/r01_traffic_gsd_n256.json), less DRAM traffic per sweep. The colouring is
+// verified against the actual pattern before it is used; every BASELINE config runs on a BoxMesh
+// (src/domain.cpp:301-308 rejects anything else). Measured at 256^3: 758 -> 747 ms per step, 26 Krylov
+// iterations with either colouring. PNPB200_BOX_COLORING=0 keeps the graph colouring.
+namespace {
+__global__ void box_color_kernel(int nx, int ny, int nv, int* __restrict__ color)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const int i = v % (nx + 1), j = (v / (nx + 1)) % (ny + 1), k = v / ((nx + 1) * (ny + 1));
+  color[v] = (i + j + k) & 3;
+}
+__global__ void check_coloring_kernel(int n, const int* __restrict__ ia, const int* __restrict__ ja,
+                                      const int* __restrict__ color, int* __restrict__ bad)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = color[i];
+  for (int p = ia[i]; p < ia[i + 1]; ++p) { const int j = ja[p]; if (j != i && color[j] == c) { *bad = 1; return; } }
+}
+#ifndef PNPB200_BOX_COLORING_DEFAULT
+#define PNPB200_BOX_COLORING_DEFAULT 1
+#endif
+void box_coloring(Handle& h, Level& L, const int* ja_nat)
+{
+  L.preset_ncolors = 0;
+  static const int on = getenv("PNPB200_BOX_COLORING") ? atoi(getenv("PNPB200_BOX_COLORING")) : PNPB200_BOX_COLORING_DEFAULT;
+  if (!on || h.box_n[0] <= 0) return;
+  cudaStream_t s = h.stream;
+  const int nv = h.nv;
+  L.preset_color.alloc(nv, s);
+  box_color_kernel<<<cdiv(nv, 256), 256, 0, s>>>(h.box_n[0], h.box_n[1], nv, L.preset_color.p); PNP_COUNT_LAUNCH();
+  DevBuf<int> bad; bad.alloc(1, s); bad.zero();
+  check_coloring_kernel<<<cdiv(nv, 256), 256, 0, s>>>(nv, L.A.ia.p, ja_nat, L.preset_color.p, bad.p); PNP_COUNT_LAUNCH();
+  int hb = 0; bad.download(&hb, 1);
+  if (hb == 0) L.preset_ncolors = 4;      // else: not the Kuhn pattern after all, colour the graph
+}
+} // namespace
+
 void build_mesh_tables(Handle& h)
 {
   cudaStream_t s = h.stream;
@@ -158,6 +205,7 @@ void build_mesh_tables(Handle& h)
     DevBuf<int> ja_nat; ja_nat.alloc(nnzb, s);
     pattern_kernel<true><<<cdiv(nv, 64), 64, 0, s>>>(nv, h.v2c_ptr.p, h.v2c_idx.p, cells, nullptr, A.ia.p, ja_nat.p, err.p);
     PNP_COUNT_LAUNCH();
+    box_coloring(h, L, ja_nat.p);
     color_and_layout(L, ja_nat.p, nullptr, s);      // fine-level colouring + colour-major row storage
   }
   A.val.alloc(9 * (size_t)nnzb, s);
@@ -236,6 +284,7 @@ void generate_box_mesh(Handle& h, int nx, int ny, int nz, double lx, double ly, 
   const size_t nv = (size_t)(nx + 1) * (ny + 1) * (nz + 1), ncube = (size_t)nx * ny * nz;
   if (nv > 0x7fffffffull / 16 || 6 * ncube > 0x7fffffffull / 4) throw Error(ERROR_INPUT_PAR, "box mesh too large for 32-bit indices");
   h.nv = (int)nv; h.nc = (int)(6 * ncube);
+  h.box_n[0] = nx; h.box_n[1] = ny; h.box_n[2] = nz;
   h.xyz.alloc(3 * nv, s); h.cells.alloc(4 * (size_t)h.nc, s);
   box_vertices_kernel<<<cdiv(nv, 256), 256, 0, s>>>(nx, ny, nz, lx, ly, lz, h.xyz.p); PNP_COUNT_LAUNCH();
   box_cells_kernel<<<cdiv(ncube, 256), 256, 0, s>>>(nx, ny, nz, reinterpret_cast<int4*>(h.cells.p)); PNP_COUNT_LAUNCH();
