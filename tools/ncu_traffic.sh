@@ -3,7 +3,7 @@
 N=${1:-256}
 python tools/probe_rows.py $N 9 1 > gpurun_out/traffic_plain_$N.log 2>&1 || exit 1
 timeout 420 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
-    --clock-control none --cache-control none -k regex:bsrt_row_kernel -c 20 --csv --log-file gpurun_out/traffic_gsd_n$N.csv \
+    --clock-control none --cache-control none -k regex:bsrt_row_kernel -c ${NLAUNCH:-20} --csv --log-file gpurun_out/traffic_gsd_n$N.csv \
     python tools/probe_rows.py $N 9 1 > gpurun_out/traffic_ncu_$N.log 2>&1
 echo "ncu exit $?"
 tail -2 gpurun_out/traffic_plain_$N.log gpurun_out/traffic_ncu_$N.log
