@@ -249,10 +249,10 @@ int block_pnp_stokes_solve(BlockSystem& S, const double* b, double* x, BlockStat
 
   const BsrT& Av = hv.hier.lv[0]->A;
   const size_t nvp = 3 * (size_t)Av.n;          // padded velocity length
-  DevBuf<double> vr, vz, vrs, vzs, tq, ts, tp, zp;
+  DevBuf<double> vr, vz, vrs, vzs, tq, tp, zp;
   vr.alloc(nvp, sv); vz.alloc(nvp, sv); vrs.alloc(nvp, sv); vzs.alloc(nvp, sv);
   vr.zero();                                     // the padding stays zero
-  tq.alloc(nq ? nq : 1, so); ts.alloc(ns, so); tp.alloc(np, so); zp.alloc(np, sp);
+  tq.alloc(nq ? nq : 1, so); tp.alloc(np, so); zp.alloc(np, sp);
   link.pass(sv, so);
 
   // ---- Stokes block: operator and block lower-triangular preconditioner
