@@ -1,0 +1,54 @@
+"""-m "not gpu": the parts of bench.py that run without a GPU — the reference arm (oracle on the
+host cores) prints exactly one JSON line with the contract's keys, rank != 0 stays silent under a
+multi-rank launch, and the SURVEY §8(d) byte model behaves."""
+import json
+import os
+import subprocess
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra=None, args=()):
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                           "--cpu-sample-n", "6", *args], capture_output=True, text=True, timeout=600, env=env)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = _run()
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "newton_steps_per_s" and d["unit"] == "Newton steps/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1e3) < 1e-6 * 1e3
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "Newton step" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["n"] == 256 and "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, ["--gpus", "2"])
+    assert out.returncode == 0 and out.stdout == ""
+
+
+def test_byte_model_counts_the_survey_terms():
+    sys.path.insert(0, ROOT)
+    import bench
+    st = types.SimpleNamespace(n_levels=3, level_rows=[1000, 100, 10], level_nnzb=[15000, 1700, 100])
+    nv, nc = 1000, 5400
+    one = bench.byte_model(st, nv, nc, 1, 30)
+    two = bench.byte_model(st, nv, nc, 2, 30)
+    # a second Krylov iteration adds one matvec, one cycle and the vectors of Gram-Schmidt step j = 1
+    b_spmv = [15000 * 76 + 1001 * 4 + 6 * 1000 * 8, 1700 * 76 + 101 * 4 + 6 * 100 * 8]
+    cycle = 3 * b_spmv[0] + 6 * (1000 + 100) * 8 + 3 * b_spmv[1] + 6 * (100 + 10) * 8
+    assert two - one == b_spmv[0] + cycle + (2 * 2 + 2) * 3 * nv * 8
+    # the [L | D | U] schedule reads less than the model, never more
+    assert bench.byte_model(st, nv, nc, 5, 30, shortcuts=True) < bench.byte_model(st, nv, nc, 5, 30)
+    # the K-cycle revisits the coarse levels
+    assert bench.byte_model(st, nv, nc, 5, 30, kcycle_levels=3) > bench.byte_model(st, nv, nc, 5, 30)
