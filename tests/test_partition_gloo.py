@@ -83,3 +83,28 @@ def test_world2_partition_halo_and_distributed_spmv(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_partition_colouring_is_proper_and_the_same_on_every_rank(oracle, pkg):
+    """the (i + j + k) mod 4 colouring the partition carries (global lattice position) is a proper
+    colouring of every rank's local mesh graph, ghosts included, and a vertex two ranks share gets the
+    same colour on both"""
+    import numpy as np
+    from importlib import import_module
+    part_mod = import_module("modular_pnp_b200.partition")
+    nx, ny, nz, world = 5, 4, 9, 3
+    seen = {}
+    for rank in range(world):
+        P = part_mod.box_slab_partition(nx, ny, nz, 2.0, 1.0, 1.6, rank, world)
+        col, cells = P["color"], P["cells"].reshape(-1, 4)
+        assert col.shape == (P["n_loc"],) and col.min() >= 0 and col.max() <= 3
+        # the four vertices of every cell carry the four colours (balanced triangulation)
+        assert np.all(np.sort(col[cells], axis=1) == np.arange(4)[None, :])
+        for g, c in zip(P["gids"], col):
+            assert seen.setdefault(int(g), int(c)) == int(c)
+    assert len(seen) == (nx + 1) * (ny + 1) * (nz + 1)
+    # and it is the colouring the device uses for a BoxMesh: same formula on the global numbering
+    G = oracle.Problem(nx, ny, nz, 2.0, 1.0, 1.6)
+    gcol = np.array([seen[g] for g in range(G.nv)])
+    gc = G.cells.reshape(-1, 4)
+    assert np.all(np.sort(gcol[gc], axis=1) == np.arange(4)[None, :])
