@@ -2,7 +2,7 @@
 (oracle/_ref/libpnpref.so, built by oracle/Makefile from /root/reference/include/EAFE.h and
 benchmarks/pnp_exact_solution/vector_linear_pnp_forms.h). Run in the authoring container only
 (needs /root/reference); the vectors travel with the repo.
-    python tests/golden/make_golden.py [main] [diode] [marker]
+    python tests/golden/make_golden.py [main] [diode] [marker] [newton]
 """
 import ctypes as C
 import os
@@ -106,7 +106,27 @@ def marker():
     print("marker golden vectors written")
 
 
+def newton():
+    """Newton history of BASELINE configs[0] (pnp_exact_solution, 50x10x10 box of [-1,1]x[-0.2,0.2]^2,
+    bsr.dat, main.cpp:317-356) from the oracle DRIVEN BY THE REFERENCE'S OWN ELEMENT KERNELS."""
+    import json
+    O.use_ref_kernels(True)
+    uu, res = O.newton_exact(50, 10, 10)
+    O.use_ref_kernels(False)
+    k = res.newton_its
+    P = O.Problem(50, 10, 10)
+    out = {"grid": [50, 10, 10], "lengths": [2.0, 0.4, 0.4], "newton_its": int(k), "converged": int(res.converged),
+           "initial_residual": float(res.initial_residual), "initial_max_residual": float(res.initial_max_residual),
+           "rel_res": [float(res.rel_res[i]) for i in range(k)], "max_res": [float(res.max_res[i]) for i in range(k)],
+           "krylov_its": [int(res.krylov_its[i]) for i in range(k)],
+           "max_nodal_error": float(np.abs(uu - P.exact).max()),
+           "solution_checksum": [float(np.sum(uu[c::3])) for c in range(3)]}
+    with open(os.path.join(ROOT, "tests", "golden", "newton_history_50x10x10.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("newton history written:", out["newton_its"], out["krylov_its"])
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["main", "diode", "marker"]
     for w in which:
-        {"main": main, "diode": diode, "marker": marker}[w]()
+        {"main": main, "diode": diode, "marker": marker, "newton": newton}[w]()

@@ -277,3 +277,24 @@ def test_diode_damped_newton_on_the_oracle(oracle):
     assert all(h[0] > 0 for h in hist)
     assert hist[0][1] < 1e-6 and hist[0][4] == 1            # the first update is cut back by the growth limit
     assert hist[-1][1] == 1.0 and hist[-1][2] < 1e-7        # full steps at the end
+
+
+def test_newton_history_matches_reference_driven_golden(oracle):
+    """BASELINE configs[0] (50x10x10, bsr.dat): the oracle with the RESTATED element kernels walks the
+    same Newton path as the golden history generated by driving the reference's own compiled kernels
+    (tests/golden/make_golden.py newton): same Newton count (8), same Krylov counts, residual
+    histories equal far below the linear-solver tolerance. The GPU path is compared with this
+    oracle run in tests/test_gpu_solver.py::test_newton_exact_solution_config."""
+    import json
+    g = json.load(open(os.path.join(GOLD, "newton_history_50x10x10.json")))
+    uu, res = oracle.newton_exact(*g["grid"], *g["lengths"])
+    assert res.newton_its == g["newton_its"] == 8 and res.converged == g["converged"] == 1
+    assert abs(res.initial_residual - g["initial_residual"]) <= 1e-12 * g["initial_residual"]
+    for k in range(res.newton_its):
+        assert abs(res.krylov_its[k] - g["krylov_its"][k]) <= 1
+        tol = 1e-6 if g["rel_res"][k] > 1e-6 else 1e-2      # the last steps sit at the linear-solver tolerance
+        assert abs(res.rel_res[k] - g["rel_res"][k]) <= tol * g["rel_res"][k]
+    # main.cpp:317-319: rel 1e-8 / max-res 1e-10
+    assert res.rel_res[res.newton_its - 1] < 1e-8 or res.max_res[res.newton_its - 1] < 1e-10
+    for c in range(3):
+        assert abs(np.sum(uu[c::3]) - g["solution_checksum"][c]) <= 1e-6 * max(1.0, abs(g["solution_checksum"][c]))
