@@ -43,13 +43,15 @@ def main():
                         RE=RE, ETA=ETA, AL=AL, BE=BE, GA=GA, A_eafe=A_eafe, A_jac=A_jac, b_res=b_res)
     # global fixture: the oracle assembler DRIVEN BY THE REFERENCE KERNELS on a 4x2x2 box
     O.use_ref_kernels(True)
-    P = O.Problem(4, 2, 2)
-    uu = P.exact + 0.1 * np.random.default_rng(1234).uniform(-1, 1, P.N)
-    uu[0::3] = np.round(uu[0::3] * 64) / 64
-    A, b = P.assemble(uu, use_eafe=True)
-    A2, _ = P.assemble(uu, use_eafe=False)
+    for grid in ((4, 2, 2), (8, 4, 4)):
+        P = O.Problem(*grid)
+        uu = P.exact + 0.1 * np.random.default_rng(1234).uniform(-1, 1, P.N)
+        uu[0::3] = np.round(uu[0::3] * 64) / 64
+        A, b = P.assemble(uu, use_eafe=True)
+        A2, _ = P.assemble(uu, use_eafe=False)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "assembled_%dx%dx%d.npz" % grid), uu=uu, IA=P.IA, JA=P.JA,
+                            A_eafe=A, A_galerkin=A2, b=b)
     O.use_ref_kernels(False)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "assembled_4x2x2.npz"), uu=uu, IA=P.IA, JA=P.JA, A_eafe=A, A_galerkin=A2, b=b)
     print("golden vectors written")
 
 

@@ -49,11 +49,12 @@ def test_element_kernels_match_reference_live(oracle):
         assert _rel(a, b) <= 1e-13
 
 
-def test_assembly_matches_reference_driven_golden(oracle):
+@pytest.mark.parametrize("grid", [(4, 2, 2), (8, 4, 4)])
+def test_assembly_matches_reference_driven_golden(oracle, grid):
     """global matrix assembled with the restated kernels == the one assembled by driving the
-    reference's own kernels (golden, 4x2x2 box, EAFE and Galerkin)"""
-    g = np.load(os.path.join(GOLD, "assembled_4x2x2.npz"))
-    P = oracle.Problem(4, 2, 2)
+    reference's own kernels (golden, 4x2x2 and 8x4x4 boxes, EAFE and Galerkin)"""
+    g = np.load(os.path.join(GOLD, "assembled_%dx%dx%d.npz" % grid))
+    P = oracle.Problem(*grid)
     assert np.array_equal(P.IA, g["IA"]) and np.array_equal(P.JA, g["JA"])
     A, b = P.assemble(g["uu"], use_eafe=True)
     assert _rel(A, g["A_eafe"]) <= 1e-13 and _rel(b, g["b"]) <= 1e-13
