@@ -40,6 +40,28 @@ def test_matrix_and_rhs_parity(oracle, pkg, gpu_lib, grid, use_eafe):
     g.close()
 
 
+@pytest.mark.parametrize("grid", [(4, 2, 2), (8, 4, 4)])
+def test_matrix_and_rhs_against_committed_golden(oracle, pkg, gpu_lib, grid):
+    """the same comparison against the COMMITTED fixtures (tests/golden/assembled_*.npz: the oracle
+    assembler driven by the reference's own compiled element kernels), EAFE and Galerkin"""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "assembled_%dx%dx%d.npz" % grid))
+    P = oracle.Problem(*grid)
+    uu = gold["uu"]
+    assert np.array_equal(uu, perturbed_state(P, quantize=True))      # the seeded input of the test above
+    g = gpu_problem(pkg, P, uu)
+    for use_eafe, key in ((True, "A_eafe"), (False, "A_galerkin")):
+        g.use_eafe(use_eafe)
+        g.assemble()
+        IA, JA, val = g.get_matrix()
+        assert np.array_equal(IA, gold["IA"]) and np.array_equal(JA, gold["JA"])
+        err = row_scaled_error(IA, val, gold[key])
+        assert err <= 2e-12, "%s row-scaled error %.3e" % (key, err)
+        b = g.get_rhs()
+        assert np.abs(b - gold["b"]).max() <= 1e-12 * np.abs(gold["b"]).max()
+    g.close()
+
+
 def test_matrix_parity_unquantized_is_conditioning_limited(oracle, pkg, gpu_lib):
     """Continuous random potentials: the reference's own d/(exp(d)-1) carries eps/|d| relative
     error, so parity is checked against 1e-12 + 8 eps/|d_min| per row."""
