@@ -85,7 +85,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def byte_model(stats, nv, nc, krylov_its, restart, kcycle_levels=0, shortcuts=False):
+def byte_model(stats, nv, nc, krylov_its, restart, kcycle_levels=0, shortcuts=False, stages=False):
     """Algorithmic bytes of one Newton step, SURVEY.md §8(d), from the run's actual level sizes
     and iteration count (fp64 = 8 B, int32 = 4 B; every array touched once per logical pass).
     shortcuts=False is the SURVEY model (a cycle = 3 full matrix sweeps per level, a matvec = 1);
@@ -122,13 +122,34 @@ def byte_model(stats, nv, nc, krylov_its, restart, kcycle_levels=0, shortcuts=Fa
     for it in range(max(krylov_its, 0)):
         j = it % restart
         b_kry += matvec[0] + b_vc + (2 * (j + 1) + 2) * N * 8
-    return b_asm + b_eafe + 2 * b_res + b_setup + b_kry + 4 * N * 8
+    total = b_asm + b_eafe + 2 * b_res + b_setup + b_kry + 4 * N * 8
+    if stages:
+        # the library's stage timers: "assemble" = Jacobian + EAFE + the rhs residual, "residual" = the
+        # residual after the update (the one the next step re-uses as its rhs)
+        return {"assemble": b_asm + b_eafe + b_res, "amg_setup": b_setup, "krylov": b_kry, "residual": b_res, "total": total}
+    return total
+
+
+CPU_EST_S = {16: 0.3, 24: 1.2, 32: 3.5, 40: 7.0, 48: 13.0, 56: 22.0, 64: 36.0}     # oracle, 1 core, first Newton step (measured, r01/r02)
+
+
+def cpu_sample_n_for(steps, budget_s, cap):
+    """largest sample box whose `steps` full Newton steps fit the wall budget of the CPU arm"""
+    if cap < min(CPU_EST_S):
+        return cap
+    best = min(CPU_EST_S)
+    for n in sorted(CPU_EST_S):
+        if n <= cap and steps * CPU_EST_S[n] <= budget_s:
+            best = n
+    return best
 
 
 def cpu_reference_leg(sample_n, steps=1):
-    """Oracle (reference element kernels when oracle/_ref is present + restated DOLFIN/FASP
-    orchestration), one host core like the serial reference, first Newton step on a bounded
-    sample box; returns seconds per step on the sample and its dof count."""
+    """The reference path on the host: the oracle (the reference's OWN compiled element kernels when
+    oracle/_ref is present + the restated DOLFIN assembler / FASP UA-AMG V(1,1) + pvfgmres of bsr.dat),
+    serial like the reference (CMakeLists.txt links FASP without OpenMP), first Newton step of the same
+    physics on a sample_n^3 box. Nothing is extrapolated: returns the measured seconds of every step,
+    the dof count and the Krylov iterations of that box."""
     from oracle import oracle as O
     used_ref = False
     if O.ref_available():
@@ -145,7 +166,61 @@ def cpu_reference_leg(sample_n, steps=1):
     if used_ref:
         O.use_ref_kernels(False)
     dof = 3 * (sample_n + 1) ** 3
-    return min(ts), dof, its, used_ref
+    return ts, dof, its, used_ref
+
+
+def workload_name(n):
+    return "pnp_exact_solution physics, %d^3 Kuhn box of [-1,1]^3 (%.2f M dof), Newton step 1 from the Dirichlet interpolant" % (n, 3 * (n + 1) ** 3 / 1e6)
+
+
+def multi_gpu_parity(pkg, problems, partition_fn, dist, rank, world, dev, it, amg):
+    """Correctness gate of the N>1 path, OUTSIDE the timed region: the partitioned
+    Newton step (halo exchange + allreduce over NCCL) against the single-GPU path on the same global
+    mesh, same bars as tests/test_gpu_multi.py: initial residual norms 1e-12, three Newton steps'
+    residuals 2e-3 (different aggregates per partition -> different but equally valid preconditioner),
+    solution 1e-4. Raises on failure; the result goes into the JSON line."""
+    import numpy as np
+    import torch
+    nx, ny, nz, lx, ly, lz = 24, 10, max(24, 4 * world), 2.0, 0.8, 2.0
+    P = partition_fn(nx, ny, nz, lx, ly, lz, rank, world)
+    g = pkg.PNP(P["xyz"], P["cells"], device=dev)
+    uid = [pkg.capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    g.comm_init(uid[0], rank, world); g.set_partition(P)
+    f = problems.exact_solution_fields(P["xyz"][0::3])
+    g.set_coefficients(f["eps"], f["fixed"], f["diff"], f["val"], f["reac"])
+    g.set_dirichlet((3 * P["bc_vertices"][:, None] + np.arange(3)).ravel().astype(np.int32))
+    g.set_solution(f["uu0"])
+    r0 = g.residual()
+    hist = [g.newton_step(it, amg) for _ in range(3)]
+    uu = g.get_solution()[:3 * P["n_own"]]
+    gd = (3 * np.asarray(P["gids"])[:P["n_own"], None] + np.arange(3)).ravel()
+    g.close()
+    # every rank checks its owned part against the single-GPU solution computed by rank 0
+    out = [None]
+    if rank == 0:
+        s = pkg.PNP(box=(nx, ny, nz, lx, ly, lz), device=dev)
+        pr = problems.exact_solution_problem(nx, ny, nz, lx, ly, lz)
+        s.set_coefficients(pr["eps"], pr["fixed"], pr["diff"], pr["val"], pr["reac"]); s.set_dirichlet(pr["bc_dofs"]); s.set_solution(pr["uu0"])
+        q0 = s.residual()
+        ref = [s.newton_step(it, amg) for _ in range(3)]
+        out = [(q0, ref, s.get_solution())]
+        s.close()
+    dist.broadcast_object_list(out, src=0)
+    q0, ref, uu_ref = out[0]
+    res0 = max(abs(r0[0] - q0[0]) / q0[0], abs(r0[1] - q0[1]) / q0[1])
+    step = max(abs(h[1] - r[1]) / r[1] for h, r in zip(hist, ref))
+    sol = float(np.abs(uu - uu_ref[gd]).max())
+    ok = res0 <= 1e-12 and step <= 2e-3 and sol <= 1e-4 and all(h[0] > 0 for h in hist) and all(r[0] > 0 for r in ref)
+    t = torch.tensor([res0, step, sol, 0.0 if ok else 1.0], device="cuda:%d" % dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res0, step, sol, bad = [float(v) for v in t.tolist()]
+    rep = {"mesh": "%dx%dx%d box, %d ranks" % (nx, ny, nz, world), "initial_residual_rel_diff": res0, "newton_step_residual_rel_diff": step,
+           "solution_max_abs_diff": sol, "krylov_its_partitioned": [h[0] for h in hist], "krylov_its_single_gpu": [r[0] for r in ref],
+           "bars": {"initial_residual": 1e-12, "newton_step_residual": 2e-3, "solution": 1e-4}, "ok": bad == 0.0}
+    if bad != 0.0:
+        raise RuntimeError("multi-GPU parity gate failed: %r" % (rep,))
+    return rep
 
 
 _JSON_FD = None
@@ -179,7 +254,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", "--box-n", dest="n", type=int, default=int(os.environ.get("PNPB200_BENCH_N", "256")))
-    ap.add_argument("--cpu-sample-n", type=int, default=48)
+    ap.add_argument("--cpu-sample-n", type=int, default=64,
+                    help="largest sample box of the CPU legs (the reference arm shrinks it until its K steps fit --cpu-budget-s)")
+    ap.add_argument("--cpu-budget-s", type=float, default=300.0, help="wall budget of the timed steps of --impl reference")
     ap.add_argument("--cycle", default=os.environ.get("PNPB200_BENCH_CYCLE", "NA"),
                     help="AMG_cycle_type: V (bsr.dat) or NA (FASP nonlinear AMLI = K-cycle; needed above ~20 M dof where V exceeds itsolver_maxit)")
     ap.add_argument("--profile", action="store_true",
@@ -192,27 +269,38 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n = args.n
     nv, nc = (n + 1) ** 3, 6 * n ** 3
-    workload = "pnp_exact_solution physics, %d^3 Kuhn box of [-1,1]^3 (%.1f M dof), Newton step 1 from the Dirichlet interpolant" % (n, 3 * nv / 1e6)
-    config = {"workload": workload, "n": n, "dofs": 3 * nv, "cells": nc, "solver": "bsr.dat (UA-AMG %s-cycle(1,1) mc-GS + vFGMRES(30), tol 1e-6, maxit %d)" % (args.cycle, args.maxit),
-              "l2_policy": "inputs_larger_than_l2"}
+    config = {"workload": workload_name(n), "n": n, "dofs": 3 * nv, "cells": nc,
+              "solver": "bsr.dat (UA-AMG %s-cycle(1,1) mc-GS + vFGMRES(30), tol 1e-6, maxit %d)" % (args.cycle, args.maxit),
+              "amg_cycle_type": args.cycle, "l2_policy": "inputs_larger_than_l2"}
 
     if args.impl == "reference":
+        # CPU arm: the reference path on the host cores, UN-EXTRAPOLATED. Every timed step is one full
+        # first Newton step of the same physics on an m^3 sample box, m the largest box whose K steps fit
+        # the wall budget; value = measured steps/s AT THAT m (config.n = m says so). The reference's
+        # solver configuration is bsr.dat's V-cycle, which is what the oracle runs.
         if rank != 0:
             return 0
         W, K = max(args.warmup, 0), max(args.steps, 1)
-        for _ in range(min(W, 1)):
-            cpu_reference_leg(16)
-        sec, dof, its, used_ref = cpu_reference_leg(args.cpu_sample_n, steps=min(K, 2))
-        scale = dof / float(3 * nv)             # linear-in-dof extrapolation (favours the CPU: its grow with n)
-        val = scale / sec
-        sample = ("first Newton step on a %d^3 box (%d dof, %d Krylov its), %.2f s on 1 core; scaled linearly in dof to the %d^3 workload"
-                  % (args.cpu_sample_n, dof, its, sec, n))
-        emit(({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
-                          "warmup": W, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1,
-                                           "kind": "port", "sample": sample + ("; reference element kernels (oracle/_ref)" if used_ref else "")},
-                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        m = cpu_sample_n_for(K, args.cpu_budget_s, args.cpu_sample_n)
+        for _ in range(min(W, 3)):
+            cpu_reference_leg(16)                # warm-up: page in the libraries / element kernels (small box)
+        ts, dof, its, used_ref = cpu_reference_leg(m, steps=K)
+        sec = sum(ts) / len(ts)
+        val = 1.0 / sec
+        cfg_ref = {"workload": workload_name(m) + " [bounded sample of the %d^3 workload]" % n, "n": m, "dofs": dof, "cells": 6 * m ** 3,
+                   "solver": "bsr.dat (UA-AMG V-cycle(1,1) GS + vFGMRES(30), tol 1e-6, maxit 100)", "amg_cycle_type": "V",
+                   "bench_workload_n": n}
+        sample = ("%d timed first Newton steps on a %d^3 box (%d dof, %d Krylov its), mean %.2f s per step, serial (1 core of %d) like the reference; "
+                  "not extrapolated%s" % (K, m, dof, its, sec, os.cpu_count() or 0, "; reference element kernels (oracle/_ref)" if used_ref else ""))
+        emit({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+              "warmup": W, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg_ref, "extrapolated": False,
+              "krylov_its_per_step": its, "us_per_dof": 1e6 * sec / dof, "seconds_per_step_each": ts,
+              "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference" if used_ref else "port", "sample": sample},
+              # context only, never the headline: what the measured us/dof would mean at the bench size if the
+              # cost were linear in dof (it is not: V-cycle iterations grow with n and exceed maxit at 256^3)
+              "linear_in_dof_projection": {"n": n, "steps_per_s": val * dof / float(3 * nv), "note": "projection, not a measurement"},
+              "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return 0
 
     import numpy as np
@@ -230,6 +318,12 @@ def main():
     dev = local_rank
     torch.cuda.set_device(dev)
 
+    cyc = {"V": 1, "W": 2, "A": 3, "NA": 4}[args.cycle]
+    it, amg = pkg.default_params(maxit=args.maxit, cycle_type=cyc)
+    parity = None
+    if world > 1 and not args.profile:
+        partition = import_module("modular_pnp_b200.partition")
+        parity = multi_gpu_parity(pkg, problems, partition.box_slab_partition, dist, rank, world, dev, it, amg)
     if world == 1:
         g = pkg.PNP(box=(n, n, n, 2.0, 2.0, 2.0), device=dev)
         pr = problems.exact_solution_problem(n, n, n, 2.0, 2.0, 2.0)
@@ -251,8 +345,6 @@ def main():
         g.set_dirichlet((3 * part["bc_vertices"][:, None] + np.arange(3)[None, :]).ravel().astype(np.int32))
         n_local_dofs = 3 * part["n_loc"]
         del part
-    cyc = {"V": 1, "W": 2, "A": 3, "NA": 4}[args.cycle]
-    it, amg = pkg.default_params(maxit=args.maxit, cycle_type=cyc)
     uu0_host = torch.from_numpy(pr["uu0"]).pin_memory()
     uu_out_host = torch.empty_like(uu0_host).pin_memory()
     uu0_dev = uu0_host.to("cuda:%d" % dev)
@@ -297,6 +389,8 @@ def main():
     W, K = max(args.warmup, 3), max(args.steps, 1)
     if args.profile:
         W, K = 1, 1
+    L.pnpb200_set_solution_device(h, C.c_void_p(uu0_dev.data_ptr()))
+    init_res = g.residual()                 # ||F(u0)||: the residual after the step is reported relative to it
     for _ in range(W):
         step_resident()
     sampler = ClockSampler(dev)
@@ -338,7 +432,12 @@ def main():
     kk = kits if kits > 0 else stats.krylov_its
     b_step = byte_model(stats, nv, nc, kk, it.restart, kcycle_levels=klev)
     b_sched = byte_model(stats, nv, nc, kk, it.restart, kcycle_levels=klev, shortcuts=True)
+    b_strict = byte_model(stats, nv, nc, kk, it.restart, kcycle_levels=0)      # SURVEY 8(d) as written: one V(1,1) per iteration
+    b_stage = byte_model(stats, nv, nc, kk, it.restart, kcycle_levels=klev, stages=True)
     step_gbs = b_step / (ms / K) / 1e6
+    stage_ms = {"assemble": stats.ms_assemble, "amg_setup": stats.ms_setup, "krylov": stats.ms_krylov, "residual": stats.ms_residual}
+    stage_frac = {k: (b_stage[k] / stage_ms[k] / 1e6 / peak if stage_ms[k] > 0 else None) for k in stage_ms}
+    l2_0, _ = init_res
     # traffic: dram bytes of one sweep (dram__bytes_read.sum + dram__bytes_write.sum over its colour
     # launches) from the committed single-pass ncu capture taken at the same n (tools/ncu_traffic.sh)
     traffic, traffic_note = None, None
@@ -370,11 +469,13 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=("1 GPU" if world == 1 else "%d GPUs: block rows in z-slabs of a %dx%dx%d box (%.1f M dof), NCCL halo exchange at every AMG level + fp64 allreduce, aggregates local to a rank, replicated dense coarsest solve" % (world, n, n, n * world, 3 * (n + 1) * (n + 1) * (n * world + 1) / 1e6))),
-               "krylov_its_per_step": its, "krylov_status_ok": bool(kits > 0),
-               "relative_residual_after_step": None if last is None else last[1],
+               "krylov_its_per_step": its, "krylov_status_ok": bool(kits > 0), "amg_cycle_type": args.cycle,
+               "l2_residual_after_step": None if last is None else last[1],
+               "relative_residual_after_step": None if last is None else last[1] / l2_0,
+               "multi_gpu_parity": parity,
                "levels": [[stats.level_rows[l], stats.level_nnzb[l], stats.level_colors[l]] for l in range(stats.n_levels)],
-               "stage_ms_last_step": {"assemble": stats.ms_assemble, "amg_setup": stats.ms_setup, "krylov": stats.ms_krylov,
-                                      "residual": stats.ms_residual},
+               "stage_ms_last_step": stage_ms,
+               "stage_roofline_frac": dict(stage_frac, note="SURVEY 8(d) algorithmic bytes of the stage / its time / peak; assemble = B_asmJ + B_eafe + one B_res (the rhs), residual = one B_res"),
                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": n_local_dofs * 8 * world, "d2h_bytes_per_step": n_local_dofs * 8 * world},
                "gpu_launches": launches,
                "clocks": clocks,
@@ -387,21 +488,47 @@ def main():
                                      "frac": spmv_bytes / spmv_ms / 1e6 / peak, "ms": spmv_ms, "algorithmic_bytes": spmv_bytes},
                             "whole_step": {"algorithmic_bytes": b_step, "achieved": step_gbs, "frac": step_gbs / peak,
                                            "note": "algorithmic_bytes = SURVEY 8(d) model (3 full sweeps + 1 matvec per cycle); scheduled_bytes = what the [L|D|U] schedule reads (2.5 passes)",
-                                           "scheduled_bytes": b_sched, "scheduled_frac": b_sched / (ms / K) / 1e6 / peak}}}
-        # CPU baseline on the box's host cores (bounded sample), N=1 only
+                                           "scheduled_bytes": b_sched, "scheduled_frac": b_sched / (ms / K) / 1e6 / peak,
+                                           "strict_v11_bytes": b_strict, "strict_v11_frac": b_strict / (ms / K) / 1e6 / peak,
+                                           "strict_note": "strict_v11 = the 8(d) formula as written (ONE V(1,1) cycle per Krylov iteration) on this run's levels and iteration count; algorithmic_bytes adds the K-cycle's repeated coarse-level visits"}}}
+        # the step must actually have solved the linear system and reduced the residual
+        if not (kits > 0 and last is not None and last[1] == last[1] and last[1] < 1e3 * l2_0):
+            out["invalid"] = "Krylov status %r / residual %r after the step" % (kits, None if last is None else last[1])
+        # CPU baseline on the box's host cores, N=1 only: ONE measured first Newton step of the oracle on the
+        # sample box (not extrapolated), and the GPU timed on the SAME box right here, so that a same-config
+        # pair exists
         if world == 1:
             try:
-                sec, dof, cits, used_ref = cpu_reference_leg(args.cpu_sample_n)
-                cval = (dof / float(3 * nv)) / sec
-                out["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": 1, "kind": "port",
-                                       "host_cores_available": os.cpu_count(),
-                                       "sample": "oracle first Newton step on a %d^3 box (%d dof, %d Krylov its) took %.2f s on 1 core; "
-                                                 "scaled linearly in dof to %d^3%s" % (args.cpu_sample_n, dof, cits, sec, n,
-                                                                                       "; reference element kernels (oracle/_ref)" if used_ref else "")}
+                m = args.cpu_sample_n
+                ts, dof, cits, used_ref = cpu_reference_leg(m)
+                sec = ts[0]
+                out["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": 1, "kind": "reference" if used_ref else "port",
+                                       "host_cores_available": os.cpu_count(), "n": m, "dofs": dof, "us_per_dof": 1e6 * sec / dof,
+                                       "sample": "ONE measured first Newton step of the oracle on a %d^3 box (%d dof, V-cycle, %d Krylov its): %.2f s on 1 core "
+                                                 "(serial like the reference); value = steps/s AT THAT SIZE, not extrapolated to %d^3%s" % (
+                                                     m, dof, cits, sec, n, "; reference element kernels (oracle/_ref)" if used_ref else "")}
+                g.close(); g = None
+                gs = pkg.PNP(box=(m, m, m, 2.0, 2.0, 2.0), device=dev)
+                prs = problems.exact_solution_problem(m, m, m, 2.0, 2.0, 2.0)
+                gs.set_coefficients(prs["eps"], prs["fixed"], prs["diff"], prs["val"], prs["reac"]); gs.set_dirichlet(prs["bc_dofs"])
+                itv, amgv = pkg.default_params(maxit=args.maxit, cycle_type=1)          # bsr.dat: V-cycle, like the CPU leg
+                same = {}
+                for nm, (i_, a_) in (("V", (itv, amgv)), (args.cycle, (it, amg))):
+                    for _ in range(3):
+                        gs.set_solution(prs["uu0"]); r_ = gs.newton_step(i_, a_)
+                    t0 = time.perf_counter()
+                    for _ in range(5):
+                        gs.set_solution(prs["uu0"]); r_ = gs.newton_step(i_, a_)     # host buffers in, like e2e
+                    same[nm] = {"gpu_steps_per_s": 5.0 / (time.perf_counter() - t0), "gpu_krylov_its": r_[0]}
+                gs.close()
+                out["cpu_same_n"] = {"n": m, "dofs": dof, "cpu_steps_per_s": 1.0 / sec, "cpu_krylov_its": cits, "cpu_cycle": "V",
+                                     "gpu": same, "ratio_same_config_V": same["V"]["gpu_steps_per_s"] * sec,
+                                     "note": "GPU: host clock around 5 x (pnpb200_set_solution from host memory + pnpb200_newton_step), same box, same bsr.dat V-cycle as the CPU leg"}
             except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
-                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "unavailable: %r" % (e,)}
+                out.setdefault("cpu_baseline", {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "unavailable: %r" % (e,)})
         emit(out)
-    g.close()
+    if g is not None:
+        g.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

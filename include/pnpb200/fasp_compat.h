@@ -33,6 +33,7 @@ typedef double REAL;
 #define ERROR_SOLVER_TYPE  -40
 #define ERROR_SOLVER_MAXIT -48
 #define ERROR_SOLVER_EXIT  -49
+#define ERROR_SOLVER_MISC  -45   /* FASP: "unknown solver runtime error" — singular coarsest level */
 #define ERROR_UNKNOWN      -99
 #define ERROR_DEVICE      -120   /* pnp-b200: CUDA device / kernel failure (no CPU fallback) */
 

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(1024) dense_invert_kernel(int nd, double* __re
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
-      if (tid == 0) { s_piv = bi; if (!(bv > 0.0)) *singular = 1; }
+      if (tid == 0) { s_piv = bi; if (!(bv > 0.0) || !isfinite(bv)) *singular = 1; }
     }
     __syncthreads();
     const int pv = s_piv;
@@ -750,8 +750,15 @@ __global__ void dense_matvec_rows_kernel(int nrows, int row0, int nd, const doub
   if (lane == 0) x[row] = a;
 }
 
-// coarsest level: every rank inverts the (small) GLOBAL coarsest matrix
-void setup_coarsest(Handle& h)
+// Largest coarsest level (scalar unknowns, global) that gets the explicit dense inverse. One CTA runs
+// the Gauss-Jordan elimination (O(nd^3) on one SM: 0.3 ms at nd = 300, the bsr.dat case; ~40 ms at
+// 1536), so anything bigger — a failed coarsening step, the multi-GPU early stop — is solved
+// iteratively instead (solve_coarsest_sweeps).
+constexpr int DENSE_COARSEST_MAX = 1536;
+
+// coarsest level: every rank inverts the (small) GLOBAL coarsest matrix. Returns false if a pivot
+// was zero or not finite (the inverse is unusable).
+bool setup_coarsest(Handle& h)
 {
   cudaStream_t s = h.stream;
   Hierarchy& H = h.hier;
@@ -766,7 +773,7 @@ void setup_coarsest(Handle& h)
   int maxown = 1;
   for (int r = 0; r < nr; ++r) { off[r + 1] = off[r] + cnt[r]; if (cnt[r] > maxown) maxown = cnt[r]; }
   const int ng = off[nr], nd = 3 * ng;
-  if (nd > 6144) throw Error(ERROR_AMG_COARSEING, "coarsest level too large for the dense solver");
+  if (nd > DENSE_COARSEST_MAX) throw Error(ERROR_AMG_COARSEING, "coarsest level too large for the dense solver");
   H.nd = nd; H.c_own = own; H.c_row0 = 3 * off[me]; H.c_maxown3 = 3 * maxown; H.c_nranks = nr;
   std::vector<int> off3(nr), cnt3(nr);
   for (int r = 0; r < nr; ++r) { off3[r] = 3 * off[r]; cnt3[r] = 3 * cnt[r]; }
@@ -796,8 +803,31 @@ void setup_coarsest(Handle& h)
   identity_kernel<<<cdiv((size_t)nd * nd, 256), 256, 0, s>>>(nd, H.dense_inv.p); PNP_COUNT_LAUNCH();
   dense_invert_kernel<<<1, 1024, 0, s>>>(nd, D.p, H.dense_inv.p, colk.p, sing.p); PNP_COUNT_LAUNCH();
   H.c_bpad.alloc((size_t)3 * maxown, s); H.c_ball.alloc((size_t)3 * maxown * nr, s); H.c_bglob.alloc(nd, s);
+  int hsing = 0;
+  PNP_CUDA(cudaMemcpyAsync(&hsing, sing.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   PNP_CUDA(cudaStreamSynchronize(s));     // host staging vectors above go out of scope
   PNP_LAUNCH_CHECK();
+  return hsing == 0;
+}
+
+// Coarsest level too large (or too singular) for the dense inverse: COARSEST_SWEEPS symmetric
+// multicolour Gauss-Seidel sweeps from a zero initial guess, in sweep space like every other level
+// (multi-GPU: hybrid GS with a halo exchange before every sweep).
+constexpr int COARSEST_SWEEPS = 8;
+void solve_coarsest_sweeps(Handle& h, Level& Z, const double* b, double* x)
+{
+  cudaStream_t s = h.stream;
+  const bool dist = h.comm.active();
+  const size_t m = 3 * (size_t)Z.A.n, mo = 3 * (size_t)owned_rows(Z);
+  if (m > mo) PNP_CUDA(cudaMemsetAsync(x + mo, 0, (m - mo) * sizeof(double), s));
+  mcgs_sweep_from_zero(Z, b, x, s);
+  for (int k = 0; k < COARSEST_SWEEPS; ++k) {
+    if (dist) halo_exchange(h, Z.halo, x, true);
+    mcgs_sweep(Z, b, x, true, s);
+    if (k + 1 == COARSEST_SWEEPS) break;
+    if (dist) halo_exchange(h, Z.halo, x, true);
+    mcgs_sweep(Z, b, x, false, s);
+  }
 }
 
 void solve_coarsest(Handle& h, const double* b, double* x)
@@ -858,12 +888,25 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
     alloc_level_vectors(C, s);
     ++l;
   }
+  if (!reuse) lv.resize(l + 1);
+  // coarsest level: explicit dense inverse when it is small (the bsr.dat case, <= coarse_dof rows),
+  // Gauss-Seidel sweeps when coarsening stopped early or a pivot of the inverse was unusable
+  {
+    int nglob, nmin;
+    global_rows(h, owned_rows(*lv.back()), &nglob, &nmin);
+    bool dense = 3 * (long)nglob <= DENSE_COARSEST_MAX;
+    if (reuse && dense != h.hier.coarse_dense) throw Error(ERROR_SOLVER_MISC, "coarsest level changed its solver under hierarchy reuse");
+    if (dense && !setup_coarsest(h)) {
+      if (reuse) throw Error(ERROR_SOLVER_MISC, "coarsest level is singular");
+      dense = false;
+    }
+    h.hier.coarse_dense = dense;
+  }
   if (!reuse) {
-    lv.resize(l + 1);
-    // grid transfer maps in sweep space; the coarsest level (dense solve) keeps row-id order
+    // grid transfer maps in sweep space; a coarsest level with the dense solve keeps row-id order
     for (int k = 0; k + 1 < (int)lv.size(); ++k) {
       Level& Lk = *lv[k]; Level& Ck = *lv[k + 1];
-      Lk.coarse_identity = (k + 2 == (int)lv.size());
+      Lk.coarse_identity = (k + 2 == (int)lv.size()) && h.hier.coarse_dense;
       const int nk = Lk.A.n;
       Lk.agg_pos.alloc(nk, s); Lk.agg_rows_pos.alloc(nk, s);
       transfer_maps_kernel<<<cdiv(nk, 256), 256, 0, s>>>(nk, Lk.A.vrowid.p, Lk.A.pos.p, Lk.agg.p, Lk.agg_rows.p,
@@ -871,7 +914,6 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
       PNP_COUNT_LAUNCH();
     }
   }
-  setup_coarsest(h);
   h.hier.symbolic_valid = true;
   if (cfg.print_level > 0) {
     PNP_CUDA(cudaStreamSynchronize(s));
@@ -994,7 +1036,7 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
   cudaStream_t s = h.stream;
   const int nl = (int)h.hier.lv.size();
   Level& L = *h.hier.lv[l];
-  if (l == nl - 1) { solve_coarsest(h, b, x); return; }
+  if (l == nl - 1) { if (h.hier.coarse_dense) solve_coarsest(h, b, x); else solve_coarsest_sweeps(h, L, b, x); return; }
   const bool kcyc = cfg.cycle_type != V_CYCLE && l <= cfg.kcycle_levels;
   if (!kcyc) { mg_cycle(h, cfg, l, b, x, nullptr); return; }
   // K-cycle: two GCR steps preconditioned by the cycle of this level (device scalars only;
@@ -1032,10 +1074,15 @@ bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, 
   cudaStream_t s = h.stream;
   auto& lv = h.hier.lv;
   const int nl = (int)lv.size();
-  if (nl == 1) {
+  if (nl == 1) {       // no coarse grid at all: the "cycle" is the coarsest-level solve on the fine matrix
     Level& Z = *lv[0];
-    vec_set(z, 0.0, 3 * (size_t)Z.A.n, s);
-    for (int k = 0; k < cfg.presmooth; ++k) mcgs_sweep(Z, r, z, false, s);
+    if (h.hier.coarse_dense) {      // the dense solve works in row-id order
+      double* t0 = Z.b.p; double* t1 = Z.x.p;     // level work vectors: unused without a cycle
+      vec_from_sweep(Z.A, r, t0, s);
+      solve_coarsest(h, t0, t1);
+      vec_to_sweep(Z.A, t1, z, s);
+    } else solve_coarsest_sweeps(h, Z, r, z);
+    (void)cfg; (void)s;
     return false;
   }
   return mg_cycle(h, cfg, 0, r, z, Az);

@@ -379,12 +379,18 @@ __global__ void __launch_bounds__(1024) finalize_norm_kernel(int nblk, const dou
 // nodal (P1): exact with the element mass matrix det/120 (1 + delta_rs) and the constant gradient.
 __global__ void __launch_bounds__(256)
 error_cells_kernel(int nc, const int4* __restrict__ cells, const double* __restrict__ xyz,
-                   const double* __restrict__ uu, const double* __restrict__ exact, double* __restrict__ partial)
+                   const double* __restrict__ uu, const double* __restrict__ exact,
+                   const int* __restrict__ vowner, int me, double* __restrict__ partial)
 {
   __shared__ double sm[32];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double l2 = 0.0, h1 = 0.0;
-  if (c < nc) {
+  bool mine = c < nc;
+  if (mine && vowner) {          // multi-GPU: a ghost-layer cell is counted by the lowest owner rank of its vertices
+    const int4 cv = cells[c];
+    mine = min(min(vowner[cv.x], vowner[cv.y]), min(vowner[cv.z], vowner[cv.w])) == me;
+  }
+  if (mine) {
     const int4 cv = cells[c];
     const int v[4] = {cv.x, cv.y, cv.z, cv.w};
     double x[4][3], g[4][3], det;
@@ -591,9 +597,13 @@ void error_norms(Handle& h, const double* d_exact, double* l2, double* h1)
   cudaStream_t s = h.stream;
   const int nblk = cdiv(h.nc, 256);
   h.red.alloc(2 * (size_t)nblk + 2, s);
-  error_cells_kernel<<<nblk, 256, 0, s>>>(h.nc, reinterpret_cast<const int4*>(h.cells.p), h.xyz.p, h.uu.p, d_exact, h.red.p + 2);
+  const bool dist = h.comm.active() && h.vowner.p;
+  if (dist) halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
+  error_cells_kernel<<<nblk, 256, 0, s>>>(h.nc, reinterpret_cast<const int4*>(h.cells.p), h.xyz.p, h.uu.p, d_exact,
+                                          dist ? h.vowner.p : nullptr, h.comm.rank, h.red.p + 2);
   PNP_COUNT_LAUNCH();
   finalize_sum2_kernel<<<1, 1024, 0, s>>>(nblk, h.red.p + 2, h.red.p); PNP_COUNT_LAUNCH();
+  comm_allreduce(h, h.red.p, 2, false);          // all ranks return the global norms
   PNP_CUDA(cudaMemcpyAsync(h.h_red, h.red.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   PNP_CUDA(cudaStreamSynchronize(s));
   *l2 = sqrt(h.h_red[0]);

@@ -128,8 +128,8 @@ int fgmres_ops(Handle& h, size_t n, const Op& A, const Op& M, const double* b, d
   const double den = b_norm > 0.0 ? b_norm : r_norm;
   const double epsilon = cfg.tol * den;
   if (relres_out) *relres_out = den > 0.0 ? r_norm / den : 0.0;
+  if (!std::isfinite(r_norm) || !std::isfinite(b_norm)) return ERROR_SOLVER_EXIT;   // before the NaN-blind comparison
   if (!(r_norm > epsilon)) return 0;
-  if (!std::isfinite(r_norm)) return ERROR_SOLVER_EXIT;
   int iter = 0, Restart = restart_max;
   double cr = 1.0;
   bool converged = false;

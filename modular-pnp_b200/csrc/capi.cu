@@ -407,6 +407,7 @@ int pnpb200_test_solver(pnpb200_handle* ph, const double* target, double* x, con
     Handle& h = ph->h; cudaStream_t s = h.stream;
     PNP_CUDA(cudaSetDevice(h.device));
     g_launches = 0;
+    halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
     assemble_system(h);                                   // linear_pnp.cpp:137
     const size_t N = 3 * (size_t)h.nv;
     DevBuf<double> t; t.alloc(N, s); t.upload(target, N);

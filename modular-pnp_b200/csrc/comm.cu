@@ -153,6 +153,19 @@ int pnpb200_set_partition(pnpb200_handle* ph, int n_owned, int n_neighbors, cons
     Handle& h = ph->h; cudaStream_t s = h.stream;
     PNP_CUDA(cudaSetDevice(h.device));
     if (n_owned > h.nv) throw Error(ERROR_INPUT_PAR, "n_owned exceeds the local vertex count");
+    if (n_neighbors > 0 && (!neighbor_ranks || !send_ptr || !recv_ptr)) throw Error(ERROR_INPUT_PAR, "neighbour lists missing");
+    if (n_neighbors > 0 && !h.comm.active()) throw Error(ERROR_INPUT_PAR, "pnpb200_set_partition with neighbours needs pnpb200_comm_init first");
+    if (n_neighbors > 0 && send_ptr[0] != 0) throw Error(ERROR_INPUT_PAR, "send_ptr must start at 0");
+    for (int k = 0; k < n_neighbors; ++k) {
+      if (neighbor_ranks[k] < 0 || neighbor_ranks[k] >= h.comm.nranks || neighbor_ranks[k] == h.comm.rank)
+        throw Error(ERROR_INPUT_PAR, "neighbour rank out of range (or this rank itself)");
+      for (int q = 0; q < k; ++q) if (neighbor_ranks[q] == neighbor_ranks[k]) throw Error(ERROR_INPUT_PAR, "neighbour rank listed twice");
+      if (send_ptr[k + 1] < send_ptr[k] || recv_ptr[k + 1] < recv_ptr[k]) throw Error(ERROR_INPUT_PAR, "send_ptr / recv_ptr must be non-decreasing");
+    }
+    if (n_neighbors > 0 && send_ptr[n_neighbors] > 0 && !send_idx) throw Error(ERROR_INPUT_PAR, "send_idx missing");
+    if (n_neighbors > 0 && (recv_ptr[0] != n_owned || recv_ptr[n_neighbors] != h.nv))
+      throw Error(ERROR_INPUT_PAR, "the ghost ranges must tile [n_owned, n_local)");
+    if (n_neighbors == 0 && n_owned != h.nv) throw Error(ERROR_INPUT_PAR, "ghost vertices without a neighbour");
     Level& F = *h.hier.lv[0];
     Halo& c = F.halo;
     F.n_own = n_owned;
@@ -174,6 +187,11 @@ int pnpb200_set_partition(pnpb200_handle* ph, int n_owned, int n_neighbors, cons
     for (size_t i = 3 * (size_t)n_owned; i < N; ++i) f[i] = 1;
     h.bcflag.upload(f.data(), N);
     h.rhs_current = false;
+    // owner rank of every local vertex: a cell that several ranks hold (ghost layer) belongs to the
+    // lowest owner rank among its vertices, a rule every holder evaluates alike (error_norms)
+    std::vector<int> own((size_t)h.nv, h.comm.rank);
+    for (int k = 0; k < n_neighbors; ++k) for (int g = c.recv_ptr[k]; g < c.recv_ptr[k + 1]; ++g) own[g] = c.nbr[k];
+    h.vowner.alloc(h.nv, s); h.vowner.upload(own.data(), h.nv);
     PNP_CUDA(cudaStreamSynchronize(s));
     return FASP_SUCCESS;
   } catch (const Error& e) { fprintf(stderr, "### pnpb200 ERROR: %s\n", e.what()); return e.code; }

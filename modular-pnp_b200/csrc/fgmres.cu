@@ -63,15 +63,18 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
   }
   const double den = b_norm > 0.0 ? b_norm : r_norm;
   const double epsilon = cfg.tol * den;
+  h.stats.krylov_its = 0;
+  // a NaN / Inf rhs or Jacobian (diverged Newton iterate) must not read as "converged in 0 iterations":
+  // every comparison with NaN is false, so the finiteness test comes first
+  if (!std::isfinite(r_norm) || !std::isfinite(b_norm)) return ERROR_SOLVER_EXIT;
   if (!(r_norm > epsilon)) return 0;
-  if (!std::isfinite(r_norm)) return ERROR_SOLVER_EXIT;
 
   int iter = 0, Restart = restart_max;
   double cr = 1.0;
   bool converged = false;
   while (iter < MaxIt) {
     rs[0] = r_norm; r_norm_old = r_norm;
-    if (r_norm == 0.0) return iter;
+    if (r_norm == 0.0) { h.stats.krylov_its = iter; return iter; }
     if (cr > cr_max || iter == 0) Restart = restart_max;
     else if (cr < cr_min) { /* keep */ }
     else { if (Restart - dstep > restart_min) Restart -= dstep; else Restart = restart_max; }
@@ -105,7 +108,7 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
         hh[i][i - 1] = tnorm;
         if (tnorm != 0.0) vec_scale(1.0 / tnorm, Vi(i), m, s);
       }
-      if (!std::isfinite(tnorm)) return ERROR_SOLVER_EXIT;
+      if (!std::isfinite(tnorm)) { h.stats.krylov_its = iter; return ERROR_SOLVER_EXIT; }
       for (int j = 1; j < i; ++j) {
         const double t = hh[j - 1][i - 1];
         hh[j - 1][i - 1] = sn[j - 1] * hh[j][i - 1] + c[j - 1] * t;
@@ -137,7 +140,7 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
     bsrt_residual(A, b, x, Vi(0), s);
     r_norm = vec_norm2(h, Vi(0), m);
     if (est_conv && r_norm <= epsilon) { converged = true; break; }
-    if (!std::isfinite(r_norm)) return ERROR_SOLVER_EXIT;
+    if (!std::isfinite(r_norm)) { h.stats.krylov_its = iter; return ERROR_SOLVER_EXIT; }
     if (r_norm <= epsilon) { converged = true; break; }
     cr = r_norm / r_norm_old;
   }

@@ -105,6 +105,7 @@ struct Hierarchy {
   DevBuf<int> c_off3, c_cnt3;
   DevBuf<double> c_bpad, c_ball, c_bglob;
   bool symbolic_valid = false;
+  bool coarse_dense = true;     // coarsest level: explicit dense inverse (else Gauss-Seidel sweeps, amg.cu)
   // CUDA graph of the coarse part of a cycle (everything below level COARSE_GRAPH_LEVEL, amg.cu):
   // the K-cycle visits those levels several times per Krylov iteration with ~200 launches of
   // microsecond kernels each; captured once per hierarchy, replayed with one cudaGraphLaunch
@@ -163,6 +164,7 @@ struct Handle {
   DevBuf<double> uu_base;       // solution the last pnpb200_solve_update started from (damped Newton: trial = base + alpha du)
   bool have_update = false;
   DevBuf<unsigned char> bcflag; // 3*nv
+  DevBuf<int> vowner;           // multi-GPU: owner rank of every local vertex (set by pnpb200_set_partition)
   double q_eafe[3] = {0, 0, 0}; // valency function at dofs 0..2 (linear_pnp.cpp:220-224)
   bool have_coef = false;
   bool rhs_current = false;     // h.rhs holds the residual of the CURRENT solution (reused as the next step's rhs)

@@ -27,9 +27,23 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f64" and d["vs_baseline"] is None
     assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1e3) < 1e-6 * 1e3
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "Newton step" in cb["sample"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] == 1 and cb["value"] == d["value"] and "Newton step" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["n"] == 256 and "workload" in d["config"]
+    # the arm times what it labels: the config names the SAMPLE box it really ran, with the
+    # cycle it really ran (bsr.dat's V-cycle), nothing extrapolated; the bench size is only referenced
+    assert d["extrapolated"] is False and d["config"]["n"] == 6 and d["config"]["amg_cycle_type"] == "V"
+    assert d["config"]["dofs"] == 3 * 7 ** 3 and d["config"]["bench_workload_n"] == 256 and "6^3" in d["config"]["workload"]
+    assert abs(d["us_per_dof"] - 1e3 * d["ms_per_step"] / d["config"]["dofs"]) < 1e-9 * d["us_per_dof"]
+    assert len(d["seconds_per_step_each"]) == d["steps"] == 1
+
+
+def test_reference_arm_shrinks_the_sample_until_k_steps_fit_the_budget():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.cpu_sample_n_for(4, 300.0, 64) == 64        # default bench.py --impl reference
+    assert bench.cpu_sample_n_for(20, 300.0, 64) == 48       # the driver's --steps 20
+    assert bench.cpu_sample_n_for(20, 300.0, 32) == 32
+    assert bench.cpu_sample_n_for(1000, 300.0, 64) == 16
 
 
 def test_reference_arm_other_ranks_exit_silently():

@@ -199,3 +199,39 @@ def test_entropy_indicator_and_cell_marking(oracle, pkg, gpu_lib):
             m, cnt, used = g.mark_cells(1e-6, target)
             assert used == t_ref and np.array_equal(m, eta > t_ref) and cnt == int((eta > t_ref).sum())
         g.close()
+
+
+@pytest.mark.parametrize("use_eafe", [True, False])
+def test_zero_row_gets_unit_diagonal(oracle, pkg, gpu_lib, use_eafe):
+    """SURVEY a8, PDE::EigenMatrix_to_dCSRmat (src/pde.cpp:596-621): a scalar row whose stored values
+    are all zero gets diag = 1. Such rows appear when an ion's diffusivity vanishes around a vertex:
+    every entry of that ion's row carries a factor D (Galerkin: forms.ufl:30-33; EAFE: the edge
+    average of alpha, EAFE.h:4857-4867). Vertex i and all its neighbours get D_1 = 0 -> row (i, 1) is
+    all-zero before the fix and exactly e_i after it, on the device as in the oracle."""
+    P = oracle.Problem(8, 4, 4)
+    X = P.xyz.reshape(-1, 3)
+    i = int(np.argmin(np.abs(X).sum(axis=1)))                     # an interior vertex
+    nbrs = P.JA[P.IA[i]:P.IA[i + 1]]
+    assert len(nbrs) == 15
+    saved = P.diff.copy()
+    P.diff[3 * nbrs + 1] = 0.0
+    uu = perturbed_state(P, quantize=True)
+    try:
+        A_ref, b_ref = P.assemble(uu, use_eafe=use_eafe)
+        g = gpu_problem(pkg, P, uu)
+    finally:
+        P.diff[:] = saved
+    g.use_eafe(use_eafe)
+    g.assemble()
+    IA, JA, val = g.get_matrix()
+    V = val.reshape(-1, 3, 3); R = A_ref.reshape(-1, 3, 3)
+    sl = slice(IA[i], IA[i + 1])
+    row, row_ref = V[sl, 1, :], R[sl, 1, :]
+    d = int(np.nonzero(JA[sl] == i)[0][0])
+    expect = np.zeros_like(row); expect[d, 1] = 1.0
+    assert np.array_equal(row_ref, expect), "oracle: the zero row must come out as e_i"
+    assert np.array_equal(row, expect), "device: the zero row must come out as e_i"
+    # the other two rows of the vertex and all other rows are untouched by the fix
+    assert np.abs(V[sl, 0, :]).sum() > 0 and np.abs(V[sl, 2, :]).sum() > 0
+    assert row_scaled_error(IA, val, A_ref) <= 1e-12
+    g.close()

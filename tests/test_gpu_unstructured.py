@@ -111,3 +111,66 @@ def test_adaptive_loop_rebuilds_the_pattern(oracle, pkg, gpu_lib):
         cells = np.vstack([keep] + subs)
     assert sizes[0] < sizes[1] < sizes[2]
     assert starts[1] < 0.1 * starts[0]        # the interpolated solution is a warm start on the refined mesh
+
+
+def test_refine_exact_newton_history_matches_oracle(oracle, pkg, gpu_lib):
+    """BASELINE configs[2] (pnp_refine_exact): Newton on the ONCE-REFINED mesh, GPU vs oracle.
+    Level 0 = the benchmark's 20x4x4 box on 2 x 0.4 x 0.4 (benchmarks/pnp_refine_exact/domain.dat),
+    solved on the device; its entropy indicator marks the top 20 % of the cells; the marked cells
+    are refined (centroid split standing in for dolfin::adapt, which stays with the caller) and the
+    solution is interpolated (adapt(Function, mesh), main.cpp:267). From that SAME start both sides
+    run the Newton loop of main.cpp:476-514 (max 15, rel 1e-8, max-res 1e-10, bsr.dat): same Newton
+    count, every step's residual norms compared relatively."""
+    P0 = oracle.Problem(20, 4, 4)
+    it, amg = pkg.default_params()
+    G0 = GeneralProblem(oracle, P0.xyz, P0.cells)
+    g = _gpu(pkg, G0, G0.uu0)
+    l2_0, mx = g.residual()
+    n, rel = 0, 1.0
+    while n < 15 and rel > 1e-8 and mx > 1e-10:
+        st, l2, mx = g.newton_step(it, amg); rel = l2 / l2_0; n += 1
+        assert st > 0
+    sol = g.get_solution().reshape(-1, 3)
+    eta = g.entropy_indicator()
+    marked, cnt, _ = g.mark_cells(float(np.quantile(eta, 0.8)))
+    g.close()
+    X = P0.xyz.reshape(-1, 3); cells = P0.cells.reshape(-1, 4).astype(np.int64)
+    split, keep = cells[marked], cells[~marked]
+    new_ids = len(X) + np.arange(len(split))
+    X1 = np.vstack([X, X[split].mean(axis=1)])
+    uu1 = np.vstack([sol, sol[split].mean(axis=1)]).ravel()
+    subs = []
+    for drop in range(4):
+        t = split.copy(); t[:, drop] = new_ids; subs.append(t)
+    cells1 = np.sort(np.vstack([keep] + subs), axis=1).astype(np.int32)
+    G1 = GeneralProblem(oracle, X1.ravel(), cells1.ravel())
+    assert G1.nc > G0.nc and np.diff(G1.IA).max() > 15
+    # oracle: main.cpp:476-514 on the refined mesh
+    prm = oracle.default_param()
+    uu = uu1.copy()
+    _, r0, m0 = G1.residual(uu)
+    hist_ref, rel, mxr = [], 1.0, m0
+    while len(hist_ref) < 15 and rel > 1e-8 and mxr > 1e-10:
+        A, b = G1.assemble(uu, True)
+        dx, its = oracle.solver_dbsr_krylov_amg(G1.IA, G1.JA, A, b, prm)
+        assert its > 0
+        uu = uu + dx
+        _, l2r, mxr = G1.residual(uu)
+        rel = l2r / r0
+        hist_ref.append((its, rel, mxr))
+    # device
+    g = _gpu(pkg, G1, uu1)
+    a0, am0 = g.residual()
+    assert abs(a0 - r0) <= 1e-12 * r0 and abs(am0 - m0) <= 1e-12 * m0
+    hist, rel, mx = [], 1.0, am0
+    while len(hist) < 15 and rel > 1e-8 and mx > 1e-10:
+        st, l2, mx = g.newton_step(it, amg); rel = l2 / a0
+        assert st > 0
+        hist.append((st, rel, mx))
+    uu_gpu = g.get_solution()
+    g.close()
+    assert len(hist) == len(hist_ref), (hist, hist_ref)
+    for k in range(len(hist)):
+        tol = 1e-3 if hist_ref[k][1] > 1e-6 else 5e-2       # same bar as test_newton_exact_solution_config
+        assert abs(hist[k][1] - hist_ref[k][1]) <= tol * hist_ref[k][1], (k, hist[k], hist_ref[k])
+    assert np.abs(uu_gpu - uu).max() <= 1e-5
