@@ -204,6 +204,38 @@ int  pnpb200_comm_init(pnpb200_handle* h, const unsigned char id[128], int rank,
  * pnpb200_set_dirichlet / after create. */
 int  pnpb200_set_partition(pnpb200_handle* h, int n_owned, int n_neighbors, const int* neighbor_ranks,
                            const int* send_ptr, const int* send_idx, const int* recv_ptr);
+/* A proper colouring of the local fine-level graph known to the caller (colour[v] in [0, n_colors),
+ * no two vertices of a cell share a colour), e.g. (i + j + k) mod 4 of the GLOBAL lattice position
+ * of a BoxMesh brick (pnpb200_partition_box): the multicolour Gauss-Seidel sweeps of the fine level
+ * then take n_colors launches instead of the ~10 of the graph colouring. Checked against the
+ * pattern on the device; ERROR_INPUT_PAR if it is not proper. Call after pnpb200_set_partition
+ * (or right after create on one GPU). */
+int  pnpb200_set_coloring(pnpb200_handle* h, int n_colors, const int* color);
+
+/* ---- mesh partitioner (host, csrc/partition.cpp): the vertex partition + halo lists that
+ * pnpb200_create / pnpb200_set_partition consume, for rank `rank`.
+ *   pnpb200_partition_box : dolfin::BoxMesh (src/domain.cpp:306-308) cut into px x py x pz bricks of
+ *     vertex planes (rank = rx + px * (ry + py * rz)), generated in closed form — only the rank's own
+ *     brick and its ghost layer are ever built. (1, 1, N) gives z-slabs.
+ *   pnpb200_partition_mesh: recursive coordinate bisection of ANY conforming tetrahedral mesh given by
+ *     its global arrays (the refined meshes of src/mesh_refiner.cpp:73-153); deterministic, so every
+ *     rank computes the same owner map.
+ * Local vertices: owned (ascending global id), then ghosts grouped by owner rank (ascending rank,
+ * ascending global id); local cells: every cell touching an owned vertex, vertices ascending in
+ * GLOBAL id (UFC order). The arrays stay owned by the partition object (pnpb200_partition_free). */
+typedef struct pnpb200_partition pnpb200_partition;
+int  pnpb200_partition_box(int nx, int ny, int nz, double lx, double ly, double lz, int px, int py, int pz, int rank,
+                           pnpb200_partition** out);
+int  pnpb200_partition_mesh(int n_vertices, const double* xyz, int n_cells, const int* cells, int n_ranks, int rank,
+                            pnpb200_partition** out);
+int  pnpb200_partition_sizes(const pnpb200_partition* p, int* n_owned, int* n_local, int* n_cells, int* n_neighbors,
+                             int* n_send, int* n_bc);
+/* gids: global vertex id of every local vertex; color: (i + j + k) mod 4 for box partitions, NULL otherwise;
+ * bc_vertices: local ids of the vertices on the two x-faces (box partitions; the benchmarks' Dirichlet set) */
+int  pnpb200_partition_arrays(const pnpb200_partition* p, const double** xyz, const int** cells, const long long** gids,
+                              const int** neighbor_ranks, const int** send_ptr, const int** send_idx, const int** recv_ptr,
+                              const int** color, const int** bc_vertices);
+void pnpb200_partition_free(pnpb200_partition* p);
 
 #ifdef __cplusplus
 }

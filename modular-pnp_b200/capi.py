@@ -170,6 +170,14 @@ def lib():
     L.pnpb200_comm_unique_id.argtypes = [C.c_char_p]
     L.pnpb200_comm_init.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
     L.pnpb200_set_partition.argtypes = [H, C.c_int, C.c_int, _i4, _i4, _i4, _i4]
+    L.pnpb200_set_coloring.argtypes = [H, C.c_int, _i4]
+    PP = C.POINTER(C.c_void_p)
+    L.pnpb200_partition_box.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 4 + [PP]
+    L.pnpb200_partition_mesh.argtypes = [C.c_int, _f8, C.c_int, _i4, C.c_int, C.c_int, PP]
+    L.pnpb200_partition_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 6
+    L.pnpb200_partition_arrays.argtypes = [C.c_void_p] + [PP] * 9
+    L.pnpb200_partition_free.argtypes = [C.c_void_p]
+    L.pnpb200_partition_free.restype = None
     # FASP-compatible surface
     L.fasp_param_input.argtypes = [C.c_char_p, C.POINTER(input_param)]
     L.fasp_param_input.restype = None
@@ -355,6 +363,10 @@ class PNP:
         _check(self.L.pnpb200_set_partition(self.h, int(part["n_own"]), nb, pad(part["nbr"]), pad(part["send_ptr"]),
                                             pad(part["send_idx"]), pad(part["recv_ptr"])), "set_partition")
 
+    def set_coloring(self, color, n_colors=None):
+        color = np.ascontiguousarray(color, dtype=np.int32)
+        _check(self.L.pnpb200_set_coloring(self.h, int(color.max()) + 1 if n_colors is None else int(n_colors), color), "set_coloring")
+
     def comm_init(self, unique_id, rank, nranks):
         _check(self.L.pnpb200_comm_init(self.h, bytes(unique_id), rank, nranks), "comm_init")
 
@@ -517,6 +529,49 @@ class PNP:
         y = np.zeros(self.N)
         _check(self.L.pnpb200_apply_matrix(self.h, np.ascontiguousarray(x, dtype=np.float64), y), "apply_matrix")
         return y
+
+
+def _partition_to_dict(L, p):
+    """copy the arrays of a pnpb200_partition object into the dict layout of partition.py, then free it"""
+    try:
+        sz = [C.c_int() for _ in range(6)]
+        _check(L.pnpb200_partition_sizes(p, *[C.byref(v) for v in sz]), "partition_sizes")
+        n_own, n_loc, n_cells, n_nbr, n_send, n_bc = [v.value for v in sz]
+        ptr = [C.c_void_p() for _ in range(9)]
+        _check(L.pnpb200_partition_arrays(p, *[C.byref(v) for v in ptr]), "partition_arrays")
+
+        def arr(v, ctype, dtype, count):
+            if count == 0 or not v.value:
+                return np.zeros(0, dtype=dtype)
+            return np.ctypeslib.as_array(C.cast(v, C.POINTER(ctype)), shape=(count,)).astype(dtype, copy=True)
+        d = dict(n_own=n_own, n_loc=n_loc,
+                 xyz=arr(ptr[0], C.c_double, np.float64, 3 * n_loc), cells=arr(ptr[1], C.c_int, np.int32, 4 * n_cells),
+                 gids=arr(ptr[2], C.c_longlong, np.int64, n_loc), nbr=arr(ptr[3], C.c_int, np.int32, n_nbr),
+                 send_ptr=arr(ptr[4], C.c_int, np.int32, n_nbr + 1), send_idx=arr(ptr[5], C.c_int, np.int32, n_send),
+                 recv_ptr=arr(ptr[6], C.c_int, np.int32, n_nbr + 1), bc_vertices=arr(ptr[8], C.c_int, np.int32, n_bc))
+        col = arr(ptr[7], C.c_int, np.int32, n_loc)
+        if len(col):
+            d["color"] = col
+        return d
+    finally:
+        L.pnpb200_partition_free(p)
+
+
+def partition_box(nx, ny, nz, lx, ly, lz, px, py, pz, rank):
+    """pnpb200_partition_box (csrc/partition.cpp): bricks of dolfin::BoxMesh, closed form, host only"""
+    L = lib()
+    p = C.c_void_p()
+    _check(L.pnpb200_partition_box(nx, ny, nz, lx, ly, lz, px, py, pz, rank, C.byref(p)), "partition_box")
+    return _partition_to_dict(L, p)
+
+
+def partition_mesh(xyz, cells, nranks, rank):
+    """pnpb200_partition_mesh: recursive coordinate bisection of any conforming tetrahedral mesh, host only"""
+    L = lib()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64).ravel(); cells = np.ascontiguousarray(cells, dtype=np.int32).ravel()
+    p = C.c_void_p()
+    _check(L.pnpb200_partition_mesh(len(xyz) // 3, xyz, len(cells) // 4, cells, nranks, rank, C.byref(p)), "partition_mesh")
+    return _partition_to_dict(L, p)
 
 
 def comm_unique_id():

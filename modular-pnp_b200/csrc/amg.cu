@@ -294,26 +294,33 @@ __global__ void rap_numeric_kernel(int cnnzb, const int4* __restrict__ crd, cons
 }
 
 // ---- grid transfer (sweep space, internal.hpp) --------------------------------------------------
-// coarse position P <- sum of the fine positions of aggregate c_rowid[P] (coarsest level: P itself)
+// coarse position P <- sum of the fine positions of aggregate c_rowid[P] (coarsest level: P itself).
+// Fine vectors hold VS doubles per row (sweep space); the coarse vector holds CS: VS, or 3 when the
+// next level is the coarsest with the dense solve (row-id order, packed).
+template <int CS>
 __global__ void restrict_kernel(int nagg, const int* __restrict__ c_rowid, const int* __restrict__ agg_ptr,
                                 const int* __restrict__ agg_rows_pos, const double* __restrict__ r, double* __restrict__ bc)
 {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 3 * nagg) return;
-  const int P = e / 3, k = e % 3;
+  if (e >= CS * nagg) return;
+  const int P = e / CS, k = e % CS;
+  if (k == 3) { bc[e] = 0.0; return; }
   const int I = c_rowid ? c_rowid[P] : P;
   double a = 0.0;
-  for (int p = agg_ptr[I]; p < agg_ptr[I + 1]; ++p) a += r[3 * (size_t)agg_rows_pos[p] + k];
+  for (int p = agg_ptr[I]; p < agg_ptr[I + 1]; ++p) a += r[(size_t)VS * (size_t)agg_rows_pos[p] + k];
   bc[e] = a;
 }
 
+template <int CS>
 __global__ void prolong_kernel(int n, const int* __restrict__ agg_pos, const double* __restrict__ ec,
                                double* __restrict__ x)
 {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 3 * n) return;
-  const int a = agg_pos[e / 3];
-  if (a >= 0) x[e] += ec[3 * (size_t)a + e % 3];
+  if (e >= VS * n) return;
+  const int k = e % VS;
+  if (k == 3) return;
+  const int a = agg_pos[e / VS];
+  if (a >= 0) x[e] += ec[(size_t)CS * (size_t)a + k];
 }
 
 // agg_pos[p] = coarse position of the aggregate of row rowid[p]; agg_rows_pos[q] = position of member agg_rows[q]
@@ -592,7 +599,7 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
     if (nghost > 0) PNP_CUDA(cudaMemcpyAsync(L.agg.p + n_own, gval.data(), (size_t)nghost * sizeof(int), cudaMemcpyHostToDevice, s));
     hc.send_idx.alloc(csend.empty() ? 1 : csend.size(), s);
     if (!csend.empty()) hc.send_idx.upload(csend.data(), csend.size());
-    hc.sendbuf.alloc(3 * (csend.empty() ? 1 : csend.size()), s);
+    hc.sendbuf.alloc(4 * (csend.empty() ? 1 : csend.size()), s);
     PNP_CUDA(cudaStreamSynchronize(s));     // gval / csend are host temporaries
     C.n_own = nagg;
   }
@@ -659,8 +666,9 @@ void rap_numeric(Handle& h, Level& L, Level& C)
 
 void alloc_level_vectors(Level& L, cudaStream_t s)
 {
-  const size_t m = 3 * (size_t)L.A.n;
-  L.x.alloc(m, s); L.b.alloc(m, s); L.w.alloc(m, s);
+  const size_t m = VS * (size_t)L.A.n;
+  auto fresh = [&](DevBuf<double>& v) { const double* old = v.p; v.alloc(m, s); if (v.p != old) v.zero(); };   // pad entries start at zero
+  fresh(L.x); fresh(L.b); fresh(L.w);
   L.dinv.alloc(9 * (size_t)L.A.n, s);
 }
 
@@ -814,19 +822,19 @@ bool setup_coarsest(Handle& h)
 // multicolour Gauss-Seidel sweeps from a zero initial guess, in sweep space like every other level
 // (multi-GPU: hybrid GS with a halo exchange before every sweep).
 constexpr int COARSEST_SWEEPS = 8;
-void solve_coarsest_sweeps(Handle& h, Level& Z, const double* b, double* x)
+void solve_coarsest_sweeps(Handle& h, Level& Z, const double* b, double* x, int bs = VS)
 {
   cudaStream_t s = h.stream;
   const bool dist = h.comm.active();
-  const size_t m = 3 * (size_t)Z.A.n, mo = 3 * (size_t)owned_rows(Z);
+  const size_t m = VS * (size_t)Z.A.n, mo = VS * (size_t)owned_rows(Z);
   if (m > mo) PNP_CUDA(cudaMemsetAsync(x + mo, 0, (m - mo) * sizeof(double), s));
-  mcgs_sweep_from_zero(Z, b, x, s);
+  mcgs_sweep_from_zero(Z, b, x, s, bs);
   for (int k = 0; k < COARSEST_SWEEPS; ++k) {
     if (dist) halo_exchange(h, Z.halo, x, true);
-    mcgs_sweep(Z, b, x, true, s);
+    mcgs_sweep(Z, b, x, true, s, bs);
     if (k + 1 == COARSEST_SWEEPS) break;
     if (dist) halo_exchange(h, Z.halo, x, true);
-    mcgs_sweep(Z, b, x, false, s);
+    mcgs_sweep(Z, b, x, false, s, bs);
   }
 }
 
@@ -988,44 +996,48 @@ void coarse_solve_graphed(Handle& h, const SolverConfig& cfg, int l)
 // If Ax != nullptr (>= 1 post-smoothing sweep) the last backward sweep also records
 // delta = x_new - x_old in L.w, and Ax = A x = b + L delta costs half a matrix pass; returns
 // whether Ax was produced.
-bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x, double* Ax)
+bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x, double* Ax, int bs = VS, int axs = VS)
 {
   cudaStream_t s = h.stream;
   Level& L = *h.hier.lv[l];
   Level& C = *h.hier.lv[l + 1];
-  const size_t m = 3 * (size_t)L.A.n;
+  const size_t m = VS * (size_t)L.A.n;
   const int own = owned_rows(L);
   const bool dist = h.comm.active();
   if (cfg.presmooth == 1 && h.sweep_shortcuts) {
-    if (m > 3 * (size_t)own) PNP_CUDA(cudaMemsetAsync(x + 3 * (size_t)own, 0, (m - 3 * (size_t)own) * sizeof(double), s));
-    mcgs_sweep_from_zero(L, b, x, s);
+    if (m > VS * (size_t)own) PNP_CUDA(cudaMemsetAsync(x + VS * (size_t)own, 0, (m - VS * (size_t)own) * sizeof(double), s));
+    mcgs_sweep_from_zero(L, b, x, s, bs);
     if (dist) halo_exchange(h, L.halo, x, true);
-    bsrt_residual_after_sweep(L, b, x, L.w.p, s);
+    bsrt_residual_after_sweep(L, b, x, L.w.p, s, bs);
   } else {
     vec_set(x, 0.0, m, s);
-    for (int k = 0; k < cfg.presmooth; ++k) { if (dist && k > 0) halo_exchange(h, L.halo, x, true); mcgs_sweep(L, b, x, false, s); }
+    for (int k = 0; k < cfg.presmooth; ++k) { if (dist && k > 0) halo_exchange(h, L.halo, x, true); mcgs_sweep(L, b, x, false, s, bs); }
     if (dist) halo_exchange(h, L.halo, x, true);
-    bsrt_residual(L.A, b, x, L.w.p, s);
+    bsrt_residual(L.A, b, x, L.w.p, s, bs, VS);
   }
   if (L.nagg > 0) {
-    restrict_kernel<<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, L.coarse_identity ? nullptr : C.A.vrowid.p, L.agg_ptr.p,
-                                                                 L.agg_rows_pos.p, L.w.p, C.b.p);
+    if (L.coarse_identity) restrict_kernel<3><<<cdiv(3 * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, nullptr, L.agg_ptr.p, L.agg_rows_pos.p, L.w.p, C.b.p);
+    else restrict_kernel<VS><<<cdiv(VS * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, C.A.vrowid.p, L.agg_ptr.p, L.agg_rows_pos.p, L.w.p, C.b.p);
     PNP_COUNT_LAUNCH();
   }
   if (l + 1 == coarse_graph_level() && l + 1 >= 1 && l + 2 < (int)h.hier.lv.size() && (!dist || coarse_graph_dist()) && !g_debug_sync) coarse_solve_graphed(h, cfg, l + 1);
   else solve_level(h, cfg, l + 1, C.b.p, C.x.p);
-  if (own > 0) { prolong_kernel<<<cdiv(3 * (size_t)own, 256), 256, 0, s>>>(own, L.agg_pos.p, C.x.p, x); PNP_COUNT_LAUNCH(); }
+  if (own > 0) {
+    if (L.coarse_identity) prolong_kernel<3><<<cdiv(VS * (size_t)own, 256), 256, 0, s>>>(own, L.agg_pos.p, C.x.p, x);
+    else prolong_kernel<VS><<<cdiv(VS * (size_t)own, 256), 256, 0, s>>>(own, L.agg_pos.p, C.x.p, x);
+    PNP_COUNT_LAUNCH();
+  }
   const bool want_ax = Ax != nullptr && cfg.postsmooth >= 1 && h.sweep_shortcuts;
   for (int k = 0; k < cfg.postsmooth; ++k) {
     if (dist) halo_exchange(h, L.halo, x, true);
-    if (want_ax && k == cfg.postsmooth - 1) mcgs_sweep_back_delta(L, b, x, L.w.p, s);
-    else mcgs_sweep(L, b, x, true, s);
+    if (want_ax && k == cfg.postsmooth - 1) mcgs_sweep_back_delta(L, b, x, L.w.p, s, bs);
+    else mcgs_sweep(L, b, x, true, s, bs);
   }
   if (want_ax) {
     // multi-GPU (hybrid GS): the ghost columns kept their pre-sweep value, so their delta — the
     // owners' delta, one halo exchange — enters the product as well
     if (dist) halo_exchange(h, L.halo, L.w.p, true);
-    bsrt_apply_after_sweep(L, b, L.w.p, Ax, s);
+    bsrt_apply_after_sweep(L, b, L.w.p, Ax, s, bs, axs);
   }
   return want_ax;
 }
@@ -1041,9 +1053,9 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
   if (!kcyc) { mg_cycle(h, cfg, l, b, x, nullptr); return; }
   // K-cycle: two GCR steps preconditioned by the cycle of this level (device scalars only;
   // multi-GPU: the dot products run over the owned rows and are summed with ncclAllReduce)
-  const size_t m = 3 * (size_t)L.A.n, mo = 3 * (size_t)owned_rows(L);
+  const size_t m = VS * (size_t)L.A.n, mo = VS * (size_t)owned_rows(L);
   const bool dist = h.comm.active();
-  L.kc.alloc(5 * m + 8, s);
+  { const double* old = L.kc.p; L.kc.alloc(5 * m + 8, s); if (L.kc.p != old) L.kc.zero(); }
   L.ksc.alloc(8 + 3 * 592, s);
   if (!L.kcnt.p) { L.kcnt.alloc(1, s); L.kcnt.zero(); }
   double* c = L.kc.p; double* v = c + m; double* rt = v + m; double* d = rt + m; double* w = d + m;
@@ -1069,7 +1081,7 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
 
 // z = M^{-1} r : one multigrid cycle from a zero initial guess (fasp_precond_dbsr_amg [EXT]):
 // V(nu1,nu2), or with AMG_cycle_type != V the K-cycle on the first cfg.kcycle_levels coarse levels
-bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az)
+bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az, int rs, int azs)
 {
   cudaStream_t s = h.stream;
   auto& lv = h.hier.lv;
@@ -1078,14 +1090,14 @@ bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, 
     Level& Z = *lv[0];
     if (h.hier.coarse_dense) {      // the dense solve works in row-id order
       double* t0 = Z.b.p; double* t1 = Z.x.p;     // level work vectors: unused without a cycle
-      vec_from_sweep(Z.A, r, t0, s);
+      vec_from_sweep(Z.A, r, t0, s, rs);
       solve_coarsest(h, t0, t1);
       vec_to_sweep(Z.A, t1, z, s);
-    } else solve_coarsest_sweeps(h, Z, r, z);
+    } else solve_coarsest_sweeps(h, Z, r, z, rs);
     (void)cfg; (void)s;
     return false;
   }
-  return mg_cycle(h, cfg, 0, r, z, Az);
+  return mg_cycle(h, cfg, 0, r, z, Az, rs, azs);
 }
 
 } // namespace pnpb200

@@ -250,7 +250,8 @@ int block_pnp_stokes_solve(BlockSystem& S, const double* b, double* x, BlockStat
   const BsrT& Av = hv.hier.lv[0]->A;
   const size_t nvp = 3 * (size_t)Av.n;          // padded velocity length
   DevBuf<double> vr, vz, vrs, vzs, tq, tp, zp;
-  vr.alloc(nvp, sv); vz.alloc(nvp, sv); vrs.alloc(nvp, sv); vzs.alloc(nvp, sv);
+  vr.alloc(nvp, sv); vz.alloc(nvp, sv); vrs.alloc(VS * (size_t)Av.n, sv); vzs.alloc(VS * (size_t)Av.n, sv);   // vrs, vzs: sweep space
+  vzs.zero();
   vr.zero();                                     // the padding stays zero
   tq.alloc(nq ? nq : 1, so); tp.alloc(np, so); zp.alloc(np, sp);
   link.pass(sv, so);

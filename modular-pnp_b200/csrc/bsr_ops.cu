@@ -49,11 +49,11 @@ namespace {
 #endif
 enum { M_SPMV = 0, M_RES = 1, M_GS = 2, M_GS0 = 3, M_RESU = 4, M_GSD = 5, M_LDELTA = 6, M_LDELTAG = 7 };
 
-template <int MODE, int MINB>
+template <int MODE, int MINB, int XS>
 __global__ void __launch_bounds__(256, MINB)
 bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* __restrict__ ja,
                 const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
-                const double* x, double* y, double* dl)
+                const double* x, double* y, double* dl, int bs, int ys)
 {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int lane = threadIdx.x & 15;
@@ -77,8 +77,8 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
 #endif
     const int jcol = ja[s + k];
     if (MODE == M_LDELTAG && k >= nl && (k == nl || jcol < n_swept)) return;
-    const size_t j = 3 * (size_t)jcol;
-    const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
+    double x0, x1, x2;
+    load_row3<XS>(x, jcol, x0, x1, x2);
     a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
     a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
     a2 += v[6 * st] * x0 + v[7 * st] * x1 + v[8 * st] * x2;
@@ -95,26 +95,28 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
   const double a = half_sum3(a0, a1, a2, lane);
   const int c = lane >> 2, i = lane & 3;
   if (MODE == M_SPMV || MODE == M_RES || MODE == M_RESU || MODE == M_LDELTA || MODE == M_LDELTAG) {
-    if (row >= 0 && i == 0 && c < 3) {
-      const size_t o = 3 * (size_t)row + c;
-      if (MODE == M_SPMV) y[o] = a;
-      else if (MODE == M_RES) y[o] = b[o] - a;
-      else if (MODE == M_RESU) y[o] = row < n_swept ? -a : b[o] - a;
-      else y[o] = b[o] + a;
+    // b and y carry bs / ys doubles per row (3 = packed: the Krylov basis, 4 = padded: pad entry kept at zero)
+    if (row >= 0 && i == 0 && c < ys) {        // c == 3: a == 0
+      const size_t o = (size_t)ys * (size_t)row + c, ob = (size_t)bs * (size_t)row + c;
+      if (MODE == M_SPMV || c == 3) y[o] = a;
+      else if (MODE == M_RES) y[o] = b[ob] - a;
+      else if (MODE == M_RESU) y[o] = row < n_swept ? -a : b[ob] - a;
+      else y[o] = b[ob] + a;
     }
   } else {
     // x_new[i] = sum_c Dinv[i][c] (b_c - a_c): lane (c, i) forms one product, two shuffles add the three c
     double part = 0.0;
-    if (row >= 0 && c < 3 && i < 3) part = dinv[9 * (size_t)t + 3 * i + c] * (b[3 * (size_t)row + c] - a);   // dinv: sweep order
+    if (row >= 0 && c < 3 && i < 3) part = dinv[9 * (size_t)t + 3 * i + c] * (b[(size_t)bs * (size_t)row + c] - a);   // dinv: sweep order
     part += __shfl_xor_sync(0xffffffffu, part, 4);
     part += __shfl_xor_sync(0xffffffffu, part, 8);
-    if (row >= 0 && lane < 3) {
-      const size_t o = 3 * (size_t)row + lane;
-      if (MODE == M_GSD) dl[o] = part - x[o];
+    if (row >= 0 && lane < XS) {               // lane 3 (padded vectors): part == 0
+      const size_t o = (size_t)XS * (size_t)row + lane;
+      if (MODE == M_GSD) dl[o] = lane < 3 ? part - x[o] : 0.0;
       y[o] = part;
     }
   }
 #else
+  static_assert(XS == 3, "the PNPB200_SUM3=0 epilogue only knows packed vectors");
   a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
   if (row >= 0 && lane < 3) {
     const size_t o = 3 * (size_t)row;
@@ -141,11 +143,11 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
 // t+2H, ... (H = half-warps in the grid) and carries the descriptor of the next two rows and the
 // column indices of the next row in registers, so that the matrix values AND the x gather of a row
 // are requested in the same instant and a row costs ONE exposed round trip.
-template <int MODE, int MINB>
+template <int MODE, int MINB, int XS>
 __global__ void __launch_bounds__(256, MINB)
 bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* __restrict__ ja,
                      const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
-                     const double* x, double* y, double* dl)
+                     const double* x, double* y, double* dl, int bs, int ys)
 {
   const int lane = threadIdx.x & 15;
   const int H = (gridDim.x * blockDim.x) >> 4;
@@ -177,8 +179,8 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
     const int c = lane >> 2, i = lane & 3;
     double bq = 0.0, dq = 0.0;          // epilogue operands, requested up front as well
     if (row >= 0 && c < 3) {
-      if (MODE == M_RES || MODE == M_LDELTA || MODE == M_LDELTAG || (MODE == M_RESU && row >= n_swept)) { if (i == 0) bq = b[3 * (size_t)row + c]; }
-      if (MODE == M_GS || MODE == M_GS0 || MODE == M_GSD) { if (i < 3) { bq = b[3 * (size_t)row + c]; dq = dinv[9 * (size_t)t + 3 * i + c]; } }
+      if (MODE == M_RES || MODE == M_LDELTA || MODE == M_LDELTAG || (MODE == M_RESU && row >= n_swept)) { if (i == 0) bq = b[(size_t)bs * (size_t)row + c]; }
+      if (MODE == M_GS || MODE == M_GS0 || MODE == M_GSD) { if (i < 3) { bq = b[(size_t)bs * (size_t)row + c]; dq = dinv[9 * (size_t)t + 3 * i + c]; } }
     }
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     auto block = [&](int k, int jc) {
@@ -192,8 +194,8 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
       const double* v = val + (9 * (size_t)s + (size_t)k);
       const int st = len;
 #endif
-      const size_t j = 3 * (size_t)jc;
-      const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
+      double x0, x1, x2;
+      load_row3<XS>(x, jc, x0, x1, x2);
       a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
       a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
       a2 += v[6 * st] * x0 + v[7 * st] * x1 + v[8 * st] * x2;
@@ -204,8 +206,8 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
     for (k += 16; k < k1; k += 16) block(k, ja[s + k]);      // rows with more than 16 blocks in range (rare)
     const double a = half_sum3(a0, a1, a2, lane);
     if (MODE == M_SPMV || MODE == M_RES || MODE == M_RESU || MODE == M_LDELTA || MODE == M_LDELTAG) {
-      if (row >= 0 && i == 0 && c < 3) {
-        const size_t o = 3 * (size_t)row + c;
+      if (row >= 0 && i == 0 && c < ys) {      // c == 3 (padded y): a == 0 and bq == 0, the pad entry stays zero
+        const size_t o = (size_t)ys * (size_t)row + c;
         if (MODE == M_SPMV) y[o] = a;
         else if (MODE == M_RES) y[o] = bq - a;
         else if (MODE == M_RESU) y[o] = row < n_swept ? -a : bq - a;
@@ -215,9 +217,9 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
       double part = dq * (bq - a);        // lanes outside (c < 3, i < 3): dq = 0
       part += __shfl_xor_sync(0xffffffffu, part, 4);
       part += __shfl_xor_sync(0xffffffffu, part, 8);
-      if (row >= 0 && lane < 3) {
-        const size_t o = 3 * (size_t)row + lane;
-        if (MODE == M_GSD) dl[o] = part - x[o];
+      if (row >= 0 && lane < XS) {             // lane 3 (padded vectors): part == 0
+        const size_t o = (size_t)XS * (size_t)row + lane;
+        if (MODE == M_GSD) dl[o] = lane < 3 ? part - x[o] : 0.0;
         y[o] = part;
       }
     }
@@ -245,9 +247,9 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
 #define PNPB200_GS_CTAS 8         // ... and the colour sweeps
 #endif
 int g_sm_count = 0;
-template <int MODE, int MINB, bool PIPE>
+template <int MODE, int MINB, bool PIPE, int XS = VS>
 void launch_rows(int nrows, int n_swept, const int4* rd, const int* ja, const BsrT& A, const double* dinv, const double* b,
-                 const double* x, double* y, double* dl, cudaStream_t s)
+                 const double* x, double* y, double* dl, cudaStream_t s, int bs = XS, int ys = XS)
 {
   if (nrows <= 0) return;
   const int full = cdiv((size_t)nrows * 16, 256);
@@ -255,14 +257,14 @@ void launch_rows(int nrows, int n_swept, const int4* rd, const int* ja, const Bs
   // persistent grid = exactly the CTAs that are resident at once (a second wave would walk the
   // gathered x window a second time: measured 6.5 vs 4.5 ms per Gauss-Seidel sweep)
   if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
-  static int per_sm = 0;             // one static per (MODE, MINB) instantiation
+  static int per_sm = 0;             // one static per (MODE, MINB, XS) instantiation
   if (per_sm == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bsrt_row_pipe_kernel<MODE, MINB>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = MINB;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bsrt_row_pipe_kernel<MODE, MINB, XS>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = MINB;
   }
   const int cap = g_sm_count * per_sm;
-  bsrt_row_pipe_kernel<MODE, MINB><<<full < cap ? full : cap, 256, 0, s>>>(nrows, n_swept, rd, ja, A.val.p, dinv, b, x, y, dl);
+  bsrt_row_pipe_kernel<MODE, MINB, XS><<<full < cap ? full : cap, 256, 0, s>>>(nrows, n_swept, rd, ja, A.val.p, dinv, b, x, y, dl, bs, ys);
   } else
-  bsrt_row_kernel<MODE, MINB><<<full, 256, 0, s>>>(nrows, n_swept, rd, ja, A.val.p, dinv, b, x, y, dl);
+  bsrt_row_kernel<MODE, MINB, XS><<<full, 256, 0, s>>>(nrows, n_swept, rd, ja, A.val.p, dinv, b, x, y, dl, bs, ys);
   PNP_COUNT_LAUNCH();
 }
 
@@ -277,7 +279,7 @@ constexpr int SMALL_LEVEL_ROWS = 512;
 __global__ void __launch_bounds__(1024, 1)
 mcgs_small_kernel(int ngroups, int reverse, int mode, const int* __restrict__ gptr, const int4* __restrict__ prd,
                   const int* __restrict__ ja, const double* __restrict__ val,
-                  const double* __restrict__ dinv, const double* __restrict__ b, double* x, double* dl)
+                  const double* __restrict__ dinv, const double* __restrict__ b, double* x, double* dl, int bs)
 {
   const int hw = threadIdx.x >> 4, nhw = blockDim.x >> 4, lane = threadIdx.x & 15;
   for (int gg = 0; gg < ngroups; ++gg) {
@@ -293,21 +295,22 @@ mcgs_small_kernel(int ngroups, int reverse, int mode, const int* __restrict__ gp
         if (k == nl) continue;
         int st;
         const double* v = val + bsrt_off(s, len, nl, k, st);
-        const size_t j = 3 * (size_t)ja[s + k];
-        const double x0 = x[j], x1 = x[j + 1], x2 = x[j + 2];
+        double x0, x1, x2;
+        load_row3<VS>(x, ja[s + k], x0, x1, x2);
         a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
         a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
         a2 += v[6 * st] * x0 + v[7 * st] * x1 + v[8 * st] * x2;
       }
       a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
       if (row >= 0 && lane < 3) {
-        const size_t o = 3 * (size_t)row;
-        const double r0 = b[o] - a0, r1 = b[o + 1] - a1, r2 = b[o + 2] - a2;
+        const size_t o = (size_t)VS * (size_t)row, ob = (size_t)bs * (size_t)row;
+        const double r0 = b[ob] - a0, r1 = b[ob + 1] - a1, r2 = b[ob + 2] - a2;
         const double* d = dinv + 9 * (size_t)p + 3 * lane;
         const double xn = d[0] * r0 + d[1] * r1 + d[2] * r2;
         if (mode == 2) dl[o + lane] = xn - x[o + lane];
         x[o + lane] = xn;
       }
+      if (VS == 4 && row >= 0 && lane == 3) { x[4 * (size_t)row + 3] = 0.0; if (mode == 2) dl[4 * (size_t)row + 3] = 0.0; }
     }
     __syncthreads();
   }
@@ -323,23 +326,23 @@ mcgs_small_kernel(int ngroups, int reverse, int mode, const int* __restrict__ gp
 // operands requested ahead of the barrier: 43 instead of 62 us per sweep of the 3.5 k-row level,
 // slower on the 80 k-row level, 0.5 % of the Krylov time in total — not kept.
 constexpr size_t SMALL_SMEM_BYTES = 200 * 1024;
-inline size_t small_level_smem(int n, int nnzb) { return (size_t)nnzb * 76 + (size_t)n * (72 + 24 + 24 + 16) + 64; }
+inline size_t small_level_smem(int n, int nnzb) { return (size_t)nnzb * 76 + (size_t)n * (72 + 16 * VS + 16) + 64; }
 __global__ void __launch_bounds__(1024, 1)
 mcgs_smem_kernel(int n, int nnzb, int ngroups, int reverse, int mode, const int* __restrict__ gptr,
                  const int4* __restrict__ prd, const int* __restrict__ ja, const double* __restrict__ val,
-                 const double* __restrict__ dinv, const double* __restrict__ b, double* x, double* dl)
+                 const double* __restrict__ dinv, const double* __restrict__ b, double* x, double* dl, int bs)
 {
   extern __shared__ double sm_d[];
   double* s_val = sm_d;                         // 9*nnzb
   double* s_dinv = s_val + 9 * (size_t)nnzb;    // 9*n   (sweep order)
-  double* s_b = s_dinv + 9 * (size_t)n;         // 3*n
-  double* s_x = s_b + 3 * (size_t)n;            // 3*n
-  int4* s_prd = reinterpret_cast<int4*>(s_x + 3 * (size_t)n + ((9 * nnzb + 15 * n) & 1));     // 16-byte aligned: n entries
+  double* s_b = s_dinv + 9 * (size_t)n;         // VS*n
+  double* s_x = s_b + VS * (size_t)n;           // VS*n
+  int4* s_prd = reinterpret_cast<int4*>(s_x + VS * (size_t)n + ((9 * nnzb + (9 + 2 * VS) * n) & 1));     // 16-byte aligned: n entries
   int* s_ja = reinterpret_cast<int*>(s_prd + n);                            // nnzb
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int e = tid; e < 9 * nnzb; e += nt) s_val[e] = val[e];
   for (int e = tid; e < 9 * n; e += nt) s_dinv[e] = dinv[e];
-  for (int e = tid; e < 3 * n; e += nt) { s_b[e] = b[e]; s_x[e] = mode == 1 ? 0.0 : x[e]; }
+  for (int e = tid; e < VS * n; e += nt) { const int k = e % VS; s_b[e] = k < 3 ? b[(size_t)bs * (e / VS) + k] : 0.0; s_x[e] = mode == 1 ? 0.0 : x[e]; }
   for (int e = tid; e < n; e += nt) s_prd[e] = prd[e];
   for (int e = tid; e < nnzb; e += nt) s_ja[e] = ja[e];
   __syncthreads();
@@ -357,7 +360,7 @@ mcgs_smem_kernel(int n, int nnzb, int ngroups, int reverse, int mode, const int*
         if (k == nl) continue;
         int st;
         const double* v = s_val + bsrt_off(s, len, nl, k, st);
-        const int j = 3 * s_ja[s + k];
+        const int j = VS * s_ja[s + k];
         const double x0 = s_x[j], x1 = s_x[j + 1], x2 = s_x[j + 2];
         a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
         a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
@@ -365,7 +368,7 @@ mcgs_smem_kernel(int n, int nnzb, int ngroups, int reverse, int mode, const int*
       }
       a0 = half_sum(a0); a1 = half_sum(a1); a2 = half_sum(a2);
       if (row >= 0 && lane < 3) {
-        const int o = 3 * row;
+        const int o = VS * row;
         const double r0 = s_b[o] - a0, r1 = s_b[o + 1] - a1, r2 = s_b[o + 2] - a2;
         const double* d = s_dinv + 9 * p + 3 * lane;
         const double xn = d[0] * r0 + d[1] * r1 + d[2] * r2;
@@ -373,6 +376,7 @@ mcgs_smem_kernel(int n, int nnzb, int ngroups, int reverse, int mode, const int*
         s_x[o + lane] = xn;
         x[o + lane] = xn;
       }
+      if (VS == 4 && row >= 0 && lane == 3) { x[4 * row + 3] = 0.0; if (mode == 2) dl[4 * row + 3] = 0.0; }
     }
     __syncthreads();
   }
@@ -610,57 +614,59 @@ __global__ void iota_kernel(int n, int* __restrict__ a)
 
 } // namespace
 
-void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s)
+void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s, int ys)
 {
-  launch_rows<M_SPMV, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, nullptr, x, y, nullptr, s);
+  launch_rows<M_SPMV, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, nullptr, x, y, nullptr, s, VS, ys);
 }
 
-void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s)
+void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s, int bs, int ys)
 {
-  launch_rows<M_RES, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, b, x, r, nullptr, s);
+  launch_rows<M_RES, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, b, x, r, nullptr, s, bs, ys);
 }
 
 void bsrt_spmv_rowid(const BsrT& A, const double* x, double* y, cudaStream_t s)
 {
-  launch_rows<M_SPMV, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A.ja.p, A, nullptr, nullptr, x, y, nullptr, s);
+  launch_rows<M_SPMV, PNPB200_NAT_CTAS, true, 3>(A.n, A.n, A.rd.p, A.ja.p, A, nullptr, nullptr, x, y, nullptr, s);
 }
 
 void bsrt_residual_rowid(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s)
 {
-  launch_rows<M_RES, PNPB200_NAT_CTAS, true>(A.n, A.n, A.rd.p, A.ja.p, A, nullptr, b, x, r, nullptr, s);
+  launch_rows<M_RES, PNPB200_NAT_CTAS, true, 3>(A.n, A.n, A.rd.p, A.ja.p, A, nullptr, b, x, r, nullptr, s);
 }
 
-void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x, double* r, cudaStream_t s)
+void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x, double* r, cudaStream_t s, int bs)
 {
   const BsrT& A = L.A;
-  launch_rows<M_RESU, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.vrd.p, A.jpos.p, A, nullptr, b, x, r, nullptr, s);
+  launch_rows<M_RESU, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.vrd.p, A.jpos.p, A, nullptr, b, x, r, nullptr, s, bs, VS);
 }
 
-void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s)
+void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s, int bs, int ys)
 {
   const BsrT& A = L.A;
-  if (owned_rows(L) != A.n) launch_rows<M_LDELTAG, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.vrd.p, A.jpos.p, A, nullptr, b, delta, y, nullptr, s);
-  else launch_rows<M_LDELTA, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, b, delta, y, nullptr, s);
+  if (owned_rows(L) != A.n) launch_rows<M_LDELTAG, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.vrd.p, A.jpos.p, A, nullptr, b, delta, y, nullptr, s, bs, ys);
+  else launch_rows<M_LDELTA, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, b, delta, y, nullptr, s, bs, ys);
 }
 
 namespace {
-__global__ void permute3_kernel(int n, const int* __restrict__ rowid, const double* __restrict__ in, double* __restrict__ out, int to_sweep)
+// row-id vectors are packed (3 per row), sweep-space vectors hold VS doubles per row (pad = 0)
+__global__ void permute3_kernel(int n, const int* __restrict__ rowid, const double* __restrict__ in, double* __restrict__ out, int to_sweep, int vs)
 {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 3 * (size_t)n) return;
-  const size_t p = e / 3; const int k = (int)(e % 3);
+  if (e >= (size_t)vs * (size_t)n) return;
+  const size_t p = e / vs; const int k = (int)(e % vs);
+  if (k == 3) { if (to_sweep) out[e] = 0.0; return; }
   const size_t r = 3 * (size_t)rowid[p] + k;
   if (to_sweep) out[e] = in[r]; else out[r] = in[e];
 }
 } // namespace
 
-void vec_to_sweep(const BsrT& A, const double* in_rowid, double* out_sweep, cudaStream_t s)
+void vec_to_sweep(const BsrT& A, const double* in_rowid, double* out_sweep, cudaStream_t s, int vs)
 {
-  permute3_kernel<<<cdiv(3 * (size_t)A.n, 256), 256, 0, s>>>(A.n, A.vrowid.p, in_rowid, out_sweep, 1); PNP_COUNT_LAUNCH();
+  permute3_kernel<<<cdiv((size_t)vs * (size_t)A.n, 256), 256, 0, s>>>(A.n, A.vrowid.p, in_rowid, out_sweep, 1, vs); PNP_COUNT_LAUNCH();
 }
-void vec_from_sweep(const BsrT& A, const double* in_sweep, double* out_rowid, cudaStream_t s)
+void vec_from_sweep(const BsrT& A, const double* in_sweep, double* out_rowid, cudaStream_t s, int vs)
 {
-  permute3_kernel<<<cdiv(3 * (size_t)A.n, 256), 256, 0, s>>>(A.n, A.vrowid.p, in_sweep, out_rowid, 0); PNP_COUNT_LAUNCH();
+  permute3_kernel<<<cdiv((size_t)vs * (size_t)A.n, 256), 256, 0, s>>>(A.n, A.vrowid.p, in_sweep, out_rowid, 0, vs); PNP_COUNT_LAUNCH();
 }
 
 void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s)
@@ -689,7 +695,7 @@ void bsrt_export_ja(const BsrT& A, int* d_ja_nat, cudaStream_t s)
 
 namespace {
 // mode 0: plain, 1: forward from a zero initial guess, 2: with delta output
-void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool reverse, int mode, cudaStream_t s)
+void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool reverse, int mode, cudaStream_t s, int bs)
 {
   const BsrT& A = L.A;
   if (A.n <= SMALL_LEVEL_ROWS && L.ngroups > 0 && small_level_smem(A.n, A.nnzb) <= SMALL_SMEM_BYTES) {
@@ -700,13 +706,13 @@ void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool rev
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     mcgs_smem_kernel<<<1, 1024, small_level_smem(A.n, A.nnzb), s>>>(A.n, A.nnzb, L.ngroups, reverse ? 1 : 0, mode, L.d_color_ptr.p,
-                                                                  A.prd.p, A.jpos.p, A.val.p, L.dinv.p, b, x, dl);
+                                                                  A.prd.p, A.jpos.p, A.val.p, L.dinv.p, b, x, dl, bs);
     PNP_COUNT_LAUNCH();
     return;
   }
   if (A.n <= SMALL_LEVEL_ROWS && L.ngroups > 0) {
     mcgs_small_kernel<<<1, 1024, 0, s>>>(L.ngroups, reverse ? 1 : 0, mode, L.d_color_ptr.p, A.prd.p, A.jpos.p, A.val.p,
-                                        L.dinv.p, b, x, dl);
+                                        L.dinv.p, b, x, dl, bs);
     PNP_COUNT_LAUNCH();
     return;
   }
@@ -716,16 +722,16 @@ void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool rev
     if (cnt == 0) continue;
     const int4* rd = A.prd.p + L.color_ptr[c];
     const double* dinv = L.dinv.p + 9 * (size_t)L.color_ptr[c];      // sweep order: this colour's piece
-    if (mode == 1) launch_rows<M_GS0, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, nullptr, s);
-    else if (mode == 2) launch_rows<M_GSD, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, dl, s);
-    else launch_rows<M_GS, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, nullptr, s);
+    if (mode == 1) launch_rows<M_GS0, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, nullptr, s, bs, VS);
+    else if (mode == 2) launch_rows<M_GSD, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, dl, s, bs, VS);
+    else launch_rows<M_GS, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, nullptr, s, bs, VS);
   }
 }
 } // namespace
 
-void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s) { sweep_impl(L, b, x, nullptr, reverse, 0, s); }
-void mcgs_sweep_from_zero(const Level& L, const double* b, double* x, cudaStream_t s) { sweep_impl(L, b, x, nullptr, false, 1, s); }
-void mcgs_sweep_back_delta(const Level& L, const double* b, double* x, double* delta, cudaStream_t s) { sweep_impl(L, b, x, delta, true, 2, s); }
+void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s, int bs) { sweep_impl(L, b, x, nullptr, reverse, 0, s, bs); }
+void mcgs_sweep_from_zero(const Level& L, const double* b, double* x, cudaStream_t s, int bs) { sweep_impl(L, b, x, nullptr, false, 1, s, bs); }
+void mcgs_sweep_back_delta(const Level& L, const double* b, double* x, double* delta, cudaStream_t s, int bs) { sweep_impl(L, b, x, delta, true, 2, s, bs); }
 
 // Colour the natural graph (A.ia, ja_nat), then lay the matrix out colour by colour.
 // `ws` (optional) supplies the temporaries during AMG setup; at create time they come from the pool.

@@ -254,6 +254,20 @@ int pnpb200_set_dirichlet(pnpb200_handle* ph, int n_bc, const int* bc_dofs)
   });
 }
 
+int pnpb200_set_coloring(pnpb200_handle* ph, int n_colors, const int* color)
+{
+  if (!ph || !color) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    PNP_CUDA(cudaSetDevice(h.device));
+    if (h.nv == 0) throw Error(ERROR_INPUT_PAR, "handle has no mesh");
+    set_fine_coloring(h, n_colors, color);
+    h.rhs_current = false;
+    PNP_CUDA(cudaStreamSynchronize(h.stream));
+    return FASP_SUCCESS;
+  });
+}
+
 int pnpb200_set_solution(pnpb200_handle* ph, const double* uu)
 {
   if (!ph || !uu) return ERROR_INPUT_PAR;
@@ -609,8 +623,9 @@ int pnpb200_apply_vcycle(pnpb200_handle* ph, const double* r, double* z)
   return guarded([&]() -> int {
     Handle& h = ph->h; cudaStream_t s = h.stream;
     if (!h.hier.symbolic_valid) throw Error(ERROR_INPUT_PAR, "no hierarchy: call pnpb200_solve first");
-    const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
-    DevBuf<double> dr, dz, t; dr.alloc(N, s); dz.alloc(N, s); t.alloc(N, s);
+    const size_t N = 3 * (size_t)h.hier.lv[0]->A.n, NS = VS * (size_t)h.hier.lv[0]->A.n;
+    DevBuf<double> dr, dz, t; dr.alloc(NS, s); dz.alloc(NS, s); t.alloc(N, s);
+    dz.zero();
     t.upload(r, N);
     const BsrT& A0 = h.hier.lv[0]->A;
     vec_to_sweep(A0, t.p, dr.p, s);         // the cycle works in sweep order
@@ -633,11 +648,12 @@ int pnpb200_probe_kernel(pnpb200_handle* ph, int which_in, int reps, double* ms_
     if (level < 0 || level >= (int)h.hier.lv.size()) throw Error(ERROR_INPUT_PAR, "probe level out of range");
     if (level > 0 && !(which <= 2 || (which >= 7 && which <= 10))) throw Error(ERROR_INPUT_PAR, "coarse-level probes: matrix passes only");
     Level& L = *h.hier.lv[level];
-    const double* rhs = level == 0 ? h.rhs.p : L.b.p;
     const BsrT& A = L.A;
-    const size_t N = 3 * (size_t)A.n;
-    DevBuf<double> x, y; x.alloc(N, s); y.alloc(N, s);
-    vec_set(x.p, 1.0, N, s); vec_set(y.p, 0.5, N, s);
+    const size_t N = 3 * (size_t)A.n, NS = VS * (size_t)A.n;      // dofs; length of a sweep-space vector
+    DevBuf<double> x, y, bsw; x.alloc(NS, s); y.alloc(NS, s);
+    vec_set(x.p, 1.0, NS, s); vec_set(y.p, 0.5, NS, s);
+    const double* rhs = L.b.p;
+    if (level == 0) { bsw.alloc(NS, s); vec_to_sweep(A, h.rhs.p, bsw.p, s); rhs = bsw.p; }   // the matrix passes run in sweep space
     const double b_mat = (double)A.nnzb * 76.0 + ((double)A.n + 1.0) * 4.0;
     double bytes = 0.0;
     auto run = [&](int k) {
@@ -645,7 +661,7 @@ int pnpb200_probe_kernel(pnpb200_handle* ph, int which_in, int reps, double* ms_
         case 0: bsrt_spmv(A, x.p, y.p, s); break;
         case 1: bsrt_residual(A, rhs, x.p, y.p, s); break;
         case 2: mcgs_sweep(L, rhs, y.p, (k & 1) != 0, s); break;
-        case 3: { double out[32]; multi_dot(h, h.kry.V.p, N, 16, y.p, N, out); break; }
+        case 3: { double out[32]; multi_dot(h, h.kry.V.p, NS, 16, y.p, NS, out); break; }
         case 4: { assemble_residual(h, h.rhs, nullptr, nullptr); break; }
         case 5: case 6: assemble_system(h); break;
         case 7: mcgs_sweep_from_zero(L, rhs, y.p, s); break;
@@ -662,7 +678,7 @@ int pnpb200_probe_kernel(pnpb200_handle* ph, int which_in, int reps, double* ms_
               if (L.ncolors == 0 || L.dinv.n < 9 * (size_t)A.n) throw Error(ERROR_INPUT_PAR, "probe 2 needs a solve first");
               bytes = b_mat + 3.0 * N * 8.0 + 72.0 * A.n; break;
       case 8: case 10: bytes = b_mat + 3.0 * N * 8.0; break;
-      case 3: if (h.kry.V.n < 17 * N) throw Error(ERROR_INPUT_PAR, "probe 3 needs a solve first");
+      case 3: if (h.kry.V.n < 17 * NS) throw Error(ERROR_INPUT_PAR, "probe 3 needs a solve first");
               bytes = 17.0 * N * 8.0; break;
       case 4: bytes = (double)h.nc * 16.0 + (double)h.nv * 24.0 + N * 8.0 * 2.0 + (double)h.nv * 16.0 + N * 8.0 * 2.0; break;
       default: bytes = (double)h.nc * 16.0 + (double)h.nv * 24.0 + N * 8.0 + (double)h.nv * 16.0 + N * 8.0 * 2.0 + (double)A.nnzb * 72.0; break;

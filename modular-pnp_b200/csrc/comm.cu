@@ -46,12 +46,13 @@ inline void nccl_check(int rc, const char* what)
   if (rc != 0) throw Error(ERROR_DEVICE, std::string("NCCL failure in ") + what + " (code " + std::to_string(rc) + ")");
 }
 
-// sendbuf[3*q + k] = vec[3*idx[q] + k]
-__global__ void pack3_kernel(int n, const int* __restrict__ idx, const double* __restrict__ vec, double* __restrict__ buf)
+// sendbuf[XS*q + k] = vec[XS*idx[q] + k]   (XS doubles per block row: 3 in row-id space, VS in sweep space)
+template <int XS>
+__global__ void pack_rows_kernel(int n, const int* __restrict__ idx, const double* __restrict__ vec, double* __restrict__ buf)
 {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 3 * n) return;
-  buf[e] = vec[3 * (size_t)idx[e / 3] + e % 3];
+  if (e >= XS * n) return;
+  buf[e] = vec[(size_t)XS * (size_t)idx[e / XS] + e % XS];
 }
 } // namespace
 
@@ -87,13 +88,19 @@ void halo_exchange(Handle& h, Halo& c, double* vec, bool sweep_space)
   const int nsend = c.send_ptr.back();
   if (sweep_space && nsend > 0 && !c.send_pos.p) throw Error(ERROR_UNKNOWN, "halo_exchange: level has no sweep-space send list");
   const int* idx = sweep_space ? c.send_pos.p : c.send_idx.p;      // ghost rows are the tail in both orders
-  if (nsend > 0) { pack3_kernel<<<cdiv(3 * (size_t)nsend, 256), 256, 0, s>>>(nsend, idx, vec, c.sendbuf.p); PNP_COUNT_LAUNCH(); }
+  const size_t xs = sweep_space ? VS : 3;      // doubles per block row of this vector
+  if (c.sendbuf.n < xs * (size_t)(nsend ? nsend : 1)) c.sendbuf.alloc(xs * (size_t)(nsend ? nsend : 1), s);
+  if (nsend > 0) {
+    if (sweep_space) pack_rows_kernel<VS><<<cdiv(VS * (size_t)nsend, 256), 256, 0, s>>>(nsend, idx, vec, c.sendbuf.p);
+    else pack_rows_kernel<3><<<cdiv(3 * (size_t)nsend, 256), 256, 0, s>>>(nsend, idx, vec, c.sendbuf.p);
+    PNP_COUNT_LAUNCH();
+  }
   Api& a = api();
   nccl_check(a.gstart(), "groupStart");
   for (size_t k = 0; k < c.nbr.size(); ++k) {
     const int ns = c.send_ptr[k + 1] - c.send_ptr[k], nr = c.recv_ptr[k + 1] - c.recv_ptr[k];
-    if (ns > 0) nccl_check(a.send(c.sendbuf.p + 3 * (size_t)c.send_ptr[k], 3 * (size_t)ns, NCCL_DOUBLE, c.nbr[k], h.comm.nccl, s), "send");
-    if (nr > 0) nccl_check(a.recv(vec + 3 * (size_t)c.recv_ptr[k], 3 * (size_t)nr, NCCL_DOUBLE, c.nbr[k], h.comm.nccl, s), "recv");
+    if (ns > 0) nccl_check(a.send(c.sendbuf.p + xs * (size_t)c.send_ptr[k], xs * (size_t)ns, NCCL_DOUBLE, c.nbr[k], h.comm.nccl, s), "send");
+    if (nr > 0) nccl_check(a.recv(vec + xs * (size_t)c.recv_ptr[k], xs * (size_t)nr, NCCL_DOUBLE, c.nbr[k], h.comm.nccl, s), "recv");
   }
   nccl_check(a.gend(), "groupEnd");
 }
@@ -177,7 +184,7 @@ int pnpb200_set_partition(pnpb200_handle* ph, int n_owned, int n_neighbors, cons
     for (int k = 0; k <= n_neighbors; ++k) if (c.recv_ptr[k] < n_owned || c.recv_ptr[k] > h.nv) throw Error(ERROR_INPUT_PAR, "ghost range outside [n_owned, n_local]");
     c.send_idx.alloc(nsend ? nsend : 1, s);
     if (nsend) c.send_idx.upload(send_idx, nsend);
-    c.sendbuf.alloc(3 * (size_t)(nsend ? nsend : 1), s);
+    c.sendbuf.alloc(4 * (size_t)(nsend ? nsend : 1), s);
     // ghost rows must not be part of the Gauss-Seidel colour groups: lay the fine level out again
     relayout_fine_level(h);
     // ghost dofs become identity rows of the local matrix (like Dirichlet rows)

@@ -10,6 +10,13 @@
 
 namespace pnpb200 {
 
+// doubles per block row in the solver's SWEEP-SPACE vectors (internal.hpp): 4 = padded to one
+// 32-byte sector per row (the pad entry is kept at zero), 3 = packed
+#ifndef PNPB200_VSTRIDE
+#define PNPB200_VSTRIDE 4
+#endif
+constexpr int VS = PNPB200_VSTRIDE;
+
 struct Error : public std::runtime_error {
   int code;
   Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
@@ -196,6 +203,22 @@ __device__ __forceinline__ size_t bsrt_off(int s, int len, int nl, int k, int& s
   stride = len;
   return 9 * (size_t)s + (size_t)k;
 #endif
+}
+// gather the three components of block row j from a vector with XS doubles per row. Sweep-space
+// vectors are padded to XS = 4 doubles (32 bytes, one DRAM sector) per row so that the gather is ONE
+// 256-bit load (LDG.E.256 on sm_100a) instead of three 8-byte loads that each walk the same 16
+// scattered sectors of a half-warp: the gathers were half of the L1 data-pipe wavefronts of the row
+// kernels (profiles/README.md, round 2). Row-id vectors (C ABI, assembly) stay packed (XS = 3).
+template <int XS>
+__device__ __forceinline__ void load_row3(const double* x, int j, double& x0, double& x1, double& x2)
+{
+  if (XS == 4) {
+    double pad;
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x0), "=d"(x1), "=d"(x2), "=d"(pad) : "l"(x + 4 * (size_t)j) : "memory");
+  } else {
+    const double* p = x + (size_t)XS * (size_t)j;
+    x0 = p[0]; x1 = p[1]; x2 = p[2];
+  }
 }
 __host__ __device__ __forceinline__ unsigned hash32(unsigned x)
 {

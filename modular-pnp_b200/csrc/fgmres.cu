@@ -31,8 +31,13 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
 {
   cudaStream_t s = h.stream;
   const BsrT& A = h.hier.lv[0]->A;
-  const size_t n = 3 * (size_t)A.n;          // local vector length (owned + ghost dofs) = basis stride
-  const size_t m = owned_dofs(h);            // reductions and updates run over the owned dofs only
+  // The Krylov basis V is PACKED (KS = 3 doubles per row): an Arnoldi step streams the whole basis twice
+  // (multi_dot, multi_axpy), padding it would cost 33 % more traffic there. The preconditioned vectors Z
+  // and the iterate x are gathered by the matrix passes and therefore padded (VS doubles per row).
+  constexpr int KS = 3;
+  const size_t n = KS * (size_t)A.n;         // V: local vector length (owned + ghost rows) = basis stride
+  const size_t m = KS * (size_t)owned_rows(*h.hier.lv[0]);   // reductions and updates run over the owned rows only
+  const size_t nz = VS * (size_t)A.n, mz = VS * (size_t)owned_rows(*h.hier.lv[0]);     // the same for Z and x
   const bool dist = h.comm.active();
   Halo& halo = h.hier.lv[0]->halo;
   auto zero_ghost = [&](double* v) { if (n > m) PNP_CUDA(cudaMemsetAsync(v + m, 0, (n - m) * sizeof(double), s)); };
@@ -40,12 +45,12 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
   const int restart_max = cfg.restart < 1 ? 1 : cfg.restart, restart_min = 3, dstep = 3;
   const double cr_max = 0.99, cr_min = 0.174, epsmac = 1e-20;
   Krylov& K = h.kry;
+  // sweep-space vectors are padded to VS doubles per row; the pad entries must be (and stay) zero
   K.V.alloc((size_t)(restart_max + 1) * n, s);
-  K.Z.alloc((size_t)restart_max * n, s);
-  K.r.alloc(n, s);
+  { const double* old = K.Z.p; K.Z.alloc((size_t)restart_max * nz, s); if (K.Z.p != old) K.Z.zero(); }
   double* V = K.V.p; double* Z = K.Z.p;
   auto Vi = [&](int i) { return V + (size_t)i * n; };
-  auto Zi = [&](int i) { return Z + (size_t)i * n; };
+  auto Zi = [&](int i) { return Z + (size_t)i * nz; };
 
   std::vector<std::vector<double>> hh(restart_max + 1, std::vector<double>(restart_max, 0.0));
   std::vector<double> c(restart_max), sn(restart_max), rs(restart_max + 1), hcol(restart_max + 2), h2(restart_max + 2),
@@ -58,7 +63,7 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
     r_norm = b_norm;
   } else {
     if (dist) halo_exchange(h, halo, x, true);
-    bsrt_residual(A, b, x, Vi(0), s);
+    bsrt_residual(A, b, x, Vi(0), s, KS, KS);
     r_norm = vec_norm2(h, Vi(0), m);
   }
   const double den = b_norm > 0.0 ? b_norm : r_norm;
@@ -86,10 +91,10 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
       {
         PhaseTimer t(h, h.stats.ms_vcycle);
         zero_ghost(Vi(i - 1));     // the preconditioner is local to the rank (block Jacobi across GPUs)
-        if (cfg.use_amg) have_Az = amg_vcycle(h, cfg, Vi(i - 1), Zi(i - 1), Vi(i));
-        else vec_copy(Zi(i - 1), Vi(i - 1), n, s);
+        if (cfg.use_amg) have_Az = amg_vcycle(h, cfg, Vi(i - 1), Zi(i - 1), Vi(i), KS, KS);
+        else vec_restride(Vi(i - 1), KS, Zi(i - 1), VS, (size_t)A.n, s);
       }
-      if (!have_Az) { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, halo, Zi(i - 1), true); bsrt_spmv(A, Zi(i - 1), Vi(i), s); }
+      if (!have_Az) { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, halo, Zi(i - 1), true); bsrt_spmv(A, Zi(i - 1), Vi(i), s, KS); }
       double tnorm;
       {
         PhaseTimer t(h, h.stats.ms_ortho);
@@ -133,11 +138,11 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
       t += rs[k];
       rs[k] = t / hh[k][k];
     }
-    multi_axpy(h, Z, n, i, rs.data(), x, m, nullptr);
+    multi_axpy(h, Z, nz, i, rs.data(), x, mz, nullptr);
     // true residual for the convergence confirmation / next cycle
     const bool est_conv = r_norm <= epsilon;
     if (dist) halo_exchange(h, halo, x, true);
-    bsrt_residual(A, b, x, Vi(0), s);
+    bsrt_residual(A, b, x, Vi(0), s, KS, KS);
     r_norm = vec_norm2(h, Vi(0), m);
     if (est_conv && r_norm <= epsilon) { converged = true; break; }
     if (!std::isfinite(r_norm)) { h.stats.krylov_its = iter; return ERROR_SOLVER_EXIT; }
@@ -155,10 +160,10 @@ int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x,
 {
   cudaStream_t s = h.stream;
   const BsrT& A = h.hier.lv[0]->A;
-  const size_t n = 3 * (size_t)A.n;
+  const size_t n = VS * (size_t)A.n;
   Krylov& K = h.kry;
-  K.bs.alloc(n, s); K.xs.alloc(n, s);
-  vec_to_sweep(A, b, K.bs.p, s);
+  K.bs.alloc(3 * (size_t)A.n, s); K.xs.alloc(n, s);       // rhs packed like the Krylov basis, iterate padded
+  vec_to_sweep(A, b, K.bs.p, s, 3);
   if (zero_guess) vec_set(K.xs.p, 0.0, n, s); else vec_to_sweep(A, x, K.xs.p, s);
   const int rc = fgmres_sweep(h, cfg, K.bs.p, K.xs.p, zero_guess);
   vec_from_sweep(A, K.xs.p, x, s);      // the last iterate, also on failure

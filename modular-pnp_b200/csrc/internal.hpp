@@ -205,6 +205,7 @@ struct Handle {
 void build_mesh_tables(Handle& h);                 // v2c, pattern, brow/dslot/tslot, omega
 void compute_k00(Handle& h);
 void relayout_fine_level(Handle& h);                // after the partition (ghost rows) is known
+void set_fine_coloring(Handle& h, int ncolors, const int* host_color);   // caller-supplied proper colouring
 void generate_box_mesh(Handle& h, int nx, int ny, int nz, double lx, double ly, double lz);   // domain_build
 // colour the graph given in natural CSR (ia, ja_nat), lay the rows out colour by colour (rs, rowid,
 // physical ja) and build brow/dslot/tslot
@@ -226,29 +227,34 @@ long mark_cells(Handle& h, const double* d_eta, double tol, long target_size, un
 // (entry q belongs to row A.vrowid[q], see BsrT): a Gauss-Seidel colour then reads b and writes x
 // in long contiguous runs. Same kernels, different index arrays: (rd, ja) for row-id space,
 // (vrd or prd, jpos) for sweep space.
-void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s);                  // y = A x      (sweep space)
-void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s); // r = b - A x  (sweep space)
+// Sweep-space vectors hold VS doubles per row (common.cuh: padded to one 32-byte sector so that the
+// gather of x is one 256-bit load). Exception: the Krylov basis V of FGMRES stays PACKED (3 per row:
+// every Arnoldi step streams the whole basis twice), so the passes that read the cycle's rhs (b) or
+// write A*z (y) take the stride of those vectors as bs / ys.
+void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s, int ys = VS);                  // y = A x      (sweep space)
+void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s, int bs = VS, int ys = VS); // r = b - A x  (sweep space)
 void bsrt_spmv_rowid(const BsrT& A, const double* x, double* y, cudaStream_t s);            // y = A x      (row-id space)
 void bsrt_residual_rowid(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s);
-void vec_to_sweep(const BsrT& A, const double* in_rowid, double* out_sweep, cudaStream_t s);
-void vec_from_sweep(const BsrT& A, const double* in_sweep, double* out_rowid, cudaStream_t s);
+void vec_to_sweep(const BsrT& A, const double* in_rowid, double* out_sweep, cudaStream_t s, int vs = VS);
+void vec_from_sweep(const BsrT& A, const double* in_sweep, double* out_rowid, cudaStream_t s, int vs = VS);
 void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s);
 void bsrt_from_fasp(const double* d_val_fasp, BsrT& A, cudaStream_t s);
 void bsrt_export_ja(const BsrT& A, int* d_ja_nat, cudaStream_t s);
 void bsrt_to_fasp(const BsrT& A, double* d_val_fasp, cudaStream_t s);
-void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s);
+void mcgs_sweep(const Level& L, const double* b, double* x, bool reverse, cudaStream_t s, int bs = VS);
 // forward sweep from a ZERO initial guess (x need not be initialised on the swept rows): lower parts only
-void mcgs_sweep_from_zero(const Level& L, const double* b, double* x, cudaStream_t s);
+void mcgs_sweep_from_zero(const Level& L, const double* b, double* x, cudaStream_t s, int bs = VS);
 // r = b - A x right after mcgs_sweep_from_zero (swept rows: r = -U x; ghost rows: full row)
-void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x, double* r, cudaStream_t s);
+void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x, double* r, cudaStream_t s, int bs = VS);
 // backward sweep that also returns delta = x_new - x_old, and y = A x_new = b + L delta after it
-void mcgs_sweep_back_delta(const Level& L, const double* b, double* x, double* delta, cudaStream_t s);
-void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s);
+void mcgs_sweep_back_delta(const Level& L, const double* b, double* x, double* delta, cudaStream_t s, int bs = VS);
+void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s, int bs = VS, int ys = VS);
 // ---- vecops.cu
 void vec_set(double* x, double v, size_t n, cudaStream_t s);
 void vec_copy(double* dst, const double* src, size_t n, cudaStream_t s);
 void vec_axpy(double a, const double* x, double* y, size_t n, cudaStream_t s);      // y += a x
 void vec_scale(double a, double* x, size_t n, cudaStream_t s);
+void vec_restride(const double* in, int is, double* out, int os, size_t nrows, cudaStream_t s);   // 3 <-> 4 doubles per row
 double vec_norm2(Handle& h, const double* x, size_t n);                              // sync
 // dots[i] = <V_i, w> for i < nv, dots[nv] = <w, w>; V_i = V + i*ld. Synchronises.
 void multi_dot(Handle& h, const double* V, size_t ld, int nvec, const double* w, size_t n, double* out_host);
@@ -293,7 +299,8 @@ int block_pnp_stokes_solve(BlockSystem& S, const double* b, double* x, BlockStat
 void amg_setup(Handle& h, const SolverConfig& cfg);
 // z = M^{-1} r. If Az != nullptr and the cycle can deliver it for half a matrix pass (at least one
 // post-smoothing sweep), Az = A z is written too and true is returned.
-bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az = nullptr);
+// r carries rs doubles per row, Az azs (the Krylov basis is packed); z is a padded sweep-space vector.
+bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az = nullptr, int rs = VS, int azs = VS);
 // ---- fgmres.cu
 // zero_guess: x is known to be all zeros on entry (linear_pnp.cpp:93), so r0 = b needs no matvec
 int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x, bool zero_guess = false);

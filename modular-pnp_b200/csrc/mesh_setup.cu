@@ -217,6 +217,27 @@ void build_mesh_tables(Handle& h)
   PNP_LAUNCH_CHECK();
 }
 
+// caller-supplied colouring of the fine level (pnpb200_set_coloring): verified against the pattern,
+// then the level is laid out again colour by colour
+void set_fine_coloring(Handle& h, int ncolors, const int* host_color)
+{
+  cudaStream_t s = h.stream;
+  Level& L = *h.hier.lv[0];
+  BsrT& A = L.A;
+  if (ncolors < 1 || ncolors > 62) throw Error(ERROR_INPUT_PAR, "pnpb200_set_coloring: 1 .. 62 colours");
+  for (int v = 0; v < A.n; ++v) if (host_color[v] < 0 || host_color[v] >= ncolors) throw Error(ERROR_INPUT_PAR, "pnpb200_set_coloring: colour out of range");
+  L.preset_color.alloc(A.n, s);
+  L.preset_color.upload(host_color, A.n);
+  DevBuf<int> ja_nat; ja_nat.alloc(A.nnzb, s);
+  bsrt_export_ja(A, ja_nat.p, s);
+  DevBuf<int> bad; bad.alloc(1, s); bad.zero();
+  check_coloring_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, ja_nat.p, L.preset_color.p, bad.p); PNP_COUNT_LAUNCH();
+  int hb = 0; bad.download(&hb, 1);
+  if (hb) { L.preset_ncolors = 0; throw Error(ERROR_INPUT_PAR, "pnpb200_set_coloring: two coupled vertices share a colour"); }
+  L.preset_ncolors = ncolors;
+  relayout_fine_level(h);
+}
+
 void relayout_fine_level(Handle& h)
 {
   cudaStream_t s = h.stream;

@@ -115,6 +115,21 @@ void vec_scale(double a, double* x, size_t n, cudaStream_t s)
   scale_kernel<<<vec_grid(n), VB, 0, s>>>(a, x, n); PNP_COUNT_LAUNCH();
 }
 
+namespace {
+__global__ void restride_kernel(size_t nrows, const double* __restrict__ in, int is, double* __restrict__ out, int os)
+{
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nrows * (size_t)os) return;
+  const size_t r = e / os; const int k = (int)(e % os);
+  out[e] = k < is && k < 3 ? in[r * is + k] : 0.0;
+}
+}
+void vec_restride(const double* in, int is, double* out, int os, size_t nrows, cudaStream_t s)
+{
+  if (is == os) { vec_copy(out, in, nrows * (size_t)is, s); return; }
+  restride_kernel<<<cdiv(nrows * (size_t)os, 256), 256, 0, s>>>(nrows, in, is, out, os); PNP_COUNT_LAUNCH();
+}
+
 void multi_dot(Handle& h, const double* V, size_t ld, int nvec, const double* w, size_t n, double* out_host)
 {
   cudaStream_t s = h.stream;

@@ -76,3 +76,43 @@ def box_slab_partition(nx, ny, nz, lx, ly, lz, rank, nranks):
                 # classes on every rank; see box_coloring in csrc/mesh_setup.cu): not consumed yet, the
                 # slabs are still coloured as general graphs on the device
                 color=((ix + iy + iz) % 4).astype(np.int32))
+
+
+# ---- the C++ partitioner of the library (csrc/partition.cpp): what bench.py and the tests use ----------
+def brick_grid(nranks, nx, ny, nz):
+    """px * py * pz = nranks with the most cube-like bricks for an nx x ny x nz box (minimal halo
+    surface); ties resolved towards cutting z, then y (x is the contiguous index of the numbering)."""
+    best, grid = None, (1, 1, nranks)
+    for px in range(1, nranks + 1):
+        if nranks % px:
+            continue
+        for py in range(1, nranks // px + 1):
+            if (nranks // px) % py:
+                continue
+            pz = nranks // (px * py)
+            if px > nx + 1 or py > ny + 1 or pz > nz + 1:
+                continue
+            bx, by, bz = (nx + 1) / px, (ny + 1) / py, (nz + 1) / pz
+            surf = min(px - 1, 2) * by * bz + min(py - 1, 2) * bx * bz + min(pz - 1, 2) * bx * by     # an interior brick has two faces per cut direction
+            key = (surf, px, py)
+            if best is None or key < best:
+                best, grid = key, (px, py, pz)
+    return grid
+
+
+def box_brick_partition(nx, ny, nz, lx, ly, lz, rank, nranks, grid=None):
+    """pnpb200_partition_box: the rank's brick of the BoxMesh (same dict layout as box_slab_partition,
+    plus the closed-form 4-colouring); grid = (px, py, pz), default brick_grid(). (1, 1, nranks) gives
+    exactly the z-slabs of box_slab_partition."""
+    from . import capi
+    px, py, pz = grid or brick_grid(nranks, nx, ny, nz)
+    assert px * py * pz == nranks
+    d = capi.partition_box(nx, ny, nz, lx, ly, lz, px, py, pz, rank)
+    d["grid"] = (px, py, pz)
+    return d
+
+
+def mesh_rcb_partition(xyz, cells, rank, nranks):
+    """pnpb200_partition_mesh: recursive coordinate bisection of any conforming tetrahedral mesh"""
+    from . import capi
+    return capi.partition_mesh(xyz, cells, nranks, rank)
