@@ -293,6 +293,188 @@ __global__ void rap_numeric_kernel(int cnnzb, const int4* __restrict__ crd, cons
   cval[co + (size_t)t * cst] = acc;
 }
 
+// ---- Galerkin product, row-wise form ------------------------------------------------------------
+// A half-warp owns one coarse row I = one aggregate. With piecewise-constant P the coarse row is the
+// sum of the aggregate's fine rows with the columns renamed j -> agg[j], so the fine matrix is read
+// exactly once, as whole contiguous rows (lane k = block k of the fine row, like the matvec). No
+// global sort of the 253 M (I,J) keys of the 256^3 fine level (22 ms + 15 ms of scattered gathers by
+// its permutation): measured 37 -> 9 ms for the first coarsening step.
+//   symbolic: the distinct coarse columns of the row go through a per-half-warp hash set in shared
+//             memory (count pass, then fill pass + rank sort -> ascending natural order);
+//   numeric : per-half-warp accumulators acc[slot][9] in shared memory, slot = position of the
+//             coarse column in the row's physical [L | D | U] order. Lanes of a fine row that map to
+//             the same coarse column add one after the other in lane order (match_any groups), fine
+//             rows in ascending order: the sum order is fixed, the result deterministic.
+// Rows with more than RAPW_MAXCOLS distinct columns are not handled here: the level then takes the
+// sort-based path below (nothing in the BASELINE configs does).
+constexpr int RAPW_HASH = 256;          // hash-set slots per half-warp (symbolic)
+constexpr int RAPW_MAXCOLS = 192;       // longest coarse row of the row-wise path
+
+constexpr int RAPW_TMPW = 64;           // rows up to this length hand their column set from the count pass to the fill pass
+
+// FILL = false: count pass. The distinct coarse columns of row I are collected in the hash set, the
+//   count goes to rowcnt[I]; sets of <= RAPW_TMPW columns are also parked (unsorted) in tmpcols so
+//   that the fill pass does not hash the row a second time.
+// FILL = true : fill pass. Column set from tmpcols (or hashed again for the few long rows), rank
+//   sort -> ascending natural order into cja[cia[I] ..].
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+rapw_symbolic_kernel(int nown_c, int nghost_c, const int* __restrict__ agg_ptr, const int* __restrict__ agg_rows,
+                     const int4* __restrict__ rd, const int* __restrict__ ja, const int* __restrict__ agg,
+                     int* __restrict__ rowcnt, int* __restrict__ maxlen, int* __restrict__ tmpcols,
+                     const int* __restrict__ cia, int* __restrict__ cja)
+{
+  __shared__ int tab[16][RAPW_HASH];
+  __shared__ int list[16][RAPW_HASH];
+  __shared__ int cnt[16];
+  const int hw = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const int I = blockIdx.x * 16 + hw;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+  if (I >= nown_c + nghost_c) return;                       // whole half-warp
+  if (I >= nown_c) {                                        // coarse ghost row: identity diagonal
+    if (lane == 0) { if (FILL) cja[cia[I]] = I; else rowcnt[I] = 1; }
+    return;
+  }
+  int n = FILL ? cia[I + 1] - cia[I] : 0;
+  if (FILL && n <= RAPW_TMPW) {
+    for (int e = lane; e < n; e += 16) list[hw][e] = tmpcols[(size_t)I * RAPW_TMPW + e];
+  } else {
+    for (int e = lane; e < RAPW_HASH; e += 16) tab[hw][e] = -1;
+    if (lane == 0) cnt[hw] = 0;
+    __syncwarp(hmask);
+    for (int m = agg_ptr[I]; m < agg_ptr[I + 1]; ++m) {
+      const int4 d = rd[agg_rows[m]];
+      for (int k = lane; k < d.y; k += 16) {
+        const int J = agg[ja[d.x + k]];
+        if (J < 0) continue;
+        unsigned h = hash32((unsigned)J) & (RAPW_HASH - 1);
+        for (int probe = 0; probe < RAPW_HASH; ++probe) {
+          const int old = atomicCAS(&tab[hw][h], -1, J);
+          if (old == -1) { list[hw][atomicAdd(&cnt[hw], 1)] = J; break; }      // first sighting: append to the dense list
+          if (old == J) break;
+          h = (h + 1) & (RAPW_HASH - 1);
+        }
+      }
+    }
+    __syncwarp(hmask);
+    n = cnt[hw];
+  }
+  if (!FILL) {
+    if (lane == 0) { rowcnt[I] = n; atomicMax(maxlen, n); }
+    if (n <= RAPW_TMPW) for (int e = lane; e < n; e += 16) tmpcols[(size_t)I * RAPW_TMPW + e] = list[hw][e];
+    return;
+  }
+  __syncwarp(hmask);
+  // ascending natural order: rank of an entry = number of smaller entries
+  const int base = cia[I];
+  for (int e = lane; e < n; e += 16) {
+    const int J = list[hw][e];
+    int rank = 0;
+    for (int q = 0; q < n; ++q) rank += list[hw][q] < J ? 1 : 0;
+    cja[base + rank] = J;
+  }
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(16 * (CAP <= 32 ? 12 : CAP <= 64 ? 6 : 2))
+rapw_numeric_kernel(int nown_c, int nghost_c, const int* __restrict__ agg_ptr, const int* __restrict__ agg_rows,
+                    const int4* __restrict__ frd, const int* __restrict__ fja, const int* __restrict__ agg,
+                    const double* __restrict__ fval, const int4* __restrict__ crd, const int* __restrict__ cja,
+                    double* __restrict__ cval)
+{
+  constexpr int HW = CAP <= 32 ? 12 : CAP <= 64 ? 6 : 2;     // half-warps per CTA (static shared memory <= 48 KB)
+  constexpr int HT = CAP <= 32 ? 64 : CAP <= 64 ? 128 : 512;  // hash map coarse column -> slot (power of two, > CAP)
+  constexpr int AS = 10;                                      // doubles per accumulator slot: 9 + pad, so that a slot is five aligned 16-byte words
+  __shared__ __align__(16) double acc[HW][CAP * AS];
+  __shared__ int2 map[HW][HT];                                // (coarse column, slot), .x = -1: empty
+  const int hw = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const int I = blockIdx.x * HW + hw;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+  if (I >= nown_c + nghost_c) return;
+  const int4 c = crd[I];                                      // (start, len, nl, row) of the coarse row
+  if (I >= nown_c) {                                          // coarse ghost row: identity block
+    if (lane < 9) { int st; const size_t o = bsrt_off(c.x, c.y, c.z, c.z, st); cval[o + (size_t)lane * st] = (lane == 0 || lane == 4 || lane == 8) ? 1.0 : 0.0; }
+    return;
+  }
+  const int len = c.y;
+  for (int e = lane; e < HT; e += 16) map[hw][e] = make_int2(-1, -1);
+  for (int e = lane; e < AS * len; e += 16) acc[hw][e] = 0.0;
+  __syncwarp(hmask);
+  for (int q = lane; q < len; q += 16) {                      // slot = position in the row's physical [L | D | U] order
+    const int J = cja[c.x + q];
+    unsigned h = hash32((unsigned)J) & (HT - 1);
+    while (atomicCAS(&map[hw][h].x, -1, J) != -1) h = (h + 1) & (HT - 1);      // columns of a row are distinct
+    map[hw][h].y = q;
+  }
+  __syncwarp(hmask);
+  // The (fine row, 16-block pass) items of the aggregate are walked with a one-item look-ahead: the
+  // loads of the next item (descriptor -> columns -> aggregate ids, and the 9 values of the lane's
+  // block) are in flight while the current one is added up. m, ps, d, dn are uniform over the half-warp.
+  int m = agg_ptr[I], ps = 0;
+  const int mend = agg_ptr[I + 1];
+  const int4 none = make_int4(0, 0, 0, 0);
+  int4 d = m < mend ? frd[agg_rows[m]] : none;
+  int4 dn = m + 1 < mend ? frd[agg_rows[m + 1]] : none;
+  auto fetch = [&](int& J, double (&v)[9]) {       // item (m, ps) into registers, then step to the next item
+    J = -1;
+    const int k = ps * 16 + lane;
+    if (k < d.y) {
+      J = agg[fja[d.x + k]];
+      int st;
+      const size_t o = bsrt_off(d.x, d.y, d.z, k, st);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) v[t] = fval[o + (size_t)t * st];
+    }
+    if ((ps + 1) * 16 < d.y) ++ps;
+    else { ++m; ps = 0; d = dn; dn = m + 1 < mend ? frd[agg_rows[m + 1]] : none; }
+  };
+  auto accumulate = [&](int J, double (&v)[9]) {
+    int slot = -1;
+    if (J >= 0) {
+      unsigned h = hash32((unsigned)J) & (HT - 1);
+      int2 e = map[hw][h];
+      while (e.x != J && e.x != -1) { h = (h + 1) & (HT - 1); e = map[hw][h]; }
+      slot = e.x == J ? e.y : -1;
+    }
+    // lanes with the same slot add in lane order, one member of every group per round (tried: summing a
+    // group in registers with shuffles first — 17 instead of 10 ms at 256^3, the shuffles cost more than
+    // the shared-memory updates they save)
+    const unsigned peers = __match_any_sync(hmask, slot) & hmask;
+    const int rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+    int rounds = slot >= 0 ? __popc(peers) : 0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { const int t = __shfl_xor_sync(hmask, rounds, o); rounds = t > rounds ? t : rounds; }
+    for (int r = 0; r < rounds; ++r) {
+      if (slot >= 0 && rank == r) {
+        double2* a2 = reinterpret_cast<double2*>(&acc[hw][slot * AS]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { double2 w = a2[t]; w.x += v[2 * t]; w.y += v[2 * t + 1]; a2[t] = w; }
+        acc[hw][slot * AS + 8] += v[8];
+      }
+      __syncwarp(hmask);
+    }
+  };
+  bool have = m < mend;
+  int Jc = -1; double vc[9];
+  if (have) fetch(Jc, vc);
+  while (have) {
+    const bool more = m < mend;
+    int Jn = -1; double vn[9];
+    if (more) fetch(Jn, vn);
+    accumulate(Jc, vc);
+    have = more; Jc = Jn;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) vc[t] = vn[t];
+  }
+  // coarse row out, BSR-T layout
+  for (int q = lane; q < len; q += 16) {
+    int st;
+    const size_t o = bsrt_off(c.x, c.y, c.z, q, st);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) cval[o + (size_t)t * st] = acc[hw][q * AS + t];
+  }
+}
+
 // ---- grid transfer (sweep space, internal.hpp) --------------------------------------------------
 // coarse position P <- sum of the fine positions of aggregate c_rowid[P] (coarsest level: P itself).
 // Fine vectors hold VS doubles per row (sweep space); the coarse vector holds CS: VS, or 3 when the
@@ -488,7 +670,9 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   const int n = A.n, nnzb = A.nnzb;
   // all large temporaries of this coarsening step live in the handle's workspace
   Workspace& ws = h.ws;
-  ws.reserve((size_t)nnzb * 60 + (size_t)n * 104 + (64u << 20), s);
+  // (the sort-based fallback of the Galerkin product needs 60 bytes per block; it re-reserves below)
+  static const bool rowwise_on = getenv("PNPB200_RAP_ROWWISE") ? atoi(getenv("PNPB200_RAP_ROWWISE")) != 0 : true;
+  ws.reserve((size_t)nnzb * (rowwise_on ? 14 : 60) + (size_t)n * 112 + (64u << 20), s);
   ws.reset();
   struct P1 { double* p; } pp; struct P2 { unsigned char* p; } iso, strong; struct P3 { int* p; void zero(cudaStream_t st) { cudaMemsetAsync(p, 0, sizeof(int), st); } } state, cnt;
   struct P4 { u64* p; } t1, t2;
@@ -617,6 +801,45 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
     iota_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, vin.p); PNP_COUNT_LAUNCH();
     sort_pairs(ws, kin.p, kout.p, vin.p, L.agg_rows.p, n, 32, s);
   }
+  // coarse structure. Row-wise path first (rapw_* kernels above): per coarse row, hash set of the
+  // renamed columns -> counts -> scan -> sorted column lists.
+  ph.reset(); ph.reset(new Phase(s, g_phase, "rap symbolic", g_phase_lvl));
+  L.rap_rowwise = false;
+  if (rowwise_on) {
+    BsrT& Ac = C.A;
+    // nothing taken from the workspace so far is still needed (the aggregates live in the level's own
+    // buffers): start over, and make sure the parked column lists fit whatever the coarsening ratio was
+    ws.reset();
+    ws.reserve((size_t)ncoarse * (4 * RAPW_TMPW + 128) + (size_t)nnzb * 4 + (64u << 20), s);
+    struct { int* p; } rowcnt, mx, tmpcols; rowcnt.p = ws.get<int>(ncoarse + 1); mx.p = ws.get<int>(1);
+    tmpcols.p = ws.get<int>((size_t)ncoarse * RAPW_TMPW);
+    PNP_CUDA(cudaMemsetAsync(rowcnt.p + ncoarse, 0, sizeof(int), s));
+    PNP_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), s));
+    rapw_symbolic_kernel<false><<<cdiv(ncoarse, 16), 256, 0, s>>>(nagg, nghost_c, L.agg_ptr.p, L.agg_rows.p, A.rd.p, A.ja.p, L.agg.p,
+                                                                 rowcnt.p, mx.p, tmpcols.p, nullptr, nullptr); PNP_COUNT_LAUNCH();
+    Ac.ia.alloc(ncoarse + 1, s);
+    exclusive_scan_int(rowcnt.p, Ac.ia.p, ncoarse + 1, s);
+    int hv[2] = {0, 0};
+    PNP_CUDA(cudaMemcpyAsync(&hv[0], Ac.ia.p + ncoarse, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaMemcpyAsync(&hv[1], mx.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PNP_CUDA(cudaStreamSynchronize(s));
+    if (hv[1] <= RAPW_MAXCOLS) {
+      const int cnnzb = hv[0];
+      Ac.n = ncoarse; Ac.nnzb = cnnzb;
+      Ac.val.alloc(9 * (size_t)cnnzb, s);
+      struct { int* p; } cja_nat; cja_nat.p = ws.get<int>(cnnzb);
+      rapw_symbolic_kernel<true><<<cdiv(ncoarse, 16), 256, 0, s>>>(nagg, nghost_c, L.agg_ptr.p, L.agg_rows.p, A.rd.p, A.ja.p, L.agg.p,
+                                                                  nullptr, nullptr, tmpcols.p, Ac.ia.p, cja_nat.p); PNP_COUNT_LAUNCH();
+      ph.reset(); ph.reset(new Phase(s, g_phase, "coarse colour+layout", g_phase_lvl));
+      color_and_layout(C, cja_nat.p, &ws, s);
+      L.rap_rowwise = true; L.rap_maxcols = hv[1];
+      return true;
+    }
+    // a coarse row is longer than the row-wise kernels hold: sort-based path, which needs the big workspace.
+    // Nothing taken from the workspace so far is still needed (aggregates live in the level's own buffers).
+    ws.reserve((size_t)nnzb * 60 + (size_t)n * 112 + (64u << 20), s);
+    ws.reset();
+  }
   // coarse structure: sort blocks by (I,J). (Tried: gathering the blocks aggregate by aggregate and
   // sorting each aggregate's ~165 entries on J with cub::DeviceSegmentedSort — the segmented sort
   // alone took 52 ms at 192^3 (107 M entries in 640 k segments) where this whole radix-sort path
@@ -659,6 +882,17 @@ void rap_numeric(Handle& h, Level& L, Level& C)
 {
   cudaStream_t s = h.stream;
   BsrT& A = L.A; BsrT& Ac = C.A;
+  if (L.rap_rowwise) {
+    const int nown = L.nagg, ngh = Ac.n - L.nagg;
+    if (L.rap_maxcols <= 32)
+      rapw_numeric_kernel<32><<<cdiv(Ac.n, 12), 192, 0, s>>>(nown, ngh, L.agg_ptr.p, L.agg_rows.p, A.rd.p, A.ja.p, L.agg.p, A.val.p, Ac.rd.p, Ac.ja.p, Ac.val.p);
+    else if (L.rap_maxcols <= 64)
+      rapw_numeric_kernel<64><<<cdiv(Ac.n, 6), 96, 0, s>>>(nown, ngh, L.agg_ptr.p, L.agg_rows.p, A.rd.p, A.ja.p, L.agg.p, A.val.p, Ac.rd.p, Ac.ja.p, Ac.val.p);
+    else
+      rapw_numeric_kernel<RAPW_MAXCOLS><<<cdiv(Ac.n, 2), 32, 0, s>>>(nown, ngh, L.agg_ptr.p, L.agg_rows.p, A.rd.p, A.ja.p, L.agg.p, A.val.p, Ac.rd.p, Ac.ja.p, Ac.val.p);
+    PNP_COUNT_LAUNCH();
+    return;
+  }
   rap_numeric_kernel<<<cdiv(9 * (size_t)Ac.nnzb, 256), 256, 0, s>>>(Ac.nnzb, Ac.rd.p, Ac.brow.p, L.rap_beg.p, L.rap_end.p,
                                                                    L.rap_perm.p, A.rd.p, A.brow.p, A.val.p, Ac.val.p);
   PNP_COUNT_LAUNCH();

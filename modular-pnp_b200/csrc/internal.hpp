@@ -76,6 +76,8 @@ struct Level {
   bool coarse_identity = false;    // the next level is the coarsest (dense solve): its vectors stay in row-id order
   // numeric RAP map: coarse block s sums fine blocks rap_perm[rap_seg[s] .. rap_seg[s+1])
   DevBuf<int> rap_beg, rap_end, rap_perm;
+  bool rap_rowwise = false;     // Galerkin product by the row-wise kernels (amg.cu: rapw_*), no sort map
+  int rap_maxcols = 0;          // longest coarse row (selects the shared-memory accumulator size)
   // work vectors (3*n)
   DevBuf<double> x, b, w;
   // K-cycle scratch: 5 vectors, device scalars + partials, block counter
