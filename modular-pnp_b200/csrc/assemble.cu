@@ -3,15 +3,20 @@
 //   Linear_PNP::apply_eafe               benchmarks/pnp_exact_solution/linear_pnp.cpp:195-285
 //   BC re-apply after EAFE               linear_pnp.cpp:78-80
 //   zero-row fix                         src/pde.cpp:596-621
-// Two passes, both atomic-free and deterministic:
+// Two passes, both atomic-free and deterministic (a sorted-key scatter: the key of a contribution is the
+// slot it is written to, fixed per mesh in mesh_setup.cu: build_assembly_tables):
 //   (A) cell kernels evaluate the quadrature sums of the generated forms
 //       (forms.h:7917-8360 bilinear, 24-point rule; :8385-8644 linear, 15-point rule) once per
-//       cell into a compact record (geometry is constant per P1 cell, so the 12x12 tensor
-//       factorises into 32 numbers);
-//   (B) block kernels own one 3x3 block (i,j) each, gather the records of the cells that
-//       contain both vertices in ascending cell order (the sorted key is the block index),
-//       evaluate the EAFE edge formula (include/EAFE.h:4851-4879) for the (k,k) entries and
-//       write the finished block once, in BSR-T layout.
+//       cell (geometry is constant per P1 cell, so the 12x12 tensor factorises into 32 numbers) and
+//       write, per local vertex pair, one 32-byte record (Q1 G, Q2 G, det M1, det M2) into the run of
+//       that vertex pair — runs are contiguous and ordered by ascending cell id;
+//   (B) block kernels own one 3x3 block (i,j) each, sum the run of {i,j} (one 256-bit load per
+//       cell, the same run serves (i,j) and (j,i)), evaluate the EAFE edge formula
+//       (include/EAFE.h:4851-4879) for the (k,k) entries and write the finished block once, in
+//       BSR-T layout.
+// The residual works the same way with 24-byte records per (cell, vertex). Round 1 wrote one
+// 256-byte record per cell and gathered 24- and 16-byte pieces of it through L2 (40 ms per
+// Jacobian, 8 ms per residual at 256^3, 3-4 sectors fetched per piece used).
 #include "internal.hpp"
 #include "fem.cuh"
 #include <cub/cub.cuh>
@@ -21,15 +26,30 @@ namespace pnpb200 {
 
 namespace {
 
+#ifndef PNPB200_ASM_CTAS
+#define PNPB200_ASM_CTAS 4      // resident CTAs per SM the pair-run block kernel is compiled for
+#endif
 constexpr int REC_EAFE = 32;   // 10 x (G, det*M1, det*M2) pair-major, then Q[2]
 constexpr int REC_FULL = 68;   // + S[2] T1[16] T2[16] (+2 pad)
 
 // ---- (A) Jacobian cell records -------------------------------------------------------------
+__device__ __forceinline__ void store_rec4(double* p, double a, double b, double c, double d)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void load_rec4(const double* p, double& a, double& b, double& c, double& d)
+{
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// FULL = false (EAFE on): pair records through cpslot. FULL = true (Galerkin-only Jacobian, no_eafe()):
+// the 68-number cell record of round 1 (the (k,k) terms are not symmetric in the vertex pair).
 template <bool FULL, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 cell_jacobian_kernel(int nc, const int4* __restrict__ cells, const double* __restrict__ xyz,
                      const double* __restrict__ uu, const double* __restrict__ diff,
-                     const double* __restrict__ val, double pscale, int cutoff, double* __restrict__ rec)
+                     const double* __restrict__ val, double pscale, int cutoff, const int* __restrict__ cpslot,
+                     double* __restrict__ rec)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
@@ -82,7 +102,20 @@ cell_jacobian_kernel(int nc, const int4* __restrict__ cells, const double* __res
       }
     }
   }
-  double* o = rec + (size_t)c * (FULL ? REC_FULL : REC_EAFE);
+  if (!FULL) {
+    // one 32-byte record per local vertex pair, into the run of that pair
+    int m = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int s = r; s < 4; ++s) {
+        const double G = det * dot3(g[r], g[s]);
+        store_rec4(rec + 4 * (size_t)cpslot[10 * (size_t)c + m], Q[0] * G, Q[1] * G, det * M[0][m], det * M[1][m]);
+        ++m;
+      }
+    return;
+  }
+  double* o = rec + (size_t)c * REC_FULL;
   // pair-major: the three numbers a block (i,j) needs from this cell are contiguous
   int m = 0;
 #pragma unroll
@@ -129,6 +162,137 @@ __device__ __forceinline__ double eafe_weight(const double* __restrict__ uu, con
   return aE * exp(beta_s);
 }
 
+// Per-vertex operands of the EAFE edge weights, one 32-byte entry per (vertex, ion): (f, exp(f), exp(beta), D)
+// with beta = eta + q phi, f = eta - beta — exactly the quantities eafe_weight() forms at an edge end, so
+// the weights built from the table are bit-identical to evaluating include/EAFE.h:4857-4867 per edge,
+// with one exp per directed edge and ion (the B(d) denominator) instead of three.
+__global__ void eafe_vertex_table_kernel(int nv, const double* __restrict__ uu, const double* __restrict__ diff,
+                                         double q1, double q2, double* __restrict__ tab)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const double phi = uu[3 * (size_t)v];
+#pragma unroll
+  for (int k = 1; k <= 2; ++k) {
+    const double qk = k == 1 ? q1 : q2;
+    const double eta = uu[3 * (size_t)v + k];
+    double beta = eta;
+    if (qk != 0.0) beta = eta + phi * qk;
+    const double f = eta - beta;
+    store_rec4(tab + 8 * (size_t)v + 4 * (k - 1), f, exp(f), exp(beta), diff[3 * (size_t)v + k]);
+  }
+}
+
+// bern[r][s] of EAFE.h:4857-4867 from the two table entries (r = row end, s = column end)
+__device__ __forceinline__ double eafe_weight_tab(double fr, double Dr, double fs, double efs, double ebs, double Ds)
+{
+  const double d = fs - fr;
+  double aE = 0.5 * (Dr + Ds) * efs;
+  aE *= (fabs(d) < 3.0e-16) ? 1.0 - 0.5 * d : d / (exp(d) - 1.0);
+  return aE * ebs;
+}
+
+// ---- (B), EAFE on: a half-warp per block row, lane k = block k of the row -------------------------
+// Lane k sums the record run of the vertex pair {i, j_k} (ascending cell id; the same run, hence the
+// same rounding, serves (i,j) and (j,i)) and evaluates the two EAFE edge weights of its block and their
+// transposes; the EAFE diagonal (zero column sums, EAFE.h:4876-4879) is a half-warp reduction of the
+// transposed weights. The run of the DIAGONAL pair {i,i} (every cell of the vertex, 24 on a Kuhn mesh
+// against 4-6 for an edge) is summed by the whole half-warp, two records per lane and a fixed shuffle
+// tree, so that no lane loops four times longer than its neighbours. Rows are visited in natural
+// order, the finished blocks go to the row's physical, colour-major position.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+assemble_pairs_kernel(int n, const int4* __restrict__ rd, const int* __restrict__ ja, const int2* __restrict__ pblk,
+                      const double* __restrict__ rec, const double* __restrict__ k00, const double* __restrict__ omega,
+                      const double* __restrict__ etab, const unsigned char* __restrict__ bcflag, double* __restrict__ val)
+{
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int lane = threadIdx.x & 15;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);      // my half-warp
+  int s = 0, len = 0, nl = 0;
+  bool bc0 = false, bc1 = false, bc2 = false;
+  double fi1 = 0, efi1 = 0, ebi1 = 0, Di1 = 0, fi2 = 0, efi2 = 0, ebi2 = 0, Di2 = 0;
+  double dg1 = 0.0, dg2 = 0.0, dm1 = 0.0, dm2 = 0.0;           // sums of the diagonal pair's run
+  if (i < n) {
+    const int4 d = rd[i];
+    s = d.x; len = d.y; nl = d.z;
+    bc0 = bcflag[3 * (size_t)i] != 0; bc1 = bcflag[3 * (size_t)i + 1] != 0; bc2 = bcflag[3 * (size_t)i + 2] != 0;
+    load_rec4(etab + 8 * (size_t)i, fi1, efi1, ebi1, Di1);
+    load_rec4(etab + 8 * (size_t)i + 4, fi2, efi2, ebi2, Di2);
+    const int2 run = pblk[s + nl];                              // the diagonal block sits behind the nl lower blocks
+    const double* r = rec + 4 * (size_t)run.x;
+    for (int q = lane; q < run.y; q += 16) {
+      double g1, g2, m1, m2;
+      load_rec4(r + 4 * (size_t)q, g1, g2, m1, m2);
+      dg1 += g1; dg2 += g2; dm1 += m1; dm2 += m2;
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    dg1 += __shfl_xor_sync(hmask, dg1, o); dg2 += __shfl_xor_sync(hmask, dg2, o);
+    dm1 += __shfl_xor_sync(hmask, dm1, o); dm2 += __shfl_xor_sync(hmask, dm2, o);
+  }
+  const int npass = (len + 15) >> 4;                          // uniform over the half-warp
+  double d1 = 0.0, d2 = 0.0;                                  // -(column sums) of the EAFE off-diagonals
+  int diag_k = -1; double diag_a[9];
+  for (int ps = 0; ps < npass; ++ps) {
+    const int k = ps * 16 + lane;
+    const bool act = k < len;
+    const int b = s + (act ? k : 0), j = act ? ja[b] : -1;
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (act) a[0] = k00[b];
+    if (act && i == j) {                          // keep the diagonal block until the column sums are known
+      a[3] = dg1; a[6] = dg2; a[1] = -dm1; a[2] = -dm2;
+      diag_k = k;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) diag_a[t] = a[t];
+      continue;
+    }
+    if (act) {
+      const int2 run = pblk[b];
+      const double* r = rec + 4 * (size_t)run.x;
+#pragma unroll 2
+      for (int q = 0; q < run.y; ++q) {
+        double g1, g2, m1, m2;
+        load_rec4(r + 4 * (size_t)q, g1, g2, m1, m2);
+        a[3] += g1;                 // (1,0): q1 D1 e^{u1} grad u0 . grad v1
+        a[6] += g2;                 // (2,0)
+        a[1] -= m1;                 // (0,1): -q1 e^{u1} u1 v0
+        a[2] -= m2;                 // (0,2)
+      }
+      const double w = omega[b];                 // omega is symmetric: the same weight serves A_ij and A_ji
+      double fj, efj, ebj, Dj;
+      load_rec4(etab + 8 * (size_t)j, fj, efj, ebj, Dj);
+      a[4] = w * eafe_weight_tab(fi1, Di1, fj, efj, ebj, Dj);
+      d1 -= w * eafe_weight_tab(fj, Dj, fi1, efi1, ebi1, Di1);
+      load_rec4(etab + 8 * (size_t)j + 4, fj, efj, ebj, Dj);
+      a[8] = w * eafe_weight_tab(fi2, Di2, fj, efj, ebj, Dj);
+      d2 -= w * eafe_weight_tab(fj, Dj, fi2, efi2, ebi2, Di2);
+      // DirichletBC::apply: row -> identity row (pattern kept)
+      if (bc0) { a[0] = 0.0; a[1] = 0.0; a[2] = 0.0; }
+      if (bc1) { a[3] = 0.0; a[4] = 0.0; a[5] = 0.0; }
+      if (bc2) { a[6] = 0.0; a[7] = 0.0; a[8] = 0.0; }
+      int st;
+      double* o = val + bsrt_off(s, len, nl, k, st);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) o[(size_t)t * st] = a[t];
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) { d1 += __shfl_xor_sync(hmask, d1, o); d2 += __shfl_xor_sync(hmask, d2, o); }
+  if (diag_k >= 0) {
+    diag_a[4] = d1; diag_a[8] = d2;
+    if (bc0) { diag_a[0] = 1.0; diag_a[1] = 0.0; diag_a[2] = 0.0; }
+    if (bc1) { diag_a[3] = 0.0; diag_a[4] = 1.0; diag_a[5] = 0.0; }
+    if (bc2) { diag_a[6] = 0.0; diag_a[7] = 0.0; diag_a[8] = 1.0; }
+    int st;
+    double* o = val + bsrt_off(s, len, nl, diag_k, st);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) o[(size_t)t * st] = diag_a[t];
+  }
+}
+
+// ---- (B), Galerkin-only Jacobian (no_eafe()): the round-1 gather from 68-number cell records -------
 // ---- (B) a half-warp per block row, lane k = block k of the row ------------------------------
 // Rows are visited in natural order so that the cell records stream through L2 once; the finished
 // blocks go to the row's physical, colour-major position. The row's incident cells are loaded
@@ -265,7 +429,7 @@ cell_residual_kernel(int nc, const int4* __restrict__ cells, const double* __res
                      const double* __restrict__ uu, const double* __restrict__ eps,
                      const double* __restrict__ fixed, const double* __restrict__ diff,
                      const double* __restrict__ val, const double* __restrict__ reac,
-                     double pscale, double* __restrict__ rec)
+                     double pscale, const int* __restrict__ cvslot, double* __restrict__ rec)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
@@ -315,9 +479,11 @@ cell_residual_kernel(int nc, const int4* __restrict__ cells, const double* __res
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int d = 0; d < 3; ++d) gu0[d] += u0[r] * g[r][d];
-  double* o = rec + 12 * (size_t)c;
+  // the three numbers for local vertex i go to that vertex' slot of this cell (3 contiguous doubles)
+  const int4 sl = reinterpret_cast<const int4*>(cvslot)[c];
+  double* o[4] = {rec + 3 * (size_t)sl.x, rec + 3 * (size_t)sl.y, rec + 3 * (size_t)sl.z, rec + 3 * (size_t)sl.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) o[i] = det * pscale * F[i] - E * (det * dot3(gu0, g[i]));
+  for (int i = 0; i < 4; ++i) o[i][0] = det * pscale * F[i] - E * (det * dot3(gu0, g[i]));
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     double guk[3] = {0, 0, 0}, gqk[3] = {0, 0, 0};
@@ -327,14 +493,13 @@ cell_residual_kernel(int nc, const int4* __restrict__ cells, const double* __res
       for (int d = 0; d < 3; ++d) { guk[d] += u[k][r] * g[r][d]; gqk[d] += q[k][r] * g[r][d]; }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      o[4 * (k + 1) + i] = det * R[k][i]
-                           - det * (s0[k] * dot3(guk, g[i]) + s1[k] * dot3(gu0, g[i]) + s2[k] * dot3(gqk, g[i]));
+      o[i][k + 1] = det * R[k][i]
+                    - det * (s0[k] * dot3(guk, g[i]) + s1[k] * dot3(gu0, g[i]) + s2[k] * dot3(gqk, g[i]));
   }
 }
 
 __global__ void __launch_bounds__(256)
-residual_gather_kernel(int nv, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
-                       const int4* __restrict__ cells, const double* __restrict__ rec,
+residual_gather_kernel(int nv, const int* __restrict__ v2c_ptr, const double* __restrict__ rec,
                        const unsigned char* __restrict__ bcflag, double* __restrict__ out,
                        double* __restrict__ partial /* [2*gridDim] sumsq, max */)
 {
@@ -343,11 +508,10 @@ residual_gather_kernel(int nv, const int* __restrict__ v2c_ptr, const int* __res
   double ss = 0.0, mx = 0.0;
   if (i < nv) {
     double b[3] = {0, 0, 0};
+    // the records of the vertex' cells: contiguous, ascending cell id
     for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; ++p) {
-      const int c = v2c_idx[p];
-      const int li = local_index(cells[c], i);
-      const double* r = rec + 12 * (size_t)c;
-      b[0] += r[li]; b[1] += r[4 + li]; b[2] += r[8 + li];
+      const double* r = rec + 3 * (size_t)p;
+      b[0] += r[0]; b[1] += r[1]; b[2] += r[2];
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -626,11 +790,11 @@ void assemble_residual(Handle& h, DevBuf<double>& out, double* l2, double* linf)
   out.alloc(3 * (size_t)h.nv, s);
   // 4 CTAs/SM (128 registers): measured 26.7 ms per residual at 256^3 vs 32.0 at 2 CTAs/SM
   cell_residual_kernel<4><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.eps.p, h.fixed.p, h.diff.p,
-                                                         h.val.p, h.reac.p, h.poisson_scale, h.cellrec.p);
+                                                         h.val.p, h.reac.p, h.poisson_scale, h.cvslot.p, h.cellrec.p);
   PNP_COUNT_LAUNCH();
   const int nblk = cdiv(h.nv, 256);
   h.red.alloc(2 * (size_t)nblk + 2, s);
-  residual_gather_kernel<<<nblk, 256, 0, s>>>(h.nv, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.bcflag.p, out.p, h.red.p + 2);
+  residual_gather_kernel<<<nblk, 256, 0, s>>>(h.nv, h.v2c_ptr.p, h.cellrec.p, h.bcflag.p, out.p, h.red.p + 2);
   PNP_COUNT_LAUNCH();
   finalize_norm_kernel<<<1, 1024, 0, s>>>(nblk, h.red.p + 2, h.red.p);
   PNP_COUNT_LAUNCH();
@@ -659,22 +823,21 @@ void assemble_system(Handle& h)
   // step's rhs (the reference assembles it again, src/pde.cpp:546), so it is only rebuilt if stale
   if (!h.rhs_current) assemble_residual(h, h.rhs, nullptr, nullptr);
   mark(1);
-  const int rs = h.use_eafe ? REC_EAFE : REC_FULL;
-  const size_t need = (size_t)h.nc * rs;
+  const size_t need = h.use_eafe ? 4 * h.n_pair_records : (size_t)h.nc * REC_FULL;
   if (h.cellrec.n < need) h.cellrec.alloc(need, s);
   if (h.use_eafe) {
     // exp-bound: 3 CTAs/SM (136 registers) is the measured optimum (23 ms; 25 at 4, 35 at 6)
-    cell_jacobian_kernel<false, 3><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, h.cellrec.p);
+    cell_jacobian_kernel<false, 3><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, h.cpslot.p, h.cellrec.p);
     PNP_COUNT_LAUNCH();
     mark(2);
-    // 6 CTAs/SM (40 registers, some spills): the gather is latency bound, occupancy beats registers
-    // (measured at 256^3: 55 ms at 3 CTAs/SM, 44 at 4, 40 at 6)
-    assemble_blocks_kernel<true, 6><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
-        A.n, A.rd.p, A.ja.p, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cellrec.p, h.k00.p, h.omega.p,
-        h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.bcflag.p, A.val.p);
+    h.eafe_tab.alloc(8 * (size_t)h.nv, s);
+    eafe_vertex_table_kernel<<<cdiv(h.nv, 256), 256, 0, s>>>(h.nv, h.uu.p, h.diff.p, h.q_eafe[1], h.q_eafe[2], h.eafe_tab.p);
+    PNP_COUNT_LAUNCH();
+    assemble_pairs_kernel<PNPB200_ASM_CTAS><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(
+        A.n, A.rd.p, A.ja.p, h.pblk.p, h.cellrec.p, h.k00.p, h.omega.p, h.eafe_tab.p, h.bcflag.p, A.val.p);
     PNP_COUNT_LAUNCH();
   } else {
-    cell_jacobian_kernel<true, 2><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, h.cellrec.p);
+    cell_jacobian_kernel<true, 2><<<cdiv(h.nc, 128), 128, 0, s>>>(h.nc, cells, h.xyz.p, h.uu.p, h.diff.p, h.val.p, h.poisson_scale, h.conc_cutoff, nullptr, h.cellrec.p);
     PNP_COUNT_LAUNCH();
     mark(2);
     assemble_blocks_kernel<false, 4><<<cdiv((size_t)A.n * 16, 256), 256, 0, s>>>(

@@ -176,7 +176,13 @@ struct Handle {
   // fine level matrix + per-pattern tables
   DevBuf<double> omega;         // nnzb: EAFE edge weights  sum_T S^T_ij
   DevBuf<double> k00;           // nnzb: permittivity stiffness (solution independent)
-  DevBuf<double> cellrec;       // per-cell quadrature records (Jacobian), reused for residual
+  DevBuf<double> cellrec;       // scatter records of the assembly (assemble.cu): 4 doubles per (cell, vertex pair) for the
+                                // Jacobian, 3 per (cell, vertex) for the residual, 68 per cell for the Galerkin-only Jacobian
+  DevBuf<int> cvslot;           // 4*nc : residual record slot of (cell, local vertex)   = position in the vertex' cell list
+  DevBuf<int> cpslot;           // 10*nc: Jacobian record index of (cell, local vertex pair)
+  DevBuf<int2> pblk;            // nnzb : (first record, count) of the pair run a block sums (physical block index)
+  DevBuf<double> eafe_tab;      // 8*nv : per (vertex, ion) operands of the EAFE edge weights (assemble.cu)
+  size_t n_pair_records = 0;
   DevBuf<double> eta;           // DG0 entropy indicator of the last pnpb200_entropy_indicator call (nc)
   bool eta_valid = false;
   // solver
@@ -206,6 +212,7 @@ struct Handle {
 // ---- mesh_setup.cu
 void build_mesh_tables(Handle& h);                 // v2c, pattern, brow/dslot/tslot, omega
 void compute_k00(Handle& h);
+void build_assembly_tables(Handle& h);                // slot tables of the atomic-free scatter for the current fine-level layout
 void relayout_fine_level(Handle& h);                // after the partition (ghost rows) is known
 void set_fine_coloring(Handle& h, int ncolors, const int* host_color);   // caller-supplied proper colouring
 void generate_box_mesh(Handle& h, int nx, int ny, int nz, double lx, double ly, double lz);   // domain_build

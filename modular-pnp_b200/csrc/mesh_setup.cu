@@ -113,7 +113,93 @@ __global__ void edge_table_kernel(int nnzb, const int* __restrict__ ja, const in
   out[b] = acc;
 }
 
+// ---- slot tables of the atomic-free scatter (assemble.cu) ----------------------------------------
+// Residual: the 3 numbers cell c contributes to its r-th vertex v go to slot p = position of c in v's
+// ascending cell list (v2c), so that the per-vertex sum reads 3 * |cells(v)| contiguous doubles.
+__global__ void cell_vertex_slot_kernel(int nv, const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
+                                        const int4* __restrict__ cells, int* __restrict__ cvslot)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  for (int p = v2c_ptr[v]; p < v2c_ptr[v + 1]; ++p) {
+    const int c = v2c_idx[p];
+    const int r = local_index(cells[c], v);
+    if (r >= 0) cvslot[4 * (size_t)c + r] = p;
+  }
+}
+
+// Jacobian: a vertex pair {i, j} (i <= j, diagonal included) owns one run of records, one per cell that
+// contains both vertices, ascending cell id. The run belongs to the UPPER block (i, j); the block (j, i)
+// reads the same run. Pass 1 counts the cells of every upper block, pass 2 hands every (cell, local pair)
+// its record index and every upper block its (start, count).
+__global__ void pair_count_kernel(int nnzb, const int* __restrict__ ja, const int* __restrict__ brow,
+                                  const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
+                                  const int4* __restrict__ cells, int* __restrict__ cnt)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nnzb) return;
+  if (b == nnzb) { cnt[b] = 0; return; }
+  const int i = brow[b], j = ja[b];
+  int n = 0;
+  if (j >= i)
+    for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; ++p) n += local_index(cells[v2c_idx[p]], j) >= 0 ? 1 : 0;
+  cnt[b] = n;
+}
+
+__global__ void pair_fill_kernel(int nnzb, const int* __restrict__ ja, const int* __restrict__ brow,
+                                 const int* __restrict__ v2c_ptr, const int* __restrict__ v2c_idx,
+                                 const int4* __restrict__ cells, const int* __restrict__ start,
+                                 int* __restrict__ cpslot, int2* __restrict__ pblk)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int i = brow[b], j = ja[b];
+  if (j < i) return;
+  int q = start[b];
+  for (int p = v2c_ptr[i]; p < v2c_ptr[i + 1]; ++p) {
+    const int c = v2c_idx[p];
+    const int4 cv = cells[c];
+    const int lj = local_index(cv, j);
+    if (lj < 0) continue;
+    cpslot[10 * (size_t)c + sym4(local_index(cv, i), lj)] = q++;
+  }
+  pblk[b] = make_int2(start[b], q - start[b]);
+}
+
+__global__ void pair_lower_kernel(int nnzb, const int* __restrict__ ja, const int* __restrict__ brow,
+                                  const int* __restrict__ tslot, int2* __restrict__ pblk)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb || ja[b] >= brow[b]) return;
+  const int t = tslot[b];
+  pblk[b] = t >= 0 ? pblk[t] : make_int2(0, 0);        // the pattern of a mesh is symmetric: t >= 0
+}
+
 } // namespace
+
+// cvslot / cpslot / pblk for the current layout of the fine level (pblk is indexed by PHYSICAL block)
+void build_assembly_tables(Handle& h)
+{
+  cudaStream_t s = h.stream;
+  const BsrT& A = h.hier.lv[0]->A;
+  const int4* cells = reinterpret_cast<const int4*>(h.cells.p);
+  const int nnzb = A.nnzb;
+  if (10 * (size_t)h.nc > 0x7fffffffull) throw Error(ERROR_INPUT_PAR, "mesh too large: more than 2^31 (cell, vertex pair) records");
+  h.cvslot.alloc(4 * (size_t)h.nc, s);
+  cell_vertex_slot_kernel<<<cdiv(h.nv, 128), 128, 0, s>>>(h.nv, h.v2c_ptr.p, h.v2c_idx.p, cells, h.cvslot.p); PNP_COUNT_LAUNCH();
+  h.cpslot.alloc(10 * (size_t)h.nc, s);
+  h.pblk.alloc(nnzb, s);
+  DevBuf<int> cnt, start; cnt.alloc((size_t)nnzb + 1, s); start.alloc((size_t)nnzb + 1, s);
+  pair_count_kernel<<<cdiv((size_t)nnzb + 1, 128), 128, 0, s>>>(nnzb, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p, cells, cnt.p); PNP_COUNT_LAUNCH();
+  exclusive_scan_int(cnt.p, start.p, (size_t)nnzb + 1, s);
+  pair_fill_kernel<<<cdiv(nnzb, 128), 128, 0, s>>>(nnzb, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p, cells, start.p, h.cpslot.p, h.pblk.p); PNP_COUNT_LAUNCH();
+  pair_lower_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, A.tslot.p, h.pblk.p); PNP_COUNT_LAUNCH();
+  int total = 0;
+  PNP_CUDA(cudaMemcpyAsync(&total, start.p + nnzb, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PNP_CUDA(cudaStreamSynchronize(s));
+  if ((size_t)total != 10 * (size_t)h.nc) throw Error(ERROR_DATA_STRUCTURE, "assembly tables: a vertex pair of a cell has no block in the pattern");
+  h.n_pair_records = (size_t)total;
+}
 
 void exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t s)
 {
@@ -214,6 +300,7 @@ void build_mesh_tables(Handle& h)
   edge_table_kernel<false><<<cdiv(nnzb, 128), 128, 0, s>>>(nnzb, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p, cells,
                                                           h.xyz.p, nullptr, h.omega.p);
   PNP_COUNT_LAUNCH();
+  build_assembly_tables(h);
   PNP_LAUNCH_CHECK();
 }
 
@@ -249,6 +336,7 @@ void relayout_fine_level(Handle& h)
   edge_table_kernel<false><<<cdiv(A.nnzb, 128), 128, 0, s>>>(A.nnzb, A.ja.p, A.brow.p, h.v2c_ptr.p, h.v2c_idx.p,
                                                             reinterpret_cast<const int4*>(h.cells.p), h.xyz.p, nullptr, h.omega.p);
   PNP_COUNT_LAUNCH();
+  build_assembly_tables(h);
   if (h.have_coef) compute_k00(h);
   h.hier.symbolic_valid = false;
 }
