@@ -732,6 +732,7 @@ void sweep_impl(const Level& L, const double* b, double* x, double* dl, bool rev
     const int c = reverse ? L.ngroups - 1 - cc : cc;
     const int cnt = L.color_ptr[c + 1] - L.color_ptr[c];
     if (cnt == 0) continue;
+    if (gs_stream_colour(L, L.color_ptr[c], L.color_ptr[c + 1], b, x, dl, mode, bs, s)) continue;   // gs_stream.cu
     const int4* rd = A.prd.p + L.color_ptr[c];
     const double* dinv = L.dinv.p + 9 * (size_t)L.color_ptr[c];      // sweep order: this colour's piece
     if (mode == 1) launch_rows<M_GS0, PNPB200_GS_CTAS, false>(cnt, cnt, rd, A.jpos.p, A, dinv, b, x, x, nullptr, s, bs, VS);
@@ -868,6 +869,7 @@ void color_and_layout(Level& L, const int* ja_nat, Workspace* ws, cudaStream_t s
   PNP_COUNT_LAUNCH();
   physical_descriptor_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.rowid.p, A.pos.p, A.rd.p, A.prd.p); PNP_COUNT_LAUNCH();
   vector_descriptor_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.vrowid.p, A.rd.p, A.vrd.p); PNP_COUNT_LAUNCH();
+  A.maxlen = max_row_length(A, s);
   int nodiag = 0;
   PNP_CUDA(cudaMemcpyAsync(&nodiag, rem, sizeof(int), cudaMemcpyDeviceToHost, s));
   PNP_CUDA(cudaStreamSynchronize(s));

@@ -1,0 +1,206 @@
+// pnp-b200 — streamed multicolour Gauss-Seidel colour launch for sm_100a: the matrix stream of a colour
+// (values, column indices, row descriptors, block inverses — all CONTIGUOUS in sweep order, 72 of every
+// ~100 bytes a row touches) is moved by the bulk-copy engine (cp.async.bulk = UBLKCP, completion on an
+// mbarrier) into a ring of shared-memory stages, GST_STAGES chunks ahead of the arithmetic; only the
+// gather of x (one 256-bit load per block) and the 24 bytes of b still go through the LSU path.
+// Why: the one-row-per-half-warp kernel of bsr_ops.cu is LATENCY bound in the colour launches (ncu at
+// 256^3: long-scoreboard stall 58 per issue, L1 data pipe 40 %, 4.9 of 6.5 TB/s): every row pays the
+// chain descriptor -> columns -> gather, and the 9 value loads of a lane sit behind the first link.
+// Here the first two links are shared-memory reads of data that landed microseconds ago.
+//   grid   : persistent, 3 CTAs per SM, CTA = 16 consumer half-warps (one row of the chunk each)
+//            + 1 producer warp (one lane issues the copies)
+//   chunk  : 16 consecutive rows of the colour = one contiguous piece of val / jpos / prd / dinv
+//   stage  : full barrier (producer arrives with expect_tx, the copies complete_tx), empty barrier
+//            (one arrival per consumer half-warp once its shared-memory reads are in registers)
+// Rows longer than GST_MAXLEN blocks do not fit a stage: levels that have one keep the plain kernel.
+#include "internal.hpp"
+
+namespace pnpb200 {
+
+namespace {
+
+constexpr int GST_ROWS = 16;
+constexpr int GST_MAXLEN = 16;
+constexpr int GST_STAGES = 3;
+constexpr int GST_THREADS = GST_ROWS * 16 + 32;
+
+struct alignas(128) GstStage {
+  double val[GST_ROWS * GST_MAXLEN * 9 + 2];      // + slack: a copy starts at the 16-byte boundary below its first byte
+  double dinv[GST_ROWS * 9 + 2];
+  int4 prd[GST_ROWS];
+  int ja[GST_ROWS * GST_MAXLEN + 4];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (16-byte aligned addresses, size a multiple of 16), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// MODE 0: x_row = D^{-1}(b - sum_{j != row} A_row,j x_j)          (one Gauss-Seidel colour)
+// MODE 2: the same, and delta_row = x_new - x_old
+template <int MODE>
+__global__ void __launch_bounds__(GST_THREADS, 3)
+gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __restrict__ pia, const int* __restrict__ jpos,
+                 const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
+                 double* x, double* __restrict__ dl, int bs)
+{
+  extern __shared__ __align__(128) unsigned char gst_smem[];
+  GstStage* stages = reinterpret_cast<GstStage*>(gst_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(gst_smem + GST_STAGES * sizeof(GstStage));
+  unsigned long long* empty = full + GST_STAGES;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < GST_STAGES; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], GST_ROWS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int nchunks = (p1 - p0 + GST_ROWS - 1) / GST_ROWS;
+
+  if (threadIdx.x >= GST_ROWS * 16) {
+    // ---- producer: one lane feeds the ring
+    if (threadIdx.x != GST_ROWS * 16) return;
+    int it = 0;
+    for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+      const int stage = it % GST_STAGES;
+      if (it >= GST_STAGES) mbar_wait(&empty[stage], ((it / GST_STAGES) - 1) & 1);      // the previous use of the slot is consumed
+      GstStage& st = stages[stage];
+      const int r0 = p0 + c * GST_ROWS, r1 = min(r0 + GST_ROWS, p1);
+      const int b0 = pia[r0], b1 = pia[r1];
+      // every copy starts at the 16-byte boundary at or below its first byte and is rounded up to 16 bytes
+      const unsigned lv = (b0 & 1) * 8u, lj = (b0 & 3) * 4u, ld = (r0 & 1) * 8u;
+      const unsigned nv = (72u * (unsigned)(b1 - b0) + lv + 15u) & ~15u;
+      const unsigned nj = (4u * (unsigned)(b1 - b0) + lj + 15u) & ~15u;
+      const unsigned nd = (72u * (unsigned)(r1 - r0) + ld + 15u) & ~15u;
+      const unsigned np = 16u * (unsigned)(r1 - r0);
+      mbar_expect_tx(&full[stage], nv + nj + nd + np);
+      bulk_g2s(st.val, reinterpret_cast<const unsigned char*>(val) + 72ull * (unsigned long long)b0 - lv, nv, &full[stage]);
+      bulk_g2s(st.ja, reinterpret_cast<const unsigned char*>(jpos) + 4ull * (unsigned long long)b0 - lj, nj, &full[stage]);
+      bulk_g2s(st.dinv, reinterpret_cast<const unsigned char*>(dinv) + 72ull * (unsigned long long)r0 - ld, nd, &full[stage]);
+      bulk_g2s(st.prd, prd + r0, np, &full[stage]);
+    }
+    return;
+  }
+
+  // ---- consumers: half-warp hw owns row hw of every chunk of this CTA
+  const int hw = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const int cc = lane >> 2, ii = lane & 3;
+  int it = 0;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int stage = it % GST_STAGES;
+    mbar_wait(&full[stage], (it / GST_STAGES) & 1);
+    const GstStage& st = stages[stage];
+    const int r0 = p0 + c * GST_ROWS;
+    const int rows = min(GST_ROWS, p1 - r0);
+    const int b0 = st.prd[0].x;
+    int row = -1, s = 0, len = 0, nl = 0;
+    if (hw < rows) { const int4 d = st.prd[hw]; s = d.x; len = d.y; nl = d.z; row = d.w; }
+    double bq = 0.0, dq = 0.0, xold = 0.0;
+    if (row >= 0 && cc < 3 && ii < 3) {
+      bq = b[(size_t)bs * (size_t)row + cc];
+      dq = st.dinv[(r0 & 1) + 9 * hw + 3 * ii + cc];
+    }
+    if (MODE == 2 && row >= 0 && lane < 3) xold = x[4 * (size_t)row + lane];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (lane < len && lane != nl) {                // rows of this path have <= 16 blocks: block k = lane
+      const int jc = st.ja[(b0 & 3) + (s - b0) + lane];
+      const bool lo = lane < nl;
+      const double* v = st.val + (b0 & 1) + 9 * (s - b0) + (lo ? lane : 8 * nl + lane);
+      const int sv = lo ? nl : len - nl;
+      double x0, x1, x2;
+      load_row3<4>(x, jc, x0, x1, x2);
+      a0 = v[0] * x0 + v[sv] * x1 + v[2 * sv] * x2;
+      a1 = v[3 * sv] * x0 + v[4 * sv] * x1 + v[5 * sv] * x2;
+      a2 = v[6 * sv] * x0 + v[7 * sv] * x1 + v[8 * sv] * x2;
+    }
+    // the shared-memory reads of this half-warp are done (their results feed a0..a2, dq): hand the slot back
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    const double a = half_sum3(a0, a1, a2, lane);
+    double part = dq * (bq - a);                   // lanes outside (c < 3, i < 3): dq = 0
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    part += __shfl_xor_sync(0xffffffffu, part, 8);
+    if (row >= 0 && lane < 4) {                    // lane 3: part == 0, the pad entry of the padded vectors
+      const size_t o = 4 * (size_t)row + lane;
+      if (MODE == 2) dl[o] = lane < 3 ? part - xold : 0.0;
+      x[o] = part;
+    }
+  }
+}
+
+__global__ void max_rowlen_kernel(int n, const int* __restrict__ ia, int* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = i < n ? ia[i + 1] - ia[i] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+constexpr size_t GST_SMEM = GST_STAGES * sizeof(GstStage) + 2 * GST_STAGES * sizeof(unsigned long long);
+
+} // namespace
+
+int max_row_length(const BsrT& A, cudaStream_t s)
+{
+  DevBuf<int> m; m.alloc(1, s); m.zero();
+  max_rowlen_kernel<<<cdiv(A.n, 256), 256, 0, s>>>(A.n, A.ia.p, m.p); PNP_COUNT_LAUNCH();
+  int h = 0; m.download(&h, 1);
+  return h;
+}
+
+// One colour launch [p0, p1) (matrix order) of a sweep over a level whose rows have <= 16 blocks and whose
+// vectors are padded (VS == 4). mode 0: plain, 2: with delta. Returns false if the level does not qualify.
+bool gs_stream_colour(const Level& L, int p0, int p1, const double* b, double* x, double* dl, int mode, int bs, cudaStream_t s)
+{
+  // read at every call so that a test can switch the path inside one process: PNPB200_GS_STREAM=0 keeps the
+  // plain kernel, PNPB200_GS_STREAM_MIN = smallest colour group (rows) that is streamed (default 4096:
+  // below that a launch is latency, not bandwidth)
+  const char* e_on = getenv("PNPB200_GS_STREAM"); const char* e_min = getenv("PNPB200_GS_STREAM_MIN");
+  const int on = e_on ? atoi(e_on) : 1, min_rows = e_min ? atoi(e_min) : 4096;
+  const BsrT& A = L.A;
+  if (!on || VS != 4 || A.maxlen <= 0 || A.maxlen > GST_MAXLEN || (mode != 0 && mode != 2) || p1 - p0 < min_rows) return false;
+  static bool configured[64] = {false};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    PNP_CUDA(cudaFuncSetAttribute(gs_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GST_SMEM));
+    PNP_CUDA(cudaFuncSetAttribute(gs_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GST_SMEM));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  static int sms = 0;
+  if (sms == 0) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int nchunks = (p1 - p0 + GST_ROWS - 1) / GST_ROWS;
+  const int grid = nchunks < 3 * sms ? nchunks : 3 * sms;
+  if (mode == 2) gs_stream_kernel<2><<<grid, GST_THREADS, GST_SMEM, s>>>(p0, p1, A.prd.p, A.pia.p, A.jpos.p, A.val.p, L.dinv.p, b, x, dl, bs);
+  else gs_stream_kernel<0><<<grid, GST_THREADS, GST_SMEM, s>>>(p0, p1, A.prd.p, A.pia.p, A.jpos.p, A.val.p, L.dinv.p, b, x, dl, bs);
+  PNP_COUNT_LAUNCH();
+  return true;
+}
+
+} // namespace pnpb200

@@ -20,6 +20,7 @@ namespace pnpb200 {
 struct BsrT {
   int n = 0;        // block rows
   int nnzb = 0;     // blocks
+  int maxlen = 0;   // longest row (blocks), set by color_and_layout
   DevBuf<int> ia;       // natural CSR offsets (row lengths, FASP import/export)
   DevBuf<int> rs;       // physical start of each row's blocks: rows are STORED colour by colour, so that a
                         // Gauss-Seidel colour sweep streams one contiguous piece of ja/val
@@ -258,6 +259,9 @@ void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x,
 // backward sweep that also returns delta = x_new - x_old, and y = A x_new = b + L delta after it
 void mcgs_sweep_back_delta(const Level& L, const double* b, double* x, double* delta, cudaStream_t s, int bs = VS);
 void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s, int bs = VS, int ys = VS);
+// ---- gs_stream.cu: bulk-copy (TMA) streamed colour launch for levels with short rows; false = not applicable
+int max_row_length(const BsrT& A, cudaStream_t s);
+bool gs_stream_colour(const Level& L, int p0, int p1, const double* b, double* x, double* dl, int mode, int bs, cudaStream_t s);
 // ---- vecops.cu
 void vec_set(double* x, double v, size_t n, cudaStream_t s);
 void vec_copy(double* dst, const double* src, size_t n, cudaStream_t s);

@@ -308,3 +308,29 @@ def test_diode_damped_newton_matches_oracle(oracle, pkg, gpu_lib, voltage):
     for k in range(8):
         assert hist[k][4] == hist_ref[k][4], (k, hist[k], hist_ref[k])
         assert abs(hist[k][2] - hist_ref[k][2]) <= 1e-3 * hist_ref[k][2], (k, hist[k], hist_ref[k])
+
+
+def test_streamed_colour_launch_is_the_same_arithmetic(oracle, pkg, system):
+    """gs_stream.cu: the bulk-copy (TMA) streamed Gauss-Seidel colour launch must reproduce the plain
+    one-row-per-half-warp kernel bit for bit (same products, same reduction tree): cycle output and
+    Krylov solution with the streamed path forced on for every colour group vs switched off."""
+    import os
+    P, g, IA, JA, val, b = system
+    it, amg = pkg.default_params()
+    rr = np.random.default_rng(12).uniform(-1, 1, P.N)
+    out = {}
+    old = {k: os.environ.get(k) for k in ("PNPB200_GS_STREAM", "PNPB200_GS_STREAM_MIN")}
+    try:
+        for on in (1, 0):
+            os.environ["PNPB200_GS_STREAM"] = str(on); os.environ["PNPB200_GS_STREAM_MIN"] = "1"
+            its = g.solve(it, amg)
+            out[on] = (its, g.get_update(), g.apply_vcycle(rr))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert out[1][0] > 0 and out[1][0] == out[0][0]
+    assert np.array_equal(out[1][2], out[0][2]), np.abs(out[1][2] - out[0][2]).max()
+    assert np.array_equal(out[1][1], out[0][1])
