@@ -628,11 +628,13 @@ __global__ void iota_kernel(int n, int* __restrict__ a)
 
 void bsrt_spmv(const BsrT& A, const double* x, double* y, cudaStream_t s, int ys)
 {
+  if (gs_stream_pass(A, M_SPMV, A.n, nullptr, x, y, VS, ys, s)) return;       // gs_stream.cu
   launch_rows<M_SPMV, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, nullptr, x, y, nullptr, s, VS, ys);
 }
 
 void bsrt_residual(const BsrT& A, const double* b, const double* x, double* r, cudaStream_t s, int bs, int ys)
 {
+  if (gs_stream_pass(A, M_RES, A.n, b, x, r, bs, ys, s)) return;
   launch_rows<M_RES, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, b, x, r, nullptr, s, bs, ys);
 }
 
@@ -649,13 +651,20 @@ void bsrt_residual_rowid(const BsrT& A, const double* b, const double* x, double
 void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x, double* r, cudaStream_t s, int bs)
 {
   const BsrT& A = L.A;
-  launch_rows<M_RESU, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.vrd.p, A.jpos.p, A, nullptr, b, x, r, nullptr, s, bs, VS);
+  const int own = owned_rows(L);
+  if (gs_stream_pass(A, M_RESU, own, b, x, r, bs, VS, s)) {
+    // the swept (owned) rows are the first `own` rows in matrix order as well; ghost rows of a multi-GPU level: full rows
+    if (own < A.n) launch_rows<M_RESU, PNPB200_GS_CTAS, false>(A.n - own, own, A.prd.p + own, A.jpos.p, A, nullptr, b, x, r, nullptr, s, bs, VS);
+    return;
+  }
+  launch_rows<M_RESU, PNPB200_NAT_CTAS, true>(A.n, own, A.vrd.p, A.jpos.p, A, nullptr, b, x, r, nullptr, s, bs, VS);
 }
 
 void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s, int bs, int ys)
 {
   const BsrT& A = L.A;
   if (owned_rows(L) != A.n) launch_rows<M_LDELTAG, PNPB200_NAT_CTAS, true>(A.n, owned_rows(L), A.vrd.p, A.jpos.p, A, nullptr, b, delta, y, nullptr, s, bs, ys);
+  else if (gs_stream_pass(A, M_LDELTA, A.n, b, delta, y, bs, ys, s)) return;
   else launch_rows<M_LDELTA, PNPB200_NAT_CTAS, true>(A.n, A.n, A.vrd.p, A.jpos.p, A, nullptr, b, delta, y, nullptr, s, bs, ys);
 }
 

@@ -23,9 +23,10 @@ constexpr int GST_ROWS = 16;
 constexpr int GST_MAXLEN = 16;
 constexpr int GST_STAGES = 3;
 constexpr int GST_THREADS = GST_ROWS * 16 + 32;
+constexpr int GST_ROWSLOT = GST_MAXLEN * 9 + 2;   // doubles per row slot of a stage (a multiple of 16 bytes)
 
 struct alignas(128) GstStage {
-  double val[GST_ROWS * GST_MAXLEN * 9 + 2];      // + slack: a copy starts at the 16-byte boundary below its first byte
+  double val[GST_ROWS * GST_ROWSLOT];             // + slack: a copy starts at the 16-byte boundary below its first byte
   double dinv[GST_ROWS * 9 + 2];
   int4 prd[GST_ROWS];
   int ja[GST_ROWS * GST_MAXLEN + 4];
@@ -63,14 +64,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// MODE 0: x_row = D^{-1}(b - sum_{j != row} A_row,j x_j)          (one Gauss-Seidel colour)
-// MODE 2: the same, and delta_row = x_new - x_old
+// The passes of bsr_ops.cu (same modes, same arithmetic, same reduction tree) over the rows [p0, p1) in
+// MATRIX order. Which part of a row a mode reads decides how the producer feeds the ring:
+//   full rows  (S_SPMV, S_RES, S_GS, S_GSD): the chunk's rows are one contiguous piece of val: ONE copy;
+//   lower part (S_GS0, S_LDELTA) / upper part (S_RESU): the part of row r is contiguous inside the row
+//              ([L | D | U] storage): producer lane r copies the part of row r into row slot r, so that
+//              half a matrix pass really moves half the bytes. The lanes fetch the descriptors of the
+//              NEXT chunk of their CTA one chunk ahead, so the producer never waits for them.
+enum { S_SPMV = 0, S_RES = 1, S_GS = 2, S_GS0 = 3, S_RESU = 4, S_GSD = 5, S_LDELTA = 6 };
+
 template <int MODE>
 __global__ void __launch_bounds__(GST_THREADS, 3)
 gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __restrict__ pia, const int* __restrict__ jpos,
                  const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
-                 double* x, double* __restrict__ dl, int bs)
+                 const double* x, double* y, double* __restrict__ dl, int bs, int ys)
 {
+  constexpr bool LOWER = MODE == S_GS0 || MODE == S_LDELTA, UPPER = MODE == S_RESU, PART = LOWER || UPPER;
+  constexpr bool SMOOTH = MODE == S_GS || MODE == S_GS0 || MODE == S_GSD;
   extern __shared__ __align__(128) unsigned char gst_smem[];
   GstStage* stages = reinterpret_cast<GstStage*>(gst_smem);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(gst_smem + GST_STAGES * sizeof(GstStage));
@@ -84,26 +94,60 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
   const int nchunks = (p1 - p0 + GST_ROWS - 1) / GST_ROWS;
 
   if (threadIdx.x >= GST_ROWS * 16) {
-    // ---- producer: one lane feeds the ring
-    if (threadIdx.x != GST_ROWS * 16) return;
+    // ---- producer warp
+    const int pl = threadIdx.x - GST_ROWS * 16;                 // lane
+    if (!PART && pl != 0) return;
+    int4 dn = make_int4(0, 0, 0, -1);
+    if (PART && pl < GST_ROWS) { const int r = p0 + blockIdx.x * GST_ROWS + pl; if (r < p1) dn = prd[r]; }
     int it = 0;
     for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
       const int stage = it % GST_STAGES;
+      const int4 d = dn;
+      if (PART) {                                               // descriptors of the CTA's next chunk, one chunk ahead
+        dn = make_int4(0, 0, 0, -1);
+        const int r = p0 + (c + (int)gridDim.x) * GST_ROWS + pl;
+        if (pl < GST_ROWS && c + (int)gridDim.x < nchunks && r < p1) dn = prd[r];
+      }
       if (it >= GST_STAGES) mbar_wait(&empty[stage], ((it / GST_STAGES) - 1) & 1);      // the previous use of the slot is consumed
       GstStage& st = stages[stage];
       const int r0 = p0 + c * GST_ROWS, r1 = min(r0 + GST_ROWS, p1);
-      const int b0 = pia[r0], b1 = pia[r1];
-      // every copy starts at the 16-byte boundary at or below its first byte and is rounded up to 16 bytes
-      const unsigned lv = (b0 & 1) * 8u, lj = (b0 & 3) * 4u, ld = (r0 & 1) * 8u;
-      const unsigned nv = (72u * (unsigned)(b1 - b0) + lv + 15u) & ~15u;
-      const unsigned nj = (4u * (unsigned)(b1 - b0) + lj + 15u) & ~15u;
-      const unsigned nd = (72u * (unsigned)(r1 - r0) + ld + 15u) & ~15u;
       const unsigned np = 16u * (unsigned)(r1 - r0);
-      mbar_expect_tx(&full[stage], nv + nj + nd + np);
-      bulk_g2s(st.val, reinterpret_cast<const unsigned char*>(val) + 72ull * (unsigned long long)b0 - lv, nv, &full[stage]);
-      bulk_g2s(st.ja, reinterpret_cast<const unsigned char*>(jpos) + 4ull * (unsigned long long)b0 - lj, nj, &full[stage]);
-      bulk_g2s(st.dinv, reinterpret_cast<const unsigned char*>(dinv) + 72ull * (unsigned long long)r0 - ld, nd, &full[stage]);
-      bulk_g2s(st.prd, prd + r0, np, &full[stage]);
+      const unsigned ld = (r0 & 1) * 8u;
+      const unsigned nd = SMOOTH ? (72u * (unsigned)(r1 - r0) + ld + 15u) & ~15u : 0u;
+      if (!PART) {
+        const int b0 = pia[r0], b1 = pia[r1];
+        // every copy starts at the 16-byte boundary at or below its first byte and is rounded up to 16 bytes
+        const unsigned lv = (b0 & 1) * 8u, lj = (b0 & 3) * 4u;
+        const unsigned nv = (72u * (unsigned)(b1 - b0) + lv + 15u) & ~15u;
+        const unsigned nj = (4u * (unsigned)(b1 - b0) + lj + 15u) & ~15u;
+        mbar_expect_tx(&full[stage], nv + nj + nd + np);
+        bulk_g2s(st.val, reinterpret_cast<const unsigned char*>(val) + 72ull * (unsigned long long)b0 - lv, nv, &full[stage]);
+        bulk_g2s(st.ja, reinterpret_cast<const unsigned char*>(jpos) + 4ull * (unsigned long long)b0 - lj, nj, &full[stage]);
+        if (SMOOTH) bulk_g2s(st.dinv, reinterpret_cast<const unsigned char*>(dinv) + 72ull * (unsigned long long)r0 - ld, nd, &full[stage]);
+        bulk_g2s(st.prd, prd + r0, np, &full[stage]);
+      } else {
+        // my row's part: lower = blocks [s, s + nl), upper = the D + U part [s + nl, s + len)
+        const int blk = LOWER ? d.x : d.x + d.z, nblk = d.w < 0 ? 0 : (LOWER ? d.z : d.y - d.z);
+        const unsigned lv = (blk & 1) * 8u;
+        const unsigned nv = nblk > 0 ? (72u * (unsigned)nblk + lv + 15u) & ~15u : 0u;
+        unsigned tot = nv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        // the chunk's column indices are one contiguous piece (first block of its first row .. end of its last row)
+        const int b0 = __shfl_sync(0xffffffffu, d.x, 0);
+        const int last = r1 - r0 - 1;
+        const int b1 = __shfl_sync(0xffffffffu, d.x + d.y, last);
+        const unsigned lj = (b0 & 3) * 4u;
+        const unsigned nj = (4u * (unsigned)(b1 - b0) + lj + 15u) & ~15u;
+        if (pl == 0) mbar_expect_tx(&full[stage], tot + nj + nd + np);
+        __syncwarp();
+        if (nv > 0) bulk_g2s(st.val + pl * GST_ROWSLOT, reinterpret_cast<const unsigned char*>(val) + 72ull * (unsigned long long)blk - lv, nv, &full[stage]);
+        if (pl == 0) {
+          bulk_g2s(st.ja, reinterpret_cast<const unsigned char*>(jpos) + 4ull * (unsigned long long)b0 - lj, nj, &full[stage]);
+          if (SMOOTH) bulk_g2s(st.dinv, reinterpret_cast<const unsigned char*>(dinv) + 72ull * (unsigned long long)r0 - ld, nd, &full[stage]);
+          bulk_g2s(st.prd, prd + r0, np, &full[stage]);
+        }
+      }
     }
     return;
   }
@@ -122,17 +166,23 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
     int row = -1, s = 0, len = 0, nl = 0;
     if (hw < rows) { const int4 d = st.prd[hw]; s = d.x; len = d.y; nl = d.z; row = d.w; }
     double bq = 0.0, dq = 0.0, xold = 0.0;
-    if (row >= 0 && cc < 3 && ii < 3) {
-      bq = b[(size_t)bs * (size_t)row + cc];
-      dq = st.dinv[(r0 & 1) + 9 * hw + 3 * ii + cc];
+    if (row >= 0 && cc < 3) {
+      if (SMOOTH) { if (ii < 3) { bq = b[(size_t)bs * (size_t)row + cc]; dq = st.dinv[(r0 & 1) + 9 * hw + 3 * ii + cc]; } }
+      else if (MODE == S_RES || MODE == S_LDELTA) { if (ii == 0) bq = b[(size_t)bs * (size_t)row + cc]; }
     }
-    if (MODE == 2 && row >= 0 && lane < 3) xold = x[4 * (size_t)row + lane];
+    if (MODE == S_GSD && row >= 0 && lane < 3) xold = x[4 * (size_t)row + lane];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    if (lane < len && lane != nl) {                // rows of this path have <= 16 blocks: block k = lane
+    // rows of this path have <= 16 blocks: block k = lane
+    const bool mine = LOWER ? lane < nl : UPPER ? (lane > nl && lane < len) : (lane < len && (!(MODE == S_GS || MODE == S_GSD) || lane != nl));
+    if (mine) {
       const int jc = st.ja[(b0 & 3) + (s - b0) + lane];
-      const bool lo = lane < nl;
-      const double* v = st.val + (b0 & 1) + 9 * (s - b0) + (lo ? lane : 8 * nl + lane);
-      const int sv = lo ? nl : len - nl;
+      const double* v; int sv;
+      if (!PART) {
+        const bool lo = lane < nl;
+        v = st.val + (b0 & 1) + 9 * (s - b0) + (lo ? lane : 8 * nl + lane);
+        sv = lo ? nl : len - nl;
+      } else if (LOWER) { v = st.val + hw * GST_ROWSLOT + (s & 1) + lane; sv = nl; }
+      else { v = st.val + hw * GST_ROWSLOT + ((s + nl) & 1) + (lane - nl); sv = len - nl; }
       double x0, x1, x2;
       load_row3<4>(x, jc, x0, x1, x2);
       a0 = v[0] * x0 + v[sv] * x1 + v[2 * sv] * x2;
@@ -143,13 +193,23 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
     const double a = half_sum3(a0, a1, a2, lane);
-    double part = dq * (bq - a);                   // lanes outside (c < 3, i < 3): dq = 0
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    part += __shfl_xor_sync(0xffffffffu, part, 8);
-    if (row >= 0 && lane < 4) {                    // lane 3: part == 0, the pad entry of the padded vectors
-      const size_t o = 4 * (size_t)row + lane;
-      if (MODE == 2) dl[o] = lane < 3 ? part - xold : 0.0;
-      x[o] = part;
+    if (!SMOOTH) {
+      if (row >= 0 && ii == 0 && cc < ys) {        // cc == 3 (padded y): a == 0 and bq == 0, the pad entry stays zero
+        const size_t o = (size_t)ys * (size_t)row + cc;
+        if (MODE == S_SPMV) y[o] = a;
+        else if (MODE == S_RES) y[o] = bq - a;
+        else if (MODE == S_RESU) y[o] = -a;
+        else y[o] = bq + a;
+      }
+    } else {
+      double part = dq * (bq - a);                 // lanes outside (c < 3, i < 3): dq = 0
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      part += __shfl_xor_sync(0xffffffffu, part, 8);
+      if (row >= 0 && lane < 4) {                  // lane 3: part == 0, the pad entry of the padded vectors
+        const size_t o = 4 * (size_t)row + lane;
+        if (MODE == S_GSD) dl[o] = lane < 3 ? part - xold : 0.0;
+        y[o] = part;
+      }
     }
   }
 }
@@ -175,31 +235,63 @@ int max_row_length(const BsrT& A, cudaStream_t s)
   return h;
 }
 
-// One colour launch [p0, p1) (matrix order) of a sweep over a level whose rows have <= 16 blocks and whose
-// vectors are padded (VS == 4). mode 0: plain, 2: with delta. Returns false if the level does not qualify.
-bool gs_stream_colour(const Level& L, int p0, int p1, const double* b, double* x, double* dl, int mode, int bs, cudaStream_t s)
+template <int MODE>
+void launch_stream(const BsrT& A, const double* dinv, int p0, int p1, const double* b, const double* x, double* y, double* dl, int bs, int ys, cudaStream_t s)
 {
-  // read at every call so that a test can switch the path inside one process: PNPB200_GS_STREAM=0 keeps the
-  // plain kernel, PNPB200_GS_STREAM_MIN = smallest colour group (rows) that is streamed (default 4096:
-  // below that a launch is latency, not bandwidth)
-  const char* e_on = getenv("PNPB200_GS_STREAM"); const char* e_min = getenv("PNPB200_GS_STREAM_MIN");
-  const int on = e_on ? atoi(e_on) : 1, min_rows = e_min ? atoi(e_min) : 4096;
-  const BsrT& A = L.A;
-  if (!on || VS != 4 || A.maxlen <= 0 || A.maxlen > GST_MAXLEN || (mode != 0 && mode != 2) || p1 - p0 < min_rows) return false;
   static bool configured[64] = {false};
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    PNP_CUDA(cudaFuncSetAttribute(gs_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GST_SMEM));
-    PNP_CUDA(cudaFuncSetAttribute(gs_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GST_SMEM));
+    PNP_CUDA(cudaFuncSetAttribute(gs_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GST_SMEM));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   static int sms = 0;
   if (sms == 0) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const int nchunks = (p1 - p0 + GST_ROWS - 1) / GST_ROWS;
   const int grid = nchunks < 3 * sms ? nchunks : 3 * sms;
-  if (mode == 2) gs_stream_kernel<2><<<grid, GST_THREADS, GST_SMEM, s>>>(p0, p1, A.prd.p, A.pia.p, A.jpos.p, A.val.p, L.dinv.p, b, x, dl, bs);
-  else gs_stream_kernel<0><<<grid, GST_THREADS, GST_SMEM, s>>>(p0, p1, A.prd.p, A.pia.p, A.jpos.p, A.val.p, L.dinv.p, b, x, dl, bs);
+  gs_stream_kernel<MODE><<<grid, GST_THREADS, GST_SMEM, s>>>(p0, p1, A.prd.p, A.pia.p, A.jpos.p, A.val.p, dinv, b, x, y, dl, bs, ys);
   PNP_COUNT_LAUNCH();
+}
+
+// Does the level qualify for the streamed kernels? Read at every call so that a test can switch the path
+// inside one process: PNPB200_GS_STREAM=0 keeps the plain kernels, PNPB200_GS_STREAM_MIN = smallest row
+// range that is streamed (default 4096: below that a launch is latency, not bandwidth).
+bool stream_ok(const BsrT& A, int nrows)
+{
+  const char* e_on = getenv("PNPB200_GS_STREAM"); const char* e_min = getenv("PNPB200_GS_STREAM_MIN");
+  const int on = e_on ? atoi(e_on) : 1, min_rows = e_min ? atoi(e_min) : 4096;
+  return on && VS == 4 && A.maxlen > 0 && A.maxlen <= GST_MAXLEN && nrows >= min_rows;
+}
+
+// One colour launch [p0, p1) (matrix order) of a sweep. mode 0: plain, 1: forward from a zero initial guess
+// (lower parts only), 2: with delta. Returns false if the level does not qualify.
+bool gs_stream_colour(const Level& L, int p0, int p1, const double* b, double* x, double* dl, int mode, int bs, cudaStream_t s)
+{
+  if (!stream_ok(L.A, p1 - p0)) return false;
+  if (mode == 2) launch_stream<S_GSD>(L.A, L.dinv.p, p0, p1, b, x, x, dl, bs, VS, s);
+  else if (mode == 1) launch_stream<S_GS0>(L.A, L.dinv.p, p0, p1, b, x, x, nullptr, bs, VS, s);
+  else launch_stream<S_GS>(L.A, L.dinv.p, p0, p1, b, x, x, nullptr, bs, VS, s);
+  return true;
+}
+
+// Natural passes over the SWEPT rows of a level (matrix positions [0, p1): every row but the ghost rows of a
+// multi-GPU level), which: 0 y = A x, 1 y = b - A x, 4 y = -U x (residual right after a forward sweep
+// from zero), 6 y = b + L x. The caller runs the plain kernel on the rows behind p1.
+bool gs_stream_pass(const BsrT& A, int which, int p1, const double* b, const double* x, double* y, int bs, int ys, cudaStream_t s)
+{
+  if (!stream_ok(A, p1)) return false;
+  // The half-row passes in natural order stay on the software-pipelined plain kernel by default: their
+  // producer issues one ~500-byte copy per row, and at that size the copy engine is slower than the LSU
+  // path (measured at 256^3: r = -U x 2.69 vs 2.30 ms, y = b + L x 2.62 vs 2.26 ms), while the forward
+  // sweep from zero gains (2.81 vs 3.09 ms: its colour launches were latency bound). PNPB200_GS_STREAM_PART=1
+  // streams them as well.
+  if (which == 4 || which == 6) { const char* e = getenv("PNPB200_GS_STREAM_PART"); if (!e || !atoi(e)) return false; }
+  switch (which) {
+    case 0: launch_stream<S_SPMV>(A, nullptr, 0, p1, b, x, y, nullptr, bs, ys, s); break;
+    case 1: launch_stream<S_RES>(A, nullptr, 0, p1, b, x, y, nullptr, bs, ys, s); break;
+    case 4: launch_stream<S_RESU>(A, nullptr, 0, p1, b, x, y, nullptr, bs, ys, s); break;
+    case 6: launch_stream<S_LDELTA>(A, nullptr, 0, p1, b, x, y, nullptr, bs, ys, s); break;
+    default: return false;
+  }
   return true;
 }
 

@@ -262,6 +262,7 @@ void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta
 // ---- gs_stream.cu: bulk-copy (TMA) streamed colour launch for levels with short rows; false = not applicable
 int max_row_length(const BsrT& A, cudaStream_t s);
 bool gs_stream_colour(const Level& L, int p0, int p1, const double* b, double* x, double* dl, int mode, int bs, cudaStream_t s);
+bool gs_stream_pass(const BsrT& A, int which, int p1, const double* b, const double* x, double* y, int bs, int ys, cudaStream_t s);
 // ---- vecops.cu
 void vec_set(double* x, double v, size_t n, cudaStream_t s);
 void vec_copy(double* dst, const double* src, size_t n, cudaStream_t s);
