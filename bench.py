@@ -187,6 +187,8 @@ def multi_gpu_parity(pkg, problems, partition_fn, dist, rank, world, dev, it, am
     uid = [pkg.capi.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     g.comm_init(uid[0], rank, world); g.set_partition(P)
+    if "color" in P:
+        g.set_coloring(P["color"], 4)
     f = problems.exact_solution_fields(P["xyz"][0::3])
     g.set_coefficients(f["eps"], f["fixed"], f["diff"], f["val"], f["reac"])
     g.set_dirichlet((3 * P["bc_vertices"][:, None] + np.arange(3)).ravel().astype(np.int32))
@@ -262,6 +264,10 @@ def main():
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: 1 warm-up + 1 timed step, no e2e / cpu_baseline / probe legs")
     ap.add_argument("--maxit", type=int, default=int(os.environ.get("PNPB200_BENCH_MAXIT", "100")))
+    ap.add_argument("--scaling", default=os.environ.get("PNPB200_BENCH_SCALING", "weak"), choices=["weak", "strong"],
+                    help="N > 1: weak = n^3 vertices per GPU (the global box grows with N), strong = the n^3 box split over the N GPUs")
+    ap.add_argument("--partition", default=os.environ.get("PNPB200_BENCH_PARTITION", "slabs"), choices=["slabs", "bricks"],
+                    help="N > 1: z-slabs (weak: box n x n x nN) or px x py x pz bricks (weak: box n px x n py x n pz), csrc/partition.cpp")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -321,29 +327,45 @@ def main():
     cyc = {"V": 1, "W": 2, "A": 3, "NA": 4}[args.cycle]
     it, amg = pkg.default_params(maxit=args.maxit, cycle_type=cyc)
     parity = None
+    partition = import_module("modular_pnp_b200.partition")
+    grid_of = (lambda nx, ny, nz: (1, 1, world)) if args.partition == "slabs" else (lambda nx, ny, nz: partition.brick_grid(world, nx, ny, nz))
+
+    def part_fn(nx, ny, nz, lx, ly, lz, r, w):
+        return partition.box_brick_partition(nx, ny, nz, lx, ly, lz, r, w, grid=grid_of(nx, ny, nz))
     if world > 1 and not args.profile:
-        partition = import_module("modular_pnp_b200.partition")
-        parity = multi_gpu_parity(pkg, problems, partition.box_slab_partition, dist, rank, world, dev, it, amg)
+        parity = multi_gpu_parity(pkg, problems, part_fn, dist, rank, world, dev, it, amg)
     if world == 1:
         g = pkg.PNP(box=(n, n, n, 2.0, 2.0, 2.0), device=dev)
         pr = problems.exact_solution_problem(n, n, n, 2.0, 2.0, 2.0)
         g.set_coefficients(pr["eps"], pr["fixed"], pr["diff"], pr["val"], pr["reac"])
         g.set_dirichlet(pr["bc_dofs"])
         n_local_dofs = 3 * nv
+        global_dofs, part_desc = 3 * nv, "1 GPU"
     else:
-        # weak scaling: the global mesh is n x n x (n*world) on [-1,1]^2 x [-world, world], block rows
-        # (vertices) partitioned into z-slabs, one per GPU; ghost planes by halo exchange over NCCL
-        partition = import_module("modular_pnp_b200.partition")
-        part = partition.box_slab_partition(n, n, n * world, 2.0, 2.0, 2.0 * world, rank, world)
+        # block rows (vertices) partitioned by the library's C++ partitioner (csrc/partition.cpp), one part per GPU;
+        # ghost vertices by halo exchange over NCCL. weak: every GPU owns ~n^3 vertices (slabs: the box is
+        # n x n x nN on [-1,1]^2 x [-N,N]; bricks: n px x n py x n pz); strong: the n^3 box of [-1,1]^3 is split.
+        if args.scaling == "strong":
+            gn, gl = (n, n, n), (2.0, 2.0, 2.0)
+        elif args.partition == "slabs":
+            gn, gl = (n, n, n * world), (2.0, 2.0, 2.0 * world)
+        else:
+            px, py, pz = partition.brick_grid(world, n, n, n)
+            gn, gl = (n * px, n * py, n * pz), (2.0 * px, 2.0 * py, 2.0 * pz)
+        part = part_fn(gn[0], gn[1], gn[2], gl[0], gl[1], gl[2], rank, world)
         g = pkg.PNP(part["xyz"], part["cells"], device=dev)
         uid = [pkg.capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         g.comm_init(uid[0], rank, world)
         g.set_partition(part)
+        g.set_coloring(part["color"], 4)       # (i + j + k) mod 4 of the global lattice: 4 colour launches per sweep, like one GPU
         pr = problems.exact_solution_fields(part["xyz"][0::3])
         g.set_coefficients(pr["eps"], pr["fixed"], pr["diff"], pr["val"], pr["reac"])
         g.set_dirichlet((3 * part["bc_vertices"][:, None] + np.arange(3)[None, :]).ravel().astype(np.int32))
         n_local_dofs = 3 * part["n_loc"]
+        global_dofs = 3 * (gn[0] + 1) * (gn[1] + 1) * (gn[2] + 1)
+        part_desc = "%d GPUs, %s of a %dx%dx%d box (%.1f M dof, %s scaling), grid %s" % (
+            world, args.partition, gn[0], gn[1], gn[2], global_dofs / 1e6, args.scaling, part["grid"])
         del part
     uu0_host = torch.from_numpy(pr["uu0"]).pin_memory()
     uu_out_host = torch.empty_like(uu0_host).pin_memory()
@@ -464,11 +486,14 @@ def main():
     if rank == 0:
         # weak scaling: one unit of work = a Newton step on one n^3-box-equivalent (the N-GPU job
         # steps an N-times larger mesh, so the whole-job aggregate is N * global steps/s)
-        value = world * K / (ms / 1e3)
-        e2e_v = world * K / (ms_e2e / 1e3)
+        # strong scaling: the job steps the same n^3 box, value = literal steps/s
+        units = world if args.scaling == "weak" else 1
+        value = units * K / (ms / 1e3)
+        e2e_v = units * K / (ms_e2e / 1e3)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=("1 GPU" if world == 1 else "%d GPUs: block rows in z-slabs of a %dx%dx%d box (%.1f M dof), NCCL halo exchange at every AMG level + fp64 allreduce, aggregates local to a rank, replicated dense coarsest solve" % (world, n, n, n * world, 3 * (n + 1) * (n + 1) * (n * world + 1) / 1e6))),
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=part_desc + ("" if world == 1 else ": NCCL halo exchange at every AMG level + fp64 allreduce, aggregates local to a rank, replicated dense coarsest solve"),
+                              global_dofs=global_dofs, global_steps_per_s=K / (ms / 1e3)),
                "krylov_its_per_step": its, "krylov_status_ok": bool(kits > 0), "amg_cycle_type": args.cycle,
                "l2_residual_after_step": None if last is None else last[1],
                "relative_residual_after_step": None if last is None else last[1] / l2_0,

@@ -197,9 +197,8 @@ INT fasp_solver_dbsr_krylov_amg(dBSRmat *A, dvector *b, dvector *x, itsolver_par
                                 AMG_param *amgparam);
 /* tests/eafe_tests/test_eafe.cpp:170 — unpreconditioned Krylov (FGMRES) on a CSR matrix, GPU */
 INT fasp_solver_dcsr_krylov(dCSRmat *A, dvector *b, dvector *x, itsolver_param *itparam);
-/* benchmarks/pnp_diode/linear_pnp.cpp:103 — "next" tier: currently routed to the
- * AMG-preconditioned solver with default AMG parameters (the diode's own test solver uses AMG,
- * benchmarks/pnp_diode/linear_pnp.cpp:162); documented deviation, see DESIGN.md */
+/* benchmarks/pnp_diode/linear_pnp.cpp:103-109 — block ILU(k)-preconditioned FGMRES on the GPU, k = ILU_lfil
+ * (pnp_diode/bsr.dat:34-38: ILU_type 2 = ILUk, lfil 2); same return convention. csrc/ilu.cu */
 INT fasp_solver_dbsr_krylov_ilu(dBSRmat *A, dvector *b, dvector *x, itsolver_param *itparam,
                                 ILU_param *iluparam);
 

@@ -54,6 +54,15 @@ void* pnpb200_get_stream(pnpb200_handle* h);
 int  pnpb200_set_coefficients(pnpb200_handle* h, const double* permittivity,
                               const double* fixed_charge, const double* diffusivity,
                               const double* valency, const double* reaction);
+/* The caller's dof numbering (PDE::get_dofs src/pde.cpp:404-431; the component-major cell dofs of
+ * vector_linear_pnp_forms.h:7706-7726 after DOLFIN's renumbering). Internally dof = 3*vertex + component.
+ * vertex_to_dof[3*v + k] = the caller's index of (vertex v, component k) — exactly dolfin::vertex_to_dof_map(V)
+ * of the mixed space; vertex_to_scalar_dof[v] the same for the P1 coefficient spaces (permittivity, fixed
+ * charge; NULL = vertex order). From then on EVERY dof-indexed host array of this header (solution,
+ * coefficients, Dirichlet dofs, rhs, update, exact solution, solver-test vectors, total charge) is in the
+ * caller's numbering; matrices (pnpb200_get_matrix) stay in vertex-block order. NULL, NULL resets. Call
+ * before pnpb200_set_coefficients / pnpb200_set_dirichlet. */
+int  pnpb200_set_dof_map(pnpb200_handle* h, const int* vertex_to_dof, const int* vertex_to_scalar_dof);
 /* PDE::set_DirichletBC / remove_Dirichlet_dof (src/pde.cpp:433-483): homogeneous Dirichlet
  * rows for the Newton update on the listed scalar dofs. */
 int  pnpb200_set_dirichlet(pnpb200_handle* h, int n_bc, const int* bc_dofs);
@@ -152,6 +161,17 @@ int  pnpb200_set_hierarchy_reuse(pnpb200_handle* h, int reuse);
  * arithmetic up to rounding (tests/test_gpu_solver.py), 2.5 instead of 4 matrix passes per
  * Krylov iteration on every level. */
 int  pnpb200_set_sweep_shortcuts(pnpb200_handle* h, int on);
+
+/* Krylov preconditioner of pnpb200_solve / _newton_step / _solve_update: kind 0 = BSR UA-AMG cycle (bsr.dat of
+ * pnp_exact_solution, default), 1 = block ILU(k) with k = ilu_lfil, the diode configuration
+ * (benchmarks/pnp_diode/linear_pnp.cpp:103-109, bsr.dat:34-38: ILUk, lfil 2). Symbolic factorisation once per
+ * pattern (host), numeric factorisation and the triangular solves on the device (csrc/ilu.cu). */
+int  pnpb200_set_preconditioner(pnpb200_handle* h, int kind, int ilu_lfil);
+/* the ILU factors of the last solve, FASP-style arrays in vertex order (parity tests): n_blocks first, then the
+ * arrays (any may be NULL); val holds L (strict lower, unit diagonal implied) and U, dinv the inverse U_ii */
+int  pnpb200_get_ilu_factors(pnpb200_handle* h, int* n_blocks, int* IA, int* JA, double* val, double* dinv);
+/* z = U^{-1} L^{-1} r with those factors (host vectors, vertex order) */
+int  pnpb200_apply_ilu(pnpb200_handle* h, const double* r, double* z);
 
 /* ---- introspection for the parity tests and the byte model of bench.py ---- */
 typedef struct pnpb200_stats {

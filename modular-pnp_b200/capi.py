@@ -171,6 +171,10 @@ def lib():
     L.pnpb200_comm_init.argtypes = [H, C.c_char_p, C.c_int, C.c_int]
     L.pnpb200_set_partition.argtypes = [H, C.c_int, C.c_int, _i4, _i4, _i4, _i4]
     L.pnpb200_set_coloring.argtypes = [H, C.c_int, _i4]
+    L.pnpb200_set_dof_map.argtypes = [H, C.c_void_p, C.c_void_p]
+    L.pnpb200_set_preconditioner.argtypes = [H, C.c_int, C.c_int]
+    L.pnpb200_get_ilu_factors.argtypes = [H, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pnpb200_apply_ilu.argtypes = [H, _f8, _f8]
     PP = C.POINTER(C.c_void_p)
     L.pnpb200_partition_box.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 4 + [PP]
     L.pnpb200_partition_mesh.argtypes = [C.c_int, _f8, C.c_int, _i4, C.c_int, C.c_int, PP]
@@ -362,6 +366,28 @@ class PNP:
         pad = lambda a: np.ascontiguousarray(a if len(a) else np.zeros(1), dtype=np.int32)
         _check(self.L.pnpb200_set_partition(self.h, int(part["n_own"]), nb, pad(part["nbr"]), pad(part["send_ptr"]),
                                             pad(part["send_idx"]), pad(part["recv_ptr"])), "set_partition")
+
+    def set_dof_map(self, vertex_to_dof=None, vertex_to_scalar_dof=None):
+        a = None if vertex_to_dof is None else np.ascontiguousarray(vertex_to_dof, dtype=np.int32)
+        b = None if vertex_to_scalar_dof is None else np.ascontiguousarray(vertex_to_scalar_dof, dtype=np.int32)
+        _check(self.L.pnpb200_set_dof_map(self.h, None if a is None else a.ctypes.data, None if b is None else b.ctypes.data), "set_dof_map")
+
+    def set_preconditioner(self, kind="amg", ilu_lfil=2):
+        _check(self.L.pnpb200_set_preconditioner(self.h, {"amg": 0, "ilu": 1}[kind], int(ilu_lfil)), "set_preconditioner")
+
+    def ilu_factors(self):
+        nb = C.c_int()
+        _check(self.L.pnpb200_get_ilu_factors(self.h, C.byref(nb), None, None, None, None), "get_ilu_factors")
+        n = self.nv
+        IA = np.zeros(n + 1, dtype=np.int32); JA = np.zeros(nb.value, dtype=np.int32)
+        val = np.zeros(9 * nb.value); dinv = np.zeros(9 * n)
+        _check(self.L.pnpb200_get_ilu_factors(self.h, C.byref(nb), IA.ctypes.data, JA.ctypes.data, val.ctypes.data, dinv.ctypes.data), "get_ilu_factors")
+        return IA, JA, val, dinv
+
+    def apply_ilu(self, r):
+        z = np.zeros(self.N)
+        _check(self.L.pnpb200_apply_ilu(self.h, np.ascontiguousarray(r, dtype=np.float64), z), "apply_ilu")
+        return z
 
     def set_coloring(self, color, n_colors=None):
         color = np.ascontiguousarray(color, dtype=np.int32)
@@ -601,10 +627,11 @@ def fasp_solver_dcsr_krylov(IA, JA, val, b, it):
     return xv._keep, st
 
 
-def fasp_solver_dbsr_krylov_ilu(IA, JA, val, b, it):
+def fasp_solver_dbsr_krylov_ilu(IA, JA, val, b, it, lfil=2):
     A = numpy_to_bsr(IA, JA, val)
     bv = numpy_to_dvec(b); xv = numpy_to_dvec(np.zeros(len(b)))
     ilu = ILU_param()
+    ilu.ILU_type = 2; ilu.ILU_lfil = lfil          # benchmarks/pnp_diode/bsr.dat:34-38
     st = lib().fasp_solver_dbsr_krylov_ilu(C.byref(A), C.byref(bv), C.byref(xv), C.byref(it), C.byref(ilu))
     return xv._keep, st
 

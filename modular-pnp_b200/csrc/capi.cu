@@ -43,6 +43,22 @@ void init_handle(Handle& h, int device)
   h.hier.lv.emplace_back(new Level);
 }
 
+// ---- caller's dof numbering (pnpb200_set_dof_map): host vectors are permuted at the boundary -----------
+// internal index 3*v + k  <->  caller's dof dofmap[3*v + k]; per-vertex scalars v <-> sdofmap[v]
+struct HostIn {           // a host vector in INTERNAL order (a permuted copy only if a map is set)
+  std::vector<double> tmp; const double* p;
+  HostIn(const std::vector<int>& map, const double* ext, size_t n) : p(ext)
+  {
+    if (!map.empty()) { tmp.resize(n); for (size_t i = 0; i < n; ++i) tmp[i] = ext[map[i]]; p = tmp.data(); }
+  }
+};
+void host_out(const std::vector<int>& map, const DevBuf<double>& d, double* ext, size_t n)
+{
+  if (map.empty()) { d.download(ext, n); return; }
+  std::vector<double> tmp = d.to_host(n);
+  for (size_t i = 0; i < n; ++i) ext[map[i]] = tmp[i];
+}
+
 struct EventSpan {
   Handle& h; double& out;
   EventSpan(Handle& hh, double& o) : h(hh), out(o) { cudaEventRecord(h.ev[0], h.stream); }
@@ -56,13 +72,14 @@ struct EventSpan {
 int solve_current(Handle& h, const itsolver_param* it, const AMG_param* amg, int* status_its)
 {
   cudaStream_t s = h.stream;
-  const SolverConfig cfg = make_config(it, amg);
+  SolverConfig cfg = make_config(it, amg);
+  if (h.precond == 1) { cfg.use_amg = 0; cfg.use_ilu = 1; cfg.ilu_lfil = h.precond_lfil; }
   const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
   h.du.alloc(N, s);
   vec_set(h.du.p, 0.0, N, s);                       // linear_pnp.cpp:93 fasp_dvec_set(..., 0.0)
   h.last_cfg = cfg;
   h.stats.ms_spmv = h.stats.ms_vcycle = h.stats.ms_ortho = 0.0;
-  { EventSpan e(h, h.stats.ms_setup); if (cfg.use_amg) amg_setup(h, cfg); e.stop(); }
+  { EventSpan e(h, h.stats.ms_setup); if (cfg.use_amg) amg_setup(h, cfg); else if (cfg.use_ilu) ilu_setup(h, cfg.ilu_lfil); e.stop(); }
   int st;
   { EventSpan e(h, h.stats.ms_krylov); st = fgmres_solve(h, cfg, h.rhs.p, h.du.p, true); e.stop(); }
   if (status_its) *status_its = st;
@@ -224,9 +241,11 @@ int pnpb200_set_coefficients(pnpb200_handle* ph, const double* eps, const double
     PNP_CUDA(cudaSetDevice(h.device));
     const size_t nv = h.nv, N = 3 * nv;
     h.eps.alloc(nv, s); h.fixed.alloc(nv, s); h.diff.alloc(N, s); h.val.alloc(N, s); h.reac.alloc(N, s);
-    h.eps.upload(eps, nv); h.fixed.upload(fixed, nv); h.diff.upload(diff, N); h.val.upload(val, N); h.reac.upload(reac, N);
+    HostIn e_(h.sdofmap, eps, nv), f_(h.sdofmap, fixed, nv), d_(h.dofmap, diff, N), v_(h.dofmap, val, N), r_(h.dofmap, reac, N);
+    h.eps.upload(e_.p, nv); h.fixed.upload(f_.p, nv); h.diff.upload(d_.p, N); h.val.upload(v_.p, N); h.reac.upload(r_.p, N);
+    PNP_CUDA(cudaStreamSynchronize(s));          // the permuted copies are host temporaries
     // Linear_PNP::apply_eafe reads the valency Function's first three dof values (linear_pnp.cpp:220-224)
-    h.q_eafe[0] = 0.0; h.q_eafe[1] = val[1]; h.q_eafe[2] = val[2];
+    h.q_eafe[0] = 0.0; h.q_eafe[1] = v_.p[1]; h.q_eafe[2] = v_.p[2];     // components 1, 2 of the first vertex (identity map: val[1], val[2])
     compute_k00(h);
     PNP_CUDA(cudaStreamSynchronize(s));
     h.have_coef = true; h.rhs_current = false;
@@ -244,12 +263,76 @@ int pnpb200_set_dirichlet(pnpb200_handle* ph, int n_bc, const int* bc_dofs)
     std::vector<unsigned char> f(N, 0);
     for (int i = 0; i < n_bc; ++i) {
       if (bc_dofs[i] < 0 || (size_t)bc_dofs[i] >= N) throw Error(ERROR_INPUT_PAR, "Dirichlet dof out of range");
-      f[bc_dofs[i]] = 1;
+      f[h.dofmap_inv.empty() ? bc_dofs[i] : h.dofmap_inv[bc_dofs[i]]] = 1;
     }
     h.bc_user = f; h.rhs_current = false;
     for (size_t i = owned_dofs(h); i < N; ++i) f[i] = 1;   // ghost rows stay identity rows
     h.bcflag.upload(f.data(), N);
     PNP_CUDA(cudaStreamSynchronize(s));
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_set_dof_map(pnpb200_handle* ph, const int* vertex_to_dof, const int* vertex_to_scalar_dof)
+{
+  if (!ph) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h;
+    const size_t nv = h.nv, N = 3 * nv;
+    if (nv == 0) throw Error(ERROR_INPUT_PAR, "handle has no mesh");
+    std::vector<int> m, inv, sm;
+    if (vertex_to_dof) {
+      m.assign(vertex_to_dof, vertex_to_dof + N); inv.assign(N, -1);
+      for (size_t i = 0; i < N; ++i) {
+        if (m[i] < 0 || (size_t)m[i] >= N || inv[m[i]] >= 0) throw Error(ERROR_INPUT_PAR, "pnpb200_set_dof_map: vertex_to_dof is not a permutation of 0 .. 3*nv-1");
+        inv[m[i]] = (int)i;
+      }
+    }
+    if (vertex_to_scalar_dof) {
+      sm.assign(vertex_to_scalar_dof, vertex_to_scalar_dof + nv);
+      std::vector<char> seen(nv, 0);
+      for (size_t v = 0; v < nv; ++v) {
+        if (sm[v] < 0 || (size_t)sm[v] >= nv || seen[sm[v]]) throw Error(ERROR_INPUT_PAR, "pnpb200_set_dof_map: vertex_to_scalar_dof is not a permutation of 0 .. nv-1");
+        seen[sm[v]] = 1;
+      }
+    }
+    h.dofmap.swap(m); h.dofmap_inv.swap(inv); h.sdofmap.swap(sm);
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_set_preconditioner(pnpb200_handle* ph, int kind, int ilu_lfil)
+{
+  if (!ph || (kind != 0 && kind != 1) || ilu_lfil < 0) return ERROR_INPUT_PAR;
+  ph->h.precond = kind; ph->h.precond_lfil = ilu_lfil;
+  return FASP_SUCCESS;
+}
+
+int pnpb200_get_ilu_factors(pnpb200_handle* ph, int* n_blocks, int* IA, int* JA, double* val, double* dinv)
+{
+  if (!ph) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    IluFactor& F = ph->h.ilu;
+    if (!F.symbolic_valid) throw Error(ERROR_INPUT_PAR, "no ILU factors: solve with the ILU preconditioner first");
+    if (n_blocks) *n_blocks = F.nnz;
+    if (IA) F.ia.download(IA, F.n + 1);
+    if (JA) F.ja.download(JA, F.nnz);
+    if (val) F.val.download(val, 9 * (size_t)F.nnz);
+    if (dinv) F.dinv.download(dinv, 9 * (size_t)F.n);
+    return FASP_SUCCESS;
+  });
+}
+
+int pnpb200_apply_ilu(pnpb200_handle* ph, const double* r, double* z)
+{
+  if (!ph || !r || !z) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    const size_t N = 3 * (size_t)h.hier.lv[0]->A.n;
+    DevBuf<double> dr, dz; dr.alloc(N, s); dz.alloc(N, s);
+    dr.upload(r, N);
+    ilu_apply(h, dr.p, 3, dz.p, 3, false);
+    dz.download(z, N);
     return FASP_SUCCESS;
   });
 }
@@ -275,7 +358,8 @@ int pnpb200_set_solution(pnpb200_handle* ph, const double* uu)
     Handle& h = ph->h;
     PNP_CUDA(cudaSetDevice(h.device));
     h.rhs_current = false;
-    h.uu.upload(uu, 3 * (size_t)h.nv);
+    HostIn u_(h.dofmap, uu, 3 * (size_t)h.nv);
+    h.uu.upload(u_.p, 3 * (size_t)h.nv);
     PNP_CUDA(cudaStreamSynchronize(h.stream));
     return FASP_SUCCESS;
   });
@@ -284,7 +368,7 @@ int pnpb200_set_solution(pnpb200_handle* ph, const double* uu)
 int pnpb200_get_solution(pnpb200_handle* ph, double* uu)
 {
   if (!ph || !uu) return ERROR_INPUT_PAR;
-  return guarded([&]() -> int { PNP_CUDA(cudaSetDevice(ph->h.device)); ph->h.uu.download(uu, 3 * (size_t)ph->h.nv); return FASP_SUCCESS; });
+  return guarded([&]() -> int { PNP_CUDA(cudaSetDevice(ph->h.device)); host_out(ph->h.dofmap, ph->h.uu, uu, 3 * (size_t)ph->h.nv); return FASP_SUCCESS; });
 }
 
 int pnpb200_set_solution_device(pnpb200_handle* ph, const double* d_uu)
@@ -370,7 +454,7 @@ int pnpb200_get_rhs(pnpb200_handle* ph, dvector* b)
   return guarded([&]() -> int {
     Handle& h = ph->h;
     if (b->row != 3 * h.nv || h.rhs.n < (size_t)b->row) throw Error(ERROR_INPUT_PAR, "rhs size mismatch / not assembled");
-    h.rhs.download(b->val, b->row);
+    host_out(h.dofmap, h.rhs, b->val, (size_t)b->row);
     return FASP_SUCCESS;
   });
 }
@@ -410,7 +494,7 @@ int pnpb200_solve(pnpb200_handle* ph, const itsolver_param* it, const AMG_param*
 int pnpb200_get_update(pnpb200_handle* ph, double* du)
 {
   if (!ph || !du) return ERROR_INPUT_PAR;
-  return guarded([&]() -> int { ph->h.du.download(du, 3 * (size_t)ph->h.hier.lv[0]->A.n); return FASP_SUCCESS; });
+  return guarded([&]() -> int { host_out(ph->h.dofmap, ph->h.du, du, 3 * (size_t)ph->h.hier.lv[0]->A.n); return FASP_SUCCESS; });
 }
 
 int pnpb200_test_solver(pnpb200_handle* ph, const double* target, double* x, const itsolver_param* it,
@@ -424,14 +508,16 @@ int pnpb200_test_solver(pnpb200_handle* ph, const double* target, double* x, con
     halo_exchange(h, h.hier.lv[0]->halo, h.uu.p);
     assemble_system(h);                                   // linear_pnp.cpp:137
     const size_t N = 3 * (size_t)h.nv;
-    DevBuf<double> t; t.alloc(N, s); t.upload(target, N);
+    HostIn t_(h.dofmap, target, N);
+    DevBuf<double> t; t.alloc(N, s); t.upload(t_.p, N);
+    PNP_CUDA(cudaStreamSynchronize(s));
     bsrt_spmv_rowid(h.hier.lv[0]->A, t.p, h.rhs.p, s);    // rhs = J * target, linear_pnp.cpp:144
     h.rhs_current = false;
     int st = 0;
     solve_current(h, it, amg, &st);
     if (status_its) *status_its = st;
     if (st < 0) memcpy(x, target, N * sizeof(double));    // linear_pnp.cpp:158-162
-    else h.du.download(x, N);
+    else host_out(h.dofmap, h.du, x, N);
     h.stats.launches = g_launches;
     return FASP_SUCCESS;
   });
@@ -522,7 +608,9 @@ int pnpb200_error_norms(pnpb200_handle* ph, const double* exact, double* l2_erro
     PNP_CUDA(cudaSetDevice(h.device));
     if (h.nv == 0) throw Error(ERROR_INPUT_PAR, "handle has no mesh");
     const size_t N = 3 * (size_t)h.nv;
-    DevBuf<double> ex; ex.alloc(N, s); ex.upload(exact, N);
+    HostIn e_(h.dofmap, exact, N);
+    DevBuf<double> ex; ex.alloc(N, s); ex.upload(e_.p, N);
+    PNP_CUDA(cudaStreamSynchronize(s));
     error_norms(h, ex.p, l2_error, h1_error);
     return FASP_SUCCESS;
   });
@@ -537,7 +625,7 @@ int pnpb200_total_charge(pnpb200_handle* ph, double* charge)
     if (!h.have_coef) throw Error(ERROR_INPUT_PAR, "coefficients not set");
     DevBuf<double> out; out.alloc(h.nv, s);
     total_charge(h, out.p);
-    out.download(charge, h.nv);
+    host_out(h.sdofmap, out, charge, (size_t)h.nv);
     return FASP_SUCCESS;
   });
 }
@@ -712,7 +800,7 @@ int pnpb200_apply_matrix(pnpb200_handle* ph, const double* x, double* y)
 // ---------------------------------------------------------------------------------------------
 // FASP-compatible solver entry points (host structs in, GPU solve, host vector out)
 // ---------------------------------------------------------------------------------------------
-static INT solve_host_bsr(dBSRmat* A, dvector* b, dvector* x, itsolver_param* it, AMG_param* amg)
+static INT solve_host_bsr(dBSRmat* A, dvector* b, dvector* x, itsolver_param* it, AMG_param* amg, const ILU_param* ilu = nullptr)
 {
   if (!A || !b || !x || !it || !b->val || !x->val) return ERROR_INPUT_PAR;
   int status = ERROR_UNKNOWN;
@@ -721,10 +809,12 @@ static INT solve_host_bsr(dBSRmat* A, dvector* b, dvector* x, itsolver_param* it
     HostSystem sys(A);
     Handle& h = sys.ph->h; cudaStream_t s = h.stream;
     const size_t N = (size_t)b->row;
-    const SolverConfig cfg = make_config(it, amg);
+    SolverConfig cfg = make_config(it, amg);
+    if (ilu) { cfg.use_amg = 0; cfg.use_ilu = 1; cfg.ilu_lfil = ilu->ILU_lfil; }
     h.rhs.alloc(N, s); h.rhs.upload(b->val, N);
     h.du.alloc(N, s); h.du.upload(x->val, N);          // x is the initial guess
     if (cfg.use_amg) amg_setup(h, cfg);
+    else if (cfg.use_ilu) ilu_setup(h, cfg.ilu_lfil);
     status = fgmres_solve(h, cfg, h.rhs.p, h.du.p);
     h.du.download(x->val, N);                           // last iterate even on failure
     return FASP_SUCCESS;
@@ -740,10 +830,10 @@ INT fasp_solver_dbsr_krylov_amg(dBSRmat* A, dvector* b, dvector* x, itsolver_par
 
 INT fasp_solver_dbsr_krylov_ilu(dBSRmat* A, dvector* b, dvector* x, itsolver_param* it, ILU_param* ilu)
 {
-  (void)ilu;                      // "next" tier: block-ILU(k) not built; AMG with bsr.dat defaults instead
-  AMG_param amg;
-  fasp_param_amg_init(&amg);
-  return solve_host_bsr(A, b, x, it, &amg);
+  // block ILU(k) with k = ILU_lfil (pnp_diode/bsr.dat: ILU_type 2 = ILUk, lfil 2), FGMRES on the device (ilu.cu).
+  // FASP's threshold variants (ILU_type 1 ILUt, 3 ILUtp) are mapped to the level-of-fill factorisation too.
+  if (!ilu) return ERROR_INPUT_PAR;
+  return solve_host_bsr(A, b, x, it, nullptr, ilu);
 }
 
 void fasp_blas_dbsr_aAxpy(const REAL alpha, const dBSRmat* A, const REAL* x, REAL* y)

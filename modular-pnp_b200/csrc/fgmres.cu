@@ -92,6 +92,7 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
         PhaseTimer t(h, h.stats.ms_vcycle);
         zero_ghost(Vi(i - 1));     // the preconditioner is local to the rank (block Jacobi across GPUs)
         if (cfg.use_amg) have_Az = amg_vcycle(h, cfg, Vi(i - 1), Zi(i - 1), Vi(i), KS, KS);
+        else if (cfg.use_ilu) ilu_apply(h, Vi(i - 1), KS, Zi(i - 1), VS, true);
         else vec_restride(Vi(i - 1), KS, Zi(i - 1), VS, (size_t)A.n, s);
       }
       if (!have_Az) { PhaseTimer t(h, h.stats.ms_spmv); if (dist) halo_exchange(h, halo, Zi(i - 1), true); bsrt_spmv(A, Zi(i - 1), Vi(i), s, KS); }

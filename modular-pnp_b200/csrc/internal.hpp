@@ -93,6 +93,7 @@ struct SolverConfig {
   int max_levels = 20; int coarse_dof = 100; double strong_coupled = 0.08; int max_aggregation = 20;
   double tentative_smooth = 0.67; int presmooth = 1, postsmooth = 1;
   int use_amg = 1;
+  int use_ilu = 0, ilu_lfil = 0;   // block ILU(k) as the Krylov preconditioner (ilu.cu) when use_amg == 0
   int cycle_type = 1;       // V_CYCLE; anything else = K-cycle (nonlinear AMLI)
   int kcycle_levels = 3;    // coarse levels 1..kcycle_levels get the Krylov acceleration (measured best at 256^3)
 };
@@ -129,6 +130,15 @@ struct Krylov {
   double* h_dots = nullptr;     // pinned host mirror
 };
 
+// block ILU(k) factors of the fine-level matrix (ilu.cu); rows in row-id order, columns ascending
+struct IluFactor {
+  int n = 0, nnz = 0, maxlen = 0, lfil = -1, pattern_nnzb = -1, epoch = 0;
+  bool symbolic_valid = false;
+  DevBuf<int> ia, ja, diag, src;     // factor pattern, position of the diagonal, source block in A (-1 = fill)
+  DevBuf<double> val, dinv, y, x;    // L\U blocks (row-major 3x3), inverse diagonal blocks, work vectors
+  DevBuf<int> flag, ticket;          // done-flags (numeric / forward / backward) and row tickets of the sync-free sweeps
+};
+
 struct Stats {
   int krylov_its = 0;
   double ms_assemble = 0, ms_setup = 0, ms_krylov = 0, ms_residual = 0;
@@ -159,6 +169,8 @@ struct Handle {
   int box_n[3] = {0, 0, 0};     // grid of a mesh generated by generate_box_mesh (0: mesh given by the caller)
   Comm comm;
   std::vector<unsigned char> bc_user;   // Dirichlet flags as set by the caller (ghost flags are added on top)
+  // caller's dof numbering (pnpb200_set_dof_map): internal 3*v + k <-> dofmap[3*v + k]; scalars v <-> sdofmap[v]; empty = identity
+  std::vector<int> dofmap, dofmap_inv, sdofmap;
   DevBuf<double> xyz;           // 3*nv
   DevBuf<int> cells;            // 4*nc
   DevBuf<int> v2c_ptr, v2c_idx; // vertex -> incident cells (ascending)
@@ -189,6 +201,8 @@ struct Handle {
   // solver
   Hierarchy hier;
   Krylov kry;
+  IluFactor ilu;
+  int precond = 0, precond_lfil = 2;   // pnpb200_set_preconditioner: 0 = AMG (bsr.dat), 1 = block ILU(k) (pnp_diode/bsr.dat)
   int reuse_hierarchy = 0;
   int sweep_shortcuts = getenv("PNPB200_NO_SWEEP_SHORTCUTS") ? 0 : 1;   // L-only / U-only / L*delta passes in the cycle
   int timing_detail = 0;
@@ -315,6 +329,9 @@ void amg_setup(Handle& h, const SolverConfig& cfg);
 // post-smoothing sweep), Az = A z is written too and true is returned.
 // r carries rs doubles per row, Az azs (the Krylov basis is packed); z is a padded sweep-space vector.
 bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az = nullptr, int rs = VS, int azs = VS);
+// ---- ilu.cu
+void ilu_setup(Handle& h, int lfil);                                         // symbolic (cached per pattern) + numeric
+void ilu_apply(Handle& h, const double* r, int rs, double* z, int zs, bool sweep_space);
 // ---- fgmres.cu
 // zero_guess: x is known to be all zeros on entry (linear_pnp.cpp:93), so r0 = b needs no matvec
 int fgmres_solve(Handle& h, const SolverConfig& cfg, const double* b, double* x, bool zero_guess = false);

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <functional>
 #include "pnp_oracle.h"
 #include "oracle_internal.hpp"
 
@@ -482,9 +483,12 @@ void orc_amg_vcycle(orc_amg* h, const double* r, double* z)
   std::copy(F.x.begin(), F.x.end(), z);
 }
 
-// fasp_solver_dbsr_pvfgmres restated [EXT]
-int orc_pvfgmres(int nrow, const int* IA, const int* JA, const double* val, const double* b,
-                 double* x, orc_amg* pc, const orc_solver_param* prm, double* hist, int hist_len)
+} // extern "C"
+
+namespace orc {
+// fasp_solver_dbsr_pvfgmres restated [EXT]; pc = the preconditioner z = M^{-1} r (null: none)
+int pvfgmres_impl(int nrow, const int* IA, const int* JA, const double* val, const double* b,
+                  double* x, const std::function<void(const double*, double*)>* pc, const orc_solver_param* prm, double* hist, int hist_len)
 {
   const int n = 3 * nrow;
   const int restart_max = std::max(1, std::min(prm->restart, prm->maxit)), restart_min = 3, dstep = 3;
@@ -517,7 +521,7 @@ int orc_pvfgmres(int nrow, const int* IA, const int* JA, const double* val, cons
     int i = 0;
     while (i < Restart && iter < MaxIt) {
       ++i; ++iter;
-      if (pc) orc_amg_vcycle(pc, pv[i - 1].data(), zv[i - 1].data()); else zv[i - 1] = pv[i - 1];
+      if (pc) (*pc)(pv[i - 1].data(), zv[i - 1].data()); else zv[i - 1] = pv[i - 1];
       bsr_spmv(nrow, IA, JA, val, 1.0, zv[i - 1].data(), 0.0, pv[i].data());
       if (!prm->ortho_cgs) {
         for (int j = 0; j < i; ++j) {           // modified Gram-Schmidt
@@ -584,6 +588,17 @@ int orc_pvfgmres(int nrow, const int* IA, const int* JA, const double* val, cons
   }
   if (iter >= MaxIt && r_norm > epsilon) return -1;   // ERROR_SOLVER_MAXIT
   return iter;
+}
+} // namespace orc
+
+extern "C" {
+
+int orc_pvfgmres(int nrow, const int* IA, const int* JA, const double* val, const double* b,
+                 double* x, orc_amg* pc, const orc_solver_param* prm, double* hist, int hist_len)
+{
+  if (!pc) return orc::pvfgmres_impl(nrow, IA, JA, val, b, x, nullptr, prm, hist, hist_len);
+  std::function<void(const double*, double*)> f = [pc](const double* r, double* z) { orc_amg_vcycle(pc, r, z); };
+  return orc::pvfgmres_impl(nrow, IA, JA, val, b, x, &f, prm, hist, hist_len);
 }
 
 int orc_solver_dbsr_krylov_amg(int nrow, const int* IA, const int* JA, const double* val,

@@ -91,6 +91,14 @@ def lib():
         L.orc_pvfgmres.restype = C.c_int
         L.orc_solver_dbsr_krylov_amg.argtypes = [C.c_int, _i4, _i4, _f8, _f8, _f8, C.POINTER(SolverParam)]
         L.orc_solver_dbsr_krylov_amg.restype = C.c_int
+        L.orc_ilu_setup.argtypes = [C.c_int, _i4, _i4, _f8, C.c_int]
+        L.orc_ilu_setup.restype = C.c_void_p
+        L.orc_ilu_nnz.argtypes = [C.c_void_p]
+        L.orc_ilu_factors.argtypes = [C.c_void_p, _i4, _i4, _f8, _f8]
+        L.orc_ilu_apply.argtypes = [C.c_void_p, _f8, _f8]
+        L.orc_ilu_free.argtypes = [C.c_void_p]
+        L.orc_solver_dbsr_krylov_ilu.argtypes = [C.c_int, _i4, _i4, _f8, _f8, _f8, C.POINTER(SolverParam), C.c_int]
+        L.orc_solver_dbsr_krylov_ilu.restype = C.c_int
         L.orc_exact_problem.argtypes = [C.c_int, _f8] + [_f8] * 6 + [C.c_void_p]
         L.orc_newton_exact.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.POINTER(SolverParam), C.c_int,
                                                                           C.c_double, C.c_double, C.c_int,
@@ -284,6 +292,40 @@ def solver_dbsr_krylov_amg(IA, JA, val, b, param):
     n = len(IA) - 1
     x = np.zeros(3 * n)
     its = lib().orc_solver_dbsr_krylov_amg(n, IA, JA, val, np.ascontiguousarray(b), x, C.byref(param))
+    return x, its
+
+
+class ILU:
+    """block ILU(k) of a BSR(3) matrix (oracle/ilu_restated.cpp): factors and z = U^{-1} L^{-1} r"""
+
+    def __init__(self, IA, JA, val, lfil):
+        self.n = len(IA) - 1
+        self.h = lib().orc_ilu_setup(self.n, np.ascontiguousarray(IA, dtype=np.int32), np.ascontiguousarray(JA, dtype=np.int32),
+                                     np.ascontiguousarray(val, dtype=np.float64), int(lfil))
+
+    def factors(self):
+        nnz = lib().orc_ilu_nnz(self.h)
+        IA = np.zeros(self.n + 1, dtype=np.int32); JA = np.zeros(nnz, dtype=np.int32)
+        val = np.zeros(9 * nnz); dinv = np.zeros(9 * self.n)
+        lib().orc_ilu_factors(self.h, IA, JA, val, dinv)
+        return IA, JA, val, dinv
+
+    def apply(self, r):
+        z = np.zeros(3 * self.n)
+        lib().orc_ilu_apply(self.h, np.ascontiguousarray(r, dtype=np.float64), z)
+        return z
+
+    def __del__(self):
+        try:
+            lib().orc_ilu_free(self.h)
+        except Exception:
+            pass
+
+
+def solver_dbsr_krylov_ilu(IA, JA, val, b, param, lfil=2):
+    n = len(IA) - 1
+    x = np.zeros(3 * n)
+    its = lib().orc_solver_dbsr_krylov_ilu(n, IA, JA, val, np.ascontiguousarray(b), x, C.byref(param), int(lfil))
     return x, its
 
 

@@ -146,6 +146,18 @@ int  orc_pvfgmres(int nrow, const int* IA, const int* JA, const double* val,
 int  orc_solver_dbsr_krylov_amg(int nrow, const int* IA, const int* JA, const double* val,
                                 const double* b, double* x, const orc_solver_param* p);
 
+/* ---- block ILU(k), fasp_solver_dbsr_krylov_ilu restated (benchmarks/pnp_diode/linear_pnp.cpp:103-109,
+ * bsr.dat:34-38: ILU_type 2 = ILUk, ILU_lfil 2); oracle/ilu_restated.cpp ---- */
+typedef struct orc_ilu orc_ilu;
+int      orc_ilu_symbolic_count(int n, const int* IA, const int* JA, int lfil, int* fIA /*n+1*/);
+orc_ilu* orc_ilu_setup(int n, const int* IA, const int* JA, const double* val, int lfil);
+int      orc_ilu_nnz(const orc_ilu* F);
+void     orc_ilu_factors(const orc_ilu* F, int* IA, int* JA, double* val, double* dinv);
+void     orc_ilu_apply(const orc_ilu* F, const double* r, double* z);
+void     orc_ilu_free(orc_ilu* F);
+int      orc_solver_dbsr_krylov_ilu(int nrow, const int* IA, const int* JA, const double* val, const double* b, double* x,
+                                    const orc_solver_param* p, int lfil);
+
 /* ---- Newton driver mirroring benchmarks/pnp_exact_solution/main.cpp:138-356 ---- */
 typedef struct {
   int    newton_its;       /* Newton_Status::iteration - 1 at exit */

@@ -235,3 +235,43 @@ def test_zero_row_gets_unit_diagonal(oracle, pkg, gpu_lib, use_eafe):
     assert np.abs(V[sl, 0, :]).sum() > 0 and np.abs(V[sl, 2, :]).sum() > 0
     assert row_scaled_error(IA, val, A_ref) <= 1e-12
     g.close()
+
+
+def test_caller_dof_numbering(oracle, pkg, gpu_lib):
+    """SURVEY a14 / pnpb200_set_dof_map: a DOLFIN-style renumbering (nodes permuted, the three dofs of a node
+    kept together, P1 coefficient spaces with their own permutation) and a fully general dof permutation.
+    Every dof-indexed array crosses the ABI in the caller's numbering; results equal the oracle's (vertex
+    numbering) after mapping back: rhs 1e-12, two Newton steps' residual norms 1e-12 / 2e-3 (as elsewhere)."""
+    P = oracle.Problem(10, 4, 4)
+    rng = np.random.default_rng(5)
+    perm_v = rng.permutation(P.nv)
+    block_map = (3 * perm_v[:, None] + np.arange(3)[None, :]).ravel()          # vertex_to_dof_map of a node-reordered space
+    general_map = rng.permutation(P.N)
+    smap = rng.permutation(P.nv)
+    uu = perturbed_state(P, quantize=True)
+    _, b_ref = P.assemble(uu, use_eafe=True)
+    _, l2_ref, mx_ref = P.residual(uu)
+    for v2d in (block_map, general_map):
+        def ext(a):                     # internal (3v + k) -> caller's numbering
+            out = np.empty_like(a); out[v2d] = a; return out
+
+        def sext(a):
+            out = np.empty_like(a); out[smap] = a; return out
+        g = pkg.PNP(P.xyz, P.cells, 0)
+        g.set_dof_map(v2d, smap)
+        g.set_coefficients(sext(P.eps), sext(P.fixed), ext(P.diff), ext(P.val), ext(P.reac))
+        g.set_dirichlet(v2d[np.nonzero(P.bcflag)[0]].astype(np.int32))
+        g.set_solution(ext(uu))
+        l2, mx = g.residual()
+        assert abs(l2 - l2_ref) <= 1e-12 * l2_ref and abs(mx - mx_ref) <= 1e-12 * mx_ref
+        g.assemble()
+        b = g.get_rhs()
+        assert np.abs(b[v2d] - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+        assert np.array_equal(g.get_solution(), ext(uu))
+        it, amg = pkg.default_params()
+        st, l2n, _ = g.newton_step(it, amg)
+        assert st > 0
+        un = g.get_solution()[v2d]                       # back to vertex numbering
+        _, l2o, _ = P.residual(un)
+        assert abs(l2n - l2o) <= 1e-10 * l2o
+        g.close()

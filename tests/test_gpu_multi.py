@@ -23,11 +23,20 @@ WORKER = textwrap.dedent('''
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
     nx, ny, nz, lx, ly, lz = 24, 10, 24, 2.0, 0.8, 2.0
-    P = part_mod.box_slab_partition(nx, ny, nz, lx, ly, lz, rank, world)
+    MODE = os.environ.get("PNPB200_TEST_PARTITION", "slabs")
+    if MODE == "rcb":       # general-mesh path: recursive coordinate bisection of the global arrays (csrc/partition.cpp)
+        s0 = pkg.PNP(box=(nx, ny, nz, lx, ly, lz), device=rank); gx, gc = s0.get_mesh(); s0.close()
+        P = part_mod.mesh_rcb_partition(gx, gc, rank, world)
+        ix = np.rint((P["xyz"][0::3] + lx / 2) * nx / lx).astype(np.int64)
+        P["bc_vertices"] = np.nonzero((ix == 0) | (ix == nx))[0].astype(np.int32)
+    else:                   # bricks of the BoxMesh in closed form; (1, 1, N) = z-slabs
+        P = part_mod.box_brick_partition(nx, ny, nz, lx, ly, lz, rank, world, grid=(1, 1, world) if MODE == "slabs" else (world, 1, 1))
     g = pkg.PNP(P["xyz"], P["cells"], device=rank)
     uid = [pkg.capi.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     g.comm_init(uid[0], rank, world); g.set_partition(P)
+    if "color" in P:
+        g.set_coloring(P["color"], 4)
     f = prob.exact_solution_fields(P["xyz"][0::3])
     g.set_coefficients(f["eps"], f["fixed"], f["diff"], f["val"], f["reac"])
     g.set_dirichlet((3 * P["bc_vertices"][:, None] + np.arange(3)).ravel().astype(np.int32))
@@ -36,6 +45,7 @@ WORKER = textwrap.dedent('''
     r0 = g.residual()
     hist = [g.newton_step(it, amg) for _ in range(3)]
     uu = g.get_solution()[:3 * P["n_own"]]
+    gd = (3 * np.asarray(P["gids"])[:P["n_own"], None] + np.arange(3)).ravel()
     g.close()
     if rank == 0:
         s = pkg.PNP(box=(nx, ny, nz, lx, ly, lz), device=0)
@@ -43,7 +53,7 @@ WORKER = textwrap.dedent('''
         s.set_coefficients(pr["eps"], pr["fixed"], pr["diff"], pr["val"], pr["reac"]); s.set_dirichlet(pr["bc_dofs"]); s.set_solution(pr["uu0"])
         q0 = s.residual()
         ref = [s.newton_step(it, amg) for _ in range(3)]
-        uu_ref = s.get_solution()[:3 * P["n_own"]]
+        uu_ref = s.get_solution()[gd]
         s.close()
         assert abs(r0[0] - q0[0]) <= 1e-12 * q0[0] and abs(r0[1] - q0[1]) <= 1e-12 * q0[1], (r0, q0)
         for (st, l2, mx), (st2, l22, mx2) in zip(hist, ref):
@@ -55,12 +65,15 @@ WORKER = textwrap.dedent('''
 ''') % ROOT
 
 
-def test_two_gpu_newton_matches_single_gpu(gpu_lib, tmp_path):
+@pytest.mark.parametrize("mode", ["slabs", "xbricks", "rcb"])
+def test_two_gpu_newton_matches_single_gpu(gpu_lib, tmp_path, mode):
+    """slabs: z-slabs (contiguous global ids); xbricks: cut along x (owned vertices strided in the global
+    numbering, neighbours through every Kuhn diagonal); rcb: the general-mesh partitioner on the same mesh"""
     if gpu_lib.pnpb200_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29621", str(script)],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, PNPB200_TEST_PARTITION=mode))
     assert out.returncode == 0 and "MULTI_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -212,11 +212,14 @@ def test_other_fasp_entry_points(oracle, pkg, system):
     pkg.lib().fasp_blas_dbsr_aAxpy(-0.5, C.byref(A), x, y2)
     ref = y - 0.5 * oracle.bsr_spmv(IA, JA, val, x)
     assert np.abs(y2 - ref).max() <= 1e-13 * np.abs(ref).max()
-    # fasp_solver_dbsr_krylov_ilu (routed to the AMG path)
+    # fasp_solver_dbsr_krylov_ilu: block ILU(2) + FGMRES on the device, same iteration count as the oracle's
     it, amg = pkg.default_params()
-    xs, st = pkg.capi.fasp_solver_dbsr_krylov_ilu(IA, JA, val, b, it)
+    xs, st = pkg.capi.fasp_solver_dbsr_krylov_ilu(IA, JA, val, b, it, lfil=2)
     assert st > 0
     assert np.linalg.norm(b - oracle.bsr_spmv(IA, JA, val, xs)) <= 1.0001 * it.tol * np.linalg.norm(b)
+    x_ref, its_ref = oracle.solver_dbsr_krylov_ilu(IA, JA, val, b, oracle.default_param(ortho_cgs=1), 2)
+    assert abs(st - its_ref) <= 1, (st, its_ref)
+    assert np.abs(xs - x_ref).max() <= 1e-5 * np.abs(x_ref).max()
     # fasp_solver_dcsr_krylov: unpreconditioned FGMRES on a scalar CSR (diagonally dominant 3n x 3n)
     n = 300
     import scipy.sparse as sp
@@ -334,3 +337,76 @@ def test_streamed_colour_launch_is_the_same_arithmetic(oracle, pkg, system):
     assert out[1][0] > 0 and out[1][0] == out[0][0]
     assert np.array_equal(out[1][2], out[0][2]), np.abs(out[1][2] - out[0][2]).max()
     assert np.array_equal(out[1][1], out[0][1])
+
+
+@pytest.mark.parametrize("lfil", [0, 1, 2])
+def test_block_ilu_factors_and_apply_match_oracle(oracle, pkg, system, lfil):
+    """csrc/ilu.cu vs oracle/ilu_restated.cpp (block ILU(k) of benchmarks/pnp_diode/bsr.dat:34-38): identical
+    level-of-fill pattern, L / U blocks and inverse diagonal blocks within 1e-12 of the largest entry,
+    z = U^{-1} L^{-1} r within 1e-11, and the preconditioned Krylov iteration count."""
+    P, g, IA, JA, val, b = system
+    g.set_solution(perturbed_state(P)); g.assemble()           # earlier tests of the module may have replaced the state
+    IA, JA, val = g.get_matrix(); b = g.get_rhs()
+    it, amg = pkg.default_params()
+    g.set_preconditioner("ilu", lfil)
+    try:
+        its = g.solve(it, amg)
+        fIA, fJA, fval, fdinv = g.ilu_factors()
+        rr = np.random.default_rng(13).uniform(-1, 1, P.N)
+        z = g.apply_ilu(rr)
+        du = g.get_update()
+    finally:
+        g.set_preconditioner("amg")
+    F = oracle.ILU(IA, JA, val, lfil)
+    oIA, oJA, oval, odinv = F.factors()
+    assert np.array_equal(fIA, oIA) and np.array_equal(fJA, oJA)
+    if lfil == 0:
+        assert np.array_equal(fIA, IA) and np.array_equal(fJA, JA)
+    else:
+        assert fIA[-1] > IA[-1]                                  # fill-in
+    assert np.abs(fval - oval).max() <= 1e-12 * np.abs(oval).max()
+    assert np.abs(fdinv - odinv).max() <= 1e-12 * np.abs(odinv).max()
+    z_ref = F.apply(rr)
+    assert np.abs(z - z_ref).max() <= 1e-11 * np.abs(z_ref).max()
+    assert its > 0
+    x_ref, its_ref = oracle.solver_dbsr_krylov_ilu(IA, JA, val, b, oracle.default_param(ortho_cgs=1), lfil)
+    assert abs(its - its_ref) <= 1, (its, its_ref)
+    assert np.linalg.norm(b - oracle.bsr_spmv(IA, JA, val, du)) <= 1.0001 * it.tol * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("voltage", [-0.3, -0.1, 0.0, 0.1])
+def test_diode_voltage_sweep_with_ilu_matches_oracle(oracle, pkg, gpu_lib, voltage):
+    """BASELINE configs[1] as the reference runs it: the diode's damped Newton with the block ILU(2)-FGMRES of
+    benchmarks/pnp_diode/linear_pnp.cpp:103-109 (bsr.dat: ILUk, lfil 2, maxit 500), bias points of the sweep
+    benchmarks/pnp_diode/main.cpp:96-113. ILU is deterministic (no aggregation choice), so device and oracle
+    build the same preconditioner: same Krylov counts (+-1) while the two paths coincide, same Newton count
+    (+-2 / 15 %: the growth limiter amplifies the 1e-6 linear-solve differences under bias), both converged."""
+    from helpers import GpuNewtonBackend, OracleNewtonBackend, diode_problem
+    P, pr = diode_problem(oracle, 40, 4, 4, voltage)
+    prm = oracle.default_param(maxit=500, ortho_cgs=1)
+
+    class OracleIlu(OracleNewtonBackend):
+        def solve(self):
+            A, b = self.P.assemble(self.uu, self.use_eafe)
+            dx, its = self.O.solver_dbsr_krylov_ilu(self.P.IA, self.P.JA, A, b, self.prm, 2)
+            self.base = self.uu.copy(); self.du = dx
+            return its
+    oracle.set_form_variant(pr.DIODE_POISSON_SCALE, True)
+    try:
+        hist_ref, conv_ref = pr.damped_newton(OracleIlu(oracle, P, prm), P.uu0, max_newton=250)
+    finally:
+        oracle.set_form_variant(1.0, False)
+    g = pkg.PNP(P.xyz, P.cells, 0)
+    g.set_coefficients(P.eps, P.fixed, P.diff, P.val, P.reac)
+    g.set_dirichlet(np.nonzero(P.bcflag)[0].astype(np.int32))
+    g.set_form_variant(pr.DIODE_POISSON_SCALE, True)
+    g.set_preconditioner("ilu", 2)
+    it, amg = pkg.default_params(maxit=500)
+    hist, conv = pr.damped_newton(GpuNewtonBackend(g, it, amg), P.uu0, max_newton=250)
+    g.close()
+    assert conv_ref and conv
+    assert all(h[0] > 0 for h in hist) and all(h[0] > 0 for h in hist_ref)
+    assert abs(len(hist) - len(hist_ref)) <= max(2, 0.15 * len(hist_ref)), (voltage, len(hist), len(hist_ref))
+    assert abs(hist[0][0] - hist_ref[0][0]) <= 1 and hist[0][4] == hist_ref[0][4]
+    assert abs(hist[0][2] - hist_ref[0][2]) <= 1e-6 * hist_ref[0][2]
+    assert hist[-1][2] < 1e-7 or hist[-1][3] < 1e-10

@@ -23,7 +23,17 @@ WORKER = textwrap.dedent('''
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     nx, ny, nz, lx, ly, lz = 6, 3, 7, 2.0, 0.8, 1.6
-    P = part_mod.box_slab_partition(nx, ny, nz, lx, ly, lz, rank, world)
+    MODE = os.environ.get("PNPB200_TEST_PARTITION", "pyslabs")
+    if MODE == "pyslabs":      # the Python reference partitioner (z-slabs)
+        P = part_mod.box_slab_partition(nx, ny, nz, lx, ly, lz, rank, world)
+    elif MODE == "rcb":        # csrc/partition.cpp: recursive coordinate bisection of the global arrays
+        G0 = O.Problem(nx, ny, nz, lx, ly, lz)
+        P = part_mod.mesh_rcb_partition(G0.xyz, G0.cells, rank, world)
+        ixg = np.rint((P["xyz"][0::3] + lx / 2) * nx / lx).astype(np.int64)
+        P["bc_vertices"] = np.nonzero((ixg == 0) | (ixg == nx))[0].astype(np.int32)
+    else:                      # csrc/partition.cpp: bricks in closed form, cut along z / x / y
+        grid = {"slabs": (1, 1, world), "xbricks": (world, 1, 1), "ybricks": (1, world, 1)}[MODE]
+        P = part_mod.box_brick_partition(nx, ny, nz, lx, ly, lz, rank, world, grid=grid)
     n_own, n_loc = P["n_own"], P["n_loc"]
     L = O.lib()
     IA = np.zeros(n_loc + 1, dtype=np.int32)
@@ -74,10 +84,14 @@ WORKER = textwrap.dedent('''
 ''') % ROOT
 
 
-def test_world2_partition_halo_and_distributed_spmv(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("mode", ["pyslabs", "slabs", "xbricks", "ybricks", "rcb"])
+def test_world2_partition_halo_and_distributed_spmv(tmp_path, mode):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", OMP_NUM_THREADS="1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", OMP_NUM_THREADS="1", PNPB200_TEST_PARTITION=mode)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
@@ -108,3 +122,43 @@ def test_partition_colouring_is_proper_and_the_same_on_every_rank(oracle, pkg):
     gcol = np.array([seen[g] for g in range(G.nv)])
     gc = G.cells.reshape(-1, 4)
     assert np.all(np.sort(gcol[gc], axis=1) == np.arange(4)[None, :])
+
+
+def test_cpp_partitioner_covers_the_mesh_exactly_once(oracle, pkg):
+    """pnpb200_partition_box (bricks) and pnpb200_partition_mesh (RCB): every vertex is owned by exactly one
+    rank; every cell appears on every rank that owns one of its vertices and nowhere else; the send list of
+    rank a for rank b is the ghost list of b from a, in the same order (ascending global id)."""
+    import numpy as np
+    from importlib import import_module
+    part_mod = import_module("modular_pnp_b200.partition")
+    nx, ny, nz, lx, ly, lz = 7, 5, 6, 2.0, 1.0, 1.6
+    G = oracle.Problem(nx, ny, nz, lx, ly, lz)
+    gcells = np.sort(G.cells.reshape(-1, 4), axis=1)
+    for world, maker in [(8, lambda r: part_mod.box_brick_partition(nx, ny, nz, lx, ly, lz, r, 8, grid=(2, 2, 2))),
+                         (6, lambda r: part_mod.box_brick_partition(nx, ny, nz, lx, ly, lz, r, 6, grid=(3, 1, 2))),
+                         (5, lambda r: part_mod.mesh_rcb_partition(G.xyz, G.cells, r, 5))]:
+        parts = [maker(r) for r in range(world)]
+        owner = -np.ones(G.nv, dtype=np.int64)
+        for r, P in enumerate(parts):
+            own = P["gids"][:P["n_own"]]
+            assert np.all(np.diff(own) > 0) and np.all(owner[own] == -1)
+            owner[own] = r
+            assert np.allclose(P["xyz"].reshape(-1, 3), G.xyz.reshape(-1, 3)[P["gids"]], rtol=0, atol=1e-15)
+        assert np.all(owner >= 0)
+        sizes = np.bincount(owner, minlength=world)
+        assert sizes.max() <= 1.35 * sizes.mean() + 8              # balanced parts
+        cell_owner_sets = [set(owner[c]) for c in gcells]
+        for r, P in enumerate(parts):
+            lc = P["gids"][P["cells"].reshape(-1, 4)]
+            assert np.all(np.diff(lc, axis=1) > 0)                  # UFC order: ascending global ids
+            expect = np.array([c for c, os_ in zip(gcells, cell_owner_sets) if r in os_])
+            assert sorted(map(tuple, lc)) == sorted(map(tuple, expect))
+            # ghosts grouped by owner (ascending), ascending gid inside; recv ranges tile [n_own, n_loc)
+            assert P["recv_ptr"][0] == P["n_own"] and P["recv_ptr"][-1] == P["n_loc"] and np.all(np.diff(P["nbr"]) > 0)
+            for k, nb in enumerate(P["nbr"]):
+                gh = P["gids"][P["recv_ptr"][k]:P["recv_ptr"][k + 1]]
+                assert np.all(owner[gh] == nb) and np.all(np.diff(gh) > 0)
+                Q = parts[nb]
+                kk = int(np.nonzero(Q["nbr"] == r)[0][0])
+                sent = Q["gids"][Q["send_idx"][Q["send_ptr"][kk]:Q["send_ptr"][kk + 1]]]
+                assert np.array_equal(sent, gh)
