@@ -206,6 +206,10 @@ int  pnpb200_apply_vcycle(pnpb200_handle* h, const double* r, double* z);
  * 6 = block assembly kernel. Needs an assembled system (and a solve for 2/3). */
 int  pnpb200_probe_kernel(pnpb200_handle* h, int which, int reps, double* ms_per_launch,
                           double* algorithmic_bytes);
+/* development aid: run matrix pass `which` (probe numbering: 0, 1, 2, 7..10) of the fine level reps + 1 times from the
+ * same input and compare the results bit by bit; out[18]: [0] repetitions that differed, [1] differing entries of
+ * the first one, [2..16] their sweep-space positions, [17] its index */
+int  pnpb200_debug_repeat_pass(pnpb200_handle* h, int which, int reps, int* out);
 /* y = J x with the assembled fine-level matrix (host vectors) */
 int  pnpb200_apply_matrix(pnpb200_handle* h, const double* x, double* y);
 

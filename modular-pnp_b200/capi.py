@@ -127,6 +127,7 @@ def lib():
     L.pnpb200_num_vertices.argtypes = [H]
     L.pnpb200_num_cells.argtypes = [H]
     L.pnpb200_probe_kernel.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.pnpb200_debug_repeat_pass.argtypes = [H, C.c_int, C.c_int, _i4]
     L.pnpb200_destroy.argtypes = [H]
     L.pnpb200_destroy.restype = None
     L.pnpb200_get_stream.argtypes = [H]
@@ -400,6 +401,11 @@ class PNP:
         ms, by = C.c_double(), C.c_double()
         _check(self.L.pnpb200_probe_kernel(self.h, which, reps, C.byref(ms), C.byref(by)), "probe_kernel")
         return ms.value, by.value
+
+    def debug_repeat_pass(self, which, reps=100):
+        out = np.zeros(18, dtype=np.int32)
+        _check(self.L.pnpb200_debug_repeat_pass(self.h, which, reps, out), "debug_repeat_pass")
+        return out
 
     def close(self):
         if self.h:

@@ -1000,31 +1000,43 @@ constexpr int DENSE_COARSEST_MAX = 1536;
 
 // coarsest level: every rank inverts the (small) GLOBAL coarsest matrix. Returns false if a pivot
 // was zero or not finite (the inverse is unusable).
-bool setup_coarsest(Handle& h)
+// Gather layout of the LAST distributed level Z of hierarchy H (its vectors are packed, row-id order): who owns how
+// many rows, where my rows start in the global numbering, the buffers of the rhs gather; gid = global id
+// of every local row (ghosts from their owners). cnt / off: per-rank row counts and offsets (host).
+void gather_layout(Handle& h, Hierarchy& H, Level& Z, DevBuf<int>& gid, std::vector<int>& cnt, std::vector<int>& off)
 {
   cudaStream_t s = h.stream;
-  Hierarchy& H = h.hier;
-  Level& Z = *H.lv.back();
   const int nr = h.comm.active() ? h.comm.nranks : 1, me = h.comm.active() ? h.comm.rank : 0;
   const int own = owned_rows(Z);
   DevBuf<int> t; t.alloc(nr + 1, s);
   PNP_CUDA(cudaMemcpyAsync(t.p + nr, &own, sizeof(int), cudaMemcpyHostToDevice, s));
   comm_allgather(h, t.p + nr, t.p, sizeof(int));
-  std::vector<int> cnt = t.to_host(nr);
-  std::vector<int> off(nr + 1, 0);
+  cnt = t.to_host(nr);
+  off.assign(nr + 1, 0);
   int maxown = 1;
   for (int r = 0; r < nr; ++r) { off[r + 1] = off[r] + cnt[r]; if (cnt[r] > maxown) maxown = cnt[r]; }
   const int ng = off[nr], nd = 3 * ng;
-  if (nd > DENSE_COARSEST_MAX) throw Error(ERROR_AMG_COARSEING, "coarsest level too large for the dense solver");
   H.nd = nd; H.c_own = own; H.c_row0 = 3 * off[me]; H.c_maxown3 = 3 * maxown; H.c_nranks = nr;
   std::vector<int> off3(nr), cnt3(nr);
   for (int r = 0; r < nr; ++r) { off3[r] = 3 * off[r]; cnt3[r] = 3 * cnt[r]; }
   H.c_off3.alloc(nr, s); H.c_cnt3.alloc(nr, s);
   H.c_off3.upload(off3.data(), nr); H.c_cnt3.upload(cnt3.data(), nr);
-  // global ids of the local rows (ghosts from their owners)
-  DevBuf<int> gid; gid.alloc(Z.A.n > 0 ? Z.A.n : 1, s);
+  gid.alloc(Z.A.n > 0 ? Z.A.n : 1, s);
   if (own > 0) { gid_kernel<<<cdiv(own, 256), 256, 0, s>>>(own, off[me], gid.p); PNP_COUNT_LAUNCH(); }
   halo_exchange_int(h, Z.halo, gid.p);
+  H.c_bpad.alloc((size_t)3 * maxown, s); H.c_ball.alloc((size_t)3 * maxown * nr, s); H.c_bglob.alloc(nd > 0 ? nd : 1, s);
+  PNP_CUDA(cudaStreamSynchronize(s));     // off3 / cnt3 are host temporaries
+}
+
+bool setup_coarsest(Handle& h)
+{
+  cudaStream_t s = h.stream;
+  Hierarchy& H = *h.cur;
+  Level& Z = *H.lv.back();
+  DevBuf<int> gid; std::vector<int> cnt, off;
+  gather_layout(h, H, Z, gid, cnt, off);
+  const int nr = H.c_nranks, own = H.c_own, nd = H.nd, maxown = H.c_maxown3 / 3;
+  if (nd > DENSE_COARSEST_MAX) throw Error(ERROR_AMG_COARSEING, "coarsest level too large for the dense solver");
   // my dense rows, padded to the largest rank, then gathered and compacted
   const size_t rowblk = (size_t)3 * maxown * nd;
   DevBuf<double> Drow, Dall, D, colk; DevBuf<int> sing;
@@ -1044,7 +1056,6 @@ bool setup_coarsest(Handle& h)
   H.dense_inv.alloc((size_t)nd * nd, s);
   identity_kernel<<<cdiv((size_t)nd * nd, 256), 256, 0, s>>>(nd, H.dense_inv.p); PNP_COUNT_LAUNCH();
   dense_invert_kernel<<<1, 1024, 0, s>>>(nd, D.p, H.dense_inv.p, colk.p, sing.p); PNP_COUNT_LAUNCH();
-  H.c_bpad.alloc((size_t)3 * maxown, s); H.c_ball.alloc((size_t)3 * maxown * nr, s); H.c_bglob.alloc(nd, s);
   int hsing = 0;
   PNP_CUDA(cudaMemcpyAsync(&hsing, sing.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   PNP_CUDA(cudaStreamSynchronize(s));     // host staging vectors above go out of scope
@@ -1072,39 +1083,190 @@ void solve_coarsest_sweeps(Handle& h, Level& Z, const double* b, double* x, int 
   }
 }
 
+// the rhs of the last distributed level (packed, row-id order) on every rank: H.c_bglob (or b itself on one GPU)
+const double* gather_rhs(Handle& h, Hierarchy& H, const double* b)
+{
+  cudaStream_t s = h.stream;
+  if (H.c_nranks <= 1) return b;
+  PNP_CUDA(cudaMemsetAsync(H.c_bpad.p, 0, (size_t)H.c_maxown3 * sizeof(double), s));
+  if (H.c_own > 0) PNP_CUDA(cudaMemcpyAsync(H.c_bpad.p, b, (size_t)3 * H.c_own * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  comm_allgather(h, H.c_bpad.p, H.c_ball.p, (size_t)H.c_maxown3 * sizeof(double));
+  compact_b_kernel<<<cdiv((size_t)H.c_nranks * H.c_maxown3, 256), 256, 0, s>>>(H.c_nranks, H.c_maxown3, H.c_off3.p, H.c_cnt3.p,
+                                                                              H.c_ball.p, H.c_bglob.p);
+  PNP_COUNT_LAUNCH();
+  return H.c_bglob.p;
+}
+
 void solve_coarsest(Handle& h, const double* b, double* x)
 {
   cudaStream_t s = h.stream;
-  Hierarchy& H = h.hier;
-  const double* bg = b;
-  if (H.c_nranks > 1) {
-    PNP_CUDA(cudaMemsetAsync(H.c_bpad.p, 0, (size_t)H.c_maxown3 * sizeof(double), s));
-    if (H.c_own > 0) PNP_CUDA(cudaMemcpyAsync(H.c_bpad.p, b, (size_t)3 * H.c_own * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    comm_allgather(h, H.c_bpad.p, H.c_ball.p, (size_t)H.c_maxown3 * sizeof(double));
-    compact_b_kernel<<<cdiv((size_t)H.c_nranks * H.c_maxown3, 256), 256, 0, s>>>(H.c_nranks, H.c_maxown3, H.c_off3.p, H.c_cnt3.p,
-                                                                                H.c_ball.p, H.c_bglob.p);
-    PNP_COUNT_LAUNCH();
-    bg = H.c_bglob.p;
-  }
+  Hierarchy& H = *h.cur;
+  const double* bg = gather_rhs(h, H, b);
   if (H.c_own > 0) {
     dense_matvec_rows_kernel<<<cdiv((size_t)3 * H.c_own * 32, 256), 256, 0, s>>>(3 * H.c_own, H.c_row0, H.nd, H.dense_inv.p, bg, x);
     PNP_COUNT_LAUNCH();
   }
 }
 
-} // namespace
+// ---- replicated coarse hierarchy (multi-GPU) ----------------------------------------
+// Below REPLICATE_ROWS global block rows a level is all latency: a distributed visit costs 3 halo
+// exchanges + 2 all-reduces of ~20 us each, and the K-cycle visits level l 2^(l-1) times per Krylov
+// iteration. So the first level that small is gathered to EVERY rank (one all-gather of its matrix per
+// setup, one all-gather of its rhs per visit) and everything below it — coarsening, colouring, cycle,
+// coarsest solve — runs redundantly with the single-GPU code, aggregates no longer confined to a rank.
+constexpr int REPLICATE_ROWS = 40000;
 
-void amg_setup(Handle& h, const SolverConfig& cfg)
+__global__ void rep_rowlen_kernel(int own, const int* __restrict__ ia, int* __restrict__ len)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < own) len[i] = ia[i + 1] - ia[i];
+}
+__global__ void rep_gid_cols_kernel(int nnz, const int* __restrict__ ja_nat, const int* __restrict__ gid, int* __restrict__ out)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) out[p] = gid[ja_nat[p]];
+}
+
+// ascending columns inside every row of a FASP-layout BSR(3) matrix (the local -> global renaming of the ghost
+// columns breaks the order the layout code relies on); one thread per row, insertion sort, rows are short
+__global__ void rep_sort_rows_kernel(int n, const int* __restrict__ ia, int* __restrict__ ja, double* __restrict__ val)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = ia[i], e = ia[i + 1];
+  for (int a = s + 1; a < e; ++a) {
+    const int key = ja[a];
+    double v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = val[9 * (size_t)a + t];
+    int b = a - 1;
+    while (b >= s && ja[b] > key) {
+      ja[b + 1] = ja[b];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) val[9 * (size_t)(b + 1) + t] = val[9 * (size_t)b + t];
+      --b;
+    }
+    ja[b + 1] = key;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) val[9 * (size_t)(b + 1) + t] = v[t];
+  }
+}
+
+void amg_setup_chain(Handle& h, Hierarchy& H, const SolverConfig& cfg);
+
+// gather the last distributed level Z of h.hier into h.hier_rep.lv[0] on every rank and build the hierarchy below it
+void setup_replicated(Handle& h, const SolverConfig& cfg, int level_index)
 {
   cudaStream_t s = h.stream;
-  auto& lv = h.hier.lv;
+  Hierarchy& H = h.hier; Hierarchy& R = h.hier_rep;
+  Level& Z = *H.lv.back();
+  DevBuf<int> gid; std::vector<int> cnt, off;
+  gather_layout(h, H, Z, gid, cnt, off);
+  const int nr = H.c_nranks, own = H.c_own, maxown = H.c_maxown3 / 3, ng = off[nr];
+  // natural (FASP) form of my owned rows with GLOBAL column ids
+  const BsrT& A = Z.A;
+  DevBuf<int> ja_nat, iah; ja_nat.alloc(A.nnzb, s);
+  bsrt_export_ja(A, ja_nat.p, s);
+  std::vector<int> ia = A.ia.to_host(A.n + 1);
+  const int mynnz = ia[own];
+  DevBuf<int> t; t.alloc(nr + 1, s);
+  PNP_CUDA(cudaMemcpyAsync(t.p + nr, &mynnz, sizeof(int), cudaMemcpyHostToDevice, s));
+  comm_allgather(h, t.p + nr, t.p, sizeof(int));
+  std::vector<int> nnz = t.to_host(nr);
+  int maxnnz = 1; std::vector<int> nzoff(nr + 1, 0);
+  for (int r = 0; r < nr; ++r) { nzoff[r + 1] = nzoff[r] + nnz[r]; if (nnz[r] > maxnnz) maxnnz = nnz[r]; }
+  DevBuf<double> vf; vf.alloc(9 * (size_t)A.nnzb, s);
+  bsrt_to_fasp(A, vf.p, s);
+  DevBuf<int> lenp, lena, jap, jaa; DevBuf<double> valp, vala;
+  lenp.alloc(maxown, s); lenp.zero(); lena.alloc((size_t)maxown * nr, s);
+  jap.alloc(maxnnz, s); jap.zero(); jaa.alloc((size_t)maxnnz * nr, s);
+  valp.alloc(9 * (size_t)maxnnz, s); vala.alloc(9 * (size_t)maxnnz * nr, s);
+  if (own > 0) { rep_rowlen_kernel<<<cdiv(own, 256), 256, 0, s>>>(own, A.ia.p, lenp.p); PNP_COUNT_LAUNCH(); }
+  if (mynnz > 0) {
+    rep_gid_cols_kernel<<<cdiv(mynnz, 256), 256, 0, s>>>(mynnz, ja_nat.p, gid.p, jap.p); PNP_COUNT_LAUNCH();
+    PNP_CUDA(cudaMemcpyAsync(valp.p, vf.p, 9 * (size_t)mynnz * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  comm_allgather(h, lenp.p, lena.p, (size_t)maxown * sizeof(int));
+  comm_allgather(h, jap.p, jaa.p, (size_t)maxnnz * sizeof(int));
+  comm_allgather(h, valp.p, vala.p, 9 * (size_t)maxnnz * sizeof(double));
+  // the global matrix: row offsets on the host (tiny), columns and values compacted rank by rank
+  std::vector<int> la = lena.to_host((size_t)maxown * nr);
+  std::vector<int> gia(ng + 1, 0);
+  for (int r = 0; r < nr; ++r) for (int i = 0; i < cnt[r]; ++i) gia[off[r] + i + 1] = la[(size_t)r * maxown + i];
+  for (int i = 0; i < ng; ++i) gia[i + 1] += gia[i];
+  if (gia[ng] != nzoff[nr]) throw Error(ERROR_DATA_STRUCTURE, "replicated level: row lengths and block counts disagree");
+  if (R.lv.empty()) R.lv.emplace_back(new Level);
+  Level& R0 = *R.lv[0];
+  R0.n_own = -1; R0.halo = Halo(); R0.preset_ncolors = 0;
+  BsrT& G = R0.A;
+  G.n = ng; G.nnzb = gia[ng];
+  G.ia.alloc(ng + 1, s); G.ia.upload(gia.data(), ng + 1);
+  G.val.alloc(9 * (size_t)G.nnzb, s);
+  DevBuf<int> gja; gja.alloc(G.nnzb, s);
+  DevBuf<double> gval; gval.alloc(9 * (size_t)G.nnzb, s);
+  for (int r = 0; r < nr; ++r)
+    if (nnz[r] > 0) {
+      PNP_CUDA(cudaMemcpyAsync(gja.p + nzoff[r], jaa.p + (size_t)r * maxnnz, (size_t)nnz[r] * sizeof(int), cudaMemcpyDeviceToDevice, s));
+      PNP_CUDA(cudaMemcpyAsync(gval.p + 9 * (size_t)nzoff[r], vala.p + 9 * (size_t)r * maxnnz, 9 * (size_t)nnz[r] * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
+  rep_sort_rows_kernel<<<cdiv(ng, 128), 128, 0, s>>>(ng, G.ia.p, gja.p, gval.p); PNP_COUNT_LAUNCH();
+  PNP_CUDA(cudaStreamSynchronize(s));     // gia is a host temporary
+  // from here on this rank works alone: same code as one GPU
+  h.comm.suspended = true;
+  Hierarchy* save = h.cur;
+  try {
+    h.cur = &R;
+    color_and_layout(R0, gja.p, nullptr, s);
+    bsrt_from_fasp(gval.p, G, s);
+    R.level_offset = level_index;
+    R.symbolic_valid = false;
+    amg_setup_chain(h, R, cfg);
+  } catch (...) { h.cur = save; h.comm.suspended = false; throw; }
+  h.cur = save; h.comm.suspended = false;
+  H.c_xglob.alloc(3 * (size_t)ng, s);
+}
+
+void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x);
+
+// x = approximate solution of the last distributed level's system, computed redundantly on the replicated hierarchy
+void solve_replicated(Handle& h, const SolverConfig& cfg, const double* b, double* x)
+{
+  cudaStream_t s = h.stream;
+  Hierarchy& H = h.hier; Hierarchy& R = h.hier_rep;
+  Level& R0 = *R.lv[0];
+  const double* bg = gather_rhs(h, H, b);
+  const bool single = R.lv.size() == 1 && R.coarse_dense;      // the gathered level is itself the coarsest: dense solve, row-id vectors
+  if (!single) vec_to_sweep(R0.A, bg, R0.b.p, s);
+  h.comm.suspended = true;
+  Hierarchy* save = h.cur;
+  try {
+    h.cur = &R;
+    if (single) solve_level(h, cfg, 0, bg, H.c_xglob.p);
+    else solve_level(h, cfg, 0, R0.b.p, R0.x.p);
+  } catch (...) { h.cur = save; h.comm.suspended = false; throw; }
+  h.cur = save; h.comm.suspended = false;
+  if (!single) vec_from_sweep(R0.A, R0.x.p, H.c_xglob.p, s);
+  if (H.c_own > 0) PNP_CUDA(cudaMemcpyAsync(x, H.c_xglob.p + H.c_row0, (size_t)3 * H.c_own * sizeof(double), cudaMemcpyDeviceToDevice, s));
+}
+
+} // namespace
+
+namespace {
+// build (or, with hierarchy reuse, refresh) the levels of H below its level 0. H is h.hier, or the replicated
+// coarse hierarchy of a multi-GPU run (then the communicator is suspended and H.level_offset > 0).
+void amg_setup_chain(Handle& h, Hierarchy& H, const SolverConfig& cfg)
+{
+  cudaStream_t s = h.stream;
+  auto& lv = H.lv;
   Level& F = *lv[0];
-  const bool reuse = h.reuse_hierarchy && h.hier.symbolic_valid;
+  const bool reuse = h.reuse_hierarchy && H.symbolic_valid;
   if (F.ncolors == 0) throw Error(ERROR_DATA_STRUCTURE, "fine level not coloured");   // done at create / upload
   alloc_level_vectors(F, s);
-  if (!reuse) h.hier.symbolic_valid = false;
-  h.hier.drop_coarse_graph();           // buffers and launch sizes belong to the hierarchy being replaced
+  if (!reuse) H.symbolic_valid = false;
+  H.drop_coarse_graph();           // buffers and launch sizes belong to the hierarchy being replaced
   const int min_cdof = cfg.coarse_dof > 50 ? cfg.coarse_dof : 50;
+  static const int rep_rows = getenv("PNPB200_REPLICATE_ROWS") ? atoi(getenv("PNPB200_REPLICATE_ROWS")) : REPLICATE_ROWS;
+  bool replicate = reuse ? H.coarse_rep : false;
   int l = 0;
   while (true) {
     Level& L = *lv[l];
@@ -1118,37 +1280,42 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
     // same number of levels (each level of the cycle is a collective)
     int nglob, nmin;
     global_rows(h, owned_rows(L), &nglob, &nmin);
-    if (!(nglob > min_cdof && l < cfg.max_levels - 1)) break;
+    if (!(nglob > min_cdof && l + H.level_offset < cfg.max_levels - 1)) break;
+    if (h.comm.active() && l >= 1 && nglob <= rep_rows) { replicate = true; break; }     // small enough: every rank takes the whole level
     if (h.comm.active() && nmin < 8) break;
-    const double theta = cfg.tentative_smooth > 1e-20 ? cfg.strong_coupled * std::pow(0.5, l) : cfg.strong_coupled;
+    const double theta = cfg.tentative_smooth > 1e-20 ? cfg.strong_coupled * std::pow(0.5, l + H.level_offset) : cfg.strong_coupled;
     // Level objects (and their device buffers) are recycled from the previous hierarchy
     if (l + 1 >= (int)lv.size()) lv.emplace_back(new Level);
     Level& C = *lv[l + 1];
-    g_phase = cfg.print_level >= 3; g_phase_lvl = l;
+    g_phase = cfg.print_level >= 3; g_phase_lvl = l + H.level_offset;
     if (!coarsen_symbolic(h, L, C, theta)) break;
     { PHASE("rap_numeric"); rap_numeric(h, L, C); }
     alloc_level_vectors(C, s);
     ++l;
   }
   if (!reuse) lv.resize(l + 1);
-  // coarsest level: explicit dense inverse when it is small (the bsr.dat case, <= coarse_dof rows),
-  // Gauss-Seidel sweeps when coarsening stopped early or a pivot of the inverse was unusable
-  {
+  // last level: replicated coarse hierarchy (multi-GPU), explicit dense inverse when it is small (the bsr.dat
+  // case, <= coarse_dof rows), Gauss-Seidel sweeps when coarsening stopped early or a pivot was unusable
+  if (replicate) {
+    H.coarse_rep = true; H.coarse_dense = false;
+    setup_replicated(h, cfg, (int)lv.size() - 1 + H.level_offset);
+  } else {
+    H.coarse_rep = false;
     int nglob, nmin;
     global_rows(h, owned_rows(*lv.back()), &nglob, &nmin);
     bool dense = 3 * (long)nglob <= DENSE_COARSEST_MAX;
-    if (reuse && dense != h.hier.coarse_dense) throw Error(ERROR_SOLVER_MISC, "coarsest level changed its solver under hierarchy reuse");
+    if (reuse && dense != H.coarse_dense) throw Error(ERROR_SOLVER_MISC, "coarsest level changed its solver under hierarchy reuse");
     if (dense && !setup_coarsest(h)) {
       if (reuse) throw Error(ERROR_SOLVER_MISC, "coarsest level is singular");
       dense = false;
     }
-    h.hier.coarse_dense = dense;
+    H.coarse_dense = dense;
   }
   if (!reuse) {
-    // grid transfer maps in sweep space; a coarsest level with the dense solve keeps row-id order
+    // grid transfer maps in sweep space; a last level with the dense or the replicated solve keeps row-id order
     for (int k = 0; k + 1 < (int)lv.size(); ++k) {
       Level& Lk = *lv[k]; Level& Ck = *lv[k + 1];
-      Lk.coarse_identity = (k + 2 == (int)lv.size()) && h.hier.coarse_dense;
+      Lk.coarse_identity = (k + 2 == (int)lv.size()) && (H.coarse_dense || H.coarse_rep);
       const int nk = Lk.A.n;
       Lk.agg_pos.alloc(nk, s); Lk.agg_rows_pos.alloc(nk, s);
       transfer_maps_kernel<<<cdiv(nk, 256), 256, 0, s>>>(nk, Lk.A.vrowid.p, Lk.A.pos.p, Lk.agg.p, Lk.agg_rows.p,
@@ -1156,13 +1323,21 @@ void amg_setup(Handle& h, const SolverConfig& cfg)
       PNP_COUNT_LAUNCH();
     }
   }
-  h.hier.symbolic_valid = true;
+  H.symbolic_valid = true;
   if (cfg.print_level > 0) {
     PNP_CUDA(cudaStreamSynchronize(s));
     for (size_t k = 0; k < lv.size(); ++k)
-      printf("  [pnpb200 amg] rank %d level %zu: rows %d (owned %d) nnzb %d colours %d\n", h.comm.rank, k, lv[k]->A.n, owned_rows(*lv[k]),
-             lv[k]->A.nnzb, lv[k]->ncolors);
+      printf("  [pnpb200 amg] rank %d level %zu%s: rows %d (owned %d) nnzb %d colours %d\n", h.comm.rank, k + H.level_offset,
+             H.level_offset ? " (replicated)" : "", lv[k]->A.n, owned_rows(*lv[k]), lv[k]->A.nnzb, lv[k]->ncolors);
   }
+}
+} // namespace
+
+void amg_setup(Handle& h, const SolverConfig& cfg)
+{
+  h.cur = &h.hier;
+  h.hier.level_offset = 0;
+  amg_setup_chain(h, h.hier, cfg);
 }
 
 namespace {
@@ -1195,7 +1370,7 @@ bool coarse_graph_dist()
 }
 void coarse_solve_graphed(Handle& h, const SolverConfig& cfg, int l)
 {
-  Hierarchy& H = h.hier;
+  Hierarchy& H = *h.cur;
   Level& C = *H.lv[l];
   cudaStream_t s = h.stream;
   const unsigned sig = hash32((unsigned)cfg.cycle_type * 7919u + (unsigned)cfg.kcycle_levels * 104729u + (unsigned)cfg.presmooth * 31u +
@@ -1233,13 +1408,18 @@ void coarse_solve_graphed(Handle& h, const SolverConfig& cfg, int l)
 bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x, double* Ax, int bs = VS, int axs = VS)
 {
   cudaStream_t s = h.stream;
-  Level& L = *h.hier.lv[l];
-  Level& C = *h.hier.lv[l + 1];
+  Hierarchy& H = *h.cur;
+  Level& L = *H.lv[l];
+  Level& C = *H.lv[l + 1];
   const size_t m = VS * (size_t)L.A.n;
   const int own = owned_rows(L);
   const bool dist = h.comm.active();
   if (cfg.presmooth == 1 && h.sweep_shortcuts) {
     if (m > VS * (size_t)own) PNP_CUDA(cudaMemsetAsync(x + VS * (size_t)own, 0, (m - VS * (size_t)own) * sizeof(double), s));
+    // debugging aid: the forward sweep from zero must never read an entry it has not written yet; PNPB200_POISON=1
+    // fills the owned part with NaN bit patterns first, so that such a read surfaces as a failed solve
+    static const bool poison = getenv("PNPB200_POISON") && atoi(getenv("PNPB200_POISON"));
+    if (poison && own > 0) PNP_CUDA(cudaMemsetAsync(x, 0xff, VS * (size_t)own * sizeof(double), s));
     mcgs_sweep_from_zero(L, b, x, s, bs);
     if (dist) halo_exchange(h, L.halo, x, true);
     bsrt_residual_after_sweep(L, b, x, L.w.p, s, bs);
@@ -1254,7 +1434,8 @@ bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double
     else restrict_kernel<VS><<<cdiv(VS * (size_t)L.nagg, 256), 256, 0, s>>>(L.nagg, C.A.vrowid.p, L.agg_ptr.p, L.agg_rows_pos.p, L.w.p, C.b.p);
     PNP_COUNT_LAUNCH();
   }
-  if (l + 1 == coarse_graph_level() && l + 1 >= 1 && l + 2 < (int)h.hier.lv.size() && (!dist || coarse_graph_dist()) && !g_debug_sync) coarse_solve_graphed(h, cfg, l + 1);
+  // (levels are counted globally: the replicated coarse hierarchy of a multi-GPU run continues the numbering)
+  if (l + 1 + H.level_offset == coarse_graph_level() && l + 1 >= 1 && (l + 2 < (int)H.lv.size() || H.coarse_rep) && (!dist || coarse_graph_dist()) && !g_debug_sync) coarse_solve_graphed(h, cfg, l + 1);
   else solve_level(h, cfg, l + 1, C.b.p, C.x.p);
   if (own > 0) {
     if (L.coarse_identity) prolong_kernel<3><<<cdiv(VS * (size_t)own, 256), 256, 0, s>>>(own, L.agg_pos.p, C.x.p, x);
@@ -1280,10 +1461,16 @@ bool mg_cycle(Handle& h, const SolverConfig& cfg, int l, const double* b, double
 void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, double* x)
 {
   cudaStream_t s = h.stream;
-  const int nl = (int)h.hier.lv.size();
-  Level& L = *h.hier.lv[l];
-  if (l == nl - 1) { if (h.hier.coarse_dense) solve_coarsest(h, b, x); else solve_coarsest_sweeps(h, L, b, x); return; }
-  const bool kcyc = cfg.cycle_type != V_CYCLE && l <= cfg.kcycle_levels;
+  Hierarchy& H = *h.cur;
+  const int nl = (int)H.lv.size();
+  Level& L = *H.lv[l];
+  if (l == nl - 1) {
+    if (H.coarse_rep) solve_replicated(h, cfg, b, x);
+    else if (H.coarse_dense) solve_coarsest(h, b, x);
+    else solve_coarsest_sweeps(h, L, b, x);
+    return;
+  }
+  const bool kcyc = cfg.cycle_type != V_CYCLE && l + H.level_offset >= 1 && l + H.level_offset <= cfg.kcycle_levels;
   if (!kcyc) { mg_cycle(h, cfg, l, b, x, nullptr); return; }
   // K-cycle: two GCR steps preconditioned by the cycle of this level (device scalars only;
   // multi-GPU: the dot products run over the owned rows and are summed with ncclAllReduce)
@@ -1318,6 +1505,7 @@ void solve_level(Handle& h, const SolverConfig& cfg, int l, const double* b, dou
 bool amg_vcycle(Handle& h, const SolverConfig& cfg, const double* r, double* z, double* Az, int rs, int azs)
 {
   cudaStream_t s = h.stream;
+  h.cur = &h.hier;
   auto& lv = h.hier.lv;
   const int nl = (int)lv.size();
   if (nl == 1) {       // no coarse grid at all: the "cycle" is the coarsest-level solve on the fine matrix

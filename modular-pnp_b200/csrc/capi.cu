@@ -666,9 +666,13 @@ int pnpb200_get_stats(const pnpb200_handle* ph, pnpb200_stats* st)
   if (!ph || !st) return ERROR_INPUT_PAR;
   const Handle& h = ph->h;
   memset(st, 0, sizeof(*st));
-  st->n_levels = (int)h.hier.lv.size();
-  for (int l = 0; l < st->n_levels && l < 32; ++l) {
-    st->level_rows[l] = h.hier.lv[l]->A.n; st->level_nnzb[l] = h.hier.lv[l]->A.nnzb; st->level_colors[l] = h.hier.lv[l]->ncolors;
+  // multi-GPU: the last distributed level is continued by the replicated coarse hierarchy (global sizes from there on)
+  std::vector<const Level*> lv;
+  for (size_t l = 0; l < h.hier.lv.size(); ++l) lv.push_back(h.hier.lv[l].get());
+  if (h.hier.coarse_rep && !h.hier_rep.lv.empty()) { lv.pop_back(); for (auto& p : h.hier_rep.lv) lv.push_back(p.get()); }
+  st->n_levels = (int)std::min<size_t>(lv.size(), 32);
+  for (int l = 0; l < st->n_levels; ++l) {
+    st->level_rows[l] = lv[l]->A.n; st->level_nnzb[l] = lv[l]->A.nnzb; st->level_colors[l] = lv[l]->ncolors;
   }
   st->krylov_its = h.stats.krylov_its; st->launches = (int)h.stats.launches;
   st->ms_assemble = h.stats.ms_assemble; st->ms_setup = h.stats.ms_setup; st->ms_krylov = h.stats.ms_krylov;
@@ -779,6 +783,78 @@ int pnpb200_probe_kernel(pnpb200_handle* ph, int which_in, int reps, double* ms_
     float ms = 0; PNP_CUDA(cudaEventElapsedTime(&ms, h.ev[2], h.ev[3]));
     if (ms_per_launch) *ms_per_launch = ms / reps;
     if (algorithmic_bytes) *algorithmic_bytes = bytes;
+    return FASP_SUCCESS;
+  });
+}
+
+namespace {
+// deterministic pseudo-random fill of a sweep-space vector (pad entries zero)
+__global__ void repro_fill_kernel(size_t n, unsigned seed, double* __restrict__ v)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned hsh = hash32((unsigned)i * 2654435761u + seed);
+  v[i] = (i & 3) == 3 ? 0.0 : (double)hsh / 4294967296.0 - 0.5;
+}
+// bitwise comparison; out[0] = number of differing entries, out[1 + k] = position of the k-th one seen (k < 15)
+__global__ void repro_compare_kernel(size_t n, const double* __restrict__ a, const double* __restrict__ b, int* __restrict__ out)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (__double_as_longlong(a[i]) != __double_as_longlong(b[i])) {
+    const int k = atomicAdd(out, 1);
+    if (k < 15) out[1 + k] = (int)i;
+  }
+}
+}
+
+// Reproducibility check of one matrix pass (the probe numbering): the pass runs once for the reference result and
+// then `reps` more times from the SAME input state; every result is compared bit by bit on the device.
+// out[0] = repetitions that differed, out[1] = differing entries of the first such repetition, out[2..16] = their
+// positions (sweep-space entry index), out[17] = that repetition's index.
+int pnpb200_debug_repeat_pass(pnpb200_handle* ph, int which, int reps, int* out)
+{
+  if (!ph || reps < 1 || !out) return ERROR_INPUT_PAR;
+  return guarded([&]() -> int {
+    Handle& h = ph->h; cudaStream_t s = h.stream;
+    PNP_CUDA(cudaSetDevice(h.device));
+    Level& L = *h.hier.lv[0];
+    const BsrT& A = L.A;
+    const size_t NS = VS * (size_t)A.n;
+    if (L.ncolors == 0 || L.dinv.n < 9 * (size_t)A.n) throw Error(ERROR_INPUT_PAR, "needs a solve first");
+    DevBuf<double> x, y, b, yref, xref; DevBuf<int> cmp;
+    x.alloc(NS, s); y.alloc(NS, s); b.alloc(NS, s); yref.alloc(NS, s); xref.alloc(NS, s); cmp.alloc(16, s);
+    const int g = (int)cdiv(NS, 256);
+    repro_fill_kernel<<<g, 256, 0, s>>>(NS, 77u, b.p);
+    auto run = [&]() {
+      repro_fill_kernel<<<g, 256, 0, s>>>(NS, 1u, x.p);
+      repro_fill_kernel<<<g, 256, 0, s>>>(NS, 2u, y.p);
+      switch (which) {
+        case 0: bsrt_spmv(A, x.p, y.p, s); break;
+        case 1: bsrt_residual(A, b.p, x.p, y.p, s); break;
+        case 2: mcgs_sweep(L, b.p, y.p, false, s); break;
+        case 12: mcgs_sweep(L, b.p, y.p, true, s); break;
+        case 7: mcgs_sweep_from_zero(L, b.p, y.p, s); break;
+        case 8: bsrt_residual_after_sweep(L, b.p, x.p, y.p, s); break;
+        case 9: mcgs_sweep_back_delta(L, b.p, y.p, x.p, s); break;
+        case 10: bsrt_apply_after_sweep(L, b.p, x.p, y.p, s); break;
+        default: throw Error(ERROR_INPUT_PAR, "unknown pass");
+      }
+    };
+    run();
+    vec_copy(yref.p, y.p, NS, s); vec_copy(xref.p, x.p, NS, s);
+    for (int k = 0; k < 18; ++k) out[k] = 0;
+    for (int r = 0; r < reps; ++r) {
+      run();
+      cmp.zero();
+      repro_compare_kernel<<<g, 256, 0, s>>>(NS, y.p, yref.p, cmp.p);
+      repro_compare_kernel<<<g, 256, 0, s>>>(NS, x.p, xref.p, cmp.p);
+      int hc[16]; cmp.download(hc, 16);
+      if (hc[0] != 0) {
+        if (out[0] == 0) { out[1] = hc[0]; for (int k = 0; k < 15; ++k) out[2 + k] = hc[1 + k]; out[17] = r; }
+        ++out[0];
+      }
+    }
     return FASP_SUCCESS;
   });
 }

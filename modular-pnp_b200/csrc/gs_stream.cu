@@ -189,9 +189,6 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
       a1 = v[3 * sv] * x0 + v[4 * sv] * x1 + v[5 * sv] * x2;
       a2 = v[6 * sv] * x0 + v[7 * sv] * x1 + v[8 * sv] * x2;
     }
-    // the shared-memory reads of this half-warp are done (their results feed a0..a2, dq): hand the slot back
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[stage]);
     const double a = half_sum3(a0, a1, a2, lane);
     if (!SMOOTH) {
       if (row >= 0 && ii == 0 && cc < ys) {        // cc == 3 (padded y): a == 0 and bq == 0, the pad entry stays zero
@@ -211,6 +208,14 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
         y[o] = part;
       }
     }
+    // Hand the slot back only HERE, after the stores that consumed every value read from it, and behind a
+    // generic -> async proxy fence. Releasing right after the shared-memory loads were ISSUED (round-2 first cut)
+    // let the producer's next bulk copy overwrite the stage while a load was still in flight: about one colour
+    // launch in a hundred computed one row from the next chunk's numbers (caught as Krylov counts that changed
+    // from run to run; tests/test_gpu_solver.py::test_streamed_passes_are_reproducible). No measurable cost.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
   }
 }
 

@@ -110,6 +110,9 @@ struct Hierarchy {
   DevBuf<double> c_bpad, c_ball, c_bglob;
   bool symbolic_valid = false;
   bool coarse_dense = true;     // coarsest level: explicit dense inverse (else Gauss-Seidel sweeps, amg.cu)
+  bool coarse_rep = false;      // multi-GPU: the last level is gathered to every rank and continued by Handle::hier_rep
+  int level_offset = 0;         // global index of lv[0] (> 0 for the replicated coarse hierarchy)
+  DevBuf<double> c_xglob;       // replicated solve: the gathered level's solution, row-id order
   // CUDA graph of the coarse part of a cycle (everything below level COARSE_GRAPH_LEVEL, amg.cu):
   // the K-cycle visits those levels several times per Krylov iteration with ~200 launches of
   // microsecond kernels each; captured once per hierarchy, replayed with one cudaGraphLaunch
@@ -156,7 +159,8 @@ struct StreamOwner {
 struct Comm {
   void* nccl = nullptr;
   int rank = 0, nranks = 1;
-  bool active() const { return nccl != nullptr && nranks > 1; }
+  bool suspended = false;       // inside the replicated coarse hierarchy every rank works alone
+  bool active() const { return nccl != nullptr && nranks > 1 && !suspended; }
   ~Comm();
 };
 
@@ -200,6 +204,8 @@ struct Handle {
   bool eta_valid = false;
   // solver
   Hierarchy hier;
+  Hierarchy hier_rep;           // multi-GPU: the small coarse levels, replicated on every rank (amg.cu: setup_replicated)
+  Hierarchy* cur = &hier;       // the hierarchy the cycle / setup helpers of amg.cu are working on
   Krylov kry;
   IluFactor ilu;
   int precond = 0, precond_lfil = 2;   // pnpb200_set_preconditioner: 0 = AMG (bsr.dat), 1 = block ILU(k) (pnp_diode/bsr.dat)

@@ -339,6 +339,31 @@ def test_streamed_colour_launch_is_the_same_arithmetic(oracle, pkg, system):
     assert np.array_equal(out[1][1], out[0][1])
 
 
+def test_streamed_passes_are_reproducible(pkg):
+    """Every fine-level matrix pass, repeated from the same input, must give the same bits. The first cut of the
+    streamed kernel released a shared-memory stage right after ISSUING its loads; about one colour launch in a
+    hundred then took a row's numbers from the next chunk (seen as Krylov counts that changed from run to run:
+    21 -> 30 on a 64^3 box). 64^3 = 274 625 rows, every colour launch on the streamed path."""
+    from importlib import import_module
+    prob = import_module("modular_pnp_b200.problems")
+    n = 64
+    g = pkg.PNP(box=(n, n, n, 2.0, 2.0, 2.0))
+    try:
+        f = prob.exact_solution_problem(n, n, n, 2.0, 2.0, 2.0)
+        g.set_coefficients(f["eps"], f["fixed"], f["diff"], f["val"], f["reac"]); g.set_dirichlet(f["bc_dofs"])
+        it, amg = pkg.default_params(cycle_type=4)
+        its = set()
+        for _ in range(25):
+            g.set_solution(f["uu0"])
+            its.add(g.newton_step(it, amg))
+        assert len(its) == 1, its                    # Krylov count and both residual norms, bit for bit
+        for which in (9, 12, 2, 7, 0, 1, 8, 10):     # GS + delta (back), GS back / forward, forward from zero, y = A x, r = b - A x, -U x, b + L x
+            out = g.debug_repeat_pass(which, 150)
+            assert out[0] == 0, (which, out.tolist())
+    finally:
+        g.close()
+
+
 @pytest.mark.parametrize("lfil", [0, 1, 2])
 def test_block_ilu_factors_and_apply_match_oracle(oracle, pkg, system, lfil):
     """csrc/ilu.cu vs oracle/ilu_restated.cpp (block ILU(k) of benchmarks/pnp_diode/bsr.dat:34-38): identical
