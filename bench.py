@@ -438,7 +438,7 @@ def main():
     # roofline of the dominant kernel. profiles/README.md (ncu launch list): the multicolour
     # Gauss-Seidel colour launches are the largest share of the device time. One "launch" of the
     # roofline line = one full backward sweep over the fine-level matrix as the cycle runs it
-    # (bsrt_row_kernel<M_GSD>: all colour launches, also writes delta = x_new - x_old), timed live
+    # (gs_stream_kernel<S_GSD>: all colour launches, also writes delta = x_new - x_old), timed live
     # with CUDA events on the library's stream. The other passes of a cycle are listed next to it.
     peak, peak_src = peaks()
     spmv_ms, spmv_bytes = g.probe_kernel(0, 20)
@@ -463,8 +463,8 @@ def main():
     # traffic: dram bytes of one sweep (dram__bytes_read.sum + dram__bytes_write.sum over its colour
     # launches) from the committed single-pass ncu capture taken at the same n (tools/ncu_traffic.sh)
     traffic, traffic_note = None, None
-    for tp in (os.path.join(ROOT, "profiles", "r01_traffic_gsd_n%d.json" % n), os.path.join(ROOT, "profiles", "r01_traffic_gsd_n256.json"),
-               os.path.join(ROOT, "profiles", "r01_traffic_ldu_n128.json")):
+    for tp in (os.path.join(ROOT, "profiles", "r02_traffic_gsd_n%d.json" % n), os.path.join(ROOT, "profiles", "r02_traffic_gsd_n256.json"),
+               os.path.join(ROOT, "profiles", "r01_traffic_gsd_n256.json")):
         if not os.path.exists(tp):
             continue
         try:
@@ -492,7 +492,7 @@ def main():
         e2e_v = units * K / (ms_e2e / 1e3)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
-               "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=part_desc + ("" if world == 1 else ": NCCL halo exchange at every AMG level + fp64 allreduce, aggregates local to a rank, replicated dense coarsest solve"),
+               "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=part_desc + ("" if world == 1 else ": NCCL halo exchange at every distributed AMG level + fp64 allreduce, aggregates local to a rank, coarse levels below 40 000 global rows replicated on every rank"),
                               global_dofs=global_dofs, global_steps_per_s=K / (ms / 1e3)),
                "krylov_its_per_step": its, "krylov_status_ok": bool(kits > 0), "amg_cycle_type": args.cycle,
                "l2_residual_after_step": None if last is None else last[1],
@@ -504,12 +504,12 @@ def main():
                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": n_local_dofs * 8 * world, "d2h_bytes_per_step": n_local_dofs * 8 * world},
                "gpu_launches": launches,
                "clocks": clocks,
-               "roofline": {"bound": "hbm", "kernel": "bsrt_row_kernel<M_GSD>: one backward multicolour Gauss-Seidel sweep of the fine level (%d colour launches)" % stats.level_colors[0],
+               "roofline": {"bound": "hbm", "kernel": "gs_stream_kernel<S_GSD> (csrc/gs_stream.cu; bsrt_row_kernel<M_GSD> with PNPB200_GS_STREAM=0): one backward multicolour Gauss-Seidel sweep of the fine level, writes x and delta (%d colour launches)" % stats.level_colors[0],
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                             "traffic_note": traffic_note, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": gs_bytes, "ms_per_launch": gs_ms,
                             "other_passes": passes,
-                            "spmv": {"kernel": "bsrt_row_pipe_kernel<M_SPMV> (y = A x, fine level)", "achieved": spmv_bytes / spmv_ms / 1e6,
+                            "spmv": {"kernel": "gs_stream_kernel<S_SPMV> (y = A x, fine level)", "achieved": spmv_bytes / spmv_ms / 1e6,
                                      "frac": spmv_bytes / spmv_ms / 1e6 / peak, "ms": spmv_ms, "algorithmic_bytes": spmv_bytes},
                             "whole_step": {"algorithmic_bytes": b_step, "achieved": step_gbs, "frac": step_gbs / peak,
                                            "note": "algorithmic_bytes = SURVEY 8(d) model (3 full sweeps + 1 matvec per cycle); scheduled_bytes = what the [L|D|U] schedule reads (2.5 passes)",
