@@ -824,6 +824,18 @@ void assemble_system(Handle& h)
   if (!h.rhs_current) assemble_residual(h, h.rhs, nullptr, nullptr);
   mark(1);
   const size_t need = h.use_eafe ? 4 * h.n_pair_records : (size_t)h.nc * REC_FULL;
+  if (h.share_scratch < 0) {
+    // can the device hold the records AND the flexible Krylov basis (31 packed + 30 padded vectors, bsr.dat's restart)?
+    const char* e = getenv("PNPB200_SHARE_SCRATCH");
+    if (e) h.share_scratch = atoi(e) ? 1 : 0;
+    else {
+      size_t fr = 0, tot = 0;
+      PNP_CUDA(cudaMemGetInfo(&fr, &tot));
+      const double held = h.cellrec.n * 8.0;                                  // already ours (pool memory does not count as free)
+      const double want = need * 8.0 * 1.0625 + (31.0 * 3 + 30.0 * VS) * 8.0 * (double)h.nv * 1.0625 + 45.0 * (double)A.nnzb;   // + hierarchy and setup workspace
+      h.share_scratch = (double)fr + held < want + 6e9 ? 1 : 0;
+    }
+  }
   if (h.cellrec.n < need) h.cellrec.alloc(need, s);
   if (h.use_eafe) {
     // exp-bound: 3 CTAs/SM (136 registers) is the measured optimum (23 ms; 25 at 4, 35 at 6)

@@ -46,9 +46,20 @@ int fgmres_sweep(Handle& h, const SolverConfig& cfg, const double* b, double* x,
   const double cr_max = 0.99, cr_min = 0.174, epsmac = 1e-20;
   Krylov& K = h.kry;
   // sweep-space vectors are padded to VS doubles per row; the pad entries must be (and stay) zero
-  K.V.alloc((size_t)(restart_max + 1) * n, s);
-  { const double* old = K.Z.p; K.Z.alloc((size_t)restart_max * nz, s); if (K.Z.p != old) K.Z.zero(); }
-  double* V = K.V.p; double* Z = K.Z.p;
+  double* V; double* Z;
+  if (h.share_scratch == 1) {
+    // low-memory mode (internal.hpp): the basis lives in the assembly's record buffer, which is dead during the solve
+    const size_t vlen = ((size_t)(restart_max + 1) * n + 15) & ~(size_t)15;      // Z stays 128-byte aligned
+    const size_t total = vlen + (size_t)restart_max * nz;
+    K.V.release(); K.Z.release();
+    if (h.cellrec.n < total) h.cellrec.alloc(total, s);
+    V = h.cellrec.p; Z = V + vlen;
+    PNP_CUDA(cudaMemsetAsync(Z, 0, (size_t)restart_max * nz * sizeof(double), s));
+  } else {
+    K.V.alloc((size_t)(restart_max + 1) * n, s);
+    { const double* old = K.Z.p; K.Z.alloc((size_t)restart_max * nz, s); if (K.Z.p != old) K.Z.zero(); }
+    V = K.V.p; Z = K.Z.p;
+  }
   auto Vi = [&](int i) { return V + (size_t)i * n; };
   auto Zi = [&](int i) { return Z + (size_t)i * nz; };
 

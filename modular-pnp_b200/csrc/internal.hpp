@@ -195,6 +195,10 @@ struct Handle {
   DevBuf<double> k00;           // nnzb: permittivity stiffness (solution independent)
   DevBuf<double> cellrec;       // scatter records of the assembly (assemble.cu): 4 doubles per (cell, vertex pair) for the
                                 // Jacobian, 3 per (cell, vertex) for the residual, 68 per cell for the Galerkin-only Jacobian
+  int share_scratch = -1;       // the records are dead once the matrix is assembled and the Krylov basis is dead once the
+                                // update is known: when the device cannot hold both (320^3: 67 + 56 GB next to 90 GB of
+                                // matrix, tables and hierarchy) the basis lives in the record buffer. -1 = not decided yet
+                                // (assemble_system decides from the free device memory), 0 = own buffers, 1 = shared
   DevBuf<int> cvslot;           // 4*nc : residual record slot of (cell, local vertex)   = position in the vertex' cell list
   DevBuf<int> cpslot;           // 10*nc: Jacobian record index of (cell, local vertex pair)
   DevBuf<int2> pblk;            // nnzb : (first record, count) of the pair run a block sums (physical block index)
