@@ -248,6 +248,10 @@ def emit(obj):
         os.write(_JSON_FD, line)
 
 
+def stats_nnzb0(g):
+    return float(g.stats().level_nnzb[0])
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -450,6 +454,10 @@ def main():
         pm, pb = g.probe_kernel(w, 10)
         passes[name] = {"ms": pm, "full_row_algorithmic_gbs": pb / pm / 1e6}
     achieved = gs_bytes / gs_ms / 1e6
+    # values per block the solve's matrix passes read on the fine level: 7 when the PNP block structure was packed
+    # (entries (1,2), (2,1) structurally zero: 60 instead of 76 bytes per block), else 9
+    fmt = g.value_format(0)
+    gs_kernel_bytes = gs_bytes - (16.0 * stats_nnzb0(g) if fmt == 7 else 0.0)
     klev = 3 if cyc != 1 else 0
     kk = kits if kits > 0 else stats.krylov_its
     b_step = byte_model(stats, nv, nc, kk, it.restart, kcycle_levels=klev)
@@ -474,7 +482,7 @@ def main():
             traffic_note = "ncu at n=%d (%s): %.4g B dram per sweep = %.2fx algorithmic (x re-read once per colour, partial sectors)" % (
                 tj.get("n"), os.path.basename(tp), tj["gs_sweep"]["dram_bytes_per_sweep"], ratio)
             ncol_cap = len(tj["gs_sweep"].get("per_launch", [])) or None
-            if tj.get("n") == n and (ncol_cap is None or ncol_cap == stats.level_colors[0]):
+            if tj.get("n") == n and (ncol_cap is None or ncol_cap == stats.level_colors[0]) and tj.get("values_per_block", 9) == fmt:
                 traffic = tj["gs_sweep"]["dram_bytes_per_sweep"]
             elif ncol_cap is not None and ncol_cap != stats.level_colors[0]:
                 traffic_note += "; captured with %d colour launches per sweep (graph colouring, PNPB200_BOX_COLORING=0), this run sweeps %d colours (closed-form BoxMesh colouring: x is re-read %d instead of %d times) -> traffic not re-measured, null" % (
@@ -508,6 +516,13 @@ def main():
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                             "traffic_note": traffic_note, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": gs_bytes, "ms_per_launch": gs_ms,
+                            "block_format": {"values_per_block": fmt, "bytes_per_block_read": 60 if fmt == 7 else 76,
+                                             "kernel_bytes_per_launch": gs_kernel_bytes, "kernel_bytes_achieved": gs_kernel_bytes / gs_ms / 1e6,
+                                             "kernel_bytes_frac": gs_kernel_bytes / gs_ms / 1e6 / peak,
+                                             "note": "achieved / frac above are on SURVEY 8(d)'s figure (76 B per stored 3x3 block); "
+                                                     "the solve reads a 7-value copy of every block where the PNP structure allows it (no cation-anion "
+                                                     "coupling: entries (1,2) and (2,1) are zero on every level), i.e. 60 B per block: kernel_bytes_* "
+                                                     "count what the kernel has to read in that format, and `traffic` is to be compared with kernel_bytes_per_launch"},
                             "other_passes": passes,
                             "spmv": {"kernel": "gs_stream_kernel<S_SPMV> (y = A x, fine level)", "achieved": spmv_bytes / spmv_ms / 1e6,
                                      "frac": spmv_bytes / spmv_ms / 1e6 / peak, "ms": spmv_ms, "algorithmic_bytes": spmv_bytes},
@@ -515,6 +530,7 @@ def main():
                                            "note": "algorithmic_bytes = SURVEY 8(d) model (3 full sweeps + 1 matvec per cycle); scheduled_bytes = what the [L|D|U] schedule reads (2.5 passes)",
                                            "scheduled_bytes": b_sched, "scheduled_frac": b_sched / (ms / K) / 1e6 / peak,
                                            "strict_v11_bytes": b_strict, "strict_v11_frac": b_strict / (ms / K) / 1e6 / peak,
+                                           "format_note": "all three byte counts use SURVEY 8(d)'s 76 B per block; with the 7-value block copy (roofline.block_format) the matrix passes of the solve read 60 B per block",
                                            "strict_note": "strict_v11 = the 8(d) formula as written (ONE V(1,1) cycle per Krylov iteration) on this run's levels and iteration count; algorithmic_bytes adds the K-cycle's repeated coarse-level visits"}}}
         # the step must actually have solved the linear system and reduced the residual
         if not (kits > 0 and last is not None and last[1] == last[1] and last[1] < 1e3 * l2_0):

@@ -206,6 +206,13 @@ int  pnpb200_apply_vcycle(pnpb200_handle* h, const double* r, double* z);
  * 6 = block assembly kernel. Needs an assembled system (and a solve for 2/3). */
 int  pnpb200_probe_kernel(pnpb200_handle* h, int which, int reps, double* ms_per_launch,
                           double* algorithmic_bytes);
+/* values per 3x3 block the matrix passes of the last solve read on `level`: 9 (FASP's dense blocks) or 7 (PNP blocks have
+ * no cation-anion coupling: entries (1,2) and (2,1) are zero on every level; the solve then reads a 7-value copy) */
+int  pnpb200_get_value_format(pnpb200_handle* h, int level);
+/* fasp_solver_dbsr_krylov_amg / _ilu (fasp_compat.h) keep the device copy of the LAST host matrix — stream, colouring,
+ * [L | D | U] layout, level buffers, ILU pattern — and re-use it when the next call brings the same sparsity pattern (one
+ * Newton step after the other, linear_pnp.cpp:101). This frees it (device memory back to the pool). */
+void pnpb200_release_host_cache(void);
 /* development aid: run matrix pass `which` (probe numbering: 0, 1, 2, 7..10) of the fine level reps + 1 times from the
  * same input and compare the results bit by bit; out[18]: [0] repetitions that differed, [1] differing entries of
  * the first one, [2..16] their sweep-space positions, [17] its index */

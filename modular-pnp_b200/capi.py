@@ -127,6 +127,9 @@ def lib():
     L.pnpb200_num_vertices.argtypes = [H]
     L.pnpb200_num_cells.argtypes = [H]
     L.pnpb200_probe_kernel.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.pnpb200_get_value_format.argtypes = [H, C.c_int]
+    L.pnpb200_release_host_cache.argtypes = []
+    L.pnpb200_release_host_cache.restype = None
     L.pnpb200_debug_repeat_pass.argtypes = [H, C.c_int, C.c_int, _i4]
     L.pnpb200_destroy.argtypes = [H]
     L.pnpb200_destroy.restype = None
@@ -401,6 +404,9 @@ class PNP:
         ms, by = C.c_double(), C.c_double()
         _check(self.L.pnpb200_probe_kernel(self.h, which, reps, C.byref(ms), C.byref(by)), "probe_kernel")
         return ms.value, by.value
+
+    def value_format(self, level=0):
+        return self.L.pnpb200_get_value_format(self.h, level)
 
     def debug_repeat_pass(self, which, reps=100):
         out = np.zeros(18, dtype=np.int32)

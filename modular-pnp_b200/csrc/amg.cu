@@ -22,19 +22,31 @@ namespace {
 
 typedef unsigned long long u64;
 
+// block infinity-norms for the strength test. PACK: the pass holds every value of the level anyway, so it also writes
+// the 7-value copy the solve's matrix passes read (bsr_ops.cu: bsrt_pack7; flag raised by a block with (1,2) / (2,1) != 0)
+template <bool PACK>
 __global__ void condense_kernel(int nnzb, const int4* __restrict__ rd, const int* __restrict__ brow,
-                                const double* __restrict__ val, double* __restrict__ pp)
+                                const double* __restrict__ val, double* __restrict__ pp, double* __restrict__ val7, int* __restrict__ general)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nnzb) return;
   const int4 d = rd[brow[b]];
   int st;
   const double* v = val + bsrt_off(d.x, d.y, d.z, b - d.x, st);
+  double e[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) e[t] = v[(size_t)t * st];
   double m = 0.0;
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
-    m = fmax(m, fabs(v[(size_t)(3 * r) * st]) + fabs(v[(size_t)(3 * r + 1) * st]) + fabs(v[(size_t)(3 * r + 2) * st]));
+  for (int r = 0; r < 3; ++r) m = fmax(m, fabs(e[3 * r]) + fabs(e[3 * r + 1]) + fabs(e[3 * r + 2]));
   pp[b] = m;
+  if (PACK) {
+    const int k = b - d.x;
+    double* w = val7 + (7 * (size_t)d.x + (size_t)(k < d.z ? k : 6 * d.z + k));
+    if (e[5] != 0.0 || e[7] != 0.0) *general = 1;
+    w[0] = e[0]; w[st] = e[1]; w[2 * (size_t)st] = e[2]; w[3 * (size_t)st] = e[3]; w[4 * (size_t)st] = e[4];
+    w[5 * (size_t)st] = e[6]; w[6 * (size_t)st] = e[8];
+  }
 }
 
 __global__ void isolated_kernel(int n, const int* __restrict__ ia, const int* __restrict__ rs,
@@ -679,7 +691,13 @@ bool coarsen_symbolic(Handle& h, Level& L, Level& C, double theta)
   {
   PHASE("strength");
   pp.p = ws.get<double>(nnzb);
-  condense_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.rd.p, A.brow.p, A.val.p, pp.p); PNP_COUNT_LAUNCH();
+  if (bsrt_pack7_wanted(h, A)) {
+    A.val7.alloc(7 * (size_t)nnzb, s);
+    A.pack_flag.alloc(1, s); A.pack_flag.zero();
+    condense_kernel<true><<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.rd.p, A.brow.p, A.val.p, pp.p, A.val7.p, A.pack_flag.p);
+    A.pack7_fresh = true;
+  } else condense_kernel<false><<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.rd.p, A.brow.p, A.val.p, pp.p, nullptr, nullptr);
+  PNP_COUNT_LAUNCH();
   iso.p = ws.get<unsigned char>(n); strong.p = ws.get<unsigned char>(nnzb);
   isolated_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, A.ia.p, A.rs.p, A.ja.p, pp.p, iso.p); PNP_COUNT_LAUNCH();
   strength_kernel<<<cdiv(nnzb, 256), 256, 0, s>>>(nnzb, A.ja.p, A.brow.p, A.dslot.p, A.tslot.p, pp.p, iso.p,
@@ -1261,6 +1279,8 @@ void amg_setup_chain(Handle& h, Hierarchy& H, const SolverConfig& cfg)
   Level& F = *lv[0];
   const bool reuse = h.reuse_hierarchy && H.symbolic_valid;
   if (F.ncolors == 0) throw Error(ERROR_DATA_STRUCTURE, "fine level not coloured");   // done at create / upload
+  for (size_t k = 1; k < lv.size(); ++k) lv[k]->A.packed7 = false;     // coarse values are rebuilt below
+  for (size_t k = 0; k < lv.size(); ++k) lv[k]->A.pack7_fresh = false;
   alloc_level_vectors(F, s);
   if (!reuse) H.symbolic_valid = false;
   H.drop_coarse_graph();           // buffers and launch sizes belong to the hierarchy being replaced
@@ -1324,6 +1344,7 @@ void amg_setup_chain(Handle& h, Hierarchy& H, const SolverConfig& cfg)
     }
   }
   H.symbolic_valid = true;
+  { PHASE("pack7"); bsrt_pack7(h, H); }     // the solve's matrix passes read 7 values per block where the structure allows
   if (cfg.print_level > 0) {
     PNP_CUDA(cudaStreamSynchronize(s));
     for (size_t k = 0; k < lv.size(); ++k)

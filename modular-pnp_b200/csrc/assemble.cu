@@ -816,6 +816,7 @@ void assemble_system(Handle& h)
   if (!h.have_coef) throw Error(ERROR_INPUT_PAR, "coefficients not set");
   const int4* cells = reinterpret_cast<const int4*>(h.cells.p);
   BsrT& A = h.hier.lv[0]->A;
+  A.packed7 = false;                    // the values are about to change: the 7-value copy of the last solve is stale
   static const bool timing = getenv("PNPB200_ASM_TIMING") != nullptr;
   auto mark = [&](int k) { if (timing) cudaEventRecord(h.ev[4 + k], s); };
   mark(0);

@@ -49,7 +49,7 @@ namespace {
 #endif
 enum { M_SPMV = 0, M_RES = 1, M_GS = 2, M_GS0 = 3, M_RESU = 4, M_GSD = 5, M_LDELTA = 6, M_LDELTAG = 7 };
 
-template <int MODE, int MINB, int XS>
+template <int MODE, int MINB, int XS, int NV>
 __global__ void __launch_bounds__(256, MINB)
 bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* __restrict__ ja,
                 const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
@@ -66,22 +66,15 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   auto block = [&](int k) {
     if ((MODE == M_GS || MODE == M_GSD) && k == nl) return;
-#if PNPB200_SPLIT_ROWS
-    // lower part: component stride nl; D + U part (k >= nl) starts 9*nl further: stride len - nl
+    // lower part: component stride nl; D + U part (k >= nl) starts NV*nl further: stride len - nl
     const bool lo = (MODE == M_GS0 || MODE == M_LDELTA) ? true : k < nl;
-    const double* v = val + (9 * (size_t)s + (size_t)(lo ? k : 8 * nl + k));
+    const double* v = val + (NV * (size_t)s + (size_t)(lo ? k : (NV - 1) * nl + k));
     const int st = lo ? nl : len - nl;
-#else
-    const double* v = val + (9 * (size_t)s + (size_t)k);
-    const int st = len;
-#endif
     const int jcol = ja[s + k];
     if (MODE == M_LDELTAG && k >= nl && (k == nl || jcol < n_swept)) return;
     double x0, x1, x2;
     load_row3<XS>(x, jcol, x0, x1, x2);
-    a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
-    a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
-    a2 += v[6 * st] * x0 + v[7 * st] * x1 + v[8 * st] * x2;
+    block_mac<NV>(v, st, x0, x1, x2, a0, a1, a2);
   };
   // the first 16 blocks of the row are peeled out of the loop so that the compiler issues their 13
   // loads back to back (a rolled loop under the register cap interleaves loads and FMAs and pays
@@ -143,7 +136,7 @@ bsrt_row_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* 
 // t+2H, ... (H = half-warps in the grid) and carries the descriptor of the next two rows and the
 // column indices of the next row in registers, so that the matrix values AND the x gather of a row
 // are requested in the same instant and a row costs ONE exposed round trip.
-template <int MODE, int MINB, int XS>
+template <int MODE, int MINB, int XS, int NV>
 __global__ void __launch_bounds__(256, MINB)
 bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const int* __restrict__ ja,
                      const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
@@ -186,19 +179,12 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
     auto block = [&](int k, int jc) {
       if ((MODE == M_GS || MODE == M_GSD) && k == nl) return;
       if (MODE == M_LDELTAG && k >= nl && (k == nl || jc < n_swept)) return;
-#if PNPB200_SPLIT_ROWS
       const bool lo = (MODE == M_GS0 || MODE == M_LDELTA) ? true : k < nl;
-      const double* v = val + (9 * (size_t)s + (size_t)(lo ? k : 8 * nl + k));
+      const double* v = val + (NV * (size_t)s + (size_t)(lo ? k : (NV - 1) * nl + k));
       const int st = lo ? nl : len - nl;
-#else
-      const double* v = val + (9 * (size_t)s + (size_t)k);
-      const int st = len;
-#endif
       double x0, x1, x2;
       load_row3<XS>(x, jc, x0, x1, x2);
-      a0 += v[0] * x0 + v[st] * x1 + v[2 * st] * x2;
-      a1 += v[3 * st] * x0 + v[4 * st] * x1 + v[5 * st] * x2;
-      a2 += v[6 * st] * x0 + v[7 * st] * x1 + v[8 * st] * x2;
+      block_mac<NV>(v, st, x0, x1, x2, a0, a1, a2);
     };
     int k = k0 + lane;
     if (jc0 >= 0) block(k, jc0);
@@ -247,25 +233,33 @@ bsrt_row_pipe_kernel(int nrows, int n_swept, const int4* __restrict__ rd, const 
 #define PNPB200_GS_CTAS 8         // ... and the colour sweeps
 #endif
 int g_sm_count = 0;
-template <int MODE, int MINB, bool PIPE, int XS = VS>
-void launch_rows(int nrows, int n_swept, const int4* rd, const int* ja, const BsrT& A, const double* dinv, const double* b,
-                 const double* x, double* y, double* dl, cudaStream_t s, int bs = XS, int ys = XS)
+template <int MODE, int MINB, bool PIPE, int XS, int NV>
+void launch_rows_nv(int nrows, int n_swept, const int4* rd, const int* ja, const double* val, const double* dinv, const double* b,
+                    const double* x, double* y, double* dl, cudaStream_t s, int bs, int ys)
 {
-  if (nrows <= 0) return;
   const int full = cdiv((size_t)nrows * 16, 256);
   if constexpr (PIPE && PNPB200_PIPE) {
   // persistent grid = exactly the CTAs that are resident at once (a second wave would walk the
   // gathered x window a second time: measured 6.5 vs 4.5 ms per Gauss-Seidel sweep)
   if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
-  static int per_sm = 0;             // one static per (MODE, MINB, XS) instantiation
+  static int per_sm = 0;             // one static per (MODE, MINB, XS, NV) instantiation
   if (per_sm == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bsrt_row_pipe_kernel<MODE, MINB, XS>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = MINB;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bsrt_row_pipe_kernel<MODE, MINB, XS, NV>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = MINB;
   }
   const int cap = g_sm_count * per_sm;
-  bsrt_row_pipe_kernel<MODE, MINB, XS><<<full < cap ? full : cap, 256, 0, s>>>(nrows, n_swept, rd, ja, A.val.p, dinv, b, x, y, dl, bs, ys);
+  bsrt_row_pipe_kernel<MODE, MINB, XS, NV><<<full < cap ? full : cap, 256, 0, s>>>(nrows, n_swept, rd, ja, val, dinv, b, x, y, dl, bs, ys);
   } else
-  bsrt_row_kernel<MODE, MINB, XS><<<full, 256, 0, s>>>(nrows, n_swept, rd, ja, A.val.p, dinv, b, x, y, dl, bs, ys);
+  bsrt_row_kernel<MODE, MINB, XS, NV><<<full, 256, 0, s>>>(nrows, n_swept, rd, ja, val, dinv, b, x, y, dl, bs, ys);
   PNP_COUNT_LAUNCH();
+}
+// the level's values: 7 per block when the level was packed after the set-up (bsrt_pack7), else FASP's 9
+template <int MODE, int MINB, bool PIPE, int XS = VS>
+void launch_rows(int nrows, int n_swept, const int4* rd, const int* ja, const BsrT& A, const double* dinv, const double* b,
+                 const double* x, double* y, double* dl, cudaStream_t s, int bs = XS, int ys = XS)
+{
+  if (nrows <= 0) return;
+  if (A.packed7) launch_rows_nv<MODE, MINB, PIPE, XS, 7>(nrows, n_swept, rd, ja, A.val7.p, dinv, b, x, y, dl, s, bs, ys);
+  else launch_rows_nv<MODE, MINB, PIPE, XS, 9>(nrows, n_swept, rd, ja, A.val.p, dinv, b, x, y, dl, s, bs, ys);
 }
 
 // Small levels (<= SMALL_LEVEL_ROWS rows): the whole multicolour sweep in ONE launch of one CTA,
@@ -696,8 +690,65 @@ void bsrt_diaginv(const BsrT& A, double* dinv, cudaStream_t s)
   PNP_COUNT_LAUNCH();
 }
 
+namespace {
+// one thread per stored block: copy its 7 structural entries into the 7-value layout (same [L | D | U] component-major
+// parts, 7 components each); raise the flag if entry (1,2) or (2,1) is not zero (a general BSR(3) matrix)
+__global__ void pack7_kernel(int nnzb, const int4* __restrict__ rd, const int* __restrict__ brow, const double* __restrict__ val,
+                             double* __restrict__ val7, int* __restrict__ general)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int4 d = rd[brow[b]];
+  const int s = d.x, len = d.y, nl = d.z, k = b - s;
+  const bool lo = k < nl;
+  const int st = lo ? nl : len - nl;
+  const double* v = val + (9 * (size_t)s + (size_t)(lo ? k : 8 * nl + k));
+  double* w = val7 + (7 * (size_t)s + (size_t)(lo ? k : 6 * nl + k));
+  if (v[5 * (size_t)st] != 0.0 || v[7 * (size_t)st] != 0.0) *general = 1;
+  w[0] = v[0]; w[st] = v[st]; w[2 * (size_t)st] = v[2 * (size_t)st];
+  w[3 * (size_t)st] = v[3 * (size_t)st]; w[4 * (size_t)st] = v[4 * (size_t)st];
+  w[5 * (size_t)st] = v[6 * (size_t)st]; w[6 * (size_t)st] = v[8 * (size_t)st];
+}
+}
+
+// policy: PNPB200_PACK7=0 keeps 9 values everywhere; not in low-memory mode (Handle::share_scratch: 320^3 has no room
+// for a second copy of the values); the one-CTA kernels of the smallest levels keep FASP's 9
+bool bsrt_pack7_wanted(const Handle& h, const BsrT& A)
+{
+  static const bool on = !(getenv("PNPB200_PACK7") && atoi(getenv("PNPB200_PACK7")) == 0);
+  return on && h.share_scratch != 1 && VS == 4 && A.n > SMALL_LEVEL_ROWS && A.nnzb >= 1 && A.rd.p && A.brow.p;
+}
+
+// End of the set-up: 7-value copies of the levels that the row kernels sweep. A level that was coarsened has its copy
+// already (written by the strength pass, which reads every value anyway); the others are packed here.
+void bsrt_pack7(Handle& h, Hierarchy& H)
+{
+  cudaStream_t s = h.stream;
+  const int nl = (int)H.lv.size();
+  std::vector<int> tried;
+  for (int l = 0; l < nl; ++l) {
+    BsrT& A = H.lv[l]->A;
+    A.packed7 = false;
+    if (!bsrt_pack7_wanted(h, A)) continue;
+    if (l == nl - 1 && (H.coarse_dense || H.coarse_rep)) continue;         // never swept
+    if (!A.pack7_fresh) {
+      A.val7.alloc(7 * (size_t)A.nnzb, s);
+      A.pack_flag.alloc(1, s); A.pack_flag.zero();
+      pack7_kernel<<<cdiv(A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.rd.p, A.brow.p, A.val.p, A.val7.p, A.pack_flag.p); PNP_COUNT_LAUNCH();
+    }
+    tried.push_back(l);
+  }
+  for (int l : tried) {
+    int general = 1;
+    H.lv[l]->A.pack_flag.download(&general, 1);
+    H.lv[l]->A.packed7 = general == 0;
+    H.lv[l]->A.pack7_fresh = false;
+  }
+}
+
 void bsrt_from_fasp(const double* d_val_fasp, BsrT& A, cudaStream_t s)
 {
+  A.packed7 = false;
   relayout_kernel<true><<<cdiv(9 * (size_t)A.nnzb, 256), 256, 0, s>>>(A.nnzb, A.ia.p, A.rs.p, A.dslot.p, A.ja.p, A.brow.p, d_val_fasp, A.val.p);
   PNP_COUNT_LAUNCH();
 }

@@ -204,6 +204,23 @@ __device__ __forceinline__ size_t bsrt_off(int s, int len, int nl, int k, int& s
   return 9 * (size_t)s + (size_t)k;
 #endif
 }
+// a += (3x3 block) * x for one stored block: v = its first value inside the row part, st = the part's component stride.
+// NV = 9: all nine entries. NV = 7: the PNP block structure — the linearised PNP system has no cation-anion coupling,
+// entries (1,2) and (2,1) of EVERY block are structurally zero on every level (unsmoothed aggregation sums blocks) —
+// stored as (0,0) (0,1) (0,2) (1,0) (1,1) (2,0) (2,2). Explicit FMA chains in a fixed order, so that the two forms
+// (and every kernel that uses them) give the same bits when the two entries are zero.
+template <int NV>
+__device__ __forceinline__ void block_mac(const double* v, int st, double x0, double x1, double x2, double& a0, double& a1, double& a2)
+{
+  a0 = __fma_rn(v[2 * st], x2, __fma_rn(v[st], x1, __fma_rn(v[0], x0, a0)));
+  if (NV == 9) {
+    a1 = __fma_rn(v[5 * st], x2, __fma_rn(v[4 * st], x1, __fma_rn(v[3 * st], x0, a1)));
+    a2 = __fma_rn(v[8 * st], x2, __fma_rn(v[7 * st], x1, __fma_rn(v[6 * st], x0, a2)));
+  } else {
+    a1 = __fma_rn(v[4 * st], x1, __fma_rn(v[3 * st], x0, a1));
+    a2 = __fma_rn(v[6 * st], x2, __fma_rn(v[5 * st], x0, a2));
+  }
+}
 // gather the three components of block row j from a vector with XS doubles per row. Sweep-space
 // vectors are padded to XS = 4 doubles (32 bytes, one DRAM sector) per row so that the gather is ONE
 // 256-bit load (LDG.E.256 on sm_100a) instead of three 8-byte loads that each walk the same 16

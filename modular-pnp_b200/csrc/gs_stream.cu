@@ -20,16 +20,22 @@ namespace pnpb200 {
 namespace {
 
 constexpr int GST_ROWS = 16;
-constexpr int GST_MAXLEN = 16;
-constexpr int GST_STAGES = 3;
 constexpr int GST_THREADS = GST_ROWS * 16 + 32;
-constexpr int GST_ROWSLOT = GST_MAXLEN * 9 + 2;   // doubles per row slot of a stage (a multiple of 16 bytes)
+// Two instantiations by the longest row of the level (ML blocks): 16 (the fine level of a Kuhn mesh: 15) and 32 (the
+// first coarse levels: mean 17.5, longest 29). A half-warp takes a row in ML / 16 rounds of 16 blocks.
+//   ML = 16: 57 KB per 3-stage ring, 3 CTAs per SM;   ML = 32: 81 KB per 2-stage ring, 2 CTAs per SM
+template <int ML> struct GstCfg {
+  static constexpr int STAGES = ML <= 16 ? 3 : 2;
+  static constexpr int CTAS = ML <= 16 ? 3 : 2;
+  static constexpr int ROWSLOT = ML * 9 + 2;      // doubles per row slot of a stage (a multiple of 16 bytes)
+};
 
+template <int ML>
 struct alignas(128) GstStage {
-  double val[GST_ROWS * GST_ROWSLOT];             // + slack: a copy starts at the 16-byte boundary below its first byte
+  double val[GST_ROWS * GstCfg<ML>::ROWSLOT];     // + slack: a copy starts at the 16-byte boundary below its first byte
   double dinv[GST_ROWS * 9 + 2];
   int4 prd[GST_ROWS];
-  int ja[GST_ROWS * GST_MAXLEN + 4];
+  int ja[GST_ROWS * ML + 4];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -73,17 +79,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 //              NEXT chunk of their CTA one chunk ahead, so the producer never waits for them.
 enum { S_SPMV = 0, S_RES = 1, S_GS = 2, S_GS0 = 3, S_RESU = 4, S_GSD = 5, S_LDELTA = 6 };
 
-template <int MODE>
-__global__ void __launch_bounds__(GST_THREADS, 3)
+template <int MODE, int ML, int NV>
+__global__ void __launch_bounds__(GST_THREADS, GstCfg<ML>::CTAS)
 gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __restrict__ pia, const int* __restrict__ jpos,
                  const double* __restrict__ val, const double* __restrict__ dinv, const double* __restrict__ b,
                  const double* x, double* y, double* __restrict__ dl, int bs, int ys)
 {
   constexpr bool LOWER = MODE == S_GS0 || MODE == S_LDELTA, UPPER = MODE == S_RESU, PART = LOWER || UPPER;
   constexpr bool SMOOTH = MODE == S_GS || MODE == S_GS0 || MODE == S_GSD;
+  constexpr int GST_STAGES = GstCfg<ML>::STAGES, GST_ROWSLOT = GstCfg<ML>::ROWSLOT;
+  using Stage = GstStage<ML>;
   extern __shared__ __align__(128) unsigned char gst_smem[];
-  GstStage* stages = reinterpret_cast<GstStage*>(gst_smem);
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(gst_smem + GST_STAGES * sizeof(GstStage));
+  Stage* stages = reinterpret_cast<Stage*>(gst_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(gst_smem + GST_STAGES * sizeof(Stage));
   unsigned long long* empty = full + GST_STAGES;
   if (threadIdx.x == 0) {
     for (int q = 0; q < GST_STAGES; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], GST_ROWS); }
@@ -109,7 +117,7 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
         if (pl < GST_ROWS && c + (int)gridDim.x < nchunks && r < p1) dn = prd[r];
       }
       if (it >= GST_STAGES) mbar_wait(&empty[stage], ((it / GST_STAGES) - 1) & 1);      // the previous use of the slot is consumed
-      GstStage& st = stages[stage];
+      Stage& st = stages[stage];
       const int r0 = p0 + c * GST_ROWS, r1 = min(r0 + GST_ROWS, p1);
       const unsigned np = 16u * (unsigned)(r1 - r0);
       const unsigned ld = (r0 & 1) * 8u;
@@ -118,10 +126,10 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
         const int b0 = pia[r0], b1 = pia[r1];
         // every copy starts at the 16-byte boundary at or below its first byte and is rounded up to 16 bytes
         const unsigned lv = (b0 & 1) * 8u, lj = (b0 & 3) * 4u;
-        const unsigned nv = (72u * (unsigned)(b1 - b0) + lv + 15u) & ~15u;
+        const unsigned nv = (8u * NV * (unsigned)(b1 - b0) + lv + 15u) & ~15u;
         const unsigned nj = (4u * (unsigned)(b1 - b0) + lj + 15u) & ~15u;
         mbar_expect_tx(&full[stage], nv + nj + nd + np);
-        bulk_g2s(st.val, reinterpret_cast<const unsigned char*>(val) + 72ull * (unsigned long long)b0 - lv, nv, &full[stage]);
+        bulk_g2s(st.val, reinterpret_cast<const unsigned char*>(val) + 8ull * NV * (unsigned long long)b0 - lv, nv, &full[stage]);
         bulk_g2s(st.ja, reinterpret_cast<const unsigned char*>(jpos) + 4ull * (unsigned long long)b0 - lj, nj, &full[stage]);
         if (SMOOTH) bulk_g2s(st.dinv, reinterpret_cast<const unsigned char*>(dinv) + 72ull * (unsigned long long)r0 - ld, nd, &full[stage]);
         bulk_g2s(st.prd, prd + r0, np, &full[stage]);
@@ -129,7 +137,7 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
         // my row's part: lower = blocks [s, s + nl), upper = the D + U part [s + nl, s + len)
         const int blk = LOWER ? d.x : d.x + d.z, nblk = d.w < 0 ? 0 : (LOWER ? d.z : d.y - d.z);
         const unsigned lv = (blk & 1) * 8u;
-        const unsigned nv = nblk > 0 ? (72u * (unsigned)nblk + lv + 15u) & ~15u : 0u;
+        const unsigned nv = nblk > 0 ? (8u * NV * (unsigned)nblk + lv + 15u) & ~15u : 0u;
         unsigned tot = nv;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
@@ -141,7 +149,7 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
         const unsigned nj = (4u * (unsigned)(b1 - b0) + lj + 15u) & ~15u;
         if (pl == 0) mbar_expect_tx(&full[stage], tot + nj + nd + np);
         __syncwarp();
-        if (nv > 0) bulk_g2s(st.val + pl * GST_ROWSLOT, reinterpret_cast<const unsigned char*>(val) + 72ull * (unsigned long long)blk - lv, nv, &full[stage]);
+        if (nv > 0) bulk_g2s(st.val + pl * GST_ROWSLOT, reinterpret_cast<const unsigned char*>(val) + 8ull * NV * (unsigned long long)blk - lv, nv, &full[stage]);
         if (pl == 0) {
           bulk_g2s(st.ja, reinterpret_cast<const unsigned char*>(jpos) + 4ull * (unsigned long long)b0 - lj, nj, &full[stage]);
           if (SMOOTH) bulk_g2s(st.dinv, reinterpret_cast<const unsigned char*>(dinv) + 72ull * (unsigned long long)r0 - ld, nd, &full[stage]);
@@ -159,7 +167,7 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
     const int stage = it % GST_STAGES;
     mbar_wait(&full[stage], (it / GST_STAGES) & 1);
-    const GstStage& st = stages[stage];
+    const Stage& st = stages[stage];
     const int r0 = p0 + c * GST_ROWS;
     const int rows = min(GST_ROWS, p1 - r0);
     const int b0 = st.prd[0].x;
@@ -172,22 +180,24 @@ gs_stream_kernel(int p0, int p1, const int4* __restrict__ prd, const int* __rest
     }
     if (MODE == S_GSD && row >= 0 && lane < 3) xold = x[4 * (size_t)row + lane];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    // rows of this path have <= 16 blocks: block k = lane
-    const bool mine = LOWER ? lane < nl : UPPER ? (lane > nl && lane < len) : (lane < len && (!(MODE == S_GS || MODE == S_GSD) || lane != nl));
-    if (mine) {
-      const int jc = st.ja[(b0 & 3) + (s - b0) + lane];
-      const double* v; int sv;
-      if (!PART) {
-        const bool lo = lane < nl;
-        v = st.val + (b0 & 1) + 9 * (s - b0) + (lo ? lane : 8 * nl + lane);
-        sv = lo ? nl : len - nl;
-      } else if (LOWER) { v = st.val + hw * GST_ROWSLOT + (s & 1) + lane; sv = nl; }
-      else { v = st.val + hw * GST_ROWSLOT + ((s + nl) & 1) + (lane - nl); sv = len - nl; }
-      double x0, x1, x2;
-      load_row3<4>(x, jc, x0, x1, x2);
-      a0 = v[0] * x0 + v[sv] * x1 + v[2 * sv] * x2;
-      a1 = v[3 * sv] * x0 + v[4 * sv] * x1 + v[5 * sv] * x2;
-      a2 = v[6 * sv] * x0 + v[7 * sv] * x1 + v[8 * sv] * x2;
+    // block k = lane + 16 * round; the sums are formed exactly as in bsr_ops.cu (a += products of block k, k ascending)
+#pragma unroll
+    for (int rnd = 0; rnd < ML / 16; ++rnd) {
+      const int k = lane + 16 * rnd;
+      const bool mine = LOWER ? k < nl : UPPER ? (k > nl && k < len) : (k < len && (!(MODE == S_GS || MODE == S_GSD) || k != nl));
+      if (mine) {
+        const int jc = st.ja[(b0 & 3) + (s - b0) + k];
+        const double* v; int sv;
+        if (!PART) {
+          const bool lo = k < nl;
+          v = st.val + (b0 & 1) + NV * (s - b0) + (lo ? k : (NV - 1) * nl + k);
+          sv = lo ? nl : len - nl;
+        } else if (LOWER) { v = st.val + hw * GST_ROWSLOT + (s & 1) + k; sv = nl; }
+        else { v = st.val + hw * GST_ROWSLOT + ((s + nl) & 1) + (k - nl); sv = len - nl; }
+        double x0, x1, x2;
+        load_row3<4>(x, jc, x0, x1, x2);
+        block_mac<NV>(v, sv, x0, x1, x2, a0, a1, a2);
+      }
     }
     const double a = half_sum3(a0, a1, a2, lane);
     if (!SMOOTH) {
@@ -228,8 +238,6 @@ __global__ void max_rowlen_kernel(int n, const int* __restrict__ ia, int* __rest
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
-constexpr size_t GST_SMEM = GST_STAGES * sizeof(GstStage) + 2 * GST_STAGES * sizeof(unsigned long long);
-
 } // namespace
 
 int max_row_length(const BsrT& A, cudaStream_t s)
@@ -240,22 +248,38 @@ int max_row_length(const BsrT& A, cudaStream_t s)
   return h;
 }
 
-template <int MODE>
-void launch_stream(const BsrT& A, const double* dinv, int p0, int p1, const double* b, const double* x, double* y, double* dl, int bs, int ys, cudaStream_t s)
+template <int MODE, int ML, int NV>
+void launch_stream_ml(const BsrT& A, const double* dinv, int p0, int p1, const double* b, const double* x, double* y, double* dl, int bs, int ys, cudaStream_t s)
 {
+  constexpr size_t SMEM = GstCfg<ML>::STAGES * sizeof(GstStage<ML>) + 2 * GstCfg<ML>::STAGES * sizeof(unsigned long long);
   static bool configured[64] = {false};
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    PNP_CUDA(cudaFuncSetAttribute(gs_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GST_SMEM));
+    PNP_CUDA(cudaFuncSetAttribute(gs_stream_kernel<MODE, ML, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   static int sms = 0;
   if (sms == 0) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const int nchunks = (p1 - p0 + GST_ROWS - 1) / GST_ROWS;
-  const int grid = nchunks < 3 * sms ? nchunks : 3 * sms;
-  gs_stream_kernel<MODE><<<grid, GST_THREADS, GST_SMEM, s>>>(p0, p1, A.prd.p, A.pia.p, A.jpos.p, A.val.p, dinv, b, x, y, dl, bs, ys);
+  const int cap = GstCfg<ML>::CTAS * sms;
+  const int grid = nchunks < cap ? nchunks : cap;
+  gs_stream_kernel<MODE, ML, NV><<<grid, GST_THREADS, SMEM, s>>>(p0, p1, A.prd.p, A.pia.p, A.jpos.p, NV == 7 ? A.val7.p : A.val.p, dinv, b, x, y, dl, bs, ys);
   PNP_COUNT_LAUNCH();
 }
+
+template <int MODE>
+void launch_stream(const BsrT& A, const double* dinv, int p0, int p1, const double* b, const double* x, double* y, double* dl, int bs, int ys, cudaStream_t s)
+{
+  if (A.maxlen <= 16) {
+    if (A.packed7) launch_stream_ml<MODE, 16, 7>(A, dinv, p0, p1, b, x, y, dl, bs, ys, s);
+    else launch_stream_ml<MODE, 16, 9>(A, dinv, p0, p1, b, x, y, dl, bs, ys, s);
+  } else {
+    if (A.packed7) launch_stream_ml<MODE, 32, 7>(A, dinv, p0, p1, b, x, y, dl, bs, ys, s);
+    else launch_stream_ml<MODE, 32, 9>(A, dinv, p0, p1, b, x, y, dl, bs, ys, s);
+  }
+}
+
+constexpr int GST_MAXLEN = 32;          // longest row the streamed kernels take
 
 // Does the level qualify for the streamed kernels? Read at every call so that a test can switch the path
 // inside one process: PNPB200_GS_STREAM=0 keeps the plain kernels, PNPB200_GS_STREAM_MIN = smallest row
@@ -264,7 +288,13 @@ bool stream_ok(const BsrT& A, int nrows)
 {
   const char* e_on = getenv("PNPB200_GS_STREAM"); const char* e_min = getenv("PNPB200_GS_STREAM_MIN");
   const int on = e_on ? atoi(e_on) : 1, min_rows = e_min ? atoi(e_min) : 4096;
-  return on && VS == 4 && A.maxlen > 0 && A.maxlen <= GST_MAXLEN && nrows >= min_rows;
+  // Rows of 17 ... 32 blocks (coarse levels) have their own instantiation (two rounds per row, 2-stage ring), but it
+  // does not pay: measured on level 1 of the 256^3 hierarchy (1.5 M rows, 11 colours): GS + delta 0.605 vs 0.649 ms,
+  // forward sweep from zero 0.500 vs 0.417 ms, Krylov stage unchanged — those launches are bound by their size
+  // (137 k rows each), not by load latency. PNPB200_GS_STREAM_MAXLEN=32 switches it on (tests do).
+  const char* e_ml = getenv("PNPB200_GS_STREAM_MAXLEN");
+  const int maxlen = e_ml ? atoi(e_ml) : 16;
+  return on && VS == 4 && A.maxlen > 0 && A.maxlen <= (maxlen < GST_MAXLEN ? maxlen : GST_MAXLEN) && nrows >= min_rows;
 }
 
 // One colour launch [p0, p1) (matrix order) of a sweep. mode 0: plain, 1: forward from a zero initial guess

@@ -40,6 +40,14 @@ struct BsrT {
   DevBuf<int> dslot;    // position (absolute block index) of the diagonal block of each row (= rs[i] + nl_i)
   DevBuf<int> tslot;    // block index of the transposed block (j,i), -1 if absent
   DevBuf<double> val;   // 9*nnzb
+  // PNP blocks have no cation-anion coupling: entries (1,2) and (2,1) are zero in every block of every level. After the
+  // AMG set-up the matrix passes of the solve read a 7-value copy in the same [L | D | U] component-major layout
+  // (7 instead of 9 components per part): 60 instead of 76 bytes per block. Built by bsrt_pack7 when every block of the
+  // level has the two zeros (a general BSR(3) matrix does not, and keeps the 9-value passes); dropped whenever val changes.
+  DevBuf<double> val7;  // 7*nnzb
+  bool packed7 = false;
+  DevBuf<int> pack_flag;      // raised by the packing pass if a block is not of the PNP structure
+  bool pack7_fresh = false;   // val7 was written during this set-up by the strength pass (amg.cu: condense_kernel<true>)
 };
 
 // halo lists of one level (block-row granularity): neighbour k gets the owned rows
@@ -283,6 +291,9 @@ void bsrt_residual_after_sweep(const Level& L, const double* b, const double* x,
 // backward sweep that also returns delta = x_new - x_old, and y = A x_new = b + L delta after it
 void mcgs_sweep_back_delta(const Level& L, const double* b, double* x, double* delta, cudaStream_t s, int bs = VS);
 void bsrt_apply_after_sweep(const Level& L, const double* b, const double* delta, double* y, cudaStream_t s, int bs = VS, int ys = VS);
+// pack the levels [0, nlevels) that the row kernels sweep: sets A.packed7 where the block structure allows it
+void bsrt_pack7(Handle& h, Hierarchy& H);
+bool bsrt_pack7_wanted(const Handle& h, const BsrT& A);
 // ---- gs_stream.cu: bulk-copy (TMA) streamed colour launch for levels with short rows; false = not applicable
 int max_row_length(const BsrT& A, cudaStream_t s);
 bool gs_stream_colour(const Level& L, int p0, int p1, const double* b, double* x, double* dl, int mode, int bs, cudaStream_t s);

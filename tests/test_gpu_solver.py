@@ -269,6 +269,35 @@ def test_fasp_entry_point_nonzero_initial_guess(oracle, pkg, system):
     assert np.abs(x_warm - x_cold).max() <= 1e-7 * np.abs(x_cold).max()
 
 
+def test_fasp_entry_point_reuses_the_layout_of_an_unchanged_pattern(oracle, pkg, system):
+    """Path A of INTEGRATION.md: the reference calls fasp_solver_dbsr_krylov_amg once per Newton step with the same
+    pattern (linear_pnp.cpp:101). The library keeps the last system's colouring / layout: a second call with new
+    VALUES on the same pattern must give exactly what a fresh system gives, and a matrix with the same sizes but
+    different columns must be recognised as a new pattern."""
+    P, g, IA, JA, val, b = system
+    it, amg = pkg.default_params()
+    L = pkg.lib()
+    L.pnpb200_release_host_cache()
+    x1, st1 = pkg.capi.fasp_solver_dbsr_krylov_amg(IA, JA, val, b, it, amg)           # builds the cached system
+    val2 = val * (1.0 + 0.05 * np.sin(np.arange(val.size)))                           # same pattern, other values
+    x2, st2 = pkg.capi.fasp_solver_dbsr_krylov_amg(IA, JA, val2, b, it, amg)          # cached layout, new values
+    L.pnpb200_release_host_cache()
+    x2f, st2f = pkg.capi.fasp_solver_dbsr_krylov_amg(IA, JA, val2, b, it, amg)        # fresh system
+    assert st1 > 0 and st2 > 0 and st2 == st2f
+    assert np.array_equal(x2, x2f)
+    assert np.linalg.norm(b - oracle.bsr_spmv(IA, JA, val2, x2)) <= 1.0001 * it.tol * np.linalg.norm(b)
+    # same ROW / NNZ, different columns: swap the positions of two off-diagonal blocks' columns in one row
+    JA3 = JA.copy(); val3 = val.copy().reshape(-1, 9)
+    row = int(np.argmax(np.diff(IA) >= 4)); s0, e0 = IA[row], IA[row + 1]
+    free = sorted(set(range(len(IA) - 1)) - set(JA[s0:e0].tolist()))
+    cols = JA[s0:e0].copy(); k = int(np.nonzero(cols != row)[0][0]); cols[k] = free[len(free) // 2]
+    order = np.argsort(cols); JA3[s0:e0] = cols[order]; val3[s0:e0] = val3[s0:e0][order]
+    x3, st3 = pkg.capi.fasp_solver_dbsr_krylov_amg(IA, JA3, val3.ravel(), b, it, amg)  # must NOT take the cached layout
+    assert st3 > 0
+    assert np.linalg.norm(b - oracle.bsr_spmv(IA, JA3, val3.ravel(), x3)) <= 1.0001 * it.tol * np.linalg.norm(b)
+    L.pnpb200_release_host_cache()
+
+
 @pytest.mark.parametrize("voltage", [0.0, -0.3, 0.1])
 def test_diode_damped_newton_matches_oracle(oracle, pkg, gpu_lib, voltage):
     """BASELINE configs[1] (pnp_diode, 40x4x4 on 2 x 0.2 x 0.2; zero, reverse and forward bias from the
@@ -322,10 +351,10 @@ def test_streamed_colour_launch_is_the_same_arithmetic(oracle, pkg, system):
     it, amg = pkg.default_params()
     rr = np.random.default_rng(12).uniform(-1, 1, P.N)
     out = {}
-    old = {k: os.environ.get(k) for k in ("PNPB200_GS_STREAM", "PNPB200_GS_STREAM_MIN")}
+    old = {k: os.environ.get(k) for k in ("PNPB200_GS_STREAM", "PNPB200_GS_STREAM_MIN", "PNPB200_GS_STREAM_MAXLEN")}
     try:
         for on in (1, 0):
-            os.environ["PNPB200_GS_STREAM"] = str(on); os.environ["PNPB200_GS_STREAM_MIN"] = "1"
+            os.environ["PNPB200_GS_STREAM"] = str(on); os.environ["PNPB200_GS_STREAM_MIN"] = "1"; os.environ["PNPB200_GS_STREAM_MAXLEN"] = "32"
             its = g.solve(it, amg)
             out[on] = (its, g.get_update(), g.apply_vcycle(rr))
     finally:
@@ -360,6 +389,20 @@ def test_streamed_passes_are_reproducible(pkg):
         for which in (9, 12, 2, 7, 0, 1, 8, 10):     # GS + delta (back), GS back / forward, forward from zero, y = A x, r = b - A x, -U x, b + L x
             out = g.debug_repeat_pass(which, 150)
             assert out[0] == 0, (which, out.tolist())
+        # level 1 (rows of up to ~29 blocks: the two-round instantiation of the streamed kernel), every colour group streamed
+        import os
+        old = {k: os.environ.get(k) for k in ("PNPB200_GS_STREAM_MIN", "PNPB200_GS_STREAM_MAXLEN")}
+        os.environ["PNPB200_GS_STREAM_MIN"] = "1"; os.environ["PNPB200_GS_STREAM_MAXLEN"] = "32"
+        try:
+            for which in (109, 107, 102, 112):
+                out = g.debug_repeat_pass(which, 300)
+                assert out[0] == 0, (which, out.tolist())
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
     finally:
         g.close()
 

@@ -40,7 +40,8 @@ if os.path.exists(tp):
     us = sum(l["gpu__time_duration.sum"] for l in sweep) / 1e3
     nv = 257 ** 3; nnzb = 253036801
     alg = nnzb * 76.0 + (nv + 1) * 4.0 + 3.0 * 3 * nv * 8 + 72.0 * nv + 3 * nv * 8
-    out = {"n": 256, "source": "gpurun_out/traffic_gsd_n256.csv (copied to profiles/%s_traffic_gsd_n256_launches.csv): ncu --profile-from-start off --metrics "
+    fmt = int(os.environ.get("VALUES_PER_BLOCK", "7"))
+    out = {"n": 256, "values_per_block": fmt, "kernel_bytes": alg - (16.0 * nnzb if fmt == 7 else 0.0), "source": "gpurun_out/traffic_gsd_n256.csv (copied to profiles/%s_traffic_gsd_n256_launches.csv): ncu --profile-from-start off --metrics "
            "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -k regex:gs_stream_kernel -c 8, "
            "python tools/probe_rows.py 256 9 1 (tools/ncu_traffic.sh); the sweep = the last 4 launches" % tag,
            "gs_sweep": {"kernel": "gs_stream_kernel<S_GSD=5>: backward sweep + delta, %d colour launches" % ncol,
