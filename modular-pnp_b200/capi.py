@@ -236,6 +236,20 @@ def lib():
     L.fasp_dvec_set.restype = None
     L.fasp_dvec_free.argtypes = [C.POINTER(dvector)]
     L.fasp_dvec_free.restype = None
+    # include/pnpb200/pnpb200_ns.h
+    L.pnpb200_ns_create.argtypes = [C.POINTER(H), C.c_int, _f8, C.c_int, _i4]
+    L.pnpb200_ns_destroy.argtypes = [H]
+    L.pnpb200_ns_destroy.restype = None
+    L.pnpb200_ns_sizes.argtypes = [H] + [C.POINTER(C.c_int)] * 4
+    L.pnpb200_ns_topology.argtypes = [H, _i4, _i4, _i4]
+    L.pnpb200_ns_set_parameters.argtypes = [H, _f8]
+    L.pnpb200_ns_set_dirichlet.argtypes = [H, C.c_int, _i4]
+    L.pnpb200_ns_set_solution.argtypes = [H, _f8, _f8, _f8]
+    L.pnpb200_ns_get_solution.argtypes = [H, _f8, _f8, _f8]
+    L.pnpb200_ns_assemble.argtypes = [H]
+    L.pnpb200_ns_get_system.argtypes = [H, C.POINTER(dCSRmat), C.POINTER(dvector)]
+    L.pnpb200_ns_residual.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.pnpb200_ns_add_update.argtypes = [H, _f8, C.c_double]
     _lib = L
     return L
 
@@ -662,3 +676,72 @@ def fasp_format_dcsr_dbsr(IA, JA, val, nb=3):
            np.ctypeslib.as_array(B.val, shape=(nb * nb * nnz,)).copy())
     lib().fasp_dbsr_free(C.byref(B))
     return out
+
+
+class PNPStokes:
+    """Device assembly of the PNP-Stokes Newton system (include/pnpb200/pnpb200_ns.h): mixed space P1^3 x RT1 x DG0,
+    dofs 3 v + k | 3 nv + facet | 3 nv + n_facets + cell (benchmarks/pnp_stokes/vector_linear_pnp_ns_forms.ufl)."""
+
+    def __init__(self, xyz, cells):
+        L = lib()
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1)
+        cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1)
+        self.nv, self.nc = xyz.size // 3, cells.size // 4
+        self.h = C.c_void_p()
+        _check(L.pnpb200_ns_create(C.byref(self.h), self.nv, xyz, self.nc, cells), "pnpb200_ns_create")
+        nf, nif, nd, nnz = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.pnpb200_ns_sizes(self.h, C.byref(nf), C.byref(nif), C.byref(nd), C.byref(nnz))
+        self.nf, self.n_interior, self.ndof, self.nnz = nf.value, nif.value, nd.value, nnz.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pnpb200_ns_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def topology(self):
+        cs = np.zeros(4 * self.nc, dtype=np.int32); cf = np.zeros(4 * self.nc, dtype=np.int32); fc = np.zeros(2 * self.nf, dtype=np.int32)
+        _check(lib().pnpb200_ns_topology(self.h, cs, cf, fc), "pnpb200_ns_topology")
+        return cs.reshape(-1, 4), cf.reshape(-1, 4), fc.reshape(-1, 2)
+
+    def set_parameters(self, par8):
+        _check(lib().pnpb200_ns_set_parameters(self.h, np.ascontiguousarray(par8, dtype=np.float64)), "pnpb200_ns_set_parameters")
+
+    def set_dirichlet(self, dofs):
+        d = np.ascontiguousarray(dofs, dtype=np.int32)
+        _check(lib().pnpb200_ns_set_dirichlet(self.h, len(d), d), "pnpb200_ns_set_dirichlet")
+
+    def set_solution(self, cc, uu, pp):
+        _check(lib().pnpb200_ns_set_solution(self.h, np.ascontiguousarray(cc, dtype=np.float64), np.ascontiguousarray(uu, dtype=np.float64),
+                                             np.ascontiguousarray(pp, dtype=np.float64)), "pnpb200_ns_set_solution")
+
+    def get_solution(self):
+        cc, uu, pp = np.zeros(3 * self.nv), np.zeros(self.nf), np.zeros(self.nc)
+        _check(lib().pnpb200_ns_get_solution(self.h, cc, uu, pp), "pnpb200_ns_get_solution")
+        return cc, uu, pp
+
+    def assemble(self):
+        _check(lib().pnpb200_ns_assemble(self.h), "pnpb200_ns_assemble")
+
+    def get_system(self):
+        """(IA, JA, val, b) of the mixed system as numpy arrays"""
+        IA = np.zeros(self.ndof + 1, dtype=np.int32); JA = np.zeros(self.nnz, dtype=np.int32); val = np.zeros(self.nnz)
+        b = np.zeros(self.ndof)
+        A = numpy_to_csr(IA, JA, val, self.ndof); bv = numpy_to_dvec(b)
+        A._keep = (IA, JA, val); A.IA = IA.ctypes.data_as(C.POINTER(INT)); A.JA = JA.ctypes.data_as(C.POINTER(INT))
+        A.val = val.ctypes.data_as(C.POINTER(REAL)); bv.val = b.ctypes.data_as(C.POINTER(REAL))
+        _check(lib().pnpb200_ns_get_system(self.h, C.byref(A), C.byref(bv)), "pnpb200_ns_get_system")
+        return IA, JA, val, b
+
+    def residual(self):
+        l2, li = C.c_double(), C.c_double()
+        _check(lib().pnpb200_ns_residual(self.h, C.byref(l2), C.byref(li)), "pnpb200_ns_residual")
+        return l2.value, li.value
+
+    def add_update(self, du, alpha=1.0):
+        _check(lib().pnpb200_ns_add_update(self.h, np.ascontiguousarray(du, dtype=np.float64), float(alpha)), "pnpb200_ns_add_update")

@@ -280,3 +280,30 @@ def damped_newton(backend, uu0, max_newton=250, rel_tol=1e-7, max_tol=1e-10, log
         if log:
             log(hist[-1])
     return hist, newton.converged()
+
+
+def rt_interpolate_constant(xyz, cells_sorted, cell_facets, facet_cells, w):
+    """Facet dofs of the lowest-order Raviart-Thomas interpolant of the constant field w on the basis of
+    include/pnpb200/pnpb200_ns.h (phi_i = s_i (x - v_i) / detJ, s = (-1, +1, -1, +1)): the dof of facet i of a cell is
+    s_i sign(detJ) 2 |F_i| (w . n_i), n_i the cell's outward unit normal. Returns (uu[n_facets], largest disagreement
+    between the two cells of an interior facet) — the disagreement is zero when the cells are UFC-ordered."""
+    X = np.asarray(xyz, dtype=np.float64).reshape(-1, 3)
+    cs = np.asarray(cells_sorted).reshape(-1, 4); cf = np.asarray(cell_facets).reshape(-1, 4)
+    nf = np.asarray(facet_cells).reshape(-1, 2).shape[0]
+    uu = np.full(nf, np.nan); mismatch = 0.0
+    w = np.asarray(w, dtype=np.float64)
+    for c in range(cs.shape[0]):
+        v = X[cs[c]]
+        detJ = np.linalg.det(v[1:] - v[0])
+        for i in range(4):
+            a, b, d = v[[j for j in range(4) if j != i]]
+            n2 = np.cross(b - a, d - a)                    # |n2| = 2 |F|
+            if np.dot(n2, a - v[i]) < 0:
+                n2 = -n2
+            val = (1.0 if i & 1 else -1.0) * np.sign(detJ) * np.dot(w, n2)
+            f = cf[c, i]
+            if np.isnan(uu[f]):
+                uu[f] = val
+            else:
+                mismatch = max(mismatch, abs(uu[f] - val))
+    return uu, mismatch

@@ -65,6 +65,13 @@ def lib():
         L.orc_marker_element.restype = C.c_double
         L.orc_entropy_indicator.argtypes = [C.c_int, _f8, C.c_int, _i4, _f8, _f8, _f8, _f8]
         L.orc_error_norms.argtypes = [C.c_int, _f8, C.c_int, _i4, _f8, _f8, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_ns_cell_a.argtypes = [_f8] * 5
+        L.orc_ns_cell_L.argtypes = [_f8] * 6
+        L.orc_ns_facet_a.argtypes = [_f8] * 4 + [C.c_int] * 2
+        L.orc_ns_facet_L.argtypes = [_f8] * 5 + [C.c_int] * 2
+        L.orc_ns_assemble.argtypes = [C.c_int, _f8, C.c_int, _i4, _i4, C.c_int, _i4, _f8, _f8, _f8, _f8, C.c_char_p,
+                                      _i4, _i4, _f8, _f8]
+        L.orc_ns_assemble.restype = C.c_long
         L.orc_csr_to_bsr3_count.argtypes = [C.c_int, _i4, _i4, _i4]
         L.orc_csr_to_bsr3_fill.argtypes = [C.c_int, _i4, _i4, _f8, _i4, _i4, _f8]
         L.orc_bsr_spmv.argtypes = [C.c_int, _i4, _i4, _f8, C.c_double, _f8, C.c_double, _f8]
@@ -338,3 +345,55 @@ def newton_exact(nx, ny, nz, lx=2.0, ly=0.4, lz=0.4, param=None, max_newton=15, 
     lib().orc_newton_exact(nx, ny, nz, lx, ly, lz, C.byref(param), max_newton, rel_tol, max_tol,
                            1 if use_eafe else 0, uu.ctypes.data, C.byref(res))
     return uu, res
+
+
+# ---- PNP-Stokes mixed system (benchmarks/pnp_stokes; oracle/ns_elements.cpp) --------------------------------------
+REF_NS_PATH = os.path.join(_HERE, "_ref", "libpnpref_ns.so")
+NS_PAR_DEFAULT = np.array([1.0, 1.0, 1.0, 1.0, -1.0, 0.1, 1.0, 1.0])      # benchmarks/pnp_stokes/main.cpp:123-132
+
+
+def ns_topology(cells):
+    """UFC ordering + facet numbering restated with numpy (dolfin::Mesh::order / init(2)): cells sorted ascending,
+    facet i of a cell opposite its i-th vertex, facets numbered in lexicographic order of their vertex triples,
+    facet_cells = (lower cell, higher cell or -1)."""
+    cs = np.sort(np.asarray(cells, dtype=np.int64).reshape(-1, 4), axis=1)
+    nc = cs.shape[0]
+    tri = np.stack([np.delete(cs, i, axis=1) for i in range(4)], axis=1).reshape(-1, 3)      # row 4 c + i
+    uniq, inv = np.unique(tri, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    nf = uniq.shape[0]
+    cell_facets = inv.reshape(nc, 4).astype(np.int32)
+    facet_cells = -np.ones((nf, 2), dtype=np.int32)
+    for c in range(nc):
+        for i in range(4):
+            f = cell_facets[c, i]
+            facet_cells[f, 0 if facet_cells[f, 0] < 0 else 1] = c
+    return np.ascontiguousarray(cs.astype(np.int32)), cell_facets, facet_cells
+
+
+def ns_assemble(xyz, cells_sorted, cell_facets, facet_cells, cc, uu, pp, par=None, bc=None, use_ref=False):
+    """dolfin::assemble(a), assemble(L) + DirichletBC::apply restated for the mixed P1^3 x RT1 x DG0 system
+    (src/pde.cpp:542-555); returns (scipy CSR, rhs). use_ref drives the reference's own compiled kernels."""
+    import scipy.sparse as sp
+    par = NS_PAR_DEFAULT if par is None else np.ascontiguousarray(par, dtype=np.float64)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64); nv = xyz.size // 3
+    cells_sorted = np.ascontiguousarray(cells_sorted, dtype=np.int32); nc = cells_sorted.size // 4
+    cell_facets = np.ascontiguousarray(cell_facets, dtype=np.int32)
+    facet_cells = np.ascontiguousarray(facet_cells, dtype=np.int32); nf = facet_cells.size // 2
+    nif = int((facet_cells.reshape(-1, 2)[:, 1] >= 0).sum())
+    ndof = 3 * nv + nf + nc
+    n = 289 * nc + 1156 * nif
+    row = np.zeros(n, dtype=np.int32); col = np.zeros(n, dtype=np.int32); val = np.zeros(n); rhs = np.zeros(ndof)
+    got = lib().orc_ns_assemble(nv, xyz.reshape(-1), nc, cells_sorted.reshape(-1), cell_facets.reshape(-1), nf,
+                                facet_cells.reshape(-1), np.ascontiguousarray(cc, dtype=np.float64),
+                                np.ascontiguousarray(uu, dtype=np.float64), np.ascontiguousarray(pp, dtype=np.float64), par,
+                                REF_NS_PATH.encode() if use_ref else None, row, col, val, rhs)
+    if got != n:
+        raise RuntimeError("orc_ns_assemble failed (%d)" % got)
+    A = sp.coo_matrix((val, (row, col)), shape=(ndof, ndof)).tocsr()
+    A.sum_duplicates(); A.sort_indices()
+    if bc is not None and len(bc):
+        keep = np.ones(ndof); keep[bc] = 0.0
+        A = (sp.diags(keep) @ A + sp.diags(1.0 - keep)).tocsr()
+        rhs[bc] = 0.0
+    return A, rhs

@@ -83,6 +83,22 @@ void orc_entropy_indicator(int nv, const double* xyz, int nc, const int* cells, 
 void orc_error_norms(int nv, const double* xyz, int nc, const int* cells, const double* uu,
                      const double* exact, double* l2, double* h1);
 
+/* ---- PNP-Stokes element kernels (benchmarks/pnp_stokes/vector_linear_pnp_ns_forms.ufl:45-74; oracle/ns_elements.cpp):
+ * P1^3 x RT1 x DG0, 17 dofs per cell, macro element of an interior facet = 34. par8 = {permittivity, diffusivity0,
+ * valency0, diffusivity1, valency1, mu, penalty1, penalty2}. Pinned against oracle/_ref/libpnpref_ns.so. ---- */
+void orc_ns_cell_a(double* A289, const double* cc12, const double* uu4, const double* par8, const double* xyz12);
+void orc_ns_cell_L(double* b17, const double* cc12, const double* uu4, const double* pp1, const double* par8, const double* xyz12);
+void orc_ns_facet_a(double* A1156, const double* par8, const double* xyz12_0, const double* xyz12_1, int facet_0, int facet_1);
+void orc_ns_facet_L(double* b34, const double* uu8, const double* par8, const double* xyz12_0, const double* xyz12_1,
+                    int facet_0, int facet_1);
+
+/* dolfin::assemble of the mixed PNP-Stokes system restated (cell loop + interior-facet loop) as COO triplets
+ * (289 nc + 1156 n_interior entries, zeros included); ref_lib = path of oracle/_ref/libpnpref_ns.so to drive the
+ * reference's own kernels, NULL = the restatement. Returns the number of triplets, -1 if ref_lib cannot be loaded. */
+long orc_ns_assemble(int nv, const double* xyz, int nc, const int* cells_sorted, const int* cell_facets, int nf,
+                     const int* facet_cells, const double* cc, const double* uu, const double* pp, const double* par8,
+                     const char* ref_lib, int* coo_row, int* coo_col, double* coo_val, double* rhs);
+
 /* ---- FASP-restated linear algebra (BSR nb=3) ---- */
 void orc_csr_to_bsr3_count(int n, const int* IA, const int* JA, int* bIA);
 void orc_csr_to_bsr3_fill(int n, const int* IA, const int* JA, const double* val,

@@ -5,6 +5,8 @@
 // K = J^{-1} row-major; det = det J (signed).
 #ifndef PNPB200_ORACLE_SHIM_UFC_GEOMETRY_H
 #define PNPB200_ORACLE_SHIM_UFC_GEOMETRY_H
+#include <cmath>
+#include <cstddef>
 
 inline void compute_jacobian_tetrahedron_3d(double* J, const double* coordinate_dofs)
 {
@@ -29,4 +31,24 @@ inline void compute_jacobian_inverse_tetrahedron_3d(double* K, double& det, cons
   K[3] = d_01 / det; K[4] = d_11 / det; K[5] = d_21 / det;
   K[6] = d_02 / det; K[7] = d_12 / det; K[8] = d_22 / det;
 }
+
+// shortest / longest edge of facet `facet` (opposite local vertex `facet`); the interior-facet kernels of
+// benchmarks/pnp_stokes/vector_linear_pnp_ns_forms.h:17253-17259 call them (their forms do not use the values)
+inline void facet_edge_lengths_tetrahedron_3d(double& lo, double& hi, std::size_t facet, const double* x)
+{
+  static const int fv[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+  lo = 1e300; hi = 0.0;
+  for (int e = 0; e < 3; ++e) {
+    const int a = fv[facet][e], b = fv[facet][(e + 1) % 3];
+    double l2 = 0.0;
+    for (int d = 0; d < 3; ++d) l2 += (x[3 * a + d] - x[3 * b + d]) * (x[3 * a + d] - x[3 * b + d]);
+    const double l = std::sqrt(l2);
+    if (l < lo) lo = l;
+    if (l > hi) hi = l;
+  }
+}
+inline void compute_min_facet_edge_length_tetrahedron_3d(double& v, std::size_t facet, const double* x)
+{ double hi; facet_edge_lengths_tetrahedron_3d(v, hi, facet, x); }
+inline void compute_max_facet_edge_length_tetrahedron_3d(double& v, std::size_t facet, const double* x)
+{ double lo; facet_edge_lengths_tetrahedron_3d(lo, v, facet, x); }
 #endif

@@ -2,7 +2,7 @@
 (oracle/_ref/libpnpref.so, built by oracle/Makefile from /root/reference/include/EAFE.h and
 benchmarks/pnp_exact_solution/vector_linear_pnp_forms.h). Run in the authoring container only
 (needs /root/reference); the vectors travel with the repo.
-    python tests/golden/make_golden.py [main] [diode] [marker] [newton]
+    python tests/golden/make_golden.py [main] [diode] [marker] [newton] [ns]
 """
 import ctypes as C
 import os
@@ -128,7 +128,53 @@ def newton():
     print("newton history written:", out["newton_its"], out["krylov_its"])
 
 
+def ns():
+    """golden vectors of the PNP-Stokes forms (P1^3 x RT1 x DG0) from the reference's own compiled kernels
+    (oracle/_ref/libpnpref_ns.so <- benchmarks/pnp_stokes/vector_linear_pnp_ns_forms.h): element tensors of random
+    cells / facet pairs, and the assembled mixed system of a 4x2x2 box driven by those kernels."""
+    ref = C.CDLL(O.REF_NS_PATH)
+    f8 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    ref.ref_ns_cell_a.argtypes = [f8] * 5
+    ref.ref_ns_cell_L.argtypes = [f8] * 6
+    ref.ref_ns_facet_a.argtypes = [f8] * 6 + [C.c_int] * 2
+    ref.ref_ns_facet_L.argtypes = [f8] * 7 + [C.c_int] * 2
+    rng = np.random.default_rng(1357)
+    n = 32
+    X0 = np.zeros((n, 12)); X1 = np.zeros((n, 12)); CC = np.zeros((n, 24)); UU = np.zeros((n, 8)); PP = np.zeros((n, 2))
+    PAR = np.zeros((n, 8)); F = np.zeros((n, 2), dtype=np.int32)
+    A_cell = np.zeros((n, 289)); b_cell = np.zeros((n, 17)); A_facet = np.zeros((n, 1156)); b_facet = np.zeros((n, 34))
+    base = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1.0])
+    for t in range(n):
+        x0 = ((base + 0.2 * rng.uniform(-1, 1, 12)) * rng.uniform(0.05, 2.0)).reshape(4, 3)
+        if t % 2:
+            x0[[1, 2]] = x0[[2, 1]]                      # negatively oriented cells too (detJ < 0)
+        f0, f1 = int(rng.integers(4)), int(rng.integers(4))
+        face = [i for i in range(4) if i != f0]
+        x1 = np.zeros((4, 3))
+        x1[[i for i in range(4) if i != f1]] = x0[face]  # same vertex order on both sides (UFC ordering)
+        x1[f1] = 2.0 * x0[face].mean(0) - x0[f0] + 0.1 * rng.uniform(-1, 1, 3) * np.abs(x0).max()
+        X0[t] = x0.reshape(-1); X1[t] = x1.reshape(-1); F[t] = (f0, f1)
+        CC[t] = rng.uniform(-1.5, 1.5, 24); UU[t] = rng.uniform(-1, 1, 8); PP[t] = rng.uniform(-1, 1, 2)
+        PAR[t] = O.NS_PAR_DEFAULT * rng.uniform(0.5, 2.0, 8)
+        ref.ref_ns_cell_a(A_cell[t], CC[t, :12].copy(), UU[t, :4].copy(), PAR[t], X0[t])
+        ref.ref_ns_cell_L(b_cell[t], CC[t, :12].copy(), UU[t, :4].copy(), PP[t, :1].copy(), PAR[t], X0[t])
+        ref.ref_ns_facet_a(A_facet[t], CC[t], UU[t], PAR[t], X0[t], X1[t], f0, f1)
+        ref.ref_ns_facet_L(b_facet[t], CC[t], UU[t], PP[t], PAR[t], X0[t], X1[t], f0, f1)
+    P = O.Problem(4, 2, 2, lx=2.0, ly=1.0, lz=1.0)
+    cs, cf, fc = O.ns_topology(P.cells)
+    nv, nc, nf = P.xyz.size // 3, cs.shape[0], fc.shape[0]
+    cc = rng.uniform(-1, 1, 3 * nv); uu = rng.uniform(-1, 1, nf); pp = rng.uniform(-1, 1, nc)
+    bc = np.flatnonzero(np.repeat(np.abs(np.abs(P.xyz.reshape(-1, 3)[:, 0]) - 1.0) < 1e-12, 3)).astype(np.int32)
+    A, b = O.ns_assemble(P.xyz, cs, cf, fc, cc, uu, pp, bc=bc, use_ref=True)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ns_kernels.npz"), X0=X0, X1=X1, F=F, CC=CC, UU=UU, PP=PP, PAR=PAR,
+                        A_cell=A_cell, b_cell=b_cell, A_facet=A_facet, b_facet=b_facet,
+                        box=np.array([4, 2, 2]), lengths=np.array([2.0, 1.0, 1.0]), cc=cc, uu=uu, pp=pp, bc=bc,
+                        cells_sorted=cs, cell_facets=cf, facet_cells=fc,
+                        IA=A.indptr.astype(np.int32), JA=A.indices.astype(np.int32), A=A.data, b=b)
+    print("PNP-Stokes golden vectors written")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["main", "diode", "marker"]
     for w in which:
-        {"main": main, "diode": diode, "marker": marker, "newton": newton}[w]()
+        {"main": main, "diode": diode, "marker": marker, "newton": newton, "ns": ns}[w]()

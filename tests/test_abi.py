@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_functions():
     names = []
-    for hdr in ("pnpb200.h", "fasp_compat.h"):
+    for hdr in ("pnpb200.h", "pnpb200_ns.h", "fasp_compat.h"):
         src = open(os.path.join(ROOT, "include", "pnpb200", hdr)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         src = re.sub(r"typedef struct[^;{]*\{.*?\}[^;]*;", "", src, flags=re.S)
