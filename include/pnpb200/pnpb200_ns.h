@@ -52,8 +52,8 @@ int  pnpb200_ns_get_solution(pnpb200_ns_system* s, double* cc, double* uu, doubl
 
 /* matrix and right-hand side of the Newton system at the current iterate (device resident) */
 int  pnpb200_ns_assemble(pnpb200_ns_system* s);
-/* copies them out: A with row = col = n_dofs, nnz as pnpb200_ns_sizes reports, IA / JA / val allocated by the caller
- * (fasp_dcsr_create); b with n_dofs entries. Columns ascending inside a row. Either may be NULL. */
+/* copies them out: A with row = col = n_dofs, nnz as pnpb200_ns_sizes reports, IA / JA / val allocated by the caller;
+ * b with n_dofs entries. Columns ascending inside a row. Either may be NULL. */
 int  pnpb200_ns_get_system(pnpb200_ns_system* s, dCSRmat* A, dvector* b);
 /* l2 and max norm of the residual vector (L assembled at the current iterate, Dirichlet rows zero) */
 int  pnpb200_ns_residual(pnpb200_ns_system* s, double* l2, double* linf);

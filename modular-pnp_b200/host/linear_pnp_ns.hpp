@@ -7,13 +7,17 @@
 //   EigenVector_to_dvector_block       linear_pnp_ns.cpp:111-130
 //   setup_fasp_linear_algebra          linear_pnp_ns.cpp:132-176 (four fasp_dcsr_getblk cuts, zero initial guess)
 //   fasp_solve                         linear_pnp_ns.cpp:178-235 (status < 0: warning, the update is still scattered)
-// Assembly of the RT1 x DG0 Stokes forms (vector_linear_pnp_ns_forms.ufl) stays with the caller.
+// Assembly: either the caller hands in the assembled mixed-space matrix (a DOLFIN build), or the system is
+// assembled on the device from the mesh and the current iterate (pnpb200/pnpb200_ns.h: the P1^3 x RT1 x DG0 forms of
+// vector_linear_pnp_ns_forms.ufl incl. the interior-facet terms) — fasp_solve(pnpb200_ns_system*), compute_residual.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
 #include <vector>
 #include "pnpb200/pnpb200.h"
+#include "pnpb200/pnpb200_ns.h"
+#include <string>
 
 class Linear_PNP_NS {
 public:
@@ -96,6 +100,47 @@ public:
     for (int i = 0; i < _pnp_dofs.row; ++i) update[_pnp_dofs.val[i]] = _fasp_soln.val[i];
     for (int i = 0; i < _stokes_dofs.row; ++i) update[_stokes_dofs.val[i]] = _fasp_soln.val[_pnp_dofs.row + i];
     return status;
+  }
+
+  // Device-assembled variants (the system object owns mesh, dofmap, Dirichlet dofs and the current iterate):
+  // get_dofs_fasp for this library's numbering 3 v + k | 3 nv + facet | 3 nv + n_facets + cell
+  void get_dofs_fasp(pnpb200_ns_system* sys, int n_vertices)
+  {
+    int nf = 0, nif = 0, nd = 0, nnz = 0;
+    pnpb200_ns_sizes(sys, &nf, &nif, &nd, &nnz);
+    const int nc = nd - 3 * n_vertices - nf;
+    std::vector<std::vector<int>> dof_map(5);
+    for (int v = 0; v < n_vertices; ++v) for (int k = 0; k < 3; ++k) dof_map[k].push_back(3 * v + k);
+    for (int f = 0; f < nf; ++f) dof_map[3].push_back(3 * n_vertices + f);
+    for (int c = 0; c < nc; ++c) dof_map[4].push_back(3 * n_vertices + nf + c);
+    get_dofs_fasp(dof_map, {0, 1, 2}, {3, 4});
+  }
+  // Linear_PNP_NS::fasp_solve (linear_pnp_ns.cpp:178-235): setup_linear_algebra on the device, the four getblk cuts,
+  // the block solve, and the update added to the iterate (:216-232)
+  INT fasp_solve(pnpb200_ns_system* sys)
+  {
+    int nf = 0, nif = 0, nd = 0, nnz = 0;
+    pnpb200_ns_sizes(sys, &nf, &nif, &nd, &nnz);
+    if (pnpb200_ns_assemble(sys) != FASP_SUCCESS) return ERROR_UNKNOWN;
+    std::vector<INT> IA(nd + 1), JA(nnz); std::vector<REAL> val(nnz), rhs(nd);
+    dCSRmat A; A.row = A.col = nd; A.nnz = nnz; A.IA = IA.data(); A.JA = JA.data(); A.val = val.data();
+    dvector b; b.row = nd; b.val = rhs.data();
+    INT status = pnpb200_ns_get_system(sys, &A, &b);
+    std::vector<double> update;
+    if (status == FASP_SUCCESS) {
+      status = fasp_solve(&A, b.val, update);
+      pnpb200_ns_add_update(sys, update.data(), 1.0);       // like the reference: the update is applied whatever the status
+    }
+    return status;
+  }
+  // PDE::compute_residual (src/pde.cpp:377-397): "l2" or "max" norm of the residual vector
+  double compute_residual(pnpb200_ns_system* sys, const std::string& norm_type)
+  {
+    double l2 = -1.0, linf = -1.0;
+    if (pnpb200_ns_residual(sys, &l2, &linf) != FASP_SUCCESS) return -1.0;
+    if (norm_type == "l2") return l2;
+    if (norm_type == "max") return linf;
+    return -1.0;
   }
 
   const ivector& pnp_dofs() const { return _pnp_dofs; }

@@ -307,3 +307,31 @@ def rt_interpolate_constant(xyz, cells_sorted, cell_facets, facet_cells, w):
             else:
                 mismatch = max(mismatch, abs(uu[f] - val))
     return uu, mismatch
+
+
+def pnp_stokes_problem(xyz, cells_sorted, cell_facets, facet_cells, lx):
+    """Data of benchmarks/pnp_stokes/main.cpp:123-153 on a box of length lx in x, in the dof numbering of
+    include/pnpb200/pnpb200_ns.h: parameters (permittivity 1, D 1 / 1, valencies +1 / -1, mu 0.1, penalties 1 / 1),
+    initial guess (cation, anion, potential) linear in x from (0, -2.30258509299, 1) to (-2.30258509299, 0, -1)
+    (main.cpp:147), Dirichlet dofs of the Newton update.
+    Boundary conditions: the PNP components on the two x faces as Linear_PNP_NS::init_BC (linear_pnp_ns.cpp:287-304).
+    The reference's velocity / pressure conditions (a DirichletBC on the single corner point, one on a facet marker of
+    the DG0 space, :295-318) select no RT1 / DG0 dof with DOLFIN's topological search, which leaves the constant
+    velocity fields in the kernel of the Newton matrix; this driver closes the system with the wall condition
+    u.n = 0 (all boundary-facet velocity dofs; the initial velocity is 0 instead of (1, 0, 0)) and pins the pressure of
+    cell 0."""
+    X = np.asarray(xyz, dtype=np.float64).reshape(-1, 3)
+    nv = X.shape[0]
+    fc = np.asarray(facet_cells).reshape(-1, 2)
+    nf, nc = fc.shape[0], np.asarray(cells_sorted).reshape(-1, 4).shape[0]
+    left = np.array([0.0, -2.30258509299, 1.0]); right = np.array([-2.30258509299, 0.0, -1.0])
+    t = (X[:, 0] + lx / 2) / lx
+    cc = (left[None, :] * (1 - t)[:, None] + right[None, :] * t[:, None]).reshape(-1)
+    on_x = np.flatnonzero(np.abs(np.abs(X[:, 0]) - lx / 2) < 1e-5 * lx)
+    bc_pnp = (3 * on_x[:, None] + np.arange(3)[None, :]).reshape(-1)
+    bc_vel = 3 * nv + np.flatnonzero(fc[:, 1] < 0)
+    bc_pres = np.array([3 * nv + nf])
+    return dict(par=np.array([1.0, 1.0, 1.0, 1.0, -1.0, 0.1, 1.0, 1.0]), cc=cc, uu=np.zeros(nf), pp=np.zeros(nc),
+                bc_dofs=np.concatenate([bc_pnp, bc_vel, bc_pres]).astype(np.int32),
+                pnp_dofs=np.arange(3 * nv, dtype=np.int32), velocity_dofs=(3 * nv + np.arange(nf)).astype(np.int32),
+                pressure_dofs=(3 * nv + nf + np.arange(nc)).astype(np.int32))
