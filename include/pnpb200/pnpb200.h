@@ -191,6 +191,8 @@ int  pnpb200_set_timing_detail(pnpb200_handle* h, int on);
  * out[3] Stokes block solves, out[4] their Krylov iterations in total; *relres = final true
  * relative residual of the coupled system */
 int  pnpb200_last_block_solve_stats(int out[5], double* relres);
+/* inner velocity-block solves of the same call (ns.dat's _v set): {solves, Krylov iterations} */
+int  pnpb200_last_block_velocity_stats(int out[2]);
 /* copy level-l hierarchy pieces to the host (FASP layout): matrix, aggregate map (length
  * level_rows[l], -1 = isolated), GS row order (rows sorted by colour). */
 int  pnpb200_get_level_matrix(pnpb200_handle* h, int level, dBSRmat* A_out);

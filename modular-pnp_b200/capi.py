@@ -320,6 +320,9 @@ def solve_pnp_stokes(blocks, b, n_vel, n_pres, params=None, x0=None):
     L.pnpb200_last_block_solve_stats(C.byref(out), C.byref(rr))
     stats = {"outer_its": out[0], "pnp_solves": out[1], "pnp_its": out[2], "stokes_solves": out[3], "stokes_its": out[4],
              "relres": rr.value}
+    vout = (C.c_int * 2)()
+    L.pnpb200_last_block_velocity_stats(C.byref(vout))
+    stats["velocity_solves"], stats["velocity_its"] = vout[0], vout[1]
     return st, xv._keep, stats
 
 

@@ -262,9 +262,20 @@ int block_pnp_stokes_solve(BlockSystem& S, const double* b, double* x, BlockStat
     // z_u = one AMG cycle of the velocity hierarchy (sweep space inside), on the velocity handle's stream
     link.pass(so, sv);
     PNP_CUDA(cudaMemcpyAsync(vr.p, r, (size_t)nu * sizeof(double), cudaMemcpyDeviceToDevice, sv));
-    vec_to_sweep(Av, vr.p, vrs.p, sv);
-    amg_vcycle(hv, S.cfg_vel, vrs.p, vzs.p);
-    vec_from_sweep(Av, vzs.p, vz.p, sv);
+    if (S.vel_krylov) {
+      // ns.dat: solver_type_v = vFGMRES, precond_type_v = AMG, itsolver_tol_v — the div-div part of the RT1 velocity
+      // block has a large near-kernel that one cycle of an aggregation hierarchy does not resolve; with an accurate
+      // velocity solve the outer Stokes iteration count is mesh independent (profiles/r02_stokes_precond.txt)
+      const int vits = fgmres_solve(hv, S.cfg_vel, vr.p, vz.p, true);
+      ++stats.vel_solves;
+      if (vits > 0) stats.vel_its += vits;
+      else if (vits == ERROR_SOLVER_MAXIT) stats.vel_its += S.cfg_vel.maxit;
+      else if (vits < 0) throw Error(vits, "velocity block solve failed");
+    } else {
+      vec_to_sweep(Av, vr.p, vrs.p, sv);
+      amg_vcycle(hv, S.cfg_vel, vrs.p, vzs.p);
+      vec_from_sweep(Av, vzs.p, vz.p, sv);
+    }
     PNP_CUDA(cudaMemcpyAsync(z, vz.p, (size_t)nu * sizeof(double), cudaMemcpyDeviceToDevice, sv));
     link.pass(sv, so);
     if (nq > 0) {

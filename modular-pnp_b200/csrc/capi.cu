@@ -1158,7 +1158,15 @@ INT fasp_solver_bdcsr_krylov_pnp_stokes(block_dCSRmat* A, dvector* b, dvector* x
       its_ns.stop_type = itparam_stokes->stop_type; its_ns.maxit = itparam_stokes->maxit; its_ns.tol = itparam_stokes->tol;
       its_ns.restart = itparam_stokes->restart; its_ns.print_level = itparam_stokes->print_level;
       S.cfg_ns = make_config(&its_ns, nullptr);
-      S.cfg_vel = make_config(nullptr, &amgparam_stokes->param_v);
+      // velocity block (ns.dat's _v set): AMG-preconditioned flexible GMRES to itsolver_tol_v, or ONE AMG cycle when the
+      // file asks for no inner iteration (itsolver_maxit_v <= 1)
+      itsolver_param its_v = its_ns;
+      its_v.maxit = itparam_stokes->pre_maxit_v; its_v.tol = itparam_stokes->pre_tol_v;
+      its_v.restart = itparam_stokes->pre_restart_v > 0 ? itparam_stokes->pre_restart_v : its_ns.restart;
+      its_v.print_level = 0;
+      S.cfg_vel = make_config(&its_v, &amgparam_stokes->param_v);
+      S.vel_krylov = itparam_stokes->pre_maxit_v > 1 && itparam_stokes->pre_tol_v > 0.0;
+      if (const char* e = getenv("PNPB200_STOKES_VEL_KRYLOV")) S.vel_krylov = atoi(e) != 0;
       DevBuf<double> db, dx; db.alloc((size_t)np + ns, s); dx.alloc((size_t)np + ns, s);
       db.upload(b->val, (size_t)np + ns); dx.upload(x->val, (size_t)np + ns);
       status = block_pnp_stokes_solve(S, db.p, dx.p, &g_block_stats);
@@ -1189,6 +1197,12 @@ int pnpb200_last_block_solve_stats(int out[5], double* relres)
   if (out) { out[0] = g_block_stats.outer_its; out[1] = g_block_stats.pnp_solves; out[2] = g_block_stats.pnp_its;
              out[3] = g_block_stats.stokes_solves; out[4] = g_block_stats.stokes_its; }
   if (relres) *relres = g_block_stats.relres;
+  return FASP_SUCCESS;
+}
+
+int pnpb200_last_block_velocity_stats(int out[2])
+{
+  if (out) { out[0] = g_block_stats.vel_solves; out[1] = g_block_stats.vel_its; }
   return FASP_SUCCESS;
 }
 

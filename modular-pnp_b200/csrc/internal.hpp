@@ -331,7 +331,7 @@ void csr_upload(const dCSRmat* A, DevCsr& D, cudaStream_t s);
 // y[i - r0] = beta * y[i - r0] + alpha * sum_{c0 <= j < c1} A_ij x[j - c0]   for rows r0 <= i < r1
 void csr_spmv(const DevCsr& A, int r0, int r1, int c0, int c1, double alpha, const double* x, double beta, double* y,
               cudaStream_t s);
-struct BlockStats { int outer_its = 0, pnp_solves = 0, pnp_its = 0, stokes_solves = 0, stokes_its = 0; double relres = 0; };
+struct BlockStats { int outer_its = 0, pnp_solves = 0, pnp_its = 0, stokes_solves = 0, stokes_its = 0, vel_solves = 0, vel_its = 0; double relres = 0; };
 struct BlockSystem {
   Handle* outer = nullptr;      // stream, reduction scratch and Krylov storage of the outer iteration
   Handle* pnp = nullptr;        // PNP block as BSR-T (3 dofs per vertex) + its AMG hierarchy
@@ -340,6 +340,7 @@ struct BlockSystem {
   int np = 0, ns = 0, nu = 0, npres = 0;
   DevBuf<double> sinv;          // npres: inverse of the diagonal of the SIMPLE Schur complement
   SolverConfig cfg_outer, cfg_pnp, cfg_ns, cfg_vel;
+  bool vel_krylov = true;       // velocity block: inner AMG-FGMRES (ns.dat's _v parameters) instead of one AMG cycle
 };
 // outer FGMRES with the block upper-triangular preconditioner; b, x device vectors of length np + ns
 int block_pnp_stokes_solve(BlockSystem& S, const double* b, double* x, BlockStats* st);
