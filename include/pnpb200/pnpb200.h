@@ -232,6 +232,9 @@ int  pnpb200_apply_matrix(pnpb200_handle* h, const double* x, double* y);
  * it to every rank (bench.py uses torch.distributed), then every rank calls pnpb200_comm_init. */
 int  pnpb200_comm_unique_id(unsigned char id[128]);
 int  pnpb200_comm_init(pnpb200_handle* h, const unsigned char id[128], int rank, int n_ranks);
+/* halo exchanges issued so far: out[0] through the peer-memory kernel (one launch: pack, NVLink stores into the
+ * neighbours' receive slots, flags, unpack), out[1] through NCCL send / recv (fallback, PNPB200_HALO_IPC=0) */
+int  pnpb200_comm_halo_counts(const pnpb200_handle* h, long long out[2]);
 /* neighbour k: send the owned vertices send_idx[send_ptr[k] .. send_ptr[k+1]) (in that order) and
  * receive its values into the local ghost vertices [recv_ptr[k], recv_ptr[k+1]). Call before
  * pnpb200_set_dirichlet / after create. */

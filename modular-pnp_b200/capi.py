@@ -414,6 +414,11 @@ class PNP:
         color = np.ascontiguousarray(color, dtype=np.int32)
         _check(self.L.pnpb200_set_coloring(self.h, int(color.max()) + 1 if n_colors is None else int(n_colors), color), "set_coloring")
 
+    def halo_counts(self):
+        out = (C.c_longlong * 2)()
+        self.L.pnpb200_comm_halo_counts(self.h, out)
+        return int(out[0]), int(out[1])
+
     def comm_init(self, unique_id, rank, nranks):
         _check(self.L.pnpb200_comm_init(self.h, bytes(unique_id), rank, nranks), "comm_init")
 

@@ -1309,6 +1309,7 @@ void amg_setup_chain(Handle& h, Hierarchy& H, const SolverConfig& cfg)
     Level& C = *lv[l + 1];
     g_phase = cfg.print_level >= 3; g_phase_lvl = l + H.level_offset;
     if (!coarsen_symbolic(h, L, C, theta)) break;
+    C.halo.ipc_slot = l + 1 + H.level_offset; C.halo.ipc_state = 0;     // peer-memory exchange: slot of this level (comm.cu)
     { PHASE("rap_numeric"); rap_numeric(h, L, C); }
     alloc_level_vectors(C, s);
     ++l;

@@ -82,6 +82,7 @@ int solve_current(Handle& h, const itsolver_param* it, const AMG_param* amg, int
   { EventSpan e(h, h.stats.ms_setup); if (cfg.use_amg) amg_setup(h, cfg); else if (cfg.use_ilu) ilu_setup(h, cfg.ilu_lfil); e.stop(); }
   int st;
   { EventSpan e(h, h.stats.ms_krylov); st = fgmres_solve(h, cfg, h.rhs.p, h.du.p, true); e.stop(); }
+  if (h.comm.active()) comm_check_ipc_error(h);     // a peer-memory halo exchange that gave up waiting for its neighbour
   if (status_its) *status_its = st;
   return FASP_SUCCESS;
 }

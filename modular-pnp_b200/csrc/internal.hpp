@@ -53,12 +53,32 @@ struct BsrT {
 // halo lists of one level (block-row granularity): neighbour k gets the owned rows
 // send_idx[send_ptr[k] .. send_ptr[k+1]) and fills the local ghost rows [recv_ptr[k], recv_ptr[k+1])
 // (ghost rows are the last rows in row-id AND in sweep order)
+// Peer-memory halo exchange (comm.cu): what ONE kernel launch needs to pack the boundary rows, store them into the
+// neighbours' receive buffers over NVLink, publish an epoch flag, wait for the neighbours' flags and unpack. Passed to the
+// kernel by value (captured into the coarse-level CUDA graph like any other argument).
+constexpr int IPC_MAX_NBR = 32;
+struct HaloIpcArgs {
+  int nnbr = 0;
+  double* peer_recv[IPC_MAX_NBR];                 // neighbour's receive buffer (mapped through CUDA IPC)
+  unsigned long long* peer_flag[IPC_MAX_NBR];     // the flag slot the neighbour watches for this rank
+  int peer_goff[IPC_MAX_NBR];                     // ghost-row offset of this rank's rows in the neighbour's receive buffer
+  int send_beg[IPC_MAX_NBR + 1];                  // this rank's send list, per neighbour
+  int recv_off[IPC_MAX_NBR], recv_cnt[IPC_MAX_NBR];    // ghost rows of neighbour k: offset behind the owned rows, count
+  int blk_beg[IPC_MAX_NBR + 1];                   // CTAs [blk_beg[k], blk_beg[k+1]) serve neighbour k
+  double* recv = nullptr; int cap = 0;            // this rank's receive buffer: 2 halves x cap rows x 4 doubles (cap is the same on every rank)
+  int ghost0 = 0;                                 // first ghost row of the level (= owned rows)
+  unsigned long long* ctl = nullptr;              // [0..31] incoming epoch flags, [32] epoch, [33] CTAs done, [34] error, [64..95] CTAs that have sent
+};
+
 struct Halo {
   std::vector<int> nbr, send_ptr, recv_ptr;
   DevBuf<int> send_idx;         // row ids
   DevBuf<int> send_pos;         // the same rows as sweep positions (solver vectors)
   DevBuf<double> sendbuf;
   DevBuf<int> isendbuf;
+  int ipc_slot = -1;            // level slot of the persistent peer-memory buffers (Comm::ipc), -1 = none
+  int ipc_state = 0;            // 0 = not prepared for these lists yet, 1 = ready, -1 = NCCL send / recv
+  HaloIpcArgs ipc;
   bool active() const { return !nbr.empty(); }
 };
 
@@ -169,6 +189,8 @@ struct Comm {
   int rank = 0, nranks = 1;
   bool suspended = false;       // inside the replicated coarse hierarchy every rank works alone
   bool active() const { return nccl != nullptr && nranks > 1 && !suspended; }
+  long n_ipc = 0, n_nccl = 0;           // halo exchanges issued through the peer-memory kernel / through NCCL send-recv
+  struct IpcArena* ipc = nullptr;       // peer-memory halo exchange: IPC-exported receive slots per level + the peers' mappings (comm.cu)
   ~Comm();
 };
 
@@ -314,6 +336,7 @@ void multi_axpy(Handle& h, const double* V, size_t ld, int nvec, const double* c
 // 3 doubles per block row; sweep_space: vec is a solver vector (indexed by sweep position), else by row id
 void halo_exchange(Handle& h, Halo& halo, double* vec, bool sweep_space = false);
 void halo_exchange_int(Handle& h, Halo& halo, int* vec);     // 1 int per block row
+void comm_check_ipc_error(Handle& h);                        // throws if a peer-memory exchange timed out
 void comm_allreduce(Handle& h, double* dev, int count, bool is_max);
 void comm_allreduce_int(Handle& h, int* dev, int count, bool is_max);
 void comm_allgather(Handle& h, const void* send, void* recv, size_t bytes_per_rank);

@@ -44,6 +44,11 @@ WORKER = textwrap.dedent('''
     it, amg = pkg.default_params()
     r0 = g.residual()
     hist = [g.newton_step(it, amg) for _ in range(3)]
+    n_ipc, n_nccl = g.halo_counts()
+    if os.environ.get("PNPB200_HALO_IPC", "1") != "0":
+        assert n_ipc > 100 and n_ipc > 20 * n_nccl, (n_ipc, n_nccl)      # the peer-memory kernel carried the exchanges
+    else:
+        assert n_ipc == 0 and n_nccl > 100
     uu = g.get_solution()[:3 * P["n_own"]]
     gd = (3 * np.asarray(P["gids"])[:P["n_own"], None] + np.arange(3)).ravel()
     g.close()
@@ -60,20 +65,23 @@ WORKER = textwrap.dedent('''
             assert st > 0 and st2 > 0
             assert abs(l2 - l22) <= 2e-3 * l22, (hist, ref)
         assert np.abs(uu - uu_ref).max() <= 1e-4
-        print("MULTI_OK", [h[0] for h in hist], [h[0] for h in ref])
+        print("MULTI_OK", [h[0] for h in hist], [h[0] for h in ref], "halo exchanges (peer kernel, nccl):", n_ipc, n_nccl)
     dist.barrier(); dist.destroy_process_group()
 ''') % ROOT
 
 
-@pytest.mark.parametrize("mode", ["slabs", "xbricks", "rcb"])
+@pytest.mark.parametrize("mode", ["slabs", "xbricks", "rcb", "slabs-nccl"])
 def test_two_gpu_newton_matches_single_gpu(gpu_lib, tmp_path, mode):
     """slabs: z-slabs (contiguous global ids); xbricks: cut along x (owned vertices strided in the global
-    numbering, neighbours through every Kuhn diagonal); rcb: the general-mesh partitioner on the same mesh"""
+    numbering, neighbours through every Kuhn diagonal); rcb: the general-mesh partitioner on the same mesh. The halo
+    exchanges go through the peer-memory kernel (comm.cu; the worker asserts it carried them), "slabs-nccl" keeps the
+    NCCL send / recv fallback under test (PNPB200_HALO_IPC=0)."""
     if gpu_lib.pnpb200_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29621", str(script)],
-                         capture_output=True, text=True, timeout=600, env=dict(os.environ, PNPB200_TEST_PARTITION=mode))
+                         capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, PNPB200_TEST_PARTITION=mode.split("-")[0], PNPB200_HALO_IPC="0" if mode.endswith("-nccl") else "1"))
     assert out.returncode == 0 and "MULTI_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
