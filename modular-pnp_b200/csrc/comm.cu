@@ -265,8 +265,19 @@ void ipc_prepare(Handle& h, Halo& c)
     g.peer_goff[k] = in[3 * k];
     g.send_beg[k + 1] = c.send_ptr[k + 1];
     g.recv_off[k] = c.recv_ptr[k] - ghost0; g.recv_cnt[k] = c.recv_ptr[k + 1] - c.recv_ptr[k];
+  }
+  // CTAs per neighbour: one per 256 rows (the pack is a dependent gather: index, then row — it needs many threads in
+  // flight, not many iterations per thread), at most 592 in total = 4 per SM, far below what is resident at once
+  int per_cta = 256;
+  for (;;) {
+    int total = 0;
+    for (int k = 0; k < nn; ++k) total += std::max(1, (std::max(c.send_ptr[k + 1] - c.send_ptr[k], g.recv_cnt[k]) + per_cta - 1) / per_cta);
+    if (total <= 592) break;
+    per_cta *= 2;
+  }
+  for (int k = 0; k < nn; ++k) {
     const int rows = std::max(c.send_ptr[k + 1] - c.send_ptr[k], g.recv_cnt[k]);
-    g.blk_beg[k + 1] = g.blk_beg[k] + std::min(8, std::max(1, (4 * rows + 4095) / 4096));
+    g.blk_beg[k + 1] = g.blk_beg[k] + std::max(1, (rows + per_cta - 1) / per_cta);
   }
   c.ipc_state = 1;
 }
