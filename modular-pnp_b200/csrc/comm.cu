@@ -233,10 +233,11 @@ void ipc_prepare(Handle& h, Halo& c)
 {
   Comm& cm = h.comm; cudaStream_t s = h.stream;
   const int nn = (int)c.nbr.size();
-  const int ghost0 = c.recv_ptr.front(), nghost = c.recv_ptr.back() - ghost0;
+  // a rank without neighbours on this level (nn == 0, empty lists) still takes part in the collective decisions below
+  const int ghost0 = c.recv_ptr.empty() ? 0 : c.recv_ptr.front(), nghost = c.recv_ptr.empty() ? 0 : c.recv_ptr.back() - ghost0;
   if (!cm.ipc) ipc_arena_init(h, c.ipc_slot == 0 ? nghost : 0);
   IpcArena& A = *cm.ipc;
-  bool ok = !A.failed && c.ipc_slot >= 0 && c.ipc_slot < IPC_NSLOTS && nn <= IPC_MAX_NBR && nghost <= A.cap;
+  bool ok = !A.failed && (nn == 0 || (c.ipc_slot >= 0 && c.ipc_slot < IPC_NSLOTS && nn <= IPC_MAX_NBR && nghost <= A.cap));
   std::vector<int> out(3 * (size_t)(nn ? nn : 1)), in(3 * (size_t)(nn ? nn : 1), 0);
   for (int k = 0; k < nn; ++k) { out[3 * k] = c.recv_ptr[k] - ghost0; out[3 * k + 1] = k; out[3 * k + 2] = ok ? 1 : 0; }
   DevBuf<int> ds, dr; ds.alloc(out.size(), s); dr.alloc(in.size(), s);
@@ -252,6 +253,7 @@ void ipc_prepare(Handle& h, Halo& c)
   for (int k = 0; k < nn; ++k) ok = ok && in[3 * k + 2] == 1 && in[3 * k + 1] >= 0 && in[3 * k + 1] < IPC_MAX_NBR;
   ok = all_agree(h, ok);
   if (!ok) { c.ipc_state = -1; return; }
+  if (nn == 0) { c.ipc_state = 2; return; }     // peer path agreed; nothing to exchange here, but the self-check is collective
   HaloIpcArgs& g = c.ipc;
   g = HaloIpcArgs();
   g.nnbr = nn; g.cap = A.cap; g.ghost0 = ghost0;
@@ -296,6 +298,7 @@ void halo_exchange_ipc(Handle& h, Halo& c, double* vec, bool sweep_space)
 void ipc_selfcheck(Handle& h, Halo& c, bool sweep_space)
 {
   cudaStream_t s = h.stream;
+  if (!c.active()) { if (!all_agree(h, true)) c.ipc_state = -1; return; }
   const int n = c.recv_ptr.back(), n_own = c.recv_ptr.front();
   const int xs = sweep_space ? VS : 3;
   DevBuf<double> t1, t2; t1.alloc((size_t)xs * n, s); t2.alloc((size_t)xs * n, s);
@@ -350,16 +353,19 @@ __global__ void pack1_kernel(int n, const int* __restrict__ idx, const int* __re
 // refresh the ghost entries of a block vector (3 doubles per row) from their owners
 void halo_exchange(Handle& h, Halo& c, double* vec, bool sweep_space)
 {
-  if (!h.comm.active() || !c.active()) return;
-  if (sweep_space && c.send_ptr.back() > 0 && !c.send_pos.p) throw Error(ERROR_UNKNOWN, "halo_exchange: level has no sweep-space send list");
+  if (!h.comm.active()) return;
+  if (c.active() && sweep_space && c.send_ptr.back() > 0 && !c.send_pos.p) throw Error(ERROR_UNKNOWN, "halo_exchange: level has no sweep-space send list");
+  // the choice of path is a collective decision (all_agree): a rank that has no neighbour on this level goes through it
+  // with the others and only then returns
   if (c.ipc_state == 0) {
     // first exchange with these lists (never inside a graph capture: the first visit of a level is direct)
     if (ipc_enabled()) ipc_prepare(h, c); else c.ipc_state = -1;
   }
-  if (c.ipc_state == 1 && h.comm.ipc && c.ipc_slot >= 0 && h.comm.ipc->checks[c.ipc_slot] < 2) {
+  if ((c.ipc_state == 1 || c.ipc_state == 2) && h.comm.ipc && c.ipc_slot >= 0 && c.ipc_slot < IPC_NSLOTS && h.comm.ipc->checks[c.ipc_slot] < 2) {
     ++h.comm.ipc->checks[c.ipc_slot];
     ipc_selfcheck(h, c, sweep_space);
   }
+  if (!c.active()) return;
   if (c.ipc_state == 1) { halo_exchange_ipc(h, c, vec, sweep_space); ++h.comm.n_ipc; }
   else { halo_exchange_nccl(h, c, vec, sweep_space); ++h.comm.n_nccl; }
 }

@@ -77,7 +77,7 @@ struct Halo {
   DevBuf<double> sendbuf;
   DevBuf<int> isendbuf;
   int ipc_slot = -1;            // level slot of the persistent peer-memory buffers (Comm::ipc), -1 = none
-  int ipc_state = 0;            // 0 = not prepared for these lists yet, 1 = ready, -1 = NCCL send / recv
+  int ipc_state = 0;            // 0 = not prepared for these lists yet, 1 = ready, 2 = ready but no neighbour here, -1 = NCCL send / recv
   HaloIpcArgs ipc;
   bool active() const { return !nbr.empty(); }
 };
