@@ -437,6 +437,7 @@ def main():
     step_e2e()
     ms_e2e, _, _, _ = timed(step_e2e, K)
     stats = g.stats()
+    halo = g.halo_counts() if world > 1 else None      # exchanges issued by this rank: (peer-memory kernel, NCCL send/recv)
     kits = its[-1]
 
     # roofline of the dominant kernel. profiles/README.md (ncu launch list): the multicolour
@@ -500,12 +501,13 @@ def main():
         e2e_v = units * K / (ms_e2e / 1e3)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
-               "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=part_desc + ("" if world == 1 else ": NCCL halo exchange at every distributed AMG level + fp64 allreduce, aggregates local to a rank, coarse levels below 40 000 global rows replicated on every rank"),
+               "dtype": "f64", "data": "synthetic", "config": dict(config, parallelism=part_desc + ("" if world == 1 else ": halo exchange at every distributed AMG level (peer-memory kernel over NVLink, NCCL send/recv as fallback: see halo_exchanges) + fp64 NCCL allreduce, aggregates local to a rank, coarse levels below 40 000 global rows replicated on every rank"),
                               global_dofs=global_dofs, global_steps_per_s=K / (ms / 1e3)),
                "krylov_its_per_step": its, "krylov_status_ok": bool(kits > 0), "amg_cycle_type": args.cycle,
                "l2_residual_after_step": None if last is None else last[1],
                "relative_residual_after_step": None if last is None else last[1] / l2_0,
                "multi_gpu_parity": parity,
+               "halo_exchanges": None if halo is None else {"peer_memory_kernel": halo[0], "nccl_send_recv": halo[1], "note": "rank 0, whole run"},
                "levels": [[stats.level_rows[l], stats.level_nnzb[l], stats.level_colors[l]] for l in range(stats.n_levels)],
                "stage_ms_last_step": stage_ms,
                "stage_roofline_frac": dict(stage_frac, note="SURVEY 8(d) algorithmic bytes of the stage / its time / peak; assemble = B_asmJ + B_eafe + one B_res (the rhs), residual = one B_res"),
