@@ -551,22 +551,40 @@ def main():
                                                  "(serial like the reference); value = steps/s AT THAT SIZE, not extrapolated to %d^3%s" % (
                                                      m, dof, cits, sec, n, "; reference element kernels (oracle/_ref)" if used_ref else "")}
                 g.close(); g = None
-                gs = pkg.PNP(box=(m, m, m, 2.0, 2.0, 2.0), device=dev)
-                prs = problems.exact_solution_problem(m, m, m, 2.0, 2.0, 2.0)
-                gs.set_coefficients(prs["eps"], prs["fixed"], prs["diff"], prs["val"], prs["reac"]); gs.set_dirichlet(prs["bc_dofs"])
-                itv, amgv = pkg.default_params(maxit=args.maxit, cycle_type=1)          # bsr.dat: V-cycle, like the CPU leg
-                same = {}
-                for nm, (i_, a_) in (("V", (itv, amgv)), (args.cycle, (it, amg))):
-                    for _ in range(3):
-                        gs.set_solution(prs["uu0"]); r_ = gs.newton_step(i_, a_)
-                    t0 = time.perf_counter()
-                    for _ in range(5):
-                        gs.set_solution(prs["uu0"]); r_ = gs.newton_step(i_, a_)     # host buffers in, like e2e
-                    same[nm] = {"gpu_steps_per_s": 5.0 / (time.perf_counter() - t0), "gpu_krylov_its": r_[0]}
-                gs.close()
+
+                def gpu_same_box(mm):
+                    """GPU on the mm^3 box through the C ABI from host buffers: bsr.dat's V-cycle (what the CPU leg runs) and the bench's cycle"""
+                    gs = pkg.PNP(box=(mm, mm, mm, 2.0, 2.0, 2.0), device=dev)
+                    prs = problems.exact_solution_problem(mm, mm, mm, 2.0, 2.0, 2.0)
+                    gs.set_coefficients(prs["eps"], prs["fixed"], prs["diff"], prs["val"], prs["reac"]); gs.set_dirichlet(prs["bc_dofs"])
+                    itv, amgv = pkg.default_params(maxit=args.maxit, cycle_type=1)          # bsr.dat: V-cycle, like the CPU leg
+                    same = {}
+                    for nm, (i_, a_) in (("V", (itv, amgv)), (args.cycle, (it, amg))):
+                        for _ in range(3):
+                            gs.set_solution(prs["uu0"]); r_ = gs.newton_step(i_, a_)
+                        t0 = time.perf_counter()
+                        for _ in range(5):
+                            gs.set_solution(prs["uu0"]); r_ = gs.newton_step(i_, a_)     # host buffers in, like e2e
+                        same[nm] = {"gpu_steps_per_s": 5.0 / (time.perf_counter() - t0), "gpu_krylov_its": r_[0]}
+                    gs.close()
+                    return same
+                same = gpu_same_box(m)
                 out["cpu_same_n"] = {"n": m, "dofs": dof, "cpu_steps_per_s": 1.0 / sec, "cpu_krylov_its": cits, "cpu_cycle": "V",
                                      "gpu": same, "ratio_same_config_V": same["V"]["gpu_steps_per_s"] * sec,
                                      "note": "GPU: host clock around 5 x (pnpb200_set_solution from host memory + pnpb200_newton_step), same box, same bsr.dat V-cycle as the CPU leg"}
+                # SURVEY 8(d): seconds per step and us per dof of the CPU path NEXT TO the GPU's at the same n, n in {32, 64}
+                table = [{"n": m, "dofs": dof, "cpu_s_per_step": sec, "cpu_us_per_dof": 1e6 * sec / dof, "cpu_krylov_its": cits,
+                          "gpu_s_per_step_V": 1.0 / same["V"]["gpu_steps_per_s"], "gpu_us_per_dof_V": 1e6 / same["V"]["gpu_steps_per_s"] / dof,
+                          "gpu_krylov_its_V": same["V"]["gpu_krylov_its"]}]
+                for m2 in (32,):
+                    if m2 >= m:
+                        continue
+                    ts2, dof2, cits2, _ = cpu_reference_leg(m2)
+                    same2 = gpu_same_box(m2)
+                    table.insert(0, {"n": m2, "dofs": dof2, "cpu_s_per_step": ts2[0], "cpu_us_per_dof": 1e6 * ts2[0] / dof2, "cpu_krylov_its": cits2,
+                                     "gpu_s_per_step_V": 1.0 / same2["V"]["gpu_steps_per_s"], "gpu_us_per_dof_V": 1e6 / same2["V"]["gpu_steps_per_s"] / dof2,
+                                     "gpu_krylov_its_V": same2["V"]["gpu_krylov_its"]})
+                out["cpu_same_n"]["table"] = table
             except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
                 out.setdefault("cpu_baseline", {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "unavailable: %r" % (e,)})
         emit(out)
