@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboracle.so")
+# PNP_ORACLE_LIB: another build of the same sources (the sanitizer build, `make -C oracle san`)
+LIB_PATH = os.environ.get("PNP_ORACLE_LIB") or os.path.join(_HERE, "liboracle.so")
 REF_PATH = os.path.join(_HERE, "_ref", "libpnpref.so")
 
 _f8 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
