@@ -1,0 +1,30 @@
+// TEST INFRASTRUCTURE ONLY (oracle/). Stand-in for <dolfin.h> so that the reference's plain-C++ host logic
+// (src/newton_status.cpp, the parameter half of src/domain.cpp) compiles where it lies without DOLFIN: the few types
+// those two files name, with no behaviour. domain_build's BoxMesh records its arguments, nothing more.
+#ifndef PNP_ORACLE_SHIM_DOLFIN_H
+#define PNP_ORACLE_SHIM_DOLFIN_H
+#include <cmath>
+#include <cstdio>
+#include <cstddef>
+#include <cstring>
+#include <string>
+namespace dolfin {
+struct Point {
+  double c[3];
+  Point(double x = 0.0, double y = 0.0, double z = 0.0) { c[0] = x; c[1] = y; c[2] = z; }
+};
+struct Mesh {
+  bool built = false;
+  double p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0};
+  int n[3] = {0, 0, 0};
+};
+struct BoxMesh : Mesh {
+  BoxMesh(const Point& a, const Point& b, int nx, int ny, int nz)
+  {
+    built = true;
+    for (int k = 0; k < 3; ++k) { p0[k] = a.c[k]; p1[k] = b.c[k]; }
+    n[0] = nx; n[1] = ny; n[2] = nz;
+  }
+};
+}
+#endif
