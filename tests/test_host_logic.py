@@ -218,6 +218,127 @@ def test_cases_cover_the_decisions(golden):
     assert golden["build"][0]["box"] == [-1.0, -0.2, -0.2, 1.0, 0.2, 0.2, 50.0, 10.0, 10.0]
 
 
+# --- the manufactured problem's data and the Dirichlet set (inputs of every parity test and of the bench) ----------------
+def _ref_lib():
+    if not os.path.exists(REF_LIB):
+        pytest.skip("oracle/_ref/libpnpref_host.so not built (needs /root/reference at build time)")
+    L = C.CDLL(REF_LIB)
+    f8 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    i4 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    u1 = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+    L.ref_exact_problem_point.argtypes = [C.c_double, f8]
+    L.ref_linear_function.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, f8, f8, C.c_int, f8, f8]
+    L.ref_dirichlet_inside.argtypes = [C.c_int, i4, f8, f8, C.c_double, C.c_int, f8, u1, u1]
+    return L
+
+
+def _ref_problem(L, xyz):
+    """the reference's own functions (benchmarks/pnp_exact_solution/main.cpp:24-78, :293-302 with src/dirichlet.cpp's
+    Linear_Function) evaluated at the vertices: what main.cpp interpolates into its coefficient Functions"""
+    X = xyz.reshape(-1, 3)
+    nv = len(X)
+    out = np.zeros((nv, 16))
+    for v in range(nv):
+        L.ref_exact_problem_point(float(X[v, 0]), out[v])
+    lo, hi = np.zeros(16), np.zeros(16)
+    L.ref_exact_problem_point(-1.0, lo); L.ref_exact_problem_point(+1.0, hi)
+    xmin, xmax = float(X[:, 0].min()), float(X[:, 0].max())
+    uu0 = np.zeros((nv, 3))
+    for k in range(3):           # PDE::set_DirichletBC: one scalar Linear_Function per component, coordinate 0
+        col = np.zeros(nv)
+        L.ref_linear_function(0, xmin, xmax, 1, lo[k:k + 1].copy(), hi[k:k + 1].copy(), nv, np.ascontiguousarray(X.ravel()), col)
+        uu0[:, k] = col
+    return dict(exact=out[:, 0:3].ravel(), diff=out[:, 9:12].ravel(), fixed=out[:, 12].copy(), reac=out[:, 13:16].ravel(),
+                uu0=uu0.ravel(), eps=np.ones(nv), val=np.tile([0.0, 1.0, -1.0], nv))
+
+
+@pytest.mark.parametrize("grid,lengths", [((50, 10, 10), (2.0, 0.4, 0.4)), ((8, 8, 8), (2.0, 2.0, 2.0)), ((7, 3, 5), (2.0, 1.0, 1.6))])
+def test_problem_data_equal_the_references_own_functions(oracle, grid, lengths):
+    """The coefficient, source, exact-solution and initial-guess arrays fed to the oracle, to the device (tests) and to
+    the bench equal what the reference's own functions give at the same vertices: bit for bit in the oracle's statement
+    (oracle/assemble.cpp, orc_exact_problem), to one unit in the last place in the numpy statements
+    (modular-pnp_b200/problems.py: bench, multi-GPU fields)."""
+    from importlib import import_module
+    from pnpb200_loader import load_package
+    load_package()
+    problems = import_module("modular_pnp_b200.problems")
+    L = _ref_lib()
+    P = oracle.Problem(*grid, *lengths)
+    ref = _ref_problem(L, P.xyz)
+    mine = dict(exact=P.exact, diff=P.diff, fixed=P.fixed, reac=P.reac, uu0=P.uu0, eps=P.eps, val=P.val)
+    py = problems.exact_solution_problem(*grid, *lengths)
+    pf = problems.exact_solution_fields(P.xyz[0::3])
+    def one_ulp(a, b):
+        return np.all(np.abs(a - b) <= np.spacing(np.abs(b)))
+    for k in ref:
+        assert np.array_equal(mine[k], ref[k]), "oracle: " + k          # same libm, same expression order: bit-equal
+        # numpy's vectorised exp differs from libm's in the last bit at a few points (measured: `reac` at one of the 51
+        # x-planes of the 50 x 10 x 10 box, 6e-17 relative; everything else bit-equal): bar = one unit in the last place
+        assert one_ulp(py[k], ref[k]), "problems.exact_solution_problem: " + k
+        if k != "uu0" or lengths[0] == 2.0:      # exact_solution_fields interpolates over the benchmark's x-range [-1, 1]
+            assert one_ulp(pf[k], ref[k]), "problems.exact_solution_fields: " + k
+    for k in ("exact", "diff", "fixed", "uu0", "eps", "val"):
+        assert np.array_equal(py[k], ref[k]), k
+
+
+def test_dirichlet_vertex_set_equals_the_references_subdomain(oracle):
+    """src/pde.cpp:433-461 + src/dirichlet.cpp:24-37: Dirichlet_Subdomain({0}, mesh_min, mesh_max, 0.1 * rmin).inside on the
+    boundary vertices = the vertex set the oracle (and through it every test) constrains."""
+    L = _ref_lib()
+    for grid, lengths in [((10, 4, 4), (2.0, 0.4, 0.4)), ((5, 6, 3), (2.0, 2.0, 1.0))]:
+        P = oracle.Problem(*grid, *lengths)
+        X = P.xyz.reshape(-1, 3)
+        mn, mx = X.min(axis=0), X.max(axis=0)
+        on_b = (np.isclose(X, mn) | np.isclose(X, mx)).any(axis=1).astype(np.uint8)
+        h = np.array(lengths) / np.array(grid)
+        # inradius of a Kuhn tetrahedron of an hx x hy x hz brick: 3 V / (sum of the face areas); V = hx hy hz / 6
+        rmin = min(_kuhn_inradii(h))
+        inside = np.zeros(P.nv, dtype=np.uint8)
+        L.ref_dirichlet_inside(1, np.array([0], dtype=np.int32), np.ascontiguousarray(mn), np.ascontiguousarray(mx), 0.1 * rmin,
+                               P.nv, np.ascontiguousarray(X.ravel()), on_b, inside)
+        assert np.array_equal(inside, P.bcflag[0::3]) and 0 < inside.sum() < P.nv
+
+
+def _kuhn_inradii(h):
+    import itertools
+    r = []
+    for perm in itertools.permutations(range(3)):
+        p = [np.zeros(3)]
+        for d in perm:
+            q = p[-1].copy(); q[d] += h[d]; p.append(q)
+        p = np.array(p)
+        vol = abs(np.linalg.det(p[1:] - p[0])) / 6.0
+        area = 0.0
+        for f in itertools.combinations(range(4), 3):
+            a, b, c = p[list(f)]
+            area += 0.5 * np.linalg.norm(np.cross(b - a, c - a))
+        r.append(3.0 * vol / area)
+    return r
+
+
+GOLDEN_POINTS = os.path.join(ROOT, "tests", "golden", "exact_problem_points.json")
+POINTS_X = [-1.0 + 2.0 * i / 50 for i in range(51)] + [-0.987654321, -0.3333333333333333, 1e-9, 0.123456789, 0.77, 0.9999]
+
+
+def test_oracle_problem_data_equal_the_committed_reference_values(oracle):
+    """the same comparison against COMMITTED outputs of the reference's functions (hex floats, exact), so that it also
+    runs where oracle/_ref is absent: main.cpp:24-78 at 57 abscissae, and the scalar Linear_Function on [-1, 1]"""
+    with open(GOLDEN_POINTS) as fh:
+        g = json.load(fh)
+    xs = np.array([float.fromhex(h) for h in g["x"]])
+    ref = np.array([[float.fromhex(h) for h in row] for row in g["values16"]])
+    uu0_ref = np.array([[float.fromhex(h) for h in row] for row in g["uu0"]])
+    nv = len(xs)
+    xyz = np.zeros((nv, 3)); xyz[:, 0] = xs
+    eps = np.zeros(nv); fixed = np.zeros(nv); diff = np.zeros(3 * nv); val = np.zeros(3 * nv); reac = np.zeros(3 * nv)
+    uu0 = np.zeros(3 * nv); exact = np.zeros(3 * nv)
+    oracle.lib().orc_exact_problem(nv, np.ascontiguousarray(xyz.ravel()), eps, fixed, diff, val, reac, uu0, exact.ctypes.data)
+    assert np.array_equal(exact.reshape(nv, 3), ref[:, 0:3]) and np.array_equal(diff.reshape(nv, 3), ref[:, 9:12])
+    assert np.array_equal(fixed, ref[:, 12]) and np.array_equal(reac.reshape(nv, 3), ref[:, 13:16])
+    assert np.array_equal(uu0.reshape(nv, 3), uu0_ref)
+    assert np.all(eps == 1.0) and np.array_equal(val.reshape(nv, 3), np.tile([0.0, 1.0, -1.0], (nv, 1)))
+
+
 if __name__ == "__main__":
     if "--write-golden" in sys.argv:
         with tempfile.TemporaryDirectory() as t:
@@ -225,3 +346,15 @@ if __name__ == "__main__":
         with open(GOLDEN, "w") as fh:
             json.dump(res, fh, indent=1)
         print("wrote", GOLDEN)
+        L = _ref_lib()
+        xyz = np.zeros((len(POINTS_X), 3)); xyz[:, 0] = POINTS_X
+        r = _ref_problem(L, xyz.ravel())
+        v16 = np.zeros((len(POINTS_X), 16))
+        for i, x in enumerate(POINTS_X):
+            L.ref_exact_problem_point(float(x), v16[i])
+        with open(GOLDEN_POINTS, "w") as fh:
+            json.dump({"source": "benchmarks/pnp_exact_solution/main.cpp:24-78 and src/dirichlet.cpp:73-90 compiled where they lie (oracle/_ref/libpnpref_host.so)",
+                       "layout16": "exact_solution(3), exact_derivative(3), exact_second(3), diffusivities(3), fixed(1), reactions(3)",
+                       "x": [float(x).hex() for x in POINTS_X], "values16": [[float(v).hex() for v in row] for row in v16],
+                       "uu0": [[float(v).hex() for v in row] for row in r["uu0"].reshape(-1, 3)]}, fh, indent=0)
+        print("wrote", GOLDEN_POINTS)
