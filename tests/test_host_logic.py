@@ -316,6 +316,57 @@ def _kuhn_inradii(h):
     return r
 
 
+REF_DIODE_LIB = os.path.join(ROOT, "oracle", "_ref", "libpnpref_diodephys.so")
+GOLDEN_DIODE = os.path.join(ROOT, "tests", "golden", "diode_problem_points.json")
+DIODE_X = [-1.0 + 2.0 * i / 40 for i in range(41)] + [-0.05, 0.05, -0.0499999, 0.0499999, -1e-12, 1e-12, 0.0123, -0.0377, 0.051, -0.051]
+DIODE_VOLTS = [0.0, -0.3, 0.1, 0.5]
+
+
+def _diode_ref_table(L):
+    f8 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    L.ref_diode_point.argtypes = [C.c_double, C.c_double, f8]
+    tab = np.zeros((len(DIODE_VOLTS), len(DIODE_X), 20))
+    for a, volt in enumerate(DIODE_VOLTS):
+        for i, x in enumerate(DIODE_X):
+            L.ref_diode_point(float(x), float(volt), tab[a, i])
+    return tab
+
+
+def _check_diode_fields(tab):
+    from importlib import import_module
+    from pnpb200_loader import load_package
+    load_package()
+    pr = import_module("modular_pnp_b200.problems")
+    xs = np.array(DIODE_X)
+    for a, volt in enumerate(DIODE_VOLTS):
+        ref = tab[a]
+        f = pr.diode_fields(xs, volt)
+        left, right = pr.diode_contacts(volt)
+        assert np.array_equal(f["diff"].reshape(-1, 3), ref[:, 0:3]) and np.array_equal(f["eps"], ref[:, 3])
+        assert np.array_equal(f["fixed"], ref[:, 4]) and np.array_equal(f["uu0"].reshape(-1, 3), ref[:, 6:9])
+        assert np.array_equal(left, ref[0, 9:12]) and np.array_equal(right, ref[0, 12:15])
+        assert np.array_equal(f["val"].reshape(-1, 3), ref[:, 15:18]) and np.all(f["reac"] == 0.0) and np.all(ref[:, 19] == 0.0)
+        assert pr.DIODE_POISSON_SCALE == ref[0, 5] and pr.DIODE_BETA == ref[0, 18]
+
+
+def test_diode_problem_data_equal_the_references_diode_h():
+    """benchmarks/pnp_diode/diode.h compiled where it lies (oracle/_ref/libpnpref_diodephys.so): diffusivities, relative
+    permittivity, fixed charge (doping profile with its junction ramp), contacts, the Initial_Guess expression, the
+    Poisson scale — at 51 abscissae (both sides of every branch point) and 4 bias voltages, BIT-EQUAL to
+    problems.diode_fields / diode_contacts, the inputs of the diode tests."""
+    if not os.path.exists(REF_DIODE_LIB):
+        pytest.skip("oracle/_ref/libpnpref_diodephys.so not built (needs /root/reference at build time)")
+    _check_diode_fields(_diode_ref_table(C.CDLL(REF_DIODE_LIB)))
+
+
+def test_diode_problem_data_equal_the_committed_reference_values():
+    with open(GOLDEN_DIODE) as fh:
+        g = json.load(fh)
+    assert [float.fromhex(h) for h in g["x"]] == [float(x) for x in DIODE_X] and g["volts"] == DIODE_VOLTS
+    tab = np.array([[[float.fromhex(h) for h in row] for row in per_volt] for per_volt in g["values20"]])
+    _check_diode_fields(tab)
+
+
 GOLDEN_POINTS = os.path.join(ROOT, "tests", "golden", "exact_problem_points.json")
 POINTS_X = [-1.0 + 2.0 * i / 50 for i in range(51)] + [-0.987654321, -0.3333333333333333, 1e-9, 0.123456789, 0.77, 0.9999]
 
@@ -358,3 +409,10 @@ if __name__ == "__main__":
                        "x": [float(x).hex() for x in POINTS_X], "values16": [[float(v).hex() for v in row] for row in v16],
                        "uu0": [[float(v).hex() for v in row] for row in r["uu0"].reshape(-1, 3)]}, fh, indent=0)
         print("wrote", GOLDEN_POINTS)
+        tab = _diode_ref_table(C.CDLL(REF_DIODE_LIB))
+        with open(GOLDEN_DIODE, "w") as fh:
+            json.dump({"source": "benchmarks/pnp_diode/diode.h compiled where it lies (oracle/_ref/libpnpref_diodephys.so, oracle/ref_wrappers_diodephys.inc)",
+                       "layout20": "diffusivities(3), relative_permittivity, fixed, 1/permittivity_factor, Initial_Guess(3), left_contact(3), right_contact(3), valencies(3), thermodynamic_beta, sum(reactions)",
+                       "x": [float(x).hex() for x in DIODE_X], "volts": DIODE_VOLTS,
+                       "values20": [[[float(v).hex() for v in row] for row in per_volt] for per_volt in tab]}, fh, indent=0)
+        print("wrote", GOLDEN_DIODE)
