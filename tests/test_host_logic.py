@@ -165,7 +165,7 @@ def run_cases(lib, pre, workdir):
 def _mirror_lib(tmp):
     so = os.path.join(tmp, "libhostmirror.so")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + HOST,
-                           os.path.join(ROOT, "tests", "host_logic_shim.cpp"), "-o", so])
+                           os.path.join(ROOT, "tests", "host_shims", "host_logic_shim.cpp"), "-o", so])
     return C.CDLL(so)
 
 
