@@ -66,3 +66,40 @@ def test_byte_model_counts_the_survey_terms():
     assert bench.byte_model(st, nv, nc, 5, 30, shortcuts=True) < bench.byte_model(st, nv, nc, 5, 30)
     # the K-cycle revisits the coarse levels
     assert bench.byte_model(st, nv, nc, 5, 30, kcycle_levels=3) > bench.byte_model(st, nv, nc, 5, 30)
+
+
+def test_committed_bench_lines_carry_every_contract_key():
+    """the evidence under profiles/ (written by bench.py on the B200 box) has the keys the measurement contract names:
+    the base line, e2e with its copy sizes, the launch count, clocks, roofline (with a non-null traffic figure at the
+    bench size) and the CPU baseline; the N > 1 lines add the parity gate and the halo-exchange path counts"""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def last_line(name):
+        with open(os.path.join(root, "profiles", name)) as fh:
+            return json.loads(fh.read().strip().splitlines()[-1])
+    d = last_line("r02_bench_n256.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "newton_steps_per_s" and d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and d["config"]["n"] == 256 and d["config"]["dofs"] == 3 * 257 ** 3
+    assert abs(d["value"] - d["steps"] / (d["ms_per_step"] * d["steps"] / 1e3)) < 1e-9 * d["value"] and d["warmup"] >= 3
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 8 * d["config"]["dofs"] == e["d2h_bytes_per_step"] and 0 < e["value"] < d["value"]
+    assert d["gpu_launches"] > 1000 * d["steps"]
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / r["ms_per_launch"] / 1e6) < 1e-6 * r["achieved"]
+    assert r["traffic"] is not None and 0.8 < r["traffic"] / r["block_format"]["kernel_bytes_per_launch"] < 1.5
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] == 1 and c["value"] > 0 and "not extrapolated" in c["sample"]
+    t = d["cpu_same_n"]["table"]
+    assert [row["n"] for row in t] == [32, 64] and all(row["cpu_s_per_step"] > 100 * row["gpu_s_per_step_V"] for row in t)
+    for name, n_gpus in (("r02_bench_4gpu_n128.json", 4), ("r02_bench_2gpu_strong_n256.json", 2)):
+        m = last_line(name)
+        assert m["n_gpus"] == n_gpus and m["multi_gpu_parity"]["ok"] is True
+        assert m["halo_exchanges"]["peer_memory_kernel"] > 0 and m["halo_exchanges"]["nccl_send_recv"] == 0
+        assert all(k > 0 for k in m["krylov_its_per_step"])
